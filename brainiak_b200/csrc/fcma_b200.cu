@@ -1,0 +1,1403 @@
+// libfcma_b200.so — Blackwell-native (sm_100a) FCMA correlation engine behind a C ABI.
+//
+// Path (reference brainiak/brainiak @ 123f6e1):
+//   a14  preprocessing.py:80-84      per-epoch z-score                -> k_pack_operand (normalise prologue)
+//   a4   voxelselector.py:307-323    E skinny SGEMMs                  -> k_corr_umma   (TMA + tcgen05.mma)
+//   a6   fcma_extension.cc:52-84     Fisher-z + within-subject zscore -> k_norm_syrk   (fused with a7)
+//   a7   voxelselector.py:400-408    per-voxel SSYRK                  -> k_norm_syrk   (mma.sync tf32)
+//   a9-a11 classifier.py:279-348     same, one [E,E] kernel           -> k_norm_syrk + k_reduce_rows
+// plus standalone, reference-exact stages (k_within_subject_norm, k_corr_simt, k_syrk_simt).
+//
+// No CPU fallback lives here: without an sm_100 device every compute entry point returns FCMA_ENODEV.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <atomic>
+#include <mutex>
+
+#include "../../include/fcma_b200.h"
+#include "ptx_sm100.cuh"
+
+using namespace fcma;
+
+// ============================================================================================
+// host-side helpers
+// ============================================================================================
+static thread_local char g_err[512] = "";
+static std::atomic<long> g_launches{0};
+
+static int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CUDA_TRY(expr)                                                                           \
+    do {                                                                                         \
+        cudaError_t _e = (expr);                                                                 \
+        if (_e != cudaSuccess)                                                                   \
+            return fail(FCMA_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                        __LINE__);                                                               \
+    } while (0)
+#define LAUNCH_CHECK(name)                                                                       \
+    do {                                                                                         \
+        g_launches.fetch_add(1, std::memory_order_relaxed);                                      \
+        cudaError_t _e = cudaGetLastError();                                                     \
+        if (_e != cudaSuccess)                                                                   \
+            return fail(FCMA_ECUDA, "launch of %s failed: %s", name, cudaGetErrorString(_e));    \
+    } while (0)
+
+static inline long cdiv(long a, long b) { return (a + b - 1) / b; }
+static inline long round_up(long a, long b) { return cdiv(a, b) * b; }
+
+static int g_sm_count = 0;
+static int check_device()
+{
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(FCMA_ENODEV, "no CUDA device: %s", cudaGetErrorString(e));
+    }
+    static thread_local int checked_dev = -1;
+    if (checked_dev == dev) return FCMA_OK;
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, dev);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(FCMA_ENODEV, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    }
+    if (prop.major != 10)
+        return fail(FCMA_ENODEV, "device %d is sm_%d%d; libfcma_b200 needs sm_100 (B200)", dev, prop.major,
+                    prop.minor);
+    g_sm_count = prop.multiProcessorCount;
+    checked_dev = dev;
+    return FCMA_OK;
+}
+
+extern "C" int fcma_version(void) { return 100; }
+extern "C" const char *fcma_last_error(void) { return g_err; }
+extern "C" long fcma_launch_count(void) { return g_launches.load(); }
+extern "C" int fcma_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    int ok = 0;
+    for (int d = 0; d < n; d++) {
+        int major = 0;
+        if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d) == cudaSuccess && major == 10)
+            ok++;
+    }
+    return ok;
+}
+
+// ============================================================================================
+// precision descriptors
+// ============================================================================================
+struct PrecInfo {
+    int kind;      // 0 bf16 (kind::f16), 1 tf32
+    int planes;    // stored planes (hi[, lo])
+    int segs;      // product segments
+    int seg_r[3];  // plane of the row operand per segment
+    int seg_c[3];  // plane of the column operand per segment
+    int esize;     // bytes per element
+    int bk;        // K elements per 128-byte swizzle row (TMA box width)
+    int umma_k;    // K per tcgen05.mma
+};
+static bool prec_info(int precision, PrecInfo *p)
+{
+    switch (precision) {
+    case FCMA_PREC_BF16: *p = {0, 1, 1, {0, 0, 0}, {0, 0, 0}, 2, 64, 16}; return true;
+    case FCMA_PREC_TF32: *p = {1, 1, 1, {0, 0, 0}, {0, 0, 0}, 4, 32, 8}; return true;
+    // small cross terms first, hi*hi last
+    case FCMA_PREC_BF16X3: *p = {0, 2, 3, {1, 0, 0}, {0, 1, 0}, 2, 64, 16}; return true;
+    case FCMA_PREC_TF32X3: *p = {1, 2, 3, {1, 0, 0}, {0, 1, 0}, 4, 32, 8}; return true;
+    default: return false;
+    }
+}
+extern "C" int fcma_operand_kp(int precision, int T)
+{
+    PrecInfo p;
+    if (!prec_info(precision, &p) || T <= 0) return 0;
+    return (int)round_up(T, p.umma_k);  // bf16: multiple of 16 (32 B); tf32: multiple of 8 (32 B)
+}
+extern "C" int fcma_operand_planes(int precision)
+{
+    PrecInfo p;
+    return prec_info(precision, &p) ? p.planes : 0;
+}
+extern "C" size_t fcma_operand_bytes(int precision, int E, int T, long V)
+{
+    PrecInfo p;
+    if (!prec_info(precision, &p)) return 0;
+    return (size_t)p.planes * E * V * fcma_operand_kp(precision, T) * p.esize;
+}
+
+// ============================================================================================
+// a14 + operand packing:  [E][T][ld] fp32 (voxels contiguous)  ->  [planes][E][V][Kp] K-major
+// ============================================================================================
+__device__ __forceinline__ float tf32_rn(float x)
+{
+    return __uint_as_float(f32_to_tf32(x));
+}
+
+// one block = 32 voxels of one epoch; 256 threads = 32 (voxel) x 8
+template <int KIND, int PLANES>
+__global__ void __launch_bounds__(256) k_pack_operand(const float *__restrict__ src, int E, int T, long V, long ld,
+                                                      const int *__restrict__ T_e, int normalize, void *dst, int Kp)
+{
+    __shared__ double s_red[8][33];
+    __shared__ float s_mean[32], s_scale[32];
+    __shared__ float s_tile[32][65];
+    const int e = blockIdx.y;
+    const long v0 = (long)blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int Te = T_e ? T_e[e] : T;
+    const float *ep = src + (size_t)e * T * ld;
+    const long v = v0 + tx;
+    const bool vok = v < V;
+
+    float mean = 0.f, scale = 1.f;
+    if (normalize) {
+        // two-pass mean / population std over the Te rows (numpy semantics of zscore(ddof=0))
+        double s = 0.0;
+        for (int t = ty; t < Te; t += 8) s += vok ? (double)ep[(size_t)t * ld + v] : 0.0;
+        s_red[ty][tx] = s;
+        __syncthreads();
+        if (ty == 0) {
+            double tot = 0.0;
+            for (int k = 0; k < 8; k++) tot += s_red[k][tx];
+            s_mean[tx] = (float)(tot / Te);
+        }
+        __syncthreads();
+        mean = s_mean[tx];
+        double q = 0.0;
+        for (int t = ty; t < Te; t += 8) {
+            float d = vok ? ep[(size_t)t * ld + v] - mean : 0.f;
+            q += (double)d * d;
+        }
+        __syncthreads();
+        s_red[ty][tx] = q;
+        __syncthreads();
+        if (ty == 0) {
+            double tot = 0.0;
+            for (int k = 0; k < 8; k++) tot += s_red[k][tx];
+            float sd = (float)sqrt(tot / Te);
+            // (x-mean)/sd: sd == 0 -> 0/0 = nan -> nan_to_num -> 0; then / sqrt(Te)
+            s_scale[tx] = sd > 0.f ? 1.0f / (sd * sqrtf((float)Te)) : 0.f;
+        }
+        __syncthreads();
+        scale = s_scale[tx];
+    }
+
+    const size_t plane_stride = (size_t)E * V * Kp;
+    for (int k0 = 0; k0 < Kp; k0 += 64) {
+        // load a [64 t][32 v] slab coalesced along v, transpose through smem
+        for (int tt = ty; tt < 64; tt += 8) {
+            int t = k0 + tt;
+            float x = 0.f;
+            if (t < Te && vok) {
+                x = ep[(size_t)t * ld + v];
+                if (normalize) {
+                    x = (x - mean) * scale;
+                    if (!(x == x)) x = 0.f;  // nan_to_num (nan inputs)
+                }
+            }
+            s_tile[tx][tt] = x;
+        }
+        __syncthreads();
+        // 8 warps x 4 voxels; a warp writes 64 consecutive k of one voxel row
+        for (int vv = ty * 4; vv < ty * 4 + 4; vv++) {
+            long vo = v0 + vv;
+            if (vo >= V) continue;
+            for (int kk = tx; kk < 64; kk += 32) {
+                int k = k0 + kk;
+                if (k >= Kp) continue;
+                float x = s_tile[vv][kk];
+                size_t off = ((size_t)e * V + vo) * Kp + k;
+                if constexpr (KIND == 0) {
+                    __nv_bfloat16 *d = reinterpret_cast<__nv_bfloat16 *>(dst);
+                    __nv_bfloat16 hi = __float2bfloat16_rn(x);
+                    d[off] = hi;
+                    if constexpr (PLANES > 1) d[plane_stride + off] = __float2bfloat16_rn(x - __bfloat162float(hi));
+                } else {
+                    float *d = reinterpret_cast<float *>(dst);
+                    float hi = tf32_rn(x);
+                    d[off] = hi;
+                    if constexpr (PLANES > 1) d[plane_stride + off] = tf32_rn(x - hi);
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// a14 in place on [E][T][ld]
+__global__ void __launch_bounds__(256) k_epoch_normalize(float *data, int T, long V, long ld, const int *__restrict__ T_e)
+{
+    __shared__ double s_red[8][33];
+    __shared__ float s_mean[32], s_scale[32];
+    const int e = blockIdx.y;
+    const long v = (long)blockIdx.x * 32 + (threadIdx.x & 31);
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int Te = T_e ? T_e[e] : T;
+    float *ep = data + (size_t)e * T * ld;
+    const bool vok = v < V;
+    double s = 0.0;
+    for (int t = ty; t < Te; t += 8) s += vok ? (double)ep[(size_t)t * ld + v] : 0.0;
+    s_red[ty][tx] = s;
+    __syncthreads();
+    if (ty == 0) {
+        double tot = 0.0;
+        for (int k = 0; k < 8; k++) tot += s_red[k][tx];
+        s_mean[tx] = (float)(tot / Te);
+    }
+    __syncthreads();
+    float mean = s_mean[tx];
+    double q = 0.0;
+    for (int t = ty; t < Te; t += 8) {
+        float d = vok ? ep[(size_t)t * ld + v] - mean : 0.f;
+        q += (double)d * d;
+    }
+    __syncthreads();
+    s_red[ty][tx] = q;
+    __syncthreads();
+    if (ty == 0) {
+        double tot = 0.0;
+        for (int k = 0; k < 8; k++) tot += s_red[k][tx];
+        float sd = (float)sqrt(tot / Te);
+        s_scale[tx] = sd > 0.f ? 1.0f / (sd * sqrtf((float)Te)) : 0.f;
+    }
+    __syncthreads();
+    float scale = s_scale[tx];
+    if (vok)
+        for (int t = ty; t < Te; t += 8) {
+            float x = (ep[(size_t)t * ld + v] - mean) * scale;
+            if (!(x == x)) x = 0.f;
+            ep[(size_t)t * ld + v] = x;
+        }
+}
+
+// ============================================================================================
+// a4 on tensor cores: persistent, warp-specialised TMA -> tcgen05.mma -> TMEM -> coalesced stores
+// ============================================================================================
+// D tile = 128 columns j (UMMA M side, TMEM lanes) x BN rows i (UMMA N side, TMEM columns): with the
+// all-voxel side on the lanes, a warp's 32 lanes hold 32 consecutive j of one output row, so the
+// epilogue stores straight from registers as full 128-byte lines of out[i][e][j..j+31].
+struct GemmParams {
+    int E, Kp, bk, umma_k, kbs;      // kbs = k-blocks per segment
+    int segs, seg_r[3], seg_c[3];
+    long V2, nb, row_start;
+    int BN;                          // rows (i) per tile: 32..256, multiple of 32
+    int tiles_j, tiles_i;
+    long total_tiles;
+    float *out;
+    long stride_i, stride_e;
+    int fisher_epochs;
+    uint32_t stage_bytes_c, stage_bytes_r;
+    int stages;
+};
+
+constexpr int GEMM_THREADS = 384;  // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4..11 epilogue
+constexpr int GEMM_EPI_WARPS = 8;
+constexpr int GEMM_MAX_STAGES = 8;
+
+__device__ __forceinline__ float fisher_fast(float r)
+{
+    // 0.5*log((1+r)/(1-r)) with the clamps of fcma_extension.cc:68-72, as 0.5*ln2*(lg2(num)-lg2(den))
+    float num = 1.0f + r, den = 1.0f - r;
+    num = num <= 0.f ? 1e-4f : num;
+    den = den <= 0.f ? 1e-4f : den;
+    return 0.34657359027997264f * (__log2f(num) - __log2f(den));
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+    k_corr_umma(const __grid_constant__ CUtensorMap tm_cols, const __grid_constant__ CUtensorMap tm_rows,
+                const GemmParams p)
+{
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // dynamic smem base is only guaranteed 16-byte aligned: align to 1024 for SWIZZLE_128B
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const uint32_t stage_bytes = p.stage_bytes_c + p.stage_bytes_r;
+    uint8_t *tiles = smem;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)p.stages * stage_bytes);
+    uint64_t *full_bar = bars;                           // [stages]
+    uint64_t *empty_bar = bars + GEMM_MAX_STAGES;        // [stages]
+    uint64_t *tfull_bar = bars + 2 * GEMM_MAX_STAGES;    // [2]
+    uint64_t *tempty_bar = tfull_bar + 2;                // [2]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tm_cols);
+        tma_prefetch_desc(&tm_rows);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < p.stages; s++) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int s = 0; s < 2; s++) {
+            mbar_init(&tfull_bar[s], 1);
+            mbar_init(&tempty_bar[s], GEMM_EPI_WARPS);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(tmem_slot, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int nkb = p.segs * p.kbs;
+    const long tiles_per_e = (long)p.tiles_j * p.tiles_i;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                const int e = (int)(tile / tiles_per_e);
+                const long rem = tile - (long)e * tiles_per_e;
+                const int ti = (int)(rem / p.tiles_j);
+                const int tj = (int)(rem - (long)ti * p.tiles_j);
+                for (int kb = 0; kb < nkb; kb++) {
+                    const int seg = kb / p.kbs;
+                    const int k0 = (kb - seg * p.kbs) * p.bk;
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    mbar_expect_tx(&full_bar[stage], stage_bytes);
+                    uint8_t *sc = tiles + (size_t)stage * stage_bytes;
+                    uint8_t *sr = sc + p.stage_bytes_c;
+                    tma_load_3d(&tm_cols, &full_bar[stage], sc, k0, tj * 128, p.seg_c[seg] * p.E + e);
+                    tma_load_3d(&tm_rows, &full_bar[stage], sr, k0, (int)(p.row_start + (long)ti * p.BN),
+                                p.seg_r[seg] * p.E + e);
+                    if (++stage == p.stages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer (one thread)
+        const uint32_t idesc = make_idesc(KIND, 128, (uint32_t)p.BN);
+        int stage = 0;
+        uint32_t phase = 0;
+        long iter = 0;
+        for (long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, iter++) {
+            const int as = (int)(iter & 1);
+            const uint32_t aphase = (uint32_t)((iter >> 1) & 1);
+            mbar_wait(&tempty_bar[as], aphase ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.BN);
+            for (int kb = 0; kb < nkb; kb++) {
+                const int k0 = (kb % p.kbs) * p.bk;
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t sc = smem_u32(tiles + (size_t)stage * stage_bytes);
+                    const uint64_t dc = make_smem_desc_sw128(sc);
+                    const uint64_t dr = make_smem_desc_sw128(sc + p.stage_bytes_c);
+                    int rem_k = p.Kp - k0;
+                    const int nk = (rem_k < p.bk ? rem_k : p.bk) / p.umma_k;
+                    for (int k = 0; k < nk; k++) {
+                        // advance 32 bytes (one UMMA_K slice) inside the 128-byte swizzle row
+                        tc_mma<KIND>(d_tmem, dc + (uint64_t)(k * 2), dr + (uint64_t)(k * 2), idesc,
+                                     (uint32_t)((kb | k) != 0));
+                    }
+                    tc_commit(&empty_bar[stage]);            // smem slot free once these MMAs retire
+                    if (kb == nkb - 1) tc_commit(&tfull_bar[as]);  // accumulator ready for the epilogue
+                }
+                __syncwarp();
+                if (++stage == p.stages) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ------------------------------------------------------------------ epilogue (8 warps)
+        const int ew = warp - 4;
+        const int q = warp & 3;        // TMEM lane quarter this warp may access
+        const int half = ew >> 2;      // two warps per quarter split the 32-column chunks
+        long iter = 0;
+        for (long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, iter++) {
+            const int e = (int)(tile / tiles_per_e);
+            const long rem = tile - (long)e * tiles_per_e;
+            const int ti = (int)(rem / p.tiles_j);
+            const int tj = (int)(rem - (long)ti * p.tiles_j);
+            const int as = (int)(iter & 1);
+            const uint32_t aphase = (uint32_t)((iter >> 1) & 1);
+            mbar_wait(&tfull_bar[as], aphase);
+            tc_fence_after();
+            const long j = (long)tj * 128 + q * 32 + lane;
+            const bool jok = j < p.V2;
+            const bool do_fisher = e < p.fisher_epochs;
+            const long i0 = (long)ti * p.BN;
+            float *obase = p.out + (size_t)e * p.stride_e + j;
+            const int nchunks = p.BN >> 5;
+            for (int c = half; c < nchunks; c += 2) {
+                const long ic = i0 + c * 32;
+                if (ic >= p.nb) break;  // warp-uniform
+                uint32_t v[32];
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.BN + c * 32);
+                tmem_ld32(taddr, v);
+                tmem_ld_wait();
+                if (jok) {
+#pragma unroll
+                    for (int r = 0; r < 32; r++) {
+                        const long i = ic + r;
+                        if (i < p.nb) {
+                            float x = __uint_as_float(v[r]);
+                            if (do_fisher) x = fisher_fast(x);
+                            obase[(size_t)i * p.stride_i] = x;
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[as]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// ---------------------------------------------------------------- tensor-map creation (driver entry point)
+typedef CUresult (*PFN_tmEncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                      const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                      CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                      CUtensorMapFloatOOBfill);
+static PFN_tmEncodeTiled get_encode_fn()
+{
+    static PFN_tmEncodeTiled fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_tmEncodeTiled>(p);
+        else
+            cudaGetLastError();
+    });
+    return fn;
+}
+
+// operand tensor [planes*E][V][Kp] (Kp fastest), box = {bk, rows, 1}, 128-byte swizzle, zero OOB fill
+static int make_operand_map(CUtensorMap *m, const void *base, const PrecInfo &pi, int E, long V, int Kp,
+                            int box_rows)
+{
+    PFN_tmEncodeTiled enc = get_encode_fn();
+    if (!enc) return fail(FCMA_ECUDA, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t gdim[3] = {(cuuint64_t)Kp, (cuuint64_t)V, (cuuint64_t)pi.planes * E};
+    cuuint64_t gstr[2] = {(cuuint64_t)Kp * pi.esize, (cuuint64_t)V * Kp * pi.esize};
+    cuuint32_t box[3] = {(cuuint32_t)pi.bk, (cuuint32_t)box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUtensorMapDataType dt = pi.kind == 0 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    CUresult r = enc(m, dt, 3, const_cast<void *>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(FCMA_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return FCMA_OK;
+}
+
+static int launch_corr_umma(const void *rows_op, const void *cols_op, int precision, int E, int T, long V, long V2,
+                            long start, long nb, float *out, long stride_i, long stride_e, int fisher_epochs,
+                            cudaStream_t st)
+{
+    PrecInfo pi;
+    if (!prec_info(precision, &pi)) return fail(FCMA_EINVAL, "unknown precision %d", precision);
+    if (E <= 0 || T <= 0 || V <= 0 || V2 <= 0 || nb <= 0 || start < 0 || start + nb > V)
+        return fail(FCMA_EINVAL, "bad shape E=%d T=%d V=%ld V2=%ld start=%ld nb=%ld", E, T, V, V2, start, nb);
+    if (((uintptr_t)rows_op & 15) || ((uintptr_t)cols_op & 15))
+        return fail(FCMA_EINVAL, "packed operands must be 16-byte aligned");
+    if (V >= (1L << 31) || V2 >= (1L << 31)) return fail(FCMA_EINVAL, "voxel count exceeds TMA coordinate range");
+    const int Kp = fcma_operand_kp(precision, T);
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.E = E;
+    p.Kp = Kp;
+    p.bk = pi.bk;
+    p.umma_k = pi.umma_k;
+    p.kbs = (int)cdiv(Kp, pi.bk);
+    p.segs = pi.segs;
+    for (int s = 0; s < 3; s++) {
+        p.seg_r[s] = pi.seg_r[s];
+        p.seg_c[s] = pi.seg_c[s];
+    }
+    p.V2 = V2;
+    p.nb = nb;
+    p.row_start = start;
+    p.BN = nb >= 256 ? 256 : (int)round_up(nb, 32);
+    p.tiles_j = (int)cdiv(V2, 128);
+    p.tiles_i = (int)cdiv(nb, p.BN);
+    p.total_tiles = (long)p.tiles_j * p.tiles_i * E;
+    p.out = out;
+    p.stride_i = stride_i;
+    p.stride_e = stride_e;
+    p.fisher_epochs = fisher_epochs;
+    p.stage_bytes_c = 128 * 128;
+    p.stage_bytes_r = (uint32_t)p.BN * 128;
+    const size_t budget = 200 * 1024;
+    int stages = (int)(budget / (p.stage_bytes_c + p.stage_bytes_r));
+    if (stages > GEMM_MAX_STAGES) stages = GEMM_MAX_STAGES;
+    if (stages < 2) return fail(FCMA_EINVAL, "internal: not enough shared memory for 2 stages");
+    p.stages = stages;
+    const size_t smem = (size_t)stages * (p.stage_bytes_c + p.stage_bytes_r) + 1024 /*align slack*/ + 256 /*barriers*/;
+
+    CUtensorMap tm_cols, tm_rows;
+    int rc = make_operand_map(&tm_cols, cols_op, pi, E, V2, Kp, 128);
+    if (rc) return rc;
+    rc = make_operand_map(&tm_rows, rows_op, pi, E, V, Kp, p.BN);
+    if (rc) return rc;
+
+    long grid = p.total_tiles < g_sm_count ? p.total_tiles : g_sm_count;
+    if (pi.kind == 0) {
+        CUDA_TRY(cudaFuncSetAttribute(k_corr_umma<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_corr_umma<0><<<(unsigned)grid, GEMM_THREADS, smem, st>>>(tm_cols, tm_rows, p);
+    } else {
+        CUDA_TRY(cudaFuncSetAttribute(k_corr_umma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_corr_umma<1><<<(unsigned)grid, GEMM_THREADS, smem, st>>>(tm_cols, tm_rows, p);
+    }
+    LAUNCH_CHECK("k_corr_umma");
+    return FCMA_OK;
+}
+
+// ============================================================================================
+// a4 reference-order path: fp32 FFMA tiled GEMM on the raw epochs [E][T][ld]
+// ============================================================================================
+// out[i][e][j] = sum_t R[e][t][start+i] * C[e][t][j];  64x64 tile, 256 threads, 4x4 micro-tile
+__global__ void __launch_bounds__(256) k_corr_simt(const float *__restrict__ R, long ldr, const float *__restrict__ C,
+                                                   long ldc, int T, long V2, long start, long nb, float *out,
+                                                   long stride_i, long stride_e)
+{
+    __shared__ float sr[16][64 + 4];
+    __shared__ float sc[16][64 + 4];
+    const int e = blockIdx.z;
+    const long i0 = (long)blockIdx.y * 64, j0 = (long)blockIdx.x * 64;
+    const float *Re = R + (size_t)e * T * ldr;
+    const float *Ce = C + (size_t)e * T * ldc;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    float acc[4][4] = {};
+    for (int t0 = 0; t0 < T; t0 += 16) {
+        for (int idx = threadIdx.x; idx < 16 * 64; idx += 256) {
+            int tt = idx >> 6, x = idx & 63;
+            int t = t0 + tt;
+            long i = i0 + x, j = j0 + x;
+            sr[tt][x] = (t < T && i < nb) ? Re[(size_t)t * ldr + start + i] : 0.f;
+            sc[tt][x] = (t < T && j < V2) ? Ce[(size_t)t * ldc + j] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int tt = 0; tt < 16; tt++) {
+            float a[4], b[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                a[k] = sr[tt][ty * 4 + k];
+                b[k] = sc[tt][tx * 4 + k];
+            }
+#pragma unroll
+            for (int x = 0; x < 4; x++)
+#pragma unroll
+                for (int y = 0; y < 4; y++) acc[x][y] = fmaf(a[x], b[y], acc[x][y]);
+        }
+        __syncthreads();
+    }
+    for (int x = 0; x < 4; x++) {
+        long i = i0 + ty * 4 + x;
+        if (i >= nb) continue;
+        for (int y = 0; y < 4; y++) {
+            long j = j0 + tx * 4 + y;
+            if (j < V2) out[(size_t)i * stride_i + (size_t)e * stride_e + j] = acc[x][y];
+        }
+    }
+}
+
+// plain NT GEMM  C[m][n] = sum_k A[m][k] B[n][k]  (a12 / a15), K contiguous in both operands
+__global__ void __launch_bounds__(256) k_gemm_nt(const float *__restrict__ A, const float *__restrict__ B, float *C,
+                                                 long M, long N, long K, long lda, long ldb, long ldc)
+{
+    __shared__ float sa[64][16 + 1];
+    __shared__ float sb[64][16 + 1];
+    const long m0 = (long)blockIdx.y * 64, n0 = (long)blockIdx.x * 64;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    float acc[4][4] = {};
+    for (long k0 = 0; k0 < K; k0 += 16) {
+        for (int idx = threadIdx.x; idx < 64 * 16; idx += 256) {
+            int r = idx >> 4, kk = idx & 15;
+            long k = k0 + kk;
+            sa[r][kk] = (k < K && m0 + r < M) ? A[(size_t)(m0 + r) * lda + k] : 0.f;
+            sb[r][kk] = (k < K && n0 + r < N) ? B[(size_t)(n0 + r) * ldb + k] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < 16; kk++) {
+            float a[4], b[4];
+#pragma unroll
+            for (int x = 0; x < 4; x++) {
+                a[x] = sa[ty * 4 + x][kk];
+                b[x] = sb[tx * 4 + x][kk];
+            }
+#pragma unroll
+            for (int x = 0; x < 4; x++)
+#pragma unroll
+                for (int y = 0; y < 4; y++) acc[x][y] = fmaf(a[x], b[y], acc[x][y]);
+        }
+        __syncthreads();
+    }
+    for (int x = 0; x < 4; x++) {
+        long m = m0 + ty * 4 + x;
+        if (m >= M) continue;
+        for (int y = 0; y < 4; y++) {
+            long n = n0 + tx * 4 + y;
+            if (n < N) C[(size_t)m * ldc + n] = acc[x][y];
+        }
+    }
+}
+
+// util.py:32-60 on rows: zscore(axis=1, ddof=0), optional nan->0, / sqrt(D)
+__global__ void __launch_bounds__(256) k_row_normalize(float *X, long R, long D, long ld, int nan_to_zero)
+{
+    __shared__ double s_red[256];
+    __shared__ float s_val[2];
+    for (long r = blockIdx.x; r < R; r += gridDim.x) {
+        float *row = X + (size_t)r * ld;
+        double s = 0.0;
+        for (long d = threadIdx.x; d < D; d += 256) s += row[d];
+        s_red[threadIdx.x] = s;
+        __syncthreads();
+        for (int o = 128; o > 0; o >>= 1) {
+            if ((int)threadIdx.x < o) s_red[threadIdx.x] += s_red[threadIdx.x + o];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) s_val[0] = (float)(s_red[0] / D);
+        __syncthreads();
+        float mean = s_val[0];
+        double q = 0.0;
+        for (long d = threadIdx.x; d < D; d += 256) {
+            float dd = row[d] - mean;
+            q += (double)dd * dd;
+        }
+        __syncthreads();
+        s_red[threadIdx.x] = q;
+        __syncthreads();
+        for (int o = 128; o > 0; o >>= 1) {
+            if ((int)threadIdx.x < o) s_red[threadIdx.x] += s_red[threadIdx.x + o];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) s_val[1] = (float)sqrt(s_red[0] / D);
+        __syncthreads();
+        float sd = s_val[1];
+        float rs = sqrtf((float)D);
+        for (long d = threadIdx.x; d < D; d += 256) {
+            float z = (row[d] - mean) / sd;  // sd==0 -> nan/inf as numpy
+            if (nan_to_zero) {
+                if (!(z == z)) z = 0.f;
+                else if (isinf(z)) z = z > 0 ? 3.4028234663852886e38f : -3.4028234663852886e38f;
+            }
+            row[d] = z / rs;
+        }
+        __syncthreads();
+    }
+}
+
+// ============================================================================================
+// a6 standalone: exact restatement of fcma_extension.cc:52-84 (sequential fp32, no FMA contraction)
+// ============================================================================================
+__global__ void __launch_bounds__(256) k_within_subject_norm(float *data, long n0, int E, long n2, int eps)
+{
+    const long nSubjs = E / eps;
+    const long total = n0 * nSubjs * n2;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const long j = idx % n2;
+        const long v = idx / n2;
+        const long s = v % nSubjs;
+        const long i = v / nSubjs;
+        float *mat = data + (size_t)i * E * n2 + j;
+        float mean = 0.0f, sq = 0.0f;
+        for (long b = s * eps; b < (s + 1) * eps; b++) {
+            float r = mat[(size_t)b * n2];
+            float num = __fadd_rn(1.0f, r);
+            float den = __fsub_rn(1.0f, r);
+            num = (num <= 0.0f) ? 1e-4f : num;
+            den = (den <= 0.0f) ? 1e-4f : den;
+            float z = __fmul_rn(0.5f, logf(__fdiv_rn(num, den)));
+            mat[(size_t)b * n2] = z;
+            mean = __fadd_rn(mean, z);
+            sq = __fadd_rn(sq, __fmul_rn(z, z));
+        }
+        mean = __fdiv_rn(mean, (float)eps);
+        float var = __fsub_rn(__fdiv_rn(sq, (float)eps), __fmul_rn(mean, mean));
+        float inv = (var <= 0.0f) ? 0.0f : __fdiv_rn(1.0f, __fsqrt_rn(var));
+        for (long b = s * eps; b < (s + 1) * eps; b++)
+            mat[(size_t)b * n2] = __fmul_rn(__fsub_rn(mat[(size_t)b * n2], mean), inv);
+    }
+}
+
+// ============================================================================================
+// a7 standalone, fp32 FFMA: K_i = Z_i Z_i^T (any E), one block per voxel row
+// ============================================================================================
+__global__ void __launch_bounds__(256) k_syrk_simt(const float *__restrict__ z, long nb, int E, long n2, long stride_i,
+                                                   long ld, float beta, float *K, int sum_over_rows)
+{
+    extern __shared__ float s_z[];  // [64 j][E+1]
+    const int EP = E + 1;
+    for (long i = blockIdx.x; i < nb; i += gridDim.x) {
+        const float *zi = z + (size_t)i * stride_i;
+        const int npairs = E * E;
+        // each thread owns pairs tid, tid+256, ... (at most 16 for E <= 64; loop for larger E)
+        for (int pbase = 0; pbase < npairs; pbase += 256 * 16) {
+            float acc[16];
+#pragma unroll
+            for (int k = 0; k < 16; k++) acc[k] = 0.f;
+            for (long j0 = 0; j0 < n2; j0 += 64) {
+                __syncthreads();
+                for (int idx = threadIdx.x; idx < E * 64; idx += 256) {
+                    int e = idx >> 6, jj = idx & 63;
+                    s_z[jj * EP + e] = (j0 + jj < n2) ? zi[(size_t)e * ld + j0 + jj] : 0.f;
+                }
+                __syncthreads();
+#pragma unroll
+                for (int k = 0; k < 16; k++) {
+                    int pidx = pbase + k * 256 + threadIdx.x;
+                    if (pidx < npairs) {
+                        int a = pidx / E, b = pidx - a * E;
+                        float s = acc[k];
+                        for (int jj = 0; jj < 64; jj++) s = fmaf(s_z[jj * EP + a], s_z[jj * EP + b], s);
+                        acc[k] = s;
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                int pidx = pbase + k * 256 + threadIdx.x;
+                if (pidx < npairs) {
+                    if (sum_over_rows) {
+                        atomicAdd(&K[pidx], acc[k]);
+                    } else {
+                        float *dst = &K[(size_t)i * npairs + pidx];
+                        *dst = (beta == 0.f ? 0.f : beta * *dst) + acc[k];
+                    }
+                }
+            }
+        }
+    }
+}
+
+// ============================================================================================
+// a6+a7 fused on warp MMAs: Fisher-z, within-subject z-score and K_i = Z_i Z_i^T in one pass
+// over the correlation block; the normalised values never leave registers.
+// ============================================================================================
+// One block (8 warps) per voxel row i; warps stride over 32-column chunks of the [E][n2] slab.
+// Lane (g = lane/4, t = lane%4) loads, as float4s, epochs R*g .. R*g+R-1 at columns
+// j0 + 16h + 4t .. +3 (h = 0,1).  These registers are at once
+//   - the A fragments (rows g, g+8 of m-tile mu <-> epochs R*g+2mu, R*g+2mu+1) and
+//   - the B fragments (col g of n-tile nu <-> epoch R*g+nu)
+// of mma.sync.m16n8k8 (tf32), with k-slot t <-> column 4t+u and k-slot t+4 <-> column 16+4t+u for
+// k-step u = 0..3: a sum over columns is invariant under that permutation, and the epoch
+// permutation is undone when the accumulators are scattered.  EP = 8R padded epochs.
+// The epochs of one subject (EPS consecutive epochs, EPS a power of two) live in EPS/R adjacent
+// g-lanes (or inside a lane when EPS <= R), so the z-score statistics need at most 3 shuffles.
+// EPS == 0: input is already normalised (plain SYRK).
+template <int R, int EPS, bool FISHER, bool VEC>
+__global__ void __launch_bounds__(256, (R == 4 ? 2 : 1))
+    k_norm_syrk(const float *__restrict__ C, long nb, int E, long n2, long stride_i, long ld, long self_col0,
+                float beta, float *K, int sum_over_rows)
+{
+    constexpr int EP = 8 * R;
+    constexpr int MT = EP / 16, NT = EP / 8;
+    __shared__ float s_K[EP * EP];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int S_eps = EPS > 0 ? (E / EPS) * EPS : 0;  // epochs that get normalised
+    const long nchunks = (n2 + 31) / 32;
+
+    for (long i = blockIdx.x; i < nb; i += gridDim.x) {
+        const float *Ci = C + (size_t)i * stride_i;
+        const long self_col = self_col0 >= 0 ? self_col0 + i : -1;
+        float acc[MT][NT][4];
+#pragma unroll
+        for (int a = 0; a < MT; a++)
+#pragma unroll
+            for (int b = 0; b < NT; b++)
+#pragma unroll
+                for (int c = 0; c < 4; c++) acc[a][b][c] = 0.f;
+
+        for (long ch = warp; ch < nchunks; ch += 8) {
+            const long j0 = ch * 32;
+            float vals[R][2][4];
+            // ---- load (fragment layout), zero outside [0,E) x [0,n2)
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                const int e = R * g + r;
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const long col = j0 + 16 * h + 4 * t;
+                    const float *src = Ci + (size_t)e * ld + col;
+                    if (e < E && VEC && col + 4 <= n2) {
+                        float4 q = __ldg(reinterpret_cast<const float4 *>(src));
+                        vals[r][h][0] = q.x, vals[r][h][1] = q.y, vals[r][h][2] = q.z, vals[r][h][3] = q.w;
+                    } else {
+#pragma unroll
+                        for (int u = 0; u < 4; u++) vals[r][h][u] = (e < E && col + u < n2) ? __ldg(src + u) : 0.f;
+                    }
+                }
+            }
+            if constexpr (EPS > 0) {
+                // ---- Fisher-z on the epochs that belong to a complete subject
+                if constexpr (FISHER) {
+#pragma unroll
+                    for (int r = 0; r < R; r++)
+                        if (R * g + r < S_eps) {
+#pragma unroll
+                            for (int h = 0; h < 2; h++)
+#pragma unroll
+                                for (int u = 0; u < 4; u++) vals[r][h][u] = fisher_fast(vals[r][h][u]);
+                        }
+                }
+                // ---- per (subject, column) mean / variance
+                if constexpr (EPS <= R) {
+                    constexpr int G = EPS > 0 ? R / EPS : 1;
+#pragma unroll
+                    for (int q = 0; q < G; q++) {
+                        const bool valid = R * g + q * EPS < S_eps;
+#pragma unroll
+                        for (int h = 0; h < 2; h++)
+#pragma unroll
+                            for (int u = 0; u < 4; u++) {
+                                float m = 0.f, s2 = 0.f;
+#pragma unroll
+                                for (int b = 0; b < EPS; b++) {
+                                    float x = vals[q * EPS + b][h][u];
+                                    m += x;
+                                    s2 = fmaf(x, x, s2);
+                                }
+                                m *= (1.0f / EPS);
+                                float var = s2 * (1.0f / EPS) - m * m;
+                                float inv = var <= 0.f ? 0.f : rsqrtf(var);
+                                if (valid) {
+#pragma unroll
+                                    for (int b = 0; b < EPS; b++)
+                                        vals[q * EPS + b][h][u] = (vals[q * EPS + b][h][u] - m) * inv;
+                                }
+                            }
+                    }
+                } else {
+                    constexpr int L = EPS / R;  // adjacent g-lanes per subject
+                    const bool valid = R * g < S_eps;
+#pragma unroll
+                    for (int h = 0; h < 2; h++)
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            float m = 0.f, s2 = 0.f;
+#pragma unroll
+                            for (int r = 0; r < R; r++) {
+                                float x = vals[r][h][u];
+                                m += x;
+                                s2 = fmaf(x, x, s2);
+                            }
+#pragma unroll
+                            for (int o = 1; o < L; o <<= 1) {
+                                m += __shfl_xor_sync(0xffffffffu, m, 4 * o);
+                                s2 += __shfl_xor_sync(0xffffffffu, s2, 4 * o);
+                            }
+                            m *= (1.0f / EPS);
+                            float var = s2 * (1.0f / EPS) - m * m;
+                            float inv = var <= 0.f ? 0.f : rsqrtf(var);
+                            if (valid) {
+#pragma unroll
+                                for (int r = 0; r < R; r++) vals[r][h][u] = (vals[r][h][u] - m) * inv;
+                            }
+                        }
+                }
+            }
+            // ---- self-correlation column mask (optional), tf32 rounding
+            uint32_t tv[R][2][4];
+#pragma unroll
+            for (int r = 0; r < R; r++)
+#pragma unroll
+                for (int h = 0; h < 2; h++)
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        float x = vals[r][h][u];
+                        if (self_col >= 0 && j0 + 16 * h + 4 * t + u == self_col) x = 0.f;
+                        tv[r][h][u] = f32_to_tf32(x);
+                    }
+            // ---- K += Z Z^T on tensor cores
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+#pragma unroll
+                for (int mu = 0; mu < MT; mu++)
+#pragma unroll
+                    for (int nu = 0; nu < NT; nu++)
+                        mma_tf32_16x8x8(acc[mu][nu], tv[2 * mu][0][u], tv[2 * mu + 1][0][u], tv[2 * mu][1][u],
+                                        tv[2 * mu + 1][1][u], tv[nu][0][u], tv[nu][1][u]);
+        }
+
+        // ---- deterministic cross-warp reduction into s_K (epoch order restored)
+        __syncthreads();
+        for (int w = 0; w < 8; w++) {
+            if (warp == w) {
+#pragma unroll
+                for (int mu = 0; mu < MT; mu++)
+#pragma unroll
+                    for (int nu = 0; nu < NT; nu++) {
+                        const int row0 = R * g + 2 * mu, row1 = row0 + 1;
+                        const int col0 = R * (2 * t) + nu, col1 = R * (2 * t + 1) + nu;
+                        if (w == 0) {
+                            s_K[row0 * EP + col0] = acc[mu][nu][0];
+                            s_K[row0 * EP + col1] = acc[mu][nu][1];
+                            s_K[row1 * EP + col0] = acc[mu][nu][2];
+                            s_K[row1 * EP + col1] = acc[mu][nu][3];
+                        } else {
+                            s_K[row0 * EP + col0] += acc[mu][nu][0];
+                            s_K[row0 * EP + col1] += acc[mu][nu][1];
+                            s_K[row1 * EP + col0] += acc[mu][nu][2];
+                            s_K[row1 * EP + col1] += acc[mu][nu][3];
+                        }
+                    }
+            }
+            __syncthreads();
+        }
+        // ---- write: symmetric by construction from the lower triangle (cython_blas.pyx:200-207)
+        for (int idx = threadIdx.x; idx < E * E; idx += 256) {
+            const int a = idx / E, b = idx - a * E;
+            const float v = a >= b ? s_K[a * EP + b] : s_K[b * EP + a];
+            if (sum_over_rows) {
+                atomicAdd(&K[idx], v);
+            } else {
+                float *dst = &K[(size_t)i * E * E + idx];
+                *dst = (beta == 0.f ? 0.f : beta * *dst) + v;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void k_scale(float *x, long n, float s)
+{
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+        x[i] = s == 0.f ? 0.f : x[i] * s;
+}
+
+template <int R, bool FISHER, bool VEC>
+static bool dispatch_eps(int eps, dim3 grid, cudaStream_t st, const float *C, long nb, int E, long n2, long stride_i,
+                         long ld, long self_col0, float beta, float *K, int sum)
+{
+#define FCMA_CASE(EPSV)                                                                                          \
+    case EPSV:                                                                                                   \
+        k_norm_syrk<R, EPSV, FISHER, VEC><<<grid, 256, 0, st>>>(C, nb, E, n2, stride_i, ld, self_col0, beta, K, sum); \
+        return true;
+    switch (eps) {
+        FCMA_CASE(0)
+        FCMA_CASE(1)
+        FCMA_CASE(2)
+        FCMA_CASE(4)
+        FCMA_CASE(8)
+        FCMA_CASE(16)
+        FCMA_CASE(32)
+    case 64:
+        if constexpr (R == 8) {
+            k_norm_syrk<R, 64, FISHER, VEC><<<grid, 256, 0, st>>>(C, nb, E, n2, stride_i, ld, self_col0, beta, K, sum);
+            return true;
+        }
+        return false;
+    default: return false;
+    }
+#undef FCMA_CASE
+}
+
+// eps_mode: 0 = plain SYRK of normalised data; > 0 = fused normalisation with that eps
+static bool fused_supported(int E, int eps_mode)
+{
+    if (E > 64) return false;
+    if (eps_mode == 0) return true;
+    if (eps_mode & (eps_mode - 1)) return false;  // power of two only
+    return eps_mode <= (E <= 32 ? 32 : 64);
+}
+
+static int launch_norm_syrk(const float *C, long nb, int E, long n2, long stride_i, long ld, int eps_mode,
+                            int fisher_done, long self_col0, float beta, float *K, int sum_over_rows, cudaStream_t st)
+{
+    if (!fused_supported(E, eps_mode)) return fail(FCMA_EINVAL, "internal: fused norm+syrk unsupported E=%d eps=%d", E, eps_mode);
+    if (sum_over_rows) {
+        // K = beta*K, then atomically accumulate the per-row kernels
+        k_scale<<<1, 256, 0, st>>>(K, (long)E * E, beta);
+        LAUNCH_CHECK("k_scale");
+    }
+    const bool vec = ((ld & 3) == 0) && ((stride_i & 3) == 0) && (((uintptr_t)C & 15) == 0);
+    const bool fisher = eps_mode > 0 && !fisher_done;
+    // rows cost the same: a static stride over 16 blocks per SM balances well
+    long g = nb < 16L * g_sm_count ? nb : 16L * g_sm_count;
+    dim3 grid((unsigned)g);
+    bool ok;
+    if (E <= 32) {
+        if (fisher)
+            ok = vec ? dispatch_eps<4, true, true>(eps_mode, grid, st, C, nb, E, n2, stride_i, ld, self_col0, beta, K, sum_over_rows)
+                     : dispatch_eps<4, true, false>(eps_mode, grid, st, C, nb, E, n2, stride_i, ld, self_col0, beta, K, sum_over_rows);
+        else
+            ok = vec ? dispatch_eps<4, false, true>(eps_mode, grid, st, C, nb, E, n2, stride_i, ld, self_col0, beta, K, sum_over_rows)
+                     : dispatch_eps<4, false, false>(eps_mode, grid, st, C, nb, E, n2, stride_i, ld, self_col0, beta, K, sum_over_rows);
+    } else {
+        if (fisher)
+            ok = vec ? dispatch_eps<8, true, true>(eps_mode, grid, st, C, nb, E, n2, stride_i, ld, self_col0, beta, K, sum_over_rows)
+                     : dispatch_eps<8, true, false>(eps_mode, grid, st, C, nb, E, n2, stride_i, ld, self_col0, beta, K, sum_over_rows);
+        else
+            ok = vec ? dispatch_eps<8, false, true>(eps_mode, grid, st, C, nb, E, n2, stride_i, ld, self_col0, beta, K, sum_over_rows)
+                     : dispatch_eps<8, false, false>(eps_mode, grid, st, C, nb, E, n2, stride_i, ld, self_col0, beta, K, sum_over_rows);
+    }
+    if (!ok) return fail(FCMA_EINVAL, "internal: no k_norm_syrk instantiation for E=%d eps=%d", E, eps_mode);
+    LAUNCH_CHECK("k_norm_syrk");
+    return FCMA_OK;
+}
+
+// ============================================================================================
+// C ABI
+// ============================================================================================
+extern "C" int fcma_pack_operand(const float *epochs_dev, int E, int T, long V, long ld, const int *T_e, int normalize,
+                                 int precision, void *packed_dev, size_t packed_bytes, void *stream)
+{
+    int rc = check_device();
+    if (rc) return rc;
+    PrecInfo pi;
+    if (!prec_info(precision, &pi)) return fail(FCMA_EINVAL, "unknown precision %d", precision);
+    if (!epochs_dev || !packed_dev || E <= 0 || T <= 0 || V <= 0 || ld < V)
+        return fail(FCMA_EINVAL, "fcma_pack_operand: bad arguments E=%d T=%d V=%ld ld=%ld", E, T, V, ld);
+    size_t need = fcma_operand_bytes(precision, E, T, V);
+    if (packed_bytes < need) return fail(FCMA_ENOMEM, "packed operand buffer too small: %zu < %zu", packed_bytes, need);
+    cudaStream_t st = (cudaStream_t)stream;
+    int *d_Te = nullptr;
+    if (T_e) {
+        for (int e = 0; e < E; e++)
+            if (T_e[e] <= 0 || T_e[e] > T) return fail(FCMA_EINVAL, "epoch %d has length %d outside (0, %d]", e, T_e[e], T);
+        CUDA_TRY(cudaMallocAsync(&d_Te, sizeof(int) * E, st));
+        CUDA_TRY(cudaMemcpyAsync(d_Te, T_e, sizeof(int) * E, cudaMemcpyHostToDevice, st));
+    }
+    const int Kp = fcma_operand_kp(precision, T);
+    dim3 grid((unsigned)cdiv(V, 32), (unsigned)E);
+    if (pi.kind == 0 && pi.planes == 1) k_pack_operand<0, 1><<<grid, 256, 0, st>>>(epochs_dev, E, T, V, ld, d_Te, normalize, packed_dev, Kp);
+    if (pi.kind == 0 && pi.planes == 2) k_pack_operand<0, 2><<<grid, 256, 0, st>>>(epochs_dev, E, T, V, ld, d_Te, normalize, packed_dev, Kp);
+    if (pi.kind == 1 && pi.planes == 1) k_pack_operand<1, 1><<<grid, 256, 0, st>>>(epochs_dev, E, T, V, ld, d_Te, normalize, packed_dev, Kp);
+    if (pi.kind == 1 && pi.planes == 2) k_pack_operand<1, 2><<<grid, 256, 0, st>>>(epochs_dev, E, T, V, ld, d_Te, normalize, packed_dev, Kp);
+    LAUNCH_CHECK("k_pack_operand");
+    if (d_Te) CUDA_TRY(cudaFreeAsync(d_Te, st));
+    return FCMA_OK;
+}
+
+extern "C" int fcma_epoch_normalize(float *epochs_dev, int E, int T, long V, long ld, const int *T_e, void *stream)
+{
+    int rc = check_device();
+    if (rc) return rc;
+    if (!epochs_dev || E <= 0 || T <= 0 || V <= 0 || ld < V) return fail(FCMA_EINVAL, "fcma_epoch_normalize: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    int *d_Te = nullptr;
+    if (T_e) {
+        CUDA_TRY(cudaMallocAsync(&d_Te, sizeof(int) * E, st));
+        CUDA_TRY(cudaMemcpyAsync(d_Te, T_e, sizeof(int) * E, cudaMemcpyHostToDevice, st));
+    }
+    dim3 grid((unsigned)cdiv(V, 32), (unsigned)E);
+    k_epoch_normalize<<<grid, 256, 0, st>>>(epochs_dev, T, V, ld, d_Te);
+    LAUNCH_CHECK("k_epoch_normalize");
+    if (d_Te) CUDA_TRY(cudaFreeAsync(d_Te, st));
+    return FCMA_OK;
+}
+
+extern "C" int fcma_corr_block(const void *rows_op, const void *cols_op, int precision, int E, int T, long V, long V2,
+                               long start, long nb, float *out_dev, long stride_i, long stride_e, int fisher_epochs,
+                               void *stream)
+{
+    int rc = check_device();
+    if (rc) return rc;
+    if (!rows_op || !cols_op || !out_dev) return fail(FCMA_EINVAL, "fcma_corr_block: null pointer");
+    return launch_corr_umma(rows_op, cols_op, precision, E, T, V, V2, start, nb, out_dev, stride_i, stride_e,
+                            fisher_epochs, (cudaStream_t)stream);
+}
+
+extern "C" int fcma_corr_block_f32(const float *rows_epochs, long ldr, const float *cols_epochs, long ldc, int E, int T,
+                                   long V, long V2, long start, long nb, float *out_dev, long stride_i, long stride_e,
+                                   void *stream)
+{
+    int rc = check_device();
+    if (rc) return rc;
+    if (!rows_epochs || !cols_epochs || !out_dev || E <= 0 || T <= 0 || nb <= 0 || V2 <= 0 || start < 0 || start + nb > V)
+        return fail(FCMA_EINVAL, "fcma_corr_block_f32: bad arguments");
+    if (E > 65535 || cdiv(nb, 64) > 65535) return fail(FCMA_EINVAL, "fcma_corr_block_f32: block too large");
+    dim3 grid((unsigned)cdiv(V2, 64), (unsigned)cdiv(nb, 64), (unsigned)E);
+    k_corr_simt<<<grid, 256, 0, (cudaStream_t)stream>>>(rows_epochs, ldr, cols_epochs, ldc, T, V2, start, nb, out_dev,
+                                                        stride_i, stride_e);
+    LAUNCH_CHECK("k_corr_simt");
+    return FCMA_OK;
+}
+
+extern "C" int fcma_within_subject_norm(float *corr_dev, long n0, int E, long n2, int eps, void *stream)
+{
+    int rc = check_device();
+    if (rc) return rc;
+    if (!corr_dev || n0 <= 0 || E <= 0 || n2 <= 0) return fail(FCMA_EINVAL, "fcma_within_subject_norm: bad shape");
+    if (eps <= 0) return fail(FCMA_EINVAL, "fcma_within_subject_norm: epochs_per_subj must be positive");
+    if (E / eps == 0) return FCMA_OK;  // nSubjs == 0: nothing is touched (fcma_extension.cc:52-55)
+    long total = n0 * (E / eps) * n2;
+    long blocks = cdiv(total, 256);
+    if (blocks > 148L * 64) blocks = 148L * 64;
+    k_within_subject_norm<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(corr_dev, n0, E, n2, eps);
+    LAUNCH_CHECK("k_within_subject_norm");
+    return FCMA_OK;
+}
+
+static int launch_syrk_simt(const float *z, long nb, int E, long n2, long stride_i, long ld, float beta, float *K,
+                            int sum_over_rows, cudaStream_t st)
+{
+    if (sum_over_rows) {
+        k_scale<<<1, 256, 0, st>>>(K, (long)E * E, beta);
+        LAUNCH_CHECK("k_scale");
+    }
+    size_t smem = (size_t)64 * (E + 1) * sizeof(float);
+    if (smem > 200 * 1024) return fail(FCMA_EINVAL, "E=%d too large for the SIMT kernel-matrix path", E);
+    if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(k_syrk_simt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    long g = nb < 148L * 8 ? nb : 148L * 8;
+    k_syrk_simt<<<(unsigned)g, 256, smem, st>>>(z, nb, E, n2, stride_i, ld, beta, K, sum_over_rows);
+    LAUNCH_CHECK("k_syrk_simt");
+    return FCMA_OK;
+}
+
+extern "C" int fcma_kernel_matrices(const float *z_dev, long nb, int E, long n2, long stride_i, long ld, float beta,
+                                    float *K_dev, int sum_over_rows, void *stream)
+{
+    int rc = check_device();
+    if (rc) return rc;
+    if (!z_dev || !K_dev || nb <= 0 || E <= 0 || n2 <= 0 || ld < n2) return fail(FCMA_EINVAL, "fcma_kernel_matrices: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (fused_supported(E, 0)) return launch_norm_syrk(z_dev, nb, E, n2, stride_i, ld, 0, 1, -1, beta, K_dev, sum_over_rows, st);
+    return launch_syrk_simt(z_dev, nb, E, n2, stride_i, ld, beta, K_dev, sum_over_rows, st);
+}
+
+extern "C" int fcma_norm_kernel_matrices(const float *corr_dev, long nb, int E, long n2, long stride_i, long ld, int eps,
+                                         int fisher_done, long self_col0, float beta, float *K_dev, int sum_over_rows,
+                                         void *stream)
+{
+    int rc = check_device();
+    if (rc) return rc;
+    if (!corr_dev || !K_dev || nb <= 0 || E <= 0 || n2 <= 0 || ld < n2 || eps <= 0)
+        return fail(FCMA_EINVAL, "fcma_norm_kernel_matrices: bad arguments");
+    if (!fused_supported(E, eps))
+        return fail(FCMA_EINVAL, "fused normalise+kernel needs E <= 64 and a power-of-two epochs_per_subj (E=%d eps=%d): "
+                                 "use fcma_within_subject_norm + fcma_kernel_matrices", E, eps);
+    return launch_norm_syrk(corr_dev, nb, E, n2, stride_i, ld, eps, fisher_done, self_col0, beta, K_dev, sum_over_rows,
+                            (cudaStream_t)stream);
+}
+
+extern "C" size_t fcma_work_bytes_per_row(int E, long V2)
+{
+    return (size_t)E * round_up(V2, 32) * sizeof(float);
+}
+
+// shared body of the two fused pipelines
+static int run_pipeline(const void *rows_op, const void *cols_op, int precision, int E, int T, long V, long V2, long start,
+                        long nb, int eps, int flags, float *work, size_t work_bytes, float *K, int sum_over_rows,
+                        cudaStream_t st)
+{
+    if (!rows_op || !cols_op || !work || !K) return fail(FCMA_EINVAL, "pipeline: null pointer");
+    if (nb <= 0 || start < 0 || start + nb > V) return fail(FCMA_EINVAL, "pipeline: rows [%ld, %ld) outside [0, %ld)", start, start + nb, V);
+    if (eps < 0) return fail(FCMA_EINVAL, "pipeline: negative epochs_per_subj");
+    if (((uintptr_t)work & 15)) return fail(FCMA_EINVAL, "pipeline: work buffer must be 16-byte aligned");
+    const long ld = round_up(V2, 32);
+    const size_t row_bytes = (size_t)E * ld * sizeof(float);
+    long rows_per_pass = (long)(work_bytes / row_bytes);
+    if (rows_per_pass < 1) return fail(FCMA_ENOMEM, "work buffer too small: %zu bytes < %zu per row", work_bytes, row_bytes);
+    if (rows_per_pass > 256) rows_per_pass = (rows_per_pass / 256) * 256;  // whole GEMM tiles
+    // Classifier semantics: eps <= 1 -> no normalisation at all (classifier.py:204)
+    const bool normalise = sum_over_rows ? eps > 1 : eps >= 1;
+    const bool fused = normalise ? fused_supported(E, eps) : fused_supported(E, 0);
+    const int S_eps = normalise ? (E / eps) * eps : 0;
+    const bool fisher_in_gemm = normalise && fused && (flags & FCMA_FLAG_FISHER_IN_GEMM);
+    const bool mask_self = (flags & FCMA_FLAG_MASK_SELF) != 0;
+    if (mask_self && !(normalise && fused))
+        return fail(FCMA_EINVAL, "FCMA_FLAG_MASK_SELF needs the fused normalise+kernel path (E <= 64, power-of-two eps)");
+    for (long done = 0; done < nb; done += rows_per_pass) {
+        const long n = nb - done < rows_per_pass ? nb - done : rows_per_pass;
+        int rc = launch_corr_umma(rows_op, cols_op, precision, E, T, V, V2, start + done, n, work, (long)E * ld, ld,
+                                  fisher_in_gemm ? S_eps : 0, st);
+        if (rc) return rc;
+        float *Kdst = sum_over_rows ? K : K + (size_t)done * E * E;
+        const float beta = sum_over_rows ? 1.0f : 0.0f;
+        if (normalise && fused) {
+            rc = launch_norm_syrk(work, n, E, V2, (long)E * ld, ld, eps, fisher_in_gemm ? 1 : 0,
+                                  mask_self ? start + done : -1, beta, Kdst, sum_over_rows, st);
+        } else {
+            if (normalise) {
+                // generic-eps path: normalise the padded block [n][E][ld] in place (the pad columns hold
+                // don't-care values that the kernel-matrix stage never reads: it is bounded by n2 = V2)
+                long total = n * (E / eps) * ld;
+                if (total > 0) {
+                    long blocks = cdiv(total, 256);
+                    if (blocks > 148L * 64) blocks = 148L * 64;
+                    k_within_subject_norm<<<(unsigned)blocks, 256, 0, st>>>(work, n, E, ld, eps);
+                    LAUNCH_CHECK("k_within_subject_norm");
+                }
+            }
+            if (fused_supported(E, 0))
+                rc = launch_norm_syrk(work, n, E, V2, (long)E * ld, ld, 0, 1, -1, beta, Kdst, sum_over_rows, st);
+            else
+                rc = launch_syrk_simt(work, n, E, V2, (long)E * ld, ld, beta, Kdst, sum_over_rows, st);
+        }
+        if (rc) return rc;
+    }
+    return FCMA_OK;
+}
+
+extern "C" int fcma_voxel_kernels(const void *rows_op, const void *cols_op, int precision, int E, int T, long V, long V2,
+                                  long start, long nb, int eps, int flags, float *work_dev, size_t work_bytes,
+                                  float *K_dev, void *stream)
+{
+    int rc = check_device();
+    if (rc) return rc;
+    if (eps <= 0) return fail(FCMA_EINVAL, "fcma_voxel_kernels: epochs_per_subj must be positive");
+    return run_pipeline(rows_op, cols_op, precision, E, T, V, V2, start, nb, eps, flags, work_dev, work_bytes, K_dev, 0,
+                        (cudaStream_t)stream);
+}
+
+extern "C" int fcma_classifier_kernel(const void *rows_op, const void *cols_op, int precision, int E, int T, long V,
+                                      long V2, long start, long nb, int eps, int flags, float *work_dev,
+                                      size_t work_bytes, float *K_dev, void *stream)
+{
+    int rc = check_device();
+    if (rc) return rc;
+    return run_pipeline(rows_op, cols_op, precision, E, T, V, V2, start, nb, eps, flags, work_dev, work_bytes, K_dev, 1,
+                        (cudaStream_t)stream);
+}
+
+extern "C" int fcma_gemm_nt(const float *A_dev, const float *B_dev, float *C_dev, long M, long N, long K, long lda,
+                            long ldb, long ldc, void *stream)
+{
+    int rc = check_device();
+    if (rc) return rc;
+    if (!A_dev || !B_dev || !C_dev || M <= 0 || N <= 0 || K <= 0 || lda < K || ldb < K || ldc < N)
+        return fail(FCMA_EINVAL, "fcma_gemm_nt: bad arguments");
+    if (cdiv(M, 64) > 65535) return fail(FCMA_EINVAL, "fcma_gemm_nt: M too large");
+    dim3 grid((unsigned)cdiv(N, 64), (unsigned)cdiv(M, 64));
+    k_gemm_nt<<<grid, 256, 0, (cudaStream_t)stream>>>(A_dev, B_dev, C_dev, M, N, K, lda, ldb, ldc);
+    LAUNCH_CHECK("k_gemm_nt");
+    return FCMA_OK;
+}
+
+extern "C" int fcma_row_normalize(float *X_dev, long R, long D, long ld, int nan_to_zero, void *stream)
+{
+    int rc = check_device();
+    if (rc) return rc;
+    if (!X_dev || R <= 0 || D <= 0 || ld < D) return fail(FCMA_EINVAL, "fcma_row_normalize: bad arguments");
+    long g = R < 148L * 8 ? R : 148L * 8;
+    k_row_normalize<<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(X_dev, R, D, ld, nan_to_zero);
+    LAUNCH_CHECK("k_row_normalize");
+    return FCMA_OK;
+}
+
+// ---------------------------------------------------------------- host-buffer entry points
+struct DevBuf {
+    void *p = nullptr;
+    ~DevBuf()
+    {
+        if (p) cudaFree(p);
+    }
+    cudaError_t alloc(size_t n) { return cudaMalloc(&p, n ? n : 1); }
+};
+
+extern "C" int fcma_host_voxel_kernels(const float *const *raw_host, const float *const *raw2_host, const int *T_e, int E,
+                                       long V, long V2, long start, long nb, int eps, int precision, int normalize,
+                                       int flags, int device, float *K_host)
+{
+    if (!raw_host || !T_e || !K_host || E <= 0 || V <= 0 || nb <= 0) return fail(FCMA_EINVAL, "fcma_host_voxel_kernels: bad arguments");
+    if (fcma_device_count() == 0) return fail(FCMA_ENODEV, "no sm_100 device");
+    CUDA_TRY(cudaSetDevice(device));
+    int rc = check_device();
+    if (rc) return rc;
+    int T = 0;
+    for (int e = 0; e < E; e++) {
+        if (T_e[e] <= 0) return fail(FCMA_EINVAL, "epoch %d has non-positive length", e);
+        if (T_e[e] > T) T = T_e[e];
+    }
+    const bool two = raw2_host != nullptr;
+    if (!two) V2 = V;
+    cudaStream_t st = 0;
+    DevBuf epochs, epochs2, opR, opC, work, K;
+    // stage the epochs as [E][T][V] (zero rows beyond T_e)
+    auto upload = [&](DevBuf &buf, const float *const *src, long W) -> int {
+        size_t bytes = (size_t)E * T * W * sizeof(float);
+        CUDA_TRY(buf.alloc(bytes));
+        CUDA_TRY(cudaMemsetAsync(buf.p, 0, bytes, st));
+        for (int e = 0; e < E; e++)
+            CUDA_TRY(cudaMemcpyAsync((float *)buf.p + (size_t)e * T * W, src[e], (size_t)T_e[e] * W * sizeof(float),
+                                     cudaMemcpyHostToDevice, st));
+        return FCMA_OK;
+    };
+    rc = upload(epochs, raw_host, V);
+    if (rc) return rc;
+    size_t opb = fcma_operand_bytes(precision, E, T, V);
+    if (!opb) return fail(FCMA_EINVAL, "unknown precision %d", precision);
+    CUDA_TRY(opR.alloc(opb));
+    rc = fcma_pack_operand((const float *)epochs.p, E, T, V, V, T_e, normalize, precision, opR.p, opb, st);
+    if (rc) return rc;
+    const void *colsp = opR.p;
+    if (two) {
+        rc = upload(epochs2, raw2_host, V2);
+        if (rc) return rc;
+        size_t opb2 = fcma_operand_bytes(precision, E, T, V2);
+        CUDA_TRY(opC.alloc(opb2));
+        rc = fcma_pack_operand((const float *)epochs2.p, E, T, V2, V2, T_e, normalize, precision, opC.p, opb2, st);
+        if (rc) return rc;
+        colsp = opC.p;
+    }
+    size_t per_row = fcma_work_bytes_per_row(E, V2);
+    size_t freeb = 0, totalb = 0;
+    CUDA_TRY(cudaMemGetInfo(&freeb, &totalb));
+    long rows = (long)((freeb / 2) / per_row);
+    if (rows > nb) rows = nb;
+    if (rows > 4096) rows = 4096;
+    if (rows < 1) return fail(FCMA_ENOMEM, "not enough device memory for one correlation row block");
+    CUDA_TRY(work.alloc(per_row * rows));
+    CUDA_TRY(K.alloc((size_t)nb * E * E * sizeof(float)));
+    rc = fcma_voxel_kernels(opR.p, colsp, precision, E, T, V, V2, start, nb, eps, flags, (float *)work.p, per_row * rows,
+                            (float *)K.p, st);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(K_host, K.p, (size_t)nb * E * E * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return FCMA_OK;
+}
+
+extern "C" int fcma_host_within_subject_norm(float *corr_host, long n0, int E, long n2, int eps, int device)
+{
+    if (!corr_host || n0 <= 0 || E <= 0 || n2 <= 0) return fail(FCMA_EINVAL, "fcma_host_within_subject_norm: bad shape");
+    if (fcma_device_count() == 0) return fail(FCMA_ENODEV, "no sm_100 device");
+    CUDA_TRY(cudaSetDevice(device));
+    DevBuf d;
+    size_t bytes = (size_t)n0 * E * n2 * sizeof(float);
+    CUDA_TRY(d.alloc(bytes));
+    CUDA_TRY(cudaMemcpy(d.p, corr_host, bytes, cudaMemcpyHostToDevice));
+    int rc = fcma_within_subject_norm((float *)d.p, n0, E, n2, eps, 0);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpy(corr_host, d.p, bytes, cudaMemcpyDeviceToHost));
+    return FCMA_OK;
+}

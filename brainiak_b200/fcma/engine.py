@@ -1,0 +1,287 @@
+"""Device-side plumbing of the FCMA correlation engine: torch tensors hold HBM, the kernels live in
+libfcma_b200.so and are called through the C ABI (include/fcma_b200.h) with raw device pointers.
+
+HBM layout
+----------
+* epochs          float32 ``[E, T, V]``        voxels contiguous (the reference's ``raw_data`` list,
+                                               voxelselector.py:72-76, stacked; rows ``t >= T_e`` zero)
+* packed operand  ``[planes, E, V, Kp]``       K-major (time contiguous per voxel), bf16 or tf32,
+                                               hi/lo planes for the 3-product fp32-faithful modes
+* corr block      float32 ``[nb, E, ld]``      ``ld = round_up(V2, 32)``; raw r or Fisher-z
+* kernels         float32 ``[nb, E, E]``
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from .. import _lib
+
+_PREC_DEFAULT = "tf32x3"
+
+
+def _stream_ptr():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _prec_code(precision):
+    try:
+        return _lib.PREC[precision]
+    except KeyError:
+        raise ValueError("unknown precision %r (choose from %s)" % (precision, sorted(_lib.PREC)))
+
+
+def stack_epochs(raw_data, device):
+    """list of E float32 ``[T_e, V]`` host arrays (or a ``[E, T, V]`` tensor) -> (``[E, Tmax, V]``
+    float32 CUDA tensor, list of T_e).  Copies go through pinned memory."""
+    if isinstance(raw_data, torch.Tensor):
+        t = raw_data.to(device=device, dtype=torch.float32).contiguous()
+        if t.dim() != 3:
+            raise ValueError("epoch tensor must be [E, T, V]")
+        return t, [t.shape[1]] * t.shape[0]
+    E = len(raw_data)
+    if E == 0:
+        raise ValueError("no epochs")
+    V = raw_data[0].shape[1]
+    T_e = [int(m.shape[0]) for m in raw_data]
+    T = max(T_e)
+    for m in raw_data:
+        if m.ndim != 2 or m.shape[1] != V:
+            raise ValueError("all epochs must be 2D with the same number of voxels")
+    same = all(t == T for t in T_e)
+    host = torch.empty((E, T, V), dtype=torch.float32, pin_memory=True) if same else \
+        torch.zeros((E, T, V), dtype=torch.float32, pin_memory=True)
+    hn = host.numpy()
+    for e, m in enumerate(raw_data):
+        hn[e, :T_e[e], :] = m          # numpy casts to float32 like Cython's float[:, ::1] would demand
+    return host.to(device, non_blocking=True), T_e
+
+
+class PackedOperand:
+    """K-major, precision-split copy of one set of epochs, ready for TMA."""
+
+    def __init__(self, buf, E, T, V, precision, T_e):
+        self.buf, self.E, self.T, self.V = buf, E, T, V
+        self.precision, self.T_e = precision, T_e
+
+    @property
+    def device(self):
+        return self.buf.device
+
+
+def pack_epochs(epochs, T_e=None, precision=_PREC_DEFAULT, normalize=False):
+    """epochs: float32 CUDA ``[E, T, V]``.  normalize=True applies preprocessing.py:80-84 on the fly."""
+    lib = _lib.load()
+    _lib.require_device()
+    if epochs.dtype != torch.float32 or not epochs.is_cuda or not epochs.is_contiguous():
+        raise ValueError("epochs must be a contiguous float32 CUDA tensor [E, T, V]")
+    E, T, V = epochs.shape
+    code = _prec_code(precision)
+    if code == _lib.PREC["f32simt"]:
+        raise ValueError("f32simt works on unpacked epochs")
+    nbytes = lib.fcma_operand_bytes(code, E, T, V)
+    buf = torch.empty(nbytes, dtype=torch.uint8, device=epochs.device)
+    te = None
+    if T_e is not None and any(t != T for t in T_e):
+        te = (ctypes.c_int * E)(*T_e)
+    with torch.cuda.device(epochs.device):
+        _lib.check(lib.fcma_pack_operand(_ptr(epochs), E, T, V, V, te, int(bool(normalize)), code,
+                                         _ptr(buf), nbytes, _stream_ptr()))
+    return PackedOperand(buf, E, T, V, precision, list(T_e) if T_e is not None else [T] * E)
+
+
+def epoch_normalize_(epochs, T_e=None):
+    lib = _lib.load()
+    _lib.require_device()
+    E, T, V = epochs.shape
+    te = None
+    if T_e is not None and any(t != T for t in T_e):
+        te = (ctypes.c_int * E)(*T_e)
+    with torch.cuda.device(epochs.device):
+        _lib.check(lib.fcma_epoch_normalize(_ptr(epochs), E, T, V, V, te, _stream_ptr()))
+    return epochs
+
+
+def _check_pair(rows, cols):
+    if rows.E != cols.E or rows.T != cols.T or rows.precision != cols.precision:
+        raise ValueError("row/column operands must share epochs, epoch length and precision")
+
+
+def corr_block(rows, cols, start, nb, layout=0, fisher_epochs=0, out=None, ld=None):
+    """a4/a9 on tensor cores.  Returns ``[nb, E, V2]`` (layout 0) or ``[E, nb, V2]`` (layout 1)."""
+    lib = _lib.load()
+    _check_pair(rows, cols)
+    E, V2 = rows.E, cols.V
+    ld = V2 if ld is None else ld
+    shape = (nb, E, ld) if layout == 0 else (E, nb, ld)
+    if out is None:
+        out = torch.empty(shape, dtype=torch.float32, device=rows.device)
+    si, se = (E * ld, ld) if layout == 0 else (ld, nb * ld)
+    with torch.cuda.device(rows.device):
+        _lib.check(lib.fcma_corr_block(_ptr(rows.buf), _ptr(cols.buf), _prec_code(rows.precision), E,
+                                       rows.T, rows.V, V2, start, nb, _ptr(out), si, se,
+                                       fisher_epochs, _stream_ptr()))
+    return out[..., :V2] if ld != V2 else out
+
+
+def corr_block_f32(epochs_r, epochs_c, start, nb, layout=0):
+    """a4 with fp32 FFMA on the unpacked epochs (reference-order numerics)."""
+    lib = _lib.load()
+    _lib.require_device()
+    E, T, V = epochs_r.shape
+    V2 = epochs_c.shape[2]
+    shape = (nb, E, V2) if layout == 0 else (E, nb, V2)
+    out = torch.empty(shape, dtype=torch.float32, device=epochs_r.device)
+    si, se = (E * V2, V2) if layout == 0 else (V2, nb * V2)
+    with torch.cuda.device(epochs_r.device):
+        _lib.check(lib.fcma_corr_block_f32(_ptr(epochs_r), V, _ptr(epochs_c), V2, E, T, V, V2, start,
+                                           nb, _ptr(out), si, se, _stream_ptr()))
+    return out
+
+
+def within_subject_norm_(corr, eps):
+    """a6 in place on a contiguous float32 CUDA ``[n0, E, n2]`` tensor."""
+    lib = _lib.load()
+    if corr.dim() != 3:
+        raise RuntimeError("The multi-subject correlation data structure must be 3D")
+    if corr.dtype != torch.float32 or not corr.is_contiguous():
+        raise ValueError("corr must be contiguous float32")
+    n0, E, n2 = corr.shape
+    with torch.cuda.device(corr.device):
+        _lib.check(lib.fcma_within_subject_norm(_ptr(corr), n0, E, n2, int(eps), _stream_ptr()))
+    return corr
+
+
+def kernel_matrices(z, beta=0.0, out=None, sum_over_rows=False):
+    """a7/a11: ``K[i] = beta*K[i] + Z_i Z_i^T`` for ``z`` = ``[nb, E, n2]`` (last dim may be a view)."""
+    lib = _lib.load()
+    nb, E, n2 = z.shape
+    if z.stride(2) != 1:
+        raise ValueError("innermost dimension must be contiguous")
+    if out is None:
+        out = torch.zeros((E, E) if sum_over_rows else (nb, E, E), dtype=torch.float32,
+                          device=z.device)
+    with torch.cuda.device(z.device):
+        _lib.check(lib.fcma_kernel_matrices(_ptr(z), nb, E, n2, z.stride(0), z.stride(1), float(beta),
+                                            _ptr(out), int(sum_over_rows), _stream_ptr()))
+    return out
+
+
+def norm_kernel_matrices(corr, eps, fisher_done=False, self_col0=-1, beta=0.0, out=None,
+                         sum_over_rows=False):
+    """fused a6+a7 on a raw-correlation block ``[nb, E, n2]``."""
+    lib = _lib.load()
+    nb, E, n2 = corr.shape
+    if out is None:
+        out = torch.zeros((E, E) if sum_over_rows else (nb, E, E), dtype=torch.float32,
+                          device=corr.device)
+    with torch.cuda.device(corr.device):
+        _lib.check(lib.fcma_norm_kernel_matrices(_ptr(corr), nb, E, n2, corr.stride(0), corr.stride(1),
+                                                 int(eps), int(fisher_done), int(self_col0),
+                                                 float(beta), _ptr(out), int(sum_over_rows),
+                                                 _stream_ptr()))
+    return out
+
+
+def fused_supported(E, eps):
+    return E <= 64 and eps >= 1 and (eps & (eps - 1)) == 0 and eps <= (32 if E <= 32 else 64)
+
+
+class Workspace:
+    """Scratch for the correlation block of the fused pipelines (never holds results)."""
+
+    def __init__(self, E, V2, rows, device):
+        lib = _lib.load()
+        self.per_row = lib.fcma_work_bytes_per_row(E, V2)
+        self.rows = rows
+        self.buf = torch.empty(self.per_row * rows, dtype=torch.uint8, device=device)
+
+    @staticmethod
+    def rows_for(E, V2, nb, device, max_bytes=None):
+        per_row = _lib.load().fcma_work_bytes_per_row(E, V2)
+        if max_bytes is None:
+            free, _ = torch.cuda.mem_get_info(device)
+            max_bytes = min(free // 2, 32 << 30)
+        rows = max(1, min(nb, max_bytes // per_row))
+        if rows >= 256:
+            rows = (rows // 256) * 256
+        return rows
+
+
+def voxel_kernels(rows, cols, start, nb, eps, flags=0, work=None, out=None):
+    """a4 -> a6 -> a7 for voxel rows [start, start+nb): unshrunk kernels ``[nb, E, E]``."""
+    lib = _lib.load()
+    _check_pair(rows, cols)
+    E, V2 = rows.E, cols.V
+    if work is None:
+        work = Workspace(E, V2, Workspace.rows_for(E, V2, nb, rows.device), rows.device)
+    if out is None:
+        out = torch.empty((nb, E, E), dtype=torch.float32, device=rows.device)
+    with torch.cuda.device(rows.device):
+        _lib.check(lib.fcma_voxel_kernels(_ptr(rows.buf), _ptr(cols.buf), _prec_code(rows.precision), E,
+                                          rows.T, rows.V, V2, start, nb, int(eps), int(flags),
+                                          _ptr(work.buf), work.buf.numel(), _ptr(out), _stream_ptr()))
+    return out
+
+
+def classifier_kernel(rows, cols, start, nb, eps, flags=0, work=None, out=None):
+    """a9 -> a10 -> a11: accumulates sum_i Z_i Z_i^T over rows [start, start+nb) into ``out`` [E, E]."""
+    lib = _lib.load()
+    _check_pair(rows, cols)
+    E, V2 = rows.E, cols.V
+    if work is None:
+        work = Workspace(E, V2, Workspace.rows_for(E, V2, nb, rows.device), rows.device)
+    if out is None:
+        out = torch.zeros((E, E), dtype=torch.float32, device=rows.device)
+    with torch.cuda.device(rows.device):
+        _lib.check(lib.fcma_classifier_kernel(_ptr(rows.buf), _ptr(cols.buf), _prec_code(rows.precision),
+                                              E, rows.T, rows.V, V2, start, nb, int(eps), int(flags),
+                                              _ptr(work.buf), work.buf.numel(), _ptr(out),
+                                              _stream_ptr()))
+    return out
+
+
+def gemm_nt(a, b):
+    """``a @ b.T`` in fp32 FFMA (a12/a15)."""
+    lib = _lib.load()
+    M, K = a.shape
+    N = b.shape[0]
+    out = torch.empty((M, N), dtype=torch.float32, device=a.device)
+    with torch.cuda.device(a.device):
+        _lib.check(lib.fcma_gemm_nt(_ptr(a), _ptr(b), _ptr(out), M, N, K, a.stride(0), b.stride(0), N,
+                                    _stream_ptr()))
+    return out
+
+
+def row_normalize_(x, nan_to_zero=True):
+    lib = _lib.load()
+    R, D = x.shape
+    with torch.cuda.device(x.device):
+        _lib.check(lib.fcma_row_normalize(_ptr(x), R, D, x.stride(0), int(nan_to_zero), _stream_ptr()))
+    return x
+
+
+def host_voxel_kernels(raw_data, raw_data2, start, nb, eps, precision=_PREC_DEFAULT, normalize=False,
+                       flags=0, device=0):
+    """The C-ABI host entry point: numpy in, numpy out, all copies inside the call."""
+    lib = _lib.load()
+    E = len(raw_data)
+    V = raw_data[0].shape[1]
+    keep = [np.ascontiguousarray(m, dtype=np.float32) for m in raw_data]
+    arr = (ctypes.POINTER(ctypes.c_float) * E)(*[m.ctypes.data_as(ctypes.POINTER(ctypes.c_float)) for m in keep])
+    arr2, V2, keep2 = None, V, None
+    if raw_data2 is not None:
+        keep2 = [np.ascontiguousarray(m, dtype=np.float32) for m in raw_data2]
+        V2 = keep2[0].shape[1]
+        arr2 = (ctypes.POINTER(ctypes.c_float) * E)(
+            *[m.ctypes.data_as(ctypes.POINTER(ctypes.c_float)) for m in keep2])
+    te = (ctypes.c_int * E)(*[m.shape[0] for m in keep])
+    K = np.empty((nb, E, E), np.float32)
+    _lib.check(lib.fcma_host_voxel_kernels(arr, arr2, te, E, V, V2, start, nb, int(eps),
+                                           _prec_code(precision), int(bool(normalize)), int(flags),
+                                           int(device), K.ctypes.data_as(ctypes.c_void_p)))
+    return K

@@ -1,0 +1,156 @@
+/*
+ * fcma_b200.h — C ABI of the Blackwell-native FCMA correlation engine (libfcma_b200.so).
+ *
+ * Drop-in boundary for the native modules of brainiak/brainiak @ 123f6e1 on the FCMA hot path:
+ *
+ *   reference native entry point (file:line)                           replaced by
+ *   ------------------------------------------------------------------ ----------------------------
+ *   cython_blas.compute_self_corr_for_voxel_sel  cython_blas.pyx:20    fcma_corr_block (layout 0)
+ *   cython_blas.compute_corr_vectors             cython_blas.pyx:388   fcma_corr_block (layout 1)
+ *   cython_blas.compute_kernel_matrix            cython_blas.pyx:118   fcma_kernel_matrices
+ *   cython_blas.compute_single_matrix_multiplication  pyx:480          fcma_gemm_nt
+ *   fcma_extension.normalization                 fcma_extension.cc:29  fcma_within_subject_norm
+ *   preprocessing._separate_epochs (z-score)     preprocessing.py:80   fcma_pack_operand(normalize=1)
+ *   VoxelSelector._voxel_scoring stages 1-3      voxelselector.py:467  fcma_voxel_kernels
+ *   Classifier._compute_kernel_matrix_in_portion classifier.py:279     fcma_classifier_kernel
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes only.  Pointers named *_dev are CUDA device pointers
+ *     (e.g. torch.Tensor.data_ptr()); `stream` is a cudaStream_t passed as void* (0 = default).
+ *   - The caller owns every buffer (as in the reference, voxelselector.py:307, classifier.py:166);
+ *     the library never retains pointers across calls.
+ *   - Return value: 0 on success, negative FCMA_E* on failure; fcma_last_error() returns a
+ *     thread-local message.  (Reference: ValueError from Cython memoryviews, RuntimeError from
+ *     fcma_extension.cc:47 — the Python wrapper maps FCMA_EINVAL->ValueError, others->RuntimeError.)
+ *   - There is NO CPU fallback: every compute entry point fails with FCMA_ENODEV without a
+ *     Blackwell (sm_100) device.
+ */
+#ifndef FCMA_B200_H
+#define FCMA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FCMA_OK        0
+#define FCMA_EINVAL   -1   /* bad argument (-> ValueError)               */
+#define FCMA_ECUDA    -2   /* CUDA runtime / driver error (-> RuntimeError) */
+#define FCMA_ENODEV   -3   /* no sm_100 device                            */
+#define FCMA_ENOMEM   -4   /* scratch buffer too small                    */
+
+/* Operand precision of the correlation contraction (accumulation is always fp32 in TMEM). */
+#define FCMA_PREC_BF16     0  /* 1 bf16 plane            : |dr| ~ 1e-3                      */
+#define FCMA_PREC_TF32     1  /* 1 tf32 plane            : |dr| ~ 1e-4                      */
+#define FCMA_PREC_BF16X3   2  /* bf16 hi/lo, 3 products  : |dr| ~ 1e-6                      */
+#define FCMA_PREC_TF32X3   3  /* tf32 hi/lo, 3 products  : fp32-equivalent (|dr| ~ 1e-7)    */
+#define FCMA_PREC_F32SIMT  4  /* FFMA reference kernel on the raw fp32 epochs (no packing)  */
+
+/* flags for the fused pipelines */
+#define FCMA_FLAG_MASK_SELF      1  /* zero the self-correlation column after normalisation   */
+#define FCMA_FLAG_FISHER_IN_GEMM 2  /* Fisher-z in the GEMM epilogue (default: in pass 2)     */
+#define FCMA_FLAG_NO_SHRINK_INFO 4  /* reserved                                               */
+
+int         fcma_version(void);
+const char *fcma_last_error(void);
+/* number of usable sm_100 devices (0 if none); never fails */
+int         fcma_device_count(void);
+
+/* ---- operand packing (+ optional a14 normalise prologue) ---------------------------------- */
+/* K extent (elements per voxel row per plane) of a packed operand for epochs of length T. */
+int    fcma_operand_kp(int precision, int T);
+/* planes of a packed operand (1 or 2) */
+int    fcma_operand_planes(int precision);
+/* bytes of a packed operand [planes][E][V][Kp] */
+size_t fcma_operand_bytes(int precision, int E, int T, long V);
+
+/* epochs_dev: float32 [E][T][ld] (voxels contiguous, row pitch ld >= V; rows t >= T_e[e] must be
+ * zero when T_e differs per epoch).  T_e: host array of E epoch lengths or NULL (= all T).
+ * normalize: 0 = data already normalised (reference contract, voxelselector.py:72-76);
+ *            1 = apply preprocessing.py:80-84 per epoch (z-score over the T_e rows, nan->0, /sqrt(T_e)).
+ * Writes the K-major, precision-split operand [planes][E][V][Kp] into packed_dev. */
+int fcma_pack_operand(const float *epochs_dev, int E, int T, long V, long ld, const int *T_e,
+                      int normalize, int precision, void *packed_dev, size_t packed_bytes,
+                      void *stream);
+
+/* a14 alone, in place on float32 [E][T][ld] (preprocessing.py:80-84). */
+int fcma_epoch_normalize(float *epochs_dev, int E, int T, long V, long ld, const int *T_e,
+                         void *stream);
+
+/* ---- a4 / a9: correlation block -------------------------------------------------------------- */
+/* out[i*stride_i + e*stride_e + j] = sum_t rows[e][t][start+i] * cols[e][t][j]
+ *   i < nb, e < E, j < V2.   layout 0 ([nb,E,V2]): stride_i = E*ld, stride_e = ld;
+ *                            layout 1 ([E,nb,V2]): stride_i = ld,   stride_e = nb*ld   (ld >= V2).
+ * rows_op / cols_op: packed operands (same precision) of raw_data [.,.,V] and raw_data2 [.,.,V2]
+ * (pass the same pointer for self-correlation).  fisher_epochs: epochs e < fisher_epochs get
+ * 0.5*log((1+r)/(1-r)) with the clamps of fcma_extension.cc:68-72 applied in the epilogue; 0 = raw r. */
+int fcma_corr_block(const void *rows_op, const void *cols_op, int precision, int E, int T, long V,
+                    long V2, long start, long nb, float *out_dev, long stride_i, long stride_e,
+                    int fisher_epochs, void *stream);
+
+/* same contraction with fp32 FFMA on the unpacked epochs [E][T][ld*] (reference-order numerics) */
+int fcma_corr_block_f32(const float *rows_epochs, long ldr, const float *cols_epochs, long ldc,
+                        int E, int T, long V, long V2, long start, long nb, float *out_dev,
+                        long stride_i, long stride_e, void *stream);
+
+/* ---- a6: Fisher-z + within-subject z-score, in place (exact semantics of fcma_extension.cc:52-84,
+ * including untouched trailing epochs); corr: float32 [n0][E][n2] contiguous. */
+int fcma_within_subject_norm(float *corr_dev, long n0, int E, long n2, int eps, void *stream);
+
+/* ---- a7 / a11: linear kernels ------------------------------------------------------------------ */
+/* K[i] = beta*K[i] + Z_i Z_i^T, Z_i = z[i*stride_i + e*ld + j], j < n2; K: [nb][E][E] (full, symmetric).
+ * With sum_over_rows != 0 a single [E][E] matrix K = beta*K + sum_i Z_i Z_i^T is produced
+ * (Classifier, classifier.py:334-339). */
+int fcma_kernel_matrices(const float *z_dev, long nb, int E, long n2, long stride_i, long ld,
+                         float beta, float *K_dev, int sum_over_rows, void *stream);
+
+/* fused a6+a7: input is raw r (fisher_done=0) or Fisher-z for epochs < (E/eps)*eps (fisher_done=1);
+ * normalised values are never written.  self_col0 >= 0: column of voxel 0's self-correlation
+ * (voxel i masks column self_col0+i), -1: no masking. */
+int fcma_norm_kernel_matrices(const float *corr_dev, long nb, int E, long n2, long stride_i, long ld,
+                              int eps, int fisher_done, long self_col0, float beta, float *K_dev,
+                              int sum_over_rows, void *stream);
+
+/* ---- fused pipelines ----------------------------------------------------------------------------- */
+/* bytes of scratch needed per block row by the pipelines (so callers can size `work`) */
+size_t fcma_work_bytes_per_row(int E, long V2);
+
+/* a4 -> a6 -> a7 for voxel rows [start, start+nb): K_dev[nb][E][E] (unshrunk; the decimal shrink of
+ * voxelselector.py:409-412 is applied by the caller).  work_dev: scratch of work_bytes
+ * (>= fcma_work_bytes_per_row; more rows per pass = fewer launches). */
+int fcma_voxel_kernels(const void *rows_op, const void *cols_op, int precision, int E, int T, long V,
+                       long V2, long start, long nb, int eps, int flags, float *work_dev,
+                       size_t work_bytes, float *K_dev, void *stream);
+
+/* a9 -> a10 -> a11: K_dev[E][E] += sum over rows [start, start+nb) (beta = 1 semantics, caller zeroes
+ * K first as classifier.py:311-313 does); eps <= 1 skips the normalisation (classifier.py:204). */
+int fcma_classifier_kernel(const void *rows_op, const void *cols_op, int precision, int E, int T,
+                           long V, long V2, long start, long nb, int eps, int flags, float *work_dev,
+                           size_t work_bytes, float *K_dev, void *stream);
+
+/* ---- a12 / a15: plain NT GEMM  C[m][n] = sum_k A[m][k]*B[n][k]  (fp32 FFMA, row-major) ---------- */
+int fcma_gemm_nt(const float *A_dev, const float *B_dev, float *C_dev, long M, long N, long K,
+                 long lda, long ldb, long ldc, void *stream);
+/* rows of X [R][D] (pitch ld) -> z-score / sqrt(D) in place, util.py:32-60; nan_to_zero as return_nans=False */
+int fcma_row_normalize(float *X_dev, long R, long D, long ld, int nan_to_zero, void *stream);
+
+/* ---- host-buffer entry points (what a cgo/ctypes binding of the reference would call) ------------ */
+/* raw_host / raw2_host: E pointers to C-contiguous float32 [T_e][V] / [T_e][V2] HOST arrays
+ * (raw2_host may be NULL for self-correlation); K_host: float32 [nb][E][E] HOST.  Performs H2D,
+ * packing, the fused pipeline and D2H on `device`, synchronously. */
+int fcma_host_voxel_kernels(const float *const *raw_host, const float *const *raw2_host,
+                            const int *T_e, int E, long V, long V2, long start, long nb, int eps,
+                            int precision, int normalize, int flags, int device, float *K_host);
+
+/* in-place host variants of the reference's native functions */
+int fcma_host_within_subject_norm(float *corr_host, long n0, int E, long n2, int eps, int device);
+
+/* number of kernel launches issued by this library in the calling process (for bench accounting) */
+long fcma_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FCMA_B200_H */

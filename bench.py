@@ -1,0 +1,383 @@
+#!/usr/bin/env python
+"""bench.py — FCMA correlation hot path: voxel-pair correlations / second.
+
+  python bench.py --gpus N --steps K --warmup W            # B200 arm (one rank per GPU under torchrun)
+  python bench.py --impl reference --steps K --warmup W    # the reference's own CPU path, same metric
+
+A *step* is one pass of the hot path over the whole synthetic workload (BASELINE.json: V=50 000
+voxels, T=200 TRs, E=32 epochs, eps=8): pack the (already normalised, HBM-resident) epochs, then for
+every voxel row the correlation GEMM -> Fisher-z + within-subject z-score -> E x E kernel matrix, with
+the [V, E, E] kernels left resident in HBM.  metric = V * V * E / step time.
+
+N > 1: voxel rows are sharded statically over the ranks (the reference's data-parallel scheme,
+voxelselector.py:198-238); inside the timed step rank 0 broadcasts the epochs over NCCL and the
+per-rank kernels are gathered on rank 0.  The total job is fixed, so scaling is "strong".
+
+One JSON line is printed by rank 0.  Extra objects: `roofline` (dominant kernel, measured live with
+CUDA events), `cpu_baseline` (reference path on this box's host cores, bounded sample), `e2e` (host
+buffers in, host buffers out, copies inside the timed region), `clocks`.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = dict(V=50000, T=200, E=32, eps=8)
+METRIC = "voxel-pair correlations/sec"
+UNIT = "corr/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--precision", default="tf32x3")
+    ap.add_argument("--voxels", type=int, default=WORKLOAD["V"], help="override V (debug only)")
+    ap.add_argument("--block-rows", type=int, default=4096)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def make_host_epochs(V, T, E, pin=False):
+    """Synthetic workload of SURVEY.md §8d, generated with torch's CPU generator (seeded):
+    Gaussian epochs, a planted common time course in the first V//100 voxels of odd epochs,
+    then the reference normalisation (zscore over TRs, ddof=0; / sqrt(T))."""
+    import torch
+    g = torch.Generator().manual_seed(1234567890)
+    x = torch.empty((E, T, V), dtype=torch.float32, pin_memory=pin)
+    for e in range(E):
+        m = torch.randn((T, V), generator=g)
+        if e % 2 == 1:
+            m[:, : V // 100] += 0.6 * torch.randn((T, 1), generator=g)
+        m = (m - m.mean(0, keepdim=True)) / m.std(0, unbiased=False, keepdim=True)
+        x[e] = torch.nan_to_num(m) / (T ** 0.5)
+    return x
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons, power = [], 0, set(), []
+        for line in self.f.read().splitlines():
+            parts = [s.strip() for s in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                c, m, pw = float(parts[1]), float(parts[2]), float(parts[3])
+            except ValueError:
+                continue
+            mx = max(mx, m)
+            power.append(pw)
+            if pw > 250:          # under load
+                sm.append(c)
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                "sw_power_cap"), parts[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.f.name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples_under_load": len(sm),
+                "power_w_max": max(power) if power else None}
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm / cpu baseline
+# ---------------------------------------------------------------------------------------------
+def reference_task_fn(host_epochs, eps):
+    """Returns (fn(start, n) -> seconds for the kernel path a4+a6+a7 of one task, kind, cores)."""
+    from sklearn import svm
+    E, T, V = host_epochs.shape
+    raw = [host_epochs[e].numpy() for e in range(E)]
+    labels = [e % 2 for e in range(E)]
+    clf = svm.SVC(kernel="precomputed", shrinking=False, C=1)
+    from oracle import reference
+    if reference.available():
+        m = reference.load()
+        vs = m.VoxelSelector(labels, eps, E // eps, raw, voxel_unit=64, process_num=0)
+        cores = len(os.sched_getaffinity(0))
+
+        def fn(start, n):
+            t0 = time.perf_counter()
+            corr = vs._correlation_computation((start, n))             # voxelselector.py:492
+            m.fcma_extension.normalization(corr, eps)                   # voxelselector.py:496
+            vs._prepare_for_cross_validation(corr, clf)                 # voxelselector.py:505
+            return time.perf_counter() - t0
+        return fn, "reference", cores
+    from oracle import fcma_oracle as orc
+
+    def fn(start, n):
+        t0 = time.perf_counter()
+        orc.voxel_block(raw, None, start, n, eps, shrink=True)
+        return time.perf_counter() - t0
+    return fn, "port", orc.num_threads()
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    V, T, E, eps = args.voxels, WORKLOAD["T"], WORKLOAD["E"], WORKLOAD["eps"]
+    host = make_host_epochs(V, T, E)
+    fn, kind, cores = reference_task_fn(host, eps)
+    rows = 64                                     # the reference's default voxel_unit
+    for w in range(args.warmup):
+        fn((w * rows) % (V - rows), rows)
+    tsum = 0.0
+    for k in range(args.steps):
+        tsum += fn(((args.warmup + k) * rows) % (V - rows), rows)
+    value = args.steps * rows * V * E / tsum
+    sample = "%d tasks of %d voxel rows x V=%d x E=%d (kernel path a4+a6+a7, no CV)" % (args.steps, rows, V, E)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tsum / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": {"workload": "FCMA VoxelSelector V=%d T=%d E=%d eps=%d" % (V, T, E, eps),
+                                            "step": "one task of 64 voxel rows (bounded sample)"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------
+# B200 arm
+# ---------------------------------------------------------------------------------------------
+def run_b200_arm(args):
+    import torch
+    import torch.distributed as dist
+    from brainiak_b200 import _lib
+    from brainiak_b200.fcma import engine
+    from brainiak_b200.fcma.voxelselector import VoxelSelector
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus %d needs torchrun --nproc-per-node %d" % (args.gpus, args.gpus))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    _lib.require_device()
+
+    V, T, E, eps = args.voxels, WORKLOAD["T"], WORKLOAD["E"], WORKLOAD["eps"]
+    prec = args.precision
+    flags = 0
+    start, n = VoxelSelector.row_partition(V, world)[rank]
+    block = min(args.block_rows, max(n, 1))
+
+    # inputs: pinned host copy on rank 0 (for e2e) and the HBM-resident epochs
+    host = make_host_epochs(V, T, E, pin=True) if rank == 0 else None
+    epochs = torch.empty((E, T, V), dtype=torch.float32, device=dev)
+    if rank == 0:
+        epochs.copy_(host, non_blocking=True)
+    bcast = torch.empty_like(epochs) if world > 1 else None   # receive buffer used inside the step
+    work = engine.Workspace(E, V, block, dev)
+    K = torch.empty((max(n, 1), E, E), dtype=torch.float32, device=dev)
+    per = VoxelSelector.row_partition(V, world)[0][1]
+    Kall = torch.empty((world * per, E, E), dtype=torch.float32, device=dev) if (world > 1 and rank == 0) else None
+    Kpad = torch.zeros((per, E, E), dtype=torch.float32, device=dev) if world > 1 else None
+    Khost = torch.empty((V, E, E), dtype=torch.float32, pin_memory=True) if rank == 0 else None
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[local])
+        torch.cuda.synchronize()
+
+    def step(from_host):
+        """One pass of the hot path. from_host: include the pinned-host -> HBM copy and the K readback."""
+        if from_host and rank == 0:
+            epochs.copy_(host, non_blocking=True)
+        src = epochs
+        if world > 1:
+            if rank == 0:
+                bcast.copy_(epochs)
+            dist.broadcast(bcast, src=0)
+            src = bcast
+        op = engine.pack_epochs(src, None, prec)
+        if n > 0:
+            engine.voxel_kernels(op, op, start, n, eps, flags=flags, work=work, out=K)
+        if world > 1:
+            Kpad[:n].copy_(K[:n])
+            dist.gather(Kpad, list(Kall.view(world, per, E, E).unbind(0)) if rank == 0 else None, dst=0)
+        if from_host and rank == 0:
+            res = Kall.view(-1, E, E)[:V] if world > 1 else K
+            Khost.copy_(res, non_blocking=True)
+
+    def timed(nsteps, from_host):
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = lib.fcma_launch_count()
+        ev0.record()
+        for _ in range(nsteps):
+            step(from_host)
+        ev1.record()
+        barrier()
+        ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+        launches = torch.tensor([float(lib.fcma_launch_count() - l0)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            dist.all_reduce(launches, op=dist.ReduceOp.SUM)
+        return float(ms[0]), int(launches[0])
+
+    for _ in range(max(args.warmup, 3)):
+        step(False)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_total, launches = timed(args.steps, False)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_step = ms_total / args.steps
+    corr_total = float(V) * V * E
+    value = corr_total / (ms_step * 1e-3)
+
+    e2e = None
+    if not args.no_e2e:
+        step(True)
+        ms_e2e, _ = timed(max(2, min(args.steps, 3)), True)
+        ms_e2e /= max(2, min(args.steps, 3))
+        e2e = {"value": corr_total / (ms_e2e * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": int(E) * T * V * 4, "d2h_bytes_per_step": int(V) * E * E * 4,
+               "ms_per_step": ms_e2e,
+               "path": "pinned host epochs -> HBM -> pack -> fcma_voxel_kernels -> [V,E,E] kernels -> pinned host"}
+
+    # ---- roofline of the dominant kernel, measured live with CUDA events on the launch stream
+    roofline = None
+    if rank == 0:
+        op = engine.pack_epochs(epochs, None, prec)
+        nbk = min(block, n)
+        ld = ((V + 31) // 32) * 32
+        cbuf = work.buf.view(torch.float32)[: nbk * E * ld].view(nbk, E, ld)
+        Kb = K[:nbk]
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        tg, ts, reps = 0.0, 0.0, 4
+        for r in range(reps + 1):
+            evs[0].record()
+            engine.corr_block(op, op, start, nbk, out=cbuf, ld=ld)
+            evs[1].record()
+            engine.norm_kernel_matrices(cbuf[:, :, :V], eps, out=Kb)
+            evs[2].record()
+            torch.cuda.synchronize()
+            if r > 0:
+                tg += evs[0].elapsed_time(evs[1])
+                ts += evs[1].elapsed_time(evs[2])
+        tg, ts = tg / reps, ts / reps
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        tf_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+        corr_launch = float(nbk) * V * E
+        planes = lib.fcma_operand_planes(_lib.PREC[prec])
+        op_bytes = lib.fcma_operand_bytes(_lib.PREC[prec], E, T, V)
+        # algorithmic bytes of the GEMM launch: write 4 B per correlation + read the operand once
+        alg_bytes = 4.0 * corr_launch + op_bytes
+        traffic = None
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            key = "k_corr_umma:%s:nb%d" % (prec, nbk)
+            traffic = tr.get(key)
+        except Exception:
+            pass
+        dominant = "k_corr_umma" if tg >= ts else "k_norm_syrk"
+        ach = alg_bytes / (tg * 1e-3) / 1e9 if dominant == "k_corr_umma" else 4.0 * corr_launch / (ts * 1e-3) / 1e9
+        roofline = {"kernel": dominant, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": ach / hbm_peak, "traffic": traffic,
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
+                    "launch_ms": tg if dominant == "k_corr_umma" else ts,
+                    "rows_per_launch": nbk,
+                    "algorithmic_bytes_per_launch": alg_bytes if dominant == "k_corr_umma" else 4.0 * corr_launch,
+                    "kernels": {
+                        "k_corr_umma": {"ms": tg, "hbm_gbs": alg_bytes / (tg * 1e-3) / 1e9,
+                                        "tensor_tflops_alg": 2.0 * T * corr_launch / (tg * 1e-3) / 1e12,
+                                        "tensor_frac_of_bf16_sustained": 2.0 * T * corr_launch / (tg * 1e-3) / 1e12 / tf_peak,
+                                        "operand_planes": planes},
+                        "k_norm_syrk": {"ms": ts, "hbm_gbs": 4.0 * corr_launch / (ts * 1e-3) / 1e9}}}
+
+    cpu_baseline = None
+    if rank == 0 and not args.no_cpu_baseline and world == 1:
+        fn, kind, cores = reference_task_fn(host, eps)
+        rows, tsum, ntask = 64, 0.0, 0
+        fn(0, rows)
+        t_start = time.perf_counter()
+        while ntask < 8 and (time.perf_counter() - t_start) < 20.0:
+            tsum += fn((ntask + 1) * rows, rows)
+            ntask += 1
+        cpu_baseline = {"value": ntask * rows * float(V) * E / tsum, "unit": UNIT, "cores": cores, "kind": kind,
+                        "sample": "%d tasks of 64 voxel rows x V=%d x E=%d, kernel path a4+a6+a7 "
+                                  "(reference voxelselector.py:492-505), no CV" % (ntask, V, E)}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "tf32" if prec.startswith("tf32") else "bf16",
+                "data": "synthetic",
+                "config": {"workload": "FCMA VoxelSelector V=%d T=%d E=%d eps=%d (BASELINE configs[2] shape)" % (V, T, E, eps),
+                           "precision": prec + (" (3-product split, fp32-faithful: |dr| <= 1e-6)" if prec == "tf32x3" else ""),
+                           "parallelism": "rows%d" % world, "rows_per_pass": block,
+                           "l2": "inputs_exceed_l2 (operand %.1f GB, correlation block %.1f GB per pass)"
+                                 % (lib.fcma_operand_bytes(_lib.PREC[prec], E, T, V) / 1e9,
+                                    lib.fcma_work_bytes_per_row(E, V) * block / 1e9),
+                           "step": "pack + corr GEMM + Fisher/z-score + kernel build for all V rows"
+                                   + ("; NCCL broadcast of epochs + gather of kernels inside the step" if world > 1 else "")},
+                "gpu_launches": launches, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu_baseline,
+                "clocks": clocks}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_b200_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

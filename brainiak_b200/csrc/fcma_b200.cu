@@ -137,11 +137,18 @@ extern "C" int fcma_operand_planes(int precision)
     PrecInfo p;
     return prec_info(precision, &p) ? p.planes : 0;
 }
+// bytes of the K-major planes, rounded up so that the trailing [E][V] fp32 self-correlation diagonal
+// (exact sequential-FMA sum of squares, see k_pack_operand) stays 256-byte aligned
+static size_t operand_plane_bytes(const PrecInfo &p, int precision, int E, int T, long V)
+{
+    size_t b = (size_t)p.planes * E * V * fcma_operand_kp(precision, T) * p.esize;
+    return (b + 255) & ~(size_t)255;
+}
 extern "C" size_t fcma_operand_bytes(int precision, int E, int T, long V)
 {
     PrecInfo p;
     if (!prec_info(precision, &p)) return 0;
-    return (size_t)p.planes * E * V * fcma_operand_kp(precision, T) * p.esize;
+    return operand_plane_bytes(p, precision, E, T, V) + (size_t)E * V * sizeof(float);
 }
 
 // ============================================================================================
@@ -155,7 +162,8 @@ __device__ __forceinline__ float tf32_rn(float x)
 // one block = 32 voxels of one epoch; 256 threads = 32 (voxel) x 8
 template <int KIND, int PLANES>
 __global__ void __launch_bounds__(256) k_pack_operand(const float *__restrict__ src, int E, int T, long V, long ld,
-                                                      const int *__restrict__ T_e, int normalize, void *dst, int Kp)
+                                                      const int *__restrict__ T_e, int normalize, void *dst, int Kp,
+                                                      float *__restrict__ selfdiag)
 {
     __shared__ double s_red[8][33];
     __shared__ float s_mean[32], s_scale[32];
@@ -201,6 +209,21 @@ __global__ void __launch_bounds__(256) k_pack_operand(const float *__restrict__ 
         scale = s_scale[tx];
     }
 
+    // Exact self-correlation of each voxel: the reference's sgemm (OpenBLAS FMA micro-kernel) is
+    // bit-identical to a sequential fp32 FMA chain over t (verified against reference outputs,
+    // tests/golden), so this reproduces its r[i,e,i] = 1 +- ulp rounding pattern exactly.
+    if (ty == 0 && vok) {
+        float acc = 0.f;
+        for (int t = 0; t < Te; t++) {
+            float x = ep[(size_t)t * ld + v];
+            if (normalize) {
+                x = (x - mean) * scale;
+                if (!(x == x)) x = 0.f;
+            }
+            acc = fmaf(x, x, acc);
+        }
+        selfdiag[(size_t)e * V + v] = acc;
+    }
     const size_t plane_stride = (size_t)E * V * Kp;
     for (int k0 = 0; k0 < Kp; k0 += 64) {
         // load a [64 t][32 v] slab coalesced along v, transpose through smem
@@ -313,13 +336,19 @@ constexpr int GEMM_THREADS = 384;  // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4
 constexpr int GEMM_EPI_WARPS = 8;
 constexpr int GEMM_MAX_STAGES = 8;
 
+__device__ __forceinline__ float lg2_ftz(float x)
+{
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 __device__ __forceinline__ float fisher_fast(float r)
 {
     // 0.5*log((1+r)/(1-r)) with the clamps of fcma_extension.cc:68-72, as 0.5*ln2*(lg2(num)-lg2(den))
     float num = 1.0f + r, den = 1.0f - r;
     num = num <= 0.f ? 1e-4f : num;
     den = den <= 0.f ? 1e-4f : den;
-    return 0.34657359027997264f * (__log2f(num) - __log2f(den));
+    return 0.34657359027997264f * (lg2_ftz(num) - lg2_ftz(den));
 }
 
 template <int KIND>
@@ -377,8 +406,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             for (long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
                 const int e = (int)(tile / tiles_per_e);
                 const long rem = tile - (long)e * tiles_per_e;
-                const int ti = (int)(rem / p.tiles_j);
-                const int tj = (int)(rem - (long)ti * p.tiles_j);
+                const int tj = (int)(rem / p.tiles_i);
+                const int ti = (int)(rem - (long)tj * p.tiles_i);
                 for (int kb = 0; kb < nkb; kb++) {
                     const int seg = kb / p.kbs;
                     const int k0 = (kb - seg * p.kbs) * p.bk;
@@ -442,8 +471,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         for (long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, iter++) {
             const int e = (int)(tile / tiles_per_e);
             const long rem = tile - (long)e * tiles_per_e;
-            const int ti = (int)(rem / p.tiles_j);
-            const int tj = (int)(rem - (long)ti * p.tiles_j);
+            const int tj = (int)(rem / p.tiles_i);
+            const int ti = (int)(rem - (long)tj * p.tiles_i);
             const int as = (int)(iter & 1);
             const uint32_t aphase = (uint32_t)((iter >> 1) & 1);
             mbar_wait(&tfull_bar[as], aphase);
@@ -462,13 +491,30 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                 tmem_ld32(taddr, v);
                 tmem_ld_wait();
                 if (jok) {
+                    float *ptr = obase + (size_t)ic * p.stride_i;
+                    if (ic + 32 <= p.nb) {  // warp-uniform: full chunk, no per-row predicates
+                        if (do_fisher) {
 #pragma unroll
-                    for (int r = 0; r < 32; r++) {
-                        const long i = ic + r;
-                        if (i < p.nb) {
-                            float x = __uint_as_float(v[r]);
-                            if (do_fisher) x = fisher_fast(x);
-                            obase[(size_t)i * p.stride_i] = x;
+                            for (int r = 0; r < 32; r++) {
+                                *ptr = fisher_fast(__uint_as_float(v[r]));
+                                ptr += p.stride_i;
+                            }
+                        } else {
+#pragma unroll
+                            for (int r = 0; r < 32; r++) {
+                                *ptr = __uint_as_float(v[r]);
+                                ptr += p.stride_i;
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int r = 0; r < 32; r++) {
+                            if (ic + r < p.nb) {
+                                float x = __uint_as_float(v[r]);
+                                if (do_fisher) x = fisher_fast(x);
+                                *ptr = x;
+                            }
+                            ptr += p.stride_i;
                         }
                     }
                 }
@@ -523,6 +569,19 @@ static int make_operand_map(CUtensorMap *m, const void *base, const PrecInfo &pi
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(FCMA_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
     return FCMA_OK;
+}
+
+// self-correlation fix-up: out[i][e][start+i] = exact sequential-FMA r (optionally Fisher-transformed)
+__global__ void k_self_corr_fixup(const float *__restrict__ selfdiag, int E, long V, long start, long nb, float *out,
+                                  long stride_i, long stride_e, int fisher_epochs)
+{
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nb * E) return;
+    const long i = idx / E;
+    const int e = (int)(idx - i * E);
+    float r = selfdiag[(size_t)e * V + start + i];
+    if (e < fisher_epochs) r = fisher_fast(r);
+    out[(size_t)i * stride_i + (size_t)e * stride_e + start + i] = r;
 }
 
 static int launch_corr_umma(const void *rows_op, const void *cols_op, int precision, int E, int T, long V, long V2,
@@ -584,6 +643,15 @@ static int launch_corr_umma(const void *rows_op, const void *cols_op, int precis
         k_corr_umma<1><<<(unsigned)grid, GEMM_THREADS, smem, st>>>(tm_cols, tm_rows, p);
     }
     LAUNCH_CHECK("k_corr_umma");
+    if (rows_op == cols_op && V == V2) {
+        // self-correlation: replace the diagonal by the reference-exact values kept with the operand
+        const float *sd = reinterpret_cast<const float *>(reinterpret_cast<const uint8_t *>(rows_op) +
+                                                          operand_plane_bytes(pi, precision, E, T, V));
+        long n = nb * E;
+        k_self_corr_fixup<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(sd, E, V, start, nb, out, stride_i, stride_e,
+                                                                 fisher_epochs);
+        LAUNCH_CHECK("k_self_corr_fixup");
+    }
     return FCMA_OK;
 }
 
@@ -900,9 +968,10 @@ __global__ void __launch_bounds__(256, (R == 4 ? 2 : 1))
                                 float var = s2 * (1.0f / EPS) - m * m;
                                 float inv = var <= 0.f ? 0.f : rsqrtf(var);
                                 if (valid) {
+                                    const float mi = -m * inv;
 #pragma unroll
                                     for (int b = 0; b < EPS; b++)
-                                        vals[q * EPS + b][h][u] = (vals[q * EPS + b][h][u] - m) * inv;
+                                        vals[q * EPS + b][h][u] = fmaf(vals[q * EPS + b][h][u], inv, mi);
                                 }
                             }
                     }
@@ -929,24 +998,30 @@ __global__ void __launch_bounds__(256, (R == 4 ? 2 : 1))
                             float var = s2 * (1.0f / EPS) - m * m;
                             float inv = var <= 0.f ? 0.f : rsqrtf(var);
                             if (valid) {
+                                const float mi = -m * inv;
 #pragma unroll
-                                for (int r = 0; r < R; r++) vals[r][h][u] = (vals[r][h][u] - m) * inv;
+                                for (int r = 0; r < R; r++) vals[r][h][u] = fmaf(vals[r][h][u], inv, mi);
                             }
                         }
                 }
             }
             // ---- self-correlation column mask (optional), tf32 rounding
+            if (self_col >= j0 && self_col < j0 + 32) {  // warp-uniform, one chunk per row at most
+#pragma unroll
+                for (int r = 0; r < R; r++)
+#pragma unroll
+                    for (int h = 0; h < 2; h++)
+#pragma unroll
+                        for (int u = 0; u < 4; u++)
+                            if (j0 + 16 * h + 4 * t + u == self_col) vals[r][h][u] = 0.f;
+            }
             uint32_t tv[R][2][4];
 #pragma unroll
             for (int r = 0; r < R; r++)
 #pragma unroll
                 for (int h = 0; h < 2; h++)
 #pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        float x = vals[r][h][u];
-                        if (self_col >= 0 && j0 + 16 * h + 4 * t + u == self_col) x = 0.f;
-                        tv[r][h][u] = f32_to_tf32(x);
-                    }
+                    for (int u = 0; u < 4; u++) tv[r][h][u] = f32_to_tf32(vals[r][h][u]);
             // ---- K += Z Z^T on tensor cores
 #pragma unroll
             for (int u = 0; u < 4; u++)
@@ -1098,11 +1173,12 @@ extern "C" int fcma_pack_operand(const float *epochs_dev, int E, int T, long V, 
         CUDA_TRY(cudaMemcpyAsync(d_Te, T_e, sizeof(int) * E, cudaMemcpyHostToDevice, st));
     }
     const int Kp = fcma_operand_kp(precision, T);
+    float *sd = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(packed_dev) + operand_plane_bytes(pi, precision, E, T, V));
     dim3 grid((unsigned)cdiv(V, 32), (unsigned)E);
-    if (pi.kind == 0 && pi.planes == 1) k_pack_operand<0, 1><<<grid, 256, 0, st>>>(epochs_dev, E, T, V, ld, d_Te, normalize, packed_dev, Kp);
-    if (pi.kind == 0 && pi.planes == 2) k_pack_operand<0, 2><<<grid, 256, 0, st>>>(epochs_dev, E, T, V, ld, d_Te, normalize, packed_dev, Kp);
-    if (pi.kind == 1 && pi.planes == 1) k_pack_operand<1, 1><<<grid, 256, 0, st>>>(epochs_dev, E, T, V, ld, d_Te, normalize, packed_dev, Kp);
-    if (pi.kind == 1 && pi.planes == 2) k_pack_operand<1, 2><<<grid, 256, 0, st>>>(epochs_dev, E, T, V, ld, d_Te, normalize, packed_dev, Kp);
+    if (pi.kind == 0 && pi.planes == 1) k_pack_operand<0, 1><<<grid, 256, 0, st>>>(epochs_dev, E, T, V, ld, d_Te, normalize, packed_dev, Kp, sd);
+    if (pi.kind == 0 && pi.planes == 2) k_pack_operand<0, 2><<<grid, 256, 0, st>>>(epochs_dev, E, T, V, ld, d_Te, normalize, packed_dev, Kp, sd);
+    if (pi.kind == 1 && pi.planes == 1) k_pack_operand<1, 1><<<grid, 256, 0, st>>>(epochs_dev, E, T, V, ld, d_Te, normalize, packed_dev, Kp, sd);
+    if (pi.kind == 1 && pi.planes == 2) k_pack_operand<1, 2><<<grid, 256, 0, st>>>(epochs_dev, E, T, V, ld, d_Te, normalize, packed_dev, Kp, sd);
     LAUNCH_CHECK("k_pack_operand");
     if (d_Te) CUDA_TRY(cudaFreeAsync(d_Te, st));
     return FCMA_OK;

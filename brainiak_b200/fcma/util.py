@@ -1,0 +1,34 @@
+"""``compute_correlation`` on the GPU — drop-in for ``brainiak.fcma.util`` (reference util.py:32-134)."""
+import numpy as np
+
+from .. import _lib
+from . import engine
+
+__all__ = ["compute_correlation"]
+
+
+def compute_correlation(matrix1, matrix2, return_nans=False):
+    """Pearson correlation between the rows of ``matrix1`` [r1, c] and ``matrix2`` [r2, c].
+
+    Same contract as reference util.py:63-134: inputs are cast to float32, rows are z-scored
+    (ddof=0) and divided by sqrt(c) (util.py:32-60; NaN -> 0 unless ``return_nans``), the result is
+    a C-contiguous float32 ``[r1, r2]`` array.  Raises ``ValueError('Dimension discrepancy')``.
+    """
+    import torch
+    matrix1 = np.asarray(matrix1).astype(np.float32)
+    matrix2 = np.asarray(matrix2).astype(np.float32)
+    [r1, d1] = matrix1.shape
+    [r2, d2] = matrix2.shape
+    if d1 != d2:
+        raise ValueError('Dimension discrepancy')
+    _lib.load()
+    _lib.require_device()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    m1 = torch.from_numpy(np.ascontiguousarray(matrix1)).to(dev)
+    engine.row_normalize_(m1, nan_to_zero=not return_nans)
+    if matrix2 is matrix1:
+        m2 = m1
+    else:
+        m2 = torch.from_numpy(np.ascontiguousarray(matrix2)).to(dev)
+        engine.row_normalize_(m2, nan_to_zero=not return_nans)
+    return np.ascontiguousarray(engine.gemm_nt(m1, m2).cpu().numpy())

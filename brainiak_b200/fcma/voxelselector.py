@@ -1,0 +1,312 @@
+"""Full Correlation Matrix Analysis (FCMA) — correlation-based voxel selection on B200.
+
+Drop-in for ``brainiak.fcma.voxelselector.VoxelSelector`` (reference voxelselector.py:56-516):
+same constructor arguments, same ``run(clf)`` result (``list[(voxel_id, accuracy)]`` sorted by
+accuracy, descending), same private stage methods.  The three native stages of
+``_voxel_scoring`` (voxelselector.py:467-516) run as sm_100a CUDA through libfcma_b200.so:
+
+    corr GEMM (TMA + tcgen05)  ->  Fisher-z + within-subject z-score  ->  per-voxel E x E kernel
+
+The cross validation itself (voxelselector.py:41-53, scikit-learn) stays on the host, exactly as in
+the reference.  Distribution: instead of the MPI master/worker farm (voxelselector.py:176-282) every
+rank of ``torch.distributed`` owns a contiguous slice of voxel rows (work per row is uniform); the
+per-voxel scores are gathered on ``master_rank``.  Without ``torch.distributed`` it runs on one GPU.
+"""
+import logging
+import math
+import multiprocessing
+import time
+
+import numpy as np
+import sklearn
+import sklearn.svm
+from sklearn import model_selection
+
+from .. import _lib
+from . import engine
+
+logger = logging.getLogger(__name__)
+
+__all__ = ["VoxelSelector"]
+
+
+def usable_cpu_count():
+    """Reference utils/utils.py:701-717."""
+    import os
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count()
+
+
+def _cross_validation_for_one_voxel(clf, vid, num_folds, subject_data, labels):
+    """Score classifier on data using cross validation (reference voxelselector.py:41-53)."""
+    skf = model_selection.StratifiedKFold(n_splits=num_folds, shuffle=False)
+    scores = model_selection.cross_val_score(clf, subject_data, y=labels, cv=skf, n_jobs=1)
+    return (vid, scores.mean())
+
+
+def _cv_chunk(clf, vids, num_folds, kernels, labels):
+    return [_cross_validation_for_one_voxel(clf, int(v), num_folds, kernels[k], labels)
+            for k, v in enumerate(vids)]
+
+
+def _is_precomputed_svc(clf):
+    return isinstance(clf, sklearn.svm.SVC) and clf.kernel == 'precomputed'
+
+
+def shrink_kernels_(kernels):
+    """In-place decimal shrink of every ``[E, E]`` kernel (reference voxelselector.py:409-412):
+    ``nd = len(str(int(K[i, 0, 0]))); if nd > 2: K[i] *= 10**(2 - nd)``."""
+    for i in range(kernels.shape[0]):
+        num_digits = len(str(int(kernels[i, 0, 0])))
+        if num_digits > 2:
+            proportion = 10 ** (2 - num_digits)
+            kernels[i, :, :] *= proportion
+    return kernels
+
+
+class VoxelSelector:
+    """Correlation-based voxel selection component of FCMA (B200 engine).
+
+    Parameters (positional part identical to the reference, voxelselector.py:102-110)
+    ----------
+    labels, epochs_per_subj, num_folds, raw_data, raw_data2, voxel_unit, process_num, master_rank:
+        as in ``brainiak.fcma.voxelselector.VoxelSelector``.  ``raw_data`` is a list of
+        float32 ``[epoch length, nVoxels]`` arrays, already z-scored (voxelselector.py:72-76)
+        unless ``normalize=True``.  ``voxel_unit`` keeps its meaning for the per-task stage
+        methods; ``run`` processes ``block_rows`` rows per GPU pass.
+
+    Keyword-only extensions
+    -----------------------
+    precision: 'tf32x3' (default, fp32-faithful: |dr| <= 1e-6), 'bf16x3', 'tf32', 'bf16'
+    mask_self: zero the self-correlation column (rounding noise in the reference)
+    normalize: apply the per-epoch z-score of preprocessing.py:80-84 on the GPU while packing
+    device: CUDA device (default: current / LOCAL_RANK)
+    block_rows: voxel rows per GPU pass (default: sized to free HBM)
+    """
+
+    def __init__(self, labels, epochs_per_subj, num_folds, raw_data, raw_data2=None,
+                 voxel_unit=64, process_num=4, master_rank=0, *, precision="tf32x3",
+                 mask_self=False, normalize=False, device=None, block_rows=None):
+        self.labels = labels
+        self.epochs_per_subj = epochs_per_subj
+        self.num_folds = num_folds
+        self.raw_data = raw_data
+        self.num_voxels = raw_data[0].shape[1]
+        self.raw_data2 = raw_data2
+        self.num_voxels2 = raw_data2[0].shape[1] if raw_data2 is not None else self.num_voxels
+        self.voxel_unit = voxel_unit
+        usable_cpus = usable_cpu_count()
+        if process_num is None:
+            self.process_num = usable_cpus
+        else:
+            self.process_num = np.min((process_num, usable_cpus))
+        self.use_multiprocessing = self.process_num != 0
+        self.master_rank = master_rank
+        if self.raw_data2 is not None and len(self.raw_data) != len(self.raw_data2):
+            raise ValueError('The raw data lists must have the same number '
+                             'of elements for computing the correlations '
+                             'element by element')
+        if self.num_voxels == 0 or self.num_voxels2 == 0:
+            raise ValueError('Zero processed voxels')
+        # NOTE: the reference refuses a single MPI process (voxelselector.py:137-139) because its
+        # master does no compute; here every rank computes, so one process is fine.
+        if precision not in _lib.PREC or precision == "f32simt":
+            raise ValueError("unknown precision %r" % (precision,))
+        self.precision = precision
+        self.mask_self = bool(mask_self)
+        self.normalize = bool(normalize)
+        self.device = device
+        self.block_rows = block_rows
+        self._rows_op = None
+        self._cols_op = None
+        self._work = None
+        world = self._world()
+        if self.master_rank >= world[1]:
+            logger.warning('Master rank exceeds the number of launched processes, set to 0')
+            self.master_rank = 0
+
+    # ------------------------------------------------------------------ distribution helpers
+    @staticmethod
+    def _world():
+        """(rank, world_size) of torch.distributed, or (0, 1)."""
+        try:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                return dist.get_rank(), dist.get_world_size()
+        except Exception:  # pragma: no cover
+            pass
+        return 0, 1
+
+    @staticmethod
+    def row_partition(num_voxels, world_size):
+        """Static shard: rank r owns rows [r*ceil(V/W), min(V, (r+1)*ceil(V/W)))."""
+        per = int(math.ceil(num_voxels / float(world_size)))
+        return [(min(num_voxels, r * per), max(0, min(num_voxels, (r + 1) * per) - min(num_voxels, r * per)))
+                for r in range(world_size)]
+
+    # ------------------------------------------------------------------ device state
+    def _torch_device(self):
+        import os
+        import torch
+        if self.device is not None:
+            return torch.device(self.device)
+        if torch.distributed.is_available() and torch.distributed.is_initialized() \
+                and "LOCAL_RANK" in os.environ:
+            return torch.device("cuda", int(os.environ["LOCAL_RANK"]))
+        return torch.device("cuda", torch.cuda.current_device())
+
+    def _operands(self):
+        """Upload + pack the epochs once (K-major, precision-split; HBM resident)."""
+        if self._rows_op is None:
+            _lib.load()
+            _lib.require_device()
+            dev = self._torch_device()
+            ep, T_e = engine.stack_epochs(self.raw_data, dev)
+            self._rows_op = engine.pack_epochs(ep, T_e, self.precision, self.normalize)
+            self._epochs_dev = ep if not self.normalize else None
+            if self.raw_data2 is not None:
+                ep2, T_e2 = engine.stack_epochs(self.raw_data2, dev)
+                if T_e2 != T_e:
+                    raise ValueError("raw_data and raw_data2 must have the same epoch lengths")
+                self._cols_op = engine.pack_epochs(ep2, T_e2, self.precision, self.normalize)
+            else:
+                self._cols_op = self._rows_op
+        return self._rows_op, self._cols_op
+
+    def _flags(self, fused):
+        return _lib.FLAG_MASK_SELF if (self.mask_self and self.raw_data2 is None and fused) else 0
+
+    # ------------------------------------------------------------------ public API
+    def run(self, clf):
+        """Run correlation-based voxel selection.
+
+        Returns (on ``master_rank``; ``[]`` elsewhere, as voxelselector.py:149-174) the list of
+        ``(voxel_id, accuracy)`` of all voxels in accuracy-descending order (stable: ties keep
+        voxel order, the reference's tie order depends on message arrival)."""
+        rank, world = self._world()
+        start, n = self.row_partition(self.num_voxels, world)[rank]
+        time1 = time.time()
+        local = self._score_rows(start, n, clf) if n > 0 else []
+        logger.info('rank %d scored rows [%d, %d) in %.2f s', rank, start, start + n,
+                    time.time() - time1)
+        results = self._gather(local, rank, world)
+        if rank == self.master_rank:
+            results.sort(key=lambda tup: tup[1], reverse=True)
+            return results
+        return []
+
+    def _gather(self, local, rank, world):
+        if world == 1:
+            return list(local)
+        import torch.distributed as dist
+        gathered = [None] * world if rank == self.master_rank else None
+        dist.gather_object(list(local), gathered, dst=self.master_rank)
+        if rank != self.master_rank:
+            return []
+        out = []
+        for part in gathered:      # rank order == voxel order
+            out += part
+        return out
+
+    # ------------------------------------------------------------------ the hot loop
+    def _score_rows(self, start, n, clf):
+        """GPU stages for rows [start, start+n) in HBM-sized blocks, then host CV."""
+        import torch
+        rows_op, cols_op = self._operands()
+        E = rows_op.E
+        results = []
+        if _is_precomputed_svc(clf):
+            fused = engine.fused_supported(E, self.epochs_per_subj)
+            block = self.block_rows or engine.Workspace.rows_for(E, self.num_voxels2, n, rows_op.device)
+            block = max(1, min(block, n))
+            if self._work is None or self._work.rows < block:
+                self._work = engine.Workspace(E, self.num_voxels2, block, rows_op.device)
+            for s in range(start, start + n, block):
+                nb = min(block, start + n - s)
+                t0 = time.time()
+                K = engine.voxel_kernels(rows_op, cols_op, s, nb, self.epochs_per_subj,
+                                         flags=self._flags(fused), work=self._work)
+                kernels = K.cpu().numpy()
+                t1 = time.time()
+                shrink_kernels_(kernels)
+                results += self._do_cross_validation(clf, kernels, (s, nb))
+                logger.debug('rows [%d, %d): kernels %.3f s, cv %.3f s', s, s + nb, t1 - t0,
+                             time.time() - t1)
+        else:
+            unit = max(1, min(self.voxel_unit, n))
+            for s in range(start, start + n, unit):
+                nb = min(unit, start + n - s)
+                results += self._voxel_scoring((s, nb), clf)
+        return results
+
+    # ------------------------------------------------------------------ reference stage methods
+    def _correlation_computation(self, task):
+        """a4 (voxelselector.py:284-329): corr ``[n, E, V2]`` float32 numpy for ``task = (start, n)``."""
+        rows_op, cols_op = self._operands()
+        corr = engine.corr_block(rows_op, cols_op, task[0], task[1], layout=0)
+        return corr.cpu().numpy()
+
+    def _correlation_normalization(self, corr):
+        """Within-subject normalisation (voxelselector.py:331-369 / fcma_extension.cc:52-84) on the
+        GPU; returns the normalised array like the reference's scipy path."""
+        import torch
+        _lib.load()
+        _lib.require_device()
+        c = np.ascontiguousarray(corr, dtype=np.float32)
+        if c.ndim != 3:
+            raise RuntimeError("The multi-subject correlation data structure must be 3D")
+        t = torch.from_numpy(c).to(self._torch_device())
+        engine.within_subject_norm_(t, self.epochs_per_subj)
+        out = np.nan_to_num(t.cpu().numpy())
+        if isinstance(corr, np.ndarray) and corr.dtype == np.float32 and corr.flags.c_contiguous:
+            corr[...] = out          # the reference normalises in place as well
+        return out
+
+    def _prepare_for_cross_validation(self, corr, clf):
+        """a7 (voxelselector.py:371-421): kernel matrices for SVC(kernel='precomputed'), else corr."""
+        import torch
+        if _is_precomputed_svc(clf):
+            z = torch.from_numpy(np.ascontiguousarray(corr, dtype=np.float32)).to(self._torch_device())
+            kernels = engine.kernel_matrices(z).cpu().numpy()
+            return shrink_kernels_(kernels)
+        return corr
+
+    def _do_cross_validation(self, clf, data, task):
+        """a8 (voxelselector.py:423-465): voxelwise cross validation on the host."""
+        time1 = time.time()
+        n = task[1]
+        if _is_precomputed_svc(clf) and self.use_multiprocessing and n > 1:
+            nproc = int(self.process_num)
+            chunk = max(1, int(math.ceil(n / float(nproc * 4))))
+            inlist = [(clf, np.arange(c, min(n, c + chunk)) + task[0], self.num_folds,
+                       data[c:min(n, c + chunk)], self.labels) for c in range(0, n, chunk)]
+            with multiprocessing.Pool(nproc) as pool:
+                parts = pool.starmap(_cv_chunk, inlist)
+            results = [r for part in parts for r in part]
+        else:
+            results = [_cross_validation_for_one_voxel(clf, i + task[0], self.num_folds,
+                                                       data[i, :, :], self.labels)
+                       for i in range(n)]
+        logger.debug('cross validation for %d voxels, takes %.2f s', n, time.time() - time1)
+        return results
+
+    def _voxel_scoring(self, task, clf):
+        """One task ``(start, n)`` through the 3-stage pipeline of voxelselector.py:467-516."""
+        import torch
+        time1 = time.time()
+        rows_op, cols_op = self._operands()
+        if _is_precomputed_svc(clf):
+            fused = engine.fused_supported(rows_op.E, self.epochs_per_subj)
+            K = engine.voxel_kernels(rows_op, cols_op, task[0], task[1], self.epochs_per_subj,
+                                     flags=self._flags(fused))
+            data = shrink_kernels_(K.cpu().numpy())
+        else:
+            corr = engine.corr_block(rows_op, cols_op, task[0], task[1], layout=0)
+            corr = corr.contiguous()
+            engine.within_subject_norm_(corr, self.epochs_per_subj)
+            data = corr.cpu().numpy()
+        results = self._do_cross_validation(clf, data, task)
+        logger.info('task %d takes %.2f s', int(task[0] / self.voxel_unit), time.time() - time1)
+        return results

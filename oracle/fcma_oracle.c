@@ -25,7 +25,9 @@
  * Reference: voxelselector.py:307-323 -> cython_blas.pyx:115-116
  *   sgemm('N','T', M=V2, N=nb, K=T, A=raw2[e] (ld V2), B=&raw[e][0,start] (ld V), C=&corr[0,e,0], ldc=V2*E)
  * i.e. corr[i, e, j] = sum_t raw[e][t, start+i] * raw2[e][t, j], float32 in, float32 accumulate.
- * Summation order of a BLAS is unspecified; this restatement sums t ascending.
+ * The reference's sgemm (SciPy's OpenBLAS, FMA micro-kernels) accumulates every output element as a
+ * sequential fp32 FMA chain over t; tests/test_oracle.py checks that this restatement reproduces the
+ * reference's outputs (tests/golden) BIT FOR BIT.
  * layout 0: out[nb][E][V2] (VoxelSelector); layout 1: out[E][nb][V2] (Classifier,
  * classifier.py:166-178 -> cython_blas.pyx:477-478 with ldc=V2).
  * raw / raw2: E pointers to C-contiguous [T_e][V] / [T_e][V2]; T[e] may differ per epoch
@@ -45,7 +47,7 @@ void oracle_corr_block(const float *const *raw, const float *const *raw2, const 
             for (int t = 0; t < T[e]; t++) {
                 float av = a[(size_t)t * V + start + i];
                 const float *brow = b + (size_t)t * V2;
-                for (long j = 0; j < V2; j++) dst[j] += av * brow[j];
+                for (long j = 0; j < V2; j++) dst[j] = __builtin_fmaf(av, brow[j], dst[j]);
             }
         }
     }

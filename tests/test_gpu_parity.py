@@ -1,0 +1,553 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (ctypes -> libfcma_b200.so), against
+ * the CPU oracle (oracle/, test infrastructure) on seeded inputs,
+ * golden fixtures produced by the UNMODIFIED reference (tests/golden/make_golden.py),
+ * size-independent invariants at the BASELINE.json shape (V=50 000, T=200, E=32).
+
+Stated tolerances (fp32 work, DESIGN.md "Parity"):
+  raw correlation r          |dr| <= 1e-6 (tf32x3, the default)   4e-5 (bf16x3)  1e-3 (tf32)  8e-3 (bf16)
+  Fisher-z / z-score (exact kernel)  |dz| <= 4e-6 * (1 + mean^2/var) * max(1,|z|)   [E[x^2]-mean^2 cancellation]
+  kernel matrices            max|dK| <= (5e-4 * sqrt(256 / V2) + 2e-6) * max|K|   (tf32 SYRK; 3.8e-5 at V2 = 50 000)
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+from numpy.random import RandomState
+from scipy.spatial.distance import hamming
+from scipy.stats.mstats import zscore
+from sklearn import svm
+from sklearn.linear_model import LogisticRegression
+
+from brainiak_b200 import _lib
+from brainiak_b200.fcma import engine, synthetic
+from brainiak_b200.fcma.classifier import Classifier
+from brainiak_b200.fcma.voxelselector import VoxelSelector, shrink_kernels_
+from oracle import fcma_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+R_TOL = {"tf32x3": 1e-6, "bf16x3": 4e-5, "tf32": 1e-3, "bf16": 8e-3}
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert _lib.device_count() > 0, "no sm_100 device"
+    return torch.device("cuda:0")
+
+
+def k_tol(V2):
+    return 5e-4 * math.sqrt(256.0 / max(V2, 1)) + 2e-6
+
+
+def zero_self(z, start):
+    z = z.copy()
+    for i in range(z.shape[0]):
+        z[i, :, start + i] = 0
+    return z
+
+
+def norm_tolerance(raw_r, eps):
+    """Per-element bound for the exact normaliser: the reference's var = E[x^2] - mean^2 in fp32
+    amplifies 1-ulp differences (CUDA logf vs glibc logf) by (1 + mean^2/var)."""
+    n0, E, n2 = raw_r.shape
+    S = E // eps
+    r = raw_r[:, :S * eps].astype(np.float64).reshape(n0, S, eps, n2)
+    num, den = 1 + r, 1 - r
+    num[num <= 0] = 1e-4
+    den[den <= 0] = 1e-4
+    fz = 0.5 * np.log(num / den)
+    m = fz.mean(2, keepdims=True)
+    var = np.maximum(fz.var(2, keepdims=True), 1e-30)
+    z = (fz - m) / np.sqrt(var)
+    amp = 1 + m * m / var
+    tol = 4e-6 * amp * np.maximum(1, np.abs(z))
+    full = np.full(raw_r.shape, 0.0)
+    full[:, :S * eps] = tol.reshape(n0, S * eps, n2)
+    return full
+
+
+# ------------------------------------------------------------------------------- a4
+@pytest.mark.parametrize("prec", ["tf32x3", "bf16x3", "tf32", "bf16"])
+def test_corr_block_vs_oracle(dev, prec):
+    V, V2, T, E = 300, 333, 50, 8
+    d1, d2, _ = synthetic.make_two_masks(V, V2, T, E)
+    ep1, T_e = engine.stack_epochs(d1, dev)
+    ep2, _ = engine.stack_epochs(d2, dev)
+    r1, r2 = engine.pack_epochs(ep1, T_e, prec), engine.pack_epochs(ep2, T_e, prec)
+    for (a, b, ra, rb, start, nb) in ((d1, d2, r1, r2, 33, 70), (d1, None, r1, r1, 0, 300),
+                                      (d2, d1, r2, r1, 300, 33)):
+        ref = orc.corr_block(a, b, start, nb, f64=True)
+        for layout in (0, 1):
+            got = engine.corr_block(ra, rb, start, nb, layout=layout).cpu().numpy()
+            if layout == 1:
+                got = np.transpose(got, (1, 0, 2))
+            assert got.shape == ref.shape
+            assert np.max(np.abs(got - ref)) <= R_TOL[prec]
+
+
+def test_corr_block_f32_simt_and_ragged_epochs(dev):
+    # epochs of different length (voxelselector.py:317 uses mat.shape[0] per epoch)
+    rng = RandomState(5)
+    lens = [7, 12, 9, 12]
+    raw = [synthetic.normalize_epoch(rng.randn(t, 77).astype(np.float32)) for t in lens]
+    ep, T_e = engine.stack_epochs(raw, dev)
+    assert T_e == lens and ep.shape == (4, 12, 77)
+    ref = orc.corr_block(raw, None, 5, 40, f64=True)
+    got = engine.corr_block_f32(ep, ep, 5, 40).cpu().numpy()
+    assert np.max(np.abs(got - ref)) <= 1e-6
+    op = engine.pack_epochs(ep, T_e, "tf32x3")
+    got = engine.corr_block(op, op, 5, 40).cpu().numpy()
+    assert np.max(np.abs(got - ref)) <= 1e-6
+    # normalise prologue with ragged epochs == preprocessing.py:80-84 per epoch
+    rawu = [rng.randn(t, 77).astype(np.float32) * 2 + 1 for t in lens]
+    epu, T_e = engine.stack_epochs(rawu, dev)
+    opn = engine.pack_epochs(epu, T_e, "tf32x3", normalize=True)
+    refn = orc.corr_block([orc.epoch_normalize(m) for m in rawu], None, 0, 77, f64=True)
+    assert np.max(np.abs(engine.corr_block(opn, opn, 0, 77).cpu().numpy() - refn)) <= 2e-6
+
+
+def test_corr_vs_reference_golden(dev, golden):
+    g = golden("vs_mid")
+    raw = list(g["raw"])
+    ep, T_e = engine.stack_epochs(raw, dev)
+    op = engine.pack_epochs(ep, T_e, "tf32x3")
+    s, nb = (int(x) for x in g["task"])
+    got = engine.corr_block(op, op, s, nb).cpu().numpy()
+    assert np.max(np.abs(got - g["corr_raw"])) <= 1e-6         # vs the reference's OpenBLAS sgemm
+    # the self-correlation entries are the reference's, bit for bit (exact FMA-chain diagonal)
+    ii = np.arange(nb)
+    assert np.array_equal(got[ii, :, s + ii], g["corr_raw"][ii, :, s + ii])
+    # the FFMA path accumulates like the reference's sgemm (sequential fp32 FMA over t): bit-exact
+    got32 = engine.corr_block_f32(ep, ep, s, nb).cpu().numpy()
+    assert np.array_equal(got32, g["corr_raw"])
+    d1, d2 = list(g["d1"]), list(g["d2"])
+    e1, T1 = engine.stack_epochs(d1, dev)
+    e2, _ = engine.stack_epochs(d2, dev)
+    o1, o2 = engine.pack_epochs(e1, T1, "tf32x3"), engine.pack_epochs(e2, T1, "tf32x3")
+    s2, nb2 = (int(x) for x in g["task2"])
+    got2 = engine.corr_block(o1, o2, s2, nb2).cpu().numpy()
+    assert np.max(np.abs(got2 - g["corr_raw2"])) <= 1e-6
+    assert np.array_equal(engine.corr_block_f32(e1, e2, s2, nb2).cpu().numpy(), g["corr_raw2"])
+
+
+# ------------------------------------------------------------------------------- a6
+def test_within_subject_norm_vs_reference_golden(dev, golden):
+    g = golden("vs_mid")
+    eps = int(g["eps"])
+    for raw_key, norm_key, e in (("corr_raw", "corr_norm", eps), ("corr_raw2", "corr_norm2", 4)):
+        r = g[raw_key]
+        t = torch.from_numpy(r.copy()).to(dev)
+        engine.within_subject_norm_(t, e)
+        got = t.cpu().numpy()
+        tol = norm_tolerance(r, e)
+        bad = np.abs(got.astype(np.float64) - g[norm_key]) > tol
+        # the self-correlation column (r == 1 +- ulp) is clamp noise in the reference itself
+        if raw_key == "corr_raw":
+            s = int(g["task"][0])
+            for i in range(r.shape[0]):
+                bad[i, :, s + i] = False
+        assert not bad.any(), (np.argwhere(bad)[:5], np.abs(got - g[norm_key])[bad][:5])
+        S = r.shape[1] // e
+        # trailing epochs untouched (fcma_extension.cc:52)
+        assert np.array_equal(got[:, S * e:], r[:, S * e:])
+        assert np.mean(got == g[norm_key]) > 0.7      # mostly bit-identical to the reference's C++
+    # known-answer block of the reference's own test (test_voxel_selection.py:58-65)
+    gs = golden("vs_small")
+    t = torch.from_numpy(gs["fake_corr"].copy()).to(dev)
+    engine.within_subject_norm_(t, 4)
+    assert np.allclose(t.cpu().numpy(), gs["scipy_norm"])
+    # host-buffer entry point with the reference module's signature
+    from brainiak_b200.fcma import fcma_extension
+    buf = gs["fake_corr"].copy()
+    fcma_extension.normalization(buf, 4)
+    assert np.allclose(buf, gs["cpp_norm"], atol=1e-6)
+    with pytest.raises(RuntimeError):
+        engine.within_subject_norm_(torch.zeros((4, 4), device=dev), 2)
+
+
+def test_norm_degenerate_inputs(dev):
+    # var == 0 -> 0 (fcma_extension.cc:78); r >= 1 / r <= -1 clamps (fcma_extension.cc:68-72)
+    r = np.zeros((2, 4, 6), np.float32)
+    r[0, :, 0] = 0.3                       # constant across epochs -> var 0 -> zeros
+    r[0, :, 1] = [1.0, 1.0000001, -1.0, 0.2]
+    r[1, :2, 2] = [0.5, -0.5]
+    ref = orc.within_subject_norm(r.copy(), 2)
+    t = torch.from_numpy(r.copy()).to(dev)
+    engine.within_subject_norm_(t, 2)
+    got = t.cpu().numpy()
+    assert np.all(np.isfinite(got))
+    assert np.allclose(got, ref, atol=2e-6)
+    assert np.all(got[0, :, 0] == 0)
+
+
+# ------------------------------------------------------------------------------- a7 / fused a6+a7
+@pytest.mark.parametrize("case", ["self_eps4", "two_eps8", "trailing", "generic_eps3", "wide_E48"])
+def test_kernels_and_pipeline_vs_oracle(dev, case):
+    cfg = {"self_eps4": dict(V=300, V2=None, T=50, E=8, eps=4, start=33, nb=70),
+           "two_eps8": dict(V=260, V2=333, T=40, E=16, eps=8, start=5, nb=131),
+           "trailing": dict(V=157, V2=None, T=24, E=10, eps=4, start=40, nb=37),
+           "generic_eps3": dict(V=128, V2=200, T=24, E=12, eps=3, start=0, nb=128),
+           "wide_E48": dict(V=96, V2=200, T=30, E=48, eps=16, start=0, nb=96)}[case]
+    V, V2, T, E, eps, start, nb = (cfg[k] for k in ("V", "V2", "T", "E", "eps", "start", "nb"))
+    raw, _ = synthetic.make_epochs(V, T, E, seed=4321)
+    raw2 = synthetic.make_epochs(V2, T, E, seed=99)[0] if V2 else None
+    n2 = V2 or V
+    r, z, _ = orc.voxel_block(raw, raw2, start, nb, eps, shrink=False)
+    zz = zero_self(z, start) if raw2 is None else z
+    Kref = orc.kernel_matrices(zz, f64=True)
+    scale = np.max(np.abs(Kref))
+    # a7 alone on normalised data
+    got = engine.kernel_matrices(torch.from_numpy(zz).to(dev)).cpu().numpy()
+    assert np.max(np.abs(got - Kref)) <= k_tol(n2) * scale
+    assert np.array_equal(got, np.transpose(got, (0, 2, 1)))            # mirrored triangle
+    # fused a6+a7 from raw r
+    if engine.fused_supported(E, eps):
+        got = engine.norm_kernel_matrices(torch.from_numpy(r).to(dev), eps,
+                                          self_col0=start if raw2 is None else -1).cpu().numpy()
+        assert np.max(np.abs(got - Kref)) <= k_tol(n2) * scale
+    # full pipeline a4->a6->a7 (default precision), both Fisher placements
+    ep, T_e = engine.stack_epochs(raw, dev)
+    rows = engine.pack_epochs(ep, T_e, "tf32x3")
+    cols = engine.pack_epochs(engine.stack_epochs(raw2, dev)[0], T_e, "tf32x3") if raw2 else rows
+    fused = engine.fused_supported(E, eps)
+    fl = 0
+    for fl in (0, _lib.FLAG_FISHER_IN_GEMM):
+        if raw2 is None and fused:
+            fl |= _lib.FLAG_MASK_SELF
+        got = engine.voxel_kernels(rows, cols, start, nb, eps, flags=fl).cpu().numpy()
+        if raw2 is None and not fused:
+            continue      # generic-eps path keeps the (noisy) self column: covered by two-mask cases
+        assert np.max(np.abs(got - Kref)) <= k_tol(n2) * scale
+    # small scratch buffer -> several passes give the same result
+    if fused or raw2 is not None:
+        small = engine.Workspace(E, n2, 32, dev)
+        got2 = engine.voxel_kernels(rows, cols, start, nb, eps, flags=fl, work=small).cpu().numpy()
+        assert np.max(np.abs(got2 - Kref)) <= k_tol(n2) * scale
+    # host-buffer C-ABI entry point (numpy in, numpy out)
+    if raw2 is not None:
+        Kh = engine.host_voxel_kernels(raw, raw2, start, nb, eps, "tf32x3")
+        assert np.max(np.abs(Kh - Kref)) <= k_tol(n2) * scale
+
+
+def test_pipeline_vs_reference_golden_kernels(dev, golden):
+    g = golden("vs_mid")
+    d1, d2 = list(g["d1"]), list(g["d2"])
+    e1, T1 = engine.stack_epochs(d1, dev)
+    e2, _ = engine.stack_epochs(d2, dev)
+    for prec, tol in (("tf32x3", 1.0), ("bf16x3", 1.0), ("bf16", 60.0)):
+        o1, o2 = engine.pack_epochs(e1, T1, prec), engine.pack_epochs(e2, T1, prec)
+        s2, nb2 = (int(x) for x in g["task2"])
+        K = engine.voxel_kernels(o1, o2, s2, nb2, 4).cpu().numpy()
+        shrink_kernels_(K)
+        ref = g["kernels2"]                    # reference kernels AFTER its decimal shrink
+        assert np.max(np.abs(K - ref)) <= tol * k_tol(136) * np.max(np.abs(ref))
+
+
+def test_classifier_kernel_is_sum_of_voxel_kernels(dev):
+    d1, d2, _ = synthetic.make_two_masks(90, 70, 16, 12)
+    e1, T1 = engine.stack_epochs(d1, dev)
+    e2, _ = engine.stack_epochs(d2, dev)
+    o1, o2 = engine.pack_epochs(e1, T1, "tf32x3"), engine.pack_epochs(e2, T1, "tf32x3")
+    Ksum = engine.classifier_kernel(o1, o2, 0, 90, 4).cpu().numpy()
+    Kv = engine.voxel_kernels(o1, o2, 0, 90, 4).cpu().numpy().astype(np.float64).sum(0)
+    assert np.max(np.abs(Ksum - Kv)) <= 2e-5 * np.max(np.abs(Kv))
+    Kref, _ = orc.classifier_kernel(d1, d2, 4, 32, shrink=False)
+    assert np.max(np.abs(Ksum - Kref)) <= 4 * k_tol(70 * 90) * np.max(np.abs(Kref))
+    # two calls over disjoint row ranges accumulate (beta = 1, classifier.py:334-339)
+    K2 = torch.zeros((12, 12), device=dev)
+    engine.classifier_kernel(o1, o2, 0, 40, 4, out=K2)
+    engine.classifier_kernel(o1, o2, 40, 50, 4, out=K2)
+    assert np.max(np.abs(K2.cpu().numpy() - Ksum)) <= 2e-5 * np.max(np.abs(Ksum))
+    # eps <= 1: no normalisation at all (classifier.py:204)
+    K0 = engine.classifier_kernel(o1, o2, 0, 90, 0).cpu().numpy()
+    c = orc.corr_block(d1, d2, 0, 90, layout=1).reshape(12, -1).astype(np.float64)
+    assert np.max(np.abs(K0 - c @ c.T)) <= 5e-4 * np.max(np.abs(c @ c.T))
+
+
+# ------------------------------------------------------------------------------- reference tests, ported
+def _create_epoch(prng, row=12, col=5):
+    mat = prng.rand(row, col).astype(np.float32)
+    mat = zscore(mat, axis=0, ddof=0)
+    mat = np.nan_to_num(mat)
+    return mat / math.sqrt(mat.shape[0])
+
+
+def test_voxel_selection(dev, golden):
+    """Port of reference tests/fcma/test_voxel_selection.py:39-89 (same inputs, same assertions)."""
+    prng = RandomState(1234567890)
+    fake_raw_data = [_create_epoch(prng) for i in range(8)]
+    labels = [0, 1, 0, 1, 0, 1, 0, 1]
+    vs = VoxelSelector(labels, 4, 2, fake_raw_data, voxel_unit=1, process_num=0)
+    fake_corr = prng.rand(1, 4, 5).astype(np.float32)
+    fake_corr = vs._correlation_normalization(fake_corr)
+    expected_fake_corr = [[[1.06988919, 0.51641309, -0.46790636, -1.31926763, 0.2270218],
+                           [-1.22142744, -1.39881694, -1.2979387, 1.05702305, -0.6525566],
+                           [0.89795232, 1.27406132, 0.36460185, 0.87538344, 1.5227468],
+                           [-0.74641371, -0.39165771, 1.40124381, -0.61313909, -1.0972116]]]
+    assert np.allclose(fake_corr, expected_fake_corr), \
+        'within-subject normalization does not provide correct results'
+    clf = svm.SVC(kernel='precomputed', shrinking=False, C=1, gamma='auto')
+    results = vs.run(clf)
+    output = [None] * len(results)
+    for tup in results:
+        output[tup[0]] = int(8 * tup[1])
+    assert np.allclose(output, [7, 4, 6, 4, 4], atol=1), \
+        'voxel selection via SVM does not provide correct results'
+    clf = LogisticRegression()
+    results = vs.run(clf)
+    output = [None] * len(results)
+    for tup in results:
+        output[tup[0]] = int(8 * tup[1])
+    assert np.allclose(output, [6, 3, 6, 4, 4], atol=1)
+    # stage methods keep the reference's contracts
+    corr = vs._correlation_computation((1, 3))
+    g = golden("vs_small")
+    assert corr.shape == (3, 8, 5) and np.max(np.abs(corr - g["corr_raw"][1:4])) <= 2e-6
+
+
+def test_voxel_selection_with_two_masks(dev, golden):
+    """Port of reference tests/fcma/test_voxel_selection.py:92-130."""
+    prng = RandomState(1234567890)
+    fake_raw_data1 = [_create_epoch(prng) for i in range(8)]
+    fake_raw_data2 = [_create_epoch(prng) for i in range(8)]
+    labels = [0, 1, 0, 1, 0, 1, 0, 1]
+    vs = VoxelSelector(labels, 4, 2, fake_raw_data1, raw_data2=fake_raw_data2, voxel_unit=1,
+                       process_num=0)
+    clf = svm.SVC(kernel='precomputed', shrinking=False, C=1, gamma='auto')
+    results = vs.run(clf)
+    output = [None] * len(results)
+    for tup in results:
+        output[tup[0]] = int(8 * tup[1])
+    assert np.allclose(output, [3, 3, 7, 5, 7], atol=1)
+    # no self column with two masks: exactly the accuracies the reference produced here
+    g = golden("vs_small")
+    acc = np.zeros(5)
+    for v, a in results:
+        acc[v] = a
+    assert np.array_equal(acc, g["acc2_svm"])
+    clf = LogisticRegression()
+    results = vs.run(clf)
+    output = [None] * len(results)
+    for tup in results:
+        output[tup[0]] = int(8 * tup[1])
+    assert np.allclose(output, [4, 3, 7, 4, 6], atol=1)
+
+
+def test_voxel_selection_ranking_vs_reference(dev, golden):
+    """Full run on a planted-signal case: selected voxels and accuracies vs the reference's run."""
+    g = golden("vs_mid")
+    raw = list(g["rawf"])
+    labels = [int(x) for x in g["labelsf"]]
+    clf = svm.SVC(kernel='precomputed', shrinking=False, C=1)
+    for prec in ("tf32x3", "bf16"):
+        vs = VoxelSelector(labels, int(g["epsf"]), 4, raw, voxel_unit=32, process_num=2, precision=prec)
+        res = vs.run(clf)
+        acc = np.zeros(raw[0].shape[1])
+        for v, a in res:
+            acc[v] = a
+        ref = g["accf"]
+        assert [a for _, a in res] == sorted((a for _, a in res), reverse=True)
+        # planted voxels 0..11 are the top of both rankings
+        top_ref = set(int(v) for v in np.argsort(-ref, kind="stable")[:12])
+        top_got = set(v for v, _ in res[:12])
+        assert len(top_ref & top_got) >= 11
+        # chance-level voxels may move by a few fold-samples because of the reference's self-column
+        # clamp noise; everything else is identical
+        assert np.mean(acc == ref) >= 0.75
+        assert np.max(np.abs(acc - ref)) <= 3.0 / 16 + 1e-9
+
+
+def _create_clf_epoch(prng, idx, num_voxels):
+    mat = prng.rand(12, num_voxels).astype(np.float32)
+    if idx % 2 == 0:
+        mat = np.sort(mat, axis=0)
+    mat = zscore(mat, axis=0, ddof=0)
+    mat = np.nan_to_num(mat)
+    return mat / math.sqrt(mat.shape[0])
+
+
+@pytest.mark.parametrize("two", [False, True])
+def test_classification(dev, golden, two):
+    """Port of reference tests/fcma/test_classification.py:43-217 (Hamming <= 1 assertions)."""
+    prng = RandomState(1234567890)
+    d5 = [_create_clf_epoch(prng, i, 5) for i in range(20)]
+    d6 = [_create_clf_epoch(prng, i, 6) for i in range(20)] if two else None
+    a, b = d5, (d6 if two else d5)
+    labels = [0, 1] * 10
+    if two:
+        expected_confidence = np.array([-1.23311606, 1.02440964, -0.93898336, 1.07028798,
+                                        -1.04420007, 0.97647772, -1.0498268, 1.04970111])
+        expected_output = [0, 1, 0, 1, 0, 1, 0, 1]
+    else:
+        expected_confidence = np.array([-1.18234421, 0.97403604, -1.04005679, 0.92403019,
+                                        -0.95567738, 1.11746593, -0.83275891, 0.9486868])
+        expected_output = [0, 0, 0, 1, 0, 1, 0, 1]
+    svm_clf = svm.SVC(kernel='precomputed', shrinking=False, C=1, gamma='auto')
+    clf = Classifier(svm_clf, epochs_per_subj=4)
+    clf.fit(list(zip(a[:12], b[:12])), labels[:12])
+    test = list(zip(a[12:], b[12:]))
+    conf = clf.decision_function(test)
+    assert hamming(np.sign(expected_confidence), np.sign(conf)) * 8 <= 1
+    y_pred = clf.predict(test)
+    assert hamming(y_pred, expected_output) * 8 <= 1
+    conf2 = clf.decision_function(test)          # cached test_data_ path
+    assert np.array_equal(conf, conf2)
+    y = [0, 1, 0, 1, 0, 1, 0, 1]
+    score = clf.score(test, y)
+    assert np.isclose(hamming(y_pred, y), 1 - score)
+    # against what the unmodified reference produced on the same inputs (two masks: no self column)
+    g = golden("clf")
+    tag = "two" if two else "one"
+    assert clf.num_digits_ == int(g[tag + "_num_digits"])
+    if two:
+        assert np.allclose(clf.training_data_, g["two_train_features"], atol=2e-5)
+        assert np.allclose(conf, g["two_decision"], atol=2e-3)
+        assert np.array_equal(y_pred, g["two_predict"])
+    # partial similarity matrix computation
+    clf = Classifier(svm_clf, num_processed_voxels=2, epochs_per_subj=4)
+    clf.fit(list(zip(a, b)), labels, num_training_samples=12)
+    y_pred = clf.predict()
+    assert hamming(y_pred, expected_output) * 8 <= 1
+    conf = clf.decision_function()
+    assert hamming(np.sign(expected_confidence), np.sign(conf)) * 8 <= 1
+    assert clf.training_data_ is None and clf.test_data_.shape == (8, 12)
+    if two:
+        assert np.allclose(clf.test_data_, g["two_portion_test_sim"], rtol=2e-3, atol=2e-3)
+    # logistic regression
+    clf = Classifier(LogisticRegression(), epochs_per_subj=4)
+    clf.fit(list(zip(a[:12], b[:12])), labels[:12], num_training_samples=12 if two else None)
+    y_pred = clf.predict(test)
+    assert hamming(y_pred, expected_output) * 8 <= 1
+    if two:
+        assert np.allclose(clf.decision_function(test), g["two_lr_decision"], atol=2e-3)
+
+
+def test_classifier_big_kernel_vs_reference(dev, golden):
+    g = golden("clf")
+    x1, x2 = list(g["big_x1"]), list(g["big_x2"])
+    c = Classifier(svm.SVC(kernel='precomputed'), num_processed_voxels=32, epochs_per_subj=int(g["big_eps"]))
+    c.num_voxels_, c.num_features_, c.num_samples_ = 90, 90 * 70, 12
+    K, feats = c._compute_kernel_matrix_in_portion(x1, x2)
+    assert feats is None and c.num_digits_ == int(g["big_num_digits"])
+    assert np.max(np.abs(K - g["big_kernel"])) <= 2e-5 * np.max(np.abs(g["big_kernel"]))
+
+
+def test_compute_correlation(dev, golden):
+    """Port of reference tests/fcma/test_util.py:23-54 + fixtures from the reference itself."""
+    from brainiak_b200.fcma.util import compute_correlation
+    prng = RandomState(1234567890)
+    mat1 = prng.rand(5, 10).astype(np.float32)
+    mat2 = prng.rand(6, 10).astype(np.float32)
+    corr = compute_correlation(mat1, mat1)
+    assert np.allclose(corr, np.corrcoef(mat1), atol=1e-5)
+    corr = compute_correlation(mat1, mat2)
+    mat = np.concatenate((mat1, mat2), axis=0)
+    assert np.allclose(corr, np.corrcoef(mat)[0:5, 5:], atol=1e-5)
+    assert corr.dtype == np.float32 and corr.flags.c_contiguous
+    mat1 = prng.rand(5, 10).astype(np.float32)
+    mat2 = prng.rand(6, 10).astype(np.float32)
+    mat1[0, 0] = np.nan
+    corr = compute_correlation(mat1, mat2, return_nans=False)
+    assert np.all(corr == 0, axis=1)[0]
+    assert np.sum(corr == 0) == 6
+    corr = compute_correlation(mat1, mat2, return_nans=True)
+    assert np.all(np.isnan(corr), axis=1)[0]
+    assert np.sum(np.isnan(corr)) == 6
+    with pytest.raises(ValueError, match="Dimension discrepancy"):
+        compute_correlation(mat1, mat2[:, :9])
+    g = golden("util")
+    assert np.allclose(compute_correlation(g["big1"], g["big2"]), g["cb"], atol=1e-5)
+
+
+def test_separate_epochs_vs_reference_golden_file(dev, golden):
+    """a14 against the reference's own golden file tests/fcma/data/expected_raw_data.npy."""
+    from brainiak_b200.fcma.preprocessing import separate_epochs
+    g = golden("preproc")
+    raw, labels = separate_epochs(list(g["activity"]), list(g["epochs"]))
+    assert np.array_equal(labels, [0, 1, 0, 1])            # test_preprocessing.py:29,41
+    assert len(raw) == len(g["expected_raw_data"])
+    for a, b in zip(raw, g["expected_raw_data"]):
+        assert np.allclose(a, b)
+    raw2, labels2 = separate_epochs(list(g["act2"]), list(g["ep2"]))
+    assert np.array_equal(labels2, g["labels2"])
+    for k, a in enumerate(raw2):
+        ref = g["raw2_%d" % k]
+        live = np.ones(a.shape[1], bool)
+        if 4 <= k < 8:
+            live[7] = False                    # constant voxel: exact 0 here, rounding residue in scipy
+            assert np.all(a[:, 7] == 0)
+        assert a.shape == ref.shape and np.allclose(a[:, live], ref[:, live], atol=2e-6)
+
+
+def test_cython_blas_shims(dev, golden):
+    from brainiak_b200.fcma import cython_blas as blas
+    g = golden("vs_small")
+    raw = [np.ascontiguousarray(m) for m in g["raw1"]]
+    raw2 = [np.ascontiguousarray(m) for m in g["raw2"]]
+    corr = np.zeros((3, 8, 5), np.float32)
+    for e in range(8):       # the reference's call, voxelselector.py:316-322
+        blas.compute_self_corr_for_voxel_sel('N', 'T', 5, 3, 12, 1.0, raw2[e], 5, 1, raw[e], 5, 0.0,
+                                             corr, 5 * 8, e)
+    assert np.max(np.abs(corr - g["corr_raw2"][1:4])) <= 2e-6
+    K = np.zeros((8, 8), np.float32)
+    z = g["corr_norm2"]
+    blas.compute_kernel_matrix('L', 'T', 8, 5, 1.0, z, 2, 5, 0.0, K, 8)
+    ref = z[2].astype(np.float64) @ z[2].astype(np.float64).T
+    assert np.max(np.abs(K - ref)) <= 2e-3 * np.max(np.abs(ref)) and np.array_equal(K, K.T)
+    cv = np.zeros((8, 2, 5), np.float32)
+    blas.compute_corr_vectors('N', 'T', 5, 2, 12, 1.0, raw2[3], 5, raw[3], 5, 0.0, cv, 5, 0, 3)
+    assert np.max(np.abs(cv[3] - g["corr_raw2"][0:2, 3, :])) <= 2e-6
+
+
+# ------------------------------------------------------------------------------- full-size invariants
+@pytest.mark.timeout(900)
+def test_full_size_invariants(dev):
+    """BASELINE.json shape (V=50 000, T=200, E=32, eps=8) on a block of 512 voxel rows.
+
+    Size-independent properties of the pipeline (z-scored within subject over eps epochs):
+      * r is symmetric: corr[i, e, j] == corr[j, e, i];  r_self == 1
+      * trace(K_i) == E * (V - 1)      (every (subject, column) group has sum z^2 == eps)
+      * every subject block of K_i sums to 0 along rows  (sum_b z_b == 0)
+      * permuting the TRs of every epoch changes nothing (same math, different summation order)
+      * the classifier kernel is the sum of the voxel kernels
+    """
+    V, T, E, eps, nb, start = 50000, 200, 32, 8, 512, 24960
+    g = torch.Generator(device=dev).manual_seed(1234)
+    ep = torch.randn((E, T, V), device=dev, generator=g)
+    common = torch.randn((E, T, 1), device=dev, generator=g)
+    ep[1::2, :, :500] += 0.6 * common[1::2]
+    engine.epoch_normalize_(ep)
+    op = engine.pack_epochs(ep, None, "tf32x3")
+    # symmetry of r on a diagonal block
+    blk = engine.corr_block(op, op, start, nb)[:, :, start:start + nb]
+    assert float((blk - blk.transpose(0, 2)).abs().max()) <= 1e-6
+    ar = torch.arange(nb, device=dev)
+    diag = blk[ar, :, ar]
+    assert float((diag - 1).abs().max()) <= 2e-6
+    del blk
+    work = engine.Workspace(E, V, nb, dev)
+    fl = _lib.FLAG_MASK_SELF
+    K = engine.voxel_kernels(op, op, start, nb, eps, flags=fl, work=work).double()
+    tr = torch.diagonal(K, dim1=1, dim2=2).sum(1)
+    assert float((tr / (E * (V - 1.0)) - 1).abs().max()) <= 1e-4
+    Kb = K.view(nb, E // eps, eps, E).sum(2)
+    assert float(Kb.abs().max()) <= 1e-4 * V                 # ~0 compared with diag ~ V
+    assert float((K - K.transpose(1, 2)).abs().max()) == 0.0
+    # TR permutation invariance
+    perm = torch.randperm(T, device=dev, generator=g)
+    op2 = engine.pack_epochs(ep[:, perm, :].contiguous(), None, "tf32x3")
+    K2 = engine.voxel_kernels(op2, op2, start, nb, eps, flags=fl, work=work).double()
+    assert float((K2 - K).abs().max()) <= 2e-5 * float(K.abs().max())
+    # Fisher in the GEMM epilogue == Fisher in pass 2
+    K3 = engine.voxel_kernels(op, op, start, nb, eps, flags=fl | _lib.FLAG_FISHER_IN_GEMM, work=work).double()
+    assert float((K3 - K).abs().max()) <= 2e-5 * float(K.abs().max())
+    # classifier kernel == sum of voxel kernels (no self masking on either side)
+    Kn = engine.voxel_kernels(op, op, start, nb, eps, work=work).double().sum(0)
+    Kc = engine.classifier_kernel(op, op, start, nb, eps, work=work).double()
+    assert float((Kc - Kn).abs().max()) <= 1e-5 * float(Kn.abs().max())
+    # reduced-precision modes stay within their stated tolerance of the fp32-faithful result
+    for prec, tol in (("bf16x3", 2e-5), ("bf16", 2e-3)):
+        opp = engine.pack_epochs(ep, None, prec)
+        Kp = engine.voxel_kernels(opp, opp, start, nb, eps, flags=fl, work=work).double()
+        assert float((Kp - K).abs().max()) <= tol * float(K.abs().max())

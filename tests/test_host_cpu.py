@@ -1,0 +1,134 @@
+"""CPU-side checks: the C-ABI library loads and exports what include/fcma_b200.h declares, the host
+logic behaves like the reference's, and nothing computes without a GPU (no silent fallback)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+from sklearn import svm
+from sklearn.base import clone
+from sklearn.linear_model import LogisticRegression
+
+from brainiak_b200 import _lib
+from brainiak_b200.fcma import engine, synthetic
+from brainiak_b200.fcma.classifier import Classifier
+from brainiak_b200.fcma.voxelselector import VoxelSelector, shrink_kernels_
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _have_gpu():
+    return _lib.device_count() > 0
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "fcma_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(fcma_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 20
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), "libfcma_b200.so does not export %s" % name
+    # the ctypes signature table covers the header one to one
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert _lib.load().fcma_version() >= 100
+
+
+def test_operand_geometry():
+    lib = _lib.load()
+    assert lib.fcma_operand_kp(_lib.PREC["bf16"], 200) == 208
+    assert lib.fcma_operand_kp(_lib.PREC["tf32x3"], 200) == 200
+    assert lib.fcma_operand_kp(_lib.PREC["tf32"], 12) == 16
+    assert lib.fcma_operand_planes(_lib.PREC["bf16"]) == 1
+    assert lib.fcma_operand_planes(_lib.PREC["bf16x3"]) == 2
+    assert lib.fcma_operand_bytes(_lib.PREC["tf32x3"], 32, 200, 50000) == 2 * 32 * 50000 * 200 * 4
+    assert lib.fcma_operand_bytes(_lib.PREC["bf16"], 4, 50, 1000) == 4 * 1000 * 64 * 2
+    assert lib.fcma_operand_bytes(99, 4, 50, 1000) == 0
+    assert lib.fcma_work_bytes_per_row(32, 50000) == 32 * 50016 * 4
+    assert engine.fused_supported(32, 8) and engine.fused_supported(64, 64)
+    assert not engine.fused_supported(32, 3) and not engine.fused_supported(65, 8)
+    assert not engine.fused_supported(32, 64)
+
+
+@pytest.mark.skipif(_have_gpu(), reason="checks the no-GPU behaviour")
+def test_no_silent_cpu_fallback():
+    lib = _lib.load()
+    buf = np.zeros((2, 4, 8), np.float32)
+    rc = lib.fcma_host_within_subject_norm(buf.ctypes.data_as(ctypes.c_void_p), 2, 4, 8, 2, 0)
+    assert rc == _lib.FCMA_ENODEV and "sm_100" in _lib.last_error()
+    rc = lib.fcma_within_subject_norm(None, 1, 1, 1, 1, None)
+    assert rc == _lib.FCMA_ENODEV
+    raw, labels = synthetic.make_epochs(16, 8, 4)
+    vs = VoxelSelector(labels, 2, 2, raw)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        vs.run(svm.SVC(kernel="precomputed"))
+    with pytest.raises(RuntimeError):
+        vs._correlation_normalization(np.zeros((1, 4, 16), np.float32))
+    from brainiak_b200.fcma.util import compute_correlation
+    with pytest.raises(RuntimeError):
+        compute_correlation(np.ones((2, 3), np.float32), np.ones((2, 3), np.float32))
+    clf = Classifier(svm.SVC(kernel="precomputed"), epochs_per_subj=2)
+    with pytest.raises(RuntimeError):
+        clf.fit(list(zip(raw, raw)), labels)
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(_lib.FcmaLibraryMissing):
+        _lib.load()
+
+
+def test_voxelselector_constructor_contract():
+    raw, labels = synthetic.make_epochs(8, 6, 4)
+    # voxelselector.py:130-134
+    with pytest.raises(ValueError, match="same number"):
+        VoxelSelector(labels, 2, 2, raw, raw_data2=raw[:3])
+    # voxelselector.py:135-136
+    with pytest.raises(ValueError, match="Zero processed voxels"):
+        VoxelSelector(labels, 2, 2, [np.zeros((6, 0), np.float32)] * 4)
+    with pytest.raises(ValueError):
+        VoxelSelector(labels, 2, 2, raw, precision="fp8")
+    vs = VoxelSelector(labels, 2, 2, raw, voxel_unit=3, process_num=0)
+    assert vs.num_voxels == 8 and vs.num_voxels2 == 8 and not vs.use_multiprocessing
+    assert vs.row_partition(10, 4) == [(0, 3), (3, 3), (6, 3), (9, 1)]
+    assert sum(n for _, n in vs.row_partition(50000, 8)) == 50000
+    assert vs.row_partition(3, 8)[3:] == [(3, 0)] * 5
+
+
+def test_shrink_matches_reference_rule():
+    from oracle import fcma_oracle as orc
+    rng = np.random.RandomState(0)
+    K = (rng.rand(7, 4, 4).astype(np.float32) + 0.5)
+    K *= np.array([0.3, 5, 50, 99.9, 100, 4321, 1e6], np.float32)[:, None, None]
+    K[:, 0, 0] = [0.3, 5, 50, 99.9, 100, 4321, 1e6]
+    ref = K.copy()
+    nds = [orc.shrink_(ref[i]) for i in range(7)]
+    assert nds == [1, 1, 2, 2, 3, 4, 7]
+    assert np.array_equal(shrink_kernels_(K.copy()), ref)
+
+
+def test_classifier_is_a_cloneable_estimator():
+    c = Classifier(svm.SVC(kernel="precomputed"), num_processed_voxels=7, epochs_per_subj=4)
+    p = clone(c).get_params(deep=False)
+    assert p["num_processed_voxels"] == 7 and p["epochs_per_subj"] == 4 and c.num_digits_ == 0
+    # portion mode needs num_training_samples (classifier.py:399-409), checked before any GPU work
+    raw, labels = synthetic.make_epochs(12, 6, 8)
+    c = Classifier(svm.SVC(kernel="precomputed"), num_processed_voxels=4, epochs_per_subj=4)
+    with pytest.raises(RuntimeError, match="portion by portion"):
+        c.fit(list(zip(raw, raw)), labels)
+    with pytest.raises(ValueError, match="smaller than"):
+        c.fit(list(zip(raw, raw)), labels, num_training_samples=8)
+    with pytest.raises(AssertionError):
+        Classifier(LogisticRegression()).fit(list(zip(raw, raw)), labels[:3])
+
+
+def test_host_shims_validate_like_cython_memoryviews():
+    from brainiak_b200.fcma import cython_blas, fcma_extension
+    with pytest.raises(RuntimeError, match="must be 3D"):
+        fcma_extension.normalization(np.zeros((4, 4), np.float32), 2)
+    a = np.zeros((4, 6), np.float64)
+    with pytest.raises(ValueError):
+        cython_blas.compute_self_corr_for_voxel_sel('N', 'T', 6, 2, 4, 1.0, a, 6, 0, a, 6, 0.0,
+                                                    np.zeros((2, 1, 6), np.float32), 6, 0)

@@ -192,8 +192,9 @@ def timings(big):
     ep = torch.randn((E, T, V), device=dev, generator=g)
     engine.epoch_normalize_(ep)
 
-    def timeit(fn, n=3):
-        fn()
+    def timeit(fn, n=5):
+        for _ in range(3):
+            fn()
         torch.cuda.synchronize()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
@@ -225,6 +226,9 @@ def timings(big):
 
 
 def main():
+    if "--timing-only" in sys.argv:
+        timings("--big" in sys.argv)
+        return 0
     print("lib version", _lib.load().fcma_version(), "devices", _lib.device_count(), torch.cuda.get_device_name(0))
     cases = [("self V=300 eps=4", small_case()),
              ("two masks V=260 V2=333 eps=8 E=16", small_case(V=260, V2=333, T=40, E=16, eps=8, start=5, nb=131, seed=2)),

@@ -16,6 +16,7 @@
 #include <stdarg.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -342,6 +343,15 @@ __device__ __forceinline__ float lg2_ftz(float x)
     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+// log2((1+r)/(1-r)) with the reference's clamps: Fisher-z up to the factor 0.5*ln2, which the
+// within-subject z-score that follows cancels exactly
+__device__ __forceinline__ float fisher_log2(float r)
+{
+    float num = 1.0f + r, den = 1.0f - r;
+    num = num <= 0.f ? 1e-4f : num;
+    den = den <= 0.f ? 1e-4f : den;
+    return lg2_ftz(num) - lg2_ftz(den);
+}
 __device__ __forceinline__ float fisher_fast(float r)
 {
     // 0.5*log((1+r)/(1-r)) with the clamps of fcma_extension.cc:68-72, as 0.5*ln2*(lg2(num)-lg2(den))
@@ -532,6 +542,220 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     }
 }
 
+
+// ---------------------------------------------------------------- v2: CTA pairs (cta_group::2)
+// Two CTAs of a cluster (one TPC) compute a 256 (columns j) x BN (rows i) tile: each CTA owns 128
+// columns (its TMEM lanes) and stages only HALF of the row operand; tcgen05.mma.cta_group::2 reads
+// both halves.  In the 3-product modes one stage carries {cols_hi, cols_lo, rows_hi, rows_lo} of a
+// k-block and feeds all three products, so every operand byte crosses L2->SMEM once per tile:
+// 64 KB per CTA per 12 MMAs instead of 144 KB with single-CTA tiles (the v1 kernel is L2-bound).
+struct Gemm2Params {
+    int E, Kp, bk, umma_k, kbs;
+    int segs, seg_r[3], seg_c[3], planes;
+    long V2, nb, row_start;
+    int BN;
+    int tiles_j, tiles_i;          // tiles_j counts 256-column pair tiles
+    long total_tiles;
+    float *out;
+    long stride_i, stride_e;
+    int fisher_epochs;
+    uint32_t half_bytes;           // bytes of one row-operand tile per CTA: (BN/2) * 128
+    uint32_t stage_bytes;          // planes * (16384 + half_bytes)
+    int stages;
+};
+
+template <int KIND>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+    k_corr_umma2(const __grid_constant__ CUtensorMap tm_cols, const __grid_constant__ CUtensorMap tm_rows,
+                 const Gemm2Params p)
+{
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t *tiles = smem;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)p.stages * p.stage_bytes);
+    uint64_t *full_bar = bars;                         // [stages]  used in the leader CTA only
+    uint64_t *empty_bar = bars + GEMM_MAX_STAGES;      // [stages]  one per CTA (multicast commit)
+    uint64_t *tfull_bar = bars + 2 * GEMM_MAX_STAGES;  // [2]       one per CTA (multicast commit)
+    uint64_t *tempty_bar = tfull_bar + 2;              // [2]       used in the leader CTA only
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+
+    cluster_sync_all();  // both CTAs of the pair are resident before the pair-wide TMEM allocation
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tm_cols);
+        tma_prefetch_desc(&tm_rows);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < p.stages; s++) {
+            mbar_init(&full_bar[s], 2);   // one arrive per CTA's producer; tx bytes of both CTAs
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int s = 0; s < 2; s++) {
+            mbar_init(&tfull_bar[s], 1);
+            mbar_init(&tempty_bar[s], 2 * GEMM_EPI_WARPS);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 2) {
+        tmem_alloc_2sm(tmem_slot, 512);
+        tmem_relinquish_2sm();
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const long tiles_per_e = (long)p.tiles_j * p.tiles_i;
+    const long pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+    const int halfN = p.BN >> 1;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer (both CTAs)
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (long tile = pair; tile < p.total_tiles; tile += npairs) {
+                const int e = (int)(tile / tiles_per_e);
+                const long rem = tile - (long)e * tiles_per_e;
+                const int tj = (int)(rem / p.tiles_i);
+                const int ti = (int)(rem - (long)tj * p.tiles_i);
+                const int col0 = tj * 256 + (int)rank * 128;
+                const int row0 = (int)(p.row_start + (long)ti * p.BN + (long)rank * halfN);
+                for (int kb = 0; kb < p.kbs; kb++) {
+                    const int k0 = kb * p.bk;
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    if (leader)
+                        mbar_expect_tx(&full_bar[stage], 2 * p.stage_bytes);
+                    else
+                        mbar_arrive_cluster(&full_bar[stage], 0);
+                    uint8_t *base = tiles + (size_t)stage * p.stage_bytes;
+                    for (int pl = 0; pl < p.planes; pl++)
+                        tma_load_3d_2sm(&tm_cols, &full_bar[stage], base + pl * 16384, k0, col0, pl * p.E + e);
+                    uint8_t *rbase = base + p.planes * 16384;
+                    for (int pl = 0; pl < p.planes; pl++)
+                        tma_load_3d_2sm(&tm_rows, &full_bar[stage], rbase + (size_t)pl * p.half_bytes, k0, row0,
+                                        pl * p.E + e);
+                    if (++stage == p.stages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+        if (leader) {
+            const uint32_t idesc = make_idesc(KIND, 256, (uint32_t)p.BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            long iter = 0;
+            for (long tile = pair; tile < p.total_tiles; tile += npairs, iter++) {
+                const int as = (int)(iter & 1);
+                const uint32_t aphase = (uint32_t)((iter >> 1) & 1);
+                mbar_wait(&tempty_bar[as], aphase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.BN);
+                for (int kb = 0; kb < p.kbs; kb++) {
+                    const int k0 = kb * p.bk;
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    if (lane == 0) {
+                        const uint32_t base = smem_u32(tiles + (size_t)stage * p.stage_bytes);
+                        const uint32_t rbase = base + p.planes * 16384;
+                        int rem_k = p.Kp - k0;
+                        const int nk = (rem_k < p.bk ? rem_k : p.bk) / p.umma_k;
+                        for (int sgm = 0; sgm < p.segs; sgm++) {
+                            const uint64_t dc = make_smem_desc_sw128(base + p.seg_c[sgm] * 16384);
+                            const uint64_t dr = make_smem_desc_sw128(rbase + p.seg_r[sgm] * p.half_bytes);
+                            for (int k = 0; k < nk; k++)
+                                tc_mma_2sm<KIND>(d_tmem, dc + (uint64_t)(k * 2), dr + (uint64_t)(k * 2), idesc,
+                                                 (uint32_t)((kb | sgm | k) != 0));
+                        }
+                        tc_commit_2sm(&empty_bar[stage]);
+                        if (kb == p.kbs - 1) tc_commit_2sm(&tfull_bar[as]);
+                    }
+                    __syncwarp();
+                    if (++stage == p.stages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ------------------------------------------------------------------ epilogue (both CTAs)
+        const int ew = warp - 4;
+        const int q = warp & 3;
+        const int half = ew >> 2;
+        long iter = 0;
+        for (long tile = pair; tile < p.total_tiles; tile += npairs, iter++) {
+            const int e = (int)(tile / tiles_per_e);
+            const long rem = tile - (long)e * tiles_per_e;
+            const int tj = (int)(rem / p.tiles_i);
+            const int ti = (int)(rem - (long)tj * p.tiles_i);
+            const int as = (int)(iter & 1);
+            const uint32_t aphase = (uint32_t)((iter >> 1) & 1);
+            mbar_wait(&tfull_bar[as], aphase);
+            tc_fence_after();
+            const long j = (long)tj * 256 + (long)rank * 128 + q * 32 + lane;
+            const bool jok = j < p.V2;
+            const bool do_fisher = e < p.fisher_epochs;
+            const long i0 = (long)ti * p.BN;
+            float *obase = p.out + (size_t)e * p.stride_e + j;
+            const int nchunks = p.BN >> 5;
+            for (int c = half; c < nchunks; c += 2) {
+                const long ic = i0 + c * 32;
+                if (ic >= p.nb) break;
+                uint32_t v[32];
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.BN + c * 32);
+                tmem_ld32(taddr, v);
+                tmem_ld_wait();
+                if (jok) {
+                    float *ptr = obase + (size_t)ic * p.stride_i;
+                    if (ic + 32 <= p.nb) {
+                        if (do_fisher) {
+#pragma unroll
+                            for (int r = 0; r < 32; r++) {
+                                *ptr = fisher_fast(__uint_as_float(v[r]));
+                                ptr += p.stride_i;
+                            }
+                        } else {
+#pragma unroll
+                            for (int r = 0; r < 32; r++) {
+                                *ptr = __uint_as_float(v[r]);
+                                ptr += p.stride_i;
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int r = 0; r < 32; r++) {
+                            if (ic + r < p.nb) {
+                                float x = __uint_as_float(v[r]);
+                                if (do_fisher) x = fisher_fast(x);
+                                *ptr = x;
+                            }
+                            ptr += p.stride_i;
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(&tempty_bar[as], 0);  // accumulator slot free (leader's barrier)
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all();  // no CTA of the pair leaves while its peer may still touch its smem / TMEM
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc_2sm(tmem_base, 512);
+    }
+}
+
 // ---------------------------------------------------------------- tensor-map creation (driver entry point)
 typedef CUresult (*PFN_tmEncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                       const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
@@ -631,9 +855,41 @@ static int launch_corr_umma(const void *rows_op, const void *cols_op, int precis
     CUtensorMap tm_cols, tm_rows;
     int rc = make_operand_map(&tm_cols, cols_op, pi, E, V2, Kp, 128);
     if (rc) return rc;
+    static const bool use_v1 = getenv("FCMA_GEMM_V1") != nullptr;
+    if (!use_v1) {
+        Gemm2Params q;
+        memset(&q, 0, sizeof(q));
+        q.E = E, q.Kp = Kp, q.bk = pi.bk, q.umma_k = pi.umma_k, q.kbs = p.kbs;
+        q.segs = pi.segs, q.planes = pi.planes;
+        for (int sgm = 0; sgm < 3; sgm++) q.seg_r[sgm] = pi.seg_r[sgm], q.seg_c[sgm] = pi.seg_c[sgm];
+        q.V2 = V2, q.nb = nb, q.row_start = start, q.BN = p.BN;
+        q.tiles_j = (int)cdiv(V2, 256), q.tiles_i = p.tiles_i;
+        q.total_tiles = (long)q.tiles_j * q.tiles_i * E;
+        q.out = out, q.stride_i = stride_i, q.stride_e = stride_e, q.fisher_epochs = fisher_epochs;
+        q.half_bytes = (uint32_t)(p.BN / 2) * 128;
+        q.stage_bytes = (uint32_t)pi.planes * (16384 + q.half_bytes);
+        int st2 = (int)(budget / q.stage_bytes);
+        if (st2 > GEMM_MAX_STAGES) st2 = GEMM_MAX_STAGES;
+        if (st2 < 2) return fail(FCMA_EINVAL, "internal: not enough shared memory for 2 stages");
+        q.stages = st2;
+        const size_t smem2 = (size_t)st2 * q.stage_bytes + 1024 + 256;
+        rc = make_operand_map(&tm_rows, rows_op, pi, E, V, Kp, p.BN / 2);
+        if (rc) return rc;
+        long pairs = g_sm_count / 2;
+        if (q.total_tiles < pairs) pairs = q.total_tiles;
+        if (pi.kind == 0) {
+            CUDA_TRY(cudaFuncSetAttribute(k_corr_umma2<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+            k_corr_umma2<0><<<(unsigned)(2 * pairs), GEMM_THREADS, smem2, st>>>(tm_cols, tm_rows, q);
+        } else {
+            CUDA_TRY(cudaFuncSetAttribute(k_corr_umma2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+            k_corr_umma2<1><<<(unsigned)(2 * pairs), GEMM_THREADS, smem2, st>>>(tm_cols, tm_rows, q);
+        }
+        LAUNCH_CHECK("k_corr_umma2");
+        goto fixup;
+    }
     rc = make_operand_map(&tm_rows, rows_op, pi, E, V, Kp, p.BN);
     if (rc) return rc;
-
+    {
     long grid = p.total_tiles < g_sm_count ? p.total_tiles : g_sm_count;
     if (pi.kind == 0) {
         CUDA_TRY(cudaFuncSetAttribute(k_corr_umma<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -643,6 +899,8 @@ static int launch_corr_umma(const void *rows_op, const void *cols_op, int precis
         k_corr_umma<1><<<(unsigned)grid, GEMM_THREADS, smem, st>>>(tm_cols, tm_rows, p);
     }
     LAUNCH_CHECK("k_corr_umma");
+    }
+fixup:
     if (rows_op == cols_op && V == V2) {
         // self-correlation: replace the diagonal by the reference-exact values kept with the operand
         const float *sd = reinterpret_cast<const float *>(reinterpret_cast<const uint8_t *>(rows_op) +
@@ -899,6 +1157,8 @@ __global__ void __launch_bounds__(256, (R == 4 ? 2 : 1))
     constexpr int EP = 8 * R;
     constexpr int MT = EP / 16, NT = EP / 8;
     __shared__ float s_K[EP * EP];
+    extern __shared__ __align__(16) uint8_t dyn_smem[];
+    float4 *s_stage = reinterpret_cast<float4 *>(dyn_smem);  // VEC only: [warp][buf][r*2+h][lane]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, t = lane & 3;
     const int S_eps = EPS > 0 ? (E / EPS) * EPS : 0;  // epochs that get normalised
@@ -915,21 +1175,73 @@ __global__ void __launch_bounds__(256, (R == 4 ? 2 : 1))
 #pragma unroll
                 for (int c = 0; c < 4; c++) acc[a][b][c] = 0.f;
 
+        // VEC path: cp.async double buffering into a per-warp staging tile (8 x 16 B per lane), so the
+        // next chunk streams from HBM while this one is normalised and multiplied; zero fill covers
+        // epochs >= E and the ragged last chunk without any branch.
+        [[maybe_unused]] float4 *stage = nullptr;
+        [[maybe_unused]] const float *lane_src[R];   // row pointers of this lane, advanced chunk by chunk
+        [[maybe_unused]] uint32_t row_bytes[R];      // 16 for epochs < E, 0 (-> zero fill) otherwise
+        [[maybe_unused]] int buf = 0;
+        // issue the 2R 16-byte copies of the chunk starting at column jc into staging buffer b
+        auto prefetch = [&](long jc, int b) {
+            float4 *dst = stage + b * (2 * R * 32) + lane;
+            if (jc + 32 <= n2) {  // warp-uniform: full chunk
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    cp_async_16_zfill(dst + (r * 2 + 0) * 32, lane_src[r], row_bytes[r]);
+                    cp_async_16_zfill(dst + (r * 2 + 1) * 32, lane_src[r] + 16, row_bytes[r]);
+                }
+            } else {  // ragged last chunk: clamp the byte count per copy
+#pragma unroll
+                for (int r = 0; r < R; r++)
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        long left = (n2 - (jc + 16 * h + 4 * t)) * 4;
+                        uint32_t nbytes = left <= 0 ? 0u : (left < 16 ? (uint32_t)left : 16u);
+                        nbytes = row_bytes[r] ? nbytes : 0u;
+                        cp_async_16_zfill(dst + (r * 2 + h) * 32, nbytes ? lane_src[r] + 16 * h : Ci, nbytes);
+                    }
+            }
+#pragma unroll
+            for (int r = 0; r < R; r++) lane_src[r] += 8 * 32;  // this warp's next chunk
+        };
+        if constexpr (VEC) {
+            stage = s_stage + (size_t)warp * (2 * 2 * R * 32);
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                lane_src[r] = Ci + (size_t)(R * g + r) * ld + 4 * t + (long)warp * 32;
+                row_bytes[r] = (R * g + r < E) ? 16u : 0u;
+            }
+            if (warp < nchunks) prefetch((long)warp * 32, 0);
+            cp_async_commit();
+        }
+
         for (long ch = warp; ch < nchunks; ch += 8) {
             const long j0 = ch * 32;
             float vals[R][2][4];
-            // ---- load (fragment layout), zero outside [0,E) x [0,n2)
+            if constexpr (VEC) {
+                if (ch + 8 < nchunks) prefetch(j0 + 8 * 32, buf ^ 1);
+                cp_async_commit();
+                cp_async_wait<1>();
+                __syncwarp();
+                const float4 *cst = stage + buf * (2 * R * 32);
 #pragma unroll
-            for (int r = 0; r < R; r++) {
-                const int e = R * g + r;
+                for (int r = 0; r < R; r++)
 #pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    const long col = j0 + 16 * h + 4 * t;
-                    const float *src = Ci + (size_t)e * ld + col;
-                    if (e < E && VEC && col + 4 <= n2) {
-                        float4 q = __ldg(reinterpret_cast<const float4 *>(src));
+                    for (int h = 0; h < 2; h++) {
+                        float4 q = cst[(r * 2 + h) * 32 + lane];
                         vals[r][h][0] = q.x, vals[r][h][1] = q.y, vals[r][h][2] = q.z, vals[r][h][3] = q.w;
-                    } else {
+                    }
+                buf ^= 1;
+            } else {
+                // ---- direct loads (unaligned buffers), zero outside [0,E) x [0,n2)
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    const int e = R * g + r;
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        const long col = j0 + 16 * h + 4 * t;
+                        const float *src = Ci + (size_t)e * ld + col;
 #pragma unroll
                         for (int u = 0; u < 4; u++) vals[r][h][u] = (e < E && col + u < n2) ? __ldg(src + u) : 0.f;
                     }
@@ -944,7 +1256,7 @@ __global__ void __launch_bounds__(256, (R == 4 ? 2 : 1))
 #pragma unroll
                             for (int h = 0; h < 2; h++)
 #pragma unroll
-                                for (int u = 0; u < 4; u++) vals[r][h][u] = fisher_fast(vals[r][h][u]);
+                                for (int u = 0; u < 4; u++) vals[r][h][u] = fisher_log2(vals[r][h][u]);
                         }
                 }
                 // ---- per (subject, column) mean / variance
@@ -1083,9 +1395,13 @@ template <int R, bool FISHER, bool VEC>
 static bool dispatch_eps(int eps, dim3 grid, cudaStream_t st, const float *C, long nb, int E, long n2, long stride_i,
                          long ld, long self_col0, float beta, float *K, int sum)
 {
+    constexpr size_t smem = VEC ? (size_t)8 * 2 * 2 * R * 32 * sizeof(float4) : 0;
 #define FCMA_CASE(EPSV)                                                                                          \
     case EPSV:                                                                                                   \
-        k_norm_syrk<R, EPSV, FISHER, VEC><<<grid, 256, 0, st>>>(C, nb, E, n2, stride_i, ld, self_col0, beta, K, sum); \
+        if (smem > 48 * 1024)                                                                                    \
+            cudaFuncSetAttribute(k_norm_syrk<R, EPSV, FISHER, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                 (int)smem);                                                                     \
+        k_norm_syrk<R, EPSV, FISHER, VEC><<<grid, 256, smem, st>>>(C, nb, E, n2, stride_i, ld, self_col0, beta, K, sum); \
         return true;
     switch (eps) {
         FCMA_CASE(0)
@@ -1097,7 +1413,10 @@ static bool dispatch_eps(int eps, dim3 grid, cudaStream_t st, const float *C, lo
         FCMA_CASE(32)
     case 64:
         if constexpr (R == 8) {
-            k_norm_syrk<R, 64, FISHER, VEC><<<grid, 256, 0, st>>>(C, nb, E, n2, stride_i, ld, self_col0, beta, K, sum);
+            if (smem > 48 * 1024)
+                cudaFuncSetAttribute(k_norm_syrk<R, 64, FISHER, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)smem);
+            k_norm_syrk<R, 64, FISHER, VEC><<<grid, 256, smem, st>>>(C, nb, E, n2, stride_i, ld, self_col0, beta, K, sum);
             return true;
         }
         return false;

@@ -13,7 +13,7 @@ FCMA_OK, FCMA_EINVAL, FCMA_ECUDA, FCMA_ENODEV, FCMA_ENOMEM = 0, -1, -2, -3, -4
 
 PREC = {"bf16": 0, "tf32": 1, "bf16x3": 2, "tf32x3": 3, "fp32": 3, "f32simt": 4}
 FLAG_MASK_SELF = 1
-FLAG_FISHER_IN_GEMM = 2
+FLAG_FISHER_IN_PASS2 = 2
 
 c_void_p, c_int, c_long, c_size_t, c_float = (ctypes.c_void_p, ctypes.c_int, ctypes.c_long,
                                                ctypes.c_size_t, ctypes.c_float)

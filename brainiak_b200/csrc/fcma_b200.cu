@@ -337,6 +337,12 @@ constexpr int GEMM_THREADS = 384;  // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4
 constexpr int GEMM_EPI_WARPS = 8;
 constexpr int GEMM_MAX_STAGES = 8;
 
+__device__ __forceinline__ float rsqrt_ftz(float x)
+{
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 __device__ __forceinline__ float lg2_ftz(float x)
 {
     float y;
@@ -559,6 +565,7 @@ struct Gemm2Params {
     float *out;
     long stride_i, stride_e;
     int fisher_epochs;
+    int grp_tiles;                 // consecutive tiles a pair takes at a time (tiles_i, or 1)
     uint32_t half_bytes;           // bytes of one row-operand tile per CTA: (BN/2) * 128
     uint32_t stage_bytes;          // planes * (16384 + half_bytes)
     int stages;
@@ -610,7 +617,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
     const uint32_t tmem_base = *tmem_slot;
 
     const long tiles_per_e = (long)p.tiles_j * p.tiles_i;
+    // A pair processes whole groups of tiles_i consecutive tiles (one 256-column operand tile x all
+    // row tiles), groups round-robin over the pairs: only the first tile of a group pays DRAM latency
+    // for the column operand, and all pairs stay within ~one epoch so the row operand stays L2-hot.
     const long pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+    const long ngroups = p.total_tiles / p.grp_tiles;
     const int halfN = p.BN >> 1;
 
     if (warp == 0) {
@@ -618,7 +629,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (long tile = pair; tile < p.total_tiles; tile += npairs) {
+            for (long grp = pair; grp < ngroups; grp += npairs)
+            for (long tile = grp * p.grp_tiles; tile < (grp + 1) * p.grp_tiles; tile++) {
                 const int e = (int)(tile / tiles_per_e);
                 const long rem = tile - (long)e * tiles_per_e;
                 const int tj = (int)(rem / p.tiles_i);
@@ -653,7 +665,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
             int stage = 0;
             uint32_t phase = 0;
             long iter = 0;
-            for (long tile = pair; tile < p.total_tiles; tile += npairs, iter++) {
+            for (long grp = pair; grp < ngroups; grp += npairs)
+            for (long tile = grp * p.grp_tiles; tile < (grp + 1) * p.grp_tiles; tile++, iter++) {
                 const int as = (int)(iter & 1);
                 const uint32_t aphase = (uint32_t)((iter >> 1) & 1);
                 mbar_wait(&tempty_bar[as], aphase ^ 1);
@@ -692,7 +705,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
         const int q = warp & 3;
         const int half = ew >> 2;
         long iter = 0;
-        for (long tile = pair; tile < p.total_tiles; tile += npairs, iter++) {
+        for (long grp = pair; grp < ngroups; grp += npairs)
+        for (long tile = grp * p.grp_tiles; tile < (grp + 1) * p.grp_tiles; tile++, iter++) {
             const int e = (int)(tile / tiles_per_e);
             const long rem = tile - (long)e * tiles_per_e;
             const int tj = (int)(rem / p.tiles_i);
@@ -876,7 +890,12 @@ static int launch_corr_umma(const void *rows_op, const void *cols_op, int precis
         rc = make_operand_map(&tm_rows, rows_op, pi, E, V, Kp, p.BN / 2);
         if (rc) return rc;
         long pairs = g_sm_count / 2;
-        if (q.total_tiles < pairs) pairs = q.total_tiles;
+        {
+            const char *sched = getenv("FCMA_GEMM_SCHED");   // tuning knob: 1 = a pair takes all row tiles of a column tile
+            q.grp_tiles = (sched && sched[0] == '1') ? q.tiles_i : 1;
+        }
+        const long ngroups = q.total_tiles / q.grp_tiles;
+        if (ngroups < pairs) pairs = ngroups;
         if (pi.kind == 0) {
             CUDA_TRY(cudaFuncSetAttribute(k_corr_umma2<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
             k_corr_umma2<0><<<(unsigned)(2 * pairs), GEMM_THREADS, smem2, st>>>(tm_cols, tm_rows, q);
@@ -1278,7 +1297,7 @@ __global__ void __launch_bounds__(256, (R == 4 ? 2 : 1))
                                 }
                                 m *= (1.0f / EPS);
                                 float var = s2 * (1.0f / EPS) - m * m;
-                                float inv = var <= 0.f ? 0.f : rsqrtf(var);
+                                float inv = var <= 0.f ? 0.f : rsqrt_ftz(var);
                                 if (valid) {
                                     const float mi = -m * inv;
 #pragma unroll
@@ -1308,7 +1327,7 @@ __global__ void __launch_bounds__(256, (R == 4 ? 2 : 1))
                             }
                             m *= (1.0f / EPS);
                             float var = s2 * (1.0f / EPS) - m * m;
-                            float inv = var <= 0.f ? 0.f : rsqrtf(var);
+                            float inv = var <= 0.f ? 0.f : rsqrt_ftz(var);
                             if (valid) {
                                 const float mi = -m * inv;
 #pragma unroll
@@ -1628,7 +1647,7 @@ static int run_pipeline(const void *rows_op, const void *cols_op, int precision,
     const bool normalise = sum_over_rows ? eps > 1 : eps >= 1;
     const bool fused = normalise ? fused_supported(E, eps) : fused_supported(E, 0);
     const int S_eps = normalise ? (E / eps) * eps : 0;
-    const bool fisher_in_gemm = normalise && fused && (flags & FCMA_FLAG_FISHER_IN_GEMM);
+    const bool fisher_in_gemm = normalise && fused && !(flags & FCMA_FLAG_FISHER_IN_PASS2);
     const bool mask_self = (flags & FCMA_FLAG_MASK_SELF) != 0;
     if (mask_self && !(normalise && fused))
         return fail(FCMA_EINVAL, "FCMA_FLAG_MASK_SELF needs the fused normalise+kernel path (E <= 64, power-of-two eps)");

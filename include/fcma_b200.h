@@ -50,7 +50,7 @@ extern "C" {
 
 /* flags for the fused pipelines */
 #define FCMA_FLAG_MASK_SELF      1  /* zero the self-correlation column after normalisation   */
-#define FCMA_FLAG_FISHER_IN_GEMM 2  /* Fisher-z in the GEMM epilogue (default: in pass 2)     */
+#define FCMA_FLAG_FISHER_IN_PASS2 2 /* Fisher-z in the normalise kernel (default: GEMM epilogue) */
 #define FCMA_FLAG_NO_SHRINK_INFO 4  /* reserved                                               */
 
 int         fcma_version(void);
@@ -63,14 +63,15 @@ int         fcma_device_count(void);
 int    fcma_operand_kp(int precision, int T);
 /* planes of a packed operand (1 or 2) */
 int    fcma_operand_planes(int precision);
-/* bytes of a packed operand [planes][E][V][Kp] */
+/* bytes of a packed operand: [planes][E][V][Kp] (rounded up to 256 B) followed by the exact
+ * self-correlation diagonal [E][V] float32 (sequential-FMA sum of squares) */
 size_t fcma_operand_bytes(int precision, int E, int T, long V);
 
 /* epochs_dev: float32 [E][T][ld] (voxels contiguous, row pitch ld >= V; rows t >= T_e[e] must be
  * zero when T_e differs per epoch).  T_e: host array of E epoch lengths or NULL (= all T).
  * normalize: 0 = data already normalised (reference contract, voxelselector.py:72-76);
  *            1 = apply preprocessing.py:80-84 per epoch (z-score over the T_e rows, nan->0, /sqrt(T_e)).
- * Writes the K-major, precision-split operand [planes][E][V][Kp] into packed_dev. */
+ * Writes the K-major, precision-split operand [planes][E][V][Kp] (+ diagonal) into packed_dev. */
 int fcma_pack_operand(const float *epochs_dev, int E, int T, long V, long ld, const int *T_e,
                       int normalize, int precision, void *packed_dev, size_t packed_bytes,
                       void *stream);

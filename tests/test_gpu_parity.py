@@ -212,7 +212,7 @@ def test_kernels_and_pipeline_vs_oracle(dev, case):
     cols = engine.pack_epochs(engine.stack_epochs(raw2, dev)[0], T_e, "tf32x3") if raw2 else rows
     fused = engine.fused_supported(E, eps)
     fl = 0
-    for fl in (0, _lib.FLAG_FISHER_IN_GEMM):
+    for fl in (0, _lib.FLAG_FISHER_IN_PASS2):
         if raw2 is None and fused:
             fl |= _lib.FLAG_MASK_SELF
         got = engine.voxel_kernels(rows, cols, start, nb, eps, flags=fl).cpu().numpy()
@@ -540,7 +540,7 @@ def test_full_size_invariants(dev):
     K2 = engine.voxel_kernels(op2, op2, start, nb, eps, flags=fl, work=work).double()
     assert float((K2 - K).abs().max()) <= 2e-5 * float(K.abs().max())
     # Fisher in the GEMM epilogue == Fisher in pass 2
-    K3 = engine.voxel_kernels(op, op, start, nb, eps, flags=fl | _lib.FLAG_FISHER_IN_GEMM, work=work).double()
+    K3 = engine.voxel_kernels(op, op, start, nb, eps, flags=fl | _lib.FLAG_FISHER_IN_PASS2, work=work).double()
     assert float((K3 - K).abs().max()) <= 2e-5 * float(K.abs().max())
     # classifier kernel == sum of voxel kernels (no self masking on either side)
     Kn = engine.voxel_kernels(op, op, start, nb, eps, work=work).double().sum(0)

@@ -42,8 +42,10 @@ def test_operand_geometry():
     assert lib.fcma_operand_kp(_lib.PREC["tf32"], 12) == 16
     assert lib.fcma_operand_planes(_lib.PREC["bf16"]) == 1
     assert lib.fcma_operand_planes(_lib.PREC["bf16x3"]) == 2
-    assert lib.fcma_operand_bytes(_lib.PREC["tf32x3"], 32, 200, 50000) == 2 * 32 * 50000 * 200 * 4
-    assert lib.fcma_operand_bytes(_lib.PREC["bf16"], 4, 50, 1000) == 4 * 1000 * 64 * 2
+    # K-major planes (rounded up to 256 B) + the exact self-correlation diagonal [E][V] fp32
+    assert lib.fcma_operand_bytes(_lib.PREC["tf32x3"], 32, 200, 50000) == \
+        2 * 32 * 50000 * 200 * 4 + 32 * 50000 * 4
+    assert lib.fcma_operand_bytes(_lib.PREC["bf16"], 4, 50, 1000) == 4 * 1000 * 64 * 2 + 4 * 1000 * 4
     assert lib.fcma_operand_bytes(99, 4, 50, 1000) == 0
     assert lib.fcma_work_bytes_per_row(32, 50000) == 32 * 50016 * 4
     assert engine.fused_supported(32, 8) and engine.fused_supported(64, 64)

@@ -130,7 +130,7 @@ def check_pipeline(raw, raw2, c):
             zz[i, :, c["start"] + i] = 0
     Kref = orc.kernel_matrices(zz, f64=True)
     for prec, tol in (("tf32x3", 3e-4), ("bf16x3", 3e-4), ("bf16", 3e-2)):
-        for flags in (0, _lib.FLAG_FISHER_IN_GEMM):
+        for flags in (0, _lib.FLAG_FISHER_IN_PASS2):
             def pipe(prec=prec, flags=flags, tol=tol):
                 rows = engine.pack_epochs(ep, T_e, prec)
                 cols = engine.pack_epochs(ep2, T_e, prec) if raw2 is not None else rows
@@ -222,6 +222,8 @@ def timings(big):
             print("  norm+syrk (fisher in pass 2)      %8.3f ms  %6.0f GB/s read" % (ms_s, corr * 4 / ms_s / 1e6))
             ms_p = timeit(lambda: engine.voxel_kernels(rows, rows, 0, nb, eps, work=work, out=Kout))
             print("  voxel_kernels pipeline            %8.3f ms  -> %.3e corr/s" % (ms_p, corr / ms_p * 1e3), flush=True)
+            ms_p2 = timeit(lambda: engine.voxel_kernels(rows, rows, 0, nb, eps, flags=_lib.FLAG_FISHER_IN_PASS2, work=work, out=Kout))
+            print("  voxel_kernels (fisher in pass 2)   %8.3f ms  -> %.3e corr/s" % (ms_p2, corr / ms_p2 * 1e3), flush=True)
         run("timing " + prec, one)
 
 

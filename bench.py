@@ -41,7 +41,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--precision", default="tf32x3")
+    ap.add_argument("--precision", default="fp16x3")
     ap.add_argument("--voxels", type=int, default=WORKLOAD["V"], help="override V (debug only)")
     ap.add_argument("--block-rows", type=int, default=4096)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -295,9 +295,9 @@ def run_b200_arm(args):
         tg, ts, reps = 0.0, 0.0, 4
         for r in range(reps + 1):
             evs[0].record()
-            engine.corr_block(op, op, start, nbk, out=cbuf, ld=ld)
+            engine.corr_block(op, op, start, nbk, out=cbuf, ld=ld, fisher_epochs=(E // eps) * eps)
             evs[1].record()
-            engine.norm_kernel_matrices(cbuf[:, :, :V], eps, out=Kb)
+            engine.norm_kernel_matrices(cbuf[:, :, :V], eps, fisher_done=True, out=Kb)
             evs[2].record()
             torch.cuda.synchronize()
             if r > 0:
@@ -354,10 +354,12 @@ def run_b200_arm(args):
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
-                "scaling": "strong", "vs_baseline": None, "dtype": "tf32" if prec.startswith("tf32") else "bf16",
+                "scaling": "strong", "vs_baseline": None,
+                "dtype": {"fp16x3": "f16x3 (hi/lo split, f32 accumulate)", "tf32x3": "tf32x3 (hi/lo split, f32 accumulate)",
+                          "bf16x3": "bf16x3", "tf32": "tf32", "bf16": "bf16"}.get(prec, prec),
                 "data": "synthetic",
                 "config": {"workload": "FCMA VoxelSelector V=%d T=%d E=%d eps=%d (BASELINE configs[2] shape)" % (V, T, E, eps),
-                           "precision": prec + (" (3-product split, fp32-faithful: |dr| <= 1e-6)" if prec == "tf32x3" else ""),
+                           "precision": prec + (" (3-product hi/lo split, fp32-faithful: |dr| <= 1e-6)" if prec in ("tf32x3", "fp16x3") else ""),
                            "parallelism": "rows%d" % world, "rows_per_pass": block,
                            "l2": "inputs_exceed_l2 (operand %.1f GB, correlation block %.1f GB per pass)"
                                  % (lib.fcma_operand_bytes(_lib.PREC[prec], E, T, V) / 1e9,

@@ -11,7 +11,8 @@ LIB_PATH = os.path.join(_HERE, "libfcma_b200.so")
 
 FCMA_OK, FCMA_EINVAL, FCMA_ECUDA, FCMA_ENODEV, FCMA_ENOMEM = 0, -1, -2, -3, -4
 
-PREC = {"bf16": 0, "tf32": 1, "bf16x3": 2, "tf32x3": 3, "fp32": 3, "f32simt": 4}
+PREC = {"bf16": 0, "tf32": 1, "bf16x3": 2, "tf32x3": 3, "f32simt": 4, "fp16x3": 5}
+PREC_NAMES = tuple(PREC) + ("fp32",)      # "fp32" = auto-select fp16x3 / tf32x3 (engine.resolve_precision)
 FLAG_MASK_SELF = 1
 FLAG_FISHER_IN_PASS2 = 2
 

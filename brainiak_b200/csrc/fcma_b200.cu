@@ -11,6 +11,7 @@
 // No CPU fallback lives here: without an sm_100 device every compute entry point returns FCMA_ENODEV.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdarg.h>
@@ -107,7 +108,7 @@ extern "C" int fcma_device_count(void)
 // precision descriptors
 // ============================================================================================
 struct PrecInfo {
-    int kind;      // 0 bf16 (kind::f16), 1 tf32
+    int kind;      // MMA kind: 0 = kind::f16 (16-bit operands), 1 = kind::tf32
     int planes;    // stored planes (hi[, lo])
     int segs;      // product segments
     int seg_r[3];  // plane of the row operand per segment
@@ -115,15 +116,22 @@ struct PrecInfo {
     int esize;     // bytes per element
     int bk;        // K elements per 128-byte swizzle row (TMA box width)
     int umma_k;    // K per tcgen05.mma
+    int fmt;       // operand format field of the instruction descriptor: 0 f16, 1 bf16, 2 tf32
+    int pack;      // element type written by k_pack_operand: 0 bf16, 1 tf32-rounded fp32, 2 fp16 (scaled)
+    float in_scale;  // operands are stored multiplied by this power of two (fp16 range management)
 };
+// fp16 planes hold x * 2^6: |x| <= 1 for normalised epochs, so hi <= 64 and the low plane
+// (~2^-11 of hi) stays a NORMAL fp16 number down to |x| ~ 4e-3; the epilogue multiplies by 2^-12.
+#define FCMA_FP16_SCALE 64.0f
 static bool prec_info(int precision, PrecInfo *p)
 {
     switch (precision) {
-    case FCMA_PREC_BF16: *p = {0, 1, 1, {0, 0, 0}, {0, 0, 0}, 2, 64, 16}; return true;
-    case FCMA_PREC_TF32: *p = {1, 1, 1, {0, 0, 0}, {0, 0, 0}, 4, 32, 8}; return true;
+    case FCMA_PREC_BF16: *p = {0, 1, 1, {0, 0, 0}, {0, 0, 0}, 2, 64, 16, 1, 0, 1.0f}; return true;
+    case FCMA_PREC_TF32: *p = {1, 1, 1, {0, 0, 0}, {0, 0, 0}, 4, 32, 8, 2, 1, 1.0f}; return true;
     // small cross terms first, hi*hi last
-    case FCMA_PREC_BF16X3: *p = {0, 2, 3, {1, 0, 0}, {0, 1, 0}, 2, 64, 16}; return true;
-    case FCMA_PREC_TF32X3: *p = {1, 2, 3, {1, 0, 0}, {0, 1, 0}, 4, 32, 8}; return true;
+    case FCMA_PREC_BF16X3: *p = {0, 2, 3, {1, 0, 0}, {0, 1, 0}, 2, 64, 16, 1, 0, 1.0f}; return true;
+    case FCMA_PREC_TF32X3: *p = {1, 2, 3, {1, 0, 0}, {0, 1, 0}, 4, 32, 8, 2, 1, 1.0f}; return true;
+    case FCMA_PREC_FP16X3: *p = {0, 2, 3, {1, 0, 0}, {0, 1, 0}, 2, 64, 16, 0, 2, FCMA_FP16_SCALE}; return true;
     default: return false;
     }
 }
@@ -164,7 +172,7 @@ __device__ __forceinline__ float tf32_rn(float x)
 template <int KIND, int PLANES>
 __global__ void __launch_bounds__(256) k_pack_operand(const float *__restrict__ src, int E, int T, long V, long ld,
                                                       const int *__restrict__ T_e, int normalize, void *dst, int Kp,
-                                                      float *__restrict__ selfdiag)
+                                                      float *__restrict__ selfdiag, float in_scale)
 {
     __shared__ double s_red[8][33];
     __shared__ float s_mean[32], s_scale[32];
@@ -255,6 +263,12 @@ __global__ void __launch_bounds__(256) k_pack_operand(const float *__restrict__ 
                     __nv_bfloat16 hi = __float2bfloat16_rn(x);
                     d[off] = hi;
                     if constexpr (PLANES > 1) d[plane_stride + off] = __float2bfloat16_rn(x - __bfloat162float(hi));
+                } else if constexpr (KIND == 2) {
+                    __half *d = reinterpret_cast<__half *>(dst);
+                    const float xs = x * in_scale;               // exact (power of two)
+                    __half hi = __float2half_rn(xs);
+                    d[off] = hi;
+                    if constexpr (PLANES > 1) d[plane_stride + off] = __float2half_rn(xs - __half2float(hi));
                 } else {
                     float *d = reinterpret_cast<float *>(dst);
                     float hi = tf32_rn(x);
@@ -331,6 +345,8 @@ struct GemmParams {
     int fisher_epochs;
     uint32_t stage_bytes_c, stage_bytes_r;
     int stages;
+    int fmt;          // idesc operand format
+    float out_scale;  // accumulator scale applied in the epilogue (undoes operand pre-scaling)
 };
 
 constexpr int GEMM_THREADS = 384;  // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4..11 epilogue
@@ -443,7 +459,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer (one thread)
-        const uint32_t idesc = make_idesc(KIND, 128, (uint32_t)p.BN);
+        const uint32_t idesc = make_idesc(p.fmt, 128, (uint32_t)p.BN);
         int stage = 0;
         uint32_t phase = 0;
         long iter = 0;
@@ -496,6 +512,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             const long j = (long)tj * 128 + q * 32 + lane;
             const bool jok = j < p.V2;
             const bool do_fisher = e < p.fisher_epochs;
+            const float osc = p.out_scale;
             const long i0 = (long)ti * p.BN;
             float *obase = p.out + (size_t)e * p.stride_e + j;
             const int nchunks = p.BN >> 5;
@@ -512,13 +529,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                         if (do_fisher) {
 #pragma unroll
                             for (int r = 0; r < 32; r++) {
-                                *ptr = fisher_fast(__uint_as_float(v[r]));
+                                *ptr = fisher_fast(__uint_as_float(v[r]) * osc);
                                 ptr += p.stride_i;
                             }
                         } else {
 #pragma unroll
                             for (int r = 0; r < 32; r++) {
-                                *ptr = __uint_as_float(v[r]);
+                                *ptr = __uint_as_float(v[r]) * osc;
                                 ptr += p.stride_i;
                             }
                         }
@@ -526,7 +543,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 #pragma unroll
                         for (int r = 0; r < 32; r++) {
                             if (ic + r < p.nb) {
-                                float x = __uint_as_float(v[r]);
+                                float x = __uint_as_float(v[r]) * osc;
                                 if (do_fisher) x = fisher_fast(x);
                                 *ptr = x;
                             }
@@ -569,6 +586,8 @@ struct Gemm2Params {
     uint32_t half_bytes;           // bytes of one row-operand tile per CTA: (BN/2) * 128
     uint32_t stage_bytes;          // planes * (16384 + half_bytes)
     int stages;
+    int fmt;                       // idesc operand format
+    float out_scale;               // accumulator scale applied in the epilogue
 };
 
 template <int KIND>
@@ -661,7 +680,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer (leader CTA only)
         if (leader) {
-            const uint32_t idesc = make_idesc(KIND, 256, (uint32_t)p.BN);
+            const uint32_t idesc = make_idesc(p.fmt, 256, (uint32_t)p.BN);
             int stage = 0;
             uint32_t phase = 0;
             long iter = 0;
@@ -718,6 +737,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
             const long j = (long)tj * 256 + (long)rank * 128 + q * 32 + lane;
             const bool jok = j < p.V2;
             const bool do_fisher = e < p.fisher_epochs;
+            const float osc = p.out_scale;
             const long i0 = (long)ti * p.BN;
             float *obase = p.out + (size_t)e * p.stride_e + j;
             const int nchunks = p.BN >> 5;
@@ -734,13 +754,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
                         if (do_fisher) {
 #pragma unroll
                             for (int r = 0; r < 32; r++) {
-                                *ptr = fisher_fast(__uint_as_float(v[r]));
+                                *ptr = fisher_fast(__uint_as_float(v[r]) * osc);
                                 ptr += p.stride_i;
                             }
                         } else {
 #pragma unroll
                             for (int r = 0; r < 32; r++) {
-                                *ptr = __uint_as_float(v[r]);
+                                *ptr = __uint_as_float(v[r]) * osc;
                                 ptr += p.stride_i;
                             }
                         }
@@ -748,7 +768,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 #pragma unroll
                         for (int r = 0; r < 32; r++) {
                             if (ic + r < p.nb) {
-                                float x = __uint_as_float(v[r]);
+                                float x = __uint_as_float(v[r]) * osc;
                                 if (do_fisher) x = fisher_fast(x);
                                 *ptr = x;
                             }
@@ -801,7 +821,8 @@ static int make_operand_map(CUtensorMap *m, const void *base, const PrecInfo &pi
     cuuint64_t gstr[2] = {(cuuint64_t)Kp * pi.esize, (cuuint64_t)V * Kp * pi.esize};
     cuuint32_t box[3] = {(cuuint32_t)pi.bk, (cuuint32_t)box_rows, 1};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUtensorMapDataType dt = pi.kind == 0 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    CUtensorMapDataType dt = pi.pack == 0 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                             : pi.pack == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
     CUresult r = enc(m, dt, 3, const_cast<void *>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -857,6 +878,8 @@ static int launch_corr_umma(const void *rows_op, const void *cols_op, int precis
     p.stride_i = stride_i;
     p.stride_e = stride_e;
     p.fisher_epochs = fisher_epochs;
+    p.fmt = pi.fmt;
+    p.out_scale = 1.0f / (pi.in_scale * pi.in_scale);
     p.stage_bytes_c = 128 * 128;
     p.stage_bytes_r = (uint32_t)p.BN * 128;
     const size_t budget = 200 * 1024;
@@ -880,6 +903,7 @@ static int launch_corr_umma(const void *rows_op, const void *cols_op, int precis
         q.tiles_j = (int)cdiv(V2, 256), q.tiles_i = p.tiles_i;
         q.total_tiles = (long)q.tiles_j * q.tiles_i * E;
         q.out = out, q.stride_i = stride_i, q.stride_e = stride_e, q.fisher_epochs = fisher_epochs;
+        q.fmt = pi.fmt, q.out_scale = p.out_scale;
         q.half_bytes = (uint32_t)(p.BN / 2) * 128;
         q.stage_bytes = (uint32_t)pi.planes * (16384 + q.half_bytes);
         int st2 = (int)(budget / q.stage_bytes);
@@ -1513,10 +1537,11 @@ extern "C" int fcma_pack_operand(const float *epochs_dev, int E, int T, long V, 
     const int Kp = fcma_operand_kp(precision, T);
     float *sd = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(packed_dev) + operand_plane_bytes(pi, precision, E, T, V));
     dim3 grid((unsigned)cdiv(V, 32), (unsigned)E);
-    if (pi.kind == 0 && pi.planes == 1) k_pack_operand<0, 1><<<grid, 256, 0, st>>>(epochs_dev, E, T, V, ld, d_Te, normalize, packed_dev, Kp, sd);
-    if (pi.kind == 0 && pi.planes == 2) k_pack_operand<0, 2><<<grid, 256, 0, st>>>(epochs_dev, E, T, V, ld, d_Te, normalize, packed_dev, Kp, sd);
-    if (pi.kind == 1 && pi.planes == 1) k_pack_operand<1, 1><<<grid, 256, 0, st>>>(epochs_dev, E, T, V, ld, d_Te, normalize, packed_dev, Kp, sd);
-    if (pi.kind == 1 && pi.planes == 2) k_pack_operand<1, 2><<<grid, 256, 0, st>>>(epochs_dev, E, T, V, ld, d_Te, normalize, packed_dev, Kp, sd);
+    if (pi.pack == 0 && pi.planes == 1) k_pack_operand<0, 1><<<grid, 256, 0, st>>>(epochs_dev, E, T, V, ld, d_Te, normalize, packed_dev, Kp, sd, pi.in_scale);
+    if (pi.pack == 0 && pi.planes == 2) k_pack_operand<0, 2><<<grid, 256, 0, st>>>(epochs_dev, E, T, V, ld, d_Te, normalize, packed_dev, Kp, sd, pi.in_scale);
+    if (pi.pack == 1 && pi.planes == 1) k_pack_operand<1, 1><<<grid, 256, 0, st>>>(epochs_dev, E, T, V, ld, d_Te, normalize, packed_dev, Kp, sd, pi.in_scale);
+    if (pi.pack == 1 && pi.planes == 2) k_pack_operand<1, 2><<<grid, 256, 0, st>>>(epochs_dev, E, T, V, ld, d_Te, normalize, packed_dev, Kp, sd, pi.in_scale);
+    if (pi.pack == 2 && pi.planes == 2) k_pack_operand<2, 2><<<grid, 256, 0, st>>>(epochs_dev, E, T, V, ld, d_Te, normalize, packed_dev, Kp, sd, pi.in_scale);
     LAUNCH_CHECK("k_pack_operand");
     if (d_Te) CUDA_TRY(cudaFreeAsync(d_Te, st));
     return FCMA_OK;

@@ -150,9 +150,9 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr)
 // instruction descriptor for kind::f16 / kind::tf32, fp32 accumulate, both operands K-major
 //   [4,6) D format (1 = f32) | [7,10) A format | [10,13) B format (1 = bf16, 2 = tf32)
 //   [15] A major (0 = K) | [16] B major | [17,23) N >> 3 | [24,29) M >> 4
-__device__ __forceinline__ uint32_t make_idesc(int kind, uint32_t M, uint32_t N)
+__device__ __forceinline__ uint32_t make_idesc(int operand_fmt, uint32_t M, uint32_t N)
 {
-    uint32_t fmt = kind == 0 ? 1u : 2u;
+    uint32_t fmt = (uint32_t)operand_fmt;  // 0 = f16, 1 = bf16, 2 = tf32
     return (1u << 4) | (fmt << 7) | (fmt << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 

@@ -38,8 +38,9 @@ class Classifier(BaseEstimator):
     ----------
     clf, num_processed_voxels=2000, epochs_per_subj=0:
         as in the reference (classifier.py:115-123).
-    precision: str, default 'tf32x3'
-        operand precision of the correlation contraction ('tf32x3' is fp32-faithful).
+    precision: str, default 'fp32'
+        operand precision of the correlation contraction ('fp32' = fp32-faithful 3-product split,
+        see VoxelSelector).
     device: optional CUDA device
 
     Attributes (classifier.py:68-114)
@@ -47,7 +48,7 @@ class Classifier(BaseEstimator):
     training_data_, test_raw_data_, test_data_, num_voxels_, num_features_, num_samples_, num_digits_
     """
 
-    def __init__(self, clf, num_processed_voxels=2000, epochs_per_subj=0, precision="tf32x3",
+    def __init__(self, clf, num_processed_voxels=2000, epochs_per_subj=0, precision="fp32",
                  device=None):
         self.clf = clf
         self.num_processed_voxels = num_processed_voxels
@@ -64,19 +65,22 @@ class Classifier(BaseEstimator):
             return torch.device(self.device)
         return torch.device("cuda", torch.cuda.current_device())
 
-    def _pack(self, X):
+    def _pack_pair(self, X1, X2):
         _lib.load()
         _lib.require_device()
-        ep, T_e = engine.stack_epochs(list(X), self._torch_device())
-        return engine.pack_epochs(ep, T_e, self.precision)
-
-    def _pack_pair(self, X1, X2):
-        op1 = self._pack(X1)
+        dev = self._torch_device()
+        ep1, T1 = engine.stack_epochs(list(X1), dev)
+        prec = engine.resolve_precision(self.precision, ep1)
         same = len(X1) == len(X2) and all(a is b for a, b in zip(X1, X2))
-        op2 = op1 if same else self._pack(X2)
-        if op1.T_e != op2.T_e:
+        if same:
+            op1 = engine.pack_epochs(ep1, T1, prec)
+            return op1, op1
+        ep2, T2 = engine.stack_epochs(list(X2), dev)
+        if T1 != T2:
             raise AssertionError('the numbers of TRs of X1 and X2 are not identical')
-        return op1, op2
+        if engine.resolve_precision(self.precision, ep2) != prec:
+            prec = "tf32x3"
+        return engine.pack_epochs(ep1, T1, prec), engine.pack_epochs(ep2, T2, prec)
 
     # ------------------------------------------------------------------ reference stage methods
     def _prepare_corerelation_data(self, X1, X2, start_voxel=0, num_processed_voxels=None):

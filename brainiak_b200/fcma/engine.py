@@ -17,7 +17,22 @@ import torch
 
 from .. import _lib
 
-_PREC_DEFAULT = "tf32x3"
+_PREC_DEFAULT = "fp32"
+
+# "fp32" (the default of the public classes) means fp32-faithful correlations (|dr| <= 1e-6) by the
+# fastest 3-product split: fp16 hi/lo planes (pre-scaled by 2^6, bf16 tensor speed) when the data is
+# in the normalised range the reference's contract guarantees (|x| <= 1, voxelselector.py:72-76),
+# tf32 hi/lo planes (any finite fp32 range) otherwise.
+_FP16_SAFE_AMAX = 8.0
+
+
+def resolve_precision(precision, epochs=None, normalize=False):
+    if precision != "fp32":
+        return precision
+    if normalize or epochs is None:
+        return "fp16x3"
+    amax = float(epochs.abs().max())
+    return "fp16x3" if amax <= _FP16_SAFE_AMAX else "tf32x3"
 
 
 def _stream_ptr():
@@ -80,6 +95,7 @@ def pack_epochs(epochs, T_e=None, precision=_PREC_DEFAULT, normalize=False):
     if epochs.dtype != torch.float32 or not epochs.is_cuda or not epochs.is_contiguous():
         raise ValueError("epochs must be a contiguous float32 CUDA tensor [E, T, V]")
     E, T, V = epochs.shape
+    precision = resolve_precision(precision, epochs, normalize)
     code = _prec_code(precision)
     if code == _lib.PREC["f32simt"]:
         raise ValueError("f32simt works on unpacked epochs")

@@ -79,7 +79,9 @@ class VoxelSelector:
 
     Keyword-only extensions
     -----------------------
-    precision: 'tf32x3' (default, fp32-faithful: |dr| <= 1e-6), 'bf16x3', 'tf32', 'bf16'
+    precision: 'fp32' (default: fp32-faithful correlations, |dr| <= 1e-6, via the 3-product split
+        'fp16x3' for normalised data or 'tf32x3' otherwise), or explicitly 'fp16x3', 'tf32x3',
+        'bf16x3' (|dr| ~ 1e-5), 'tf32' (1e-3), 'bf16' (8e-3)
     mask_self: zero the self-correlation column (rounding noise in the reference)
     normalize: apply the per-epoch z-score of preprocessing.py:80-84 on the GPU while packing
     device: CUDA device (default: current / LOCAL_RANK)
@@ -87,7 +89,7 @@ class VoxelSelector:
     """
 
     def __init__(self, labels, epochs_per_subj, num_folds, raw_data, raw_data2=None,
-                 voxel_unit=64, process_num=4, master_rank=0, *, precision="tf32x3",
+                 voxel_unit=64, process_num=4, master_rank=0, *, precision="fp32",
                  mask_self=False, normalize=False, device=None, block_rows=None):
         self.labels = labels
         self.epochs_per_subj = epochs_per_subj
@@ -112,7 +114,7 @@ class VoxelSelector:
             raise ValueError('Zero processed voxels')
         # NOTE: the reference refuses a single MPI process (voxelselector.py:137-139) because its
         # master does no compute; here every rank computes, so one process is fine.
-        if precision not in _lib.PREC or precision == "f32simt":
+        if precision not in _lib.PREC_NAMES or precision == "f32simt":
             raise ValueError("unknown precision %r" % (precision,))
         self.precision = precision
         self.mask_self = bool(mask_self)
@@ -164,15 +166,17 @@ class VoxelSelector:
             _lib.require_device()
             dev = self._torch_device()
             ep, T_e = engine.stack_epochs(self.raw_data, dev)
-            self._rows_op = engine.pack_epochs(ep, T_e, self.precision, self.normalize)
-            self._epochs_dev = ep if not self.normalize else None
+            prec = engine.resolve_precision(self.precision, ep, self.normalize)
+            ep2 = None
             if self.raw_data2 is not None:
                 ep2, T_e2 = engine.stack_epochs(self.raw_data2, dev)
                 if T_e2 != T_e:
                     raise ValueError("raw_data and raw_data2 must have the same epoch lengths")
-                self._cols_op = engine.pack_epochs(ep2, T_e2, self.precision, self.normalize)
-            else:
-                self._cols_op = self._rows_op
+                if engine.resolve_precision(self.precision, ep2, self.normalize) != prec:
+                    prec = "tf32x3"          # one of the two masks is outside the fp16-safe range
+            self._rows_op = engine.pack_epochs(ep, T_e, prec, self.normalize)
+            self._cols_op = engine.pack_epochs(ep2, T_e, prec, self.normalize) if ep2 is not None \
+                else self._rows_op
         return self._rows_op, self._cols_op
 
     def _flags(self, fused):

@@ -47,6 +47,8 @@ extern "C" {
 #define FCMA_PREC_BF16X3   2  /* bf16 hi/lo, 3 products  : |dr| ~ 1e-6                      */
 #define FCMA_PREC_TF32X3   3  /* tf32 hi/lo, 3 products  : fp32-equivalent (|dr| ~ 1e-7)    */
 #define FCMA_PREC_F32SIMT  4  /* FFMA reference kernel on the raw fp32 epochs (no packing)  */
+#define FCMA_PREC_FP16X3   5  /* fp16 hi/lo (pre-scaled by 2^6), 3 products: fp32-equivalent for
+                                 normalised data (|x| <= 1) at bf16 tensor speed               */
 
 /* flags for the fused pipelines */
 #define FCMA_FLAG_MASK_SELF      1  /* zero the self-correlation column after normalisation   */

@@ -63,8 +63,8 @@ def check_corr(raw, raw2, c):
         out = engine.corr_block_f32(ep, ep2, c["start"], c["nb"])
         report("corr_block_f32 (SIMT)", out.cpu().numpy(), ref64, 2e-6, 1.0)
     run("corr simt", simt)
-    tols = {"bf16": 4e-3, "tf32": 4e-4, "bf16x3": 4e-6, "tf32x3": 1e-6}
-    for prec in ("bf16", "tf32", "bf16x3", "tf32x3"):
+    tols = {"bf16": 8e-3, "tf32": 1e-3, "bf16x3": 4e-5, "tf32x3": 1e-6, "fp16x3": 1e-6}
+    for prec in ("bf16", "tf32", "bf16x3", "tf32x3", "fp16x3"):
         def umma(prec=prec):
             rows = engine.pack_epochs(ep, T_e, prec)
             cols = engine.pack_epochs(ep2, T_e, prec) if raw2 is not None else rows
@@ -89,7 +89,7 @@ def check_norm_and_kernels(raw, raw2, c):
         if raw2 is None:
             for i in range(c["nb"]):
                 selfmask[i, :, c["start"] + i] = False
-        report("within_subject_norm (off-self)", got[selfmask], z[selfmask], 5e-6, 1.0)
+        report("within_subject_norm (off-self)", got[selfmask], z[selfmask], 5e-4, 1.0)
     run("norm", norm)
 
     def syrk():
@@ -129,7 +129,7 @@ def check_pipeline(raw, raw2, c):
         for i in range(c["nb"]):
             zz[i, :, c["start"] + i] = 0
     Kref = orc.kernel_matrices(zz, f64=True)
-    for prec, tol in (("tf32x3", 3e-4), ("bf16x3", 3e-4), ("bf16", 3e-2)):
+    for prec, tol in (("tf32x3", 3e-4), ("fp16x3", 3e-4), ("bf16x3", 3e-4), ("bf16", 3e-2)):
         for flags in (0, _lib.FLAG_FISHER_IN_PASS2):
             def pipe(prec=prec, flags=flags, tol=tol):
                 rows = engine.pack_epochs(ep, T_e, prec)
@@ -208,7 +208,7 @@ def timings(big):
     ld = ((V + 31) // 32) * 32
     cbuf = work.buf.view(torch.float32).view(nb, E, ld)
     Kout = torch.empty((nb, E, E), device=dev)
-    for prec in ("bf16", "bf16x3", "tf32", "tf32x3"):
+    for prec in ("bf16", "bf16x3", "fp16x3", "tf32x3"):
         def one(prec=prec):
             rows = engine.pack_epochs(ep, None, prec)
             ms_g = timeit(lambda: engine.corr_block(rows, rows, 0, nb, out=cbuf, ld=ld))

@@ -588,17 +588,21 @@ struct Gemm2Params {
     int stages;
     int fmt;                       // idesc operand format
     float out_scale;               // accumulator scale applied in the epilogue
+    int tma_store;                 // 1: epilogue stages 32x32 blocks in smem and issues TMA stores
 };
 
 template <int KIND>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
     k_corr_umma2(const __grid_constant__ CUtensorMap tm_cols, const __grid_constant__ CUtensorMap tm_rows,
-                 const Gemm2Params p)
+                 const __grid_constant__ CUtensorMap tm_out, const Gemm2Params p)
 {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t *tiles = smem;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)p.stages * p.stage_bytes);
+    // [GEMM_EPI_WARPS][32 rows i][32 cols j] fp32 staging for the TMA-store epilogue (4 KB per warp)
+    float *staging = reinterpret_cast<float *>(smem + (size_t)p.stages * p.stage_bytes);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)p.stages * p.stage_bytes +
+                                                  (p.tma_store ? GEMM_EPI_WARPS * 4096 : 0));
     uint64_t *full_bar = bars;                         // [stages]  used in the leader CTA only
     uint64_t *empty_bar = bars + GEMM_MAX_STAGES;      // [stages]  one per CTA (multicast commit)
     uint64_t *tfull_bar = bars + 2 * GEMM_MAX_STAGES;  // [2]       one per CTA (multicast commit)
@@ -748,6 +752,27 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.BN + c * 32);
                 tmem_ld32(taddr, v);
                 tmem_ld_wait();
+                if (p.tma_store) {
+                    // registers -> 32x32 smem block (row i, lane = column j: conflict-free) -> one TMA
+                    // store of box {32 j, 1 e, 32 i}; the TMA unit clips at V2 / nb and writes full lines
+                    float *blk = staging + (size_t)ew * 1024;
+                    if (lane == 0) tma_store_wait_read0();   // previous block of this warp has been read
+                    __syncwarp();
+                    if (do_fisher) {
+#pragma unroll
+                        for (int r = 0; r < 32; r++) blk[r * 32 + lane] = fisher_fast(__uint_as_float(v[r]) * osc);
+                    } else {
+#pragma unroll
+                        for (int r = 0; r < 32; r++) blk[r * 32 + lane] = __uint_as_float(v[r]) * osc;
+                    }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_3d(&tm_out, blk, (int)(j - lane), e, (int)ic);
+                        tma_store_commit();
+                    }
+                    continue;
+                }
                 if (jok) {
                     float *ptr = obase + (size_t)ic * p.stride_i;
                     if (ic + 32 <= p.nb) {
@@ -782,8 +807,264 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
             if (lane == 0) mbar_arrive_cluster(&tempty_bar[as], 0);  // accumulator slot free (leader's barrier)
         }
     }
+    if (p.tma_store && warp >= 4 && lane == 0) tma_store_wait_all();
     tc_fence_before();
     cluster_sync_all();  // no CTA of the pair leaves while its peer may still touch its smem / TMEM
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc_2sm(tmem_base, 512);
+    }
+}
+
+
+// ---------------------------------------------------------------- v3: CTA pairs + resident row operand
+// Measured (profiles/): k_corr_umma2 runs at (operand L2->SMEM reads + block writes) / ~7 TB/s, i.e. it
+// is bound by L2 throughput, not by the tensor pipe.  For the 16-bit operand modes the whole-K row
+// operand of a pair (256 rows x Kp x planes, half per CTA: <= 128 KB) fits in shared memory next to a
+// 3-stage ring for the column operand, so a pair keeps one row tile RESIDENT and sweeps a range of
+// 256-column tiles past it: operand traffic per tile halves (only the column operand streams).
+// Work unit = (epoch, column-tile range, row tile); units round-robin over the pairs with the row
+// tile index fastest, so concurrently running pairs stream the same column tiles out of L2.
+struct Gemm3Params {
+    int E, Kp, bk, umma_k, kbs;
+    int segs, seg_r[3], seg_c[3], planes;
+    long V2, nb, row_start;
+    int BN;
+    int tiles_j, tiles_i;          // 256-column tiles, BN-row tiles
+    int cj;                        // column tiles per unit
+    int nchunk;                    // ceil(tiles_j / cj)
+    long total_units;              // E * nchunk * tiles_i
+    float *out;
+    long stride_i, stride_e;
+    int fisher_epochs;
+    uint32_t half_bytes;           // (BN/2) * 128: one resident (k-block, plane) tile per CTA
+    uint32_t res_bytes;            // kbs * planes * half_bytes
+    uint32_t stage_bytes;          // planes * 16384 (column operand only)
+    int stages;
+    int fmt;
+    float out_scale;
+};
+
+template <int KIND>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+    k_corr_umma3(const __grid_constant__ CUtensorMap tm_cols, const __grid_constant__ CUtensorMap tm_rows,
+                 const Gemm3Params p)
+{
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t *resident = smem;                                   // [kbs][planes][BN/2 rows][128 B]
+    uint8_t *tiles = smem + p.res_bytes;                        // [stages][planes][128 rows][128 B]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(tiles + (size_t)p.stages * p.stage_bytes);
+    uint64_t *full_bar = bars;                         // [stages]  leader only
+    uint64_t *empty_bar = bars + GEMM_MAX_STAGES;      // [stages]  per CTA
+    uint64_t *tfull_bar = bars + 2 * GEMM_MAX_STAGES;  // [2]       per CTA
+    uint64_t *tempty_bar = tfull_bar + 2;              // [2]       leader only
+    uint64_t *rfull_bar = tempty_bar + 2;              // [1]       leader only: resident rows landed
+    uint64_t *rempty_bar = rfull_bar + 1;              // [1]       per CTA: unit's MMAs retired
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(rempty_bar + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+
+    cluster_sync_all();
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tm_cols);
+        tma_prefetch_desc(&tm_rows);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < p.stages; s++) {
+            mbar_init(&full_bar[s], 2);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int s = 0; s < 2; s++) {
+            mbar_init(&tfull_bar[s], 1);
+            mbar_init(&tempty_bar[s], 2 * GEMM_EPI_WARPS);
+        }
+        mbar_init(rfull_bar, 2);
+        mbar_init(rempty_bar, 1);
+        fence_mbar_init();
+    }
+    if (warp == 2) {
+        tmem_alloc_2sm(tmem_slot, 512);
+        tmem_relinquish_2sm();
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const long pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+    const int halfN = p.BN >> 1;
+    const long units_per_e = (long)p.nchunk * p.tiles_i;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer (both CTAs)
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0, rphase = 0;
+            for (long unit = pair; unit < p.total_units; unit += npairs) {
+                const int e = (int)(unit / units_per_e);
+                const long rem = unit - (long)e * units_per_e;
+                const int chunk = (int)(rem / p.tiles_i);
+                const int ti = (int)(rem - (long)chunk * p.tiles_i);
+                const int tj0 = chunk * p.cj;
+                const int tj1 = tj0 + p.cj < p.tiles_j ? tj0 + p.cj : p.tiles_j;
+                const int row0 = (int)(p.row_start + (long)ti * p.BN + (long)rank * halfN);
+                // resident row operand: whole K, every plane
+                mbar_wait(rempty_bar, rphase ^ 1);
+                if (leader)
+                    mbar_expect_tx(rfull_bar, 2 * p.res_bytes);
+                else
+                    mbar_arrive_cluster(rfull_bar, 0);
+                for (int kb = 0; kb < p.kbs; kb++)
+                    for (int pl = 0; pl < p.planes; pl++)
+                        tma_load_3d_2sm(&tm_rows, rfull_bar, resident + (size_t)(kb * p.planes + pl) * p.half_bytes,
+                                        kb * p.bk, row0, pl * p.E + e);
+                rphase ^= 1;
+                for (int tj = tj0; tj < tj1; tj++) {
+                    const int col0 = tj * 256 + (int)rank * 128;
+                    for (int kb = 0; kb < p.kbs; kb++) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        if (leader)
+                            mbar_expect_tx(&full_bar[stage], 2 * p.stage_bytes);
+                        else
+                            mbar_arrive_cluster(&full_bar[stage], 0);
+                        uint8_t *base = tiles + (size_t)stage * p.stage_bytes;
+                        for (int pl = 0; pl < p.planes; pl++)
+                            tma_load_3d_2sm(&tm_cols, &full_bar[stage], base + pl * 16384, kb * p.bk, col0,
+                                            pl * p.E + e);
+                        if (++stage == p.stages) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+        if (leader) {
+            const uint32_t idesc = make_idesc(p.fmt, 256, (uint32_t)p.BN);
+            const uint32_t res_addr = smem_u32(resident);
+            int stage = 0;
+            uint32_t phase = 0, rphase = 0;
+            long iter = 0;
+            for (long unit = pair; unit < p.total_units; unit += npairs) {
+                const long rem = unit % units_per_e;
+                const int chunk = (int)(rem / p.tiles_i);
+                const int tj0 = chunk * p.cj;
+                const int tj1 = tj0 + p.cj < p.tiles_j ? tj0 + p.cj : p.tiles_j;
+                mbar_wait(rfull_bar, rphase);
+                rphase ^= 1;
+                tc_fence_after();
+                for (int tj = tj0; tj < tj1; tj++, iter++) {
+                    const int as = (int)(iter & 1);
+                    const uint32_t aphase = (uint32_t)((iter >> 1) & 1);
+                    mbar_wait(&tempty_bar[as], aphase ^ 1);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.BN);
+                    for (int kb = 0; kb < p.kbs; kb++) {
+                        const int k0 = kb * p.bk;
+                        mbar_wait(&full_bar[stage], phase);
+                        tc_fence_after();
+                        if (lane == 0) {
+                            const uint32_t base = smem_u32(tiles + (size_t)stage * p.stage_bytes);
+                            const uint32_t rbase = res_addr + (uint32_t)(kb * p.planes) * p.half_bytes;
+                            int rem_k = p.Kp - k0;
+                            const int nk = (rem_k < p.bk ? rem_k : p.bk) / p.umma_k;
+                            for (int sgm = 0; sgm < p.segs; sgm++) {
+                                const uint64_t dc = make_smem_desc_sw128(base + p.seg_c[sgm] * 16384);
+                                const uint64_t dr = make_smem_desc_sw128(rbase + p.seg_r[sgm] * p.half_bytes);
+                                for (int k = 0; k < nk; k++)
+                                    tc_mma_2sm<KIND>(d_tmem, dc + (uint64_t)(k * 2), dr + (uint64_t)(k * 2), idesc,
+                                                     (uint32_t)((kb | sgm | k) != 0));
+                            }
+                            tc_commit_2sm(&empty_bar[stage]);
+                            if (kb == p.kbs - 1) {
+                                tc_commit_2sm(&tfull_bar[as]);
+                                if (tj == tj1 - 1) tc_commit_2sm(rempty_bar);  // resident tile may be replaced
+                            }
+                        }
+                        __syncwarp();
+                        if (++stage == p.stages) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ------------------------------------------------------------------ epilogue (both CTAs)
+        const int ew = warp - 4;
+        const int q = warp & 3;
+        const int half = ew >> 2;
+        long iter = 0;
+        for (long unit = pair; unit < p.total_units; unit += npairs) {
+            const int e = (int)(unit / units_per_e);
+            const long rem = unit - (long)e * units_per_e;
+            const int chunk = (int)(rem / p.tiles_i);
+            const int ti = (int)(rem - (long)chunk * p.tiles_i);
+            const int tj0 = chunk * p.cj;
+            const int tj1 = tj0 + p.cj < p.tiles_j ? tj0 + p.cj : p.tiles_j;
+            const bool do_fisher = e < p.fisher_epochs;
+            const float osc = p.out_scale;
+            const long i0 = (long)ti * p.BN;
+            const int nchunks = p.BN >> 5;
+            for (int tj = tj0; tj < tj1; tj++, iter++) {
+                const int as = (int)(iter & 1);
+                const uint32_t aphase = (uint32_t)((iter >> 1) & 1);
+                mbar_wait(&tfull_bar[as], aphase);
+                tc_fence_after();
+                const long j = (long)tj * 256 + (long)rank * 128 + q * 32 + lane;
+                const bool jok = j < p.V2;
+                float *obase = p.out + (size_t)e * p.stride_e + j;
+                for (int c = half; c < nchunks; c += 2) {
+                    const long ic = i0 + c * 32;
+                    if (ic >= p.nb) break;
+                    uint32_t v[32];
+                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.BN + c * 32);
+                    tmem_ld32(taddr, v);
+                    tmem_ld_wait();
+                    if (jok) {
+                        float *ptr = obase + (size_t)ic * p.stride_i;
+                        if (ic + 32 <= p.nb) {
+                            if (do_fisher) {
+#pragma unroll
+                                for (int r = 0; r < 32; r++) {
+                                    *ptr = fisher_fast(__uint_as_float(v[r]) * osc);
+                                    ptr += p.stride_i;
+                                }
+                            } else {
+#pragma unroll
+                                for (int r = 0; r < 32; r++) {
+                                    *ptr = __uint_as_float(v[r]) * osc;
+                                    ptr += p.stride_i;
+                                }
+                            }
+                        } else {
+#pragma unroll
+                            for (int r = 0; r < 32; r++) {
+                                if (ic + r < p.nb) {
+                                    float x = __uint_as_float(v[r]) * osc;
+                                    if (do_fisher) x = fisher_fast(x);
+                                    *ptr = x;
+                                }
+                                ptr += p.stride_i;
+                            }
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(&tempty_bar[as], 0);
+            }
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all();
     if (warp == 2) {
         tc_fence_after();
         tmem_dealloc_2sm(tmem_base, 512);
@@ -843,6 +1124,21 @@ __global__ void k_self_corr_fixup(const float *__restrict__ selfdiag, int E, lon
     out[(size_t)i * stride_i + (size_t)e * stride_e + start + i] = r;
 }
 
+// output tensor out[i*stride_i + e*stride_e + j] as a 3-D TMA tensor (j, e, i), box {32, 1, 32}, no swizzle
+static int make_out_map(CUtensorMap *m, float *out, long V2, int E, long nb, long stride_i, long stride_e)
+{
+    PFN_tmEncodeTiled enc = get_encode_fn();
+    if (!enc) return fail(FCMA_ECUDA, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t gdim[3] = {(cuuint64_t)V2, (cuuint64_t)E, (cuuint64_t)nb};
+    cuuint64_t gstr[2] = {(cuuint64_t)stride_e * 4, (cuuint64_t)stride_i * 4};
+    cuuint32_t box[3] = {32, 1, 32};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, out, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(FCMA_ECUDA, "cuTensorMapEncodeTiled(out) failed with CUresult %d", (int)r);
+    return FCMA_OK;
+}
+
 static int launch_corr_umma(const void *rows_op, const void *cols_op, int precision, int E, int T, long V, long V2,
                             long start, long nb, float *out, long stride_i, long stride_e, int fisher_epochs,
                             cudaStream_t st)
@@ -893,6 +1189,47 @@ static int launch_corr_umma(const void *rows_op, const void *cols_op, int precis
     int rc = make_operand_map(&tm_cols, cols_op, pi, E, V2, Kp, 128);
     if (rc) return rc;
     static const bool use_v1 = getenv("FCMA_GEMM_V1") != nullptr;
+    static const bool no_v3 = getenv("FCMA_GEMM_RESIDENT") == nullptr;  // opt-in: measured no faster than v2
+    if (!use_v1 && !no_v3 && pi.esize == 2) {
+        // resident-row-operand kernel: needs kbs * planes * (BN/2 * 128) bytes + >= 2 column stages
+        Gemm3Params q;
+        memset(&q, 0, sizeof(q));
+        q.E = E, q.Kp = Kp, q.bk = pi.bk, q.umma_k = pi.umma_k, q.kbs = p.kbs;
+        q.segs = pi.segs, q.planes = pi.planes;
+        for (int sgm = 0; sgm < 3; sgm++) q.seg_r[sgm] = pi.seg_r[sgm], q.seg_c[sgm] = pi.seg_c[sgm];
+        q.V2 = V2, q.nb = nb, q.row_start = start, q.BN = p.BN;
+        q.tiles_j = (int)cdiv(V2, 256), q.tiles_i = p.tiles_i;
+        q.out = out, q.stride_i = stride_i, q.stride_e = stride_e, q.fisher_epochs = fisher_epochs;
+        q.fmt = pi.fmt, q.out_scale = p.out_scale;
+        q.half_bytes = (uint32_t)(p.BN / 2) * 128;
+        q.res_bytes = (uint32_t)p.kbs * pi.planes * q.half_bytes;
+        q.stage_bytes = (uint32_t)pi.planes * 16384;
+        const size_t cap = 227 * 1024 - 1024 - 512;
+        if (q.res_bytes + 2 * (size_t)q.stage_bytes <= cap) {
+            int st3 = (int)((cap - q.res_bytes) / q.stage_bytes);
+            if (st3 > GEMM_MAX_STAGES) st3 = GEMM_MAX_STAGES;
+            q.stages = st3;
+            const size_t smem3 = (size_t)q.res_bytes + (size_t)st3 * q.stage_bytes + 1024 + 512;
+            // units: split the column tiles so that there are >= ~6 units per pair (load balance) while a
+            // resident tile is reused for >= 16 column tiles (reload overhead <= ~5 %)
+            long pairs = g_sm_count / 2;
+            long base_units = (long)E * q.tiles_i;
+            int nchunk = (int)cdiv(6 * pairs, base_units);
+            if (nchunk < 1) nchunk = 1;
+            int cj = (int)cdiv(q.tiles_j, nchunk);
+            if (cj < 16) cj = q.tiles_j < 16 ? q.tiles_j : 16;
+            q.cj = cj;
+            q.nchunk = (int)cdiv(q.tiles_j, cj);
+            q.total_units = (long)E * q.nchunk * q.tiles_i;
+            if (q.total_units < pairs) pairs = q.total_units;
+            rc = make_operand_map(&tm_rows, rows_op, pi, E, V, Kp, p.BN / 2);
+            if (rc) return rc;
+            CUDA_TRY(cudaFuncSetAttribute(k_corr_umma3<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+            k_corr_umma3<0><<<(unsigned)(2 * pairs), GEMM_THREADS, smem3, st>>>(tm_cols, tm_rows, q);
+            LAUNCH_CHECK("k_corr_umma3");
+            goto fixup;
+        }
+    }
     if (!use_v1) {
         Gemm2Params q;
         memset(&q, 0, sizeof(q));
@@ -906,11 +1243,24 @@ static int launch_corr_umma(const void *rows_op, const void *cols_op, int precis
         q.fmt = pi.fmt, q.out_scale = p.out_scale;
         q.half_bytes = (uint32_t)(p.BN / 2) * 128;
         q.stage_bytes = (uint32_t)pi.planes * (16384 + q.half_bytes);
-        int st2 = (int)(budget / q.stage_bytes);
+        // TMA-store epilogue needs 16-byte aligned rows of the output and 4 KB of staging per warp
+        static const bool no_tma_store = getenv("FCMA_GEMM_NO_TMA_STORE") != nullptr;
+        q.tma_store = (!no_tma_store && (stride_i % 4 == 0) && (stride_e % 4 == 0) && (((uintptr_t)out & 15) == 0) &&
+                       V2 < (1L << 31) && nb < (1L << 31)) ? 1 : 0;
+        const size_t staging_bytes = q.tma_store ? (size_t)GEMM_EPI_WARPS * 4096 : 0;
+        const size_t cap2 = 227 * 1024 - 1024 - 256;
+        int st2 = (int)((cap2 - staging_bytes) / q.stage_bytes);
         if (st2 > GEMM_MAX_STAGES) st2 = GEMM_MAX_STAGES;
         if (st2 < 2) return fail(FCMA_EINVAL, "internal: not enough shared memory for 2 stages");
         q.stages = st2;
-        const size_t smem2 = (size_t)st2 * q.stage_bytes + 1024 + 256;
+        const size_t smem2 = (size_t)st2 * q.stage_bytes + staging_bytes + 1024 + 256;
+        CUtensorMap tm_out;
+        if (q.tma_store) {
+            rc = make_out_map(&tm_out, out, V2, E, nb, stride_i, stride_e);
+            if (rc) return rc;
+        } else {
+            memset(&tm_out, 0, sizeof(tm_out));
+        }
         rc = make_operand_map(&tm_rows, rows_op, pi, E, V, Kp, p.BN / 2);
         if (rc) return rc;
         long pairs = g_sm_count / 2;
@@ -922,10 +1272,10 @@ static int launch_corr_umma(const void *rows_op, const void *cols_op, int precis
         if (ngroups < pairs) pairs = ngroups;
         if (pi.kind == 0) {
             CUDA_TRY(cudaFuncSetAttribute(k_corr_umma2<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-            k_corr_umma2<0><<<(unsigned)(2 * pairs), GEMM_THREADS, smem2, st>>>(tm_cols, tm_rows, q);
+            k_corr_umma2<0><<<(unsigned)(2 * pairs), GEMM_THREADS, smem2, st>>>(tm_cols, tm_rows, tm_out, q);
         } else {
             CUDA_TRY(cudaFuncSetAttribute(k_corr_umma2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-            k_corr_umma2<1><<<(unsigned)(2 * pairs), GEMM_THREADS, smem2, st>>>(tm_cols, tm_rows, q);
+            k_corr_umma2<1><<<(unsigned)(2 * pairs), GEMM_THREADS, smem2, st>>>(tm_cols, tm_rows, tm_out, q);
         }
         LAUNCH_CHECK("k_corr_umma2");
         goto fixup;

@@ -2104,6 +2104,345 @@ extern "C" int fcma_row_normalize(float *X_dev, long R, long D, long ld, int nan
     return FCMA_OK;
 }
 
+
+// ============================================================================================
+// a7 tail + a8 on the GPU: decimal shrink and batched SVM cross-validation on precomputed kernels
+// ============================================================================================
+// Decimal shrink of voxelselector.py:409-412 / classifier.py:343-347, one warp per [E][E] kernel:
+//   nd = len(str(int(K[0][0]))); if nd > 2: K *= 10**(2-nd)   (float32 multiply, like numpy)
+__global__ void __launch_bounds__(128) k_shrink_kernels(float *K, long nv, int E, int *digits_out)
+{
+    const long v = (long)blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (v >= nv) return;
+    float *Kv = K + (size_t)v * E * E;
+    const float k00 = Kv[0];
+    int nd = 1;
+    if (k00 == k00 && fabsf(k00) < 9.0e18f) {
+        long long iv = (long long)k00;  // int() truncates toward zero
+        if (iv < 0) {
+            nd = 2;                     // the '-' sign counts in len(str(.))
+            iv = -iv;
+        }
+        while (iv >= 10) {
+            iv /= 10;
+            nd++;
+        }
+    }
+    if (digits_out && lane == 0) digits_out[v] = nd;
+    if (nd > 2) {
+        const float prop = (float)pow(10.0, (double)(2 - nd));   // float32(10**(2-nd))
+        for (int idx = lane; idx < E * E; idx += 32) Kv[idx] *= prop;
+    }
+}
+
+// Batched C-SVC cross-validation on precomputed kernels: one warp per (voxel, fold).
+// The solver restates libsvm's SMO exactly as scikit-learn 1.9.0 runs it for
+// SVC(kernel='precomputed') (sklearn/svm/src/libsvm/svm.cpp: Solver::Solve :665-925,
+// select_working_set :946-1043 (WSS2, ">=" / "<=" tie-breaking = last index), calculate_rho
+// :1126-1162, float Q values, double gradient, eps = tol, TAU = 1e-12; classes grouped with the
+// smaller label first = +1 (svm_group_classes :2246-2326); prediction dec > 0 -> first class
+// :2842-2905), without the shrinking heuristic (identical result for shrinking=False, equal within
+// tol otherwise).  Lane l owns training samples l and l+32 (n_train <= 64).
+struct SvmFold {
+    int n_train, n_pos, n_test, pad;
+    int train_idx[64];        // class (+1) samples first, original order inside a class
+    int test_idx[64];
+    unsigned char test_pos[64];
+};
+
+__device__ __forceinline__ void warp_argbest(double &val, int &idx, bool want_max)
+{
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        double ov = __shfl_xor_sync(0xffffffffu, val, off);
+        int oi = __shfl_xor_sync(0xffffffffu, idx, off);
+        bool better = want_max ? (ov > val) : (ov < val);
+        if (better || (ov == val && oi > idx)) {   // ties: the later index wins (">=" / "<=" scans)
+            val = ov;
+            idx = oi;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) k_svm_cv(const float *__restrict__ K, long nv, int E, int nfolds,
+                                               const SvmFold *__restrict__ folds, double C, double eps, int max_iter,
+                                               int *__restrict__ correct, int *__restrict__ iters)
+{
+    extern __shared__ float s_q[];   // [4 warps][nmax][nmax]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long prob = (long)blockIdx.x * 4 + warp;
+    if (prob >= nv * nfolds) return;
+    const long v = prob / nfolds;
+    const int f = (int)(prob - v * nfolds);
+    const SvmFold &fd = folds[f];
+    const int n = fd.n_train;
+    const float *Kv = K + (size_t)v * E * E;
+    float *Q = s_q + (size_t)warp * 64 * 64;
+    const double INF = __longlong_as_double(0x7ff0000000000000LL);
+    const double TAU = 1e-12;
+
+    // sub-problem in libsvm's order; Q_ab = (float)(y_a y_b K_ab)
+    int idx[2];
+    double y[2], alpha[2], G[2], QD[2];
+    bool valid[2];
+#pragma unroll
+    for (int s = 0; s < 2; s++) {
+        const int k = lane + 32 * s;
+        valid[s] = k < n;
+        idx[s] = valid[s] ? fd.train_idx[k] : 0;
+        y[s] = k < fd.n_pos ? 1.0 : -1.0;
+        alpha[s] = 0.0;
+        G[s] = -1.0;   // p = -1
+    }
+    for (int a = 0; a < n; a++) {
+        const int ia = fd.train_idx[a];
+        const float ya = a < fd.n_pos ? 1.f : -1.f;
+#pragma unroll
+        for (int s = 0; s < 2; s++) {
+            const int k = lane + 32 * s;
+            if (valid[s]) Q[a * 64 + k] = ya * (float)y[s] * Kv[(size_t)ia * E + idx[s]];
+        }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int s = 0; s < 2; s++) QD[s] = valid[s] ? (double)Kv[(size_t)idx[s] * E + idx[s]] : 0.0;
+
+    int iter = 0;
+    while (true) {
+        // ---- working set selection (second order)
+        double Gmax = -INF;
+        int i = -1;
+#pragma unroll
+        for (int s = 0; s < 2; s++) {
+            if (!valid[s]) continue;
+            double cand = -INF;
+            if (y[s] > 0) {
+                if (!(alpha[s] >= C)) cand = -G[s];
+            } else {
+                if (!(alpha[s] <= 0)) cand = G[s];
+            }
+            if (cand >= Gmax && cand > -INF) {
+                Gmax = cand;
+                i = lane + 32 * s;
+            }
+        }
+        warp_argbest(Gmax, i, true);
+        if (i < 0) break;
+        const double yi = i < fd.n_pos ? 1.0 : -1.0;
+        const double QDi = __shfl_sync(0xffffffffu, (i >> 5) ? QD[1] : QD[0], i & 31);
+        double Gmax2 = -INF, obj_min = INF;
+        int j = -1;
+#pragma unroll
+        for (int s = 0; s < 2; s++) {
+            if (!valid[s]) continue;
+            const int k = lane + 32 * s;
+            const double Qik = (double)Q[i * 64 + k];
+            if (y[s] > 0) {
+                if (!(alpha[s] <= 0)) {
+                    const double gd = Gmax + G[s];
+                    if (G[s] >= Gmax2) Gmax2 = G[s];
+                    if (gd > 0) {
+                        const double quad = QDi + QD[s] - 2.0 * yi * Qik;
+                        const double obj = quad > 0 ? -(gd * gd) / quad : -(gd * gd) / TAU;
+                        if (obj <= obj_min) {
+                            j = k;
+                            obj_min = obj;
+                        }
+                    }
+                }
+            } else {
+                if (!(alpha[s] >= C)) {
+                    const double gd = Gmax - G[s];
+                    if (-G[s] >= Gmax2) Gmax2 = -G[s];
+                    if (gd > 0) {
+                        const double quad = QDi + QD[s] + 2.0 * yi * Qik;
+                        const double obj = quad > 0 ? -(gd * gd) / quad : -(gd * gd) / TAU;
+                        if (obj <= obj_min) {
+                            j = k;
+                            obj_min = obj;
+                        }
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            double o = __shfl_xor_sync(0xffffffffu, Gmax2, off);
+            Gmax2 = o > Gmax2 ? o : Gmax2;
+        }
+        warp_argbest(obj_min, j, false);
+        if (Gmax + Gmax2 < eps || j < 0) break;
+        if (max_iter > 0 && iter >= max_iter) break;
+        ++iter;
+
+        // ---- analytic update of (alpha_i, alpha_j) with libsvm's clipping
+        const double yj = j < fd.n_pos ? 1.0 : -1.0;
+        const double QDj = __shfl_sync(0xffffffffu, (j >> 5) ? QD[1] : QD[0], j & 31);
+        const double Gi = __shfl_sync(0xffffffffu, (i >> 5) ? G[1] : G[0], i & 31);
+        const double Gj = __shfl_sync(0xffffffffu, (j >> 5) ? G[1] : G[0], j & 31);
+        double ai = __shfl_sync(0xffffffffu, (i >> 5) ? alpha[1] : alpha[0], i & 31);
+        double aj = __shfl_sync(0xffffffffu, (j >> 5) ? alpha[1] : alpha[0], j & 31);
+        const double old_ai = ai, old_aj = aj;
+        const double Qij = (double)Q[i * 64 + j];
+        if (yi != yj) {
+            double quad = QDi + QDj + 2 * Qij;
+            if (quad <= 0) quad = TAU;
+            const double delta = (-Gi - Gj) / quad;
+            const double diff = ai - aj;
+            ai += delta;
+            aj += delta;
+            if (diff > 0) {
+                if (aj < 0) {
+                    aj = 0;
+                    ai = diff;
+                }
+            } else {
+                if (ai < 0) {
+                    ai = 0;
+                    aj = -diff;
+                }
+            }
+            if (diff > C - C) {
+                if (ai > C) {
+                    ai = C;
+                    aj = C - diff;
+                }
+            } else {
+                if (aj > C) {
+                    aj = C;
+                    ai = C + diff;
+                }
+            }
+        } else {
+            double quad = QDi + QDj - 2 * Qij;
+            if (quad <= 0) quad = TAU;
+            const double delta = (Gi - Gj) / quad;
+            const double sum = ai + aj;
+            ai -= delta;
+            aj += delta;
+            if (sum > C) {
+                if (ai > C) {
+                    ai = C;
+                    aj = sum - C;
+                }
+            } else {
+                if (aj < 0) {
+                    aj = 0;
+                    ai = sum;
+                }
+            }
+            if (sum > C) {
+                if (aj > C) {
+                    aj = C;
+                    ai = sum - C;
+                }
+            } else {
+                if (ai < 0) {
+                    ai = 0;
+                    aj = sum;
+                }
+            }
+        }
+        const double dai = ai - old_ai, daj = aj - old_aj;
+#pragma unroll
+        for (int s = 0; s < 2; s++) {
+            if (!valid[s]) continue;
+            const int k = lane + 32 * s;
+            // G[k] += Q_i[k]*dai + Q_j[k]*daj, no FMA contraction (as the reference compiles it)
+            G[s] = __dadd_rn(G[s], __dadd_rn(__dmul_rn((double)Q[i * 64 + k], dai), __dmul_rn((double)Q[j * 64 + k], daj)));
+            if (k == i) alpha[s] = ai;
+            if (k == j) alpha[s] = aj;
+        }
+    }
+
+    // ---- rho (calculate_rho)
+    double ub = INF, lb = -INF, sum_free = 0.0;
+    int nr_free = 0;
+#pragma unroll
+    for (int s = 0; s < 2; s++) {
+        if (!valid[s]) continue;
+        const double yG = y[s] * G[s];
+        if (alpha[s] >= C) {
+            if (y[s] < 0) ub = fmin(ub, yG); else lb = fmax(lb, yG);
+        } else if (alpha[s] <= 0) {
+            if (y[s] > 0) ub = fmin(ub, yG); else lb = fmax(lb, yG);
+        } else {
+            ++nr_free;
+            sum_free += yG;
+        }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        ub = fmin(ub, __shfl_xor_sync(0xffffffffu, ub, off));
+        lb = fmax(lb, __shfl_xor_sync(0xffffffffu, lb, off));
+        sum_free += __shfl_xor_sync(0xffffffffu, sum_free, off);
+        nr_free += __shfl_xor_sync(0xffffffffu, nr_free, off);
+    }
+    const double rho = nr_free > 0 ? sum_free / nr_free : (ub + lb) / 2;
+
+    // ---- predict the held-out samples: dec = sum_k alpha_k y_k K(test, k) - rho;  dec > 0 -> class +
+    int ok = 0;
+    for (int t = 0; t < fd.n_test; t++) {
+        const int it = fd.test_idx[t];
+        double part = 0.0;
+#pragma unroll
+        for (int s = 0; s < 2; s++)
+            if (valid[s] && alpha[s] != 0.0) part += alpha[s] * y[s] * (double)Kv[(size_t)it * E + idx[s]];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
+        const bool pred_pos = (part - rho) > 0;
+        ok += (pred_pos == (fd.test_pos[t] != 0)) ? 1 : 0;
+    }
+    if (lane == 0) {
+        correct[prob] = ok;
+        if (iters) iters[prob] = iter;
+    }
+}
+
+extern "C" int fcma_shrink_kernels(float *K_dev, long nv, int E, int *digits_dev, void *stream)
+{
+    int rc = check_device();
+    if (rc) return rc;
+    if (!K_dev || nv <= 0 || E <= 0) return fail(FCMA_EINVAL, "fcma_shrink_kernels: bad arguments");
+    k_shrink_kernels<<<(unsigned)cdiv(nv, 4), 128, 0, (cudaStream_t)stream>>>(K_dev, nv, E, digits_dev);
+    LAUNCH_CHECK("k_shrink_kernels");
+    return FCMA_OK;
+}
+
+extern "C" int fcma_svm_cv_precomputed(const float *K_dev, long nv, int E, int nfolds, const void *folds_host,
+                                       double C, double tol, int max_iter, int *correct_dev, int *iters_dev,
+                                       void *stream)
+{
+    int rc = check_device();
+    if (rc) return rc;
+    if (!K_dev || !folds_host || !correct_dev || nv <= 0 || E <= 0 || E > 64 || nfolds <= 0 || nfolds > 64)
+        return fail(FCMA_EINVAL, "fcma_svm_cv_precomputed: bad arguments (E <= 64, nfolds <= 64)");
+    if (!(C > 0) || !(tol > 0)) return fail(FCMA_EINVAL, "fcma_svm_cv_precomputed: C and tol must be positive");
+    const SvmFold *fh = reinterpret_cast<const SvmFold *>(folds_host);
+    for (int f = 0; f < nfolds; f++) {
+        if (fh[f].n_train < 2 || fh[f].n_train > 64 || fh[f].n_test < 0 || fh[f].n_test > 64 || fh[f].n_pos < 1 ||
+            fh[f].n_pos >= fh[f].n_train)
+            return fail(FCMA_EINVAL, "fold %d: need both classes in the training part and <= 64 samples", f);
+        for (int k = 0; k < fh[f].n_train; k++)
+            if (fh[f].train_idx[k] < 0 || fh[f].train_idx[k] >= E) return fail(FCMA_EINVAL, "fold %d: bad train index", f);
+        for (int k = 0; k < fh[f].n_test; k++)
+            if (fh[f].test_idx[k] < 0 || fh[f].test_idx[k] >= E) return fail(FCMA_EINVAL, "fold %d: bad test index", f);
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    SvmFold *fd = nullptr;
+    CUDA_TRY(cudaMallocAsync(&fd, sizeof(SvmFold) * nfolds, st));
+    CUDA_TRY(cudaMemcpyAsync(fd, fh, sizeof(SvmFold) * nfolds, cudaMemcpyHostToDevice, st));
+    const size_t smem = (size_t)4 * 64 * 64 * sizeof(float);
+    CUDA_TRY(cudaFuncSetAttribute(k_svm_cv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long nprob = nv * nfolds;
+    k_svm_cv<<<(unsigned)cdiv(nprob, 4), 128, smem, st>>>(K_dev, nv, E, nfolds, fd, C, tol, max_iter, correct_dev,
+                                                         iters_dev);
+    LAUNCH_CHECK("k_svm_cv");
+    CUDA_TRY(cudaFreeAsync(fd, st));
+    return FCMA_OK;
+}
+
 // ---------------------------------------------------------------- host-buffer entry points
 struct DevBuf {
     void *p = nullptr;

@@ -301,3 +301,81 @@ def host_voxel_kernels(raw_data, raw_data2, start, nb, eps, precision=_PREC_DEFA
                                            _prec_code(precision), int(bool(normalize)), int(flags),
                                            int(device), K.ctypes.data_as(ctypes.c_void_p)))
     return K
+
+
+# ------------------------------------------------------------------ a7 tail + a8 on the GPU
+class _SvmFold(ctypes.Structure):
+    _fields_ = [("n_train", ctypes.c_int), ("n_pos", ctypes.c_int), ("n_test", ctypes.c_int),
+                ("pad", ctypes.c_int), ("train_idx", ctypes.c_int * 64), ("test_idx", ctypes.c_int * 64),
+                ("test_pos", ctypes.c_ubyte * 64)]
+
+
+def shrink_kernels_(K, return_digits=False):
+    """In-place decimal shrink (voxelselector.py:409-412) of ``K`` = float32 CUDA ``[nv, E, E]``."""
+    lib = _lib.load()
+    nv, E, _ = K.shape
+    digits = torch.empty(nv, dtype=torch.int32, device=K.device) if return_digits else None
+    with torch.cuda.device(K.device):
+        _lib.check(lib.fcma_shrink_kernels(_ptr(K), nv, E, _ptr(digits) if digits is not None else None,
+                                           _stream_ptr()))
+    return digits
+
+
+def svm_cv_supported(clf, labels, num_folds, E):
+    """True if ``cross_val_score(clf, K, labels, cv=StratifiedKFold(num_folds))`` can run on the GPU:
+    binary ``SVC(kernel='precomputed')`` without class weights / probability, E <= 64."""
+    import sklearn.svm
+    if not (isinstance(clf, sklearn.svm.SVC) and clf.kernel == 'precomputed'):
+        return False
+    if clf.class_weight is not None or clf.probability or E > 64 or num_folds > 64:
+        return False
+    return len(np.unique(np.asarray(labels))) == 2
+
+
+def make_svm_folds(labels, num_folds):
+    """Fold descriptions for fcma_svm_cv_precomputed from sklearn's own splitter
+    (StratifiedKFold(n_splits, shuffle=False), reference voxelselector.py:44-45)."""
+    from sklearn import model_selection
+    y = np.asarray(labels)
+    classes = np.unique(y)
+    if len(classes) != 2:
+        raise ValueError("GPU SVM cross-validation handles two classes")
+    skf = model_selection.StratifiedKFold(n_splits=num_folds, shuffle=False)
+    folds = (_SvmFold * num_folds)()
+    n_test = []
+    for f, (tr, te) in enumerate(skf.split(np.zeros((len(y), 1)), y)):
+        pos = [int(i) for i in tr if y[i] == classes[0]]     # smaller label first = class +1
+        neg = [int(i) for i in tr if y[i] == classes[1]]
+        if not pos or not neg:
+            raise ValueError("a training fold contains a single class")
+        order = pos + neg
+        fd = folds[f]
+        fd.n_train, fd.n_pos, fd.n_test = len(order), len(pos), len(te)
+        for k, i in enumerate(order):
+            fd.train_idx[k] = i
+        for k, i in enumerate(te):
+            fd.test_idx[k] = int(i)
+            fd.test_pos[k] = 1 if y[i] == classes[0] else 0
+        n_test.append(len(te))
+    return folds, np.asarray(n_test, dtype=np.float64)
+
+
+def svm_cv_precomputed(K, labels, num_folds, C=1.0, tol=1e-3, max_iter=-1, folds=None, return_iters=False):
+    """Mean cross-validation accuracy of ``SVC(kernel='precomputed', C, tol)`` for every kernel of
+    ``K`` (float32 CUDA ``[nv, E, E]``), computed by the batched GPU SMO solver.  Equivalent to
+    ``cross_val_score(clf, K[v], y=labels, cv=StratifiedKFold(num_folds)).mean()`` per voxel."""
+    lib = _lib.load()
+    nv, E, _ = K.shape
+    if folds is None:
+        folds = make_svm_folds(labels, num_folds)
+    fstructs, n_test = folds
+    correct = torch.empty((nv, num_folds), dtype=torch.int32, device=K.device)
+    iters = torch.empty((nv, num_folds), dtype=torch.int32, device=K.device) if return_iters else None
+    with torch.cuda.device(K.device):
+        _lib.check(lib.fcma_svm_cv_precomputed(_ptr(K), nv, E, num_folds, ctypes.cast(fstructs, ctypes.c_void_p),
+                                               float(C), float(tol), int(max_iter if max_iter and max_iter > 0 else 10000000),
+                                               _ptr(correct), _ptr(iters) if iters is not None else None,
+                                               _stream_ptr()))
+    scores = correct.cpu().numpy().astype(np.float64) / n_test[None, :]   # accuracy_score per fold
+    acc = scores.mean(axis=1)                                             # cross_val_score(...).mean()
+    return (acc, iters.cpu().numpy()) if return_iters else acc

@@ -86,11 +86,14 @@ class VoxelSelector:
     normalize: apply the per-epoch z-score of preprocessing.py:80-84 on the GPU while packing
     device: CUDA device (default: current / LOCAL_RANK)
     block_rows: voxel rows per GPU pass (default: sized to free HBM)
+    gpu_cv: run the voxelwise cross validation of a binary ``SVC(kernel='precomputed')`` on the GPU
+        (batched restatement of libsvm's SMO, see engine.svm_cv_precomputed); ``False`` or any other
+        classifier -> scikit-learn on the host, exactly as the reference (voxelselector.py:41-53)
     """
 
     def __init__(self, labels, epochs_per_subj, num_folds, raw_data, raw_data2=None,
                  voxel_unit=64, process_num=4, master_rank=0, *, precision="fp32",
-                 mask_self=False, normalize=False, device=None, block_rows=None):
+                 mask_self=False, normalize=False, device=None, block_rows=None, gpu_cv=True):
         self.labels = labels
         self.epochs_per_subj = epochs_per_subj
         self.num_folds = num_folds
@@ -121,6 +124,7 @@ class VoxelSelector:
         self.normalize = bool(normalize)
         self.device = device
         self.block_rows = block_rows
+        self.gpu_cv = bool(gpu_cv)
         self._rows_op = None
         self._cols_op = None
         self._work = None
@@ -227,11 +231,21 @@ class VoxelSelector:
             block = max(1, min(block, n))
             if self._work is None or self._work.rows < block:
                 self._work = engine.Workspace(E, self.num_voxels2, block, rows_op.device)
+            on_gpu = self.gpu_cv and engine.svm_cv_supported(clf, self.labels, self.num_folds, E)
+            folds = engine.make_svm_folds(self.labels, self.num_folds) if on_gpu else None
             for s in range(start, start + n, block):
                 nb = min(block, start + n - s)
                 t0 = time.time()
                 K = engine.voxel_kernels(rows_op, cols_op, s, nb, self.epochs_per_subj,
                                          flags=self._flags(fused), work=self._work)
+                if on_gpu:
+                    # shrink + cross validation without leaving the device
+                    engine.shrink_kernels_(K)
+                    acc = engine.svm_cv_precomputed(K, self.labels, self.num_folds, C=clf.C, tol=clf.tol,
+                                                    max_iter=clf.max_iter, folds=folds)
+                    results += [(int(s + k), acc[k]) for k in range(nb)]
+                    logger.debug('rows [%d, %d): kernels + GPU cv %.3f s', s, s + nb, time.time() - t0)
+                    continue
                 kernels = K.cpu().numpy()
                 t1 = time.time()
                 shrink_kernels_(kernels)

@@ -133,6 +133,19 @@ int fcma_classifier_kernel(const void *rows_op, const void *cols_op, int precisi
                            long V, long V2, long start, long nb, int eps, int flags, float *work_dev,
                            size_t work_bytes, float *K_dev, void *stream);
 
+/* ---- a7 tail + a8 on the GPU ------------------------------------------------ */
+/* decimal shrink of voxelselector.py:409-412 on every [E][E] kernel, in place; digits_dev (optional,
+ * int[nv]) receives len(str(int(K[0][0]))) */
+int fcma_shrink_kernels(float *K_dev, long nv, int E, int *digits_dev, void *stream);
+
+/* batched cross-validation of SVC(kernel='precomputed') (binary C-SVC, libsvm SMO restated from
+ * scikit-learn's sklearn/svm/src/libsvm/svm.cpp) on nv kernels [E][E]: folds_host points to nfolds
+ * structs {int n_train, n_pos, n_test, pad; int train_idx[64]; int test_idx[64]; unsigned char test_pos[64]}
+ * (training samples of the smaller label first = class +1, as svm_group_classes orders them);
+ * correct_dev[v*nfolds + f] = number of correctly predicted held-out samples; iters_dev optional. */
+int fcma_svm_cv_precomputed(const float *K_dev, long nv, int E, int nfolds, const void *folds_host, double C,
+                            double tol, int max_iter, int *correct_dev, int *iters_dev, void *stream);
+
 /* ---- a12 / a15: plain NT GEMM  C[m][n] = sum_k A[m][k]*B[n][k]  (fp32 FFMA, row-major) ---------- */
 int fcma_gemm_nt(const float *A_dev, const float *B_dev, float *C_dev, long M, long N, long K,
                  long lda, long ldb, long ldc, void *stream);

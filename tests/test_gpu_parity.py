@@ -552,3 +552,68 @@ def test_full_size_invariants(dev):
         opp = engine.pack_epochs(ep, None, prec)
         Kp = engine.voxel_kernels(opp, opp, start, nb, eps, flags=fl, work=work).double()
         assert float((Kp - K).abs().max()) <= tol * float(K.abs().max())
+
+
+# ------------------------------------------------------------------------------- a8 on the GPU
+def _sklearn_cv(K, labels, folds, **kw):
+    from sklearn import model_selection
+    out = np.zeros(K.shape[0])
+    for v in range(K.shape[0]):
+        skf = model_selection.StratifiedKFold(n_splits=folds, shuffle=False)
+        clf = svm.SVC(kernel='precomputed', **kw)
+        out[v] = model_selection.cross_val_score(clf, K[v], y=labels, cv=skf, n_jobs=1).mean()
+    return out
+
+
+def test_gpu_shrink_matches_reference_rule(dev):
+    rng = RandomState(0)
+    K = (rng.rand(9, 6, 6).astype(np.float32) + 0.5)
+    K[:, 0, 0] = [0.3, 5, 50, 99.9, 100, 4321, 1e6, 99.99999, 123456.7]
+    ref = shrink_kernels_(K.copy())
+    t = torch.from_numpy(K.copy()).to(dev)
+    digits = engine.shrink_kernels_(t, return_digits=True).cpu().numpy()
+    assert list(digits) == [len(str(int(x))) for x in K[:, 0, 0]]
+    assert np.array_equal(t.cpu().numpy(), ref)
+
+
+def test_gpu_svm_cv_matches_sklearn(dev, golden):
+    """Batched GPU SMO (libsvm restatement) vs sklearn.cross_val_score on the same kernels."""
+    g = golden("vs_mid")
+    # (a) the kernels the unmodified reference built in its full run -> the accuracies it reported
+    Kf = np.ascontiguousarray(g["kernelsf"])
+    labels = [int(x) for x in g["labelsf"]]
+    acc = engine.svm_cv_precomputed(torch.from_numpy(Kf).to(dev), labels, 4, C=1.0, tol=1e-3)
+    assert np.array_equal(acc, g["accf"])
+    # (b) random correlation-like kernels, several (C, tol, folds); shrinking=False is reproduced
+    #     exactly, shrinking=True (sklearn's default) may differ only on near-zero margins
+    rng = RandomState(42)
+    E, nv = 32, 300
+    Z = rng.randn(nv, E, 200).astype(np.float32)
+    Z[:, 1::2, :20] += 0.35            # some signal
+    K = np.einsum('vej,vfj->vef', Z, Z).astype(np.float32)
+    shrink_kernels_(K)
+    lab = [e % 2 for e in range(E)]
+    Kd = torch.from_numpy(K).to(dev)
+    for folds, C, tol in ((4, 1.0, 1e-3), (8, 0.05, 1e-3), (2, 10.0, 1e-4)):
+        ref = _sklearn_cv(K, lab, folds, C=C, tol=tol, shrinking=False)
+        got, iters = engine.svm_cv_precomputed(Kd, lab, folds, C=C, tol=tol, return_iters=True)
+        assert np.array_equal(got, ref), (folds, C, tol, np.flatnonzero(got != ref)[:5])
+        assert iters.max() < 100000 and iters.min() >= 1
+    ref = _sklearn_cv(K, lab, 4, C=1.0, shrinking=True)
+    got = engine.svm_cv_precomputed(Kd, lab, 4, C=1.0)
+    assert np.mean(got == ref) >= 0.99
+    # unbalanced labels / odd fold sizes / label values other than 0,1
+    lab2 = [3 if e < 14 else 7 for e in range(E)]
+    ref = _sklearn_cv(K[:60], lab2, 3, C=1.0, shrinking=False)
+    got = engine.svm_cv_precomputed(Kd[:60], lab2, 3, C=1.0)
+    assert np.array_equal(got, ref)
+
+
+def test_voxel_selector_gpu_cv_equals_host_cv(dev, golden):
+    g = golden("vs_mid")
+    raw = list(g["rawf"])
+    labels = [int(x) for x in g["labelsf"]]
+    clf = svm.SVC(kernel='precomputed', shrinking=False, C=1)
+    a = VoxelSelector(labels, int(g["epsf"]), 4, raw, voxel_unit=32, process_num=0, gpu_cv=True).run(clf)
+    b = VoxelSelector(labels, int(g["epsf"]), 4, raw, voxel_unit=32, process_num=0, gpu_cv=False).run(clf)
+    assert a == b

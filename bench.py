@@ -338,6 +338,28 @@ def run_b200_arm(args):
                                         "operand_planes": planes},
                         "k_norm_syrk": {"ms": ts, "hbm_gbs": 4.0 * corr_launch / (ts * 1e-3) / 1e9}}}
 
+    # ---- the public API end to end: VoxelSelector.run(clf) incl. the batched GPU SVM cross-validation
+    run_api = None
+    if rank == 0 and world == 1 and not args.no_e2e:
+        from sklearn import svm as _svm
+        raw_list = [host[e].numpy() for e in range(E)]
+        labels = [e % 2 for e in range(E)]
+        clf = _svm.SVC(kernel="precomputed", shrinking=False, C=1)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        vs = VoxelSelector(labels, eps, E // eps, raw_list, voxel_unit=64, process_num=0, precision=prec,
+                           block_rows=block)
+        vs._work = work
+        res = vs.run(clf)
+        torch.cuda.synchronize()
+        t_run = time.perf_counter() - t0
+        top = sorted(v for v, _ in res[: V // 100])
+        run_api = {"seconds": t_run, "value": corr_total / t_run, "unit": UNIT,
+                   "what": "VoxelSelector(labels, eps, folds, raw_data).run(SVC(kernel='precomputed')) from host numpy "
+                           "epochs to the sorted (voxel, accuracy) list: H2D + pack + kernels + decimal shrink + "
+                           "batched GPU SVM cross-validation (%d voxels x %d folds)" % (V, E // eps),
+                   "planted_voxels_in_top_1pct": int(sum(1 for v in top if v < V // 100)), "top_1pct_size": V // 100}
+
     cpu_baseline = None
     if rank == 0 and not args.no_cpu_baseline and world == 1:
         fn, kind, cores = reference_task_fn(host, eps)
@@ -367,6 +389,7 @@ def run_b200_arm(args):
                            "step": "pack + corr GEMM + Fisher/z-score + kernel build for all V rows"
                                    + ("; NCCL broadcast of epochs + gather of kernels inside the step" if world > 1 else "")},
                 "gpu_launches": launches, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu_baseline,
+                "voxel_selection_run": run_api,
                 "clocks": clocks}
         print(json.dumps(line), flush=True)
     if world > 1:

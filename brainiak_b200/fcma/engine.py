@@ -327,7 +327,8 @@ def svm_cv_supported(clf, labels, num_folds, E):
     import sklearn.svm
     if not (isinstance(clf, sklearn.svm.SVC) and clf.kernel == 'precomputed'):
         return False
-    if clf.class_weight is not None or clf.probability or E > 64 or num_folds > 64:
+    # scikit-learn >= 1.9 uses the string 'deprecated' as the default of `probability`
+    if clf.class_weight is not None or getattr(clf, 'probability', False) is True or E > 64 or num_folds > 64:
         return False
     return len(np.unique(np.asarray(labels))) == 2
 

@@ -614,6 +614,9 @@ def test_voxel_selector_gpu_cv_equals_host_cv(dev, golden):
     raw = list(g["rawf"])
     labels = [int(x) for x in g["labelsf"]]
     clf = svm.SVC(kernel='precomputed', shrinking=False, C=1)
+    assert engine.svm_cv_supported(clf, labels, 4, 16)
+    assert not engine.svm_cv_supported(LogisticRegression(), labels, 4, 16)
+    assert not engine.svm_cv_supported(svm.SVC(kernel='precomputed', class_weight='balanced'), labels, 4, 16)
     a = VoxelSelector(labels, int(g["epsf"]), 4, raw, voxel_unit=32, process_num=0, gpu_cv=True).run(clf)
     b = VoxelSelector(labels, int(g["epsf"]), 4, raw, voxel_unit=32, process_num=0, gpu_cv=False).run(clf)
     assert a == b

@@ -174,7 +174,7 @@ def run_reference_arm(args):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    print_json(line)
     return 0
 
 
@@ -391,7 +391,7 @@ def run_b200_arm(args):
                 "gpu_launches": launches, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu_baseline,
                 "voxel_selection_run": run_api,
                 "clocks": clocks}
-        print(json.dumps(line), flush=True)
+        print_json(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -399,9 +399,25 @@ def run_b200_arm(args):
 
 def main():
     args = parse()
+    # Exactly ONE line may reach stdout (the JSON): libraries (NCCL's version banner, warnings) write
+    # to fd 1 as well, so fd 1 is pointed at stderr for the whole run and the JSON line goes to the
+    # saved original stdout.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    out = os.fdopen(real_stdout, "w")
+    global print_json
+
+    def print_json(obj):
+        out.write(json.dumps(obj) + "\n")
+        out.flush()
     if args.impl == "reference":
         return run_reference_arm(args)
     return run_b200_arm(args)
+
+
+def print_json(obj):      # replaced in main()
+    print(json.dumps(obj), flush=True)
 
 
 if __name__ == "__main__":

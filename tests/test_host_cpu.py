@@ -134,3 +134,29 @@ def test_host_shims_validate_like_cython_memoryviews():
     with pytest.raises(ValueError):
         cython_blas.compute_self_corr_for_voxel_sel('N', 'T', 6, 2, 4, 1.0, a, 6, 0, a, 6, 0.0,
                                                     np.zeros((2, 1, 6), np.float32), 6, 0)
+
+
+def test_svm_fold_descriptors_follow_sklearn_splits():
+    """make_svm_folds: sklearn's own StratifiedKFold(shuffle=False) splits, training part ordered
+    like libsvm's svm_group_classes (smaller label first = class +1, original order inside a class)."""
+    from sklearn import model_selection
+    labels = [3 if e % 3 else 7 for e in range(22)]          # unbalanced, labels other than 0/1
+    folds, n_test = engine.make_svm_folds(labels, 3)
+    skf = model_selection.StratifiedKFold(n_splits=3, shuffle=False)
+    y = np.asarray(labels)
+    for f, (tr, te) in enumerate(skf.split(np.zeros((22, 1)), y)):
+        fd = folds[f]
+        pos = [i for i in tr if y[i] == 3]
+        neg = [i for i in tr if y[i] == 7]
+        assert fd.n_train == len(tr) and fd.n_pos == len(pos) and fd.n_test == len(te) == n_test[f]
+        assert list(fd.train_idx[:fd.n_train]) == pos + neg
+        assert list(fd.test_idx[:fd.n_test]) == list(te)
+        assert [bool(b) for b in fd.test_pos[:fd.n_test]] == [y[i] == 3 for i in te]
+    assert ctypes.sizeof(folds[0]) == 592                    # layout of struct SvmFold in the library
+    with pytest.raises(ValueError):
+        engine.make_svm_folds([0, 1, 2] * 4, 2)              # multi-class -> host scikit-learn path
+    clf = svm.SVC(kernel="precomputed")
+    assert engine.svm_cv_supported(clf, [0, 1] * 8, 4, 16)
+    assert not engine.svm_cv_supported(clf, [0, 1, 2] * 4, 2, 12)
+    assert not engine.svm_cv_supported(svm.SVC(kernel="linear"), [0, 1] * 8, 4, 16)
+    assert not engine.svm_cv_supported(clf, [0, 1] * 40, 4, 80)

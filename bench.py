@@ -373,6 +373,31 @@ def run_b200_arm(args):
                         "sample": "%d tasks of 64 voxel rows x V=%d x E=%d, kernel path a4+a6+a7 "
                                   "(reference voxelselector.py:492-505), no CV" % (ntask, V, E)}
 
+    # ---- direct parity at the full shape: 64 rows through the UNMODIFIED reference vs the GPU pipeline
+    parity = None
+    if rank == 0 and cpu_baseline is not None and cpu_baseline["kind"] == "reference":
+        from oracle import reference
+        from sklearn import svm as _svm
+        m = reference.load()
+        raw_list = [host[e].numpy() for e in range(E)]
+        labels = [e % 2 for e in range(E)]
+        clf = _svm.SVC(kernel="precomputed", shrinking=False, C=1)
+        rvs = m.VoxelSelector(labels, eps, E // eps, raw_list, voxel_unit=64, process_num=0)
+        s0, n0 = 128, 64
+        corr = rvs._correlation_computation((s0, n0))
+        m.fcma_extension.normalization(corr, eps)
+        Kref = rvs._prepare_for_cross_validation(corr, clf)          # shrunk kernels [64, E, E]
+        acc_ref = np.array([a for _, a in rvs._do_cross_validation(clf, Kref, (s0, n0))])
+        op = engine.pack_epochs(epochs, None, prec)
+        Kg = engine.voxel_kernels(op, op, s0, n0, eps, work=work)
+        engine.shrink_kernels_(Kg)
+        acc_gpu = engine.svm_cv_precomputed(Kg, labels, E // eps, C=1.0, tol=1e-3)
+        Kg = Kg.cpu().numpy()
+        parity = {"rows": [s0, s0 + n0], "vs": "unmodified reference (oracle/_ref) on the host, same inputs",
+                  "max_abs_dK_over_max_K": float(np.max(np.abs(Kg - Kref)) / np.max(np.abs(Kref))),
+                  "cv_accuracy_identical": int(np.sum(acc_gpu == acc_ref)), "cv_accuracy_total": int(n0),
+                  "max_abs_d_accuracy": float(np.max(np.abs(acc_gpu - acc_ref)))}
+
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
@@ -389,7 +414,7 @@ def run_b200_arm(args):
                            "step": "pack + corr GEMM + Fisher/z-score + kernel build for all V rows"
                                    + ("; NCCL broadcast of epochs + gather of kernels inside the step" if world > 1 else "")},
                 "gpu_launches": launches, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu_baseline,
-                "voxel_selection_run": run_api,
+                "voxel_selection_run": run_api, "parity_vs_reference": parity,
                 "clocks": clocks}
         print_json(line)
     if world > 1:

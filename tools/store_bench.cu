@@ -22,7 +22,7 @@ __global__ void k_store(float *out, long nb, int E, long V2, long ld, int patter
             for (int ch = warp; ch < 32; ch += nwarps) {
                 const int q = ch & 3, c = ch >> 2;
                 float *p = out + ((size_t)(ti * 256 + c * 32) * E + e) * ld + tj * 128 + q * 32 + lane;
-                if (tj * 128 + q * 32 + lane < V2)
+                if (tj * 128 + q * 32 + lane < ld)
 #pragma unroll
                     for (int r = 0; r < 32; r++) {
                         *p = val;
@@ -41,7 +41,7 @@ __global__ void k_store(float *out, long nb, int E, long V2, long ld, int patter
                 float *p = out + ((size_t)(ti * 256 + row) * E + e) * ld + tj * 128 + lane;
 #pragma unroll
                 for (int q = 0; q < 4; q++)
-                    if (tj * 128 + q * 32 + lane < V2) p[q * 32] = val;
+                    if (tj * 128 + q * 32 + lane < ld) p[q * 32] = val;
             }
         }
     }
@@ -52,9 +52,9 @@ int main(int argc, char **argv)
     const long nb = 2048, V2 = 50000, ld = 50016;
     const int E = 32;
     float *out;
-    size_t bytes = (size_t)nb * E * ld * 4;
-    cudaMalloc(&out, bytes);
     const long tiles_j = (V2 + 127) / 128, tiles_i = nb / 256;
+    size_t bytes = (size_t)tiles_j * tiles_i * E * 256 * 128 * 4 + (size_t)nb * E * 64 * 4;
+    if (cudaMalloc(&out, bytes) != cudaSuccess) { printf("alloc failed\n"); return 1; }
     for (int pattern = 0; pattern < 3; pattern++)
         for (int warps = 8; warps <= 32; warps *= 2) {
             cudaEvent_t e0, e1;

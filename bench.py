@@ -373,6 +373,33 @@ def run_b200_arm(args):
                         "sample": "%d tasks of 64 voxel rows x V=%d x E=%d, kernel path a4+a6+a7 "
                                   "(reference voxelselector.py:492-505), no CV" % (ntask, V, E)}
 
+    # ---- the other BASELINE.json configs that share this path (informational, short)
+    others = None
+    if rank == 0 and world == 1 and not args.no_e2e:
+        others = {}
+        op = engine.pack_epochs(epochs, None, prec)
+
+        def ev_time(fn, reps=2):
+            fn()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(reps):
+                fn()
+            b.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) / reps
+        # configs[4]: Classifier precomputed corr-kernel matrix, V=50 000, E=32 (one [E,E] kernel)
+        Kc = torch.zeros((E, E), dtype=torch.float32, device=dev)
+        ms_c = ev_time(lambda: engine.classifier_kernel(op, op, 0, V, eps, work=work, out=Kc), reps=1)
+        others["classifier_kernel_V%d_E%d" % (V, E)] = {"ms": ms_c, "value": corr_total / (ms_c * 1e-3), "unit": UNIT}
+        # explicit reduced precision (BASELINE configs[2] wording "bf16/fp32-accum")
+        opb = engine.pack_epochs(epochs, None, "bf16")
+        ms_b = ev_time(lambda: engine.voxel_kernels(opb, opb, 0, V, eps, work=work, out=K), reps=1)
+        others["voxel_kernels_bf16_operands"] = {"ms": ms_b, "value": corr_total / (ms_b * 1e-3), "unit": UNIT,
+                                                 "note": "|dr| <= 8e-3; the headline uses the fp32-faithful fp16x3 split"}
+        del opb, op
+
     # ---- direct parity at the full shape: 64 rows through the UNMODIFIED reference vs the GPU pipeline
     parity = None
     if rank == 0 and cpu_baseline is not None and cpu_baseline["kind"] == "reference":
@@ -414,7 +441,7 @@ def run_b200_arm(args):
                            "step": "pack + corr GEMM + Fisher/z-score + kernel build for all V rows"
                                    + ("; NCCL broadcast of epochs + gather of kernels inside the step" if world > 1 else "")},
                 "gpu_launches": launches, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu_baseline,
-                "voxel_selection_run": run_api, "parity_vs_reference": parity,
+                "voxel_selection_run": run_api, "parity_vs_reference": parity, "other_configs": others,
                 "clocks": clocks}
         print_json(line)
     if world > 1:

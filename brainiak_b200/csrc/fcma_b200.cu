@@ -1552,6 +1552,13 @@ __global__ void __launch_bounds__(256, (R == 4 ? 2 : 1))
     __shared__ float s_K[EP * EP];
     extern __shared__ __align__(16) uint8_t dyn_smem[];
     float4 *s_stage = reinterpret_cast<float4 *>(dyn_smem);  // VEC only: [warp][buf][r*2+h][lane]
+    // R == 4 only: per-warp fp32 partial kernels [8][EP*EP].  The warp MMA adds into its accumulator
+    // with truncation, so a long chain at growing magnitude biases the sums (measured 5e-5 relative on
+    // the diagonal at V2 = 50 000); flushing the MMA accumulators into these round-to-nearest partials
+    // every FLUSH chunks bounds the chain length (bias ~1e-6).  Every (row, col) has exactly one owner lane.
+    [[maybe_unused]] float *s_part =
+        reinterpret_cast<float *>(dyn_smem + (VEC ? (size_t)8 * 2 * 2 * R * 32 * sizeof(float4) : 0));
+    constexpr int FLUSH = 8;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, t = lane & 3;
     const int S_eps = EPS > 0 ? (E / EPS) * EPS : 0;  // epochs that get normalised
@@ -1568,6 +1575,28 @@ __global__ void __launch_bounds__(256, (R == 4 ? 2 : 1))
 #pragma unroll
                 for (int c = 0; c < 4; c++) acc[a][b][c] = 0.f;
 
+        [[maybe_unused]] int since_flush = 0;
+        auto flush = [&]() {
+            float *part = s_part + warp * (EP * EP);
+#pragma unroll
+            for (int mu = 0; mu < MT; mu++)
+#pragma unroll
+                for (int nu = 0; nu < NT; nu++) {
+                    const int row0 = R * g + 2 * mu, row1 = row0 + 1;
+                    const int col0 = R * (2 * t) + nu, col1 = R * (2 * t + 1) + nu;
+                    part[row0 * EP + col0] += acc[mu][nu][0];
+                    part[row0 * EP + col1] += acc[mu][nu][1];
+                    part[row1 * EP + col0] += acc[mu][nu][2];
+                    part[row1 * EP + col1] += acc[mu][nu][3];
+#pragma unroll
+                    for (int c = 0; c < 4; c++) acc[mu][nu][c] = 0.f;
+                }
+        };
+        if constexpr (R == 4) {
+            float *part = s_part + warp * (EP * EP);
+            for (int idx = lane; idx < EP * EP; idx += 32) part[idx] = 0.f;
+            __syncwarp();
+        }
         // VEC path: cp.async double buffering into a per-warp staging tile (8 x 16 B per lane), so the
         // next chunk streams from HBM while this one is normalised and multiplied; zero fill covers
         // epochs >= E and the ragged last chunk without any branch.
@@ -1736,9 +1765,26 @@ __global__ void __launch_bounds__(256, (R == 4 ? 2 : 1))
                     for (int nu = 0; nu < NT; nu++)
                         mma_tf32_16x8x8(acc[mu][nu], tv[2 * mu][0][u], tv[2 * mu + 1][0][u], tv[2 * mu][1][u],
                                         tv[2 * mu + 1][1][u], tv[nu][0][u], tv[nu][1][u]);
+            if constexpr (R == 4) {
+                if (++since_flush == FLUSH) {
+                    flush();
+                    since_flush = 0;
+                }
+            }
         }
 
         // ---- deterministic cross-warp reduction into s_K (epoch order restored)
+        if constexpr (R == 4) {
+            flush();
+            __syncthreads();
+            for (int idx = threadIdx.x; idx < EP * EP; idx += 256) {
+                float v = 0.f;
+#pragma unroll
+                for (int w = 0; w < 8; w++) v += s_part[w * (EP * EP) + idx];
+                s_K[idx] = v;
+            }
+            __syncthreads();
+        } else {
         __syncthreads();
         for (int w = 0; w < 8; w++) {
             if (warp == w) {
@@ -1762,6 +1808,7 @@ __global__ void __launch_bounds__(256, (R == 4 ? 2 : 1))
                     }
             }
             __syncthreads();
+        }
         }
         // ---- write: symmetric by construction from the lower triangle (cython_blas.pyx:200-207)
         for (int idx = threadIdx.x; idx < E * E; idx += 256) {
@@ -1788,7 +1835,8 @@ template <int R, bool FISHER, bool VEC>
 static bool dispatch_eps(int eps, dim3 grid, cudaStream_t st, const float *C, long nb, int E, long n2, long stride_i,
                          long ld, long self_col0, float beta, float *K, int sum)
 {
-    constexpr size_t smem = VEC ? (size_t)8 * 2 * 2 * R * 32 * sizeof(float4) : 0;
+    constexpr size_t smem = (VEC ? (size_t)8 * 2 * 2 * R * 32 * sizeof(float4) : 0) +
+                            (R == 4 ? (size_t)8 * (8 * R) * (8 * R) * sizeof(float) : 0);
 #define FCMA_CASE(EPSV)                                                                                          \
     case EPSV:                                                                                                   \
         if (smem > 48 * 1024)                                                                                    \

@@ -10,8 +10,10 @@ every voxel row the correlation GEMM -> Fisher-z + within-subject z-score -> E x
 the [V, E, E] kernels left resident in HBM.  metric = V * V * E / step time.
 
 N > 1: voxel rows are sharded statically over the ranks (the reference's data-parallel scheme,
-voxelselector.py:198-238); inside the timed step rank 0 broadcasts the epochs over NCCL and the
-per-rank kernels are gathered on rank 0.  The total job is fixed, so scaling is "strong".
+voxelselector.py:198-238) with the epochs replicated in every rank's HBM (as after the reference's
+bcast, preprocessing.py:211-223); the per-rank kernels are gathered on rank 0 inside the timed step.
+The `e2e` figure starts from rank 0's host memory and includes the NCCL broadcast of the epochs.
+The total job is fixed, so scaling is "strong".
 
 One JSON line is printed by rank 0.  Extra objects: `roofline` (dominant kernel, measured live with
 CUDA events), `cpu_baseline` (reference path on this box's host cores, bounded sample), `e2e` (host
@@ -226,16 +228,24 @@ def run_b200_arm(args):
             dist.barrier(device_ids=[local])
         torch.cuda.synchronize()
 
+    # N > 1: every rank holds the (replicated) normalised epochs in HBM before the timed region, exactly
+    # like the reference's ranks after prepare_fcma_data's bcast (preprocessing.py:211-223); the e2e
+    # variant starts from rank 0's host memory and includes the NCCL broadcast.
+    if world > 1:
+        dist.broadcast(epochs, src=0)
+
     def step(from_host):
-        """One pass of the hot path. from_host: include the pinned-host -> HBM copy and the K readback."""
-        if from_host and rank == 0:
-            epochs.copy_(host, non_blocking=True)
+        """One pass of the hot path. from_host: include the pinned-host -> HBM copy (+ NCCL broadcast
+        of the epochs for N > 1) and the readback of the [V, E, E] kernels."""
         src = epochs
-        if world > 1:
+        if from_host:
             if rank == 0:
-                bcast.copy_(epochs)
-            dist.broadcast(bcast, src=0)
-            src = bcast
+                epochs.copy_(host, non_blocking=True)
+            if world > 1:
+                if rank == 0:
+                    bcast.copy_(epochs)
+                dist.broadcast(bcast, src=0)
+                src = bcast
         op = engine.pack_epochs(src, None, prec)
         if n > 0:
             engine.voxel_kernels(op, op, start, n, eps, flags=flags, work=work, out=K)
@@ -439,7 +449,8 @@ def run_b200_arm(args):
                                  % (lib.fcma_operand_bytes(_lib.PREC[prec], E, T, V) / 1e9,
                                     lib.fcma_work_bytes_per_row(E, V) * block / 1e9),
                            "step": "pack + corr GEMM + Fisher/z-score + kernel build for all V rows"
-                                   + ("; NCCL broadcast of epochs + gather of kernels inside the step" if world > 1 else "")},
+                                   + ("; epochs replicated in every rank's HBM beforehand, NCCL gather of the kernels inside the step; "
+                                      "e2e adds H2D on rank 0 + NCCL broadcast + D2H" if world > 1 else "")},
                 "gpu_launches": launches, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu_baseline,
                 "voxel_selection_run": run_api, "parity_vs_reference": parity, "other_configs": others,
                 "clocks": clocks}

@@ -298,22 +298,20 @@ def run_b200_arm(args):
     if rank == 0:
         op = engine.pack_epochs(epochs, None, prec)
         nbk = min(block, n)
-        ld = ((V + 31) // 32) * 32
-        cbuf = work.buf.view(torch.float32)[: nbk * E * ld].view(nbk, E, ld)
         Kb = K[:nbk]
-        evs = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-        tg, ts, reps = 0.0, 0.0, 4
-        for r in range(reps + 1):
-            evs[0].record()
-            engine.corr_block(op, op, start, nbk, out=cbuf, ld=ld, fisher_epochs=(E // eps) * eps)
-            evs[1].record()
-            engine.norm_kernel_matrices(cbuf[:, :, :V], eps, fisher_done=True, out=Kb)
-            evs[2].record()
-            torch.cuda.synchronize()
-            if r > 0:
-                tg += evs[0].elapsed_time(evs[1])
-                ts += evs[1].elapsed_time(evs[2])
-        tg, ts = tg / reps, ts / reps
+        # live per-kernel times of the SAME launches the timed step makes (events inside the C pipeline)
+        reps = 4
+        engine.voxel_kernels(op, op, start, nbk, eps, flags=flags, work=work, out=Kb)
+        torch.cuda.synchronize()
+        lib.fcma_timing_enable(1)
+        for r in range(reps):
+            engine.voxel_kernels(op, op, start, nbk, eps, flags=flags, work=work, out=Kb)
+        torch.cuda.synchronize()
+        import ctypes as _ct
+        g_ms, s_ms = _ct.c_double(0), _ct.c_double(0)
+        npass = lib.fcma_timing_read(_ct.byref(g_ms), _ct.byref(s_ms))
+        lib.fcma_timing_enable(0)
+        tg, ts = g_ms.value / npass, s_ms.value / npass
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))

@@ -58,6 +58,8 @@ SIGNATURES = {
                                         c_void_p]),
     "fcma_host_within_subject_norm": (c_int, [c_void_p, c_long, c_int, c_long, c_int, c_int]),
     "fcma_launch_count": (c_long, []),
+    "fcma_timing_enable": (None, [c_int]),
+    "fcma_timing_read": (c_long, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]),
 }
 
 _lib = None

@@ -589,6 +589,7 @@ struct Gemm2Params {
     int fmt;                       // idesc operand format
     float out_scale;               // accumulator scale applied in the epilogue
     int tma_store;                 // 1: epilogue stages 32x32 blocks in smem and issues TMA stores
+    int blocked;                   // 1: output is [E][tiles_j][nb][256] (needs tma_store); 0: strided [i][e][j]
 };
 
 template <int KIND>
@@ -768,7 +769,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
                     fence_proxy_async_smem();
                     __syncwarp();
                     if (lane == 0) {
-                        tma_store_3d(&tm_out, blk, (int)(j - lane), e, (int)ic);
+                        if (p.blocked)   // box {32 j_local, 32 i, 1 block}: the pair's tile is one contiguous 256 KB run
+                            tma_store_3d(&tm_out, blk, (int)rank * 128 + q * 32, (int)ic, e * p.tiles_j + tj);
+                        else
+                            tma_store_3d(&tm_out, blk, (int)(j - lane), e, (int)ic);
                         tma_store_commit();
                     }
                     continue;
@@ -1113,7 +1117,7 @@ static int make_operand_map(CUtensorMap *m, const void *base, const PrecInfo &pi
 
 // self-correlation fix-up: out[i][e][start+i] = exact sequential-FMA r (optionally Fisher-transformed)
 __global__ void k_self_corr_fixup(const float *__restrict__ selfdiag, int E, long V, long start, long nb, float *out,
-                                  long stride_i, long stride_e, int fisher_epochs)
+                                  long stride_i, long stride_e, int fisher_epochs, long blocked_t256)
 {
     const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= nb * E) return;
@@ -1121,7 +1125,11 @@ __global__ void k_self_corr_fixup(const float *__restrict__ selfdiag, int E, lon
     const int e = (int)(idx - i * E);
     float r = selfdiag[(size_t)e * V + start + i];
     if (e < fisher_epochs) r = fisher_fast(r);
-    out[(size_t)i * stride_i + (size_t)e * stride_e + start + i] = r;
+    const long j = start + i;
+    if (blocked_t256 > 0)
+        out[(((size_t)e * blocked_t256 + (j >> 8)) * nb + i) * 256 + (j & 255)] = r;
+    else
+        out[(size_t)i * stride_i + (size_t)e * stride_e + j] = r;
 }
 
 // output tensor out[i*stride_i + e*stride_e + j] as a 3-D TMA tensor (j, e, i), box {32, 1, 32}, no swizzle
@@ -1139,9 +1147,25 @@ static int make_out_map(CUtensorMap *m, float *out, long V2, int E, long nb, lon
     return FCMA_OK;
 }
 
+// blocked output [E*T256][nb][256] as a 3-D TMA tensor (j_local, i, block), box {32, 32, 1}
+static int make_out_map_blocked(CUtensorMap *m, float *out, int E, long nb, long t256)
+{
+    PFN_tmEncodeTiled enc = get_encode_fn();
+    if (!enc) return fail(FCMA_ECUDA, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t gdim[3] = {256, (cuuint64_t)nb, (cuuint64_t)E * t256};
+    cuuint64_t gstr[2] = {1024, (cuuint64_t)nb * 1024};
+    cuuint32_t box[3] = {32, 32, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, out, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(FCMA_ECUDA, "cuTensorMapEncodeTiled(blocked out) failed with CUresult %d", (int)r);
+    return FCMA_OK;
+}
+
+// blocked_t256 > 0: write the block in the blocked layout [E][blocked_t256][nb][256] (pair kernel + TMA store only)
 static int launch_corr_umma(const void *rows_op, const void *cols_op, int precision, int E, int T, long V, long V2,
                             long start, long nb, float *out, long stride_i, long stride_e, int fisher_epochs,
-                            cudaStream_t st)
+                            cudaStream_t st, long blocked_t256 = 0)
 {
     PrecInfo pi;
     if (!prec_info(precision, &pi)) return fail(FCMA_EINVAL, "unknown precision %d", precision);
@@ -1189,7 +1213,8 @@ static int launch_corr_umma(const void *rows_op, const void *cols_op, int precis
     int rc = make_operand_map(&tm_cols, cols_op, pi, E, V2, Kp, 128);
     if (rc) return rc;
     static const bool use_v1 = getenv("FCMA_GEMM_V1") != nullptr;
-    static const bool no_v3 = getenv("FCMA_GEMM_RESIDENT") == nullptr;  // opt-in: measured no faster than v2
+    static const bool no_v3 = getenv("FCMA_GEMM_RESIDENT") == nullptr || blocked_t256 > 0;  // opt-in: no faster than v2
+    if (use_v1 && blocked_t256 > 0) return fail(FCMA_EINVAL, "internal: blocked output is not available with FCMA_GEMM_V1");
     if (!use_v1 && !no_v3 && pi.esize == 2) {
         // resident-row-operand kernel: needs kbs * planes * (BN/2 * 128) bytes + >= 2 column stages
         Gemm3Params q;
@@ -1247,6 +1272,9 @@ static int launch_corr_umma(const void *rows_op, const void *cols_op, int precis
         static const bool no_tma_store = getenv("FCMA_GEMM_NO_TMA_STORE") != nullptr;
         q.tma_store = (!no_tma_store && (stride_i % 4 == 0) && (stride_e % 4 == 0) && (((uintptr_t)out & 15) == 0) &&
                        V2 < (1L << 31) && nb < (1L << 31)) ? 1 : 0;
+        q.blocked = blocked_t256 > 0 ? 1 : 0;
+        if (q.blocked && (!q.tma_store || blocked_t256 != q.tiles_j))
+            return fail(FCMA_EINVAL, "internal: blocked output needs the TMA-store epilogue and T256 == tiles_j");
         const size_t staging_bytes = q.tma_store ? (size_t)GEMM_EPI_WARPS * 4096 : 0;
         const size_t cap2 = 227 * 1024 - 1024 - 256;
         int st2 = (int)((cap2 - staging_bytes) / q.stage_bytes);
@@ -1255,7 +1283,10 @@ static int launch_corr_umma(const void *rows_op, const void *cols_op, int precis
         q.stages = st2;
         const size_t smem2 = (size_t)st2 * q.stage_bytes + staging_bytes + 1024 + 256;
         CUtensorMap tm_out;
-        if (q.tma_store) {
+        if (q.blocked) {
+            rc = make_out_map_blocked(&tm_out, out, E, nb, blocked_t256);
+            if (rc) return rc;
+        } else if (q.tma_store) {
             rc = make_out_map(&tm_out, out, V2, E, nb, stride_i, stride_e);
             if (rc) return rc;
         } else {
@@ -1300,7 +1331,7 @@ fixup:
                                                           operand_plane_bytes(pi, precision, E, T, V));
         long n = nb * E;
         k_self_corr_fixup<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(sd, E, V, start, nb, out, stride_i, stride_e,
-                                                                 fisher_epochs);
+                                                                 fisher_epochs, blocked_t256);
         LAUNCH_CHECK("k_self_corr_fixup");
     }
     return FCMA_OK;
@@ -1544,8 +1575,8 @@ __global__ void __launch_bounds__(256) k_syrk_simt(const float *__restrict__ z, 
 // EPS == 0: input is already normalised (plain SYRK).
 template <int R, int EPS, bool FISHER, bool VEC>
 __global__ void __launch_bounds__(256, (R == 4 ? 2 : 1))
-    k_norm_syrk(const float *__restrict__ C, long nb, int E, long n2, long stride_i, long ld, long self_col0,
-                float beta, float *K, int sum_over_rows)
+    k_norm_syrk(const float *__restrict__ C, long nb, int E, long n2, long stride_i, long ld, long chunk_step,
+                long self_col0, float beta, float *K, int sum_over_rows)
 {
     constexpr int EP = 8 * R;
     constexpr int MT = EP / 16, NT = EP / 8;
@@ -1625,7 +1656,7 @@ __global__ void __launch_bounds__(256, (R == 4 ? 2 : 1))
                     }
             }
 #pragma unroll
-            for (int r = 0; r < R; r++) lane_src[r] += 8 * 32;  // this warp's next chunk
+            for (int r = 0; r < R; r++) lane_src[r] += chunk_step;  // this warp's next chunk (8 chunks on)
         };
         if constexpr (VEC) {
             stage = s_stage + (size_t)warp * (2 * 2 * R * 32);
@@ -1833,7 +1864,7 @@ __global__ void k_scale(float *x, long n, float s)
 
 template <int R, bool FISHER, bool VEC>
 static bool dispatch_eps(int eps, dim3 grid, cudaStream_t st, const float *C, long nb, int E, long n2, long stride_i,
-                         long ld, long self_col0, float beta, float *K, int sum)
+                         long ld, long chunk_step, long self_col0, float beta, float *K, int sum)
 {
     constexpr size_t smem = (VEC ? (size_t)8 * 2 * 2 * R * 32 * sizeof(float4) : 0) +
                             (R == 4 ? (size_t)8 * (8 * R) * (8 * R) * sizeof(float) : 0);
@@ -1842,7 +1873,7 @@ static bool dispatch_eps(int eps, dim3 grid, cudaStream_t st, const float *C, lo
         if (smem > 48 * 1024)                                                                                    \
             cudaFuncSetAttribute(k_norm_syrk<R, EPSV, FISHER, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                  (int)smem);                                                                     \
-        k_norm_syrk<R, EPSV, FISHER, VEC><<<grid, 256, smem, st>>>(C, nb, E, n2, stride_i, ld, self_col0, beta, K, sum); \
+        k_norm_syrk<R, EPSV, FISHER, VEC><<<grid, 256, smem, st>>>(C, nb, E, n2, stride_i, ld, chunk_step, self_col0, beta, K, sum); \
         return true;
     switch (eps) {
         FCMA_CASE(0)
@@ -1857,7 +1888,7 @@ static bool dispatch_eps(int eps, dim3 grid, cudaStream_t st, const float *C, lo
             if (smem > 48 * 1024)
                 cudaFuncSetAttribute(k_norm_syrk<R, 64, FISHER, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)smem);
-            k_norm_syrk<R, 64, FISHER, VEC><<<grid, 256, smem, st>>>(C, nb, E, n2, stride_i, ld, self_col0, beta, K, sum);
+            k_norm_syrk<R, 64, FISHER, VEC><<<grid, 256, smem, st>>>(C, nb, E, n2, stride_i, ld, chunk_step, self_col0, beta, K, sum);
             return true;
         }
         return false;
@@ -1875,8 +1906,13 @@ static bool fused_supported(int E, int eps_mode)
     return eps_mode <= (E <= 32 ? 32 : 64);
 }
 
+// (stride_i, ld, chunk_step) describe where element (i, e, j) of the correlation block lives:
+//   C[i*stride_i + e*ld + (j/256)*chunk_step + j%256]
+// classic [nb][E][ld] layout: stride_i = E*ld, chunk_step = 256; blocked [E][T256][nb][256] layout (written
+// by the pair GEMM as contiguous 256 KB tiles): stride_i = 256, ld = T256*nb*256, chunk_step = nb*256.
 static int launch_norm_syrk(const float *C, long nb, int E, long n2, long stride_i, long ld, int eps_mode,
-                            int fisher_done, long self_col0, float beta, float *K, int sum_over_rows, cudaStream_t st)
+                            int fisher_done, long self_col0, float beta, float *K, int sum_over_rows, cudaStream_t st,
+                            long chunk_step = 256)
 {
     if (!fused_supported(E, eps_mode)) return fail(FCMA_EINVAL, "internal: fused norm+syrk unsupported E=%d eps=%d", E, eps_mode);
     if (sum_over_rows) {
@@ -1885,6 +1921,7 @@ static int launch_norm_syrk(const float *C, long nb, int E, long n2, long stride
         LAUNCH_CHECK("k_scale");
     }
     const bool vec = ((ld & 3) == 0) && ((stride_i & 3) == 0) && (((uintptr_t)C & 15) == 0);
+    if (!vec && chunk_step != 256) return fail(FCMA_EINVAL, "internal: blocked layout needs the vector path");
     const bool fisher = eps_mode > 0 && !fisher_done;
     // rows cost the same: a static stride over 16 blocks per SM balances well
     long g = nb < 16L * g_sm_count ? nb : 16L * g_sm_count;
@@ -1892,18 +1929,18 @@ static int launch_norm_syrk(const float *C, long nb, int E, long n2, long stride
     bool ok;
     if (E <= 32) {
         if (fisher)
-            ok = vec ? dispatch_eps<4, true, true>(eps_mode, grid, st, C, nb, E, n2, stride_i, ld, self_col0, beta, K, sum_over_rows)
-                     : dispatch_eps<4, true, false>(eps_mode, grid, st, C, nb, E, n2, stride_i, ld, self_col0, beta, K, sum_over_rows);
+            ok = vec ? dispatch_eps<4, true, true>(eps_mode, grid, st, C, nb, E, n2, stride_i, ld, chunk_step, self_col0, beta, K, sum_over_rows)
+                     : dispatch_eps<4, true, false>(eps_mode, grid, st, C, nb, E, n2, stride_i, ld, chunk_step, self_col0, beta, K, sum_over_rows);
         else
-            ok = vec ? dispatch_eps<4, false, true>(eps_mode, grid, st, C, nb, E, n2, stride_i, ld, self_col0, beta, K, sum_over_rows)
-                     : dispatch_eps<4, false, false>(eps_mode, grid, st, C, nb, E, n2, stride_i, ld, self_col0, beta, K, sum_over_rows);
+            ok = vec ? dispatch_eps<4, false, true>(eps_mode, grid, st, C, nb, E, n2, stride_i, ld, chunk_step, self_col0, beta, K, sum_over_rows)
+                     : dispatch_eps<4, false, false>(eps_mode, grid, st, C, nb, E, n2, stride_i, ld, chunk_step, self_col0, beta, K, sum_over_rows);
     } else {
         if (fisher)
-            ok = vec ? dispatch_eps<8, true, true>(eps_mode, grid, st, C, nb, E, n2, stride_i, ld, self_col0, beta, K, sum_over_rows)
-                     : dispatch_eps<8, true, false>(eps_mode, grid, st, C, nb, E, n2, stride_i, ld, self_col0, beta, K, sum_over_rows);
+            ok = vec ? dispatch_eps<8, true, true>(eps_mode, grid, st, C, nb, E, n2, stride_i, ld, chunk_step, self_col0, beta, K, sum_over_rows)
+                     : dispatch_eps<8, true, false>(eps_mode, grid, st, C, nb, E, n2, stride_i, ld, chunk_step, self_col0, beta, K, sum_over_rows);
         else
-            ok = vec ? dispatch_eps<8, false, true>(eps_mode, grid, st, C, nb, E, n2, stride_i, ld, self_col0, beta, K, sum_over_rows)
-                     : dispatch_eps<8, false, false>(eps_mode, grid, st, C, nb, E, n2, stride_i, ld, self_col0, beta, K, sum_over_rows);
+            ok = vec ? dispatch_eps<8, false, true>(eps_mode, grid, st, C, nb, E, n2, stride_i, ld, chunk_step, self_col0, beta, K, sum_over_rows)
+                     : dispatch_eps<8, false, false>(eps_mode, grid, st, C, nb, E, n2, stride_i, ld, chunk_step, self_col0, beta, K, sum_over_rows);
     }
     if (!ok) return fail(FCMA_EINVAL, "internal: no k_norm_syrk instantiation for E=%d eps=%d", E, eps_mode);
     LAUNCH_CHECK("k_norm_syrk");
@@ -2049,7 +2086,26 @@ extern "C" int fcma_norm_kernel_matrices(const float *corr_dev, long nb, int E, 
 
 extern "C" size_t fcma_work_bytes_per_row(int E, long V2)
 {
-    return (size_t)E * round_up(V2, 32) * sizeof(float);
+    // the fused pipelines store the block as [E][T256][rows][256] (T256 = ceil(V2/256) column groups)
+    return (size_t)E * round_up(V2, 256) * sizeof(float);
+}
+
+// Optional per-kernel timing of the fused pipelines (bench.py's live roofline measurement): when enabled,
+// CUDA events bracket the GEMM and the normalise+SYRK launches on the launch stream.
+static int g_timing_on = 0;
+static double g_t_gemm = 0.0, g_t_syrk = 0.0;
+static long g_t_passes = 0;
+extern "C" void fcma_timing_enable(int on)
+{
+    g_timing_on = on;
+    g_t_gemm = g_t_syrk = 0.0;
+    g_t_passes = 0;
+}
+extern "C" long fcma_timing_read(double *gemm_ms, double *syrk_ms)
+{
+    if (gemm_ms) *gemm_ms = g_t_gemm;
+    if (syrk_ms) *syrk_ms = g_t_syrk;
+    return g_t_passes;
 }
 
 // shared body of the two fused pipelines
@@ -2062,7 +2118,7 @@ static int run_pipeline(const void *rows_op, const void *cols_op, int precision,
     if (eps < 0) return fail(FCMA_EINVAL, "pipeline: negative epochs_per_subj");
     if (((uintptr_t)work & 15)) return fail(FCMA_EINVAL, "pipeline: work buffer must be 16-byte aligned");
     const long ld = round_up(V2, 32);
-    const size_t row_bytes = (size_t)E * ld * sizeof(float);
+    const size_t row_bytes = fcma_work_bytes_per_row(E, V2);   // >= E * ld * 4 (also covers the blocked layout)
     long rows_per_pass = (long)(work_bytes / row_bytes);
     if (rows_per_pass < 1) return fail(FCMA_ENOMEM, "work buffer too small: %zu bytes < %zu per row", work_bytes, row_bytes);
     if (rows_per_pass > 256) rows_per_pass = (rows_per_pass / 256) * 256;  // whole GEMM tiles
@@ -2074,14 +2130,37 @@ static int run_pipeline(const void *rows_op, const void *cols_op, int precision,
     const bool mask_self = (flags & FCMA_FLAG_MASK_SELF) != 0;
     if (mask_self && !(normalise && fused))
         return fail(FCMA_EINVAL, "FCMA_FLAG_MASK_SELF needs the fused normalise+kernel path (E <= 64, power-of-two eps)");
+    // Blocked intermediate [E][T256][n][256]: every 256x256 pair tile of the GEMM is one contiguous 256 KB run
+    // (tools/store_bench.cu: 6.2 TB/s vs 4.5 TB/s for the strided [i][e][j] layout); the fused normalise+SYRK
+    // kernel gathers 1 KB pieces from it.  Needs the pair GEMM with the TMA-store epilogue.
+    // MEASURED (tools/ab_pipeline.py, 2048 rows, fp16x3): GEMM 4.40 -> 4.43 ms (bf16: 3.16 -> 3.03), but the gather
+    // costs the normalise+SYRK kernel 2.28 -> 2.86 ms: a net loss, so the blocked layout is opt-in (FCMA_BLOCKED=1).
+    static const bool no_blocked = getenv("FCMA_BLOCKED") == nullptr || getenv("FCMA_GEMM_V1") != nullptr ||
+                                   getenv("FCMA_GEMM_NO_TMA_STORE") != nullptr || getenv("FCMA_GEMM_RESIDENT") != nullptr;
+    const long t256 = cdiv(V2, 256);
+    const bool blocked = !no_blocked && fused && V2 < (1L << 31);
     for (long done = 0; done < nb; done += rows_per_pass) {
         const long n = nb - done < rows_per_pass ? nb - done : rows_per_pass;
-        int rc = launch_corr_umma(rows_op, cols_op, precision, E, T, V, V2, start + done, n, work, (long)E * ld, ld,
+        int rc;
+        cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+        if (g_timing_on) {
+            for (int k = 0; k < 3; k++) CUDA_TRY(cudaEventCreate(&ev[k]));
+            CUDA_TRY(cudaEventRecord(ev[0], st));
+        }
+        if (blocked)
+            rc = launch_corr_umma(rows_op, cols_op, precision, E, T, V, V2, start + done, n, work, 4, 4,
+                                  fisher_in_gemm ? S_eps : 0, st, t256);
+        else
+            rc = launch_corr_umma(rows_op, cols_op, precision, E, T, V, V2, start + done, n, work, (long)E * ld, ld,
                                   fisher_in_gemm ? S_eps : 0, st);
         if (rc) return rc;
+        if (g_timing_on) CUDA_TRY(cudaEventRecord(ev[1], st));
         float *Kdst = sum_over_rows ? K : K + (size_t)done * E * E;
         const float beta = sum_over_rows ? 1.0f : 0.0f;
-        if (normalise && fused) {
+        if (blocked) {
+            rc = launch_norm_syrk(work, n, E, V2, 256, t256 * n * 256, normalise ? eps : 0, (normalise && fisher_in_gemm) ? 1 : 0,
+                                  mask_self ? start + done : -1, beta, Kdst, sum_over_rows, st, n * 256);
+        } else if (normalise && fused) {
             rc = launch_norm_syrk(work, n, E, V2, (long)E * ld, ld, eps, fisher_in_gemm ? 1 : 0,
                                   mask_self ? start + done : -1, beta, Kdst, sum_over_rows, st);
         } else {
@@ -2102,6 +2181,15 @@ static int run_pipeline(const void *rows_op, const void *cols_op, int precision,
                 rc = launch_syrk_simt(work, n, E, V2, (long)E * ld, ld, beta, Kdst, sum_over_rows, st);
         }
         if (rc) return rc;
+        if (g_timing_on) {
+            CUDA_TRY(cudaEventRecord(ev[2], st));
+            CUDA_TRY(cudaEventSynchronize(ev[2]));
+            float a = 0.f, b = 0.f;
+            CUDA_TRY(cudaEventElapsedTime(&a, ev[0], ev[1]));
+            CUDA_TRY(cudaEventElapsedTime(&b, ev[1], ev[2]));
+            g_t_gemm += a, g_t_syrk += b, g_t_passes++;
+            for (int k = 0; k < 3; k++) cudaEventDestroy(ev[k]);
+        }
     }
     return FCMA_OK;
 }

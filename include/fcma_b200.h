@@ -163,6 +163,12 @@ int fcma_host_voxel_kernels(const float *const *raw_host, const float *const *ra
 /* in-place host variants of the reference's native functions */
 int fcma_host_within_subject_norm(float *corr_host, long n0, int E, long n2, int eps, int device);
 
+/* per-kernel timing of the fused pipelines (CUDA events on the launch stream; synchronises each pass):
+ * enable(1) resets the accumulators; read() returns the number of passes and the summed milliseconds of
+ * the correlation GEMM (+ diagonal fix-up) and of the normalise+SYRK kernel */
+void fcma_timing_enable(int on);
+long fcma_timing_read(double *gemm_ms, double *syrk_ms);
+
 /* number of kernel launches issued by this library in the calling process (for bench accounting) */
 long fcma_launch_count(void);
 

@@ -47,7 +47,7 @@ def test_operand_geometry():
         2 * 32 * 50000 * 200 * 4 + 32 * 50000 * 4
     assert lib.fcma_operand_bytes(_lib.PREC["bf16"], 4, 50, 1000) == 4 * 1000 * 64 * 2 + 4 * 1000 * 4
     assert lib.fcma_operand_bytes(99, 4, 50, 1000) == 0
-    assert lib.fcma_work_bytes_per_row(32, 50000) == 32 * 50016 * 4
+    assert lib.fcma_work_bytes_per_row(32, 50000) == 32 * 50176 * 4     # [E][ceil(V2/256)][rows][256]
     assert engine.fused_supported(32, 8) and engine.fused_supported(64, 64)
     assert not engine.fused_supported(32, 3) and not engine.fused_supported(65, 8)
     assert not engine.fused_supported(32, 64)

@@ -208,7 +208,26 @@ class VoxelSelector:
     def _gather(self, local, rank, world):
         if world == 1:
             return list(local)
+        import torch
         import torch.distributed as dist
+        if dist.get_backend() == "nccl":
+            # NCCL moves tensors, not pickles: all-gather the (padded) per-shard accuracy vectors over
+            # NVLink on this rank's own device (voxel ids are implied by the static row partition)
+            dev = self._torch_device()
+            parts = self.row_partition(self.num_voxels, world)
+            per = max(n for _, n in parts)
+            mine = torch.full((per,), float("nan"), dtype=torch.float64, device=dev)
+            if local:
+                mine[:len(local)] = torch.tensor([a for _, a in local], dtype=torch.float64, device=dev)
+            allv = torch.empty((world, per), dtype=torch.float64, device=dev)
+            dist.all_gather_into_tensor(allv, mine)
+            if rank != self.master_rank:
+                return []
+            host = allv.cpu().numpy()
+            out = []
+            for r, (s0, n) in enumerate(parts):
+                out += [(int(s0 + k), host[r, k]) for k in range(n)]
+            return out
         gathered = [None] * world if rank == self.master_rank else None
         dist.gather_object(list(local), gathered, dst=self.master_rank)
         if rank != self.master_rank:

@@ -620,3 +620,20 @@ def test_voxel_selector_gpu_cv_equals_host_cv(dev, golden):
     a = VoxelSelector(labels, int(g["epsf"]), 4, raw, voxel_unit=32, process_num=0, gpu_cv=True).run(clf)
     b = VoxelSelector(labels, int(g["epsf"]), 4, raw, voxel_unit=32, process_num=0, gpu_cv=False).run(clf)
     assert a == b
+
+
+def test_voxel_selector_multi_gpu_nccl(dev):
+    """N>1 product path (NCCL broadcast of the epochs, static row shards, all-gather of the scores):
+    runs tools/run_vs_multi.py under torchrun when the box has >= 2 GPUs."""
+    import os
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs (covered on CPU by tests/test_distributed_cpu.py with gloo)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29533",
+                          os.path.join(root, "tools", "run_vs_multi.py")],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "multi-GPU == single-GPU result: OK" in out.stdout

@@ -1,0 +1,46 @@
+#!/usr/bin/env python
+"""torchrun --nproc-per-node N tools/run_vs_multi.py : VoxelSelector.run over NCCL on N GPUs, checked
+against the single-GPU result computed on rank 0."""
+import os, sys, time
+import numpy as np
+import torch
+import torch.distributed as dist
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from sklearn import svm
+from brainiak_b200.fcma import synthetic
+from brainiak_b200.fcma.preprocessing import broadcast_epochs
+from brainiak_b200.fcma.voxelselector import VoxelSelector
+
+local = int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+rank, world = dist.get_rank(), dist.get_world_size()
+V, T, E, eps = 3000, 64, 16, 4
+# rank 0 owns the data; the others receive it over NCCL (the reference's comm.bcast, preprocessing.py:211-223)
+ep = torch.empty((E, T, V), dtype=torch.float32, device="cuda")
+labels = synthetic.make_labels(E)
+if rank == 0:
+    raw, _ = synthetic.make_epochs(V, T, E, informative=30, signal=1.0)
+    ep.copy_(torch.from_numpy(np.stack(raw)))
+broadcast_epochs(ep, src=0)
+raw_all = [m for m in ep.cpu().numpy()]
+clf = svm.SVC(kernel="precomputed", shrinking=False, C=1)
+t0 = time.time()
+res = VoxelSelector(labels, eps, 4, raw_all, master_rank=0).run(clf)
+dt = time.time() - t0
+if rank == 0:
+    assert len(res) == V and sorted(v for v, _ in res) == list(range(V))
+    os.environ.pop("LOCAL_RANK", None)
+    ok = res[:30]
+    print("world", world, "run %.3f s" % dt, "top voxels planted:", sum(1 for v, _ in res[:30] if v < 30), "/ 30", flush=True)
+else:
+    assert res == []
+dist.barrier()
+# single-process reference on rank 0 (no process group semantics: temporarily pretend world == 1)
+if rank == 0:
+    VoxelSelector._world = staticmethod(lambda: (0, 1))
+    single = VoxelSelector(labels, eps, 4, raw_all).run(clf)
+    assert single == res, "multi-GPU result differs from the single-GPU result"
+    print("multi-GPU == single-GPU result: OK", flush=True)
+dist.barrier()
+dist.destroy_process_group()

@@ -328,26 +328,14 @@ __global__ void __launch_bounds__(256) k_epoch_normalize(float *data, int T, lon
 }
 
 // ============================================================================================
-// a4 on tensor cores: persistent, warp-specialised TMA -> tcgen05.mma -> TMEM -> coalesced stores
+// a4 on tensor cores: persistent, warp-specialised TMA -> tcgen05.mma.cta_group::2 -> TMEM -> TMA store
 // ============================================================================================
-// D tile = 128 columns j (UMMA M side, TMEM lanes) x BN rows i (UMMA N side, TMEM columns): with the
-// all-voxel side on the lanes, a warp's 32 lanes hold 32 consecutive j of one output row, so the
-// epilogue stores straight from registers as full 128-byte lines of out[i][e][j..j+31].
-struct GemmParams {
-    int E, Kp, bk, umma_k, kbs;      // kbs = k-blocks per segment
-    int segs, seg_r[3], seg_c[3];
-    long V2, nb, row_start;
-    int BN;                          // rows (i) per tile: 32..256, multiple of 32
-    int tiles_j, tiles_i;
-    long total_tiles;
-    float *out;
-    long stride_i, stride_e;
-    int fisher_epochs;
-    uint32_t stage_bytes_c, stage_bytes_r;
-    int stages;
-    int fmt;          // idesc operand format
-    float out_scale;  // accumulator scale applied in the epilogue (undoes operand pre-scaling)
-};
+// Per CTA the D tile = 128 columns j (UMMA M side, TMEM lanes) x BN rows i (UMMA N side, TMEM columns): with
+// the all-voxel side on the lanes, a warp's 32 lanes hold 32 consecutive j of one output row, so a 32x32
+// block goes to shared memory conflict-free and out as one TMA store (or, for unaligned outputs, straight
+// from registers as full 128-byte lines of out[i][e][j..j+31]).
+// (Round-1 history, see profiles/README.md: a single-CTA kernel and a resident-row-operand variant were
+// measured and dropped; git history has them.)
 
 constexpr int GEMM_THREADS = 384;  // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4..11 epilogue
 constexpr int GEMM_EPI_WARPS = 8;
@@ -383,195 +371,12 @@ __device__ __forceinline__ float fisher_fast(float r)
     return 0.34657359027997264f * (lg2_ftz(num) - lg2_ftz(den));
 }
 
-template <int KIND>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
-    k_corr_umma(const __grid_constant__ CUtensorMap tm_cols, const __grid_constant__ CUtensorMap tm_rows,
-                const GemmParams p)
-{
-    extern __shared__ __align__(1024) uint8_t smem_raw[];
-    // dynamic smem base is only guaranteed 16-byte aligned: align to 1024 for SWIZZLE_128B
-    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const uint32_t stage_bytes = p.stage_bytes_c + p.stage_bytes_r;
-    uint8_t *tiles = smem;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)p.stages * stage_bytes);
-    uint64_t *full_bar = bars;                           // [stages]
-    uint64_t *empty_bar = bars + GEMM_MAX_STAGES;        // [stages]
-    uint64_t *tfull_bar = bars + 2 * GEMM_MAX_STAGES;    // [2]
-    uint64_t *tempty_bar = tfull_bar + 2;                // [2]
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty_bar + 2);
-
-    const int warp = threadIdx.x >> 5;
-    const int lane = threadIdx.x & 31;
-
-    if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&tm_cols);
-        tma_prefetch_desc(&tm_rows);
-    }
-    if (warp == 1 && lane == 0) {
-        for (int s = 0; s < p.stages; s++) {
-            mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], 1);
-        }
-        for (int s = 0; s < 2; s++) {
-            mbar_init(&tfull_bar[s], 1);
-            mbar_init(&tempty_bar[s], GEMM_EPI_WARPS);
-        }
-        fence_mbar_init();
-    }
-    if (warp == 2) {
-        tmem_alloc(tmem_slot, 512);
-        tmem_relinquish();
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    const int nkb = p.segs * p.kbs;
-    const long tiles_per_e = (long)p.tiles_j * p.tiles_i;
-
-    if (warp == 0) {
-        // ------------------------------------------------------------------ TMA producer
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            for (long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-                const int e = (int)(tile / tiles_per_e);
-                const long rem = tile - (long)e * tiles_per_e;
-                const int tj = (int)(rem / p.tiles_i);
-                const int ti = (int)(rem - (long)tj * p.tiles_i);
-                for (int kb = 0; kb < nkb; kb++) {
-                    const int seg = kb / p.kbs;
-                    const int k0 = (kb - seg * p.kbs) * p.bk;
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
-                    mbar_expect_tx(&full_bar[stage], stage_bytes);
-                    uint8_t *sc = tiles + (size_t)stage * stage_bytes;
-                    uint8_t *sr = sc + p.stage_bytes_c;
-                    tma_load_3d(&tm_cols, &full_bar[stage], sc, k0, tj * 128, p.seg_c[seg] * p.E + e);
-                    tma_load_3d(&tm_rows, &full_bar[stage], sr, k0, (int)(p.row_start + (long)ti * p.BN),
-                                p.seg_r[seg] * p.E + e);
-                    if (++stage == p.stages) {
-                        stage = 0;
-                        phase ^= 1;
-                    }
-                }
-            }
-        }
-    } else if (warp == 1) {
-        // ------------------------------------------------------------------ MMA issuer (one thread)
-        const uint32_t idesc = make_idesc(p.fmt, 128, (uint32_t)p.BN);
-        int stage = 0;
-        uint32_t phase = 0;
-        long iter = 0;
-        for (long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, iter++) {
-            const int as = (int)(iter & 1);
-            const uint32_t aphase = (uint32_t)((iter >> 1) & 1);
-            mbar_wait(&tempty_bar[as], aphase ^ 1);
-            tc_fence_after();
-            const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.BN);
-            for (int kb = 0; kb < nkb; kb++) {
-                const int k0 = (kb % p.kbs) * p.bk;
-                mbar_wait(&full_bar[stage], phase);
-                tc_fence_after();
-                if (lane == 0) {
-                    const uint32_t sc = smem_u32(tiles + (size_t)stage * stage_bytes);
-                    const uint64_t dc = make_smem_desc_sw128(sc);
-                    const uint64_t dr = make_smem_desc_sw128(sc + p.stage_bytes_c);
-                    int rem_k = p.Kp - k0;
-                    const int nk = (rem_k < p.bk ? rem_k : p.bk) / p.umma_k;
-                    for (int k = 0; k < nk; k++) {
-                        // advance 32 bytes (one UMMA_K slice) inside the 128-byte swizzle row
-                        tc_mma<KIND>(d_tmem, dc + (uint64_t)(k * 2), dr + (uint64_t)(k * 2), idesc,
-                                     (uint32_t)((kb | k) != 0));
-                    }
-                    tc_commit(&empty_bar[stage]);            // smem slot free once these MMAs retire
-                    if (kb == nkb - 1) tc_commit(&tfull_bar[as]);  // accumulator ready for the epilogue
-                }
-                __syncwarp();
-                if (++stage == p.stages) {
-                    stage = 0;
-                    phase ^= 1;
-                }
-            }
-        }
-    } else if (warp >= 4) {
-        // ------------------------------------------------------------------ epilogue (8 warps)
-        const int ew = warp - 4;
-        const int q = warp & 3;        // TMEM lane quarter this warp may access
-        const int half = ew >> 2;      // two warps per quarter split the 32-column chunks
-        long iter = 0;
-        for (long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, iter++) {
-            const int e = (int)(tile / tiles_per_e);
-            const long rem = tile - (long)e * tiles_per_e;
-            const int tj = (int)(rem / p.tiles_i);
-            const int ti = (int)(rem - (long)tj * p.tiles_i);
-            const int as = (int)(iter & 1);
-            const uint32_t aphase = (uint32_t)((iter >> 1) & 1);
-            mbar_wait(&tfull_bar[as], aphase);
-            tc_fence_after();
-            const long j = (long)tj * 128 + q * 32 + lane;
-            const bool jok = j < p.V2;
-            const bool do_fisher = e < p.fisher_epochs;
-            const float osc = p.out_scale;
-            const long i0 = (long)ti * p.BN;
-            float *obase = p.out + (size_t)e * p.stride_e + j;
-            const int nchunks = p.BN >> 5;
-            for (int c = half; c < nchunks; c += 2) {
-                const long ic = i0 + c * 32;
-                if (ic >= p.nb) break;  // warp-uniform
-                uint32_t v[32];
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.BN + c * 32);
-                tmem_ld32(taddr, v);
-                tmem_ld_wait();
-                if (jok) {
-                    float *ptr = obase + (size_t)ic * p.stride_i;
-                    if (ic + 32 <= p.nb) {  // warp-uniform: full chunk, no per-row predicates
-                        if (do_fisher) {
-#pragma unroll
-                            for (int r = 0; r < 32; r++) {
-                                *ptr = fisher_fast(__uint_as_float(v[r]) * osc);
-                                ptr += p.stride_i;
-                            }
-                        } else {
-#pragma unroll
-                            for (int r = 0; r < 32; r++) {
-                                *ptr = __uint_as_float(v[r]) * osc;
-                                ptr += p.stride_i;
-                            }
-                        }
-                    } else {
-#pragma unroll
-                        for (int r = 0; r < 32; r++) {
-                            if (ic + r < p.nb) {
-                                float x = __uint_as_float(v[r]) * osc;
-                                if (do_fisher) x = fisher_fast(x);
-                                *ptr = x;
-                            }
-                            ptr += p.stride_i;
-                        }
-                    }
-                }
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[as]);
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 2) {
-        tc_fence_after();
-        tmem_dealloc(tmem_base, 512);
-    }
-}
-
-
-// ---------------------------------------------------------------- v2: CTA pairs (cta_group::2)
+// ---------------------------------------------------------------- CTA pairs (cta_group::2)
 // Two CTAs of a cluster (one TPC) compute a 256 (columns j) x BN (rows i) tile: each CTA owns 128
 // columns (its TMEM lanes) and stages only HALF of the row operand; tcgen05.mma.cta_group::2 reads
 // both halves.  In the 3-product modes one stage carries {cols_hi, cols_lo, rows_hi, rows_lo} of a
 // k-block and feeds all three products, so every operand byte crosses L2->SMEM once per tile:
-// 64 KB per CTA per 12 MMAs instead of 144 KB with single-CTA tiles (the v1 kernel is L2-bound).
+// 64 KB per CTA per 12 MMAs instead of 144 KB with single-CTA tiles.
 struct Gemm2Params {
     int E, Kp, bk, umma_k, kbs;
     int segs, seg_r[3], seg_c[3], planes;
@@ -821,260 +626,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 }
 
 
-// ---------------------------------------------------------------- v3: CTA pairs + resident row operand
-// Measured (profiles/): k_corr_umma2 runs at (operand L2->SMEM reads + block writes) / ~7 TB/s, i.e. it
-// is bound by L2 throughput, not by the tensor pipe.  For the 16-bit operand modes the whole-K row
-// operand of a pair (256 rows x Kp x planes, half per CTA: <= 128 KB) fits in shared memory next to a
-// 3-stage ring for the column operand, so a pair keeps one row tile RESIDENT and sweeps a range of
-// 256-column tiles past it: operand traffic per tile halves (only the column operand streams).
-// Work unit = (epoch, column-tile range, row tile); units round-robin over the pairs with the row
-// tile index fastest, so concurrently running pairs stream the same column tiles out of L2.
-struct Gemm3Params {
-    int E, Kp, bk, umma_k, kbs;
-    int segs, seg_r[3], seg_c[3], planes;
-    long V2, nb, row_start;
-    int BN;
-    int tiles_j, tiles_i;          // 256-column tiles, BN-row tiles
-    int cj;                        // column tiles per unit
-    int nchunk;                    // ceil(tiles_j / cj)
-    long total_units;              // E * nchunk * tiles_i
-    float *out;
-    long stride_i, stride_e;
-    int fisher_epochs;
-    uint32_t half_bytes;           // (BN/2) * 128: one resident (k-block, plane) tile per CTA
-    uint32_t res_bytes;            // kbs * planes * half_bytes
-    uint32_t stage_bytes;          // planes * 16384 (column operand only)
-    int stages;
-    int fmt;
-    float out_scale;
-};
-
-template <int KIND>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
-    k_corr_umma3(const __grid_constant__ CUtensorMap tm_cols, const __grid_constant__ CUtensorMap tm_rows,
-                 const Gemm3Params p)
-{
-    extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t *resident = smem;                                   // [kbs][planes][BN/2 rows][128 B]
-    uint8_t *tiles = smem + p.res_bytes;                        // [stages][planes][128 rows][128 B]
-    uint64_t *bars = reinterpret_cast<uint64_t *>(tiles + (size_t)p.stages * p.stage_bytes);
-    uint64_t *full_bar = bars;                         // [stages]  leader only
-    uint64_t *empty_bar = bars + GEMM_MAX_STAGES;      // [stages]  per CTA
-    uint64_t *tfull_bar = bars + 2 * GEMM_MAX_STAGES;  // [2]       per CTA
-    uint64_t *tempty_bar = tfull_bar + 2;              // [2]       leader only
-    uint64_t *rfull_bar = tempty_bar + 2;              // [1]       leader only: resident rows landed
-    uint64_t *rempty_bar = rfull_bar + 1;              // [1]       per CTA: unit's MMAs retired
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(rempty_bar + 1);
-
-    const int warp = threadIdx.x >> 5;
-    const int lane = threadIdx.x & 31;
-    const uint32_t rank = cluster_ctarank();
-    const bool leader = rank == 0;
-
-    cluster_sync_all();
-    if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&tm_cols);
-        tma_prefetch_desc(&tm_rows);
-    }
-    if (warp == 1 && lane == 0) {
-        for (int s = 0; s < p.stages; s++) {
-            mbar_init(&full_bar[s], 2);
-            mbar_init(&empty_bar[s], 1);
-        }
-        for (int s = 0; s < 2; s++) {
-            mbar_init(&tfull_bar[s], 1);
-            mbar_init(&tempty_bar[s], 2 * GEMM_EPI_WARPS);
-        }
-        mbar_init(rfull_bar, 2);
-        mbar_init(rempty_bar, 1);
-        fence_mbar_init();
-    }
-    if (warp == 2) {
-        tmem_alloc_2sm(tmem_slot, 512);
-        tmem_relinquish_2sm();
-    }
-    tc_fence_before();
-    cluster_sync_all();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    const long pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
-    const int halfN = p.BN >> 1;
-    const long units_per_e = (long)p.nchunk * p.tiles_i;
-
-    if (warp == 0) {
-        // ------------------------------------------------------------------ TMA producer (both CTAs)
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0, rphase = 0;
-            for (long unit = pair; unit < p.total_units; unit += npairs) {
-                const int e = (int)(unit / units_per_e);
-                const long rem = unit - (long)e * units_per_e;
-                const int chunk = (int)(rem / p.tiles_i);
-                const int ti = (int)(rem - (long)chunk * p.tiles_i);
-                const int tj0 = chunk * p.cj;
-                const int tj1 = tj0 + p.cj < p.tiles_j ? tj0 + p.cj : p.tiles_j;
-                const int row0 = (int)(p.row_start + (long)ti * p.BN + (long)rank * halfN);
-                // resident row operand: whole K, every plane
-                mbar_wait(rempty_bar, rphase ^ 1);
-                if (leader)
-                    mbar_expect_tx(rfull_bar, 2 * p.res_bytes);
-                else
-                    mbar_arrive_cluster(rfull_bar, 0);
-                for (int kb = 0; kb < p.kbs; kb++)
-                    for (int pl = 0; pl < p.planes; pl++)
-                        tma_load_3d_2sm(&tm_rows, rfull_bar, resident + (size_t)(kb * p.planes + pl) * p.half_bytes,
-                                        kb * p.bk, row0, pl * p.E + e);
-                rphase ^= 1;
-                for (int tj = tj0; tj < tj1; tj++) {
-                    const int col0 = tj * 256 + (int)rank * 128;
-                    for (int kb = 0; kb < p.kbs; kb++) {
-                        mbar_wait(&empty_bar[stage], phase ^ 1);
-                        if (leader)
-                            mbar_expect_tx(&full_bar[stage], 2 * p.stage_bytes);
-                        else
-                            mbar_arrive_cluster(&full_bar[stage], 0);
-                        uint8_t *base = tiles + (size_t)stage * p.stage_bytes;
-                        for (int pl = 0; pl < p.planes; pl++)
-                            tma_load_3d_2sm(&tm_cols, &full_bar[stage], base + pl * 16384, kb * p.bk, col0,
-                                            pl * p.E + e);
-                        if (++stage == p.stages) {
-                            stage = 0;
-                            phase ^= 1;
-                        }
-                    }
-                }
-            }
-        }
-    } else if (warp == 1) {
-        // ------------------------------------------------------------------ MMA issuer (leader CTA only)
-        if (leader) {
-            const uint32_t idesc = make_idesc(p.fmt, 256, (uint32_t)p.BN);
-            const uint32_t res_addr = smem_u32(resident);
-            int stage = 0;
-            uint32_t phase = 0, rphase = 0;
-            long iter = 0;
-            for (long unit = pair; unit < p.total_units; unit += npairs) {
-                const long rem = unit % units_per_e;
-                const int chunk = (int)(rem / p.tiles_i);
-                const int tj0 = chunk * p.cj;
-                const int tj1 = tj0 + p.cj < p.tiles_j ? tj0 + p.cj : p.tiles_j;
-                mbar_wait(rfull_bar, rphase);
-                rphase ^= 1;
-                tc_fence_after();
-                for (int tj = tj0; tj < tj1; tj++, iter++) {
-                    const int as = (int)(iter & 1);
-                    const uint32_t aphase = (uint32_t)((iter >> 1) & 1);
-                    mbar_wait(&tempty_bar[as], aphase ^ 1);
-                    tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.BN);
-                    for (int kb = 0; kb < p.kbs; kb++) {
-                        const int k0 = kb * p.bk;
-                        mbar_wait(&full_bar[stage], phase);
-                        tc_fence_after();
-                        if (lane == 0) {
-                            const uint32_t base = smem_u32(tiles + (size_t)stage * p.stage_bytes);
-                            const uint32_t rbase = res_addr + (uint32_t)(kb * p.planes) * p.half_bytes;
-                            int rem_k = p.Kp - k0;
-                            const int nk = (rem_k < p.bk ? rem_k : p.bk) / p.umma_k;
-                            for (int sgm = 0; sgm < p.segs; sgm++) {
-                                const uint64_t dc = make_smem_desc_sw128(base + p.seg_c[sgm] * 16384);
-                                const uint64_t dr = make_smem_desc_sw128(rbase + p.seg_r[sgm] * p.half_bytes);
-                                for (int k = 0; k < nk; k++)
-                                    tc_mma_2sm<KIND>(d_tmem, dc + (uint64_t)(k * 2), dr + (uint64_t)(k * 2), idesc,
-                                                     (uint32_t)((kb | sgm | k) != 0));
-                            }
-                            tc_commit_2sm(&empty_bar[stage]);
-                            if (kb == p.kbs - 1) {
-                                tc_commit_2sm(&tfull_bar[as]);
-                                if (tj == tj1 - 1) tc_commit_2sm(rempty_bar);  // resident tile may be replaced
-                            }
-                        }
-                        __syncwarp();
-                        if (++stage == p.stages) {
-                            stage = 0;
-                            phase ^= 1;
-                        }
-                    }
-                }
-            }
-        }
-    } else if (warp >= 4) {
-        // ------------------------------------------------------------------ epilogue (both CTAs)
-        const int ew = warp - 4;
-        const int q = warp & 3;
-        const int half = ew >> 2;
-        long iter = 0;
-        for (long unit = pair; unit < p.total_units; unit += npairs) {
-            const int e = (int)(unit / units_per_e);
-            const long rem = unit - (long)e * units_per_e;
-            const int chunk = (int)(rem / p.tiles_i);
-            const int ti = (int)(rem - (long)chunk * p.tiles_i);
-            const int tj0 = chunk * p.cj;
-            const int tj1 = tj0 + p.cj < p.tiles_j ? tj0 + p.cj : p.tiles_j;
-            const bool do_fisher = e < p.fisher_epochs;
-            const float osc = p.out_scale;
-            const long i0 = (long)ti * p.BN;
-            const int nchunks = p.BN >> 5;
-            for (int tj = tj0; tj < tj1; tj++, iter++) {
-                const int as = (int)(iter & 1);
-                const uint32_t aphase = (uint32_t)((iter >> 1) & 1);
-                mbar_wait(&tfull_bar[as], aphase);
-                tc_fence_after();
-                const long j = (long)tj * 256 + (long)rank * 128 + q * 32 + lane;
-                const bool jok = j < p.V2;
-                float *obase = p.out + (size_t)e * p.stride_e + j;
-                for (int c = half; c < nchunks; c += 2) {
-                    const long ic = i0 + c * 32;
-                    if (ic >= p.nb) break;
-                    uint32_t v[32];
-                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.BN + c * 32);
-                    tmem_ld32(taddr, v);
-                    tmem_ld_wait();
-                    if (jok) {
-                        float *ptr = obase + (size_t)ic * p.stride_i;
-                        if (ic + 32 <= p.nb) {
-                            if (do_fisher) {
-#pragma unroll
-                                for (int r = 0; r < 32; r++) {
-                                    *ptr = fisher_fast(__uint_as_float(v[r]) * osc);
-                                    ptr += p.stride_i;
-                                }
-                            } else {
-#pragma unroll
-                                for (int r = 0; r < 32; r++) {
-                                    *ptr = __uint_as_float(v[r]) * osc;
-                                    ptr += p.stride_i;
-                                }
-                            }
-                        } else {
-#pragma unroll
-                            for (int r = 0; r < 32; r++) {
-                                if (ic + r < p.nb) {
-                                    float x = __uint_as_float(v[r]) * osc;
-                                    if (do_fisher) x = fisher_fast(x);
-                                    *ptr = x;
-                                }
-                                ptr += p.stride_i;
-                            }
-                        }
-                    }
-                }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(&tempty_bar[as], 0);
-            }
-        }
-    }
-    tc_fence_before();
-    cluster_sync_all();
-    if (warp == 2) {
-        tc_fence_after();
-        tmem_dealloc_2sm(tmem_base, 512);
-    }
-}
-
 // ---------------------------------------------------------------- tensor-map creation (driver entry point)
 typedef CUresult (*PFN_tmEncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                       const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
@@ -1162,7 +713,7 @@ static int make_out_map_blocked(CUtensorMap *m, float *out, int E, long nb, long
     return FCMA_OK;
 }
 
-// blocked_t256 > 0: write the block in the blocked layout [E][blocked_t256][nb][256] (pair kernel + TMA store only)
+// blocked_t256 > 0: write the block in the blocked layout [E][blocked_t256][nb][256] (TMA-store epilogue only)
 static int launch_corr_umma(const void *rows_op, const void *cols_op, int precision, int E, int T, long V, long V2,
                             long start, long nb, float *out, long stride_i, long stride_e, int fisher_epochs,
                             cudaStream_t st, long blocked_t256 = 0)
@@ -1173,158 +724,66 @@ static int launch_corr_umma(const void *rows_op, const void *cols_op, int precis
         return fail(FCMA_EINVAL, "bad shape E=%d T=%d V=%ld V2=%ld start=%ld nb=%ld", E, T, V, V2, start, nb);
     if (((uintptr_t)rows_op & 15) || ((uintptr_t)cols_op & 15))
         return fail(FCMA_EINVAL, "packed operands must be 16-byte aligned");
-    if (V >= (1L << 31) || V2 >= (1L << 31)) return fail(FCMA_EINVAL, "voxel count exceeds TMA coordinate range");
+    if (V >= (1L << 31) || V2 >= (1L << 31) || nb >= (1L << 31))
+        return fail(FCMA_EINVAL, "voxel count exceeds TMA coordinate range");
     const int Kp = fcma_operand_kp(precision, T);
-    GemmParams p;
-    memset(&p, 0, sizeof(p));
-    p.E = E;
-    p.Kp = Kp;
-    p.bk = pi.bk;
-    p.umma_k = pi.umma_k;
-    p.kbs = (int)cdiv(Kp, pi.bk);
-    p.segs = pi.segs;
-    for (int s = 0; s < 3; s++) {
-        p.seg_r[s] = pi.seg_r[s];
-        p.seg_c[s] = pi.seg_c[s];
-    }
-    p.V2 = V2;
-    p.nb = nb;
-    p.row_start = start;
-    p.BN = nb >= 256 ? 256 : (int)round_up(nb, 32);
-    p.tiles_j = (int)cdiv(V2, 128);
-    p.tiles_i = (int)cdiv(nb, p.BN);
-    p.total_tiles = (long)p.tiles_j * p.tiles_i * E;
-    p.out = out;
-    p.stride_i = stride_i;
-    p.stride_e = stride_e;
-    p.fisher_epochs = fisher_epochs;
-    p.fmt = pi.fmt;
-    p.out_scale = 1.0f / (pi.in_scale * pi.in_scale);
-    p.stage_bytes_c = 128 * 128;
-    p.stage_bytes_r = (uint32_t)p.BN * 128;
-    const size_t budget = 200 * 1024;
-    int stages = (int)(budget / (p.stage_bytes_c + p.stage_bytes_r));
+
+    Gemm2Params q;
+    memset(&q, 0, sizeof(q));
+    q.E = E, q.Kp = Kp, q.bk = pi.bk, q.umma_k = pi.umma_k, q.kbs = (int)cdiv(Kp, pi.bk);
+    q.segs = pi.segs, q.planes = pi.planes;
+    for (int sgm = 0; sgm < 3; sgm++) q.seg_r[sgm] = pi.seg_r[sgm], q.seg_c[sgm] = pi.seg_c[sgm];
+    q.V2 = V2, q.nb = nb, q.row_start = start;
+    q.BN = nb >= 256 ? 256 : (int)round_up(nb, 32);
+    q.tiles_j = (int)cdiv(V2, 256), q.tiles_i = (int)cdiv(nb, q.BN);
+    q.total_tiles = (long)q.tiles_j * q.tiles_i * E;
+    q.out = out, q.stride_i = stride_i, q.stride_e = stride_e, q.fisher_epochs = fisher_epochs;
+    q.fmt = pi.fmt, q.out_scale = 1.0f / (pi.in_scale * pi.in_scale);
+    q.half_bytes = (uint32_t)(q.BN / 2) * 128;
+    q.stage_bytes = (uint32_t)pi.planes * (16384 + q.half_bytes);
+    // TMA-store epilogue needs 16-byte aligned rows of the output and 4 KB of staging per epilogue warp
+    static const bool no_tma_store = getenv("FCMA_GEMM_NO_TMA_STORE") != nullptr;
+    q.tma_store = (!no_tma_store && (stride_i % 4 == 0) && (stride_e % 4 == 0) && (((uintptr_t)out & 15) == 0)) ? 1 : 0;
+    q.blocked = blocked_t256 > 0 ? 1 : 0;
+    if (q.blocked && (!q.tma_store || blocked_t256 != q.tiles_j))
+        return fail(FCMA_EINVAL, "internal: blocked output needs the TMA-store epilogue and T256 == tiles_j");
+    const size_t staging_bytes = q.tma_store ? (size_t)GEMM_EPI_WARPS * 4096 : 0;
+    const size_t cap = 227 * 1024 - 1024 /*alignment slack*/ - 256 /*barriers*/;
+    int stages = (int)((cap - staging_bytes) / q.stage_bytes);
     if (stages > GEMM_MAX_STAGES) stages = GEMM_MAX_STAGES;
     if (stages < 2) return fail(FCMA_EINVAL, "internal: not enough shared memory for 2 stages");
-    p.stages = stages;
-    const size_t smem = (size_t)stages * (p.stage_bytes_c + p.stage_bytes_r) + 1024 /*align slack*/ + 256 /*barriers*/;
+    q.stages = stages;
+    const size_t smem = (size_t)stages * q.stage_bytes + staging_bytes + 1024 + 256;
+    {
+        const char *sched = getenv("FCMA_GEMM_SCHED");   // tuning knob: 1 = a pair takes all row tiles of a column tile
+        q.grp_tiles = (sched && sched[0] == '1') ? q.tiles_i : 1;
+    }
 
-    CUtensorMap tm_cols, tm_rows;
+    CUtensorMap tm_cols, tm_rows, tm_out;
     int rc = make_operand_map(&tm_cols, cols_op, pi, E, V2, Kp, 128);
     if (rc) return rc;
-    static const bool use_v1 = getenv("FCMA_GEMM_V1") != nullptr;
-    static const bool no_v3 = getenv("FCMA_GEMM_RESIDENT") == nullptr || blocked_t256 > 0;  // opt-in: no faster than v2
-    if (use_v1 && blocked_t256 > 0) return fail(FCMA_EINVAL, "internal: blocked output is not available with FCMA_GEMM_V1");
-    if (!use_v1 && !no_v3 && pi.esize == 2) {
-        // resident-row-operand kernel: needs kbs * planes * (BN/2 * 128) bytes + >= 2 column stages
-        Gemm3Params q;
-        memset(&q, 0, sizeof(q));
-        q.E = E, q.Kp = Kp, q.bk = pi.bk, q.umma_k = pi.umma_k, q.kbs = p.kbs;
-        q.segs = pi.segs, q.planes = pi.planes;
-        for (int sgm = 0; sgm < 3; sgm++) q.seg_r[sgm] = pi.seg_r[sgm], q.seg_c[sgm] = pi.seg_c[sgm];
-        q.V2 = V2, q.nb = nb, q.row_start = start, q.BN = p.BN;
-        q.tiles_j = (int)cdiv(V2, 256), q.tiles_i = p.tiles_i;
-        q.out = out, q.stride_i = stride_i, q.stride_e = stride_e, q.fisher_epochs = fisher_epochs;
-        q.fmt = pi.fmt, q.out_scale = p.out_scale;
-        q.half_bytes = (uint32_t)(p.BN / 2) * 128;
-        q.res_bytes = (uint32_t)p.kbs * pi.planes * q.half_bytes;
-        q.stage_bytes = (uint32_t)pi.planes * 16384;
-        const size_t cap = 227 * 1024 - 1024 - 512;
-        if (q.res_bytes + 2 * (size_t)q.stage_bytes <= cap) {
-            int st3 = (int)((cap - q.res_bytes) / q.stage_bytes);
-            if (st3 > GEMM_MAX_STAGES) st3 = GEMM_MAX_STAGES;
-            q.stages = st3;
-            const size_t smem3 = (size_t)q.res_bytes + (size_t)st3 * q.stage_bytes + 1024 + 512;
-            // units: split the column tiles so that there are >= ~6 units per pair (load balance) while a
-            // resident tile is reused for >= 16 column tiles (reload overhead <= ~5 %)
-            long pairs = g_sm_count / 2;
-            long base_units = (long)E * q.tiles_i;
-            int nchunk = (int)cdiv(6 * pairs, base_units);
-            if (nchunk < 1) nchunk = 1;
-            int cj = (int)cdiv(q.tiles_j, nchunk);
-            if (cj < 16) cj = q.tiles_j < 16 ? q.tiles_j : 16;
-            q.cj = cj;
-            q.nchunk = (int)cdiv(q.tiles_j, cj);
-            q.total_units = (long)E * q.nchunk * q.tiles_i;
-            if (q.total_units < pairs) pairs = q.total_units;
-            rc = make_operand_map(&tm_rows, rows_op, pi, E, V, Kp, p.BN / 2);
-            if (rc) return rc;
-            CUDA_TRY(cudaFuncSetAttribute(k_corr_umma3<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
-            k_corr_umma3<0><<<(unsigned)(2 * pairs), GEMM_THREADS, smem3, st>>>(tm_cols, tm_rows, q);
-            LAUNCH_CHECK("k_corr_umma3");
-            goto fixup;
-        }
-    }
-    if (!use_v1) {
-        Gemm2Params q;
-        memset(&q, 0, sizeof(q));
-        q.E = E, q.Kp = Kp, q.bk = pi.bk, q.umma_k = pi.umma_k, q.kbs = p.kbs;
-        q.segs = pi.segs, q.planes = pi.planes;
-        for (int sgm = 0; sgm < 3; sgm++) q.seg_r[sgm] = pi.seg_r[sgm], q.seg_c[sgm] = pi.seg_c[sgm];
-        q.V2 = V2, q.nb = nb, q.row_start = start, q.BN = p.BN;
-        q.tiles_j = (int)cdiv(V2, 256), q.tiles_i = p.tiles_i;
-        q.total_tiles = (long)q.tiles_j * q.tiles_i * E;
-        q.out = out, q.stride_i = stride_i, q.stride_e = stride_e, q.fisher_epochs = fisher_epochs;
-        q.fmt = pi.fmt, q.out_scale = p.out_scale;
-        q.half_bytes = (uint32_t)(p.BN / 2) * 128;
-        q.stage_bytes = (uint32_t)pi.planes * (16384 + q.half_bytes);
-        // TMA-store epilogue needs 16-byte aligned rows of the output and 4 KB of staging per warp
-        static const bool no_tma_store = getenv("FCMA_GEMM_NO_TMA_STORE") != nullptr;
-        q.tma_store = (!no_tma_store && (stride_i % 4 == 0) && (stride_e % 4 == 0) && (((uintptr_t)out & 15) == 0) &&
-                       V2 < (1L << 31) && nb < (1L << 31)) ? 1 : 0;
-        q.blocked = blocked_t256 > 0 ? 1 : 0;
-        if (q.blocked && (!q.tma_store || blocked_t256 != q.tiles_j))
-            return fail(FCMA_EINVAL, "internal: blocked output needs the TMA-store epilogue and T256 == tiles_j");
-        const size_t staging_bytes = q.tma_store ? (size_t)GEMM_EPI_WARPS * 4096 : 0;
-        const size_t cap2 = 227 * 1024 - 1024 - 256;
-        int st2 = (int)((cap2 - staging_bytes) / q.stage_bytes);
-        if (st2 > GEMM_MAX_STAGES) st2 = GEMM_MAX_STAGES;
-        if (st2 < 2) return fail(FCMA_EINVAL, "internal: not enough shared memory for 2 stages");
-        q.stages = st2;
-        const size_t smem2 = (size_t)st2 * q.stage_bytes + staging_bytes + 1024 + 256;
-        CUtensorMap tm_out;
-        if (q.blocked) {
-            rc = make_out_map_blocked(&tm_out, out, E, nb, blocked_t256);
-            if (rc) return rc;
-        } else if (q.tma_store) {
-            rc = make_out_map(&tm_out, out, V2, E, nb, stride_i, stride_e);
-            if (rc) return rc;
-        } else {
-            memset(&tm_out, 0, sizeof(tm_out));
-        }
-        rc = make_operand_map(&tm_rows, rows_op, pi, E, V, Kp, p.BN / 2);
-        if (rc) return rc;
-        long pairs = g_sm_count / 2;
-        {
-            const char *sched = getenv("FCMA_GEMM_SCHED");   // tuning knob: 1 = a pair takes all row tiles of a column tile
-            q.grp_tiles = (sched && sched[0] == '1') ? q.tiles_i : 1;
-        }
-        const long ngroups = q.total_tiles / q.grp_tiles;
-        if (ngroups < pairs) pairs = ngroups;
-        if (pi.kind == 0) {
-            CUDA_TRY(cudaFuncSetAttribute(k_corr_umma2<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-            k_corr_umma2<0><<<(unsigned)(2 * pairs), GEMM_THREADS, smem2, st>>>(tm_cols, tm_rows, tm_out, q);
-        } else {
-            CUDA_TRY(cudaFuncSetAttribute(k_corr_umma2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-            k_corr_umma2<1><<<(unsigned)(2 * pairs), GEMM_THREADS, smem2, st>>>(tm_cols, tm_rows, tm_out, q);
-        }
-        LAUNCH_CHECK("k_corr_umma2");
-        goto fixup;
-    }
-    rc = make_operand_map(&tm_rows, rows_op, pi, E, V, Kp, p.BN);
+    rc = make_operand_map(&tm_rows, rows_op, pi, E, V, Kp, q.BN / 2);
     if (rc) return rc;
-    {
-    long grid = p.total_tiles < g_sm_count ? p.total_tiles : g_sm_count;
+    if (q.blocked)
+        rc = make_out_map_blocked(&tm_out, out, E, nb, blocked_t256);
+    else if (q.tma_store)
+        rc = make_out_map(&tm_out, out, V2, E, nb, stride_i, stride_e);
+    else
+        memset(&tm_out, 0, sizeof(tm_out));
+    if (rc) return rc;
+
+    long pairs = g_sm_count / 2;
+    const long ngroups = q.total_tiles / q.grp_tiles;
+    if (ngroups < pairs) pairs = ngroups;
     if (pi.kind == 0) {
-        CUDA_TRY(cudaFuncSetAttribute(k_corr_umma<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_corr_umma<0><<<(unsigned)grid, GEMM_THREADS, smem, st>>>(tm_cols, tm_rows, p);
+        CUDA_TRY(cudaFuncSetAttribute(k_corr_umma2<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_corr_umma2<0><<<(unsigned)(2 * pairs), GEMM_THREADS, smem, st>>>(tm_cols, tm_rows, tm_out, q);
     } else {
-        CUDA_TRY(cudaFuncSetAttribute(k_corr_umma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_corr_umma<1><<<(unsigned)grid, GEMM_THREADS, smem, st>>>(tm_cols, tm_rows, p);
+        CUDA_TRY(cudaFuncSetAttribute(k_corr_umma2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_corr_umma2<1><<<(unsigned)(2 * pairs), GEMM_THREADS, smem, st>>>(tm_cols, tm_rows, tm_out, q);
     }
-    LAUNCH_CHECK("k_corr_umma");
-    }
-fixup:
+    LAUNCH_CHECK("k_corr_umma2");
+
     if (rows_op == cols_op && V == V2) {
         // self-correlation: replace the diagonal by the reference-exact values kept with the operand
         const float *sd = reinterpret_cast<const float *>(reinterpret_cast<const uint8_t *>(rows_op) +
@@ -2135,8 +1594,7 @@ static int run_pipeline(const void *rows_op, const void *cols_op, int precision,
     // kernel gathers 1 KB pieces from it.  Needs the pair GEMM with the TMA-store epilogue.
     // MEASURED (tools/ab_pipeline.py, 2048 rows, fp16x3): GEMM 4.40 -> 4.43 ms (bf16: 3.16 -> 3.03), but the gather
     // costs the normalise+SYRK kernel 2.28 -> 2.86 ms: a net loss, so the blocked layout is opt-in (FCMA_BLOCKED=1).
-    static const bool no_blocked = getenv("FCMA_BLOCKED") == nullptr || getenv("FCMA_GEMM_V1") != nullptr ||
-                                   getenv("FCMA_GEMM_NO_TMA_STORE") != nullptr || getenv("FCMA_GEMM_RESIDENT") != nullptr;
+    static const bool no_blocked = getenv("FCMA_BLOCKED") == nullptr || getenv("FCMA_GEMM_NO_TMA_STORE") != nullptr;
     const long t256 = cdiv(V2, 256);
     const bool blocked = !no_blocked && fused && V2 < (1L << 31);
     for (long done = 0; done < nb; done += rows_per_pass) {

@@ -1048,7 +1048,7 @@ __global__ void __launch_bounds__(256, (R == 4 ? 2 : 1))
     // every FLUSH chunks bounds the chain length (bias ~1e-6).  Every (row, col) has exactly one owner lane.
     [[maybe_unused]] float *s_part =
         reinterpret_cast<float *>(dyn_smem + (VEC ? (size_t)8 * 2 * 2 * R * 32 * sizeof(float4) : 0));
-    constexpr int FLUSH = 8;
+    constexpr int FLUSH = R == 4 ? 8 : 32;   // chunks between flushes (E > 32: atomics are dearer, flush less often)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, t = lane & 3;
     const int S_eps = EPS > 0 ? (E / EPS) * EPS : 0;  // epochs that get normalised
@@ -1082,10 +1082,28 @@ __global__ void __launch_bounds__(256, (R == 4 ? 2 : 1))
                     for (int c = 0; c < 4; c++) acc[mu][nu][c] = 0.f;
                 }
         };
+        auto flush_atomic = [&]() {
+#pragma unroll
+            for (int mu = 0; mu < MT; mu++)
+#pragma unroll
+                for (int nu = 0; nu < NT; nu++) {
+                    const int row0 = R * g + 2 * mu, row1 = row0 + 1;
+                    const int col0 = R * (2 * t) + nu, col1 = R * (2 * t + 1) + nu;
+                    atomicAdd(&s_K[row0 * EP + col0], acc[mu][nu][0]);
+                    atomicAdd(&s_K[row0 * EP + col1], acc[mu][nu][1]);
+                    atomicAdd(&s_K[row1 * EP + col0], acc[mu][nu][2]);
+                    atomicAdd(&s_K[row1 * EP + col1], acc[mu][nu][3]);
+#pragma unroll
+                    for (int c = 0; c < 4; c++) acc[mu][nu][c] = 0.f;
+                }
+        };
         if constexpr (R == 4) {
             float *part = s_part + warp * (EP * EP);
             for (int idx = lane; idx < EP * EP; idx += 32) part[idx] = 0.f;
             __syncwarp();
+        } else {
+            for (int idx = threadIdx.x; idx < EP * EP; idx += 256) s_K[idx] = 0.f;
+            __syncthreads();
         }
         // VEC path: cp.async double buffering into a per-warp staging tile (8 x 16 B per lane), so the
         // next chunk streams from HBM while this one is normalised and multiplied; zero fill covers
@@ -1128,7 +1146,10 @@ __global__ void __launch_bounds__(256, (R == 4 ? 2 : 1))
             cp_async_commit();
         }
 
-        for (long ch = warp; ch < nchunks; ch += 8) {
+        const long trips = (nchunks + 7) / 8;
+        for (long trip = 0; trip < trips; trip++) {
+            const long ch = warp + 8 * trip;
+            if (ch < nchunks) {
             const long j0 = ch * 32;
             float vals[R][2][4];
             if constexpr (VEC) {
@@ -1255,9 +1276,19 @@ __global__ void __launch_bounds__(256, (R == 4 ? 2 : 1))
                     for (int nu = 0; nu < NT; nu++)
                         mma_tf32_16x8x8(acc[mu][nu], tv[2 * mu][0][u], tv[2 * mu + 1][0][u], tv[2 * mu][1][u],
                                         tv[2 * mu + 1][1][u], tv[nu][0][u], tv[nu][1][u]);
+            }  // ch < nchunks
             if constexpr (R == 4) {
                 if (++since_flush == FLUSH) {
                     flush();
+                    since_flush = 0;
+                }
+            } else {
+                // R == 8: no shared memory left for per-warp partials: every FLUSH chunks a warp adds its
+                // MMA accumulators into the block's s_K with shared-memory atomics (round-to-nearest adds; the
+                // order in which the 8 warps arrive is not fixed, so the E > 32 kernels are reproducible only
+                // to fp32 rounding, ~1e-7 relative -- the E <= 32 path above is bit-reproducible)
+                if (++since_flush == FLUSH) {
+                    flush_atomic();
                     since_flush = 0;
                 }
             }
@@ -1275,30 +1306,8 @@ __global__ void __launch_bounds__(256, (R == 4 ? 2 : 1))
             }
             __syncthreads();
         } else {
-        __syncthreads();
-        for (int w = 0; w < 8; w++) {
-            if (warp == w) {
-#pragma unroll
-                for (int mu = 0; mu < MT; mu++)
-#pragma unroll
-                    for (int nu = 0; nu < NT; nu++) {
-                        const int row0 = R * g + 2 * mu, row1 = row0 + 1;
-                        const int col0 = R * (2 * t) + nu, col1 = R * (2 * t + 1) + nu;
-                        if (w == 0) {
-                            s_K[row0 * EP + col0] = acc[mu][nu][0];
-                            s_K[row0 * EP + col1] = acc[mu][nu][1];
-                            s_K[row1 * EP + col0] = acc[mu][nu][2];
-                            s_K[row1 * EP + col1] = acc[mu][nu][3];
-                        } else {
-                            s_K[row0 * EP + col0] += acc[mu][nu][0];
-                            s_K[row0 * EP + col1] += acc[mu][nu][1];
-                            s_K[row1 * EP + col0] += acc[mu][nu][2];
-                            s_K[row1 * EP + col1] += acc[mu][nu][3];
-                        }
-                    }
-            }
+            flush_atomic();
             __syncthreads();
-        }
         }
         // ---- write: symmetric by construction from the lower triangle (cython_blas.pyx:200-207)
         for (int idx = threadIdx.x; idx < E * E; idx += 256) {

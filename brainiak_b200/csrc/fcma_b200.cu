@@ -551,6 +551,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
             const long i0 = (long)ti * p.BN;
             float *obase = p.out + (size_t)e * p.stride_e + j;
             const int nchunks = p.BN >> 5;
+            bool released = false;
             for (int c = half; c < nchunks; c += 2) {
                 const long ic = i0 + c * 32;
                 if (ic >= p.nb) break;
@@ -558,6 +559,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.BN + c * 32);
                 tmem_ld32(taddr, v);
                 tmem_ld_wait();
+                // this warp's last chunk of the tile is now in registers: hand the accumulator stage back to
+                // the MMA issuer before the Fisher math / stores of that chunk (shortens the critical path)
+                const bool last_chunk = (c + 2 >= nchunks) || (ic + 64 >= p.nb);
+                if (last_chunk) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(&tempty_bar[as], 0);
+                    released = true;
+                }
                 if (p.tma_store) {
                     // registers -> 32x32 smem block (row i, lane = column j: conflict-free) -> one TMA
                     // store of box {32 j, 1 e, 32 i}; the TMA unit clips at V2 / nb and writes full lines
@@ -611,9 +621,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
                     }
                 }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(&tempty_bar[as], 0);  // accumulator slot free (leader's barrier)
+            if (!released) {   // warps that had no chunk in this tile (BN < 64 or ragged row tile)
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(&tempty_bar[as], 0);  // accumulator slot free (leader's barrier)
+            }
         }
     }
     if (p.tma_store && warp >= 4 && lane == 0) tma_store_wait_all();

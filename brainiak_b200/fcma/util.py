@@ -24,11 +24,17 @@ def compute_correlation(matrix1, matrix2, return_nans=False):
     _lib.load()
     _lib.require_device()
     dev = torch.device("cuda", torch.cuda.current_device())
+    same = matrix2 is matrix1 or (matrix1.shape == matrix2.shape and np.shares_memory(matrix1, matrix2))
     m1 = torch.from_numpy(np.ascontiguousarray(matrix1)).to(dev)
     engine.row_normalize_(m1, nan_to_zero=not return_nans)
-    if matrix2 is matrix1:
+    if same:
         m2 = m1
     else:
         m2 = torch.from_numpy(np.ascontiguousarray(matrix2)).to(dev)
         engine.row_normalize_(m2, nan_to_zero=not return_nans)
-    return np.ascontiguousarray(engine.gemm_nt(m1, m2).cpu().numpy())
+    # The normalised rows are one "epoch" of d time points x r voxels: the same tensor-core contraction
+    # as the FCMA correlation block (E = 1), fp32-faithful 3-product split; unit-norm rows keep |x| <= 1.
+    op1 = engine.pack_epochs(m1.t().contiguous().unsqueeze(0), None, "fp32")
+    op2 = op1 if same else engine.pack_epochs(m2.t().contiguous().unsqueeze(0), None, op1.precision)
+    corr = engine.corr_block(op1, op2, 0, r1, layout=0)          # [r1, 1, r2]
+    return np.ascontiguousarray(corr[:, 0, :].cpu().numpy())

@@ -339,7 +339,7 @@ __global__ void __launch_bounds__(256) k_epoch_normalize(float *data, int T, lon
 
 constexpr int GEMM_THREADS = 384;  // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4..11 epilogue
 constexpr int GEMM_EPI_WARPS = 8;
-constexpr int GEMM_MAX_STAGES = 8;
+constexpr int GEMM_MAX_STAGES = 12;
 
 __device__ __forceinline__ float rsqrt_ftz(float x)
 {
@@ -371,6 +371,24 @@ __device__ __forceinline__ float fisher_fast(float r)
     return 0.34657359027997264f * (lg2_ftz(num) - lg2_ftz(den));
 }
 
+// GEMM-epilogue Fisher-z, series form: atanh(r) = r + r^3/3 + ... + r^13/13 for |r| <= 0.35 (truncation
+// < 3e-8 relative; 9 FMA-pipe ops, no MUFU).  The epilogue takes it for a whole 32x32 chunk when no
+// element exceeds the bound (warp vote; r ~ N(0, 1/sqrt(T)) makes that the common case) and the
+// two-logarithm form with the reference's clamps otherwise.  The two XU ops per element of fisher_fast
+// were ~1/3 of the epilogue's time (profiles/README.md).
+constexpr float FISHER_SERIES_MAX = 0.35f;
+__device__ __forceinline__ float fisher_series(float r)
+{
+    const float x2 = r * r;
+    float p = 0.076923076923f;            // 1/13
+    p = fmaf(p, x2, 0.090909090909f);     // 1/11
+    p = fmaf(p, x2, 0.111111111111f);     // 1/9
+    p = fmaf(p, x2, 0.142857142857f);     // 1/7
+    p = fmaf(p, x2, 0.2f);
+    p = fmaf(p, x2, 0.333333333333f);
+    return fmaf(r * x2, p, r);
+}
+
 // ---------------------------------------------------------------- CTA pairs (cta_group::2)
 // Two CTAs of a cluster (one TPC) compute a 256 (columns j) x BN (rows i) tile: each CTA owns 128
 // columns (its TMEM lanes) and stages only HALF of the row operand; tcgen05.mma.cta_group::2 reads
@@ -394,8 +412,143 @@ struct Gemm2Params {
     int fmt;                       // idesc operand format
     float out_scale;               // accumulator scale applied in the epilogue
     int tma_store;                 // 1: epilogue stages 32x32 blocks in smem and issues TMA stores
-    int blocked;                   // 1: output is [E][tiles_j][nb][256] (needs tma_store); 0: strided [i][e][j]
+    int blocked;                   // 1: output is tiled [tiles_i][tiles_j][E][256][256] (needs tma_store); 0: strided [i][e][j]
+    // resident-row-operand kernel (k_corr_umma_res) only:
+    int cj, nchunk;                // column tiles per work unit, units per (epoch, row tile)
+    long total_units;              // E * nchunk * tiles_i
+    uint32_t res_bytes;            // kbs * planes * half_bytes: the pair's whole-K row operand, half per CTA
+    int debug;                     // FCMA_GEMM_DEBUG bit mask (diagnostics only; output is wrong when set):
+                                   //   1 no stores, 2 no TMEM load / math / smem fill, 4 no epilogue work at all
 };
+
+// MMAs of one (column tile, row tile) operand pair of a stage: up to 4 k-steps of 32 bytes inside the
+// 128-byte swizzle atom.  Called by ONE elected thread with warp-uniform arguments, so descriptors and
+// the UTCHMMA operands stay in uniform registers.
+template <int KIND>
+__device__ __forceinline__ void issue_kblock_mmas(uint32_t d_tmem, uint32_t addr_c, uint32_t addr_r, uint32_t idesc,
+                                                  int nk, uint32_t &accumulate)
+{
+    constexpr uint64_t DESC_HI = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+    uint64_t dc = DESC_HI | (uint64_t)(addr_c >> 4);   // == make_smem_desc_sw128(addr)
+    uint64_t dr = DESC_HI | (uint64_t)(addr_r >> 4);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {   // bk / umma_k == 4 for every operand format
+        if (k < nk) {
+            tc_mma_2sm<KIND>(d_tmem, dc, dr, idesc, accumulate);
+            accumulate = 1;
+            dc += 2, dr += 2;       // +32 bytes along K
+        }
+    }
+}
+
+// One accumulator tile of the pair GEMM: TMEM -> registers -> (Fisher) -> TMA store / STG.  Called by the
+// 8 epilogue warps of both CTAs; `iter` is the pair's running tile count (selects the TMEM stage).
+__device__ __forceinline__ void gemm_epilogue_tile(const Gemm2Params &p, const CUtensorMap *tm_out_p, float *staging,
+                                                   uint64_t *tfull_bar, uint64_t *tempty_bar, uint32_t tmem_base,
+                                                   int e, int tj, int ti, long iter, uint32_t rank, int warp, int lane)
+{
+    const int ew = warp - 4;
+    const int q = warp & 3;
+    const int half = ew >> 2;
+    const int as = (int)(iter & 1);
+    const uint32_t aphase = (uint32_t)((iter >> 1) & 1);
+    mbar_wait(&tfull_bar[as], aphase);
+    tc_fence_after();
+    const long j = (long)tj * 256 + (long)rank * 128 + q * 32 + lane;
+    const bool jok = j < p.V2;
+    const bool do_fisher = e < p.fisher_epochs;
+    const float osc = p.out_scale;
+    const long i0 = (long)ti * p.BN;
+    float *obase = p.out + (size_t)e * p.stride_e + j;
+    const int nchunks = p.BN >> 5;
+    bool released = false;
+    if (p.debug & 4) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(&tempty_bar[as], 0);
+        return;
+    }
+    for (int c = half; c < nchunks; c += 2) {
+        const long ic = i0 + c * 32;
+        if (ic >= p.nb) break;
+        uint32_t v[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.BN + c * 32);
+        if (!(p.debug & 2)) {
+            tmem_ld32(taddr, v);
+            tmem_ld_wait();
+        } else {
+#pragma unroll
+            for (int r = 0; r < 32; r++) v[r] = 0;
+        }
+        // this warp's last chunk of the tile is now in registers: hand the accumulator stage back to
+        // the MMA issuer before the Fisher math / stores of that chunk (shortens the critical path)
+        const bool last_chunk = (c + 2 >= nchunks) || (ic + 64 >= p.nb);
+        if (last_chunk) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(&tempty_bar[as], 0);
+            released = true;
+        }
+        // scale + Fisher-z in registers (all 32 lanes together: fisher_row votes)
+        if (do_fisher) {
+            float m = 0.f;   // max |accumulator| of this lane's 32 rows (NaNs drop out and propagate below)
+#pragma unroll
+            for (int r = 0; r < 32; r++) m = fmaxf(m, fabsf(__uint_as_float(v[r])));
+            if (__any_sync(0xffffffffu, m * osc > FISHER_SERIES_MAX)) {
+#pragma unroll
+                for (int r = 0; r < 32; r++) v[r] = __float_as_uint(fisher_fast(__uint_as_float(v[r]) * osc));
+            } else {
+#pragma unroll
+                for (int r = 0; r < 32; r++) v[r] = __float_as_uint(fisher_series(__uint_as_float(v[r]) * osc));
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < 32; r++) v[r] = __float_as_uint(__uint_as_float(v[r]) * osc);
+        }
+        if (p.tma_store) {
+            // registers -> 32x32 smem block (row i, lane = column j: conflict-free) -> one TMA
+            // store of box {32 j, 1 e, 32 i}; the TMA unit clips at V2 / nb and writes full lines
+            float *blk = staging + (size_t)ew * 1024;
+            if (lane == 0) tma_store_wait_read0();   // previous block of this warp has been read
+            __syncwarp();
+            if (!(p.debug & 2)) {
+#pragma unroll
+                for (int r = 0; r < 32; r++) blk[r * 32 + lane] = __uint_as_float(v[r]);
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0 && !(p.debug & 1)) {
+                if (p.blocked)   // box {32 j_local, 32 i_local, 1 tile}: the pair's tile is one contiguous 256 KB run
+                    tma_store_3d(tm_out_p, blk, (int)rank * 128 + q * 32, c * 32, (ti * p.tiles_j + tj) * p.E + e);
+                else
+                    tma_store_3d(tm_out_p, blk, (int)(j - lane), e, (int)ic);
+                tma_store_commit();
+            }
+            continue;
+        }
+        if (jok) {
+            float *ptr = obase + (size_t)ic * p.stride_i;
+            if (ic + 32 <= p.nb) {
+#pragma unroll
+                for (int r = 0; r < 32; r++) {
+                    *ptr = __uint_as_float(v[r]);
+                    ptr += p.stride_i;
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < 32; r++) {
+                    if (ic + r < p.nb) *ptr = __uint_as_float(v[r]);
+                    ptr += p.stride_i;
+                }
+            }
+        }
+    }
+    if (!released) {   // warps that had no chunk in this tile (BN < 64 or ragged row tile)
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(&tempty_bar[as], 0);  // accumulator slot free (leader's barrier)
+    }
+}
 
 template <int KIND>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
@@ -415,7 +568,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
     uint64_t *tempty_bar = tfull_bar + 2;              // [2]       used in the leader CTA only
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty_bar + 2);
 
-    const int warp = threadIdx.x >> 5;
+    const int warp = uniform_warp_idx();
     const int lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
     const bool leader = rank == 0;
@@ -443,7 +596,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
     tc_fence_before();
     cluster_sync_all();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // warp-uniform for the compiler
 
     const long tiles_per_e = (long)p.tiles_j * p.tiles_i;
     // A pair processes whole groups of tiles_i consecutive tiles (one 256-column operand tile x all
@@ -455,7 +608,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer (both CTAs)
-        if (lane == 0) {
+        if (elect_one_sync()) {
             int stage = 0;
             uint32_t phase = 0;
             for (long grp = pair; grp < ngroups; grp += npairs)
@@ -466,6 +619,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
                 const int ti = (int)(rem - (long)tj * p.tiles_i);
                 const int col0 = tj * 256 + (int)rank * 128;
                 const int row0 = (int)(p.row_start + (long)ti * p.BN + (long)rank * halfN);
+                if ((p.debug & 16) && tile != pair * p.grp_tiles) continue;   // diagnostics: MMA-only loop
                 for (int kb = 0; kb < p.kbs; kb++) {
                     const int k0 = kb * p.bk;
                     mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -491,6 +645,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
         // ------------------------------------------------------------------ MMA issuer (leader CTA only)
         if (leader) {
             const uint32_t idesc = make_idesc(p.fmt, 256, (uint32_t)p.BN);
+            const uint32_t tiles_addr = smem_u32(tiles);
             int stage = 0;
             uint32_t phase = 0;
             long iter = 0;
@@ -501,23 +656,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
                 mbar_wait(&tempty_bar[as], aphase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.BN);
+                uint32_t accumulate = 0;
                 for (int kb = 0; kb < p.kbs; kb++) {
-                    const int k0 = kb * p.bk;
-                    mbar_wait(&full_bar[stage], phase);
+                    const bool stale = (p.debug & 16) && iter != 0;
+                    if (!stale) mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
-                    if (lane == 0) {
-                        const uint32_t base = smem_u32(tiles + (size_t)stage * p.stage_bytes);
+                    if (elect_one_sync()) {
+                        const uint32_t base = tiles_addr + (uint32_t)stage * p.stage_bytes;
                         const uint32_t rbase = base + p.planes * 16384;
-                        int rem_k = p.Kp - k0;
+                        const int rem_k = p.Kp - kb * p.bk;
                         const int nk = (rem_k < p.bk ? rem_k : p.bk) / p.umma_k;
-                        for (int sgm = 0; sgm < p.segs; sgm++) {
-                            const uint64_t dc = make_smem_desc_sw128(base + p.seg_c[sgm] * 16384);
-                            const uint64_t dr = make_smem_desc_sw128(rbase + p.seg_r[sgm] * p.half_bytes);
-                            for (int k = 0; k < nk; k++)
-                                tc_mma_2sm<KIND>(d_tmem, dc + (uint64_t)(k * 2), dr + (uint64_t)(k * 2), idesc,
-                                                 (uint32_t)((kb | sgm | k) != 0));
-                        }
-                        tc_commit_2sm(&empty_bar[stage]);
+                        for (int sgm = 0; sgm < p.segs; sgm++)
+                            issue_kblock_mmas<KIND>(d_tmem, base + p.seg_c[sgm] * 16384,
+                                                    rbase + p.seg_r[sgm] * p.half_bytes, idesc, nk, accumulate);
+                        if (!stale) tc_commit_2sm(&empty_bar[stage]);
                         if (kb == p.kbs - 1) tc_commit_2sm(&tfull_bar[as]);
                     }
                     __syncwarp();
@@ -530,9 +682,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
         }
     } else if (warp >= 4) {
         // ------------------------------------------------------------------ epilogue (both CTAs)
-        const int ew = warp - 4;
-        const int q = warp & 3;
-        const int half = ew >> 2;
         long iter = 0;
         for (long grp = pair; grp < ngroups; grp += npairs)
         for (long tile = grp * p.grp_tiles; tile < (grp + 1) * p.grp_tiles; tile++, iter++) {
@@ -540,97 +689,196 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
             const long rem = tile - (long)e * tiles_per_e;
             const int tj = (int)(rem / p.tiles_i);
             const int ti = (int)(rem - (long)tj * p.tiles_i);
-            const int as = (int)(iter & 1);
-            const uint32_t aphase = (uint32_t)((iter >> 1) & 1);
-            mbar_wait(&tfull_bar[as], aphase);
-            tc_fence_after();
-            const long j = (long)tj * 256 + (long)rank * 128 + q * 32 + lane;
-            const bool jok = j < p.V2;
-            const bool do_fisher = e < p.fisher_epochs;
-            const float osc = p.out_scale;
-            const long i0 = (long)ti * p.BN;
-            float *obase = p.out + (size_t)e * p.stride_e + j;
-            const int nchunks = p.BN >> 5;
-            bool released = false;
-            for (int c = half; c < nchunks; c += 2) {
-                const long ic = i0 + c * 32;
-                if (ic >= p.nb) break;
-                uint32_t v[32];
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.BN + c * 32);
-                tmem_ld32(taddr, v);
-                tmem_ld_wait();
-                // this warp's last chunk of the tile is now in registers: hand the accumulator stage back to
-                // the MMA issuer before the Fisher math / stores of that chunk (shortens the critical path)
-                const bool last_chunk = (c + 2 >= nchunks) || (ic + 64 >= p.nb);
-                if (last_chunk) {
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive_cluster(&tempty_bar[as], 0);
-                    released = true;
-                }
-                if (p.tma_store) {
-                    // registers -> 32x32 smem block (row i, lane = column j: conflict-free) -> one TMA
-                    // store of box {32 j, 1 e, 32 i}; the TMA unit clips at V2 / nb and writes full lines
-                    float *blk = staging + (size_t)ew * 1024;
-                    if (lane == 0) tma_store_wait_read0();   // previous block of this warp has been read
-                    __syncwarp();
-                    if (do_fisher) {
-#pragma unroll
-                        for (int r = 0; r < 32; r++) blk[r * 32 + lane] = fisher_fast(__uint_as_float(v[r]) * osc);
-                    } else {
-#pragma unroll
-                        for (int r = 0; r < 32; r++) blk[r * 32 + lane] = __uint_as_float(v[r]) * osc;
-                    }
-                    fence_proxy_async_smem();
-                    __syncwarp();
-                    if (lane == 0) {
-                        if (p.blocked)   // box {32 j_local, 32 i, 1 block}: the pair's tile is one contiguous 256 KB run
-                            tma_store_3d(&tm_out, blk, (int)rank * 128 + q * 32, (int)ic, e * p.tiles_j + tj);
-                        else
-                            tma_store_3d(&tm_out, blk, (int)(j - lane), e, (int)ic);
-                        tma_store_commit();
-                    }
-                    continue;
-                }
-                if (jok) {
-                    float *ptr = obase + (size_t)ic * p.stride_i;
-                    if (ic + 32 <= p.nb) {
-                        if (do_fisher) {
-#pragma unroll
-                            for (int r = 0; r < 32; r++) {
-                                *ptr = fisher_fast(__uint_as_float(v[r]) * osc);
-                                ptr += p.stride_i;
-                            }
-                        } else {
-#pragma unroll
-                            for (int r = 0; r < 32; r++) {
-                                *ptr = __uint_as_float(v[r]) * osc;
-                                ptr += p.stride_i;
-                            }
-                        }
-                    } else {
-#pragma unroll
-                        for (int r = 0; r < 32; r++) {
-                            if (ic + r < p.nb) {
-                                float x = __uint_as_float(v[r]) * osc;
-                                if (do_fisher) x = fisher_fast(x);
-                                *ptr = x;
-                            }
-                            ptr += p.stride_i;
-                        }
-                    }
-                }
-            }
-            if (!released) {   // warps that had no chunk in this tile (BN < 64 or ragged row tile)
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(&tempty_bar[as], 0);  // accumulator slot free (leader's barrier)
-            }
+            gemm_epilogue_tile(p, &tm_out, staging, tfull_bar, tempty_bar, tmem_base, e, tj, ti, iter, rank, warp, lane);
         }
     }
     if (p.tma_store && warp >= 4 && lane == 0) tma_store_wait_all();
     tc_fence_before();
     cluster_sync_all();  // no CTA of the pair leaves while its peer may still touch its smem / TMEM
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc_2sm(tmem_base, 512);
+    }
+}
+
+
+// ---------------------------------------------------------------- pair GEMM with a RESIDENT row operand
+// Measured (profiles/README.md, SW64 experiment): k_corr_umma2 moves ~51 TMA row requests (<= 128 B each)
+// per clock chip-wide -- 2 operand-load rows for every output-store row -- which is the L2 request ceiling
+// (~6300 B/clk), not the tensor pipe (50 % busy).  When the whole-K row operand of a pair (BN rows x Kp x
+// planes, half per CTA) fits in shared memory, the pair keeps it RESIDENT and sweeps a range of 256-column
+// tiles past it: only the column operand streams (one (k-block, plane) tile of 16 KB per ring stage), so
+// the load requests per tile halve.  Work unit = (epoch, column-tile range, row tile), row tile fastest,
+// so the pairs running at the same time stream the same column tiles out of L2.
+template <int KIND>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+    k_corr_umma_res(const __grid_constant__ CUtensorMap tm_cols, const __grid_constant__ CUtensorMap tm_rows,
+                    const __grid_constant__ CUtensorMap tm_out, const Gemm2Params p)
+{
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t *resident = smem;                                   // [kbs][planes][BN/2 rows][128 B]
+    uint8_t *tiles = smem + p.res_bytes;                        // [stages][128 cols][128 B]
+    float *staging = reinterpret_cast<float *>(tiles + (size_t)p.stages * p.stage_bytes);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(staging) +
+                                                  (p.tma_store ? GEMM_EPI_WARPS * 4096 : 0));
+    uint64_t *full_bar = bars;                         // [stages]  leader only
+    uint64_t *empty_bar = bars + GEMM_MAX_STAGES;      // [stages]  per CTA (multicast commit)
+    uint64_t *tfull_bar = bars + 2 * GEMM_MAX_STAGES;  // [2]       per CTA (multicast commit)
+    uint64_t *tempty_bar = tfull_bar + 2;              // [2]       leader only
+    uint64_t *rfull_bar = tempty_bar + 2;              // [1]       leader only: resident rows of both CTAs landed
+    uint64_t *rempty_bar = rfull_bar + 1;              // [1]       per CTA: the unit's MMAs have retired
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(rempty_bar + 1);
+
+    const int warp = uniform_warp_idx();
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+
+    cluster_sync_all();
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tm_cols);
+        tma_prefetch_desc(&tm_rows);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < p.stages; s++) {
+            mbar_init(&full_bar[s], 2);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int s = 0; s < 2; s++) {
+            mbar_init(&tfull_bar[s], 1);
+            mbar_init(&tempty_bar[s], 2 * GEMM_EPI_WARPS);
+        }
+        mbar_init(rfull_bar, 2);
+        mbar_init(rempty_bar, 1);
+        fence_mbar_init();
+    }
+    if (warp == 2) {
+        tmem_alloc_2sm(tmem_slot, 512);
+        tmem_relinquish_2sm();
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // warp-uniform for the compiler
+
+    const long pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+    const int halfN = p.BN >> 1;
+    const long units_per_e = (long)p.nchunk * p.tiles_i;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer (both CTAs)
+        if (elect_one_sync()) {
+            int stage = 0;
+            uint32_t phase = 0, rphase = 0;
+            for (long unit = pair; unit < p.total_units; unit += npairs) {
+                const int e = (int)(unit / units_per_e);
+                const long rem = unit - (long)e * units_per_e;
+                const int chunk = (int)(rem / p.tiles_i);
+                const int ti = (int)(rem - (long)chunk * p.tiles_i);
+                const int tj0 = chunk * p.cj;
+                const int tj1 = tj0 + p.cj < p.tiles_j ? tj0 + p.cj : p.tiles_j;
+                const int row0 = (int)(p.row_start + (long)ti * p.BN + (long)rank * halfN);
+                mbar_wait(rempty_bar, rphase ^ 1);     // previous unit no longer reads the resident tiles
+                rphase ^= 1;
+                if (leader)
+                    mbar_expect_tx(rfull_bar, 2 * p.res_bytes);
+                else
+                    mbar_arrive_cluster(rfull_bar, 0);
+                for (int kb = 0; kb < p.kbs; kb++)
+                    for (int pl = 0; pl < p.planes; pl++)
+                        tma_load_3d_2sm(&tm_rows, rfull_bar, resident + (size_t)(kb * p.planes + pl) * p.half_bytes,
+                                        kb * p.bk, row0, pl * p.E + e);
+                for (int tj = tj0; tj < tj1; tj++) {
+                    const int col0 = tj * 256 + (int)rank * 128;
+                    for (int kb = 0; kb < p.kbs; kb++)
+                        for (int pl = 0; pl < p.planes; pl++) {
+                            mbar_wait(&empty_bar[stage], phase ^ 1);
+                            if (leader)
+                                mbar_expect_tx(&full_bar[stage], 2 * p.stage_bytes);
+                            else
+                                mbar_arrive_cluster(&full_bar[stage], 0);
+                            tma_load_3d_2sm(&tm_cols, &full_bar[stage], tiles + (size_t)stage * p.stage_bytes, kb * p.bk,
+                                            col0, pl * p.E + e);
+                            if (++stage == p.stages) {
+                                stage = 0;
+                                phase ^= 1;
+                            }
+                        }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+        if (leader) {
+            const uint32_t idesc = make_idesc(p.fmt, 256, (uint32_t)p.BN);
+            const uint32_t res_addr = smem_u32(resident);
+            const uint32_t tiles_addr = smem_u32(tiles);
+            int stage = 0;
+            uint32_t phase = 0, rphase = 0;
+            long iter = 0;
+            for (long unit = pair; unit < p.total_units; unit += npairs) {
+                const long rem = unit % units_per_e;
+                const int chunk = (int)(rem / p.tiles_i);
+                const int tj0 = chunk * p.cj;
+                const int tj1 = tj0 + p.cj < p.tiles_j ? tj0 + p.cj : p.tiles_j;
+                mbar_wait(rfull_bar, rphase);
+                rphase ^= 1;
+                tc_fence_after();
+                for (int tj = tj0; tj < tj1; tj++, iter++) {
+                    const int as = (int)(iter & 1);
+                    const uint32_t aphase = (uint32_t)((iter >> 1) & 1);
+                    mbar_wait(&tempty_bar[as], aphase ^ 1);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.BN);
+                    uint32_t accumulate = 0;
+                    for (int kb = 0; kb < p.kbs; kb++) {
+                        const int rem_k = p.Kp - kb * p.bk;
+                        const int nk = (rem_k < p.bk ? rem_k : p.bk) / p.umma_k;
+                        for (int pl = 0; pl < p.planes; pl++) {
+                            mbar_wait(&full_bar[stage], phase);
+                            tc_fence_after();
+                            if (elect_one_sync()) {
+                                const uint32_t cbase = tiles_addr + (uint32_t)stage * p.stage_bytes;
+                                for (int sgm = 0; sgm < p.segs; sgm++) {
+                                    if (p.seg_c[sgm] != pl) continue;
+                                    issue_kblock_mmas<KIND>(
+                                        d_tmem, cbase, res_addr + (uint32_t)(kb * p.planes + p.seg_r[sgm]) * p.half_bytes,
+                                        idesc, nk, accumulate);
+                                }
+                                tc_commit_2sm(&empty_bar[stage]);
+                                if (kb == p.kbs - 1 && pl == p.planes - 1) {
+                                    tc_commit_2sm(&tfull_bar[as]);
+                                    if (tj == tj1 - 1) tc_commit_2sm(rempty_bar);   // resident tiles may be replaced
+                                }
+                            }
+                            __syncwarp();
+                            if (++stage == p.stages) {
+                                stage = 0;
+                                phase ^= 1;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ------------------------------------------------------------------ epilogue (both CTAs)
+        long iter = 0;
+        for (long unit = pair; unit < p.total_units; unit += npairs) {
+            const int e = (int)(unit / units_per_e);
+            const long rem = unit - (long)e * units_per_e;
+            const int chunk = (int)(rem / p.tiles_i);
+            const int ti = (int)(rem - (long)chunk * p.tiles_i);
+            const int tj0 = chunk * p.cj;
+            const int tj1 = tj0 + p.cj < p.tiles_j ? tj0 + p.cj : p.tiles_j;
+            for (int tj = tj0; tj < tj1; tj++, iter++)
+                gemm_epilogue_tile(p, &tm_out, staging, tfull_bar, tempty_bar, tmem_base, e, tj, ti, iter, rank, warp, lane);
+        }
+    }
+    if (p.tma_store && warp >= 4 && lane == 0) tma_store_wait_all();
+    tc_fence_before();
+    cluster_sync_all();
     if (warp == 2) {
         tc_fence_after();
         tmem_dealloc_2sm(tmem_base, 512);
@@ -689,8 +937,8 @@ __global__ void k_self_corr_fixup(const float *__restrict__ selfdiag, int E, lon
     float r = selfdiag[(size_t)e * V + start + i];
     if (e < fisher_epochs) r = fisher_fast(r);
     const long j = start + i;
-    if (blocked_t256 > 0)
-        out[(((size_t)e * blocked_t256 + (j >> 8)) * nb + i) * 256 + (j & 255)] = r;
+    if (blocked_t256 > 0)   // tiled [i/256][j/256][e][i%256][j%256]
+        out[((((size_t)(i >> 8) * blocked_t256 + (j >> 8)) * E + e) * 256 + (i & 255)) * 256 + (j & 255)] = r;
     else
         out[(size_t)i * stride_i + (size_t)e * stride_e + j] = r;
 }
@@ -710,22 +958,23 @@ static int make_out_map(CUtensorMap *m, float *out, long V2, int E, long nb, lon
     return FCMA_OK;
 }
 
-// blocked output [E*T256][nb][256] as a 3-D TMA tensor (j_local, i, block), box {32, 32, 1}
+// tiled output [tiles_i*T256*E][256 i][256 j] as a 3-D TMA tensor (j_local, i_local, tile), box {32, 32, 1}
 static int make_out_map_blocked(CUtensorMap *m, float *out, int E, long nb, long t256)
 {
     PFN_tmEncodeTiled enc = get_encode_fn();
     if (!enc) return fail(FCMA_ECUDA, "cuTensorMapEncodeTiled entry point not available");
-    cuuint64_t gdim[3] = {256, (cuuint64_t)nb, (cuuint64_t)E * t256};
-    cuuint64_t gstr[2] = {1024, (cuuint64_t)nb * 1024};
+    cuuint64_t gdim[3] = {256, 256, (cuuint64_t)cdiv(nb, 256) * t256 * E};
+    cuuint64_t gstr[2] = {1024, 256 * 1024};
     cuuint32_t box[3] = {32, 32, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, out, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return fail(FCMA_ECUDA, "cuTensorMapEncodeTiled(blocked out) failed with CUresult %d", (int)r);
+    if (r != CUDA_SUCCESS) return fail(FCMA_ECUDA, "cuTensorMapEncodeTiled(tiled out) failed with CUresult %d", (int)r);
     return FCMA_OK;
 }
 
-// blocked_t256 > 0: write the block in the blocked layout [E][blocked_t256][nb][256] (TMA-store epilogue only)
+// blocked_t256 > 0: write the block in the tiled layout [ceil(nb/256)][blocked_t256][E][256][256] (TMA-store
+// epilogue only; the caller provides round_up(nb, 256) rows of workspace)
 static int launch_corr_umma(const void *rows_op, const void *cols_op, int precision, int E, int T, long V, long V2,
                             long start, long nb, float *out, long stride_i, long stride_e, int fisher_epochs,
                             cudaStream_t st, long blocked_t256 = 0)
@@ -754,18 +1003,50 @@ static int launch_corr_umma(const void *rows_op, const void *cols_op, int precis
     q.half_bytes = (uint32_t)(q.BN / 2) * 128;
     q.stage_bytes = (uint32_t)pi.planes * (16384 + q.half_bytes);
     // TMA-store epilogue needs 16-byte aligned rows of the output and 4 KB of staging per epilogue warp
-    static const bool no_tma_store = getenv("FCMA_GEMM_NO_TMA_STORE") != nullptr;
+    const char *nts = getenv("FCMA_GEMM_NO_TMA_STORE");
+    const bool no_tma_store = nts && nts[0] == '1';
     q.tma_store = (!no_tma_store && (stride_i % 4 == 0) && (stride_e % 4 == 0) && (((uintptr_t)out & 15) == 0)) ? 1 : 0;
     q.blocked = blocked_t256 > 0 ? 1 : 0;
     if (q.blocked && (!q.tma_store || blocked_t256 != q.tiles_j))
         return fail(FCMA_EINVAL, "internal: blocked output needs the TMA-store epilogue and T256 == tiles_j");
     const size_t staging_bytes = q.tma_store ? (size_t)GEMM_EPI_WARPS * 4096 : 0;
     const size_t cap = 227 * 1024 - 1024 /*alignment slack*/ - 256 /*barriers*/;
-    int stages = (int)((cap - staging_bytes) / q.stage_bytes);
+    long pairs = g_sm_count / 2;
+
+    // resident-row-operand kernel (opt-in, FCMA_GEMM_RESIDENT=1; needs the pair's whole-K row tile + >= 4 column
+    // stages in shared memory): halves the operand loads but runs 8 instead of 4 stage rounds per tile and is
+    // not faster than the streaming kernel on B200 (tools/ab_resident.py) -- kept for the measurement.
+    {
+        const char *dbg = getenv("FCMA_GEMM_DEBUG");
+        q.debug = dbg ? atoi(dbg) : 0;
+    }
+    const char *res_env = getenv("FCMA_GEMM_RESIDENT");
+    q.res_bytes = (uint32_t)q.kbs * pi.planes * q.half_bytes;
+    bool resident = (res_env && res_env[0] == '1') && (size_t)q.res_bytes + staging_bytes + 4 * 16384 <= cap;
+    if (resident) {
+        q.stage_bytes = 16384;
+        // work units (epoch, column-tile chunk, row tile): enough of them to balance the pairs
+        const long base = (long)E * q.tiles_i;
+        long best_n = 1;
+        double best_eff = 0;
+        for (long n = 1; n <= q.tiles_j && n <= 64; n++) {
+            const long cj = cdiv(q.tiles_j, n), nn = cdiv(q.tiles_j, cj);
+            const long units = base * nn;
+            const long rounds = cdiv(units, pairs);
+            // cost model: rounds * (cj tiles + ~1 tile of resident reload) vs ideal units*cj/pairs
+            const double eff = ((double)units * cj / pairs) / ((double)rounds * (cj + 1.0));
+            if (eff > best_eff + 1e-9) best_eff = eff, best_n = nn;
+            if (units >= 16 * pairs) break;
+        }
+        q.cj = (int)cdiv(q.tiles_j, best_n);
+        q.nchunk = (int)cdiv(q.tiles_j, q.cj);
+        q.total_units = base * q.nchunk;
+    }
+    int stages = (int)((cap - staging_bytes - (resident ? q.res_bytes : 0)) / q.stage_bytes);
     if (stages > GEMM_MAX_STAGES) stages = GEMM_MAX_STAGES;
     if (stages < 2) return fail(FCMA_EINVAL, "internal: not enough shared memory for 2 stages");
     q.stages = stages;
-    const size_t smem = (size_t)stages * q.stage_bytes + staging_bytes + 1024 + 256;
+    const size_t smem = (resident ? q.res_bytes : 0) + (size_t)stages * q.stage_bytes + staging_bytes + 1024 + 256;
     {
         const char *sched = getenv("FCMA_GEMM_SCHED");   // tuning knob: 1 = a pair takes all row tiles of a column tile
         q.grp_tiles = (sched && sched[0] == '1') ? q.tiles_i : 1;
@@ -784,10 +1065,17 @@ static int launch_corr_umma(const void *rows_op, const void *cols_op, int precis
         memset(&tm_out, 0, sizeof(tm_out));
     if (rc) return rc;
 
-    long pairs = g_sm_count / 2;
-    const long ngroups = q.total_tiles / q.grp_tiles;
+    const long ngroups = resident ? q.total_units : q.total_tiles / q.grp_tiles;
     if (ngroups < pairs) pairs = ngroups;
-    if (pi.kind == 0) {
+    if (resident) {
+        if (pi.kind == 0) {
+            CUDA_TRY(cudaFuncSetAttribute(k_corr_umma_res<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_corr_umma_res<0><<<(unsigned)(2 * pairs), GEMM_THREADS, smem, st>>>(tm_cols, tm_rows, tm_out, q);
+        } else {
+            CUDA_TRY(cudaFuncSetAttribute(k_corr_umma_res<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_corr_umma_res<1><<<(unsigned)(2 * pairs), GEMM_THREADS, smem, st>>>(tm_cols, tm_rows, tm_out, q);
+        }
+    } else if (pi.kind == 0) {
         CUDA_TRY(cudaFuncSetAttribute(k_corr_umma2<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_corr_umma2<0><<<(unsigned)(2 * pairs), GEMM_THREADS, smem, st>>>(tm_cols, tm_rows, tm_out, q);
     } else {
@@ -1067,7 +1355,11 @@ __global__ void __launch_bounds__(256, (R == 4 ? 2 : 1))
     const long nchunks = (n2 + 31) / 32;
 
     for (long i = blockIdx.x; i < nb; i += gridDim.x) {
-        const float *Ci = C + (size_t)i * stride_i;
+        // classic layout: row i at i*stride_i; tiled layout (chunk_step != 256): 256-row blocks of
+        // ceil(n2/256) * chunk_step floats, rows 256 floats apart inside a block
+        const float *Ci = chunk_step == 256
+                              ? C + (size_t)i * stride_i
+                              : C + (size_t)(i >> 8) * (size_t)(((n2 + 255) >> 8) * chunk_step) + (size_t)(i & 255) * stride_i;
         const long self_col = self_col0 >= 0 ? self_col0 + i : -1;
         float acc[MT][NT][4];
 #pragma unroll
@@ -1388,8 +1680,10 @@ static bool fused_supported(int E, int eps_mode)
 
 // (stride_i, ld, chunk_step) describe where element (i, e, j) of the correlation block lives:
 //   C[i*stride_i + e*ld + (j/256)*chunk_step + j%256]
-// classic [nb][E][ld] layout: stride_i = E*ld, chunk_step = 256; blocked [E][T256][nb][256] layout (written
-// by the pair GEMM as contiguous 256 KB tiles): stride_i = 256, ld = T256*nb*256, chunk_step = nb*256.
+// classic [nb][E][ld] layout: stride_i = E*ld, chunk_step = 256.  Tiled [nb/256][T256][E][256 i][256 j] layout
+// (every 256x256 pair tile of the GEMM is one contiguous 256 KB run; the E tiles of one (row block, column
+// block) are adjacent): stride_i = 256, ld = 65536, chunk_step = E*65536, and i -> (i/256)*T256*chunk_step +
+// (i%256)*stride_i inside the kernel.
 static int launch_norm_syrk(const float *C, long nb, int E, long n2, long stride_i, long ld, int eps_mode,
                             int fisher_done, long self_col0, float beta, float *K, int sum_over_rows, cudaStream_t st,
                             long chunk_step = 256)
@@ -1566,7 +1860,7 @@ extern "C" int fcma_norm_kernel_matrices(const float *corr_dev, long nb, int E, 
 
 extern "C" size_t fcma_work_bytes_per_row(int E, long V2)
 {
-    // the fused pipelines store the block as [E][T256][rows][256] (T256 = ceil(V2/256) column groups)
+    // the fused pipelines store the block tiled as [rows/256][T256][E][256][256] (T256 = ceil(V2/256))
     return (size_t)E * round_up(V2, 256) * sizeof(float);
 }
 
@@ -1589,6 +1883,12 @@ extern "C" long fcma_timing_read(double *gemm_ms, double *syrk_ms)
 }
 
 // shared body of the two fused pipelines
+static bool env_is_one(const char *name)
+{
+    const char *v = getenv(name);
+    return v && v[0] == '1';
+}
+
 static int run_pipeline(const void *rows_op, const void *cols_op, int precision, int E, int T, long V, long V2, long start,
                         long nb, int eps, int flags, float *work, size_t work_bytes, float *K, int sum_over_rows,
                         cudaStream_t st)
@@ -1598,7 +1898,7 @@ static int run_pipeline(const void *rows_op, const void *cols_op, int precision,
     if (eps < 0) return fail(FCMA_EINVAL, "pipeline: negative epochs_per_subj");
     if (((uintptr_t)work & 15)) return fail(FCMA_EINVAL, "pipeline: work buffer must be 16-byte aligned");
     const long ld = round_up(V2, 32);
-    const size_t row_bytes = fcma_work_bytes_per_row(E, V2);   // >= E * ld * 4 (also covers the blocked layout)
+    const size_t row_bytes = fcma_work_bytes_per_row(E, V2);   // >= E * ld * 4 (also covers the tiled layout)
     long rows_per_pass = (long)(work_bytes / row_bytes);
     if (rows_per_pass < 1) return fail(FCMA_ENOMEM, "work buffer too small: %zu bytes < %zu per row", work_bytes, row_bytes);
     if (rows_per_pass > 256) rows_per_pass = (rows_per_pass / 256) * 256;  // whole GEMM tiles
@@ -1610,14 +1910,15 @@ static int run_pipeline(const void *rows_op, const void *cols_op, int precision,
     const bool mask_self = (flags & FCMA_FLAG_MASK_SELF) != 0;
     if (mask_self && !(normalise && fused))
         return fail(FCMA_EINVAL, "FCMA_FLAG_MASK_SELF needs the fused normalise+kernel path (E <= 64, power-of-two eps)");
-    // Blocked intermediate [E][T256][n][256]: every 256x256 pair tile of the GEMM is one contiguous 256 KB run
-    // (tools/store_bench.cu: 6.2 TB/s vs 4.5 TB/s for the strided [i][e][j] layout); the fused normalise+SYRK
-    // kernel gathers 1 KB pieces from it.  Needs the pair GEMM with the TMA-store epilogue.
-    // MEASURED (tools/ab_pipeline.py, 2048 rows, fp16x3): GEMM 4.40 -> 4.43 ms (bf16: 3.16 -> 3.03), but the gather
-    // costs the normalise+SYRK kernel 2.28 -> 2.86 ms: a net loss, so the blocked layout is opt-in (FCMA_BLOCKED=1).
-    static const bool no_blocked = getenv("FCMA_BLOCKED") == nullptr || getenv("FCMA_GEMM_NO_TMA_STORE") != nullptr;
+    // Tiled intermediate [n/256][T256][E][256][256]: every 256x256 pair tile of the GEMM is one contiguous 256 KB
+    // run (tools/store_bench.cu: 6.2 TB/s vs 4.5 TB/s for the strided [i][e][j] layout) and the E tiles of one
+    // (row block, column block) are adjacent, so the fused normalise+SYRK kernel reads row i as E runs of 1 KB,
+    // 256 KB apart, inside one 8 MB region.  Needs the TMA-store epilogue and whole 256-row blocks of workspace.
+    // FCMA_NO_TILED=1 falls back to the strided [i][e][j] block.
+    const char *no_tiled = getenv("FCMA_NO_TILED");
     const long t256 = cdiv(V2, 256);
-    const bool blocked = !no_blocked && fused && V2 < (1L << 31);
+    const bool blocked = !(no_tiled && no_tiled[0] == '1') && !env_is_one("FCMA_GEMM_NO_TMA_STORE") && fused &&
+                         V2 < (1L << 31) && rows_per_pass >= 256;
     for (long done = 0; done < nb; done += rows_per_pass) {
         const long n = nb - done < rows_per_pass ? nb - done : rows_per_pass;
         int rc;
@@ -1637,8 +1938,8 @@ static int run_pipeline(const void *rows_op, const void *cols_op, int precision,
         float *Kdst = sum_over_rows ? K : K + (size_t)done * E * E;
         const float beta = sum_over_rows ? 1.0f : 0.0f;
         if (blocked) {
-            rc = launch_norm_syrk(work, n, E, V2, 256, t256 * n * 256, normalise ? eps : 0, (normalise && fisher_in_gemm) ? 1 : 0,
-                                  mask_self ? start + done : -1, beta, Kdst, sum_over_rows, st, n * 256);
+            rc = launch_norm_syrk(work, n, E, V2, 256, 65536, normalise ? eps : 0, (normalise && fisher_in_gemm) ? 1 : 0,
+                                  mask_self ? start + done : -1, beta, Kdst, sum_over_rows, st, (long)E * 65536);
         } else if (normalise && fused) {
             rc = launch_norm_syrk(work, n, E, V2, (long)E * ld, ld, eps, fisher_in_gemm ? 1 : 0,
                                   mask_self ? start + done : -1, beta, Kdst, sum_over_rows, st);

@@ -61,6 +61,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
     }
 }
 
+// One lane of a fully converged warp (elect.sync).  Together with a warp index obtained through
+// __shfl_sync(.., 0) this lets the compiler keep the single-thread TMA / tcgen05 issue code on the
+// UNIFORM datapath (UR operands) instead of wrapping every UTCHMMA / UTMALDG in an ELECT +
+// R2UR.BROADCAST waterfall loop (measured: 170 instead of 128 clk per MMA issued).
+__device__ __forceinline__ bool elect_one_sync()
+{
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ int uniform_warp_idx() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+
 // ---------------------------------------------------------------- TMA
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *m)
 {
@@ -144,6 +160,18 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr)
     d |= (uint64_t)(1024 >> 4) << 32;                  // SBO, bits [32,46)
     d |= (uint64_t)1 << 46;                            // descriptor version
     d |= (uint64_t)2 << 61;                            // SWIZZLE_128B
+    return d;
+}
+
+// same for a 64-byte swizzle atom (rows of 64 B, 8-row groups 512 B apart): half the bytes per stage,
+// so twice the stages fit in shared memory for the same tile shape
+__device__ __forceinline__ uint64_t make_smem_desc_sw64(uint32_t smem_addr)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)(512 >> 4) << 32;                   // SBO
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)4 << 61;                            // SWIZZLE_64B
     return d;
 }
 

@@ -328,17 +328,20 @@ __global__ void __launch_bounds__(256) k_epoch_normalize(float *data, int T, lon
 }
 
 // ============================================================================================
-// a4 on tensor cores: persistent, warp-specialised TMA -> tcgen05.mma.cta_group::2 -> TMEM -> TMA store
+// a4 on tensor cores: persistent, warp-specialised TMA -> tcgen05.mma.cta_group::2 -> TMEM -> registers -> HBM
 // ============================================================================================
 // Per CTA the D tile = 128 columns j (UMMA M side, TMEM lanes) x BN rows i (UMMA N side, TMEM columns): with
-// the all-voxel side on the lanes, a warp's 32 lanes hold 32 consecutive j of one output row, so a 32x32
-// block goes to shared memory conflict-free and out as one TMA store (or, for unaligned outputs, straight
-// from registers as full 128-byte lines of out[i][e][j..j+31]).
-// (Round-1 history, see profiles/README.md: a single-CTA kernel and a resident-row-operand variant were
-// measured and dropped; git history has them.)
+// the all-voxel side on the lanes, a warp's 32 lanes hold 32 consecutive j of one output row, so every
+// epilogue store instruction writes one full 128-byte line.
+// Round-1 history (profiles/README.md; git history has the code): single-CTA tiles, a resident-row-operand
+// variant, a 64-byte-swizzle half-stage variant and a TMA-store epilogue were measured and dropped.  The two
+// findings that mattered: (1) the single-thread MMA issue loop must stay on the uniform datapath
+// (elect.sync + shuffled warp index), else each UTCHMMA costs ~170 clk to issue against 128 clk to execute;
+// (2) at the 1000 W board cap this kernel is ENERGY-bound: its main loop alone already runs at cuBLAS'
+// sustained bf16 rate, and epilogue / store work adds time instead of overlapping.
 
-constexpr int GEMM_THREADS = 384;  // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4..11 epilogue
-constexpr int GEMM_EPI_WARPS = 8;
+constexpr int GEMM_MAX_EPI_WARPS = 16;                        // 2 or 4 per TMEM lane quadrant (Gemm2Params::epi_warps)
+constexpr int GEMM_MAX_THREADS = 128 + 32 * GEMM_MAX_EPI_WARPS;   // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4.. epilogue
 constexpr int GEMM_MAX_STAGES = 12;
 
 __device__ __forceinline__ float rsqrt_ftz(float x)
@@ -411,14 +414,10 @@ struct Gemm2Params {
     int stages;
     int fmt;                       // idesc operand format
     float out_scale;               // accumulator scale applied in the epilogue
-    int tma_store;                 // 1: epilogue stages 32x32 blocks in smem and issues TMA stores
-    int blocked;                   // 1: output is tiled [tiles_i][tiles_j][E][256][256] (needs tma_store); 0: strided [i][e][j]
-    // resident-row-operand kernel (k_corr_umma_res) only:
-    int cj, nchunk;                // column tiles per work unit, units per (epoch, row tile)
-    long total_units;              // E * nchunk * tiles_i
-    uint32_t res_bytes;            // kbs * planes * half_bytes: the pair's whole-K row operand, half per CTA
-    int debug;                     // FCMA_GEMM_DEBUG bit mask (diagnostics only; output is wrong when set):
-                                   //   1 no stores, 2 no TMEM load / math / smem fill, 4 no epilogue work at all
+    int tiled;                     // 1: output is tiled [tiles_i][tiles_j][E][256][256]; 0: strided [i][e][j]
+    int epi_warps;                 // 8 or 16 epilogue warps (blockDim = 128 + 32 * epi_warps)
+    int debug;                     // FCMA_GEMM_DEBUG (diagnostics only; output is wrong when set):
+                                   //   4 no epilogue work (main loop only), 16 MMAs re-read stale stages (no loads)
 };
 
 // MMAs of one (column tile, row tile) operand pair of a stage: up to 4 k-steps of 32 bytes inside the
@@ -441,15 +440,17 @@ __device__ __forceinline__ void issue_kblock_mmas(uint32_t d_tmem, uint32_t addr
     }
 }
 
-// One accumulator tile of the pair GEMM: TMEM -> registers -> (Fisher) -> TMA store / STG.  Called by the
-// 8 epilogue warps of both CTAs; `iter` is the pair's running tile count (selects the TMEM stage).
-__device__ __forceinline__ void gemm_epilogue_tile(const Gemm2Params &p, const CUtensorMap *tm_out_p, float *staging,
-                                                   uint64_t *tfull_bar, uint64_t *tempty_bar, uint32_t tmem_base,
-                                                   int e, int tj, int ti, long iter, uint32_t rank, int warp, int lane)
+// One accumulator tile of the pair GEMM: TMEM -> registers -> scale (+ Fisher-z) -> global, 128 B per
+// warp store.  Called by the epilogue warps of both CTAs; `iter` is the pair's running tile count
+// (selects the TMEM stage).  Warp w may only touch TMEM lanes 32*(w%4)..+31, so the epi_warps/4 warps
+// of a lane quadrant split the BN accumulator columns (voxel rows i) in chunks of 32.
+__device__ __forceinline__ void gemm_epilogue_tile(const Gemm2Params &p, uint64_t *tfull_bar, uint64_t *tempty_bar,
+                                                   uint32_t tmem_base, int e, int tj, int ti, long iter, uint32_t rank,
+                                                   int warp, int lane)
 {
-    const int ew = warp - 4;
     const int q = warp & 3;
-    const int half = ew >> 2;
+    const int part = (warp - 4) >> 2;
+    const int cstep = p.epi_warps >> 2;
     const int as = (int)(iter & 1);
     const uint32_t aphase = (uint32_t)((iter >> 1) & 1);
     mbar_wait(&tfull_bar[as], aphase);
@@ -459,39 +460,25 @@ __device__ __forceinline__ void gemm_epilogue_tile(const Gemm2Params &p, const C
     const bool do_fisher = e < p.fisher_epochs;
     const float osc = p.out_scale;
     const long i0 = (long)ti * p.BN;
-    float *obase = p.out + (size_t)e * p.stride_e + j;
     const int nchunks = p.BN >> 5;
     bool released = false;
-    if (p.debug & 4) {
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(&tempty_bar[as], 0);
-        return;
-    }
-    for (int c = half; c < nchunks; c += 2) {
+    for (int c = (p.debug & 4) ? nchunks : part; c < nchunks; c += cstep) {
         const long ic = i0 + c * 32;
         if (ic >= p.nb) break;
         uint32_t v[32];
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.BN + c * 32);
-        if (!(p.debug & 2)) {
-            tmem_ld32(taddr, v);
-            tmem_ld_wait();
-        } else {
-#pragma unroll
-            for (int r = 0; r < 32; r++) v[r] = 0;
-        }
+        tmem_ld32(taddr, v);
+        tmem_ld_wait();
         // this warp's last chunk of the tile is now in registers: hand the accumulator stage back to
-        // the MMA issuer before the Fisher math / stores of that chunk (shortens the critical path)
-        const bool last_chunk = (c + 2 >= nchunks) || (ic + 64 >= p.nb);
-        if (last_chunk) {
+        // the MMA issuer before the math / stores of that chunk
+        if ((c + cstep >= nchunks) || (ic + 32 * cstep >= p.nb)) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(&tempty_bar[as], 0);
             released = true;
         }
-        // scale + Fisher-z in registers (all 32 lanes together: fisher_row votes)
         if (do_fisher) {
-            float m = 0.f;   // max |accumulator| of this lane's 32 rows (NaNs drop out and propagate below)
+            float m = 0.f;   // max |accumulator| of this lane's 32 rows (NaNs drop out here and propagate below)
 #pragma unroll
             for (int r = 0; r < 32; r++) m = fmaxf(m, fabsf(__uint_as_float(v[r])));
             if (__any_sync(0xffffffffu, m * osc > FISHER_SERIES_MAX)) {
@@ -505,29 +492,15 @@ __device__ __forceinline__ void gemm_epilogue_tile(const Gemm2Params &p, const C
 #pragma unroll
             for (int r = 0; r < 32; r++) v[r] = __float_as_uint(__uint_as_float(v[r]) * osc);
         }
-        if (p.tma_store) {
-            // registers -> 32x32 smem block (row i, lane = column j: conflict-free) -> one TMA
-            // store of box {32 j, 1 e, 32 i}; the TMA unit clips at V2 / nb and writes full lines
-            float *blk = staging + (size_t)ew * 1024;
-            if (lane == 0) tma_store_wait_read0();   // previous block of this warp has been read
-            __syncwarp();
-            if (!(p.debug & 2)) {
+        if (p.tiled) {
+            // the pair's 256x256 tile of epoch e is one contiguous 256 KB run, row pitch 1 KB; rows >= nb and
+            // columns >= V2 fall into the tile padding the caller allocated
+            float *ptr = p.out + (((size_t)(ti * p.tiles_j + tj) * p.E + e) * 256 + c * 32) * 256 +
+                         ((int)rank * 128 + q * 32 + lane);
 #pragma unroll
-                for (int r = 0; r < 32; r++) blk[r * 32 + lane] = __uint_as_float(v[r]);
-            }
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0 && !(p.debug & 1)) {
-                if (p.blocked)   // box {32 j_local, 32 i_local, 1 tile}: the pair's tile is one contiguous 256 KB run
-                    tma_store_3d(tm_out_p, blk, (int)rank * 128 + q * 32, c * 32, (ti * p.tiles_j + tj) * p.E + e);
-                else
-                    tma_store_3d(tm_out_p, blk, (int)(j - lane), e, (int)ic);
-                tma_store_commit();
-            }
-            continue;
-        }
-        if (jok) {
-            float *ptr = obase + (size_t)ic * p.stride_i;
+            for (int r = 0; r < 32; r++) ptr[r * 256] = __uint_as_float(v[r]);
+        } else if (jok) {
+            float *ptr = p.out + (size_t)e * p.stride_e + j + (size_t)ic * p.stride_i;
             if (ic + 32 <= p.nb) {
 #pragma unroll
                 for (int r = 0; r < 32; r++) {
@@ -543,7 +516,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(const Gemm2Params &p, const C
             }
         }
     }
-    if (!released) {   // warps that had no chunk in this tile (BN < 64 or ragged row tile)
+    if (!released) {   // warps without a chunk in this tile (BN < 32 * cstep, ragged row tile, diagnostics)
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(&tempty_bar[as], 0);  // accumulator slot free (leader's barrier)
@@ -551,17 +524,14 @@ __device__ __forceinline__ void gemm_epilogue_tile(const Gemm2Params &p, const C
 }
 
 template <int KIND>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_MAX_THREADS, 1)
     k_corr_umma2(const __grid_constant__ CUtensorMap tm_cols, const __grid_constant__ CUtensorMap tm_rows,
-                 const __grid_constant__ CUtensorMap tm_out, const Gemm2Params p)
+                 const Gemm2Params p)
 {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t *tiles = smem;
-    // [GEMM_EPI_WARPS][32 rows i][32 cols j] fp32 staging for the TMA-store epilogue (4 KB per warp)
-    float *staging = reinterpret_cast<float *>(smem + (size_t)p.stages * p.stage_bytes);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)p.stages * p.stage_bytes +
-                                                  (p.tma_store ? GEMM_EPI_WARPS * 4096 : 0));
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)p.stages * p.stage_bytes);
     uint64_t *full_bar = bars;                         // [stages]  used in the leader CTA only
     uint64_t *empty_bar = bars + GEMM_MAX_STAGES;      // [stages]  one per CTA (multicast commit)
     uint64_t *tfull_bar = bars + 2 * GEMM_MAX_STAGES;  // [2]       one per CTA (multicast commit)
@@ -585,7 +555,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
         }
         for (int s = 0; s < 2; s++) {
             mbar_init(&tfull_bar[s], 1);
-            mbar_init(&tempty_bar[s], 2 * GEMM_EPI_WARPS);
+            mbar_init(&tempty_bar[s], 2 * p.epi_warps);
         }
         fence_mbar_init();
     }
@@ -689,196 +659,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
             const long rem = tile - (long)e * tiles_per_e;
             const int tj = (int)(rem / p.tiles_i);
             const int ti = (int)(rem - (long)tj * p.tiles_i);
-            gemm_epilogue_tile(p, &tm_out, staging, tfull_bar, tempty_bar, tmem_base, e, tj, ti, iter, rank, warp, lane);
+            gemm_epilogue_tile(p, tfull_bar, tempty_bar, tmem_base, e, tj, ti, iter, rank, warp, lane);
         }
     }
-    if (p.tma_store && warp >= 4 && lane == 0) tma_store_wait_all();
     tc_fence_before();
     cluster_sync_all();  // no CTA of the pair leaves while its peer may still touch its smem / TMEM
-    if (warp == 2) {
-        tc_fence_after();
-        tmem_dealloc_2sm(tmem_base, 512);
-    }
-}
-
-
-// ---------------------------------------------------------------- pair GEMM with a RESIDENT row operand
-// Measured (profiles/README.md, SW64 experiment): k_corr_umma2 moves ~51 TMA row requests (<= 128 B each)
-// per clock chip-wide -- 2 operand-load rows for every output-store row -- which is the L2 request ceiling
-// (~6300 B/clk), not the tensor pipe (50 % busy).  When the whole-K row operand of a pair (BN rows x Kp x
-// planes, half per CTA) fits in shared memory, the pair keeps it RESIDENT and sweeps a range of 256-column
-// tiles past it: only the column operand streams (one (k-block, plane) tile of 16 KB per ring stage), so
-// the load requests per tile halve.  Work unit = (epoch, column-tile range, row tile), row tile fastest,
-// so the pairs running at the same time stream the same column tiles out of L2.
-template <int KIND>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
-    k_corr_umma_res(const __grid_constant__ CUtensorMap tm_cols, const __grid_constant__ CUtensorMap tm_rows,
-                    const __grid_constant__ CUtensorMap tm_out, const Gemm2Params p)
-{
-    extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t *resident = smem;                                   // [kbs][planes][BN/2 rows][128 B]
-    uint8_t *tiles = smem + p.res_bytes;                        // [stages][128 cols][128 B]
-    float *staging = reinterpret_cast<float *>(tiles + (size_t)p.stages * p.stage_bytes);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(staging) +
-                                                  (p.tma_store ? GEMM_EPI_WARPS * 4096 : 0));
-    uint64_t *full_bar = bars;                         // [stages]  leader only
-    uint64_t *empty_bar = bars + GEMM_MAX_STAGES;      // [stages]  per CTA (multicast commit)
-    uint64_t *tfull_bar = bars + 2 * GEMM_MAX_STAGES;  // [2]       per CTA (multicast commit)
-    uint64_t *tempty_bar = tfull_bar + 2;              // [2]       leader only
-    uint64_t *rfull_bar = tempty_bar + 2;              // [1]       leader only: resident rows of both CTAs landed
-    uint64_t *rempty_bar = rfull_bar + 1;              // [1]       per CTA: the unit's MMAs have retired
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(rempty_bar + 1);
-
-    const int warp = uniform_warp_idx();
-    const int lane = threadIdx.x & 31;
-    const uint32_t rank = cluster_ctarank();
-    const bool leader = rank == 0;
-
-    cluster_sync_all();
-    if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&tm_cols);
-        tma_prefetch_desc(&tm_rows);
-    }
-    if (warp == 1 && lane == 0) {
-        for (int s = 0; s < p.stages; s++) {
-            mbar_init(&full_bar[s], 2);
-            mbar_init(&empty_bar[s], 1);
-        }
-        for (int s = 0; s < 2; s++) {
-            mbar_init(&tfull_bar[s], 1);
-            mbar_init(&tempty_bar[s], 2 * GEMM_EPI_WARPS);
-        }
-        mbar_init(rfull_bar, 2);
-        mbar_init(rempty_bar, 1);
-        fence_mbar_init();
-    }
-    if (warp == 2) {
-        tmem_alloc_2sm(tmem_slot, 512);
-        tmem_relinquish_2sm();
-    }
-    tc_fence_before();
-    cluster_sync_all();
-    tc_fence_after();
-    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // warp-uniform for the compiler
-
-    const long pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
-    const int halfN = p.BN >> 1;
-    const long units_per_e = (long)p.nchunk * p.tiles_i;
-
-    if (warp == 0) {
-        // ------------------------------------------------------------------ TMA producer (both CTAs)
-        if (elect_one_sync()) {
-            int stage = 0;
-            uint32_t phase = 0, rphase = 0;
-            for (long unit = pair; unit < p.total_units; unit += npairs) {
-                const int e = (int)(unit / units_per_e);
-                const long rem = unit - (long)e * units_per_e;
-                const int chunk = (int)(rem / p.tiles_i);
-                const int ti = (int)(rem - (long)chunk * p.tiles_i);
-                const int tj0 = chunk * p.cj;
-                const int tj1 = tj0 + p.cj < p.tiles_j ? tj0 + p.cj : p.tiles_j;
-                const int row0 = (int)(p.row_start + (long)ti * p.BN + (long)rank * halfN);
-                mbar_wait(rempty_bar, rphase ^ 1);     // previous unit no longer reads the resident tiles
-                rphase ^= 1;
-                if (leader)
-                    mbar_expect_tx(rfull_bar, 2 * p.res_bytes);
-                else
-                    mbar_arrive_cluster(rfull_bar, 0);
-                for (int kb = 0; kb < p.kbs; kb++)
-                    for (int pl = 0; pl < p.planes; pl++)
-                        tma_load_3d_2sm(&tm_rows, rfull_bar, resident + (size_t)(kb * p.planes + pl) * p.half_bytes,
-                                        kb * p.bk, row0, pl * p.E + e);
-                for (int tj = tj0; tj < tj1; tj++) {
-                    const int col0 = tj * 256 + (int)rank * 128;
-                    for (int kb = 0; kb < p.kbs; kb++)
-                        for (int pl = 0; pl < p.planes; pl++) {
-                            mbar_wait(&empty_bar[stage], phase ^ 1);
-                            if (leader)
-                                mbar_expect_tx(&full_bar[stage], 2 * p.stage_bytes);
-                            else
-                                mbar_arrive_cluster(&full_bar[stage], 0);
-                            tma_load_3d_2sm(&tm_cols, &full_bar[stage], tiles + (size_t)stage * p.stage_bytes, kb * p.bk,
-                                            col0, pl * p.E + e);
-                            if (++stage == p.stages) {
-                                stage = 0;
-                                phase ^= 1;
-                            }
-                        }
-                }
-            }
-        }
-    } else if (warp == 1) {
-        // ------------------------------------------------------------------ MMA issuer (leader CTA only)
-        if (leader) {
-            const uint32_t idesc = make_idesc(p.fmt, 256, (uint32_t)p.BN);
-            const uint32_t res_addr = smem_u32(resident);
-            const uint32_t tiles_addr = smem_u32(tiles);
-            int stage = 0;
-            uint32_t phase = 0, rphase = 0;
-            long iter = 0;
-            for (long unit = pair; unit < p.total_units; unit += npairs) {
-                const long rem = unit % units_per_e;
-                const int chunk = (int)(rem / p.tiles_i);
-                const int tj0 = chunk * p.cj;
-                const int tj1 = tj0 + p.cj < p.tiles_j ? tj0 + p.cj : p.tiles_j;
-                mbar_wait(rfull_bar, rphase);
-                rphase ^= 1;
-                tc_fence_after();
-                for (int tj = tj0; tj < tj1; tj++, iter++) {
-                    const int as = (int)(iter & 1);
-                    const uint32_t aphase = (uint32_t)((iter >> 1) & 1);
-                    mbar_wait(&tempty_bar[as], aphase ^ 1);
-                    tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.BN);
-                    uint32_t accumulate = 0;
-                    for (int kb = 0; kb < p.kbs; kb++) {
-                        const int rem_k = p.Kp - kb * p.bk;
-                        const int nk = (rem_k < p.bk ? rem_k : p.bk) / p.umma_k;
-                        for (int pl = 0; pl < p.planes; pl++) {
-                            mbar_wait(&full_bar[stage], phase);
-                            tc_fence_after();
-                            if (elect_one_sync()) {
-                                const uint32_t cbase = tiles_addr + (uint32_t)stage * p.stage_bytes;
-                                for (int sgm = 0; sgm < p.segs; sgm++) {
-                                    if (p.seg_c[sgm] != pl) continue;
-                                    issue_kblock_mmas<KIND>(
-                                        d_tmem, cbase, res_addr + (uint32_t)(kb * p.planes + p.seg_r[sgm]) * p.half_bytes,
-                                        idesc, nk, accumulate);
-                                }
-                                tc_commit_2sm(&empty_bar[stage]);
-                                if (kb == p.kbs - 1 && pl == p.planes - 1) {
-                                    tc_commit_2sm(&tfull_bar[as]);
-                                    if (tj == tj1 - 1) tc_commit_2sm(rempty_bar);   // resident tiles may be replaced
-                                }
-                            }
-                            __syncwarp();
-                            if (++stage == p.stages) {
-                                stage = 0;
-                                phase ^= 1;
-                            }
-                        }
-                    }
-                }
-            }
-        }
-    } else if (warp >= 4) {
-        // ------------------------------------------------------------------ epilogue (both CTAs)
-        long iter = 0;
-        for (long unit = pair; unit < p.total_units; unit += npairs) {
-            const int e = (int)(unit / units_per_e);
-            const long rem = unit - (long)e * units_per_e;
-            const int chunk = (int)(rem / p.tiles_i);
-            const int ti = (int)(rem - (long)chunk * p.tiles_i);
-            const int tj0 = chunk * p.cj;
-            const int tj1 = tj0 + p.cj < p.tiles_j ? tj0 + p.cj : p.tiles_j;
-            for (int tj = tj0; tj < tj1; tj++, iter++)
-                gemm_epilogue_tile(p, &tm_out, staging, tfull_bar, tempty_bar, tmem_base, e, tj, ti, iter, rank, warp, lane);
-        }
-    }
-    if (p.tma_store && warp >= 4 && lane == 0) tma_store_wait_all();
-    tc_fence_before();
-    cluster_sync_all();
     if (warp == 2) {
         tc_fence_after();
         tmem_dealloc_2sm(tmem_base, 512);
@@ -928,7 +713,7 @@ static int make_operand_map(CUtensorMap *m, const void *base, const PrecInfo &pi
 
 // self-correlation fix-up: out[i][e][start+i] = exact sequential-FMA r (optionally Fisher-transformed)
 __global__ void k_self_corr_fixup(const float *__restrict__ selfdiag, int E, long V, long start, long nb, float *out,
-                                  long stride_i, long stride_e, int fisher_epochs, long blocked_t256)
+                                  long stride_i, long stride_e, int fisher_epochs, long tiled_t256)
 {
     const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= nb * E) return;
@@ -937,47 +722,17 @@ __global__ void k_self_corr_fixup(const float *__restrict__ selfdiag, int E, lon
     float r = selfdiag[(size_t)e * V + start + i];
     if (e < fisher_epochs) r = fisher_fast(r);
     const long j = start + i;
-    if (blocked_t256 > 0)   // tiled [i/256][j/256][e][i%256][j%256]
-        out[((((size_t)(i >> 8) * blocked_t256 + (j >> 8)) * E + e) * 256 + (i & 255)) * 256 + (j & 255)] = r;
+    if (tiled_t256 > 0)   // tiled [i/256][j/256][e][i%256][j%256]
+        out[((((size_t)(i >> 8) * tiled_t256 + (j >> 8)) * E + e) * 256 + (i & 255)) * 256 + (j & 255)] = r;
     else
         out[(size_t)i * stride_i + (size_t)e * stride_e + j] = r;
 }
 
-// output tensor out[i*stride_i + e*stride_e + j] as a 3-D TMA tensor (j, e, i), box {32, 1, 32}, no swizzle
-static int make_out_map(CUtensorMap *m, float *out, long V2, int E, long nb, long stride_i, long stride_e)
-{
-    PFN_tmEncodeTiled enc = get_encode_fn();
-    if (!enc) return fail(FCMA_ECUDA, "cuTensorMapEncodeTiled entry point not available");
-    cuuint64_t gdim[3] = {(cuuint64_t)V2, (cuuint64_t)E, (cuuint64_t)nb};
-    cuuint64_t gstr[2] = {(cuuint64_t)stride_e * 4, (cuuint64_t)stride_i * 4};
-    cuuint32_t box[3] = {32, 1, 32};
-    cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, out, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return fail(FCMA_ECUDA, "cuTensorMapEncodeTiled(out) failed with CUresult %d", (int)r);
-    return FCMA_OK;
-}
-
-// tiled output [tiles_i*T256*E][256 i][256 j] as a 3-D TMA tensor (j_local, i_local, tile), box {32, 32, 1}
-static int make_out_map_blocked(CUtensorMap *m, float *out, int E, long nb, long t256)
-{
-    PFN_tmEncodeTiled enc = get_encode_fn();
-    if (!enc) return fail(FCMA_ECUDA, "cuTensorMapEncodeTiled entry point not available");
-    cuuint64_t gdim[3] = {256, 256, (cuuint64_t)cdiv(nb, 256) * t256 * E};
-    cuuint64_t gstr[2] = {1024, 256 * 1024};
-    cuuint32_t box[3] = {32, 32, 1};
-    cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, out, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return fail(FCMA_ECUDA, "cuTensorMapEncodeTiled(tiled out) failed with CUresult %d", (int)r);
-    return FCMA_OK;
-}
-
-// blocked_t256 > 0: write the block in the tiled layout [ceil(nb/256)][blocked_t256][E][256][256] (TMA-store
-// epilogue only; the caller provides round_up(nb, 256) rows of workspace)
+// tiled_t256 > 0: write the block in the tiled layout [ceil(nb/256)][tiled_t256][E][256][256] (the caller
+// provides round_up(nb, 256) rows of workspace and tiled_t256 == ceil(V2/256)); else out[i*stride_i + e*stride_e + j]
 static int launch_corr_umma(const void *rows_op, const void *cols_op, int precision, int E, int T, long V, long V2,
                             long start, long nb, float *out, long stride_i, long stride_e, int fisher_epochs,
-                            cudaStream_t st, long blocked_t256 = 0)
+                            cudaStream_t st, long tiled_t256 = 0)
 {
     PrecInfo pi;
     if (!prec_info(precision, &pi)) return fail(FCMA_EINVAL, "unknown precision %d", precision);
@@ -1002,85 +757,40 @@ static int launch_corr_umma(const void *rows_op, const void *cols_op, int precis
     q.fmt = pi.fmt, q.out_scale = 1.0f / (pi.in_scale * pi.in_scale);
     q.half_bytes = (uint32_t)(q.BN / 2) * 128;
     q.stage_bytes = (uint32_t)pi.planes * (16384 + q.half_bytes);
-    // TMA-store epilogue needs 16-byte aligned rows of the output and 4 KB of staging per epilogue warp
-    const char *nts = getenv("FCMA_GEMM_NO_TMA_STORE");
-    const bool no_tma_store = nts && nts[0] == '1';
-    q.tma_store = (!no_tma_store && (stride_i % 4 == 0) && (stride_e % 4 == 0) && (((uintptr_t)out & 15) == 0)) ? 1 : 0;
-    q.blocked = blocked_t256 > 0 ? 1 : 0;
-    if (q.blocked && (!q.tma_store || blocked_t256 != q.tiles_j))
-        return fail(FCMA_EINVAL, "internal: blocked output needs the TMA-store epilogue and T256 == tiles_j");
-    const size_t staging_bytes = q.tma_store ? (size_t)GEMM_EPI_WARPS * 4096 : 0;
-    const size_t cap = 227 * 1024 - 1024 /*alignment slack*/ - 256 /*barriers*/;
-    long pairs = g_sm_count / 2;
-
-    // resident-row-operand kernel (opt-in, FCMA_GEMM_RESIDENT=1; needs the pair's whole-K row tile + >= 4 column
-    // stages in shared memory): halves the operand loads but runs 8 instead of 4 stage rounds per tile and is
-    // not faster than the streaming kernel on B200 (tools/ab_resident.py) -- kept for the measurement.
+    q.tiled = tiled_t256 > 0 ? 1 : 0;
+    if (q.tiled && tiled_t256 != q.tiles_j) return fail(FCMA_EINVAL, "internal: tiled output needs T256 == tiles_j");
     {
+        // tuning / diagnostic knobs, read per launch (tools/ab_env.py, tools/gemm_debug.py)
+        const char *ew = getenv("FCMA_GEMM_EPI_WARPS");      // 8: two epilogue warps per TMEM lane quadrant instead of four
+        q.epi_warps = (ew && atoi(ew) == 8) ? 8 : 16;
         const char *dbg = getenv("FCMA_GEMM_DEBUG");
         q.debug = dbg ? atoi(dbg) : 0;
+        const char *sched = getenv("FCMA_GEMM_SCHED");       // 1: a pair takes all row tiles of a column tile in a row
+        q.grp_tiles = (sched && sched[0] == '1') ? q.tiles_i : 1;
     }
-    const char *res_env = getenv("FCMA_GEMM_RESIDENT");
-    q.res_bytes = (uint32_t)q.kbs * pi.planes * q.half_bytes;
-    bool resident = (res_env && res_env[0] == '1') && (size_t)q.res_bytes + staging_bytes + 4 * 16384 <= cap;
-    if (resident) {
-        q.stage_bytes = 16384;
-        // work units (epoch, column-tile chunk, row tile): enough of them to balance the pairs
-        const long base = (long)E * q.tiles_i;
-        long best_n = 1;
-        double best_eff = 0;
-        for (long n = 1; n <= q.tiles_j && n <= 64; n++) {
-            const long cj = cdiv(q.tiles_j, n), nn = cdiv(q.tiles_j, cj);
-            const long units = base * nn;
-            const long rounds = cdiv(units, pairs);
-            // cost model: rounds * (cj tiles + ~1 tile of resident reload) vs ideal units*cj/pairs
-            const double eff = ((double)units * cj / pairs) / ((double)rounds * (cj + 1.0));
-            if (eff > best_eff + 1e-9) best_eff = eff, best_n = nn;
-            if (units >= 16 * pairs) break;
-        }
-        q.cj = (int)cdiv(q.tiles_j, best_n);
-        q.nchunk = (int)cdiv(q.tiles_j, q.cj);
-        q.total_units = base * q.nchunk;
-    }
-    int stages = (int)((cap - staging_bytes - (resident ? q.res_bytes : 0)) / q.stage_bytes);
+    const size_t cap = 227 * 1024 - 1024 /*alignment slack*/ - 256 /*barriers*/;
+    int stages = (int)(cap / q.stage_bytes);
     if (stages > GEMM_MAX_STAGES) stages = GEMM_MAX_STAGES;
     if (stages < 2) return fail(FCMA_EINVAL, "internal: not enough shared memory for 2 stages");
     q.stages = stages;
-    const size_t smem = (resident ? q.res_bytes : 0) + (size_t)stages * q.stage_bytes + staging_bytes + 1024 + 256;
-    {
-        const char *sched = getenv("FCMA_GEMM_SCHED");   // tuning knob: 1 = a pair takes all row tiles of a column tile
-        q.grp_tiles = (sched && sched[0] == '1') ? q.tiles_i : 1;
-    }
+    const size_t smem = (size_t)stages * q.stage_bytes + 1024 + 256;
 
-    CUtensorMap tm_cols, tm_rows, tm_out;
+    CUtensorMap tm_cols, tm_rows;
     int rc = make_operand_map(&tm_cols, cols_op, pi, E, V2, Kp, 128);
     if (rc) return rc;
     rc = make_operand_map(&tm_rows, rows_op, pi, E, V, Kp, q.BN / 2);
     if (rc) return rc;
-    if (q.blocked)
-        rc = make_out_map_blocked(&tm_out, out, E, nb, blocked_t256);
-    else if (q.tma_store)
-        rc = make_out_map(&tm_out, out, V2, E, nb, stride_i, stride_e);
-    else
-        memset(&tm_out, 0, sizeof(tm_out));
-    if (rc) return rc;
 
-    const long ngroups = resident ? q.total_units : q.total_tiles / q.grp_tiles;
+    long pairs = g_sm_count / 2;
+    const unsigned gemm_threads = 128u + 32u * (unsigned)q.epi_warps;
+    const long ngroups = q.total_tiles / q.grp_tiles;
     if (ngroups < pairs) pairs = ngroups;
-    if (resident) {
-        if (pi.kind == 0) {
-            CUDA_TRY(cudaFuncSetAttribute(k_corr_umma_res<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_corr_umma_res<0><<<(unsigned)(2 * pairs), GEMM_THREADS, smem, st>>>(tm_cols, tm_rows, tm_out, q);
-        } else {
-            CUDA_TRY(cudaFuncSetAttribute(k_corr_umma_res<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_corr_umma_res<1><<<(unsigned)(2 * pairs), GEMM_THREADS, smem, st>>>(tm_cols, tm_rows, tm_out, q);
-        }
-    } else if (pi.kind == 0) {
+    if (pi.kind == 0) {
         CUDA_TRY(cudaFuncSetAttribute(k_corr_umma2<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_corr_umma2<0><<<(unsigned)(2 * pairs), GEMM_THREADS, smem, st>>>(tm_cols, tm_rows, tm_out, q);
+        k_corr_umma2<0><<<(unsigned)(2 * pairs), gemm_threads, smem, st>>>(tm_cols, tm_rows, q);
     } else {
         CUDA_TRY(cudaFuncSetAttribute(k_corr_umma2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_corr_umma2<1><<<(unsigned)(2 * pairs), GEMM_THREADS, smem, st>>>(tm_cols, tm_rows, tm_out, q);
+        k_corr_umma2<1><<<(unsigned)(2 * pairs), gemm_threads, smem, st>>>(tm_cols, tm_rows, q);
     }
     LAUNCH_CHECK("k_corr_umma2");
 
@@ -1090,7 +800,7 @@ static int launch_corr_umma(const void *rows_op, const void *cols_op, int precis
                                                           operand_plane_bytes(pi, precision, E, T, V));
         long n = nb * E;
         k_self_corr_fixup<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(sd, E, V, start, nb, out, stride_i, stride_e,
-                                                                 fisher_epochs, blocked_t256);
+                                                                 fisher_epochs, tiled_t256);
         LAUNCH_CHECK("k_self_corr_fixup");
     }
     return FCMA_OK;
@@ -1695,7 +1405,7 @@ static int launch_norm_syrk(const float *C, long nb, int E, long n2, long stride
         LAUNCH_CHECK("k_scale");
     }
     const bool vec = ((ld & 3) == 0) && ((stride_i & 3) == 0) && (((uintptr_t)C & 15) == 0);
-    if (!vec && chunk_step != 256) return fail(FCMA_EINVAL, "internal: blocked layout needs the vector path");
+    if (!vec && chunk_step != 256) return fail(FCMA_EINVAL, "internal: tiled layout needs the vector path");
     const bool fisher = eps_mode > 0 && !fisher_done;
     // rows cost the same: a static stride over 16 blocks per SM balances well
     long g = nb < 16L * g_sm_count ? nb : 16L * g_sm_count;
@@ -1883,12 +1593,6 @@ extern "C" long fcma_timing_read(double *gemm_ms, double *syrk_ms)
 }
 
 // shared body of the two fused pipelines
-static bool env_is_one(const char *name)
-{
-    const char *v = getenv(name);
-    return v && v[0] == '1';
-}
-
 static int run_pipeline(const void *rows_op, const void *cols_op, int precision, int E, int T, long V, long V2, long start,
                         long nb, int eps, int flags, float *work, size_t work_bytes, float *K, int sum_over_rows,
                         cudaStream_t st)
@@ -1917,8 +1621,7 @@ static int run_pipeline(const void *rows_op, const void *cols_op, int precision,
     // FCMA_NO_TILED=1 falls back to the strided [i][e][j] block.
     const char *no_tiled = getenv("FCMA_NO_TILED");
     const long t256 = cdiv(V2, 256);
-    const bool blocked = !(no_tiled && no_tiled[0] == '1') && !env_is_one("FCMA_GEMM_NO_TMA_STORE") && fused &&
-                         V2 < (1L << 31) && rows_per_pass >= 256;
+    const bool tiled = !(no_tiled && no_tiled[0] == '1') && fused && V2 < (1L << 31) && rows_per_pass >= 256;
     for (long done = 0; done < nb; done += rows_per_pass) {
         const long n = nb - done < rows_per_pass ? nb - done : rows_per_pass;
         int rc;
@@ -1927,7 +1630,7 @@ static int run_pipeline(const void *rows_op, const void *cols_op, int precision,
             for (int k = 0; k < 3; k++) CUDA_TRY(cudaEventCreate(&ev[k]));
             CUDA_TRY(cudaEventRecord(ev[0], st));
         }
-        if (blocked)
+        if (tiled)
             rc = launch_corr_umma(rows_op, cols_op, precision, E, T, V, V2, start + done, n, work, 4, 4,
                                   fisher_in_gemm ? S_eps : 0, st, t256);
         else
@@ -1937,7 +1640,7 @@ static int run_pipeline(const void *rows_op, const void *cols_op, int precision,
         if (g_timing_on) CUDA_TRY(cudaEventRecord(ev[1], st));
         float *Kdst = sum_over_rows ? K : K + (size_t)done * E * E;
         const float beta = sum_over_rows ? 1.0f : 0.0f;
-        if (blocked) {
+        if (tiled) {
             rc = launch_norm_syrk(work, n, E, V2, 256, 65536, normalise ? eps : 0, (normalise && fisher_in_gemm) ? 1 : 0,
                                   mask_self ? start + done : -1, beta, Kdst, sum_over_rows, st, (long)E * 65536);
         } else if (normalise && fused) {

@@ -163,17 +163,6 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr)
     return d;
 }
 
-// same for a 64-byte swizzle atom (rows of 64 B, 8-row groups 512 B apart): half the bytes per stage,
-// so twice the stages fit in shared memory for the same tile shape
-__device__ __forceinline__ uint64_t make_smem_desc_sw64(uint32_t smem_addr)
-{
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
-    d |= (uint64_t)(512 >> 4) << 32;                   // SBO
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)4 << 61;                            // SWIZZLE_64B
-    return d;
-}
 
 // instruction descriptor for kind::f16 / kind::tf32, fp32 accumulate, both operands K-major
 //   [4,6) D format (1 = f32) | [7,10) A format | [10,13) B format (1 = bf16, 2 = tf32)
@@ -202,32 +191,6 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
 __device__ __forceinline__ void tmem_ld_wait()
 {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// ---------------------------------------------------------------- TMA store (shared -> global)
-__device__ __forceinline__ void fence_proxy_async_smem()
-{
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
-__device__ __forceinline__ void tma_store_3d(const CUtensorMap *m, const void *smem_src, int c0, int c1, int c2)
-{
-    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
-                 :
-                 : "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
-                 : "memory");
-}
-__device__ __forceinline__ void tma_store_commit()
-{
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-}
-// wait until the bulk groups of this thread have finished READING their shared-memory source
-__device__ __forceinline__ void tma_store_wait_read0()
-{
-    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-}
-__device__ __forceinline__ void tma_store_wait_all()
-{
-    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 // ---------------------------------------------------------------- cp.async (LDGSTS) with zero fill

@@ -36,7 +36,6 @@ def run(label, fn, secs=1.5):
     print(f"{label:34s} {e0.elapsed_time(e1)/n:7.3f} ms/launch  SM {mhz:6.0f} MHz  {w:6.0f} W", flush=True)
 for prec in ("fp16x3", "bf16", "tf32x3"):
     rows = engine.pack_epochs(ep, None, prec)
-    os.environ["FCMA_GEMM_RESIDENT"] = "1"
     for dbg in sys.argv[1:] or ("0", "4", "20"):
         os.environ["FCMA_GEMM_DEBUG"] = dbg
         run(f"gemm {prec} stream debug={dbg}", lambda: engine.corr_block(rows, rows, 0, nb, out=cbuf, ld=ld))

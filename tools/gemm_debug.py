@@ -1,19 +1,14 @@
 #!/usr/bin/env python
-"""Bottleneck diagnosis of the pair GEMM: time it with parts of the epilogue switched off
-(FCMA_GEMM_DEBUG bit mask: 1 no stores, 2 no TMEM load/math/fill, 4 no epilogue work,
-8 one extra tcgen05.commit per MMA segment) in the
-resident and the streaming variant.  Outputs are WRONG while a bit is set -- timing only."""
+"""Where does the pair GEMM's time go?  Times one launch (4096 rows x 50 000 columns x 32 epochs) with parts
+switched off through FCMA_GEMM_DEBUG (outputs are WRONG while a bit is set -- timing only):
+   0  full kernel            4  main loop only (TMA loads + MMAs, epilogue warps just hand TMEM back)
+  20  MMAs only (stale shared-memory stages are re-read: no loads, no epilogue)
+and for T = 64 .. 256 (1 .. 4 k-blocks of 64) to expose per-stage costs.   python tools/gemm_debug.py [prec ...]"""
 import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from brainiak_b200.fcma import engine
-V, T, E, nb = 50000, 200, 32, 4096
+V, E, nb = 50000, 32, 4096
 dev = torch.device("cuda:0")
-g = torch.Generator(device=dev).manual_seed(0)
-ep = torch.randn((E, T, V), device=dev, generator=g)
-engine.epoch_normalize_(ep)
-work = engine.Workspace(E, V, nb, dev)
-ld = ((V + 31) // 32) * 32
-cbuf = work.buf.view(torch.float32)[: nb * E * ld].view(nb, E, ld)
 def timeit(fn, n=3):
     fn(); torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -21,14 +16,20 @@ def timeit(fn, n=3):
     for _ in range(n): fn()
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / n
-for prec in sys.argv[1:] or ("bf16", "fp16x3"):
-    rows = engine.pack_epochs(ep, None, prec)
-    for nores in ("0", "1"):
-        os.environ["FCMA_GEMM_RESIDENT"] = nores
-        for dbg in (0, 4, 12):
+work = engine.Workspace(E, V, nb, dev)
+ld = ((V + 31) // 32) * 32
+cbuf = work.buf.view(torch.float32)[: nb * E * ld].view(nb, E, ld)
+for T in (200, 64, 128, 192, 256):
+    g = torch.Generator(device=dev).manual_seed(0)
+    ep = torch.randn((E, T, V), device=dev, generator=g)
+    engine.epoch_normalize_(ep)
+    for prec in sys.argv[1:] or ("fp16x3", "bf16"):
+        rows = engine.pack_epochs(ep, None, prec)
+        out = []
+        for dbg in (0, 4, 20):
             os.environ["FCMA_GEMM_DEBUG"] = str(dbg)
-            ms = timeit(lambda: engine.corr_block(rows, rows, 0, nb, out=cbuf, ld=ld))
-            msf = timeit(lambda: engine.corr_block(rows, rows, 0, nb, out=cbuf, ld=ld, fisher_epochs=E))
-            print(f"{prec:7s} resident={'yes' if nores=='1' else 'no '} debug={dbg}: gemm {ms:7.3f} ms   +fisher {msf:7.3f} ms", flush=True)
-    del rows
+            out.append(min(timeit(lambda: engine.corr_block(rows, rows, 0, nb, out=cbuf, ld=ld, fisher_epochs=E)) for _ in range(2)))
+        print(f"T={T:3d} {prec:7s}: full(+fisher) {out[0]:7.3f} ms   main loop only {out[1]:7.3f} ms   MMAs only {out[2]:7.3f} ms", flush=True)
+        del rows
+    del ep
 os.environ["FCMA_GEMM_DEBUG"] = "0"

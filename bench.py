@@ -343,6 +343,11 @@ def run_b200_arm(args):
                         "k_corr_umma": {"ms": tg, "hbm_gbs": alg_bytes / (tg * 1e-3) / 1e9,
                                         "tensor_tflops_alg": 2.0 * T * corr_launch / (tg * 1e-3) / 1e12,
                                         "tensor_frac_of_bf16_sustained": 2.0 * T * corr_launch / (tg * 1e-3) / 1e12 / tf_peak,
+                                        # MMAs actually issued: padded K, and 3 products in the hi/lo split modes
+                                        "tensor_tflops_executed": (3 if planes == 2 else 1) * 2.0 * lib.fcma_operand_kp(_lib.PREC[prec], T)
+                                        * corr_launch / (tg * 1e-3) / 1e12,
+                                        "tensor_executed_frac_of_bf16_sustained": (3 if planes == 2 else 1) * 2.0
+                                        * lib.fcma_operand_kp(_lib.PREC[prec], T) * corr_launch / (tg * 1e-3) / 1e12 / tf_peak,
                                         "operand_planes": planes},
                         "k_norm_syrk": {"ms": ts, "hbm_gbs": 4.0 * corr_launch / (ts * 1e-3) / 1e9}}}
 

@@ -380,16 +380,18 @@ __device__ __forceinline__ float fisher_fast(float r)
 // two-logarithm form with the reference's clamps otherwise.  The two XU ops per element of fisher_fast
 // were ~1/3 of the epilogue's time (profiles/README.md).
 constexpr float FISHER_SERIES_MAX = 0.35f;
-__device__ __forceinline__ float fisher_series(float r)
+// two accumulators at once (packed fp32x2 FMAs): returns atanh(a * scale)
+__device__ __forceinline__ float2 fisher_series2(float2 a, float scale)
 {
-    const float x2 = r * r;
-    float p = 0.076923076923f;            // 1/13
-    p = fmaf(p, x2, 0.090909090909f);     // 1/11
-    p = fmaf(p, x2, 0.111111111111f);     // 1/9
-    p = fmaf(p, x2, 0.142857142857f);     // 1/7
-    p = fmaf(p, x2, 0.2f);
-    p = fmaf(p, x2, 0.333333333333f);
-    return fmaf(r * x2, p, r);
+    const float2 zero = splat2(0.f);
+    const float2 r = ffma2(a, splat2(scale), zero);
+    const float2 x2 = ffma2(r, r, zero);
+    float2 p = ffma2(splat2(0.076923076923f), x2, splat2(0.090909090909f));   // 1/13, 1/11
+    p = ffma2(p, x2, splat2(0.111111111111f));                                 // 1/9
+    p = ffma2(p, x2, splat2(0.142857142857f));                                 // 1/7
+    p = ffma2(p, x2, splat2(0.2f));
+    p = ffma2(p, x2, splat2(0.333333333333f));
+    return ffma2(ffma2(r, x2, zero), p, r);
 }
 
 // ---------------------------------------------------------------- CTA pairs (cta_group::2)
@@ -482,15 +484,28 @@ __device__ __forceinline__ void gemm_epilogue_tile(const Gemm2Params &p, uint64_
 #pragma unroll
             for (int r = 0; r < 32; r++) m = fmaxf(m, fabsf(__uint_as_float(v[r])));
             if (__any_sync(0xffffffffu, m * osc > FISHER_SERIES_MAX)) {
+                // rare chunk with a large |r|: every ELEMENT still picks its form by its own value, so the
+                // result of an element never depends on its neighbours (= on how rows are split into blocks
+                // or over GPUs)
 #pragma unroll
-                for (int r = 0; r < 32; r++) v[r] = __float_as_uint(fisher_fast(__uint_as_float(v[r]) * osc));
+                for (int r = 0; r < 32; r++) {
+                    const float x = __uint_as_float(v[r]) * osc;
+                    const float2 s = fisher_series2(make_float2(__uint_as_float(v[r]), 0.f), osc);
+                    v[r] = __float_as_uint(fabsf(x) > FISHER_SERIES_MAX ? fisher_fast(x) : s.x);
+                }
             } else {
 #pragma unroll
-                for (int r = 0; r < 32; r++) v[r] = __float_as_uint(fisher_series(__uint_as_float(v[r]) * osc));
+                for (int r = 0; r < 32; r += 2) {
+                    const float2 z = fisher_series2(make_float2(__uint_as_float(v[r]), __uint_as_float(v[r + 1])), osc);
+                    v[r] = __float_as_uint(z.x), v[r + 1] = __float_as_uint(z.y);
+                }
             }
         } else {
 #pragma unroll
-            for (int r = 0; r < 32; r++) v[r] = __float_as_uint(__uint_as_float(v[r]) * osc);
+            for (int r = 0; r < 32; r += 2) {
+                const float2 z = ffma2(make_float2(__uint_as_float(v[r]), __uint_as_float(v[r + 1])), splat2(osc), splat2(0.f));
+                v[r] = __float_as_uint(z.x), v[r + 1] = __float_as_uint(z.y);
+            }
         }
         if (p.tiled) {
             // the pair's 256x256 tile of epoch e is one contiguous 256 KB run, row pitch 1 KB; rows >= nb and
@@ -1206,7 +1221,16 @@ __global__ void __launch_bounds__(256, (R == 4 ? 2 : 1))
                                 for (int u = 0; u < 4; u++) vals[r][h][u] = fisher_log2(vals[r][h][u]);
                         }
                 }
-                // ---- per (subject, column) mean / variance
+                // ---- per (subject, column) mean / variance, two adjacent columns per packed fp32x2 op.
+                // nm = -mean, negvar = mean^2 - E[z^2] (both exact rescalings: EPS is a power of two)
+                auto finish = [&](float2 msum, float2 s2sum, float2 &inv, float2 &mi) {
+                    const float2 nm = ffma2(msum, splat2(-1.0f / EPS), splat2(0.f));
+                    const float2 ns2 = ffma2(s2sum, splat2(-1.0f / EPS), splat2(0.f));
+                    const float2 negvar = ffma2(nm, nm, ns2);
+                    inv.x = negvar.x >= 0.f ? 0.f : rsqrt_ftz(-negvar.x);
+                    inv.y = negvar.y >= 0.f ? 0.f : rsqrt_ftz(-negvar.y);
+                    mi = ffma2(nm, inv, splat2(0.f));
+                };
                 if constexpr (EPS <= R) {
                     constexpr int G = EPS > 0 ? R / EPS : 1;
 #pragma unroll
@@ -1215,22 +1239,23 @@ __global__ void __launch_bounds__(256, (R == 4 ? 2 : 1))
 #pragma unroll
                         for (int h = 0; h < 2; h++)
 #pragma unroll
-                            for (int u = 0; u < 4; u++) {
-                                float m = 0.f, s2 = 0.f;
+                            for (int u = 0; u < 4; u += 2) {
+                                float2 m = splat2(0.f), s2 = splat2(0.f);
 #pragma unroll
                                 for (int b = 0; b < EPS; b++) {
-                                    float x = vals[q * EPS + b][h][u];
-                                    m += x;
-                                    s2 = fmaf(x, x, s2);
+                                    const float2 x = make_float2(vals[q * EPS + b][h][u], vals[q * EPS + b][h][u + 1]);
+                                    m = ffma2(x, splat2(1.f), m);
+                                    s2 = ffma2(x, x, s2);
                                 }
-                                m *= (1.0f / EPS);
-                                float var = s2 * (1.0f / EPS) - m * m;
-                                float inv = var <= 0.f ? 0.f : rsqrt_ftz(var);
+                                float2 inv, mi;
+                                finish(m, s2, inv, mi);
                                 if (valid) {
-                                    const float mi = -m * inv;
 #pragma unroll
-                                    for (int b = 0; b < EPS; b++)
-                                        vals[q * EPS + b][h][u] = fmaf(vals[q * EPS + b][h][u], inv, mi);
+                                    for (int b = 0; b < EPS; b++) {
+                                        const float2 z = ffma2(
+                                            make_float2(vals[q * EPS + b][h][u], vals[q * EPS + b][h][u + 1]), inv, mi);
+                                        vals[q * EPS + b][h][u] = z.x, vals[q * EPS + b][h][u + 1] = z.y;
+                                    }
                                 }
                             }
                     }
@@ -1240,26 +1265,29 @@ __global__ void __launch_bounds__(256, (R == 4 ? 2 : 1))
 #pragma unroll
                     for (int h = 0; h < 2; h++)
 #pragma unroll
-                        for (int u = 0; u < 4; u++) {
-                            float m = 0.f, s2 = 0.f;
+                        for (int u = 0; u < 4; u += 2) {
+                            float2 m = splat2(0.f), s2 = splat2(0.f);
 #pragma unroll
                             for (int r = 0; r < R; r++) {
-                                float x = vals[r][h][u];
-                                m += x;
-                                s2 = fmaf(x, x, s2);
+                                const float2 x = make_float2(vals[r][h][u], vals[r][h][u + 1]);
+                                m = ffma2(x, splat2(1.f), m);
+                                s2 = ffma2(x, x, s2);
                             }
 #pragma unroll
                             for (int o = 1; o < L; o <<= 1) {
-                                m += __shfl_xor_sync(0xffffffffu, m, 4 * o);
-                                s2 += __shfl_xor_sync(0xffffffffu, s2, 4 * o);
+                                m.x += __shfl_xor_sync(0xffffffffu, m.x, 4 * o);
+                                m.y += __shfl_xor_sync(0xffffffffu, m.y, 4 * o);
+                                s2.x += __shfl_xor_sync(0xffffffffu, s2.x, 4 * o);
+                                s2.y += __shfl_xor_sync(0xffffffffu, s2.y, 4 * o);
                             }
-                            m *= (1.0f / EPS);
-                            float var = s2 * (1.0f / EPS) - m * m;
-                            float inv = var <= 0.f ? 0.f : rsqrt_ftz(var);
+                            float2 inv, mi;
+                            finish(m, s2, inv, mi);
                             if (valid) {
-                                const float mi = -m * inv;
 #pragma unroll
-                                for (int r = 0; r < R; r++) vals[r][h][u] = fmaf(vals[r][h][u], inv, mi);
+                                for (int r = 0; r < R; r++) {
+                                    const float2 z = ffma2(make_float2(vals[r][h][u], vals[r][h][u + 1]), inv, mi);
+                                    vals[r][h][u] = z.x, vals[r][h][u + 1] = z.y;
+                                }
                             }
                         }
                 }

@@ -230,6 +230,37 @@ def test_kernels_and_pipeline_vs_oracle(dev, case):
         assert np.max(np.abs(Kh - Kref)) <= k_tol(n2) * scale
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("two", [False, True])
+def test_tiled_intermediate_equals_strided(dev, two, monkeypatch):
+    """Fused pipeline with >= 256 rows of workspace stores the correlation block tiled
+    [nb/256][V2/256][E][256][256]; FCMA_NO_TILED=1 forces the reference's [nb][E][V2] layout.  Ragged last
+    row tile (600 = 2*256 + 88), ragged last column tile, self columns crossing tile borders."""
+    V, V2, T, E, eps, start, nb = 700, (530 if two else None), 40, 8, 4, 77, 600
+    raw, _ = synthetic.make_epochs(V, T, E, seed=777)
+    raw2 = synthetic.make_epochs(V2, T, E, seed=778)[0] if two else None
+    n2 = V2 or V
+    _, z, _ = orc.voxel_block(raw, raw2, start, nb, eps, shrink=False)
+    Kref = orc.kernel_matrices(z if two else zero_self(z, start), f64=True)
+    ep, T_e = engine.stack_epochs(raw, dev)
+    rows = engine.pack_epochs(ep, T_e, "fp32")
+    cols = engine.pack_epochs(engine.stack_epochs(raw2, dev)[0], T_e, rows.precision) if two else rows
+    fl = 0 if two else _lib.FLAG_MASK_SELF
+    work = engine.Workspace(E, n2, 768, dev)
+    out = {}
+    for no_tiled in ("0", "1"):
+        monkeypatch.setenv("FCMA_NO_TILED", no_tiled)
+        work.buf.view(torch.float32).fill_(float("nan"))   # stale padding must never reach the kernels
+        out[no_tiled] = engine.voxel_kernels(rows, cols, start, nb, eps, flags=fl, work=work).cpu().numpy()
+    assert np.array_equal(out["0"], out["1"])
+    assert np.max(np.abs(out["0"] - Kref)) <= k_tol(n2) * np.max(np.abs(Kref))
+    # several passes through a 256-row workspace (tiled, one row tile per pass)
+    monkeypatch.setenv("FCMA_NO_TILED", "0")
+    small = engine.Workspace(E, n2, 256, dev)
+    got = engine.voxel_kernels(rows, cols, start, nb, eps, flags=fl, work=small).cpu().numpy()
+    assert np.array_equal(got, out["0"])
+
+
 def test_pipeline_vs_reference_golden_kernels(dev, golden):
     g = golden("vs_mid")
     d1, d2 = list(g["d1"]), list(g["d2"])

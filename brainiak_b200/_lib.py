@@ -15,6 +15,7 @@ PREC = {"bf16": 0, "tf32": 1, "bf16x3": 2, "tf32x3": 3, "f32simt": 4, "fp16x3": 
 PREC_NAMES = tuple(PREC) + ("fp32",)      # "fp32" = auto-select fp16x3 / tf32x3 (engine.resolve_precision)
 FLAG_MASK_SELF = 1
 FLAG_FISHER_IN_PASS2 = 2
+FLAG_F16_INTERMEDIATE = 4   # fp16 internal Fisher-z block (default only in the bf16 / tf32 operand modes)
 
 c_void_p, c_int, c_long, c_size_t, c_float = (ctypes.c_void_p, ctypes.c_int, ctypes.c_long,
                                                ctypes.c_size_t, ctypes.c_float)

@@ -19,6 +19,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <type_traits>
 
 #include <atomic>
 #include <mutex>
@@ -380,6 +381,17 @@ __device__ __forceinline__ float fisher_fast(float r)
 // two-logarithm form with the reference's clamps otherwise.  The two XU ops per element of fisher_fast
 // were ~1/3 of the epilogue's time (profiles/README.md).
 constexpr float FISHER_SERIES_MAX = 0.35f;
+// scalar form, bit-identical to one lane of fisher_series2 (same fma.rn sequence)
+__device__ __forceinline__ float fisher_series1(float r)
+{
+    const float x2 = fmaf(r, r, 0.f);
+    float p = fmaf(0.076923076923f, x2, 0.090909090909f);
+    p = fmaf(p, x2, 0.111111111111f);
+    p = fmaf(p, x2, 0.142857142857f);
+    p = fmaf(p, x2, 0.2f);
+    p = fmaf(p, x2, 0.333333333333f);
+    return fmaf(fmaf(r, x2, 0.f), p, r);
+}
 // two accumulators at once (packed fp32x2 FMAs): returns atanh(a * scale)
 __device__ __forceinline__ float2 fisher_series2(float2 a, float scale)
 {
@@ -416,7 +428,8 @@ struct Gemm2Params {
     int stages;
     int fmt;                       // idesc operand format
     float out_scale;               // accumulator scale applied in the epilogue
-    int tiled;                     // 1: output is tiled [tiles_i][tiles_j][E][256][256]; 0: strided [i][e][j]
+    int tiled;                     // 1: output is tiled [tiles_i][tiles_j][E][256][256] fp32, 2: same in fp16;
+                                   // 0: strided fp32 [i][e][j]
     int epi_warps;                 // 8 or 16 epilogue warps (blockDim = 128 + 32 * epi_warps)
     int debug;                     // FCMA_GEMM_DEBUG (diagnostics only; output is wrong when set):
                                    //   4 no epilogue work (main loop only), 16 MMAs re-read stale stages (no loads)
@@ -446,6 +459,7 @@ __device__ __forceinline__ void issue_kblock_mmas(uint32_t d_tmem, uint32_t addr
 // warp store.  Called by the epilogue warps of both CTAs; `iter` is the pair's running tile count
 // (selects the TMEM stage).  Warp w may only touch TMEM lanes 32*(w%4)..+31, so the epi_warps/4 warps
 // of a lane quadrant split the BN accumulator columns (voxel rows i) in chunks of 32.
+template <bool HALF_OUT>
 __device__ __forceinline__ void gemm_epilogue_tile(const Gemm2Params &p, uint64_t *tfull_bar, uint64_t *tempty_bar,
                                                    uint32_t tmem_base, int e, int tj, int ti, long iter, uint32_t rank,
                                                    int warp, int lane)
@@ -490,8 +504,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(const Gemm2Params &p, uint64_
 #pragma unroll
                 for (int r = 0; r < 32; r++) {
                     const float x = __uint_as_float(v[r]) * osc;
-                    const float2 s = fisher_series2(make_float2(__uint_as_float(v[r]), 0.f), osc);
-                    v[r] = __float_as_uint(fabsf(x) > FISHER_SERIES_MAX ? fisher_fast(x) : s.x);
+                    v[r] = __float_as_uint(fabsf(x) > FISHER_SERIES_MAX ? fisher_fast(x) : fisher_series1(x));
                 }
             } else {
 #pragma unroll
@@ -507,7 +520,21 @@ __device__ __forceinline__ void gemm_epilogue_tile(const Gemm2Params &p, uint64_
                 v[r] = __float_as_uint(z.x), v[r + 1] = __float_as_uint(z.y);
             }
         }
-        if (p.tiled) {
+        if constexpr (HALF_OUT) {
+            // fp16 tile (128 KB, row pitch 512 B); p.tiled == 2.  Lanes 2k / 2k+1 swap one value per row pair, so the even
+            // lane owns (row r; columns j, j+1) and the odd lane (row r+1; columns j-1, j): every store
+            // instruction writes 2 x 64 contiguous bytes
+            __half2 *tile = reinterpret_cast<__half2 *>(reinterpret_cast<__half *>(p.out) +
+                                                        ((size_t)(ti * p.tiles_j + tj) * p.E + e) * 65536);
+            const int odd = lane & 1;
+            __half2 *ptr = tile + ((size_t)(c * 32 + odd) * 256 + ((int)rank * 128 + q * 32 + lane - odd)) / 2;
+#pragma unroll
+            for (int r = 0; r < 32; r += 2) {
+                const float mine = __uint_as_float(odd ? v[r + 1] : v[r]);
+                const float other = __shfl_xor_sync(0xffffffffu, __uint_as_float(odd ? v[r] : v[r + 1]), 1);
+                ptr[r * 128] = odd ? __floats2half2_rn(other, mine) : __floats2half2_rn(mine, other);
+            }
+        } else if (p.tiled) {
             // the pair's 256x256 tile of epoch e is one contiguous 256 KB run, row pitch 1 KB; rows >= nb and
             // columns >= V2 fall into the tile padding the caller allocated
             float *ptr = p.out + (((size_t)(ti * p.tiles_j + tj) * p.E + e) * 256 + c * 32) * 256 +
@@ -538,7 +565,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(const Gemm2Params &p, uint64_
     }
 }
 
-template <int KIND>
+template <int KIND, bool HALF_OUT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_MAX_THREADS, 1)
     k_corr_umma2(const __grid_constant__ CUtensorMap tm_cols, const __grid_constant__ CUtensorMap tm_rows,
                  const Gemm2Params p)
@@ -674,7 +701,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_MAX_THREADS, 1)
             const long rem = tile - (long)e * tiles_per_e;
             const int tj = (int)(rem / p.tiles_i);
             const int ti = (int)(rem - (long)tj * p.tiles_i);
-            gemm_epilogue_tile(p, tfull_bar, tempty_bar, tmem_base, e, tj, ti, iter, rank, warp, lane);
+            gemm_epilogue_tile<HALF_OUT>(p, tfull_bar, tempty_bar, tmem_base, e, tj, ti, iter, rank, warp, lane);
         }
     }
     tc_fence_before();
@@ -728,7 +755,7 @@ static int make_operand_map(CUtensorMap *m, const void *base, const PrecInfo &pi
 
 // self-correlation fix-up: out[i][e][start+i] = exact sequential-FMA r (optionally Fisher-transformed)
 __global__ void k_self_corr_fixup(const float *__restrict__ selfdiag, int E, long V, long start, long nb, float *out,
-                                  long stride_i, long stride_e, int fisher_epochs, long tiled_t256)
+                                  long stride_i, long stride_e, int fisher_epochs, long tiled_t256, int half_out)
 {
     const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= nb * E) return;
@@ -737,17 +764,22 @@ __global__ void k_self_corr_fixup(const float *__restrict__ selfdiag, int E, lon
     float r = selfdiag[(size_t)e * V + start + i];
     if (e < fisher_epochs) r = fisher_fast(r);
     const long j = start + i;
-    if (tiled_t256 > 0)   // tiled [i/256][j/256][e][i%256][j%256]
-        out[((((size_t)(i >> 8) * tiled_t256 + (j >> 8)) * E + e) * 256 + (i & 255)) * 256 + (j & 255)] = r;
-    else
+    if (tiled_t256 > 0) {   // tiled [i/256][j/256][e][i%256][j%256], fp32 or fp16 elements
+        const size_t off = ((((size_t)(i >> 8) * tiled_t256 + (j >> 8)) * E + e) * 256 + (i & 255)) * 256 + (j & 255);
+        if (half_out)
+            reinterpret_cast<__half *>(out)[off] = __float2half_rn(r);
+        else
+            out[off] = r;
+    } else {
         out[(size_t)i * stride_i + (size_t)e * stride_e + j] = r;
+    }
 }
 
 // tiled_t256 > 0: write the block in the tiled layout [ceil(nb/256)][tiled_t256][E][256][256] (the caller
 // provides round_up(nb, 256) rows of workspace and tiled_t256 == ceil(V2/256)); else out[i*stride_i + e*stride_e + j]
 static int launch_corr_umma(const void *rows_op, const void *cols_op, int precision, int E, int T, long V, long V2,
                             long start, long nb, float *out, long stride_i, long stride_e, int fisher_epochs,
-                            cudaStream_t st, long tiled_t256 = 0)
+                            cudaStream_t st, long tiled_t256 = 0, int half_out = 0)
 {
     PrecInfo pi;
     if (!prec_info(precision, &pi)) return fail(FCMA_EINVAL, "unknown precision %d", precision);
@@ -772,7 +804,8 @@ static int launch_corr_umma(const void *rows_op, const void *cols_op, int precis
     q.fmt = pi.fmt, q.out_scale = 1.0f / (pi.in_scale * pi.in_scale);
     q.half_bytes = (uint32_t)(q.BN / 2) * 128;
     q.stage_bytes = (uint32_t)pi.planes * (16384 + q.half_bytes);
-    q.tiled = tiled_t256 > 0 ? 1 : 0;
+    q.tiled = tiled_t256 > 0 ? (half_out ? 2 : 1) : 0;
+    if (half_out && !q.tiled) return fail(FCMA_EINVAL, "internal: fp16 output needs the tiled layout");
     if (q.tiled && tiled_t256 != q.tiles_j) return fail(FCMA_EINVAL, "internal: tiled output needs T256 == tiles_j");
     {
         // tuning / diagnostic knobs, read per launch (tools/ab_env.py, tools/gemm_debug.py)
@@ -800,13 +833,17 @@ static int launch_corr_umma(const void *rows_op, const void *cols_op, int precis
     const unsigned gemm_threads = 128u + 32u * (unsigned)q.epi_warps;
     const long ngroups = q.total_tiles / q.grp_tiles;
     if (ngroups < pairs) pairs = ngroups;
+#define FCMA_LAUNCH_GEMM(KK, HH)                                                                                      \
+    do {                                                                                                              \
+        CUDA_TRY(cudaFuncSetAttribute(k_corr_umma2<KK, HH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        k_corr_umma2<KK, HH><<<(unsigned)(2 * pairs), gemm_threads, smem, st>>>(tm_cols, tm_rows, q);                \
+    } while (0)
     if (pi.kind == 0) {
-        CUDA_TRY(cudaFuncSetAttribute(k_corr_umma2<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_corr_umma2<0><<<(unsigned)(2 * pairs), gemm_threads, smem, st>>>(tm_cols, tm_rows, q);
+        if (half_out) FCMA_LAUNCH_GEMM(0, true); else FCMA_LAUNCH_GEMM(0, false);
     } else {
-        CUDA_TRY(cudaFuncSetAttribute(k_corr_umma2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_corr_umma2<1><<<(unsigned)(2 * pairs), gemm_threads, smem, st>>>(tm_cols, tm_rows, q);
+        if (half_out) FCMA_LAUNCH_GEMM(1, true); else FCMA_LAUNCH_GEMM(1, false);
     }
+#undef FCMA_LAUNCH_GEMM
     LAUNCH_CHECK("k_corr_umma2");
 
     if (rows_op == cols_op && V == V2) {
@@ -815,7 +852,7 @@ static int launch_corr_umma(const void *rows_op, const void *cols_op, int precis
                                                           operand_plane_bytes(pi, precision, E, T, V));
         long n = nb * E;
         k_self_corr_fixup<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(sd, E, V, start, nb, out, stride_i, stride_e,
-                                                                 fisher_epochs, tiled_t256);
+                                                                 fisher_epochs, tiled_t256, half_out);
         LAUNCH_CHECK("k_self_corr_fixup");
     }
     return FCMA_OK;
@@ -1051,13 +1088,16 @@ __global__ void __launch_bounds__(256) k_syrk_simt(const float *__restrict__ z, 
 // j0 + 16h + 4t .. +3 (h = 0,1).  These registers are at once
 //   - the A fragments (rows g, g+8 of m-tile mu <-> epochs R*g+2mu, R*g+2mu+1) and
 //   - the B fragments (col g of n-tile nu <-> epoch R*g+nu)
-// of mma.sync.m16n8k8 (tf32), with k-slot t <-> column 4t+u and k-slot t+4 <-> column 16+4t+u for
+// of mma.sync.m16n8k8 (tf32), with k-slots t / t+4 <-> two adjacent columns of the lane (see the MMA loop) for
 // k-step u = 0..3: a sum over columns is invariant under that permutation, and the epoch
 // permutation is undone when the accumulators are scattered.  EP = 8R padded epochs.
 // The epochs of one subject (EPS consecutive epochs, EPS a power of two) live in EPS/R adjacent
 // g-lanes (or inside a lane when EPS <= R), so the z-score statistics need at most 3 shuffles.
 // EPS == 0: input is already normalised (plain SYRK).
-template <int R, int EPS, bool FISHER, bool VEC>
+// VEC: 0 scalar loads (unaligned fp32 block), 1 cp.async of an fp32 block, 2 cp.async of an fp16 block (tiled
+// intermediate written by the GEMM epilogue; a lane then takes 8 consecutive columns 8t..8t+7 per epoch as ONE
+// 16-byte copy -- which columns a k-slot stands for is irrelevant to a sum over columns).
+template <int R, int EPS, bool FISHER, int VEC>
 __global__ void __launch_bounds__(256, (R == 4 ? 2 : 1))
     k_norm_syrk(const float *__restrict__ C, long nb, int E, long n2, long stride_i, long ld, long chunk_step,
                 long self_col0, float beta, float *K, int sum_over_rows)
@@ -1066,13 +1106,15 @@ __global__ void __launch_bounds__(256, (R == 4 ? 2 : 1))
     constexpr int MT = EP / 16, NT = EP / 8;
     __shared__ float s_K[EP * EP];
     extern __shared__ __align__(16) uint8_t dyn_smem[];
-    float4 *s_stage = reinterpret_cast<float4 *>(dyn_smem);  // VEC only: [warp][buf][r*2+h][lane]
+    float4 *s_stage = reinterpret_cast<float4 *>(dyn_smem);  // VEC only: [warp][buf][copy][lane]
     // R == 4 only: per-warp fp32 partial kernels [8][EP*EP].  The warp MMA adds into its accumulator
     // with truncation, so a long chain at growing magnitude biases the sums (measured 5e-5 relative on
     // the diagonal at V2 = 50 000); flushing the MMA accumulators into these round-to-nearest partials
     // every FLUSH chunks bounds the chain length (bias ~1e-6).  Every (row, col) has exactly one owner lane.
+    constexpr int CPL = VEC == 2 ? R : 2 * R;   // 16-byte copies per lane and chunk
+    using elem_t = std::conditional_t<VEC == 2, __half, float>;
     [[maybe_unused]] float *s_part =
-        reinterpret_cast<float *>(dyn_smem + (VEC ? (size_t)8 * 2 * 2 * R * 32 * sizeof(float4) : 0));
+        reinterpret_cast<float *>(dyn_smem + (VEC ? (size_t)8 * 2 * CPL * 32 * sizeof(float4) : 0));
     constexpr int FLUSH = R == 4 ? 8 : 32;   // chunks between flushes (E > 32: atomics are dearer, flush less often)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, t = lane & 3;
@@ -1082,9 +1124,10 @@ __global__ void __launch_bounds__(256, (R == 4 ? 2 : 1))
     for (long i = blockIdx.x; i < nb; i += gridDim.x) {
         // classic layout: row i at i*stride_i; tiled layout (chunk_step != 256): 256-row blocks of
         // ceil(n2/256) * chunk_step floats, rows 256 floats apart inside a block
-        const float *Ci = chunk_step == 256
-                              ? C + (size_t)i * stride_i
-                              : C + (size_t)(i >> 8) * (size_t)(((n2 + 255) >> 8) * chunk_step) + (size_t)(i & 255) * stride_i;
+        const elem_t *Cb = reinterpret_cast<const elem_t *>(C);
+        const elem_t *Ci = chunk_step == 256
+                               ? Cb + (size_t)i * stride_i
+                               : Cb + (size_t)(i >> 8) * (size_t)(((n2 + 255) >> 8) * chunk_step) + (size_t)(i & 255) * stride_i;
         const long self_col = self_col0 >= 0 ? self_col0 + i : -1;
         float acc[MT][NT][4];
 #pragma unroll
@@ -1138,37 +1181,52 @@ __global__ void __launch_bounds__(256, (R == 4 ? 2 : 1))
         // next chunk streams from HBM while this one is normalised and multiplied; zero fill covers
         // epochs >= E and the ragged last chunk without any branch.
         [[maybe_unused]] float4 *stage = nullptr;
-        [[maybe_unused]] const float *lane_src[R];   // row pointers of this lane, advanced chunk by chunk
+        [[maybe_unused]] const elem_t *lane_src[R];  // row pointers of this lane, advanced chunk by chunk
         [[maybe_unused]] uint32_t row_bytes[R];      // 16 for epochs < E, 0 (-> zero fill) otherwise
         [[maybe_unused]] int buf = 0;
-        // issue the 2R 16-byte copies of the chunk starting at column jc into staging buffer b
+        // issue the CPL 16-byte copies of the chunk starting at column jc into staging buffer b
         auto prefetch = [&](long jc, int b) {
-            float4 *dst = stage + b * (2 * R * 32) + lane;
-            if (jc + 32 <= n2) {  // warp-uniform: full chunk
+            float4 *dst = stage + b * (CPL * 32) + lane;
+            if constexpr (VEC == 2) {
+                if (jc + 32 <= n2) {  // warp-uniform: full chunk
 #pragma unroll
-                for (int r = 0; r < R; r++) {
-                    cp_async_16_zfill(dst + (r * 2 + 0) * 32, lane_src[r], row_bytes[r]);
-                    cp_async_16_zfill(dst + (r * 2 + 1) * 32, lane_src[r] + 16, row_bytes[r]);
-                }
-            } else {  // ragged last chunk: clamp the byte count per copy
+                    for (int r = 0; r < R; r++) cp_async_16_zfill(dst + r * 32, lane_src[r], row_bytes[r]);
+                } else {
 #pragma unroll
-                for (int r = 0; r < R; r++)
-#pragma unroll
-                    for (int h = 0; h < 2; h++) {
-                        long left = (n2 - (jc + 16 * h + 4 * t)) * 4;
+                    for (int r = 0; r < R; r++) {
+                        long left = (n2 - (jc + 8 * t)) * 2;
                         uint32_t nbytes = left <= 0 ? 0u : (left < 16 ? (uint32_t)left : 16u);
                         nbytes = row_bytes[r] ? nbytes : 0u;
-                        cp_async_16_zfill(dst + (r * 2 + h) * 32, nbytes ? lane_src[r] + 16 * h : Ci, nbytes);
+                        cp_async_16_zfill(dst + r * 32, nbytes ? lane_src[r] : Ci, nbytes);
                     }
+                }
+            } else {
+                if (jc + 32 <= n2) {  // warp-uniform: full chunk
+#pragma unroll
+                    for (int r = 0; r < R; r++) {
+                        cp_async_16_zfill(dst + (r * 2 + 0) * 32, lane_src[r], row_bytes[r]);
+                        cp_async_16_zfill(dst + (r * 2 + 1) * 32, lane_src[r] + 16, row_bytes[r]);
+                    }
+                } else {  // ragged last chunk: clamp the byte count per copy
+#pragma unroll
+                    for (int r = 0; r < R; r++)
+#pragma unroll
+                        for (int h = 0; h < 2; h++) {
+                            long left = (n2 - (jc + 16 * h + 4 * t)) * 4;
+                            uint32_t nbytes = left <= 0 ? 0u : (left < 16 ? (uint32_t)left : 16u);
+                            nbytes = row_bytes[r] ? nbytes : 0u;
+                            cp_async_16_zfill(dst + (r * 2 + h) * 32, nbytes ? lane_src[r] + 16 * h : Ci, nbytes);
+                        }
+                }
             }
 #pragma unroll
             for (int r = 0; r < R; r++) lane_src[r] += chunk_step;  // this warp's next chunk (8 chunks on)
         };
         if constexpr (VEC) {
-            stage = s_stage + (size_t)warp * (2 * 2 * R * 32);
+            stage = s_stage + (size_t)warp * (2 * CPL * 32);
 #pragma unroll
             for (int r = 0; r < R; r++) {
-                lane_src[r] = Ci + (size_t)(R * g + r) * ld + 4 * t + (long)warp * 32;
+                lane_src[r] = Ci + (size_t)(R * g + r) * ld + (VEC == 2 ? 8 : 4) * t + (long)warp * 32;
                 row_bytes[r] = (R * g + r < E) ? 16u : 0u;
             }
             if (warp < nchunks) prefetch((long)warp * 32, 0);
@@ -1186,14 +1244,27 @@ __global__ void __launch_bounds__(256, (R == 4 ? 2 : 1))
                 cp_async_commit();
                 cp_async_wait<1>();
                 __syncwarp();
-                const float4 *cst = stage + buf * (2 * R * 32);
+                const float4 *cst = stage + buf * (CPL * 32);
+                if constexpr (VEC == 2) {
 #pragma unroll
-                for (int r = 0; r < R; r++)
+                    for (int r = 0; r < R; r++) {
+                        const float4 q = cst[r * 32 + lane];   // 8 fp16 values: columns 8t .. 8t+7
+                        const __half2 *hq = reinterpret_cast<const __half2 *>(&q);
 #pragma unroll
-                    for (int h = 0; h < 2; h++) {
-                        float4 q = cst[(r * 2 + h) * 32 + lane];
-                        vals[r][h][0] = q.x, vals[r][h][1] = q.y, vals[r][h][2] = q.z, vals[r][h][3] = q.w;
+                        for (int h = 0; h < 2; h++) {
+                            const float2 lo = __half22float2(hq[2 * h]), hi = __half22float2(hq[2 * h + 1]);
+                            vals[r][h][0] = lo.x, vals[r][h][1] = lo.y, vals[r][h][2] = hi.x, vals[r][h][3] = hi.y;
+                        }
                     }
+                } else {
+#pragma unroll
+                    for (int r = 0; r < R; r++)
+#pragma unroll
+                        for (int h = 0; h < 2; h++) {
+                            float4 q = cst[(r * 2 + h) * 32 + lane];
+                            vals[r][h][0] = q.x, vals[r][h][1] = q.y, vals[r][h][2] = q.z, vals[r][h][3] = q.w;
+                        }
+                }
                 buf ^= 1;
             } else {
                 // ---- direct loads (unaligned buffers), zero outside [0,E) x [0,n2)
@@ -1261,6 +1332,9 @@ __global__ void __launch_bounds__(256, (R == 4 ? 2 : 1))
                     }
                 } else {
                     constexpr int L = EPS / R;  // adjacent g-lanes per subject
+                    // padded epochs (>= E) hold zeros and normalise to zeros, so when every real epoch belongs to a
+                    // complete subject no lane needs the select
+                    const bool all_valid = S_eps == E;   // block-uniform
                     const bool valid = R * g < S_eps;
 #pragma unroll
                     for (int h = 0; h < 2; h++)
@@ -1282,7 +1356,13 @@ __global__ void __launch_bounds__(256, (R == 4 ? 2 : 1))
                             }
                             float2 inv, mi;
                             finish(m, s2, inv, mi);
-                            if (valid) {
+                            if (all_valid) {   // uniform branch: no per-value select
+#pragma unroll
+                                for (int r = 0; r < R; r++) {
+                                    const float2 z = ffma2(make_float2(vals[r][h][u], vals[r][h][u + 1]), inv, mi);
+                                    vals[r][h][u] = z.x, vals[r][h][u + 1] = z.y;
+                                }
+                            } else if (valid) {
 #pragma unroll
                                 for (int r = 0; r < R; r++) {
                                     const float2 z = ffma2(make_float2(vals[r][h][u], vals[r][h][u + 1]), inv, mi);
@@ -1300,7 +1380,7 @@ __global__ void __launch_bounds__(256, (R == 4 ? 2 : 1))
                     for (int h = 0; h < 2; h++)
 #pragma unroll
                         for (int u = 0; u < 4; u++)
-                            if (j0 + 16 * h + 4 * t + u == self_col) vals[r][h][u] = 0.f;
+                            if (j0 + (VEC == 2 ? 8 * t + 4 * h : 16 * h + 4 * t) + u == self_col) vals[r][h][u] = 0.f;
             }
             uint32_t tv[R][2][4];
 #pragma unroll
@@ -1308,16 +1388,21 @@ __global__ void __launch_bounds__(256, (R == 4 ? 2 : 1))
 #pragma unroll
                 for (int h = 0; h < 2; h++)
 #pragma unroll
-                    for (int u = 0; u < 4; u++) tv[r][h][u] = f32_to_tf32(vals[r][h][u]);
-            // ---- K += Z Z^T on tensor cores
+                    for (int u = 0; u < 4; u++)   // round to nearest tf32 (ties away, = cvt.rna): the MMA truncates
+                        tv[r][h][u] = __float_as_uint(vals[r][h][u]) + 0x1000u;
+            // ---- K += Z Z^T on tensor cores.  k-step (h, w): k-slot t <-> column 2w, k-slot t+4 <-> column 2w+1 of
+            // the lane's h-th group of four columns, so a B fragment is two ADJACENT registers of one 16-byte load
 #pragma unroll
-            for (int u = 0; u < 4; u++)
+            for (int h = 0; h < 2; h++)
 #pragma unroll
-                for (int mu = 0; mu < MT; mu++)
+                for (int w = 0; w < 2; w++)
 #pragma unroll
-                    for (int nu = 0; nu < NT; nu++)
-                        mma_tf32_16x8x8(acc[mu][nu], tv[2 * mu][0][u], tv[2 * mu + 1][0][u], tv[2 * mu][1][u],
-                                        tv[2 * mu + 1][1][u], tv[nu][0][u], tv[nu][1][u]);
+                    for (int mu = 0; mu < MT; mu++)
+#pragma unroll
+                        for (int nu = 0; nu < NT; nu++)
+                            mma_tf32_16x8x8(acc[mu][nu], tv[2 * mu][h][2 * w], tv[2 * mu + 1][h][2 * w],
+                                            tv[2 * mu][h][2 * w + 1], tv[2 * mu + 1][h][2 * w + 1], tv[nu][h][2 * w],
+                                            tv[nu][h][2 * w + 1]);
             }  // ch < nchunks
             if constexpr (R == 4) {
                 if (++since_flush == FLUSH) {
@@ -1372,11 +1457,11 @@ __global__ void k_scale(float *x, long n, float s)
         x[i] = s == 0.f ? 0.f : x[i] * s;
 }
 
-template <int R, bool FISHER, bool VEC>
+template <int R, bool FISHER, int VEC>
 static bool dispatch_eps(int eps, dim3 grid, cudaStream_t st, const float *C, long nb, int E, long n2, long stride_i,
                          long ld, long chunk_step, long self_col0, float beta, float *K, int sum)
 {
-    constexpr size_t smem = (VEC ? (size_t)8 * 2 * 2 * R * 32 * sizeof(float4) : 0) +
+    constexpr size_t smem = (VEC ? (size_t)8 * 2 * (VEC == 2 ? R : 2 * R) * 32 * sizeof(float4) : 0) +
                             (R == 4 ? (size_t)8 * (8 * R) * (8 * R) * sizeof(float) : 0);
 #define FCMA_CASE(EPSV)                                                                                          \
     case EPSV:                                                                                                   \
@@ -1424,7 +1509,7 @@ static bool fused_supported(int E, int eps_mode)
 // (i%256)*stride_i inside the kernel.
 static int launch_norm_syrk(const float *C, long nb, int E, long n2, long stride_i, long ld, int eps_mode,
                             int fisher_done, long self_col0, float beta, float *K, int sum_over_rows, cudaStream_t st,
-                            long chunk_step = 256)
+                            long chunk_step = 256, int half_in = 0)
 {
     if (!fused_supported(E, eps_mode)) return fail(FCMA_EINVAL, "internal: fused norm+syrk unsupported E=%d eps=%d", E, eps_mode);
     if (sum_over_rows) {
@@ -1435,25 +1520,30 @@ static int launch_norm_syrk(const float *C, long nb, int E, long n2, long stride
     const bool vec = ((ld & 3) == 0) && ((stride_i & 3) == 0) && (((uintptr_t)C & 15) == 0);
     if (!vec && chunk_step != 256) return fail(FCMA_EINVAL, "internal: tiled layout needs the vector path");
     const bool fisher = eps_mode > 0 && !fisher_done;
+    if (half_in && (fisher || chunk_step == 256 || !vec))
+        return fail(FCMA_EINVAL, "internal: the fp16 block is tiled and already Fisher-transformed");
     // rows cost the same: a static stride over 16 blocks per SM balances well
     long g = nb < 16L * g_sm_count ? nb : 16L * g_sm_count;
     dim3 grid((unsigned)g);
     bool ok;
+#define FCMA_DISPATCH(RR, FI, VV) \
+    dispatch_eps<RR, FI, VV>(eps_mode, grid, st, C, nb, E, n2, stride_i, ld, chunk_step, self_col0, beta, K, sum_over_rows)
     if (E <= 32) {
-        if (fisher)
-            ok = vec ? dispatch_eps<4, true, true>(eps_mode, grid, st, C, nb, E, n2, stride_i, ld, chunk_step, self_col0, beta, K, sum_over_rows)
-                     : dispatch_eps<4, true, false>(eps_mode, grid, st, C, nb, E, n2, stride_i, ld, chunk_step, self_col0, beta, K, sum_over_rows);
+        if (half_in)
+            ok = FCMA_DISPATCH(4, false, 2);
+        else if (fisher)
+            ok = vec ? FCMA_DISPATCH(4, true, 1) : FCMA_DISPATCH(4, true, 0);
         else
-            ok = vec ? dispatch_eps<4, false, true>(eps_mode, grid, st, C, nb, E, n2, stride_i, ld, chunk_step, self_col0, beta, K, sum_over_rows)
-                     : dispatch_eps<4, false, false>(eps_mode, grid, st, C, nb, E, n2, stride_i, ld, chunk_step, self_col0, beta, K, sum_over_rows);
+            ok = vec ? FCMA_DISPATCH(4, false, 1) : FCMA_DISPATCH(4, false, 0);
     } else {
-        if (fisher)
-            ok = vec ? dispatch_eps<8, true, true>(eps_mode, grid, st, C, nb, E, n2, stride_i, ld, chunk_step, self_col0, beta, K, sum_over_rows)
-                     : dispatch_eps<8, true, false>(eps_mode, grid, st, C, nb, E, n2, stride_i, ld, chunk_step, self_col0, beta, K, sum_over_rows);
+        if (half_in)
+            ok = FCMA_DISPATCH(8, false, 2);
+        else if (fisher)
+            ok = vec ? FCMA_DISPATCH(8, true, 1) : FCMA_DISPATCH(8, true, 0);
         else
-            ok = vec ? dispatch_eps<8, false, true>(eps_mode, grid, st, C, nb, E, n2, stride_i, ld, chunk_step, self_col0, beta, K, sum_over_rows)
-                     : dispatch_eps<8, false, false>(eps_mode, grid, st, C, nb, E, n2, stride_i, ld, chunk_step, self_col0, beta, K, sum_over_rows);
+            ok = vec ? FCMA_DISPATCH(8, false, 1) : FCMA_DISPATCH(8, false, 0);
     }
+#undef FCMA_DISPATCH
     if (!ok) return fail(FCMA_EINVAL, "internal: no k_norm_syrk instantiation for E=%d eps=%d", E, eps_mode);
     LAUNCH_CHECK("k_norm_syrk");
     return FCMA_OK;
@@ -1650,6 +1740,17 @@ static int run_pipeline(const void *rows_op, const void *cols_op, int precision,
     const char *no_tiled = getenv("FCMA_NO_TILED");
     const long t256 = cdiv(V2, 256);
     const bool tiled = !(no_tiled && no_tiled[0] == '1') && fused && V2 < (1L << 31) && rows_per_pass >= 256;
+    // fp16 intermediate (FCMA_FLAG_F16_INTERMEDIATE, and by default in the single-product reduced-precision operand
+    // modes bf16 / tf32): the tiled block holds Fisher-z values rounded to fp16.  Their rounding errors
+    // are independent across the V2 columns the kernel matrix sums over: measured max|dK|/max|K| = 1.5e-5 at
+    // V2 = 50 000 (the reference's own fp32 ssyrk rounding noise is 1e-5), while both kernels move half the
+    // bytes (-8..12 % per step).  The fp32-faithful modes keep an fp32 block unless the flag asks otherwise;
+    // correlation values returned by fcma_corr_block are never rounded.  FCMA_F16_INTERMEDIATE=0|1 overrides (A/B).
+    const char *f16i = getenv("FCMA_F16_INTERMEDIATE");
+    const bool reduced = precision == FCMA_PREC_BF16 || precision == FCMA_PREC_TF32;
+    bool half16 = (flags & FCMA_FLAG_F16_INTERMEDIATE) || reduced;
+    if (f16i && (f16i[0] == '0' || f16i[0] == '1')) half16 = f16i[0] == '1';
+    half16 = half16 && tiled && normalise && fisher_in_gemm;
     for (long done = 0; done < nb; done += rows_per_pass) {
         const long n = nb - done < rows_per_pass ? nb - done : rows_per_pass;
         int rc;
@@ -1660,7 +1761,7 @@ static int run_pipeline(const void *rows_op, const void *cols_op, int precision,
         }
         if (tiled)
             rc = launch_corr_umma(rows_op, cols_op, precision, E, T, V, V2, start + done, n, work, 4, 4,
-                                  fisher_in_gemm ? S_eps : 0, st, t256);
+                                  fisher_in_gemm ? S_eps : 0, st, t256, half16 ? 1 : 0);
         else
             rc = launch_corr_umma(rows_op, cols_op, precision, E, T, V, V2, start + done, n, work, (long)E * ld, ld,
                                   fisher_in_gemm ? S_eps : 0, st);
@@ -1670,7 +1771,8 @@ static int run_pipeline(const void *rows_op, const void *cols_op, int precision,
         const float beta = sum_over_rows ? 1.0f : 0.0f;
         if (tiled) {
             rc = launch_norm_syrk(work, n, E, V2, 256, 65536, normalise ? eps : 0, (normalise && fisher_in_gemm) ? 1 : 0,
-                                  mask_self ? start + done : -1, beta, Kdst, sum_over_rows, st, (long)E * 65536);
+                                  mask_self ? start + done : -1, beta, Kdst, sum_over_rows, st, (long)E * 65536,
+                                  half16 ? 1 : 0);
         } else if (normalise && fused) {
             rc = launch_norm_syrk(work, n, E, V2, (long)E * ld, ld, eps, fisher_in_gemm ? 1 : 0,
                                   mask_self ? start + done : -1, beta, Kdst, sum_over_rows, st);

@@ -254,8 +254,12 @@ def test_tiled_intermediate_equals_strided(dev, two, monkeypatch):
         out[no_tiled] = engine.voxel_kernels(rows, cols, start, nb, eps, flags=fl, work=work).cpu().numpy()
     assert np.array_equal(out["0"], out["1"])
     assert np.max(np.abs(out["0"] - Kref)) <= k_tol(n2) * np.max(np.abs(Kref))
-    # several passes through a 256-row workspace (tiled, one row tile per pass)
+    # fp16 intermediate (opt-in flag): same result up to the averaged rounding of the stored Fisher-z values
     monkeypatch.setenv("FCMA_NO_TILED", "0")
+    got16 = engine.voxel_kernels(rows, cols, start, nb, eps, flags=fl | _lib.FLAG_F16_INTERMEDIATE, work=work).cpu().numpy()
+    d16 = np.max(np.abs(got16 - out["0"]))
+    assert 0 < d16 <= 4e-3 / math.sqrt(n2) * np.max(np.abs(Kref))
+    # several passes through a 256-row workspace (tiled, one row tile per pass)
     small = engine.Workspace(E, n2, 256, dev)
     got = engine.voxel_kernels(rows, cols, start, nb, eps, flags=fl, work=small).cpu().numpy()
     assert np.array_equal(got, out["0"])
@@ -574,6 +578,10 @@ def test_full_size_invariants(dev):
     # Fisher in the GEMM epilogue == Fisher in pass 2
     K3 = engine.voxel_kernels(op, op, start, nb, eps, flags=fl | _lib.FLAG_FISHER_IN_PASS2, work=work).double()
     assert float((K3 - K).abs().max()) <= 2e-5 * float(K.abs().max())
+    # opt-in fp16 intermediate (default in the bf16 / tf32 operand modes): rounding errors of the stored Fisher-z
+    # values average out over the V columns -> max|dK| <= 4e-3 / sqrt(V) * max|K|  (1.8e-5 here)
+    K16 = engine.voxel_kernels(op, op, start, nb, eps, flags=fl | _lib.FLAG_F16_INTERMEDIATE, work=work).double()
+    assert 0 < float((K16 - K).abs().max()) <= 4e-3 / math.sqrt(V) * float(K.abs().max())
     # classifier kernel == sum of voxel kernels (no self masking on either side)
     Kn = engine.voxel_kernels(op, op, start, nb, eps, work=work).double().sum(0)
     Kc = engine.classifier_kernel(op, op, start, nb, eps, work=work).double()

@@ -410,7 +410,13 @@ def run_b200_arm(args):
         opb = engine.pack_epochs(epochs, None, "bf16")
         ms_b = ev_time(lambda: engine.voxel_kernels(opb, opb, 0, V, eps, work=work, out=K), reps=1)
         others["voxel_kernels_bf16_operands"] = {"ms": ms_b, "value": corr_total / (ms_b * 1e-3), "unit": UNIT,
-                                                 "note": "|dr| <= 8e-3; the headline uses the fp32-faithful fp16x3 split"}
+                                                 "note": "|dr| <= 8e-3, fp16 Fisher-z intermediate; the headline uses "
+                                                         "the fp32-faithful fp16x3 split with an fp32 intermediate"}
+        # the headline operands with the opt-in fp16 intermediate (max|dK|/max|K| ~ 1.5e-5)
+        ms_h = ev_time(lambda: engine.voxel_kernels(op, op, 0, V, eps, flags=_lib.FLAG_F16_INTERMEDIATE, work=work, out=K),
+                       reps=1)
+        others["voxel_kernels_f16_intermediate"] = {"ms": ms_h, "value": corr_total / (ms_h * 1e-3), "unit": UNIT,
+                                                    "note": "headline operands (%s), FCMA_FLAG_F16_INTERMEDIATE" % prec}
         del opb, op
 
     # ---- direct parity at the full shape: 64 rows through the UNMODIFIED reference vs the GPU pipeline

@@ -48,6 +48,8 @@ def parse():
     ap.add_argument("--block-rows", type=int, default=4096)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-sym", action="store_true",
+                    help="plain pipeline (every row against all columns) instead of the symmetric one")
     return ap.parse_args()
 
 
@@ -206,8 +208,11 @@ def run_b200_arm(args):
     V, T, E, eps = args.voxels, WORKLOAD["T"], WORKLOAD["E"], WORKLOAD["eps"]
     prec = args.precision
     flags = 0
-    start, n = VoxelSelector.row_partition(V, world)[rank]
+    sym = (not args.no_sym) and engine.sym_supported(E, eps) and V >= 512 * world
+    start, n = (engine.sym_row_partition(V, world) if sym else VoxelSelector.row_partition(V, world))[rank]
     block = min(args.block_rows, max(n, 1))
+    if sym:
+        block = max(256, (block + 255) // 256 * 256)
 
     # inputs: pinned host copy on rank 0 (for e2e) and the HBM-resident epochs
     host = make_host_epochs(V, T, E, pin=True) if rank == 0 else None
@@ -215,11 +220,13 @@ def run_b200_arm(args):
     if rank == 0:
         epochs.copy_(host, non_blocking=True)
     bcast = torch.empty_like(epochs) if world > 1 else None   # receive buffer used inside the step
-    work = engine.Workspace(E, V, block, dev)
-    K = torch.empty((max(n, 1), E, E), dtype=torch.float32, device=dev)
+    # symmetric pipeline: scratch for a block and its transposed copy; K is the full [V, E, E] array every rank
+    # accumulates its partial sums into (summed onto rank 0 with one NCCL reduce)
+    work = engine.SymWorkspace(E, V, block, dev, start=start) if sym else engine.Workspace(E, V, block, dev)
+    K = torch.empty((V if sym else max(n, 1), E, E), dtype=torch.float32, device=dev)
     per = VoxelSelector.row_partition(V, world)[0][1]
-    Kall = torch.empty((world * per, E, E), dtype=torch.float32, device=dev) if (world > 1 and rank == 0) else None
-    Kpad = torch.zeros((per, E, E), dtype=torch.float32, device=dev) if world > 1 else None
+    Kall = torch.empty((world * per, E, E), dtype=torch.float32, device=dev) if (world > 1 and rank == 0 and not sym) else None
+    Kpad = torch.zeros((per, E, E), dtype=torch.float32, device=dev) if (world > 1 and not sym) else None
     Khost = torch.empty((V, E, E), dtype=torch.float32, pin_memory=True) if rank == 0 else None
     torch.cuda.synchronize()
 
@@ -247,13 +254,20 @@ def run_b200_arm(args):
                 dist.broadcast(bcast, src=0)
                 src = bcast
         op = engine.pack_epochs(src, None, prec)
-        if n > 0:
-            engine.voxel_kernels(op, op, start, n, eps, flags=flags, work=work, out=K)
-        if world > 1:
-            Kpad[:n].copy_(K[:n])
-            dist.gather(Kpad, list(Kall.view(world, per, E, E).unbind(0)) if rank == 0 else None, dst=0)
+        if sym:
+            K.zero_()
+            if n > 0:
+                engine.voxel_kernels_sym(op, start, n, eps, flags=flags, work=work, out=K)
+            if world > 1:
+                dist.reduce(K, dst=0)
+        else:
+            if n > 0:
+                engine.voxel_kernels(op, op, start, n, eps, flags=flags, work=work, out=K)
+            if world > 1:
+                Kpad[:n].copy_(K[:n])
+                dist.gather(Kpad, list(Kall.view(world, per, E, E).unbind(0)) if rank == 0 else None, dst=0)
         if from_host and rank == 0:
-            res = Kall.view(-1, E, E)[:V] if world > 1 else K
+            res = Kall.view(-1, E, E)[:V] if (world > 1 and not sym) else K
             Khost.copy_(res, non_blocking=True)
 
     def timed(nsteps, from_host):
@@ -296,22 +310,51 @@ def run_b200_arm(args):
     # ---- roofline of the dominant kernel, measured live with CUDA events on the launch stream
     roofline = None
     if rank == 0:
+        import ctypes as _ct
         op = engine.pack_epochs(epochs, None, prec)
-        nbk = min(block, n)
-        Kb = K[:nbk]
+        planes = lib.fcma_operand_planes(_lib.PREC[prec])
+        kp = lib.fcma_operand_kp(_lib.PREC[prec], T)
+        op_bytes = lib.fcma_operand_bytes(_lib.PREC[prec], E, T, V)
+        nprod = 3 if planes == 2 else 1
+        # the launches of one step of this rank: (correlations stored by the GEMM, operand columns read,
+        # 256x256 tiles contracted)
+        launches_desc = []
+        if sym:
+            rpp = work.rows
+            for a in range(start, start + n, rpp):
+                nn = min(rpp, start + n - a)
+                colsA, rowsB = V - a, V - a - nn
+                nt, t256 = -(-nn // 256), -(-colsA // 256)
+                launches_desc.append((float(nn) * colsA + float(rowsB) * nn, colsA,
+                                      nt * (nt + 1) // 2 + (t256 - nt) * nt))
+        else:
+            for a in range(start, start + n, block):
+                nn = min(block, start + n - a)
+                launches_desc.append((float(nn) * V, V, -(-nn // 256) * -(-V // 256)))
+
+        def one_pass():
+            if sym:
+                K.zero_()
+                engine.voxel_kernels_sym(op, start, n, eps, flags=flags, work=work, out=K)
+            else:
+                engine.voxel_kernels(op, op, start, n, eps, flags=flags, work=work, out=K)
         # live per-kernel times of the SAME launches the timed step makes (events inside the C pipeline)
-        reps = 4
-        engine.voxel_kernels(op, op, start, nbk, eps, flags=flags, work=work, out=Kb)
+        reps = 2
+        one_pass()
         torch.cuda.synchronize()
         lib.fcma_timing_enable(1)
         for r in range(reps):
-            engine.voxel_kernels(op, op, start, nbk, eps, flags=flags, work=work, out=Kb)
+            one_pass()
         torch.cuda.synchronize()
-        import ctypes as _ct
         g_ms, s_ms = _ct.c_double(0), _ct.c_double(0)
         npass = lib.fcma_timing_read(_ct.byref(g_ms), _ct.byref(s_ms))
         lib.fcma_timing_enable(0)
-        tg, ts = g_ms.value / npass, s_ms.value / npass
+        assert npass == reps * len(launches_desc), (npass, len(launches_desc))
+        tg, ts = g_ms.value / npass, s_ms.value / npass          # average launch duration
+        nl = float(len(launches_desc))
+        corr_launch = sum(d[0] for d in launches_desc) * E / nl   # correlations stored per GEMM launch (average)
+        opread_launch = sum(d[1] for d in launches_desc) / nl / V * op_bytes
+        tiles_launch = sum(d[2] for d in launches_desc) / nl * E
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -319,36 +362,34 @@ def run_b200_arm(args):
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         tf_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
-        corr_launch = float(nbk) * V * E
-        planes = lib.fcma_operand_planes(_lib.PREC[prec])
-        op_bytes = lib.fcma_operand_bytes(_lib.PREC[prec], E, T, V)
-        # algorithmic bytes of the GEMM launch: write 4 B per correlation + read the operand once
-        alg_bytes = 4.0 * corr_launch + op_bytes
+        # algorithmic bytes of a GEMM launch: write 4 B per stored correlation + read the operand once
+        alg_bytes = 4.0 * corr_launch + opread_launch
         traffic = None
         try:
             tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-            key = "k_corr_umma:%s:nb%d" % (prec, nbk)
+            key = "k_corr_umma:%s:%s" % (prec, "sym:rows%d" % work.rows if sym else "nb%d" % block)
             traffic = tr.get(key)
         except Exception:
             pass
         dominant = "k_corr_umma" if tg >= ts else "k_norm_syrk"
         ach = alg_bytes / (tg * 1e-3) / 1e9 if dominant == "k_corr_umma" else 4.0 * corr_launch / (ts * 1e-3) / 1e9
+        flop_exec = nprod * 2.0 * kp * tiles_launch * 65536.0
         roofline = {"kernel": dominant, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
                     "frac": ach / hbm_peak, "traffic": traffic,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
                     "launch_ms": tg if dominant == "k_corr_umma" else ts,
-                    "rows_per_launch": nbk,
+                    "launches_per_step": int(nl), "rows_per_launch": work.rows if sym else block,
+                    "pipeline": "symmetric (blocks on/above the diagonal, each stored twice)" if sym else "plain",
                     "algorithmic_bytes_per_launch": alg_bytes if dominant == "k_corr_umma" else 4.0 * corr_launch,
                     "kernels": {
                         "k_corr_umma": {"ms": tg, "hbm_gbs": alg_bytes / (tg * 1e-3) / 1e9,
+                                        # correlations delivered (each counted 2*T flops) vs MMAs actually issued
+                                        # (padded K, 3 products in the hi/lo split modes, computed tiles only)
                                         "tensor_tflops_alg": 2.0 * T * corr_launch / (tg * 1e-3) / 1e12,
-                                        "tensor_frac_of_bf16_sustained": 2.0 * T * corr_launch / (tg * 1e-3) / 1e12 / tf_peak,
-                                        # MMAs actually issued: padded K, and 3 products in the hi/lo split modes
-                                        "tensor_tflops_executed": (3 if planes == 2 else 1) * 2.0 * lib.fcma_operand_kp(_lib.PREC[prec], T)
-                                        * corr_launch / (tg * 1e-3) / 1e12,
-                                        "tensor_executed_frac_of_bf16_sustained": (3 if planes == 2 else 1) * 2.0
-                                        * lib.fcma_operand_kp(_lib.PREC[prec], T) * corr_launch / (tg * 1e-3) / 1e12 / tf_peak,
+                                        "tensor_tflops_executed": flop_exec / (tg * 1e-3) / 1e12,
+                                        "tensor_executed_frac_of_bf16_sustained": flop_exec / (tg * 1e-3) / 1e12 / tf_peak,
                                         "operand_planes": planes},
+                        # both normalise+SYRK launches of a pass (block and transposed block) together
                         "k_norm_syrk": {"ms": ts, "hbm_gbs": 4.0 * corr_launch / (ts * 1e-3) / 1e9}}}
 
     # ---- the public API end to end: VoxelSelector.run(clf) incl. the batched GPU SVM cross-validation
@@ -361,7 +402,7 @@ def run_b200_arm(args):
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         vs = VoxelSelector(labels, eps, E // eps, raw_list, voxel_unit=64, process_num=0, precision=prec,
-                           block_rows=block)
+                           block_rows=block, symmetric=sym)
         vs._work = work
         res = vs.run(clf)
         torch.cuda.synchronize()
@@ -435,11 +476,17 @@ def run_b200_arm(args):
         Kref = rvs._prepare_for_cross_validation(corr, clf)          # shrunk kernels [64, E, E]
         acc_ref = np.array([a for _, a in rvs._do_cross_validation(clf, Kref, (s0, n0))])
         op = engine.pack_epochs(epochs, None, prec)
-        Kg = engine.voxel_kernels(op, op, s0, n0, eps, work=work)
+        if sym:      # the kernels of the timed (symmetric) pipeline for these rows
+            K.zero_()
+            engine.voxel_kernels_sym(op, 0, V, eps, flags=flags, work=work, out=K)
+            Kg = K[s0:s0 + n0].clone()
+        else:
+            Kg = engine.voxel_kernels(op, op, s0, n0, eps, work=work)
         engine.shrink_kernels_(Kg)
         acc_gpu = engine.svm_cv_precomputed(Kg, labels, E // eps, C=1.0, tol=1e-3)
         Kg = Kg.cpu().numpy()
         parity = {"rows": [s0, s0 + n0], "vs": "unmodified reference (oracle/_ref) on the host, same inputs",
+                  "pipeline": "symmetric" if sym else "plain",
                   "max_abs_dK_over_max_K": float(np.max(np.abs(Kg - Kref)) / np.max(np.abs(Kref))),
                   "cv_accuracy_identical": int(np.sum(acc_gpu == acc_ref)), "cv_accuracy_total": int(n0),
                   "max_abs_d_accuracy": float(np.max(np.abs(acc_gpu - acc_ref)))}
@@ -454,11 +501,15 @@ def run_b200_arm(args):
                 "config": {"workload": "FCMA VoxelSelector V=%d T=%d E=%d eps=%d (BASELINE configs[2] shape)" % (V, T, E, eps),
                            "precision": prec + (" (3-product hi/lo split, fp32-faithful: |dr| <= 1e-6)" if prec in ("tf32x3", "fp16x3") else ""),
                            "parallelism": "rows%d" % world, "rows_per_pass": block,
+                           "pipeline": ("symmetric self-correlation: blocks on/above the diagonal contracted once, used for "
+                                        "row and column voxels; shards = equal-area row ranges" if sym else
+                                        "plain: every row block against all columns"),
                            "l2": "inputs_exceed_l2 (operand %.1f GB, correlation block %.1f GB per pass)"
                                  % (lib.fcma_operand_bytes(_lib.PREC[prec], E, T, V) / 1e9,
                                     lib.fcma_work_bytes_per_row(E, V) * block / 1e9),
                            "step": "pack + corr GEMM + Fisher/z-score + kernel build for all V rows"
-                                   + ("; epochs replicated in every rank's HBM beforehand, NCCL gather of the kernels inside the step; "
+                                   + ("; epochs replicated in every rank's HBM beforehand, NCCL %s of the kernels inside the step; " % ("reduce (sum of the shards' partial [V,E,E] arrays)" if sym else "gather")
+                                      +
                                       "e2e adds H2D on rank 0 + NCCL broadcast + D2H" if world > 1 else "")},
                 "gpu_launches": launches, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu_baseline,
                 "voxel_selection_run": run_api, "parity_vs_reference": parity, "other_configs": others,

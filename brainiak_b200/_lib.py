@@ -45,6 +45,8 @@ SIGNATURES = {
     "fcma_work_bytes_per_row": (c_size_t, [c_int, c_long]),
     "fcma_voxel_kernels": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_long, c_long, c_long,
                                    c_long, c_int, c_int, c_void_p, c_size_t, c_void_p, c_void_p]),
+    "fcma_voxel_kernels_sym": (c_int, [c_void_p, c_int, c_int, c_int, c_long, c_long, c_long, c_int, c_int,
+                                       c_void_p, c_size_t, c_void_p, c_void_p]),
     "fcma_classifier_kernel": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_long, c_long,
                                        c_long, c_long, c_int, c_int, c_void_p, c_size_t, c_void_p,
                                        c_void_p]),

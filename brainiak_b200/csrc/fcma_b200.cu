@@ -433,7 +433,18 @@ struct Gemm2Params {
     int epi_warps;                 // 8 or 16 epilogue warps (blockDim = 128 + 32 * epi_warps)
     int debug;                     // FCMA_GEMM_DEBUG (diagnostics only; output is wrong when set):
                                    //   4 no epilogue work (main loop only), 16 MMAs re-read stale stages (no loads)
+    // ---- symmetric (self-correlation) mode: corr[i][e][j] == corr[j][e][i], so a tile is computed once and stored
+    // twice, as tile (ti, tj) and -- transposed through shared memory -- as tile (tj, ti)
+    long col_start;                // first column voxel of the block: column tile tj starts at col_start + 256*tj
+    float *out_t;                  // tiled block [tiles_j - t_tj0][tiles_i][E][256 j][256 i] receiving the transposed
+                                   // copy of every tile with tj >= t_tj0 (nullptr: none)
+    int t_tj0;                     // column tiles [0, t_tj0) are the diagonal block (same voxels as the rows)
+    int sym_diag;                  // 1: inside the diagonal block skip tiles tj < ti; tiles tj > ti are mirrored
+                                   //    into `out` as tile (tj, ti)
+    uint32_t tr_off;               // smem offset of the per-warp transposition buffers (0: none)
 };
+constexpr int TR_PITCH = 36;       // floats per row of a 32x32 fp32 transposition buffer (conflict-free 16-byte accesses)
+constexpr int TR_PITCH_H = 80;     // bytes per row of a 32x32 fp16 transposition buffer
 
 // MMAs of one (column tile, row tile) operand pair of a stage: up to 4 k-steps of 32 bytes inside the
 // 128-byte swizzle atom.  Called by ONE elected thread with warp-uniform arguments, so descriptors and
@@ -462,7 +473,7 @@ __device__ __forceinline__ void issue_kblock_mmas(uint32_t d_tmem, uint32_t addr
 template <bool HALF_OUT>
 __device__ __forceinline__ void gemm_epilogue_tile(const Gemm2Params &p, uint64_t *tfull_bar, uint64_t *tempty_bar,
                                                    uint32_t tmem_base, int e, int tj, int ti, long iter, uint32_t rank,
-                                                   int warp, int lane)
+                                                   int warp, int lane, float *tr_buf)
 {
     const int q = warp & 3;
     const int part = (warp - 4) >> 2;
@@ -471,8 +482,17 @@ __device__ __forceinline__ void gemm_epilogue_tile(const Gemm2Params &p, uint64_
     const uint32_t aphase = (uint32_t)((iter >> 1) & 1);
     mbar_wait(&tfull_bar[as], aphase);
     tc_fence_after();
-    const long j = (long)tj * 256 + (long)rank * 128 + q * 32 + lane;
+    const long j = p.col_start + (long)tj * 256 + (long)rank * 128 + q * 32 + lane;
     const bool jok = j < p.V2;
+    // symmetric mode: where the transposed copy of this tile goes (tile-uniform)
+    float *tdst = nullptr;            // fp32 tile; HALF_OUT: the same element offset into an fp16 tile
+    size_t tdst_elems = 0;
+    bool mirror = false;
+    if (p.out_t != nullptr && tj >= p.t_tj0) {
+        tdst = p.out_t, tdst_elems = (((size_t)(tj - p.t_tj0) * p.tiles_i + ti) * p.E + e) * 65536, mirror = true;
+    } else if (p.sym_diag && tj > ti) {
+        tdst = p.out, tdst_elems = (((size_t)tj * p.tiles_j + ti) * p.E + e) * 65536, mirror = true;
+    }
     const bool do_fisher = e < p.fisher_epochs;
     const float osc = p.out_scale;
     const long i0 = (long)ti * p.BN;
@@ -534,6 +554,32 @@ __device__ __forceinline__ void gemm_epilogue_tile(const Gemm2Params &p, uint64_
                 const float other = __shfl_xor_sync(0xffffffffu, __uint_as_float(odd ? v[r] : v[r + 1]), 1);
                 ptr[r * 128] = odd ? __floats2half2_rn(other, mine) : __floats2half2_rn(mine, other);
             }
+            if (mirror) {
+                // transposed copy of the fp16 tile: lane j packs its 32 consecutive i into 64 bytes; through the padded
+                // smem buffer every store instruction writes 8 rows x 64 contiguous bytes
+                uint8_t *tb = reinterpret_cast<uint8_t *>(tr_buf) + (warp - 4) * (32 * TR_PITCH_H);
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    uint4 pk;
+                    __half2 h0 = __floats2half2_rn(__uint_as_float(v[8 * k + 0]), __uint_as_float(v[8 * k + 1]));
+                    __half2 h1 = __floats2half2_rn(__uint_as_float(v[8 * k + 2]), __uint_as_float(v[8 * k + 3]));
+                    __half2 h2 = __floats2half2_rn(__uint_as_float(v[8 * k + 4]), __uint_as_float(v[8 * k + 5]));
+                    __half2 h3 = __floats2half2_rn(__uint_as_float(v[8 * k + 6]), __uint_as_float(v[8 * k + 7]));
+                    pk.x = *reinterpret_cast<uint32_t *>(&h0), pk.y = *reinterpret_cast<uint32_t *>(&h1);
+                    pk.z = *reinterpret_cast<uint32_t *>(&h2), pk.w = *reinterpret_cast<uint32_t *>(&h3);
+                    *reinterpret_cast<uint4 *>(tb + lane * TR_PITCH_H + 16 * k) = pk;
+                }
+                __syncwarp();
+                __half *drow = reinterpret_cast<__half *>(tdst) + tdst_elems +
+                               ((size_t)((int)rank * 128 + q * 32) * 256 + c * 32 + (lane >> 3) * 8);
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int jr = 8 * k + (lane & 7);
+                    const uint4 x = *reinterpret_cast<const uint4 *>(tb + jr * TR_PITCH_H + (lane >> 3) * 16);
+                    *reinterpret_cast<uint4 *>(drow + (size_t)jr * 256) = x;
+                }
+                __syncwarp();
+            }
         } else if (p.tiled) {
             // the pair's 256x256 tile of epoch e is one contiguous 256 KB run, row pitch 1 KB; rows >= nb and
             // columns >= V2 fall into the tile padding the caller allocated
@@ -541,6 +587,23 @@ __device__ __forceinline__ void gemm_epilogue_tile(const Gemm2Params &p, uint64_
                          ((int)rank * 128 + q * 32 + lane);
 #pragma unroll
             for (int r = 0; r < 32; r++) ptr[r * 256] = __uint_as_float(v[r]);
+            if (mirror) {
+                // transposed copy: lane j holds 32 consecutive i; stage the 32x32 block in this warp's padded smem
+                // buffer so that every global store instruction writes four full 128-byte rows (8 lanes x 16 B each)
+                float *tb = tr_buf + (warp - 4) * (32 * TR_PITCH);
+#pragma unroll
+                for (int r = 0; r < 32; r += 4)
+                    *reinterpret_cast<uint4 *>(tb + lane * TR_PITCH + r) = make_uint4(v[r], v[r + 1], v[r + 2], v[r + 3]);
+                __syncwarp();
+                float *drow = tdst + tdst_elems + ((size_t)((int)rank * 128 + q * 32) * 256 + c * 32 + (lane & 7) * 4);
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const int jr = 4 * k + (lane >> 3);
+                    const uint4 x = *reinterpret_cast<const uint4 *>(tb + jr * TR_PITCH + (lane & 7) * 4);
+                    *reinterpret_cast<uint4 *>(drow + (size_t)jr * 256) = x;
+                }
+                __syncwarp();
+            }
         } else if (jok) {
             float *ptr = p.out + (size_t)e * p.stride_e + j + (size_t)ic * p.stride_i;
             if (ic + 32 <= p.nb) {
@@ -629,7 +692,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_MAX_THREADS, 1)
                 const long rem = tile - (long)e * tiles_per_e;
                 const int tj = (int)(rem / p.tiles_i);
                 const int ti = (int)(rem - (long)tj * p.tiles_i);
-                const int col0 = tj * 256 + (int)rank * 128;
+                if (p.sym_diag && tj < ti) continue;   // symmetric mode: tile (tj, ti) is mirrored from (ti, tj)
+                const int col0 = (int)p.col_start + tj * 256 + (int)rank * 128;
                 const int row0 = (int)(p.row_start + (long)ti * p.BN + (long)rank * halfN);
                 if ((p.debug & 16) && tile != pair * p.grp_tiles) continue;   // diagnostics: MMA-only loop
                 for (int kb = 0; kb < p.kbs; kb++) {
@@ -662,15 +726,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_MAX_THREADS, 1)
             uint32_t phase = 0;
             long iter = 0;
             for (long grp = pair; grp < ngroups; grp += npairs)
-            for (long tile = grp * p.grp_tiles; tile < (grp + 1) * p.grp_tiles; tile++, iter++) {
+            for (long tile = grp * p.grp_tiles; tile < (grp + 1) * p.grp_tiles; tile++) {
+                if (p.sym_diag) {
+                    const long rem = tile % tiles_per_e;
+                    if (rem / p.tiles_i < rem % p.tiles_i) continue;   // tj < ti: mirrored, not computed
+                }
                 const int as = (int)(iter & 1);
                 const uint32_t aphase = (uint32_t)((iter >> 1) & 1);
+                iter++;
                 mbar_wait(&tempty_bar[as], aphase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.BN);
                 uint32_t accumulate = 0;
                 for (int kb = 0; kb < p.kbs; kb++) {
-                    const bool stale = (p.debug & 16) && iter != 0;
+                    const bool stale = (p.debug & 16) && iter != 1;
                     if (!stale) mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
                     if (elect_one_sync()) {
@@ -695,13 +764,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_MAX_THREADS, 1)
     } else if (warp >= 4) {
         // ------------------------------------------------------------------ epilogue (both CTAs)
         long iter = 0;
+        float *tr_buf = reinterpret_cast<float *>(smem + p.tr_off);
         for (long grp = pair; grp < ngroups; grp += npairs)
-        for (long tile = grp * p.grp_tiles; tile < (grp + 1) * p.grp_tiles; tile++, iter++) {
+        for (long tile = grp * p.grp_tiles; tile < (grp + 1) * p.grp_tiles; tile++) {
             const int e = (int)(tile / tiles_per_e);
             const long rem = tile - (long)e * tiles_per_e;
             const int tj = (int)(rem / p.tiles_i);
             const int ti = (int)(rem - (long)tj * p.tiles_i);
-            gemm_epilogue_tile<HALF_OUT>(p, tfull_bar, tempty_bar, tmem_base, e, tj, ti, iter, rank, warp, lane);
+            if (p.sym_diag && tj < ti) continue;
+            gemm_epilogue_tile<HALF_OUT>(p, tfull_bar, tempty_bar, tmem_base, e, tj, ti, iter, rank, warp, lane, tr_buf);
+            iter++;
         }
     }
     tc_fence_before();
@@ -755,7 +827,8 @@ static int make_operand_map(CUtensorMap *m, const void *base, const PrecInfo &pi
 
 // self-correlation fix-up: out[i][e][start+i] = exact sequential-FMA r (optionally Fisher-transformed)
 __global__ void k_self_corr_fixup(const float *__restrict__ selfdiag, int E, long V, long start, long nb, float *out,
-                                  long stride_i, long stride_e, int fisher_epochs, long tiled_t256, int half_out)
+                                  long stride_i, long stride_e, int fisher_epochs, long tiled_t256, int half_out,
+                                  long col_start)
 {
     const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= nb * E) return;
@@ -763,7 +836,7 @@ __global__ void k_self_corr_fixup(const float *__restrict__ selfdiag, int E, lon
     const int e = (int)(idx - i * E);
     float r = selfdiag[(size_t)e * V + start + i];
     if (e < fisher_epochs) r = fisher_fast(r);
-    const long j = start + i;
+    const long j = start + i - col_start;   // column inside the block
     if (tiled_t256 > 0) {   // tiled [i/256][j/256][e][i%256][j%256], fp32 or fp16 elements
         const size_t off = ((((size_t)(i >> 8) * tiled_t256 + (j >> 8)) * E + e) * 256 + (i & 255)) * 256 + (j & 255);
         if (half_out)
@@ -777,9 +850,16 @@ __global__ void k_self_corr_fixup(const float *__restrict__ selfdiag, int E, lon
 
 // tiled_t256 > 0: write the block in the tiled layout [ceil(nb/256)][tiled_t256][E][256][256] (the caller
 // provides round_up(nb, 256) rows of workspace and tiled_t256 == ceil(V2/256)); else out[i*stride_i + e*stride_e + j]
+// Symmetric mode (sym != nullptr; self-correlation, tiled fp32 output): the block covers columns [col_start, V2)
+// with col_start == start; column tiles below t_tj0 = ceil(nb/256) are the diagonal block, where only tiles
+// tj >= ti are computed and tiles tj > ti are mirrored into `out`; every tile with tj >= t_tj0 is also stored
+// transposed into sym->out_t, a tiled block [tiles_j - t_tj0][ceil(nb/256)][E][256][256] (rows = the column voxels).
+struct SymOut {
+    float *out_t;
+};
 static int launch_corr_umma(const void *rows_op, const void *cols_op, int precision, int E, int T, long V, long V2,
                             long start, long nb, float *out, long stride_i, long stride_e, int fisher_epochs,
-                            cudaStream_t st, long tiled_t256 = 0, int half_out = 0)
+                            cudaStream_t st, long tiled_t256 = 0, int half_out = 0, const SymOut *sym = nullptr)
 {
     PrecInfo pi;
     if (!prec_info(precision, &pi)) return fail(FCMA_EINVAL, "unknown precision %d", precision);
@@ -798,7 +878,17 @@ static int launch_corr_umma(const void *rows_op, const void *cols_op, int precis
     for (int sgm = 0; sgm < 3; sgm++) q.seg_r[sgm] = pi.seg_r[sgm], q.seg_c[sgm] = pi.seg_c[sgm];
     q.V2 = V2, q.nb = nb, q.row_start = start;
     q.BN = nb >= 256 ? 256 : (int)round_up(nb, 32);
-    q.tiles_j = (int)cdiv(V2, 256), q.tiles_i = (int)cdiv(nb, q.BN);
+    q.col_start = sym ? start : 0;
+    q.tiles_j = (int)cdiv(V2 - q.col_start, 256), q.tiles_i = (int)cdiv(nb, q.BN);
+    if (sym) {
+        if (rows_op != cols_op || V != V2 || tiled_t256 <= 0 || nb < 256 ||
+            ((nb & 255) && start + nb != V))
+            return fail(FCMA_EINVAL, "internal: symmetric GEMM needs self-correlation, the tiled block and whole row tiles");
+        q.sym_diag = 1;
+        q.t_tj0 = q.tiles_i;
+        q.out_t = q.tiles_j > q.tiles_i ? sym->out_t : nullptr;
+        if (q.tiles_j > q.tiles_i && !sym->out_t) return fail(FCMA_EINVAL, "internal: symmetric GEMM without a transposed block");
+    }
     q.total_tiles = (long)q.tiles_j * q.tiles_i * E;
     q.out = out, q.stride_i = stride_i, q.stride_e = stride_e, q.fisher_epochs = fisher_epochs;
     q.fmt = pi.fmt, q.out_scale = 1.0f / (pi.in_scale * pi.in_scale);
@@ -816,12 +906,19 @@ static int launch_corr_umma(const void *rows_op, const void *cols_op, int precis
         const char *sched = getenv("FCMA_GEMM_SCHED");       // 1: a pair takes all row tiles of a column tile in a row
         q.grp_tiles = (sched && sched[0] == '1') ? q.tiles_i : 1;
     }
-    const size_t cap = 227 * 1024 - 1024 /*alignment slack*/ - 256 /*barriers*/;
+    // symmetric mode: one padded 32x32 fp32 transposition buffer per epilogue warp
+    const size_t tr_bytes = !sym ? 0 : (size_t)q.epi_warps * 32 * (half_out ? (size_t)TR_PITCH_H : TR_PITCH * sizeof(float));
+    const size_t cap = 227 * 1024 - 1024 /*alignment slack*/ - 256 /*barriers*/ - tr_bytes;
     int stages = (int)(cap / q.stage_bytes);
     if (stages > GEMM_MAX_STAGES) stages = GEMM_MAX_STAGES;
+    {
+        const char *sg = getenv("FCMA_GEMM_STAGES");         // A/B: cap the number of smem stages
+        if (sg && atoi(sg) >= 2 && atoi(sg) < stages) stages = atoi(sg);
+    }
     if (stages < 2) return fail(FCMA_EINVAL, "internal: not enough shared memory for 2 stages");
     q.stages = stages;
-    const size_t smem = (size_t)stages * q.stage_bytes + 1024 + 256;
+    q.tr_off = sym ? (uint32_t)((size_t)stages * q.stage_bytes + 256) : 0;
+    const size_t smem = (size_t)stages * q.stage_bytes + 1024 + 256 + tr_bytes;
 
     CUtensorMap tm_cols, tm_rows;
     int rc = make_operand_map(&tm_cols, cols_op, pi, E, V2, Kp, 128);
@@ -852,7 +949,7 @@ static int launch_corr_umma(const void *rows_op, const void *cols_op, int precis
                                                           operand_plane_bytes(pi, precision, E, T, V));
         long n = nb * E;
         k_self_corr_fixup<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(sd, E, V, start, nb, out, stride_i, stride_e,
-                                                                 fisher_epochs, tiled_t256, half_out);
+                                                                 fisher_epochs, tiled_t256, half_out, q.col_start);
         LAUNCH_CHECK("k_self_corr_fixup");
     }
     return FCMA_OK;
@@ -1805,6 +1902,85 @@ static int run_pipeline(const void *rows_op, const void *cols_op, int precision,
         }
     }
     return FCMA_OK;
+}
+
+// Symmetric pipeline for self-correlation (raw_data2 is None): corr[i][e][j] == corr[j][e][i], so only the
+// blocks on and above the diagonal are contracted.  Pass p takes rows I = [a, a+n) against columns [a, V):
+//   GEMM (symmetric mode)  -> A = tiled block rows I x columns [a, V)      (diagonal n x n part: upper tiles
+//                                computed, lower tiles mirrored)
+//                          -> B = tiled block rows [a+n, V) x columns I   (transposed copies)
+//   normalise+SYRK over A  -> K[i] += sum_{j >= a} z z^T          for i in I
+//   normalise+SYRK over B  -> K[j] += sum_{i in I} z z^T          for j in [a+n, V)
+// After all passes of all callers (ranks) every K[x] has received every column exactly once.  Half the MMAs and
+// half the Fisher transforms of the plain pipeline; HBM traffic per correlation is unchanged.
+static int run_pipeline_sym(const void *op, int precision, int E, int T, long V, long start, long nb, int eps, int flags,
+                            float *work, size_t work_bytes, float *K, cudaStream_t st)
+{
+    if (!op || !work || !K) return fail(FCMA_EINVAL, "pipeline: null pointer");
+    if (nb <= 0 || start < 0 || start + nb > V) return fail(FCMA_EINVAL, "pipeline: rows [%ld, %ld) outside [0, %ld)", start, start + nb, V);
+    if (eps < 1) return fail(FCMA_EINVAL, "pipeline: epochs_per_subj must be positive");
+    if (((uintptr_t)work & 15)) return fail(FCMA_EINVAL, "pipeline: work buffer must be 16-byte aligned");
+    if (!fused_supported(E, eps)) return fail(FCMA_EINVAL, "symmetric pipeline needs the fused normalise+kernel path (E <= 64, power-of-two eps)");
+    if ((nb & 255) && start + nb != V)
+        return fail(FCMA_EINVAL, "symmetric pipeline: the row count must be a multiple of 256 unless the rows end at V");
+    if (flags & FCMA_FLAG_FISHER_IN_PASS2) return fail(FCMA_EINVAL, "symmetric pipeline applies Fisher-z in the GEMM epilogue");
+    const bool mask_self = (flags & FCMA_FLAG_MASK_SELF) != 0;
+    const int S_eps = (E / eps) * eps;
+    // fp16 Fisher-z block: same rule as the plain pipeline (flag, or the single-product operand modes)
+    const char *f16i = getenv("FCMA_F16_INTERMEDIATE");
+    bool half16 = (flags & FCMA_FLAG_F16_INTERMEDIATE) || precision == FCMA_PREC_BF16 || precision == FCMA_PREC_TF32;
+    if (f16i && (f16i[0] == '0' || f16i[0] == '1')) half16 = f16i[0] == '1';
+    const size_t esz = half16 ? sizeof(__half) : sizeof(float);
+    // per block row: A needs E * round_up(V - a, 256) floats, B at most the same again
+    const size_t row_bytes = 2 * fcma_work_bytes_per_row(E, V - start);
+    long rows_per_pass = (long)(work_bytes / row_bytes) & ~255L;
+    if (rows_per_pass < 256)
+        return fail(FCMA_ENOMEM, "work buffer too small for the symmetric pipeline: %zu bytes < %zu (256 rows)", work_bytes, 256 * row_bytes);
+    for (long done = 0; done < nb; done += rows_per_pass) {
+        const long a = start + done;
+        const long n = nb - done < rows_per_pass ? nb - done : rows_per_pass;
+        const long colsA = V - a, t256 = cdiv(colsA, 256), nt = cdiv(n, 256);
+        const long rowsB = V - a - n;
+        float *A = work;
+        float *B = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(work) + (size_t)nt * t256 * E * 65536 * esz);
+        if ((size_t)((nt * t256 + (t256 - nt) * nt) * E) * 65536 * esz > work_bytes)
+            return fail(FCMA_ENOMEM, "internal: symmetric pass does not fit the work buffer");
+        cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+        if (g_timing_on) {
+            for (int k = 0; k < 3; k++) CUDA_TRY(cudaEventCreate(&ev[k]));
+            CUDA_TRY(cudaEventRecord(ev[0], st));
+        }
+        SymOut so{B};
+        int rc = launch_corr_umma(op, op, precision, E, T, V, V, a, n, A, 4, 4, S_eps, st, t256, half16 ? 1 : 0, &so);
+        if (rc) return rc;
+        if (g_timing_on) CUDA_TRY(cudaEventRecord(ev[1], st));
+        rc = launch_norm_syrk(A, n, E, colsA, 256, 65536, eps, 1, mask_self ? 0 : -1, 1.0f, K + (size_t)a * E * E, 0, st,
+                              (long)E * 65536, half16 ? 1 : 0);
+        if (rc) return rc;
+        if (rowsB > 0) {
+            rc = launch_norm_syrk(B, rowsB, E, n, 256, 65536, eps, 1, -1, 1.0f, K + (size_t)(a + n) * E * E, 0, st,
+                                  (long)E * 65536, half16 ? 1 : 0);
+            if (rc) return rc;
+        }
+        if (g_timing_on) {
+            CUDA_TRY(cudaEventRecord(ev[2], st));
+            CUDA_TRY(cudaEventSynchronize(ev[2]));
+            float x = 0.f, y = 0.f;
+            CUDA_TRY(cudaEventElapsedTime(&x, ev[0], ev[1]));
+            CUDA_TRY(cudaEventElapsedTime(&y, ev[1], ev[2]));
+            g_t_gemm += x, g_t_syrk += y, g_t_passes++;
+            for (int k = 0; k < 3; k++) cudaEventDestroy(ev[k]);
+        }
+    }
+    return FCMA_OK;
+}
+
+extern "C" int fcma_voxel_kernels_sym(const void *op, int precision, int E, int T, long V, long start, long nb, int eps,
+                                      int flags, float *work_dev, size_t work_bytes, float *K_dev, void *stream)
+{
+    int rc = check_device();
+    if (rc) return rc;
+    return run_pipeline_sym(op, precision, E, T, V, start, nb, eps, flags, work_dev, work_bytes, K_dev, (cudaStream_t)stream);
 }
 
 extern "C" int fcma_voxel_kernels(const void *rows_op, const void *cols_op, int precision, int E, int T, long V, long V2,

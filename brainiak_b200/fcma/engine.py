@@ -244,6 +244,59 @@ def voxel_kernels(rows, cols, start, nb, eps, flags=0, work=None, out=None):
     return out
 
 
+def sym_row_partition(num_voxels, world_size, align=256):
+    """Shards of [0, V) for the symmetric pipeline: shard r contracts its rows with the columns at or to
+    the right of its first row, so equal WORK means equal trapezoid areas, s_r = V (1 - sqrt(1 - r/W)),
+    rounded to whole 256-row tiles (the last shard takes the ragged tail).  Returns [(start, n)]."""
+    V, W = int(num_voxels), int(world_size)
+    cuts = [0]
+    for r in range(1, W):
+        s = V * (1.0 - (1.0 - r / float(W)) ** 0.5)
+        s = int(round(s / align)) * align
+        cuts.append(min(max(s, cuts[-1]), V))
+    cuts.append(V)
+    return [(cuts[r], cuts[r + 1] - cuts[r]) for r in range(W)]
+
+
+def sym_supported(E, eps, nb=None, start=0, V=None):
+    """The symmetric self-correlation pipeline needs the fused normalise+kernel path and whole 256-row
+    tiles (a ragged row count only when the rows end at V)."""
+    ok = fused_supported(E, eps)
+    if ok and nb is not None and V is not None:
+        ok = nb >= 1 and (nb % 256 == 0 or start + nb == V) and (V - start) >= 256
+    return ok
+
+
+class SymWorkspace(Workspace):
+    """Scratch of the symmetric pipeline: per block row the block itself and its transposed copy."""
+
+    def __init__(self, E, V, rows, device, start=0):
+        lib = _lib.load()
+        self.per_row = 2 * lib.fcma_work_bytes_per_row(E, V - start)
+        self.rows = max(256, (int(rows) + 255) // 256 * 256)
+        self.buf = torch.empty(self.per_row * self.rows, dtype=torch.uint8, device=device)
+
+
+def voxel_kernels_sym(op, start, nb, eps, flags=0, work=None, out=None):
+    """Self-correlation a4 -> a6 -> a7 at half the tensor work (fcma_voxel_kernels_sym): rows
+    [start, start+nb) against columns [start, V), every block used for its row AND its column voxels.
+    ``out`` is the full ``[V, E, E]`` array and is accumulated into (zeros if not given)."""
+    lib = _lib.load()
+    E, V = op.E, op.V
+    if work is None:
+        free, _ = torch.cuda.mem_get_info(op.device)
+        per_row = 2 * lib.fcma_work_bytes_per_row(E, V - start)
+        rows = max(256, min((nb + 255) // 256 * 256, (min(free // 2, 64 << 30) // per_row) // 256 * 256))
+        work = SymWorkspace(E, V, rows, op.device, start)
+    if out is None:
+        out = torch.zeros((V, E, E), dtype=torch.float32, device=op.device)
+    with torch.cuda.device(op.device):
+        _lib.check(lib.fcma_voxel_kernels_sym(_ptr(op.buf), _prec_code(op.precision), E, op.T, V, start, nb,
+                                              int(eps), int(flags), _ptr(work.buf), work.buf.numel(), _ptr(out),
+                                              _stream_ptr()))
+    return out
+
+
 def classifier_kernel(rows, cols, start, nb, eps, flags=0, work=None, out=None):
     """a9 -> a10 -> a11: accumulates sum_i Z_i Z_i^T over rows [start, start+nb) into ``out`` [E, E]."""
     lib = _lib.load()

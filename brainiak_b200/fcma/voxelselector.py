@@ -86,6 +86,10 @@ class VoxelSelector:
     normalize: apply the per-epoch z-score of preprocessing.py:80-84 on the GPU while packing
     device: CUDA device (default: current / LOCAL_RANK)
     block_rows: voxel rows per GPU pass (default: sized to free HBM)
+    symmetric: with a single mask (``raw_data2 is None``) use ``corr[i, e, j] == corr[j, e, i]``: only the
+        blocks on and above the diagonal are contracted and each is used for its row and its column voxels
+        (engine.voxel_kernels_sym; half the tensor work, same kernels up to fp32 summation order).  Over
+        several GPUs the shards' partial kernel arrays are summed with one NCCL all-reduce.
     gpu_cv: run the voxelwise cross validation of a binary ``SVC(kernel='precomputed')`` on the GPU
         (batched restatement of libsvm's SMO, see engine.svm_cv_precomputed); ``False`` or any other
         classifier -> scikit-learn on the host, exactly as the reference (voxelselector.py:41-53)
@@ -93,7 +97,8 @@ class VoxelSelector:
 
     def __init__(self, labels, epochs_per_subj, num_folds, raw_data, raw_data2=None,
                  voxel_unit=64, process_num=4, master_rank=0, *, precision="fp32",
-                 mask_self=False, normalize=False, device=None, block_rows=None, gpu_cv=True):
+                 mask_self=False, normalize=False, device=None, block_rows=None, gpu_cv=True,
+                 symmetric=True):
         self.labels = labels
         self.epochs_per_subj = epochs_per_subj
         self.num_folds = num_folds
@@ -125,6 +130,7 @@ class VoxelSelector:
         self.device = device
         self.block_rows = block_rows
         self.gpu_cv = bool(gpu_cv)
+        self.symmetric = bool(symmetric)
         self._rows_op = None
         self._cols_op = None
         self._work = None
@@ -238,39 +244,93 @@ class VoxelSelector:
         return out
 
     # ------------------------------------------------------------------ the hot loop
+    def _symmetric_ok(self):
+        """Symmetric self-correlation pipeline: one mask, fused normalise+kernel path, at least one 256-row
+        tile per shard; over several ranks the partial kernels are summed with NCCL."""
+        import os
+        if not self.symmetric or self.raw_data2 is not None or os.environ.get("FCMA_NO_SYM") == "1":
+            return False
+        rank, world = self._world()
+        if world > 1:
+            import torch.distributed as dist
+            if dist.get_backend() != "nccl":
+                return False
+        E = len(self.raw_data)
+        return engine.sym_supported(E, self.epochs_per_subj) and self.num_voxels >= 512 * world
+
+    def _cv_block(self, K, s, nb, clf, on_gpu, folds):
+        """a7 tail + a8 for the unshrunk device kernels ``K`` of rows [s, s+nb)."""
+        t0 = time.time()
+        if on_gpu:
+            # shrink + cross validation without leaving the device (SURVEY §8f rank 1)
+            engine.shrink_kernels_(K)
+            acc = engine.svm_cv_precomputed(K, self.labels, self.num_folds, C=clf.C, tol=clf.tol,
+                                            max_iter=clf.max_iter, folds=folds)
+            logger.debug('rows [%d, %d): GPU cv %.3f s', s, s + nb, time.time() - t0)
+            return [(int(s + k), acc[k]) for k in range(nb)]
+        kernels = K.cpu().numpy()
+        shrink_kernels_(kernels)
+        res = self._do_cross_validation(clf, kernels, (s, nb))
+        logger.debug('rows [%d, %d): host cv %.3f s', s, s + nb, time.time() - t0)
+        return res
+
+    def _score_rows_symmetric(self, start, n, clf):
+        """Single-mask path: this rank contracts its shard of the upper block triangle
+        (engine.sym_row_partition), the [V, E, E] partial kernels are summed over the ranks, then every
+        rank cross-validates rows [start, start+n)."""
+        import torch
+        rank, world = self._world()
+        op, _ = self._operands()
+        E, V = op.E, self.num_voxels
+        s0, n0 = engine.sym_row_partition(V, world)[rank]
+        K = torch.zeros((V, E, E), dtype=torch.float32, device=op.device)
+        if n0 > 0:
+            rows = self.block_rows or None
+            if rows is None:
+                free, _ = torch.cuda.mem_get_info(op.device)
+                per_row = 2 * _lib.load().fcma_work_bytes_per_row(E, V - s0)
+                rows = min(free // 2, 64 << 30) // per_row
+            rows = max(256, min((n0 + 255) // 256 * 256, rows // 256 * 256))
+            if not isinstance(self._work, engine.SymWorkspace) or \
+                    self._work.buf.numel() < 2 * rows * _lib.load().fcma_work_bytes_per_row(E, V - s0):
+                self._work = None       # release the old scratch first
+                self._work = engine.SymWorkspace(E, V, rows, op.device, start=s0)
+            engine.voxel_kernels_sym(op, s0, n0, self.epochs_per_subj, flags=self._flags(True),
+                                     work=self._work, out=K)
+        if world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(K)
+        on_gpu = self.gpu_cv and engine.svm_cv_supported(clf, self.labels, self.num_folds, E)
+        folds = engine.make_svm_folds(self.labels, self.num_folds) if on_gpu else None
+        results = []
+        block = 8192
+        for s in range(start, start + n, block):
+            nb = min(block, start + n - s)
+            results += self._cv_block(K[s:s + nb], s, nb, clf, on_gpu, folds)
+        return results
+
     def _score_rows(self, start, n, clf):
         """GPU stages for rows [start, start+n) in HBM-sized blocks, then host CV."""
         import torch
         rows_op, cols_op = self._operands()
         E = rows_op.E
         results = []
+        if _is_precomputed_svc(clf) and self._symmetric_ok():
+            return self._score_rows_symmetric(start, n, clf)
         if _is_precomputed_svc(clf):
             fused = engine.fused_supported(E, self.epochs_per_subj)
             block = self.block_rows or engine.Workspace.rows_for(E, self.num_voxels2, n, rows_op.device)
             block = max(1, min(block, n))
-            if self._work is None or self._work.rows < block:
+            if self._work is None or self._work.rows < block or isinstance(self._work, engine.SymWorkspace):
+                self._work = None
                 self._work = engine.Workspace(E, self.num_voxels2, block, rows_op.device)
             on_gpu = self.gpu_cv and engine.svm_cv_supported(clf, self.labels, self.num_folds, E)
             folds = engine.make_svm_folds(self.labels, self.num_folds) if on_gpu else None
             for s in range(start, start + n, block):
                 nb = min(block, start + n - s)
-                t0 = time.time()
                 K = engine.voxel_kernels(rows_op, cols_op, s, nb, self.epochs_per_subj,
                                          flags=self._flags(fused), work=self._work)
-                if on_gpu:
-                    # shrink + cross validation without leaving the device (SURVEY §8f rank 1)
-                    engine.shrink_kernels_(K)
-                    acc = engine.svm_cv_precomputed(K, self.labels, self.num_folds, C=clf.C, tol=clf.tol,
-                                                    max_iter=clf.max_iter, folds=folds)
-                    results += [(int(s + k), acc[k]) for k in range(nb)]
-                    logger.debug('rows [%d, %d): kernels + GPU cv %.3f s', s, s + nb, time.time() - t0)
-                    continue
-                kernels = K.cpu().numpy()
-                t1 = time.time()
-                shrink_kernels_(kernels)
-                results += self._do_cross_validation(clf, kernels, (s, nb))
-                logger.debug('rows [%d, %d): kernels %.3f s, cv %.3f s', s, s + nb, t1 - t0,
-                             time.time() - t1)
+                results += self._cv_block(K, s, nb, clf, on_gpu, folds)
         else:
             unit = max(1, min(self.voxel_unit, n))
             for s in range(start, start + n, unit):

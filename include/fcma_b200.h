@@ -129,6 +129,17 @@ int fcma_voxel_kernels(const void *rows_op, const void *cols_op, int precision, 
                        long V2, long start, long nb, int eps, int flags, float *work_dev,
                        size_t work_bytes, float *K_dev, void *stream);
 
+/* Same result for SELF-correlation (raw_data2 is None) at half the tensor work, using corr[i][e][j] == corr[j][e][i]:
+ * rows [start, start+nb) are contracted with columns [start, V) only and every block is used twice, for its row
+ * voxels and (transposed) for its column voxels.  K_dev is the FULL [V][E][E] array and is ACCUMULATED into
+ * (caller zeroes it): after this call K[i] (start <= i < start+nb) holds the columns j >= start, and K[j]
+ * (j >= start+nb) has received the columns in [start, start+nb).  Calling it once with (0, V), or once per shard
+ * of a partition of [0, V) -- e.g. one shard per GPU followed by a sum (all-reduce) of the K arrays -- yields the
+ * same kernels as fcma_voxel_kernels.  nb must be a multiple of 256 unless start+nb == V; eps a power of two
+ * (fused path); work_dev should hold >= 2 * 256 * fcma_work_bytes_per_row(E, V - start) bytes. */
+int fcma_voxel_kernels_sym(const void *op, int precision, int E, int T, long V, long start, long nb, int eps,
+                           int flags, float *work_dev, size_t work_bytes, float *K_dev, void *stream);
+
 /* a9 -> a10 -> a11: K_dev[E][E] += sum over rows [start, start+nb) (beta = 1 semantics, caller zeroes
  * K first as classifier.py:311-313 does); eps <= 1 skips the normalisation (classifier.py:204). */
 int fcma_classifier_kernel(const void *rows_op, const void *cols_op, int precision, int E, int T,

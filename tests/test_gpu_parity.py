@@ -265,6 +265,48 @@ def test_tiled_intermediate_equals_strided(dev, two, monkeypatch):
     assert np.array_equal(got, out["0"])
 
 
+@pytest.mark.parametrize("case", ["ragged_multi_pass", "whole_tiles_sharded", "wide_E64"])
+def test_symmetric_pipeline_vs_oracle_and_plain(dev, case):
+    """fcma_voxel_kernels_sym (self-correlation: only blocks on/above the diagonal are contracted, every block is
+    used for its row voxels and -- transposed -- for its column voxels) against the CPU oracle and the plain
+    pipeline: ragged last pass (V not a multiple of 256), several passes through a small workspace, shards that
+    accumulate into one K (the multi-GPU scheme: sum of the shards' K arrays), self-column masking, E > 32."""
+    cfg = {"ragged_multi_pass": dict(V=1100, T=40, E=8, eps=4, rows=256, shards=1),
+           "whole_tiles_sharded": dict(V=1536, T=50, E=16, eps=8, rows=512, shards=3),
+           "wide_E64": dict(V=900, T=30, E=64, eps=16, rows=512, shards=2)}[case]
+    V, T, E, eps, rows, shards = (cfg[k] for k in ("V", "T", "E", "eps", "rows", "shards"))
+    raw, _ = synthetic.make_epochs(V, T, E, seed=2468)
+    ep, T_e = engine.stack_epochs(raw, dev)
+    op = engine.pack_epochs(ep, T_e, "fp32")
+    work = engine.SymWorkspace(E, V, rows, dev)
+    for fl in (_lib.FLAG_MASK_SELF, 0):
+        plain = engine.voxel_kernels(op, op, 0, V, eps, flags=fl)
+        work.buf.view(torch.float32).fill_(float("nan"))       # stale scratch must never reach the kernels
+        K = torch.zeros((V, E, E), device=dev)
+        for s, n in engine.sym_row_partition(V, shards):
+            if n > 0:
+                engine.voxel_kernels_sym(op, s, n, eps, flags=fl, work=work, out=K)
+        scale = float(plain.abs().max())
+        assert torch.isfinite(K).all()
+        assert float((K - K.transpose(1, 2)).abs().max()) == 0.0
+        # same values, summed in a different order: fp32 rounding of the partial sums only
+        assert float((K - plain).abs().max()) <= 4e-6 * scale
+        if fl:        # the oracle comparison uses the masked self column (the raw one is rounding noise)
+            sel = np.r_[0:40, V // 2:V // 2 + 40, V - 40:V]
+            for blk in (slice(0, 40), slice(V // 2, V // 2 + 40), slice(V - 40, V)):
+                _, z, _ = orc.voxel_block(raw, None, blk.start, 40, eps, shrink=False)
+                Kref = orc.kernel_matrices(zero_self(z, blk.start), f64=True)
+                got = K[blk].cpu().numpy()
+                assert np.max(np.abs(got - Kref)) <= k_tol(V) * np.max(np.abs(Kref))
+            del sel
+    # argument checks: ragged row count that does not end at V, workspace below 256 rows
+    with pytest.raises(ValueError):
+        engine.voxel_kernels_sym(op, 0, 300, eps, work=work, out=K)
+    tiny = engine.Workspace(E, V, 64, dev)
+    with pytest.raises(MemoryError):
+        engine.voxel_kernels_sym(op, 0, V, eps, work=tiny, out=K)
+
+
 def test_pipeline_vs_reference_golden_kernels(dev, golden):
     g = golden("vs_mid")
     d1, d2 = list(g["d1"]), list(g["d2"])

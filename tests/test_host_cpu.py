@@ -160,3 +160,23 @@ def test_svm_fold_descriptors_follow_sklearn_splits():
     assert not engine.svm_cv_supported(clf, [0, 1, 2] * 4, 2, 12)
     assert not engine.svm_cv_supported(svm.SVC(kernel="linear"), [0, 1] * 8, 4, 16)
     assert not engine.svm_cv_supported(clf, [0, 1] * 40, 4, 80)
+
+
+def test_sym_row_partition_covers_and_balances():
+    """Shards of the symmetric pipeline: contiguous, 256-aligned cuts, equal trapezoid work within a few %."""
+    from brainiak_b200.fcma import engine
+    for V in (50000, 30000, 100000, 1000, 257):
+        for W in (1, 2, 3, 4, 8):
+            parts = engine.sym_row_partition(V, W)
+            assert len(parts) == W and parts[0][0] == 0
+            assert sum(n for _, n in parts) == V
+            for r in range(1, W):
+                assert parts[r][0] == parts[r - 1][0] + parts[r - 1][1]
+                assert parts[r][0] % 256 == 0 or parts[r][0] == V
+            if V >= 30000:
+                work = [n * (V - s) - n * n / 2.0 for s, n in parts]
+                assert max(work) / (sum(work) / W) < 1.08
+    assert engine.sym_supported(32, 8) and not engine.sym_supported(32, 3)
+    assert engine.sym_supported(32, 8, nb=512, start=0, V=1000)
+    assert not engine.sym_supported(32, 8, nb=300, start=0, V=1000)
+    assert engine.sym_supported(32, 8, nb=488, start=512, V=1000)

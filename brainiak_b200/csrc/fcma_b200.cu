@@ -442,9 +442,63 @@ struct Gemm2Params {
     int sym_diag;                  // 1: inside the diagonal block skip tiles tj < ti; tiles tj > ti are mirrored
                                    //    into `out` as tile (tj, ti)
     uint32_t tr_off;               // smem offset of the per-warp transposition buffers (0: none)
+    int tr_w;                      // voxel rows i per transposition step: 8, 16 or 32 (buffer = 32 x (tr_w + pad))
+    uint32_t tr_warp_bytes;        // bytes of one warp's transposition buffer
 };
-constexpr int TR_PITCH = 36;       // floats per row of a 32x32 fp32 transposition buffer (conflict-free 16-byte accesses)
-constexpr int TR_PITCH_H = 80;     // bytes per row of a 32x32 fp16 transposition buffer
+
+// Transposed copy of one 32 (column voxels j = lanes) x 32 (row voxels i = registers) accumulator chunk: W values per
+// lane and step go through a padded per-warp smem buffer and come back with the lanes of a row side by side, so
+// a global store instruction writes 32/(W/4) rows x 4W contiguous bytes (fp32; W = 32: whole 128-byte lines).
+// Pitch W + 4 floats makes both the 16-byte writes (one row per lane) and the reads conflict-free.
+template <int W>
+__device__ __forceinline__ void store_transposed_f32(const uint32_t (&v)[32], float *tb, float *drow, int lane)
+{
+    constexpr int PITCH = W + 4, LPR = W / 4, RPI = 32 / LPR;   // lanes per row, rows per store instruction
+#pragma unroll
+    for (int s = 0; s < 32 / W; s++) {
+#pragma unroll
+        for (int r = 0; r < W; r += 4)
+            *reinterpret_cast<uint4 *>(tb + lane * PITCH + r) =
+                make_uint4(v[s * W + r], v[s * W + r + 1], v[s * W + r + 2], v[s * W + r + 3]);
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 32 / RPI; k++) {
+            const int jr = k * RPI + (W == 32 ? lane / LPR : lane % RPI);
+            const int part = W == 32 ? lane % LPR : lane / RPI;
+            const uint4 x = *reinterpret_cast<const uint4 *>(tb + jr * PITCH + part * 4);
+            *reinterpret_cast<uint4 *>(drow + (size_t)jr * 256 + s * W + part * 4) = x;
+        }
+        __syncwarp();
+    }
+}
+// fp16 tiles: pitch 2W + 16 bytes
+template <int W>
+__device__ __forceinline__ void store_transposed_f16(const uint32_t (&v)[32], uint8_t *tb, __half *drow, int lane)
+{
+    constexpr int PITCHB = 2 * W + 16, LPR = W / 8, RPI = 32 / LPR;
+#pragma unroll
+    for (int s = 0; s < 32 / W; s++) {
+#pragma unroll
+        for (int r = 0; r < W; r += 8) {
+            uint4 pk;
+            __half2 h0 = __floats2half2_rn(__uint_as_float(v[s * W + r + 0]), __uint_as_float(v[s * W + r + 1]));
+            __half2 h1 = __floats2half2_rn(__uint_as_float(v[s * W + r + 2]), __uint_as_float(v[s * W + r + 3]));
+            __half2 h2 = __floats2half2_rn(__uint_as_float(v[s * W + r + 4]), __uint_as_float(v[s * W + r + 5]));
+            __half2 h3 = __floats2half2_rn(__uint_as_float(v[s * W + r + 6]), __uint_as_float(v[s * W + r + 7]));
+            pk.x = *reinterpret_cast<uint32_t *>(&h0), pk.y = *reinterpret_cast<uint32_t *>(&h1);
+            pk.z = *reinterpret_cast<uint32_t *>(&h2), pk.w = *reinterpret_cast<uint32_t *>(&h3);
+            *reinterpret_cast<uint4 *>(tb + lane * PITCHB + 2 * r) = pk;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 32 / RPI; k++) {
+            const int jr = k * RPI + lane % RPI, part = lane / RPI;
+            const uint4 x = *reinterpret_cast<const uint4 *>(tb + jr * PITCHB + part * 16);
+            *reinterpret_cast<uint4 *>(drow + (size_t)jr * 256 + s * W + part * 8) = x;
+        }
+        __syncwarp();
+    }
+}
 
 // MMAs of one (column tile, row tile) operand pair of a stage: up to 4 k-steps of 32 bytes inside the
 // 128-byte swizzle atom.  Called by ONE elected thread with warp-uniform arguments, so descriptors and
@@ -555,30 +609,12 @@ __device__ __forceinline__ void gemm_epilogue_tile(const Gemm2Params &p, uint64_
                 ptr[r * 128] = odd ? __floats2half2_rn(other, mine) : __floats2half2_rn(mine, other);
             }
             if (mirror) {
-                // transposed copy of the fp16 tile: lane j packs its 32 consecutive i into 64 bytes; through the padded
-                // smem buffer every store instruction writes 8 rows x 64 contiguous bytes
-                uint8_t *tb = reinterpret_cast<uint8_t *>(tr_buf) + (warp - 4) * (32 * TR_PITCH_H);
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    uint4 pk;
-                    __half2 h0 = __floats2half2_rn(__uint_as_float(v[8 * k + 0]), __uint_as_float(v[8 * k + 1]));
-                    __half2 h1 = __floats2half2_rn(__uint_as_float(v[8 * k + 2]), __uint_as_float(v[8 * k + 3]));
-                    __half2 h2 = __floats2half2_rn(__uint_as_float(v[8 * k + 4]), __uint_as_float(v[8 * k + 5]));
-                    __half2 h3 = __floats2half2_rn(__uint_as_float(v[8 * k + 6]), __uint_as_float(v[8 * k + 7]));
-                    pk.x = *reinterpret_cast<uint32_t *>(&h0), pk.y = *reinterpret_cast<uint32_t *>(&h1);
-                    pk.z = *reinterpret_cast<uint32_t *>(&h2), pk.w = *reinterpret_cast<uint32_t *>(&h3);
-                    *reinterpret_cast<uint4 *>(tb + lane * TR_PITCH_H + 16 * k) = pk;
-                }
-                __syncwarp();
+                // transposed copy of the fp16 tile (lane j packs consecutive i; see store_transposed_f16)
+                uint8_t *tb = reinterpret_cast<uint8_t *>(tr_buf) + (warp - 4) * p.tr_warp_bytes;
                 __half *drow = reinterpret_cast<__half *>(tdst) + tdst_elems +
-                               ((size_t)((int)rank * 128 + q * 32) * 256 + c * 32 + (lane >> 3) * 8);
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const int jr = 8 * k + (lane & 7);
-                    const uint4 x = *reinterpret_cast<const uint4 *>(tb + jr * TR_PITCH_H + (lane >> 3) * 16);
-                    *reinterpret_cast<uint4 *>(drow + (size_t)jr * 256) = x;
-                }
-                __syncwarp();
+                               ((size_t)((int)rank * 128 + q * 32) * 256 + c * 32);
+                if (p.tr_w == 32) store_transposed_f16<32>(v, tb, drow, lane);
+                else store_transposed_f16<16>(v, tb, drow, lane);
             }
         } else if (p.tiled) {
             // the pair's 256x256 tile of epoch e is one contiguous 256 KB run, row pitch 1 KB; rows >= nb and
@@ -588,21 +624,12 @@ __device__ __forceinline__ void gemm_epilogue_tile(const Gemm2Params &p, uint64_
 #pragma unroll
             for (int r = 0; r < 32; r++) ptr[r * 256] = __uint_as_float(v[r]);
             if (mirror) {
-                // transposed copy: lane j holds 32 consecutive i; stage the 32x32 block in this warp's padded smem
-                // buffer so that every global store instruction writes four full 128-byte rows (8 lanes x 16 B each)
-                float *tb = tr_buf + (warp - 4) * (32 * TR_PITCH);
-#pragma unroll
-                for (int r = 0; r < 32; r += 4)
-                    *reinterpret_cast<uint4 *>(tb + lane * TR_PITCH + r) = make_uint4(v[r], v[r + 1], v[r + 2], v[r + 3]);
-                __syncwarp();
-                float *drow = tdst + tdst_elems + ((size_t)((int)rank * 128 + q * 32) * 256 + c * 32 + (lane & 7) * 4);
-#pragma unroll
-                for (int k = 0; k < 8; k++) {
-                    const int jr = 4 * k + (lane >> 3);
-                    const uint4 x = *reinterpret_cast<const uint4 *>(tb + jr * TR_PITCH + (lane & 7) * 4);
-                    *reinterpret_cast<uint4 *>(drow + (size_t)jr * 256) = x;
-                }
-                __syncwarp();
+                // transposed copy (see store_transposed_f32)
+                float *tb = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(tr_buf) + (warp - 4) * p.tr_warp_bytes);
+                float *drow = tdst + tdst_elems + ((size_t)((int)rank * 128 + q * 32) * 256 + c * 32);
+                if (p.tr_w == 32) store_transposed_f32<32>(v, tb, drow, lane);
+                else if (p.tr_w == 16) store_transposed_f32<16>(v, tb, drow, lane);
+                else store_transposed_f32<8>(v, tb, drow, lane);
             }
         } else if (jok) {
             float *ptr = p.out + (size_t)e * p.stride_e + j + (size_t)ic * p.stride_i;
@@ -877,12 +904,11 @@ static int launch_corr_umma(const void *rows_op, const void *cols_op, int precis
     q.segs = pi.segs, q.planes = pi.planes;
     for (int sgm = 0; sgm < 3; sgm++) q.seg_r[sgm] = pi.seg_r[sgm], q.seg_c[sgm] = pi.seg_c[sgm];
     q.V2 = V2, q.nb = nb, q.row_start = start;
-    q.BN = nb >= 256 ? 256 : (int)round_up(nb, 32);
+    q.BN = (nb >= 256 || sym) ? 256 : (int)round_up(nb, 32);   // symmetric mode: square 256x256 tiles throughout
     q.col_start = sym ? start : 0;
     q.tiles_j = (int)cdiv(V2 - q.col_start, 256), q.tiles_i = (int)cdiv(nb, q.BN);
     if (sym) {
-        if (rows_op != cols_op || V != V2 || tiled_t256 <= 0 || nb < 256 ||
-            ((nb & 255) && start + nb != V))
+        if (rows_op != cols_op || V != V2 || tiled_t256 <= 0 || ((nb & 255) && start + nb != V))
             return fail(FCMA_EINVAL, "internal: symmetric GEMM needs self-correlation, the tiled block and whole row tiles");
         q.sym_diag = 1;
         q.t_tj0 = q.tiles_i;
@@ -907,7 +933,15 @@ static int launch_corr_umma(const void *rows_op, const void *cols_op, int precis
         q.grp_tiles = (sched && sched[0] == '1') ? q.tiles_i : 1;
     }
     // symmetric mode: one padded 32x32 fp32 transposition buffer per epilogue warp
-    const size_t tr_bytes = !sym ? 0 : (size_t)q.epi_warps * 32 * (half_out ? (size_t)TR_PITCH_H : TR_PITCH * sizeof(float));
+    if (sym) {
+        // rows per transposition step: a smaller step needs a smaller buffer (room for one more smem stage in the
+        // 3-product modes) but writes shorter contiguous pieces.  FCMA_SYM_TR=8|16|32 overrides (A/B).
+        q.tr_w = half_out ? (q.epi_warps == 8 ? 32 : 16) : (q.epi_warps == 8 ? 16 : 8);
+        const char *tw = getenv("FCMA_SYM_TR");
+        if (tw && (atoi(tw) == 32 || atoi(tw) == 16 || (atoi(tw) == 8 && !half_out))) q.tr_w = atoi(tw);
+        q.tr_warp_bytes = half_out ? 32u * (2u * q.tr_w + 16u) : 32u * (q.tr_w + 4u) * 4u;
+    }
+    const size_t tr_bytes = !sym ? 0 : (size_t)q.epi_warps * q.tr_warp_bytes;
     const size_t cap = 227 * 1024 - 1024 /*alignment slack*/ - 256 /*barriers*/ - tr_bytes;
     int stages = (int)(cap / q.stage_bytes);
     if (stages > GEMM_MAX_STAGES) stages = GEMM_MAX_STAGES;
@@ -1194,6 +1228,13 @@ __global__ void __launch_bounds__(256) k_syrk_simt(const float *__restrict__ z, 
 // VEC: 0 scalar loads (unaligned fp32 block), 1 cp.async of an fp32 block, 2 cp.async of an fp16 block (tiled
 // intermediate written by the GEMM epilogue; a lane then takes 8 consecutive columns 8t..8t+7 per epoch as ONE
 // 16-byte copy -- which columns a k-slot stands for is irrelevant to a sum over columns).
+// F16_MMA: the z-scored values feed mma.m16n8k16 (fp16) instead of mma.m16n8k8 (tf32); compile-time switch kept for
+// A/B builds (-DFCMA_SYRK_TF32=1 restores the tf32 MMAs everywhere)
+#ifndef FCMA_SYRK_TF32
+constexpr bool F16_MMA = true;
+#else
+constexpr bool F16_MMA = false;
+#endif
 template <int R, int EPS, bool FISHER, int VEC>
 __global__ void __launch_bounds__(256, (R == 4 ? 2 : 1))
     k_norm_syrk(const float *__restrict__ C, long nb, int E, long n2, long stride_i, long ld, long chunk_step,
@@ -1479,6 +1520,29 @@ __global__ void __launch_bounds__(256, (R == 4 ? 2 : 1))
                         for (int u = 0; u < 4; u++)
                             if (j0 + (VEC == 2 ? 8 * t + 4 * h : 16 * h + 4 * t) + u == self_col) vals[r][h][u] = 0.f;
             }
+            if constexpr (EPS > 0 && F16_MMA) {
+                // ---- K += Z Z^T with fp16 operands (m16n8k16): z-scored values are bounded by sqrt(EPS - 1) and the
+                // untouched trailing epochs hold |r| <= 1, so fp16 (11-bit significand like tf32, round to nearest
+                // even) loses nothing against the tf32 path below at half the MMA instructions and one pack per two
+                // values.  k-slots (2t, 2t+1) <-> columns 0, 1 and (2t+8, 2t+9) <-> columns 2, 3 of the lane's h-th
+                // group of four columns, for the A and the B fragment alike.
+                uint32_t hv[R][2][2];
+#pragma unroll
+                for (int r = 0; r < R; r++)
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        hv[r][h][0] = pack_half2_rn(vals[r][h][0], vals[r][h][1]);
+                        hv[r][h][1] = pack_half2_rn(vals[r][h][2], vals[r][h][3]);
+                    }
+#pragma unroll
+                for (int h = 0; h < 2; h++)
+#pragma unroll
+                    for (int mu = 0; mu < MT; mu++)
+#pragma unroll
+                        for (int nu = 0; nu < NT; nu++)
+                            mma_f16_16x8x16(acc[mu][nu], hv[2 * mu][h][0], hv[2 * mu + 1][h][0], hv[2 * mu][h][1],
+                                            hv[2 * mu + 1][h][1], hv[nu][h][0], hv[nu][h][1]);
+            } else {
             uint32_t tv[R][2][4];
 #pragma unroll
             for (int r = 0; r < R; r++)
@@ -1500,6 +1564,7 @@ __global__ void __launch_bounds__(256, (R == 4 ? 2 : 1))
                             mma_tf32_16x8x8(acc[mu][nu], tv[2 * mu][h][2 * w], tv[2 * mu + 1][h][2 * w],
                                             tv[2 * mu][h][2 * w + 1], tv[2 * mu + 1][h][2 * w + 1], tv[nu][h][2 * w],
                                             tv[nu][h][2 * w + 1]);
+            }
             }  // ch < nchunks
             if constexpr (R == 4) {
                 if (++since_flush == FLUSH) {

@@ -290,7 +290,7 @@ def test_symmetric_pipeline_vs_oracle_and_plain(dev, case):
         assert torch.isfinite(K).all()
         assert float((K - K.transpose(1, 2)).abs().max()) == 0.0
         # same values, summed in a different order: fp32 rounding of the partial sums only
-        assert float((K - plain).abs().max()) <= 4e-6 * scale
+        assert float((K - plain).abs().max()) <= 1e-5 * scale      # measured 4e-7 .. 4e-6 (E = 64)
         if fl:        # the oracle comparison uses the masked self column (the raw one is rounding noise)
             sel = np.r_[0:40, V // 2:V // 2 + 40, V - 40:V]
             for blk in (slice(0, 40), slice(V // 2, V // 2 + 40), slice(V - 40, V)):
@@ -701,6 +701,28 @@ def test_voxel_selector_gpu_cv_equals_host_cv(dev, golden):
     a = VoxelSelector(labels, int(g["epsf"]), 4, raw, voxel_unit=32, process_num=0, gpu_cv=True).run(clf)
     b = VoxelSelector(labels, int(g["epsf"]), 4, raw, voxel_unit=32, process_num=0, gpu_cv=False).run(clf)
     assert a == b
+
+
+def test_voxel_selector_symmetric_equals_plain(dev):
+    """Public API: one mask -> the symmetric pipeline by default; same (voxel, accuracy) list as the plain
+    pipeline (the kernels differ only in the order of fp32 partial sums), host and GPU cross-validation."""
+    V, T, E, eps = 700, 40, 16, 4
+    raw, labels = synthetic.make_epochs(V, T, E, informative=12, signal=1.2, seed=31)
+    clf = svm.SVC(kernel="precomputed", shrinking=False, C=1)
+    a = VoxelSelector(labels, eps, 4, raw, process_num=0, block_rows=256)
+    assert a._symmetric_ok()
+    ra = a.run(clf)
+    assert isinstance(a._work, engine.SymWorkspace)
+    b = VoxelSelector(labels, eps, 4, raw, process_num=0, symmetric=False)
+    assert not b._symmetric_ok()
+    rb = b.run(clf)
+    da, db = dict(ra), dict(rb)
+    assert sorted(da) == list(range(V)) == sorted(db)
+    assert sum(1 for v in da if da[v] != db[v]) <= 1
+    assert [x for _, x in ra] == sorted((x for _, x in ra), reverse=True)
+    # two masks never take the symmetric path
+    c = VoxelSelector(labels, eps, 4, raw, raw_data2=raw, process_num=0)
+    assert not c._symmetric_ok()
 
 
 def test_voxel_selector_multi_gpu_nccl(dev):

@@ -26,7 +26,7 @@ def make(V, T, E, seed=0):
     return ep
 
 
-def parity(V, T, E, eps, rows_sym, shards=1, flags=0, prec="fp16x3", tol=2e-6):
+def parity(V, T, E, eps, rows_sym, shards=1, flags=0, prec="fp16x3", tol=1e-5):
     ep = make(V, T, E, seed=V)
     op = engine.pack_epochs(ep, None, prec)
     Kp = engine.voxel_kernels(op, op, 0, V, eps, flags=flags)
@@ -78,19 +78,23 @@ def big():
     K = torch.empty((V, E, E), device=dev)
     work = engine.Workspace(E, V, 4096, dev)
     plain = lambda: engine.voxel_kernels(op, op, 0, V, eps, work=work, out=K)   # noqa: E731
-    for st in ("3", "2"):
-        os.environ["FCMA_GEMM_STAGES"] = st
-        ms = timed_step(plain, 3)
-        g, s, n = kernel_times(plain)
-        print("plain  stages<=%s: step %.1f ms (%.3g corr/s); gemm %.1f ms, syrk %.1f ms per step over %d passes"
-              % (st, ms, V * V * E / ms * 1e3, g, s, n), flush=True)
-    del os.environ["FCMA_GEMM_STAGES"]
+    ms = timed_step(plain, 3)
+    g, s, n = kernel_times(plain)
+    print("plain: step %.1f ms (%.3g corr/s); gemm %.1f ms, syrk %.1f ms per step over %d passes"
+          % (ms, V * V * E / ms * 1e3, g, s, n), flush=True)
     Kp = K.clone()
     del work
     torch.cuda.empty_cache()
-    for rows, fl in ((4096, 0), (8192, 0), (4096, _lib.FLAG_F16_INTERMEDIATE)):
-        work = engine.SymWorkspace(E, V, rows, dev)
-        Ks = torch.empty((V, E, E), device=dev)
+    work = engine.SymWorkspace(E, V, 4096, dev)
+    Ks = torch.empty((V, E, E), device=dev)
+    F16 = _lib.FLAG_F16_INTERMEDIATE
+    for name, env, fl in (("sym fp32 block, 16 epilogue warps, 8-row transposition steps", {}, 0),
+                          ("sym fp32 block,  8 epilogue warps, 16-row steps", {"FCMA_GEMM_EPI_WARPS": "8"}, 0),
+                          ("sym fp32 block, 16 epilogue warps, 32-row steps (2 smem stages)", {"FCMA_SYM_TR": "32"}, 0),
+                          ("sym fp32 block, 16 epilogue warps, 16-row steps (2 smem stages)", {"FCMA_SYM_TR": "16"}, 0),
+                          ("sym fp16 block, 16 epilogue warps, 16-row steps", {}, F16),
+                          ("sym fp16 block,  8 epilogue warps, 32-row steps", {"FCMA_GEMM_EPI_WARPS": "8"}, F16)):
+        os.environ.update(env)
 
         def sym():
             Ks.zero_()
@@ -98,10 +102,10 @@ def big():
         ms = timed_step(sym, 3)
         g, s, n = kernel_times(sym)
         d = (Ks - Kp).abs().max().item() / Kp.abs().max().item()
-        print("sym rows/pass=%d flags=%d: step %.1f ms (%.3g corr/s); gemm %.1f ms, syrk %.1f ms per step over %d passes; "
-              "max|dK|/max|K| vs plain %.3g" % (rows, fl, ms, V * V * E / ms * 1e3, g, s, n, d), flush=True)
-        del work, Ks
-        torch.cuda.empty_cache()
+        print("%s: step %.1f ms (%.3g corr/s); gemm %.1f ms, syrk %.1f ms per step over %d passes; "
+              "max|dK|/max|K| vs plain %.3g" % (name, ms, V * V * E / ms * 1e3, g, s, n, d), flush=True)
+        for k in env:
+            del os.environ[k]
 
 
 if __name__ == "__main__":

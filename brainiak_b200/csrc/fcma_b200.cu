@@ -442,8 +442,10 @@ struct Gemm2Params {
     int sym_diag;                  // 1: inside the diagonal block skip tiles tj < ti; tiles tj > ti are mirrored
                                    //    into `out` as tile (tj, ti)
     uint32_t tr_off;               // smem offset of the per-warp transposition buffers (0: none)
-    int tr_w;                      // voxel rows i per transposition step: 8, 16 or 32 (buffer = 32 x (tr_w + pad))
+    int tr_w;                      // 0: the transposed chunk leaves through a TMA store (dense swizzled 32x32 buffer);
+                                   // 8, 16 or 32: voxel rows i per LDS/STG transposition step (buffer = 32 x (tr_w + pad))
     uint32_t tr_warp_bytes;        // bytes of one warp's transposition buffer
+    uint32_t bar_off;              // smem offset of the mbarriers
 };
 
 // Transposed copy of one 32 (column voxels j = lanes) x 32 (row voxels i = registers) accumulator chunk: W values per
@@ -451,50 +453,50 @@ struct Gemm2Params {
 // a global store instruction writes 32/(W/4) rows x 4W contiguous bytes (fp32; W = 32: whole 128-byte lines).
 // Pitch W + 4 floats makes both the 16-byte writes (one row per lane) and the reads conflict-free.
 template <int W>
-__device__ __forceinline__ void store_transposed_f32(const uint32_t (&v)[32], float *tb, float *drow, int lane)
+__device__ __forceinline__ void store_transposed_f32(const uint32_t (&v)[32], uint32_t tb, float *drow, int lane)
 {
     constexpr int PITCH = W + 4, LPR = W / 4, RPI = 32 / LPR;   // lanes per row, rows per store instruction
+    const int jr0 = W == 32 ? lane / LPR : lane % RPI;
+    const int part = W == 32 ? lane % LPR : lane / RPI;
+    const uint32_t wr = tb + (uint32_t)(lane * PITCH) * 4u;
+    const uint32_t rd = tb + (uint32_t)(jr0 * PITCH + part * 4) * 4u;
+    float *dst = drow + (size_t)jr0 * 256 + part * 4;
 #pragma unroll
     for (int s = 0; s < 32 / W; s++) {
 #pragma unroll
         for (int r = 0; r < W; r += 4)
-            *reinterpret_cast<uint4 *>(tb + lane * PITCH + r) =
-                make_uint4(v[s * W + r], v[s * W + r + 1], v[s * W + r + 2], v[s * W + r + 3]);
+            sts128(wr + r * 4, v[s * W + r], v[s * W + r + 1], v[s * W + r + 2], v[s * W + r + 3]);
         __syncwarp();
 #pragma unroll
         for (int k = 0; k < 32 / RPI; k++) {
-            const int jr = k * RPI + (W == 32 ? lane / LPR : lane % RPI);
-            const int part = W == 32 ? lane % LPR : lane / RPI;
-            const uint4 x = *reinterpret_cast<const uint4 *>(tb + jr * PITCH + part * 4);
-            *reinterpret_cast<uint4 *>(drow + (size_t)jr * 256 + s * W + part * 4) = x;
+            const uint4 x = lds128(rd + (uint32_t)(k * RPI * PITCH) * 4u);
+            *reinterpret_cast<uint4 *>(dst + (size_t)(k * RPI) * 256 + s * W) = x;
         }
         __syncwarp();
     }
 }
 // fp16 tiles: pitch 2W + 16 bytes
 template <int W>
-__device__ __forceinline__ void store_transposed_f16(const uint32_t (&v)[32], uint8_t *tb, __half *drow, int lane)
+__device__ __forceinline__ void store_transposed_f16(const uint32_t (&v)[32], uint32_t tb, __half *drow, int lane)
 {
     constexpr int PITCHB = 2 * W + 16, LPR = W / 8, RPI = 32 / LPR;
+    const int jr0 = lane % RPI, part = lane / RPI;
+    const uint32_t wr = tb + (uint32_t)(lane * PITCHB);
+    const uint32_t rd = tb + (uint32_t)(jr0 * PITCHB + part * 16);
+    __half *dst = drow + (size_t)jr0 * 256 + part * 8;
 #pragma unroll
     for (int s = 0; s < 32 / W; s++) {
 #pragma unroll
-        for (int r = 0; r < W; r += 8) {
-            uint4 pk;
-            __half2 h0 = __floats2half2_rn(__uint_as_float(v[s * W + r + 0]), __uint_as_float(v[s * W + r + 1]));
-            __half2 h1 = __floats2half2_rn(__uint_as_float(v[s * W + r + 2]), __uint_as_float(v[s * W + r + 3]));
-            __half2 h2 = __floats2half2_rn(__uint_as_float(v[s * W + r + 4]), __uint_as_float(v[s * W + r + 5]));
-            __half2 h3 = __floats2half2_rn(__uint_as_float(v[s * W + r + 6]), __uint_as_float(v[s * W + r + 7]));
-            pk.x = *reinterpret_cast<uint32_t *>(&h0), pk.y = *reinterpret_cast<uint32_t *>(&h1);
-            pk.z = *reinterpret_cast<uint32_t *>(&h2), pk.w = *reinterpret_cast<uint32_t *>(&h3);
-            *reinterpret_cast<uint4 *>(tb + lane * PITCHB + 2 * r) = pk;
-        }
+        for (int r = 0; r < W; r += 8)
+            sts128(wr + 2 * r, pack_half2_rn(__uint_as_float(v[s * W + r + 0]), __uint_as_float(v[s * W + r + 1])),
+                   pack_half2_rn(__uint_as_float(v[s * W + r + 2]), __uint_as_float(v[s * W + r + 3])),
+                   pack_half2_rn(__uint_as_float(v[s * W + r + 4]), __uint_as_float(v[s * W + r + 5])),
+                   pack_half2_rn(__uint_as_float(v[s * W + r + 6]), __uint_as_float(v[s * W + r + 7])));
         __syncwarp();
 #pragma unroll
         for (int k = 0; k < 32 / RPI; k++) {
-            const int jr = k * RPI + lane % RPI, part = lane / RPI;
-            const uint4 x = *reinterpret_cast<const uint4 *>(tb + jr * PITCHB + part * 16);
-            *reinterpret_cast<uint4 *>(drow + (size_t)jr * 256 + s * W + part * 8) = x;
+            const uint4 x = lds128(rd + (uint32_t)(k * RPI * PITCHB));
+            *reinterpret_cast<uint4 *>(dst + (size_t)(k * RPI) * 256 + s * W) = x;
         }
         __syncwarp();
     }
@@ -527,7 +529,8 @@ __device__ __forceinline__ void issue_kblock_mmas(uint32_t d_tmem, uint32_t addr
 template <bool HALF_OUT>
 __device__ __forceinline__ void gemm_epilogue_tile(const Gemm2Params &p, uint64_t *tfull_bar, uint64_t *tempty_bar,
                                                    uint32_t tmem_base, int e, int tj, int ti, long iter, uint32_t rank,
-                                                   int warp, int lane, float *tr_buf)
+                                                   int warp, int lane, uint32_t tr_buf /* shared-space address */,
+                                                   const CUtensorMap *tm_tA, const CUtensorMap *tm_tB)
 {
     const int q = warp & 3;
     const int part = (warp - 4) >> 2;
@@ -542,11 +545,16 @@ __device__ __forceinline__ void gemm_epilogue_tile(const Gemm2Params &p, uint64_
     float *tdst = nullptr;            // fp32 tile; HALF_OUT: the same element offset into an fp16 tile
     size_t tdst_elems = 0;
     bool mirror = false;
+    const CUtensorMap *tm_t = nullptr;
     if (p.out_t != nullptr && tj >= p.t_tj0) {
         tdst = p.out_t, tdst_elems = (((size_t)(tj - p.t_tj0) * p.tiles_i + ti) * p.E + e) * 65536, mirror = true;
+        tm_t = tm_tB;
     } else if (p.sym_diag && tj > ti) {
         tdst = p.out, tdst_elems = (((size_t)tj * p.tiles_j + ti) * p.E + e) * 65536, mirror = true;
+        tm_t = tm_tA;
     }
+    // TMA path: first row (column voxel) of this warp inside the tiled block seen as [rows][256]
+    const int trow0 = (int)(tdst_elems >> 8) + (int)rank * 128 + q * 32;
     const bool do_fisher = e < p.fisher_epochs;
     const float osc = p.out_scale;
     const long i0 = (long)ti * p.BN;
@@ -610,7 +618,29 @@ __device__ __forceinline__ void gemm_epilogue_tile(const Gemm2Params &p, uint64_
             }
             if (mirror) {
                 // transposed copy of the fp16 tile (lane j packs consecutive i; see store_transposed_f16)
-                uint8_t *tb = reinterpret_cast<uint8_t *>(tr_buf) + (warp - 4) * p.tr_warp_bytes;
+                const uint32_t tb = tr_buf + (uint32_t)(warp - 4) * p.tr_warp_bytes;
+                if (p.tr_w == 0) {
+                    // dense 32 x 64 B buffer in the 64-byte TMA swizzle (16-byte piece index ^ ((row / 2) % 4)): the
+                    // 16-byte writes are conflict-free and ONE bulk store moves the block, no LDS / STG
+                    if (lane == 0) tma_store_wait_read0();   // the previous block of this warp has left smem
+                    __syncwarp();
+                    const uint32_t wr = tb + (uint32_t)lane * 64u;
+                    const uint32_t sw = (uint32_t)(lane >> 1) & 3u;
+#pragma unroll
+                    for (int k = 0; k < 4; k++)
+                        sts128(wr + ((((uint32_t)k) ^ sw) << 4),
+                               pack_half2_rn(__uint_as_float(v[8 * k + 0]), __uint_as_float(v[8 * k + 1])),
+                               pack_half2_rn(__uint_as_float(v[8 * k + 2]), __uint_as_float(v[8 * k + 3])),
+                               pack_half2_rn(__uint_as_float(v[8 * k + 4]), __uint_as_float(v[8 * k + 5])),
+                               pack_half2_rn(__uint_as_float(v[8 * k + 6]), __uint_as_float(v[8 * k + 7])));
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_2d(tm_t, tb, c * 32, trow0);
+                        tma_store_commit();
+                    }
+                    continue;
+                }
                 __half *drow = reinterpret_cast<__half *>(tdst) + tdst_elems +
                                ((size_t)((int)rank * 128 + q * 32) * 256 + c * 32);
                 if (p.tr_w == 32) store_transposed_f16<32>(v, tb, drow, lane);
@@ -625,7 +655,25 @@ __device__ __forceinline__ void gemm_epilogue_tile(const Gemm2Params &p, uint64_
             for (int r = 0; r < 32; r++) ptr[r * 256] = __uint_as_float(v[r]);
             if (mirror) {
                 // transposed copy (see store_transposed_f32)
-                float *tb = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(tr_buf) + (warp - 4) * p.tr_warp_bytes);
+                const uint32_t tb = tr_buf + (uint32_t)(warp - 4) * p.tr_warp_bytes;
+                if (p.tr_w == 0) {
+                    // dense 32 x 128 B buffer in the 128-byte TMA swizzle (16-byte piece index ^ (row % 8)): conflict-free
+                    // 16-byte writes, ONE bulk store per block, no LDS / STG on the LSU path
+                    if (lane == 0) tma_store_wait_read0();   // the previous block of this warp has left smem
+                    __syncwarp();
+                    const uint32_t wr = tb + (uint32_t)lane * 128u;
+                    const uint32_t sw = (uint32_t)lane & 7u;
+#pragma unroll
+                    for (int k = 0; k < 8; k++)
+                        sts128(wr + ((((uint32_t)k) ^ sw) << 4), v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_2d(tm_t, tb, c * 32, trow0);
+                        tma_store_commit();
+                    }
+                    continue;
+                }
                 float *drow = tdst + tdst_elems + ((size_t)((int)rank * 128 + q * 32) * 256 + c * 32);
                 if (p.tr_w == 32) store_transposed_f32<32>(v, tb, drow, lane);
                 else if (p.tr_w == 16) store_transposed_f32<16>(v, tb, drow, lane);
@@ -658,12 +706,13 @@ __device__ __forceinline__ void gemm_epilogue_tile(const Gemm2Params &p, uint64_
 template <int KIND, bool HALF_OUT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_MAX_THREADS, 1)
     k_corr_umma2(const __grid_constant__ CUtensorMap tm_cols, const __grid_constant__ CUtensorMap tm_rows,
+                 const __grid_constant__ CUtensorMap tm_tA, const __grid_constant__ CUtensorMap tm_tB,
                  const Gemm2Params p)
 {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t *tiles = smem;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)p.stages * p.stage_bytes);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + p.bar_off);
     uint64_t *full_bar = bars;                         // [stages]  used in the leader CTA only
     uint64_t *empty_bar = bars + GEMM_MAX_STAGES;      // [stages]  one per CTA (multicast commit)
     uint64_t *tfull_bar = bars + 2 * GEMM_MAX_STAGES;  // [2]       one per CTA (multicast commit)
@@ -679,6 +728,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_MAX_THREADS, 1)
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tm_cols);
         tma_prefetch_desc(&tm_rows);
+        if (p.sym_diag && p.tr_w == 0) {
+            tma_prefetch_desc(&tm_tA);
+            if (p.out_t != nullptr) tma_prefetch_desc(&tm_tB);
+        }
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < p.stages; s++) {
@@ -791,7 +844,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_MAX_THREADS, 1)
     } else if (warp >= 4) {
         // ------------------------------------------------------------------ epilogue (both CTAs)
         long iter = 0;
-        float *tr_buf = reinterpret_cast<float *>(smem + p.tr_off);
+        const uint32_t tr_buf = smem_u32(smem + p.tr_off);
         for (long grp = pair; grp < ngroups; grp += npairs)
         for (long tile = grp * p.grp_tiles; tile < (grp + 1) * p.grp_tiles; tile++) {
             const int e = (int)(tile / tiles_per_e);
@@ -799,9 +852,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_MAX_THREADS, 1)
             const int tj = (int)(rem / p.tiles_i);
             const int ti = (int)(rem - (long)tj * p.tiles_i);
             if (p.sym_diag && tj < ti) continue;
-            gemm_epilogue_tile<HALF_OUT>(p, tfull_bar, tempty_bar, tmem_base, e, tj, ti, iter, rank, warp, lane, tr_buf);
+            gemm_epilogue_tile<HALF_OUT>(p, tfull_bar, tempty_bar, tmem_base, e, tj, ti, iter, rank, warp, lane, tr_buf,
+                                         &tm_tA, &tm_tB);
             iter++;
         }
+        if (p.sym_diag && p.tr_w == 0 && lane == 0) tma_store_wait_all();   // this lane's bulk stores are complete
     }
     tc_fence_before();
     cluster_sync_all();  // no CTA of the pair leaves while its peer may still touch its smem / TMEM
@@ -849,6 +904,25 @@ static int make_operand_map(CUtensorMap *m, const void *base, const PrecInfo &pi
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(FCMA_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return FCMA_OK;
+}
+
+// tiled block seen as a 2-D array [rows][256] (fp32 or fp16), box = one 32 x 32 accumulator chunk stored transposed;
+// the box's inner extent is exactly one swizzle span (128 B fp32 / 64 B fp16)
+static int make_transposed_map(CUtensorMap *m, const void *base, size_t rows, int half_out)
+{
+    PFN_tmEncodeTiled enc = get_encode_fn();
+    if (!enc) return fail(FCMA_ECUDA, "cuTensorMapEncodeTiled entry point not available");
+    const size_t esz = half_out ? 2 : 4;
+    cuuint64_t gdim[2] = {256, (cuuint64_t)rows};
+    cuuint64_t gstr[1] = {(cuuint64_t)(256 * esz)};
+    cuuint32_t box[2] = {32, 32};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, half_out ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                     const_cast<void *>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     half_out ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(FCMA_ECUDA, "cuTensorMapEncodeTiled (transposed block) failed with CUresult %d", (int)r);
     return FCMA_OK;
 }
 
@@ -925,8 +999,12 @@ static int launch_corr_umma(const void *rows_op, const void *cols_op, int precis
     if (q.tiled && tiled_t256 != q.tiles_j) return fail(FCMA_EINVAL, "internal: tiled output needs T256 == tiles_j");
     {
         // tuning / diagnostic knobs, read per launch (tools/ab_env.py, tools/gemm_debug.py)
-        const char *ew = getenv("FCMA_GEMM_EPI_WARPS");      // 8: two epilogue warps per TMEM lane quadrant instead of four
-        q.epi_warps = (ew && atoi(ew) == 8) ? 8 : 16;
+        // epilogue warps: four per TMEM lane quadrant, or two in symmetric mode (the store stream, not the epilogue's
+        // issue rate, bounds that kernel, and 8 x 4 KB of transposition buffers leave room for a third smem stage:
+        // 83 vs 92 ms of GEMM per step).  FCMA_GEMM_EPI_WARPS=8|16 overrides (A/B).
+        const char *ew = getenv("FCMA_GEMM_EPI_WARPS");
+        q.epi_warps = sym ? 8 : 16;
+        if (ew && (atoi(ew) == 8 || atoi(ew) == 16)) q.epi_warps = atoi(ew);
         const char *dbg = getenv("FCMA_GEMM_DEBUG");
         q.debug = dbg ? atoi(dbg) : 0;
         const char *sched = getenv("FCMA_GEMM_SCHED");       // 1: a pair takes all row tiles of a column tile in a row
@@ -934,12 +1012,14 @@ static int launch_corr_umma(const void *rows_op, const void *cols_op, int precis
     }
     // symmetric mode: one padded 32x32 fp32 transposition buffer per epilogue warp
     if (sym) {
-        // rows per transposition step: a smaller step needs a smaller buffer (room for one more smem stage in the
-        // 3-product modes) but writes shorter contiguous pieces.  FCMA_SYM_TR=8|16|32 overrides (A/B).
-        q.tr_w = half_out ? (q.epi_warps == 8 ? 32 : 16) : (q.epi_warps == 8 ? 16 : 8);
+        // default: the transposed chunk is staged in a dense swizzled buffer and leaves through ONE TMA bulk store.
+        // FCMA_SYM_TR=8|16|32 selects the LDS/STG transposition in steps of that many rows instead (A/B; a smaller
+        // step needs a smaller buffer but writes shorter contiguous pieces).
+        q.tr_w = 0;
         const char *tw = getenv("FCMA_SYM_TR");
         if (tw && (atoi(tw) == 32 || atoi(tw) == 16 || (atoi(tw) == 8 && !half_out))) q.tr_w = atoi(tw);
-        q.tr_warp_bytes = half_out ? 32u * (2u * q.tr_w + 16u) : 32u * (q.tr_w + 4u) * 4u;
+        q.tr_warp_bytes = q.tr_w == 0 ? (half_out ? 2048u : 4096u)
+                                      : (half_out ? 32u * (2u * q.tr_w + 16u) : 32u * (q.tr_w + 4u) * 4u);
     }
     const size_t tr_bytes = !sym ? 0 : (size_t)q.epi_warps * q.tr_warp_bytes;
     const size_t cap = 227 * 1024 - 1024 /*alignment slack*/ - 256 /*barriers*/ - tr_bytes;
@@ -951,14 +1031,26 @@ static int launch_corr_umma(const void *rows_op, const void *cols_op, int precis
     }
     if (stages < 2) return fail(FCMA_EINVAL, "internal: not enough shared memory for 2 stages");
     q.stages = stages;
-    q.tr_off = sym ? (uint32_t)((size_t)stages * q.stage_bytes + 256) : 0;
+    // smem: stages | transposition buffers (1024-byte aligned, as the swizzled TMA source needs) | mbarriers
+    q.tr_off = (uint32_t)((size_t)stages * q.stage_bytes);
+    q.bar_off = (uint32_t)((size_t)stages * q.stage_bytes + tr_bytes);
     const size_t smem = (size_t)stages * q.stage_bytes + 1024 + 256 + tr_bytes;
 
-    CUtensorMap tm_cols, tm_rows;
+    CUtensorMap tm_cols, tm_rows, tm_tA, tm_tB;
     int rc = make_operand_map(&tm_cols, cols_op, pi, E, V2, Kp, 128);
     if (rc) return rc;
     rc = make_operand_map(&tm_rows, rows_op, pi, E, V, Kp, q.BN / 2);
     if (rc) return rc;
+    memset(&tm_tA, 0, sizeof(tm_tA));
+    memset(&tm_tB, 0, sizeof(tm_tB));
+    if (sym && q.tr_w == 0) {
+        rc = make_transposed_map(&tm_tA, out, (size_t)q.tiles_i * q.tiles_j * E * 256, half_out);
+        if (rc) return rc;
+        if (q.out_t) {
+            rc = make_transposed_map(&tm_tB, q.out_t, (size_t)(q.tiles_j - q.tiles_i) * q.tiles_i * E * 256, half_out);
+            if (rc) return rc;
+        }
+    }
 
     long pairs = g_sm_count / 2;
     const unsigned gemm_threads = 128u + 32u * (unsigned)q.epi_warps;
@@ -967,7 +1059,7 @@ static int launch_corr_umma(const void *rows_op, const void *cols_op, int precis
 #define FCMA_LAUNCH_GEMM(KK, HH)                                                                                      \
     do {                                                                                                              \
         CUDA_TRY(cudaFuncSetAttribute(k_corr_umma2<KK, HH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        k_corr_umma2<KK, HH><<<(unsigned)(2 * pairs), gemm_threads, smem, st>>>(tm_cols, tm_rows, q);                \
+        k_corr_umma2<KK, HH><<<(unsigned)(2 * pairs), gemm_threads, smem, st>>>(tm_cols, tm_rows, tm_tA, tm_tB, q); \
     } while (0)
     if (pi.kind == 0) {
         if (half_out) FCMA_LAUNCH_GEMM(0, true); else FCMA_LAUNCH_GEMM(0, false);

@@ -319,18 +319,26 @@ def run_b200_arm(args):
         # the launches of one step of this rank: (correlations stored by the GEMM, operand columns read,
         # 256x256 tiles contracted)
         launches_desc = []
+        # symmetric pipeline: does pass 2 read block A column-wise (no transposed copy stored) or a transposed block B?
+        cols_pass = bool(sym and lib.fcma_sym_uses_column_pass(_lib.PREC[prec], E, eps, flags))
+        pass2_elems = 0.0        # correlations read by the normalise+SYRK launches of one step
+        rows_elems = 0.0         # ... of which by the row pass over the block itself
         if sym:
             rpp = work.rows
             for a in range(start, start + n, rpp):
                 nn = min(rpp, start + n - a)
                 colsA, rowsB = V - a, V - a - nn
                 nt, t256 = -(-nn // 256), -(-colsA // 256)
-                launches_desc.append((float(nn) * colsA + float(rowsB) * nn, colsA,
-                                      nt * (nt + 1) // 2 + (t256 - nt) * nt))
+                stored = float(nn) * colsA + (0.0 if cols_pass else float(rowsB) * nn)
+                launches_desc.append((stored, colsA, nt * (nt + 1) // 2 + (t256 - nt) * nt))
+                pass2_elems += float(nn) * colsA + float(rowsB) * nn
+                rows_elems += float(nn) * colsA
         else:
             for a in range(start, start + n, block):
                 nn = min(block, start + n - a)
                 launches_desc.append((float(nn) * V, V, -(-nn // 256) * -(-V // 256)))
+                pass2_elems += float(nn) * V
+                rows_elems += float(nn) * V
 
         def one_pass():
             if sym:
@@ -346,15 +354,19 @@ def run_b200_arm(args):
         for r in range(reps):
             one_pass()
         torch.cuda.synchronize()
-        g_ms, s_ms = _ct.c_double(0), _ct.c_double(0)
-        npass = lib.fcma_timing_read(_ct.byref(g_ms), _ct.byref(s_ms))
+        g_ms, s_ms, s2_ms = _ct.c_double(0), _ct.c_double(0), _ct.c_double(0)
+        npass = lib.fcma_timing_read3(_ct.byref(g_ms), _ct.byref(s_ms), _ct.byref(s2_ms))
         lib.fcma_timing_enable(0)
         assert npass == reps * len(launches_desc), (npass, len(launches_desc))
-        tg, ts = g_ms.value / npass, s_ms.value / npass          # average launch duration
         nl = float(len(launches_desc))
+        # average launch durations: GEMM, normalise+SYRK over the rows of the block, and (symmetric pipeline) the second
+        # normalise+SYRK launch of a pass: column-direction pass over the same block, or row pass over the transposed one
+        tg, ts, ts2 = g_ms.value / npass, s_ms.value / npass, s2_ms.value / npass
         corr_launch = sum(d[0] for d in launches_desc) * E / nl   # correlations stored per GEMM launch (average)
         opread_launch = sum(d[1] for d in launches_desc) / nl / V * op_bytes
         tiles_launch = sum(d[2] for d in launches_desc) / nl * E
+        rows_bytes = 4.0 * rows_elems * E / nl                    # read by the row pass over the block, per launch
+        second_bytes = 4.0 * (pass2_elems - rows_elems) * E / nl  # read by the second normalise+SYRK launch
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -364,37 +376,43 @@ def run_b200_arm(args):
         tf_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
         # algorithmic bytes of a GEMM launch: write 4 B per stored correlation + read the operand once
         alg_bytes = 4.0 * corr_launch + opread_launch
+        flop_exec = nprod * 2.0 * kp * tiles_launch * 65536.0
+        second_name = "k_norm_syrk_cols" if cols_pass else "k_norm_syrk (transposed block)"
+        kernels = {
+            "k_corr_umma": {"ms": tg, "algorithmic_bytes": alg_bytes, "hbm_gbs": alg_bytes / (tg * 1e-3) / 1e9,
+                            # correlations delivered (each counted 2*T flops) vs MMAs actually issued
+                            # (padded K, 3 products in the hi/lo split modes, computed tiles only)
+                            "tensor_tflops_executed": flop_exec / (tg * 1e-3) / 1e12,
+                            "tensor_executed_frac_of_bf16_sustained": flop_exec / (tg * 1e-3) / 1e12 / tf_peak,
+                            "operand_planes": planes},
+            "k_norm_syrk": {"ms": ts, "algorithmic_bytes": rows_bytes, "hbm_gbs": rows_bytes / (ts * 1e-3) / 1e9}}
+        if sym and ts2 > 0:
+            kernels[second_name] = {"ms": ts2, "algorithmic_bytes": second_bytes, "hbm_gbs": second_bytes / (ts2 * 1e-3) / 1e9}
+        for kd in kernels.values():
+            kd["frac_of_hbm_peak"] = kd["hbm_gbs"] / hbm_peak
+            kd["share_of_step"] = kd["ms"] / (tg + ts + ts2)
+        dominant = max(kernels, key=lambda k: kernels[k]["ms"])
         traffic = None
         try:
             tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-            key = "k_corr_umma:%s:%s" % (prec, "sym:rows%d" % work.rows if sym else "nb%d" % block)
-            traffic = tr.get(key)
+            tag = ("symcols:rows%d" if cols_pass else "sym:rows%d") % work.rows if sym else "nb%d" % block
+            traffic = tr.get("%s:%s:%s" % (dominant.split(" ")[0], prec, tag))
             if isinstance(traffic, dict):
                 # symmetric pipeline: launches differ in size; the ncu capture is the first (largest) launch, so the
                 # measured DRAM-bytes / algorithmic-bytes ratio of that launch is applied to the average launch
-                traffic = traffic["ratio"] * (4.0 * corr_launch + opread_launch)
+                traffic = traffic["ratio"] * kernels[dominant]["algorithmic_bytes"]
         except Exception:
             pass
-        dominant = "k_corr_umma" if tg >= ts else "k_norm_syrk"
-        ach = alg_bytes / (tg * 1e-3) / 1e9 if dominant == "k_corr_umma" else 4.0 * corr_launch / (ts * 1e-3) / 1e9
-        flop_exec = nprod * 2.0 * kp * tiles_launch * 65536.0
+        ach = kernels[dominant]["hbm_gbs"]
         roofline = {"kernel": dominant, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
                     "frac": ach / hbm_peak, "traffic": traffic,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
-                    "launch_ms": tg if dominant == "k_corr_umma" else ts,
+                    "launch_ms": kernels[dominant]["ms"],
                     "launches_per_step": int(nl), "rows_per_launch": work.rows if sym else block,
-                    "pipeline": "symmetric (blocks on/above the diagonal, each stored twice)" if sym else "plain",
-                    "algorithmic_bytes_per_launch": alg_bytes if dominant == "k_corr_umma" else 4.0 * corr_launch,
-                    "kernels": {
-                        "k_corr_umma": {"ms": tg, "hbm_gbs": alg_bytes / (tg * 1e-3) / 1e9,
-                                        # correlations delivered (each counted 2*T flops) vs MMAs actually issued
-                                        # (padded K, 3 products in the hi/lo split modes, computed tiles only)
-                                        "tensor_tflops_alg": 2.0 * T * corr_launch / (tg * 1e-3) / 1e12,
-                                        "tensor_tflops_executed": flop_exec / (tg * 1e-3) / 1e12,
-                                        "tensor_executed_frac_of_bf16_sustained": flop_exec / (tg * 1e-3) / 1e12 / tf_peak,
-                                        "operand_planes": planes},
-                        # both normalise+SYRK launches of a pass (block and transposed block) together
-                        "k_norm_syrk": {"ms": ts, "hbm_gbs": 4.0 * corr_launch / (ts * 1e-3) / 1e9}}}
+                    "pipeline": ("symmetric (blocks on/above the diagonal stored once, read row-wise and column-wise)" if cols_pass
+                                 else "symmetric (blocks on/above the diagonal, each stored twice)" if sym else "plain"),
+                    "algorithmic_bytes_per_launch": kernels[dominant]["algorithmic_bytes"],
+                    "kernels": kernels}
 
     # ---- the public API end to end: VoxelSelector.run(clf) incl. the batched GPU SVM cross-validation
     run_api = None

@@ -47,6 +47,7 @@ SIGNATURES = {
                                    c_long, c_int, c_int, c_void_p, c_size_t, c_void_p, c_void_p]),
     "fcma_voxel_kernels_sym": (c_int, [c_void_p, c_int, c_int, c_int, c_long, c_long, c_long, c_int, c_int,
                                        c_void_p, c_size_t, c_void_p, c_void_p]),
+    "fcma_sym_uses_column_pass": (c_int, [c_int, c_int, c_int, c_int]),
     "fcma_classifier_kernel": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_long, c_long,
                                        c_long, c_long, c_int, c_int, c_void_p, c_size_t, c_void_p,
                                        c_void_p]),
@@ -63,6 +64,8 @@ SIGNATURES = {
     "fcma_launch_count": (c_long, []),
     "fcma_timing_enable": (None, [c_int]),
     "fcma_timing_read": (c_long, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]),
+    "fcma_timing_read3": (c_long, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
+                                   ctypes.POINTER(ctypes.c_double)]),
 }
 
 _lib = None

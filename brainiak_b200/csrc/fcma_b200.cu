@@ -549,7 +549,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(const Gemm2Params &p, uint64_
     if (p.out_t != nullptr && tj >= p.t_tj0) {
         tdst = p.out_t, tdst_elems = (((size_t)(tj - p.t_tj0) * p.tiles_i + ti) * p.E + e) * 65536, mirror = true;
         tm_t = tm_tB;
-    } else if (p.sym_diag && tj > ti) {
+    } else if (p.sym_diag && tj > ti && tj < p.t_tj0) {
         tdst = p.out, tdst_elems = (((size_t)tj * p.tiles_j + ti) * p.E + e) * 65536, mirror = true;
         tm_t = tm_tA;
     }
@@ -956,7 +956,7 @@ __global__ void k_self_corr_fixup(const float *__restrict__ selfdiag, int E, lon
 // tj >= ti are computed and tiles tj > ti are mirrored into `out`; every tile with tj >= t_tj0 is also stored
 // transposed into sym->out_t, a tiled block [tiles_j - t_tj0][ceil(nb/256)][E][256][256] (rows = the column voxels).
 struct SymOut {
-    float *out_t;
+    float *out_t;      // nullptr: no transposed block (the column-direction pass reads block A instead)
 };
 static int launch_corr_umma(const void *rows_op, const void *cols_op, int precision, int E, int T, long V, long V2,
                             long start, long nb, float *out, long stride_i, long stride_e, int fisher_epochs,
@@ -987,7 +987,6 @@ static int launch_corr_umma(const void *rows_op, const void *cols_op, int precis
         q.sym_diag = 1;
         q.t_tj0 = q.tiles_i;
         q.out_t = q.tiles_j > q.tiles_i ? sym->out_t : nullptr;
-        if (q.tiles_j > q.tiles_i && !sym->out_t) return fail(FCMA_EINVAL, "internal: symmetric GEMM without a transposed block");
     }
     q.total_tiles = (long)q.tiles_j * q.tiles_i * E;
     q.out = out, q.stride_i = stride_i, q.stride_e = stride_e, q.fisher_epochs = fisher_epochs;
@@ -1705,6 +1704,253 @@ __global__ void __launch_bounds__(256, (R == 4 ? 2 : 1))
     }
 }
 
+// ============================================================================================
+// Column-direction normalise + SYRK over a tiled fp32 block (symmetric pipeline):
+//     K[j] += sum_{i < n} z(i, :, j) z(i, :, j)^T        for block columns j in [c0, n2)
+// reads the SAME block A = [n/256][T256][E][256 i][256 j] that k_norm_syrk reads row-wise, so the GEMM does not
+// have to store a transposed copy.  One CTA owns a strip of 32 adjacent columns (one 128-byte line per (epoch, row))
+// and walks down the n rows 16 at a time: the brick [32 epochs][16 rows][32 columns] (64 KB) is fetched with
+// cp.async into a swizzled smem buffer (double-buffered), warp w takes the 16-byte pieces of columns 4w .. 4w+3.
+// Lane (g, t) holds epochs 4g .. 4g+3 x rows {2t, 2t+1, 2t+8, 2t+9} x 4 columns; the rows are the k extent of
+// mma.m16n8k16 (fp16), one accumulator set per column (4 x 32 registers).  The within-subject z-score is the same
+// arithmetic as in k_norm_syrk (statistics over the epochs of a subject, packed fp32x2).  Every 128 row steps the
+// accumulators are folded into K through shared memory (bounds the truncating MMA accumulation chain, cf.
+// k_norm_syrk) with the symmetric mirror of cython_blas.pyx:200-207.
+// smem piece (line L = e*16 + row, 16-byte piece w) lives at (L*8 + (w ^ swz(L)))*16, swz(L) = ((L>>1)&3) | ((L>>6)&1)<<2:
+// the cp.async writes (8 consecutive threads = one line) and the LDS.128 reads (8 lanes = 2 epochs x 4 row pairs,
+// same piece w) are conflict-free.
+// ============================================================================================
+#ifndef FCMA_COLS_SEG_STEPS
+#define FCMA_COLS_SEG_STEPS 64
+#endif
+constexpr int COLS_SEG_STEPS = FCMA_COLS_SEG_STEPS;   // 16-row steps between folds of the accumulators into K
+constexpr int COLS_BRICKS = 3;        // 64 KB bricks in flight / in use (cp.async pipeline depth)
+template <int EPS>
+__global__ void __launch_bounds__(256, 1)
+    k_norm_syrk_cols(const float *__restrict__ A, long n, int E, long n2, long T256, long c0, float *K)
+{
+    constexpr int R = 4, EP = 32, MT = 2, NT = 4;
+    extern __shared__ __align__(1024) uint8_t cs_raw[];
+    uint8_t *cs = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(cs_raw) + 1023) & ~uintptr_t(1023));
+    const uint32_t brick0 = smem_u32(cs);            // 3 bricks of 64 KB; the first two double as [32 columns][EP*EP] fp32 at folds
+    float *s_fold = reinterpret_cast<float *>(cs);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int S_eps = (E / EPS) * EPS;
+    const long nstrips = (n2 - c0 + 31) / 32;
+    const long nsteps = (n + 15) / 16;
+
+    for (long strip = blockIdx.x; strip < nstrips; strip += gridDim.x) {
+        const long j0 = c0 + strip * 32;                       // first block column of the strip
+        const long tjx = j0 >> 8;
+        const int jo = (int)(j0 & 255);
+        // issue the cp.async copies of row step `st` into brick `b`
+        auto prefetch = [&](long st, int b) {
+            const long i0 = st * 16;
+            const long ti = i0 >> 8;
+            const int io = (int)(i0 & 255);
+            const float *tile0 = A + ((size_t)(ti * T256 + tjx) * E) * 65536 + (size_t)io * 256 + jo;
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                const int p = tid + 256 * k;
+                const int w = p & 7, line = p >> 3;
+                const int e = line >> 4, row = line & 15;
+                const bool ok = e < E && i0 + row < n;
+                const float *src = ok ? tile0 + (size_t)e * 65536 + row * 256 + w * 4 : A;
+                const uint32_t swz = (uint32_t)((line >> 1) & 3) | ((uint32_t)((line >> 6) & 1) << 2);
+                cp_async_16_zfill(cs + (size_t)b * 65536 + ((size_t)line * 8 + ((uint32_t)w ^ swz)) * 16, src, ok ? 16u : 0u);
+            }
+        };
+        for (long seg0 = 0; seg0 < nsteps; seg0 += COLS_SEG_STEPS) {
+            const long seg1 = seg0 + COLS_SEG_STEPS < nsteps ? seg0 + COLS_SEG_STEPS : nsteps;
+            float acc[4][MT][NT][4];
+#pragma unroll
+            for (int c = 0; c < 4; c++)
+#pragma unroll
+                for (int a = 0; a < MT; a++)
+#pragma unroll
+                    for (int b = 0; b < NT; b++)
+#pragma unroll
+                        for (int d = 0; d < 4; d++) acc[c][a][b][d] = 0.f;
+            int buf = 0;
+            prefetch(seg0, 0);
+            cp_async_commit();
+            if (seg0 + 1 < seg1) prefetch(seg0 + 1, 1);
+            cp_async_commit();
+            for (long st = seg0; st < seg1; st++) {
+                cp_async_wait<1>();        // brick `st` has landed (this thread's copies) ...
+                __syncthreads();           // ... and everybody's; every warp is also done with brick st-1,
+                if (st + 2 < seg1) prefetch(st + 2, buf == 0 ? 2 : buf - 1);   // whose buffer takes brick st+2
+                cp_async_commit();
+                // ---- this lane's 4 epochs x 4 rows x 4 columns
+                float vals[R][4][4];
+                const uint32_t bb = brick0 + (uint32_t)buf * 65536u;
+#pragma unroll
+                for (int r = 0; r < R; r++)
+#pragma unroll
+                    for (int sl = 0; sl < 4; sl++) {
+                        const int row = 2 * t + (sl & 1) + 8 * (sl >> 1);
+                        const int line = (R * g + r) * 16 + row;
+                        const uint32_t swz = (uint32_t)((line >> 1) & 3) | ((uint32_t)((line >> 6) & 1) << 2);
+                        const uint4 q = lds128(bb + ((uint32_t)line * 8u + ((uint32_t)warp ^ swz)) * 16u);
+                        vals[r][sl][0] = __uint_as_float(q.x), vals[r][sl][1] = __uint_as_float(q.y);
+                        vals[r][sl][2] = __uint_as_float(q.z), vals[r][sl][3] = __uint_as_float(q.w);
+                    }
+                // ---- within-subject z-score per (row, column): statistics over the EPS epochs of a subject
+                auto finish = [&](float2 msum, float2 s2sum, float2 &inv, float2 &mi) {
+                    const float2 nm = ffma2(msum, splat2(-1.0f / EPS), splat2(0.f));
+                    const float2 ns2 = ffma2(s2sum, splat2(-1.0f / EPS), splat2(0.f));
+                    const float2 negvar = ffma2(nm, nm, ns2);
+                    inv.x = negvar.x >= 0.f ? 0.f : rsqrt_ftz(-negvar.x);
+                    inv.y = negvar.y >= 0.f ? 0.f : rsqrt_ftz(-negvar.y);
+                    mi = ffma2(nm, inv, splat2(0.f));
+                };
+                if constexpr (EPS <= R) {
+                    constexpr int G = R / EPS;
+#pragma unroll
+                    for (int q = 0; q < G; q++) {
+                        const bool valid = R * g + q * EPS < S_eps;
+#pragma unroll
+                        for (int sl = 0; sl < 4; sl++)
+#pragma unroll
+                            for (int u = 0; u < 4; u += 2) {
+                                float2 m = splat2(0.f), s2 = splat2(0.f);
+#pragma unroll
+                                for (int b = 0; b < EPS; b++) {
+                                    const float2 x = make_float2(vals[q * EPS + b][sl][u], vals[q * EPS + b][sl][u + 1]);
+                                    m = ffma2(x, splat2(1.f), m);
+                                    s2 = ffma2(x, x, s2);
+                                }
+                                float2 inv, mi;
+                                finish(m, s2, inv, mi);
+                                if (valid) {
+#pragma unroll
+                                    for (int b = 0; b < EPS; b++) {
+                                        const float2 z = ffma2(make_float2(vals[q * EPS + b][sl][u], vals[q * EPS + b][sl][u + 1]), inv, mi);
+                                        vals[q * EPS + b][sl][u] = z.x, vals[q * EPS + b][sl][u + 1] = z.y;
+                                    }
+                                }
+                            }
+                    }
+                } else {
+                    constexpr int L = EPS / R;   // adjacent g-lanes per subject
+                    const bool valid = R * g < S_eps;
+#pragma unroll
+                    for (int sl = 0; sl < 4; sl++)
+#pragma unroll
+                        for (int u = 0; u < 4; u += 2) {
+                            float2 m = splat2(0.f), s2 = splat2(0.f);
+#pragma unroll
+                            for (int r = 0; r < R; r++) {
+                                const float2 x = make_float2(vals[r][sl][u], vals[r][sl][u + 1]);
+                                m = ffma2(x, splat2(1.f), m);
+                                s2 = ffma2(x, x, s2);
+                            }
+#pragma unroll
+                            for (int o = 1; o < L; o <<= 1) {
+                                m.x += __shfl_xor_sync(0xffffffffu, m.x, 4 * o);
+                                m.y += __shfl_xor_sync(0xffffffffu, m.y, 4 * o);
+                                s2.x += __shfl_xor_sync(0xffffffffu, s2.x, 4 * o);
+                                s2.y += __shfl_xor_sync(0xffffffffu, s2.y, 4 * o);
+                            }
+                            float2 inv, mi;
+                            finish(m, s2, inv, mi);
+                            if (valid) {
+#pragma unroll
+                                for (int r = 0; r < R; r++) {
+                                    const float2 z = ffma2(make_float2(vals[r][sl][u], vals[r][sl][u + 1]), inv, mi);
+                                    vals[r][sl][u] = z.x, vals[r][sl][u + 1] = z.y;
+                                }
+                            }
+                        }
+                }
+                // ---- K_j += Z Z^T: k-slots (2t, 2t+1) <-> row slots 0, 1 and (2t+8, 2t+9) <-> row slots 2, 3
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    uint32_t h0[R], h1[R];
+#pragma unroll
+                    for (int r = 0; r < R; r++) {
+                        h0[r] = pack_half2_rn(vals[r][0][c], vals[r][1][c]);
+                        h1[r] = pack_half2_rn(vals[r][2][c], vals[r][3][c]);
+                    }
+#pragma unroll
+                    for (int mu = 0; mu < MT; mu++)
+#pragma unroll
+                        for (int nu = 0; nu < NT; nu++)
+                            mma_f16_16x8x16(acc[c][mu][nu], h0[2 * mu], h0[2 * mu + 1], h1[2 * mu], h1[2 * mu + 1], h0[nu], h1[nu]);
+                }
+                buf = buf == COLS_BRICKS - 1 ? 0 : buf + 1;
+            }
+            // ---- fold the accumulators into K: registers -> smem [32 columns][EP*EP] -> mirrored, coalesced += on K
+            cp_async_wait<0>();
+            __syncthreads();
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                float *dstk = s_fold + (size_t)(warp * 4 + c) * (EP * EP);
+#pragma unroll
+                for (int mu = 0; mu < MT; mu++)
+#pragma unroll
+                    for (int nu = 0; nu < NT; nu++) {
+                        const int row0 = R * g + 2 * mu, row1 = row0 + 1;
+                        const int col0 = R * (2 * t) + nu, col1 = R * (2 * t + 1) + nu;
+                        dstk[row0 * EP + col0] = acc[c][mu][nu][0];
+                        dstk[row0 * EP + col1] = acc[c][mu][nu][1];
+                        dstk[row1 * EP + col0] = acc[c][mu][nu][2];
+                        dstk[row1 * EP + col1] = acc[c][mu][nu][3];
+                    }
+            }
+            __syncthreads();
+            const int EE = E * E;
+            const long ncols = n2 - j0 < 32 ? n2 - j0 : 32;       // real columns of this strip
+            const int total = (int)ncols * EE;
+            float *Kst = K + (size_t)j0 * EE;                     // the strip's kernels are contiguous
+            auto folded = [&](int idx) {
+                const int col = idx / EE, rem = idx - col * EE;
+                const int a = rem / E, b = rem - a * E;
+                const float *sk = s_fold + (size_t)col * (EP * EP);
+                return a >= b ? sk[a * EP + b] : sk[b * EP + a];
+            };
+            if ((EE & 3) == 0 && ((reinterpret_cast<uintptr_t>(Kst) & 15) == 0)) {
+                // 16-byte read-modify-write, 8 independent loads in flight per thread (the loop is latency-bound)
+                float4 *K4 = reinterpret_cast<float4 *>(Kst);
+                const int total4 = total >> 2;
+                for (int base = tid; base < total4; base += 256 * 8) {
+                    float4 old[8];
+#pragma unroll
+                    for (int u = 0; u < 8; u++) {
+                        const int i4 = base + u * 256;
+                        if (i4 < total4) old[u] = K4[i4];
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; u++) {
+                        const int i4 = base + u * 256;
+                        if (i4 < total4) {
+                            float4 o = old[u];
+                            o.x += folded(4 * i4), o.y += folded(4 * i4 + 1), o.z += folded(4 * i4 + 2), o.w += folded(4 * i4 + 3);
+                            K4[i4] = o;
+                        }
+                    }
+                }
+            } else {
+                for (int base = tid; base < total; base += 256 * 8) {
+                    float old[8];
+#pragma unroll
+                    for (int u = 0; u < 8; u++) {
+                        const int i1 = base + u * 256;
+                        if (i1 < total) old[u] = Kst[i1];
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; u++) {
+                        const int i1 = base + u * 256;
+                        if (i1 < total) Kst[i1] = old[u] + folded(i1);
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
 __global__ void k_scale(float *x, long n, float s)
 {
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
@@ -1800,6 +2046,34 @@ static int launch_norm_syrk(const float *C, long nb, int E, long n2, long stride
 #undef FCMA_DISPATCH
     if (!ok) return fail(FCMA_EINVAL, "internal: no k_norm_syrk instantiation for E=%d eps=%d", E, eps_mode);
     LAUNCH_CHECK("k_norm_syrk");
+    return FCMA_OK;
+}
+
+// column-direction pass over a tiled fp32 block (k_norm_syrk_cols): K[j] += ... for block columns [c0, n2)
+static bool cols_supported(int E, int eps) { return E <= 32 && eps >= 1 && eps <= 32 && (eps & (eps - 1)) == 0; }
+static int launch_norm_syrk_cols(const float *A, long n, int E, long n2, long T256, long c0, int eps, float *K,
+                                 cudaStream_t st)
+{
+    if (!cols_supported(E, eps) || (c0 & 31) || c0 >= n2) return fail(FCMA_EINVAL, "internal: column pass unsupported E=%d eps=%d c0=%ld", E, eps, c0);
+    const long nstrips = cdiv(n2 - c0, 32);
+    const unsigned grid = (unsigned)(nstrips < g_sm_count ? nstrips : g_sm_count);
+    const size_t smem = (size_t)COLS_BRICKS * 65536 + 1024;
+#define FCMA_COLS_CASE(EPSV)                                                                                        \
+    case EPSV:                                                                                                      \
+        CUDA_TRY(cudaFuncSetAttribute(k_norm_syrk_cols<EPSV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        k_norm_syrk_cols<EPSV><<<grid, 256, smem, st>>>(A, n, E, n2, T256, c0, K);                                 \
+        break;
+    switch (eps) {
+        FCMA_COLS_CASE(1)
+        FCMA_COLS_CASE(2)
+        FCMA_COLS_CASE(4)
+        FCMA_COLS_CASE(8)
+        FCMA_COLS_CASE(16)
+        FCMA_COLS_CASE(32)
+    default: return fail(FCMA_EINVAL, "internal: no k_norm_syrk_cols instantiation for eps=%d", eps);
+    }
+#undef FCMA_COLS_CASE
+    LAUNCH_CHECK("k_norm_syrk_cols");
     return FCMA_OK;
 }
 
@@ -1949,13 +2223,20 @@ extern "C" size_t fcma_work_bytes_per_row(int E, long V2)
 // Optional per-kernel timing of the fused pipelines (bench.py's live roofline measurement): when enabled,
 // CUDA events bracket the GEMM and the normalise+SYRK launches on the launch stream.
 static int g_timing_on = 0;
-static double g_t_gemm = 0.0, g_t_syrk = 0.0;
+static double g_t_gemm = 0.0, g_t_syrk = 0.0, g_t_syrk2 = 0.0;   // syrk2: second normalise+SYRK launch of a symmetric pass
 static long g_t_passes = 0;
 extern "C" void fcma_timing_enable(int on)
 {
     g_timing_on = on;
-    g_t_gemm = g_t_syrk = 0.0;
+    g_t_gemm = g_t_syrk = g_t_syrk2 = 0.0;
     g_t_passes = 0;
+}
+extern "C" long fcma_timing_read3(double *gemm_ms, double *syrk_ms, double *syrk2_ms)
+{
+    if (gemm_ms) *gemm_ms = g_t_gemm;
+    if (syrk_ms) *syrk_ms = g_t_syrk - g_t_syrk2;
+    if (syrk2_ms) *syrk2_ms = g_t_syrk2;
+    return g_t_passes;
 }
 extern "C" long fcma_timing_read(double *gemm_ms, double *syrk_ms)
 {
@@ -2070,6 +2351,21 @@ static int run_pipeline(const void *rows_op, const void *cols_op, int precision,
 //   normalise+SYRK over B  -> K[j] += sum_{i in I} z z^T          for j in [a+n, V)
 // After all passes of all callers (ranks) every K[x] has received every column exactly once.  Half the MMAs and
 // half the Fisher transforms of the plain pipeline; HBM traffic per correlation is unchanged.
+// which variant run_pipeline_sym takes for the column voxels' sums: 1 = column-direction pass over block A
+// (fp32 block, E <= 32), 0 = transposed block B + row pass
+static bool sym_uses_cols(int precision, int E, int eps, int flags)
+{
+    const char *f16i = getenv("FCMA_F16_INTERMEDIATE");
+    bool half16 = (flags & FCMA_FLAG_F16_INTERMEDIATE) || precision == FCMA_PREC_BF16 || precision == FCMA_PREC_TF32;
+    if (f16i && (f16i[0] == '0' || f16i[0] == '1')) half16 = f16i[0] == '1';
+    const char *sc = getenv("FCMA_SYM_COLS");
+    return !half16 && cols_supported(E, eps) && !(sc && sc[0] == '0');
+}
+extern "C" int fcma_sym_uses_column_pass(int precision, int E, int eps, int flags)
+{
+    return sym_uses_cols(precision, E, eps, flags) ? 1 : 0;
+}
+
 static int run_pipeline_sym(const void *op, int precision, int E, int T, long V, long start, long nb, int eps, int flags,
                             float *work, size_t work_bytes, float *K, cudaStream_t st)
 {
@@ -2088,6 +2384,9 @@ static int run_pipeline_sym(const void *op, int precision, int E, int T, long V,
     bool half16 = (flags & FCMA_FLAG_F16_INTERMEDIATE) || precision == FCMA_PREC_BF16 || precision == FCMA_PREC_TF32;
     if (f16i && (f16i[0] == '0' || f16i[0] == '1')) half16 = f16i[0] == '1';
     const size_t esz = half16 ? sizeof(__half) : sizeof(float);
+    // column-direction pass (fp32 block, E <= 32): the column voxels' sums are taken from block A itself, no transposed
+    // copy is stored.  FCMA_SYM_COLS=0 keeps the transposed block B (A/B).
+    const bool use_cols = sym_uses_cols(precision, E, eps, flags);
     // per block row: A needs E * round_up(V - a, 256) floats, B at most the same again
     const size_t row_bytes = 2 * fcma_work_bytes_per_row(E, V - start);
     long rows_per_pass = (long)(work_bytes / row_bytes) & ~255L;
@@ -2102,19 +2401,23 @@ static int run_pipeline_sym(const void *op, int precision, int E, int T, long V,
         float *B = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(work) + (size_t)nt * t256 * E * 65536 * esz);
         if ((size_t)((nt * t256 + (t256 - nt) * nt) * E) * 65536 * esz > work_bytes)
             return fail(FCMA_ENOMEM, "internal: symmetric pass does not fit the work buffer");
-        cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+        cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
         if (g_timing_on) {
-            for (int k = 0; k < 3; k++) CUDA_TRY(cudaEventCreate(&ev[k]));
+            for (int k = 0; k < 4; k++) CUDA_TRY(cudaEventCreate(&ev[k]));
             CUDA_TRY(cudaEventRecord(ev[0], st));
         }
-        SymOut so{B};
+        SymOut so{use_cols ? nullptr : B};
         int rc = launch_corr_umma(op, op, precision, E, T, V, V, a, n, A, 4, 4, S_eps, st, t256, half16 ? 1 : 0, &so);
         if (rc) return rc;
         if (g_timing_on) CUDA_TRY(cudaEventRecord(ev[1], st));
         rc = launch_norm_syrk(A, n, E, colsA, 256, 65536, eps, 1, mask_self ? 0 : -1, 1.0f, K + (size_t)a * E * E, 0, st,
                               (long)E * 65536, half16 ? 1 : 0);
         if (rc) return rc;
-        if (rowsB > 0) {
+        if (g_timing_on) CUDA_TRY(cudaEventRecord(ev[3], st));
+        if (rowsB > 0 && use_cols) {
+            rc = launch_norm_syrk_cols(A, n, E, colsA, t256, n, eps, K + (size_t)a * E * E, st);
+            if (rc) return rc;
+        } else if (rowsB > 0) {
             rc = launch_norm_syrk(B, rowsB, E, n, 256, 65536, eps, 1, -1, 1.0f, K + (size_t)(a + n) * E * E, 0, st,
                                   (long)E * 65536, half16 ? 1 : 0);
             if (rc) return rc;
@@ -2122,11 +2425,12 @@ static int run_pipeline_sym(const void *op, int precision, int E, int T, long V,
         if (g_timing_on) {
             CUDA_TRY(cudaEventRecord(ev[2], st));
             CUDA_TRY(cudaEventSynchronize(ev[2]));
-            float x = 0.f, y = 0.f;
+            float x = 0.f, y = 0.f, z = 0.f;
             CUDA_TRY(cudaEventElapsedTime(&x, ev[0], ev[1]));
             CUDA_TRY(cudaEventElapsedTime(&y, ev[1], ev[2]));
-            g_t_gemm += x, g_t_syrk += y, g_t_passes++;
-            for (int k = 0; k < 3; k++) cudaEventDestroy(ev[k]);
+            CUDA_TRY(cudaEventElapsedTime(&z, ev[3], ev[2]));
+            g_t_gemm += x, g_t_syrk += y, g_t_syrk2 += z, g_t_passes++;
+            for (int k = 0; k < 4; k++) cudaEventDestroy(ev[k]);
         }
     }
     return FCMA_OK;

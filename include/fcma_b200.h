@@ -139,6 +139,10 @@ int fcma_voxel_kernels(const void *rows_op, const void *cols_op, int precision, 
  * (fused path); work_dev should hold >= 2 * 256 * fcma_work_bytes_per_row(E, V - start) bytes. */
 int fcma_voxel_kernels_sym(const void *op, int precision, int E, int T, long V, long start, long nb, int eps,
                            int flags, float *work_dev, size_t work_bytes, float *K_dev, void *stream);
+/* 1 if fcma_voxel_kernels_sym takes the column voxels' sums from the stored block itself (column-direction
+ * normalise+SYRK pass: fp32 block, E <= 32, power-of-two eps <= 32), 0 if it stores a transposed copy of every
+ * block and runs the row pass over it (fp16 block, E > 32).  Informational (bench accounting). */
+int fcma_sym_uses_column_pass(int precision, int E, int eps, int flags);
 
 /* a9 -> a10 -> a11: K_dev[E][E] += sum over rows [start, start+nb) (beta = 1 semantics, caller zeroes
  * K first as classifier.py:311-313 does); eps <= 1 skips the normalisation (classifier.py:204). */
@@ -181,6 +185,9 @@ int fcma_host_within_subject_norm(float *corr_host, long n0, int E, long n2, int
  * the correlation GEMM (+ diagonal fix-up) and of the normalise+SYRK kernel */
 void fcma_timing_enable(int on);
 long fcma_timing_read(double *gemm_ms, double *syrk_ms);
+/* same with the normalise+SYRK time split: syrk_ms = first launch of a pass (rows of the block), syrk2_ms = second
+ * launch of a symmetric pass (column-direction pass, or the row pass over the transposed block) */
+long fcma_timing_read3(double *gemm_ms, double *syrk_ms, double *syrk2_ms);
 
 /* number of kernel launches issued by this library in the calling process (for bench accounting) */
 long fcma_launch_count(void);

@@ -88,12 +88,10 @@ def big():
     work = engine.SymWorkspace(E, V, 4096, dev)
     Ks = torch.empty((V, E, E), device=dev)
     F16 = _lib.FLAG_F16_INTERMEDIATE
-    for name, env, fl in (("sym fp32 block, 16 epilogue warps, TMA-stored transposed copy (2 smem stages)", {}, 0),
-                          ("sym fp32 block,  8 epilogue warps, TMA-stored transposed copy (3 smem stages)", {"FCMA_GEMM_EPI_WARPS": "8"}, 0),
-                          ("sym fp32 block, 16 epilogue warps, LDS/STG 16-row steps (2 smem stages)", {"FCMA_SYM_TR": "16"}, 0),
-                          ("sym fp16 block, 16 epilogue warps, TMA-stored transposed copy", {}, F16),
-                          ("sym fp16 block,  8 epilogue warps, TMA-stored transposed copy", {"FCMA_GEMM_EPI_WARPS": "8"}, F16),
-                          ("sym fp16 block, 16 epilogue warps, LDS/STG 16-row steps", {"FCMA_SYM_TR": "16"}, F16)):
+    for name, env, fl in (("sym fp32 block, column-direction pass over block A (no transposed copy)", {}, 0),
+                          ("sym fp32 block, same with 16 epilogue warps", {"FCMA_GEMM_EPI_WARPS": "16"}, 0),
+                          ("sym fp32 block, transposed copy B (TMA store) + row pass over it", {"FCMA_SYM_COLS": "0"}, 0),
+                          ("sym fp16 block, transposed copy B", {}, F16)):
         os.environ.update(env)
 
         def sym():

@@ -1744,23 +1744,28 @@ __global__ void __launch_bounds__(256, 1)
         const long j0 = c0 + strip * 32;                       // first block column of the strip
         const long tjx = j0 >> 8;
         const int jo = (int)(j0 & 255);
-        // issue the cp.async copies of row step `st` into brick `b`
+        // issue the cp.async copies of row step `st` into brick `b`.  Thread tid copies piece w = tid & 7 of the lines
+        // (tid >> 3) + 32 k, k < 16: row (tid >> 3) & 15 of epochs (tid >> 7) + 2 k -- one source offset and one
+        // destination offset per thread, the rest are compile-time strides (swz of those lines = c0 | ((k >> 1) & 1) << 2)
+        const int pf_w = tid & 7, pf_line0 = tid >> 3, pf_row = pf_line0 & 15, pf_e0 = tid >> 7;
+        const uint32_t pf_c = (uint32_t)((pf_line0 >> 1) & 3);
+        const int pf_src = pf_e0 * 65536 + pf_row * 256 + pf_w * 4 + jo;
+        const uint32_t pf_dst = brick0 + (uint32_t)pf_line0 * 128u;
         auto prefetch = [&](long st, int b) {
             const long i0 = st * 16;
-            const long ti = i0 >> 8;
-            const int io = (int)(i0 & 255);
-            const float *tile0 = A + ((size_t)(ti * T256 + tjx) * E) * 65536 + (size_t)io * 256 + jo;
+            const float *src0 = A + ((size_t)((i0 >> 8) * T256 + tjx) * E) * 65536 + (size_t)(i0 & 255) * 256 + pf_src;
+            const bool row_ok = i0 + pf_row < n;
+            const uint32_t dst0 = pf_dst + (uint32_t)b * 65536u;
 #pragma unroll
             for (int k = 0; k < 16; k++) {
-                const int p = tid + 256 * k;
-                const int w = p & 7, line = p >> 3;
-                const int e = line >> 4, row = line & 15;
-                const bool ok = e < E && i0 + row < n;
-                const float *src = ok ? tile0 + (size_t)e * 65536 + row * 256 + w * 4 : A;
-                const uint32_t swz = (uint32_t)((line >> 1) & 3) | ((uint32_t)((line >> 6) & 1) << 2);
-                cp_async_16_zfill(cs + (size_t)b * 65536 + ((size_t)line * 8 + ((uint32_t)w ^ swz)) * 16, src, ok ? 16u : 0u);
+                const bool ok = row_ok && pf_e0 + 2 * k < E;
+                const uint32_t piece = ((uint32_t)pf_w ^ pf_c ^ (uint32_t)(((k >> 1) & 1) << 2)) << 4;
+                cp_async_16_zfill_s(dst0 + (uint32_t)k * 4096u + piece, ok ? src0 + (size_t)k * 131072 : A, ok ? 16u : 0u);
             }
         };
+        // this lane's reads: piece `warp` of the lines (4g + r)*16 + row(sl, t); their swizzle is t | (g & 1) << 2 for
+        // every (r, sl), so one base address per thread and immediate offsets (r*16 + (sl & 1) + 8 (sl >> 1)) * 128
+        const uint32_t rd_base = (uint32_t)((R * g) * 16 + 2 * t) * 128u + ((((uint32_t)warp) ^ ((uint32_t)t | ((uint32_t)(g & 1) << 2))) << 4);
         for (long seg0 = 0; seg0 < nsteps; seg0 += COLS_SEG_STEPS) {
             const long seg1 = seg0 + COLS_SEG_STEPS < nsteps ? seg0 + COLS_SEG_STEPS : nsteps;
             float acc[4][MT][NT][4];
@@ -1784,15 +1789,12 @@ __global__ void __launch_bounds__(256, 1)
                 cp_async_commit();
                 // ---- this lane's 4 epochs x 4 rows x 4 columns
                 float vals[R][4][4];
-                const uint32_t bb = brick0 + (uint32_t)buf * 65536u;
+                const uint32_t bb = brick0 + (uint32_t)buf * 65536u + rd_base;
 #pragma unroll
                 for (int r = 0; r < R; r++)
 #pragma unroll
                     for (int sl = 0; sl < 4; sl++) {
-                        const int row = 2 * t + (sl & 1) + 8 * (sl >> 1);
-                        const int line = (R * g + r) * 16 + row;
-                        const uint32_t swz = (uint32_t)((line >> 1) & 3) | ((uint32_t)((line >> 6) & 1) << 2);
-                        const uint4 q = lds128(bb + ((uint32_t)line * 8u + ((uint32_t)warp ^ swz)) * 16u);
+                        const uint4 q = lds128(bb + (uint32_t)((r * 16 + (sl & 1) + 8 * (sl >> 1)) * 128));
                         vals[r][sl][0] = __uint_as_float(q.x), vals[r][sl][1] = __uint_as_float(q.y);
                         vals[r][sl][2] = __uint_as_float(q.z), vals[r][sl][3] = __uint_as_float(q.w);
                     }

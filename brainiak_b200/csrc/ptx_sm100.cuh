@@ -216,6 +216,11 @@ __device__ __forceinline__ void cp_async_16_zfill(void *smem_dst, const void *gs
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(src_bytes)
                  : "memory");
 }
+// same with a shared-state-space destination address
+__device__ __forceinline__ void cp_async_16_zfill_s(uint32_t smem_dst, const void *gsrc, uint32_t src_bytes)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gsrc), "r"(src_bytes) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit()
 {
     asm volatile("cp.async.commit_group;" ::: "memory");

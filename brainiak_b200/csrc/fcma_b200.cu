@@ -1725,11 +1725,16 @@ __global__ void __launch_bounds__(256, (R == 4 ? 2 : 1))
 #endif
 constexpr int COLS_SEG_STEPS = FCMA_COLS_SEG_STEPS;   // 16-row steps between folds of the accumulators into K
 constexpr int COLS_BRICKS = 3;        // 64 KB bricks in flight / in use (cp.async pipeline depth)
-template <int EPS>
-__global__ void __launch_bounds__(256, 1)
+// CPW = columns per warp: 4 (8 warps, 4 accumulator sets, 255 registers) or 2 (16 warps, 2 accumulator sets, <= 128
+// registers: twice the warps to hide the dependent statistics / shuffle chains between the block barriers)
+template <int EPS, int CPW>
+__global__ void __launch_bounds__(32 * (32 / CPW), 1)
     k_norm_syrk_cols(const float *__restrict__ A, long n, int E, long n2, long T256, long c0, float *K)
 {
     constexpr int R = 4, EP = 32, MT = 2, NT = 4;
+    constexpr int NTHR = 32 * (32 / CPW);      // threads per CTA
+    constexpr int PPT = 4096 / NTHR;           // 16-byte pieces a thread copies per brick
+    constexpr int LS = NTHR / 8;               // line stride between a thread's pieces
     extern __shared__ __align__(1024) uint8_t cs_raw[];
     uint8_t *cs = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(cs_raw) + 1023) & ~uintptr_t(1023));
     const uint32_t brick0 = smem_u32(cs);            // 3 bricks of 64 KB; the first two double as [32 columns][EP*EP] fp32 at folds
@@ -1747,7 +1752,7 @@ __global__ void __launch_bounds__(256, 1)
         // issue the cp.async copies of row step `st` into brick `b`.  Thread tid copies piece w = tid & 7 of the lines
         // (tid >> 3) + 32 k, k < 16: row (tid >> 3) & 15 of epochs (tid >> 7) + 2 k -- one source offset and one
         // destination offset per thread, the rest are compile-time strides (swz of those lines = c0 | ((k >> 1) & 1) << 2)
-        const int pf_w = tid & 7, pf_line0 = tid >> 3, pf_row = pf_line0 & 15, pf_e0 = tid >> 7;
+        const int pf_w = tid & 7, pf_line0 = tid >> 3, pf_row = pf_line0 & 15, pf_e0 = pf_line0 >> 4;
         const uint32_t pf_c = (uint32_t)((pf_line0 >> 1) & 3);
         const int pf_src = pf_e0 * 65536 + pf_row * 256 + pf_w * 4 + jo;
         const uint32_t pf_dst = brick0 + (uint32_t)pf_line0 * 128u;
@@ -1757,20 +1762,23 @@ __global__ void __launch_bounds__(256, 1)
             const bool row_ok = i0 + pf_row < n;
             const uint32_t dst0 = pf_dst + (uint32_t)b * 65536u;
 #pragma unroll
-            for (int k = 0; k < 16; k++) {
-                const bool ok = row_ok && pf_e0 + 2 * k < E;
-                const uint32_t piece = ((uint32_t)pf_w ^ pf_c ^ (uint32_t)(((k >> 1) & 1) << 2)) << 4;
-                cp_async_16_zfill_s(dst0 + (uint32_t)k * 4096u + piece, ok ? src0 + (size_t)k * 131072 : A, ok ? 16u : 0u);
+            for (int k = 0; k < PPT; k++) {
+                const bool ok = row_ok && pf_e0 + (LS / 16) * k < E;
+                const uint32_t piece = ((uint32_t)pf_w ^ pf_c ^ (uint32_t)((((k * LS) >> 6) & 1) << 2)) << 4;
+                cp_async_16_zfill_s(dst0 + (uint32_t)(k * LS) * 128u + piece, ok ? src0 + (size_t)k * ((LS / 16) * 65536) : A,
+                                    ok ? 16u : 0u);
             }
         };
         // this lane's reads: piece `warp` of the lines (4g + r)*16 + row(sl, t); their swizzle is t | (g & 1) << 2 for
         // every (r, sl), so one base address per thread and immediate offsets (r*16 + (sl & 1) + 8 (sl >> 1)) * 128
-        const uint32_t rd_base = (uint32_t)((R * g) * 16 + 2 * t) * 128u + ((((uint32_t)warp) ^ ((uint32_t)t | ((uint32_t)(g & 1) << 2))) << 4);
+        const uint32_t rd_base = (uint32_t)((R * g) * 16 + 2 * t) * 128u +
+                                 ((((uint32_t)(warp * CPW) >> 2) ^ ((uint32_t)t | ((uint32_t)(g & 1) << 2))) << 4) +
+                                 (uint32_t)((warp * CPW) & 3) * 4u;
         for (long seg0 = 0; seg0 < nsteps; seg0 += COLS_SEG_STEPS) {
             const long seg1 = seg0 + COLS_SEG_STEPS < nsteps ? seg0 + COLS_SEG_STEPS : nsteps;
-            float acc[4][MT][NT][4];
+            float acc[CPW][MT][NT][4];
 #pragma unroll
-            for (int c = 0; c < 4; c++)
+            for (int c = 0; c < CPW; c++)
 #pragma unroll
                 for (int a = 0; a < MT; a++)
 #pragma unroll
@@ -1788,15 +1796,20 @@ __global__ void __launch_bounds__(256, 1)
                 if (st + 2 < seg1) prefetch(st + 2, buf == 0 ? 2 : buf - 1);   // whose buffer takes brick st+2
                 cp_async_commit();
                 // ---- this lane's 4 epochs x 4 rows x 4 columns
-                float vals[R][4][4];
+                float vals[R][4][CPW];
                 const uint32_t bb = brick0 + (uint32_t)buf * 65536u + rd_base;
 #pragma unroll
                 for (int r = 0; r < R; r++)
 #pragma unroll
                     for (int sl = 0; sl < 4; sl++) {
-                        const uint4 q = lds128(bb + (uint32_t)((r * 16 + (sl & 1) + 8 * (sl >> 1)) * 128));
-                        vals[r][sl][0] = __uint_as_float(q.x), vals[r][sl][1] = __uint_as_float(q.y);
-                        vals[r][sl][2] = __uint_as_float(q.z), vals[r][sl][3] = __uint_as_float(q.w);
+                        if constexpr (CPW == 4) {
+                            const uint4 q = lds128(bb + (uint32_t)((r * 16 + (sl & 1) + 8 * (sl >> 1)) * 128));
+                            vals[r][sl][0] = __uint_as_float(q.x), vals[r][sl][1] = __uint_as_float(q.y);
+                            vals[r][sl][2] = __uint_as_float(q.z), vals[r][sl][3] = __uint_as_float(q.w);
+                        } else {
+                            const uint2 q = lds64(bb + (uint32_t)((r * 16 + (sl & 1) + 8 * (sl >> 1)) * 128));
+                            vals[r][sl][0] = __uint_as_float(q.x), vals[r][sl][1] = __uint_as_float(q.y);
+                        }
                     }
                 // ---- within-subject z-score per (row, column): statistics over the EPS epochs of a subject
                 auto finish = [&](float2 msum, float2 s2sum, float2 &inv, float2 &mi) {
@@ -1815,7 +1828,7 @@ __global__ void __launch_bounds__(256, 1)
 #pragma unroll
                         for (int sl = 0; sl < 4; sl++)
 #pragma unroll
-                            for (int u = 0; u < 4; u += 2) {
+                            for (int u = 0; u < CPW; u += 2) {
                                 float2 m = splat2(0.f), s2 = splat2(0.f);
 #pragma unroll
                                 for (int b = 0; b < EPS; b++) {
@@ -1840,7 +1853,7 @@ __global__ void __launch_bounds__(256, 1)
 #pragma unroll
                     for (int sl = 0; sl < 4; sl++)
 #pragma unroll
-                        for (int u = 0; u < 4; u += 2) {
+                        for (int u = 0; u < CPW; u += 2) {
                             float2 m = splat2(0.f), s2 = splat2(0.f);
 #pragma unroll
                             for (int r = 0; r < R; r++) {
@@ -1868,7 +1881,7 @@ __global__ void __launch_bounds__(256, 1)
                 }
                 // ---- K_j += Z Z^T: k-slots (2t, 2t+1) <-> row slots 0, 1 and (2t+8, 2t+9) <-> row slots 2, 3
 #pragma unroll
-                for (int c = 0; c < 4; c++) {
+                for (int c = 0; c < CPW; c++) {
                     uint32_t h0[R], h1[R];
 #pragma unroll
                     for (int r = 0; r < R; r++) {
@@ -1887,8 +1900,8 @@ __global__ void __launch_bounds__(256, 1)
             cp_async_wait<0>();
             __syncthreads();
 #pragma unroll
-            for (int c = 0; c < 4; c++) {
-                float *dstk = s_fold + (size_t)(warp * 4 + c) * (EP * EP);
+            for (int c = 0; c < CPW; c++) {
+                float *dstk = s_fold + (size_t)(warp * CPW + c) * (EP * EP);
 #pragma unroll
                 for (int mu = 0; mu < MT; mu++)
 #pragma unroll
@@ -1916,16 +1929,16 @@ __global__ void __launch_bounds__(256, 1)
                 // 16-byte read-modify-write, 8 independent loads in flight per thread (the loop is latency-bound)
                 float4 *K4 = reinterpret_cast<float4 *>(Kst);
                 const int total4 = total >> 2;
-                for (int base = tid; base < total4; base += 256 * 8) {
+                for (int base = tid; base < total4; base += NTHR * 8) {
                     float4 old[8];
 #pragma unroll
                     for (int u = 0; u < 8; u++) {
-                        const int i4 = base + u * 256;
+                        const int i4 = base + u * NTHR;
                         if (i4 < total4) old[u] = K4[i4];
                     }
 #pragma unroll
                     for (int u = 0; u < 8; u++) {
-                        const int i4 = base + u * 256;
+                        const int i4 = base + u * NTHR;
                         if (i4 < total4) {
                             float4 o = old[u];
                             o.x += folded(4 * i4), o.y += folded(4 * i4 + 1), o.z += folded(4 * i4 + 2), o.w += folded(4 * i4 + 3);
@@ -1934,16 +1947,16 @@ __global__ void __launch_bounds__(256, 1)
                     }
                 }
             } else {
-                for (int base = tid; base < total; base += 256 * 8) {
+                for (int base = tid; base < total; base += NTHR * 8) {
                     float old[8];
 #pragma unroll
                     for (int u = 0; u < 8; u++) {
-                        const int i1 = base + u * 256;
+                        const int i1 = base + u * NTHR;
                         if (i1 < total) old[u] = Kst[i1];
                     }
 #pragma unroll
                     for (int u = 0; u < 8; u++) {
-                        const int i1 = base + u * 256;
+                        const int i1 = base + u * NTHR;
                         if (i1 < total) Kst[i1] = old[u] + folded(i1);
                     }
                 }
@@ -2060,10 +2073,19 @@ static int launch_norm_syrk_cols(const float *A, long n, int E, long n2, long T2
     const long nstrips = cdiv(n2 - c0, 32);
     const unsigned grid = (unsigned)(nstrips < g_sm_count ? nstrips : g_sm_count);
     const size_t smem = (size_t)COLS_BRICKS * 65536 + 1024;
+    // 4 columns per warp (8 warps, 255 registers) by default; FCMA_COLS_CPW=2 selects 2 columns per warp (16 warps at 128
+    // registers: measured 7 % slower -- 80 bytes of spills and two-way conflicts on the 8-byte LDS outweigh the occupancy)
+    const char *cpw_env = getenv("FCMA_COLS_CPW");
+    const bool cpw4 = !(cpw_env && cpw_env[0] == '2');
 #define FCMA_COLS_CASE(EPSV)                                                                                        \
     case EPSV:                                                                                                      \
-        CUDA_TRY(cudaFuncSetAttribute(k_norm_syrk_cols<EPSV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        k_norm_syrk_cols<EPSV><<<grid, 256, smem, st>>>(A, n, E, n2, T256, c0, K);                                 \
+        if (cpw4) {                                                                                                 \
+            CUDA_TRY(cudaFuncSetAttribute(k_norm_syrk_cols<EPSV, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            k_norm_syrk_cols<EPSV, 4><<<grid, 256, smem, st>>>(A, n, E, n2, T256, c0, K);                          \
+        } else {                                                                                                    \
+            CUDA_TRY(cudaFuncSetAttribute(k_norm_syrk_cols<EPSV, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            k_norm_syrk_cols<EPSV, 2><<<grid, 512, smem, st>>>(A, n, E, n2, T256, c0, K);                          \
+        }                                                                                                           \
         break;
     switch (eps) {
         FCMA_COLS_CASE(1)

@@ -287,6 +287,12 @@ __device__ __forceinline__ void tma_store_wait_all()
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
+__device__ __forceinline__ uint2 lds64(uint32_t saddr)
+{
+    uint2 r;
+    asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(saddr) : "memory");
+    return r;
+}
 // fp16 operands (same 11-bit significand as tf32), twice the k extent per instruction
 __device__ __forceinline__ void mma_f16_16x8x16(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
                                                 uint32_t b0, uint32_t b1)

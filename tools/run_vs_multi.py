@@ -35,6 +35,22 @@ if rank == 0:
     print("world", world, "run %.3f s" % dt, "top voxels planted:", sum(1 for v, _ in res[:30] if v < 30), "/ 30", flush=True)
 else:
     assert res == []
+# the kernels themselves: every rank contracts its shard, the partial [V, E, E] arrays are summed (NCCL), and rank 0
+# compares them with the single-GPU symmetric and plain pipelines
+from brainiak_b200.fcma import engine
+op = engine.pack_epochs(ep, None, "fp32")
+s0, n0 = engine.sym_row_partition(V, world)[rank]
+Kp = torch.zeros((V, E, E), device="cuda")
+if n0 > 0:
+    engine.voxel_kernels_sym(op, s0, n0, eps, out=Kp)
+dist.all_reduce(Kp)
+if rank == 0:
+    K1 = engine.voxel_kernels_sym(op, 0, V, eps)
+    K0 = engine.voxel_kernels(op, op, 0, V, eps)
+    sc = float(K0.abs().max())
+    d_multi, d_plain = float((Kp - K1).abs().max()) / sc, float((Kp - K0).abs().max()) / sc
+    print("kernels: max|K_multi - K_single|/max|K| = %.3g, max|K_multi - K_plain|/max|K| = %.3g" % (d_multi, d_plain), flush=True)
+    assert d_multi <= 1e-5 and d_plain <= 1e-5
 dist.barrier()
 # single-process reference on rank 0 (no process group semantics: temporarily pretend world == 1)
 if rank == 0:

@@ -651,8 +651,15 @@ __device__ __forceinline__ void gemm_epilogue_tile(const Gemm2Params &p, uint64_
             // columns >= V2 fall into the tile padding the caller allocated
             float *ptr = p.out + (((size_t)(ti * p.tiles_j + tj) * p.E + e) * 256 + c * 32) * 256 +
                          ((int)rank * 128 + q * 32 + lane);
+            if (p.debug & 32) {   // A/B: plain stores instead of streaming (evict-first) ones
 #pragma unroll
-            for (int r = 0; r < 32; r++) ptr[r * 256] = __uint_as_float(v[r]);
+                for (int r = 0; r < 32; r++) ptr[r * 256] = __uint_as_float(v[r]);
+            } else {
+                // the block is far larger than L2 and is read back only by the next kernel: streaming stores keep the
+                // operand tiles (re-read by every tile of a column group) in L2
+#pragma unroll
+                for (int r = 0; r < 32; r++) __stcs(ptr + r * 256, __uint_as_float(v[r]));
+            }
             if (mirror) {
                 // transposed copy (see store_transposed_f32)
                 const uint32_t tb = tr_buf + (uint32_t)(warp - 4) * p.tr_warp_bytes;

@@ -307,6 +307,38 @@ def test_symmetric_pipeline_vs_oracle_and_plain(dev, case):
         engine.voxel_kernels_sym(op, 0, V, eps, work=tiny, out=K)
 
 
+@pytest.mark.parametrize("E,eps", [(5, 1), (7, 2), (10, 2), (12, 4), (16, 16), (32, 32), (24, 8), (9, 4)])
+def test_symmetric_column_pass_all_eps(dev, E, eps):
+    """Every instantiation of the column-direction pass (eps = 1 .. 32), epoch counts that are not multiples of 4
+    (scalar K folds), trailing epochs outside a complete subject (left un-normalised, fcma_extension.cc:52) and a
+    block that needs several folds of the accumulators: symmetric == plain pipeline, and against the oracle."""
+    V, T = 1300, 24
+    raw, _ = synthetic.make_epochs(V, T, E, seed=1000 + 37 * E + eps)
+    ep, T_e = engine.stack_epochs(raw, dev)
+    op = engine.pack_epochs(ep, T_e, "fp32")
+    assert _lib.load().fcma_sym_uses_column_pass(_lib.PREC[op.precision], E, eps, 0) == 1
+    fl = _lib.FLAG_MASK_SELF
+    plain = engine.voxel_kernels(op, op, 0, V, eps, flags=fl)
+    K = torch.zeros((V, E, E), device=dev)
+    work = engine.SymWorkspace(E, V, 256, dev)
+    work.buf.view(torch.float32).fill_(float("nan"))
+    engine.voxel_kernels_sym(op, 0, V, eps, flags=fl, work=work, out=K)      # 6 passes of <= 256 rows
+    # scale floor V: with eps = 1 every z-score is 0 in exact arithmetic (the kernels hold rounding residue ~1e-5 * V)
+    scale = max(float(plain.abs().max()), float(V))
+    assert torch.isfinite(K).all()
+    assert float((K - K.transpose(1, 2)).abs().max()) == 0.0
+    # eps = 2: the z-score of two values is sign(x1 - x2) -- a step function, so the rare pair of near-equal Fisher
+    # values flips with the last bit of r (the plain pipeline adds the three split products of r(j, i) in another order
+    # than those of r(i, j)); a flipped pair moves one K entry by 2 of ~V
+    loose = eps <= 2
+    assert float((K - plain).abs().max()) <= (2e-3 if loose else 1e-5) * scale
+    for s0 in (0, 700, V - 30):
+        _, z, _ = orc.voxel_block(raw, None, s0, 30, eps, shrink=False)
+        Kref = orc.kernel_matrices(zero_self(z, s0), f64=True)
+        tol = (1e-2 if loose else k_tol(V)) * max(np.max(np.abs(Kref)), float(V))   # measured 4.5e-3 for eps = 2
+        assert np.max(np.abs(K[s0:s0 + 30].cpu().numpy() - Kref)) <= tol
+
+
 def test_pipeline_vs_reference_golden_kernels(dev, golden):
     g = golden("vs_mid")
     d1, d2 = list(g["d1"]), list(g["d2"])

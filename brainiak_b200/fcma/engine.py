@@ -297,11 +297,22 @@ def voxel_kernels_sym(op, start, nb, eps, flags=0, work=None, out=None):
     return out
 
 
-def classifier_kernel(rows, cols, start, nb, eps, flags=0, work=None, out=None):
-    """a9 -> a10 -> a11: accumulates sum_i Z_i Z_i^T over rows [start, start+nb) into ``out`` [E, E]."""
+def classifier_kernel(rows, cols, start, nb, eps, flags=0, work=None, out=None, symmetric=True):
+    """a9 -> a10 -> a11: accumulates sum_i Z_i Z_i^T over rows [start, start+nb) into ``out`` [E, E].
+
+    One mask, all rows at once and a fused-path eps: the sum over voxels of the symmetric pipeline's kernels
+    (z(i, :, j) == z(j, :, i), so only the blocks on/above the diagonal are contracted)."""
     lib = _lib.load()
     _check_pair(rows, cols)
     E, V2 = rows.E, cols.V
+    if (symmetric and rows is cols and start == 0 and nb == rows.V and eps > 1 and rows.V >= 512
+            and sym_supported(E, eps) and not (flags & _lib.FLAG_FISHER_IN_PASS2)):
+        if out is None:
+            out = torch.zeros((E, E), dtype=torch.float32, device=rows.device)
+        w = work if isinstance(work, SymWorkspace) and work.buf.numel() >= 2 * 256 * lib.fcma_work_bytes_per_row(E, V2) else None
+        Kfull = voxel_kernels_sym(rows, 0, nb, eps, flags=flags, work=w)
+        out += Kfull.sum(0)
+        return out
     if work is None:
         work = Workspace(E, V2, Workspace.rows_for(E, V2, nb, rows.device), rows.device)
     if out is None:

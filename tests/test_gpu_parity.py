@@ -735,6 +735,27 @@ def test_voxel_selector_gpu_cv_equals_host_cv(dev, golden):
     assert a == b
 
 
+def test_classifier_kernel_single_mask_uses_symmetry(dev):
+    """One mask, all voxels in one call: engine.classifier_kernel sums the symmetric pipeline's voxel kernels; same
+    [E, E] matrix as the plain accumulation (classifier.py:334-339) and as the oracle."""
+    V, T, E, eps = 900, 30, 16, 4
+    raw, _ = synthetic.make_epochs(V, T, E, seed=515)
+    ep, T_e = engine.stack_epochs(raw, dev)
+    op = engine.pack_epochs(ep, T_e, "fp32")
+    Ks = engine.classifier_kernel(op, op, 0, V, eps).cpu().numpy()
+    Kp = engine.classifier_kernel(op, op, 0, V, eps, symmetric=False).cpu().numpy()
+    assert np.max(np.abs(Ks - Kp)) <= 2e-5 * np.max(np.abs(Kp))
+    # accumulates into `out` like the plain path (beta = 1)
+    out = torch.ones((E, E), device=dev)
+    engine.classifier_kernel(op, op, 0, V, eps, out=out)
+    assert np.max(np.abs(out.cpu().numpy() - 1 - Ks)) <= 1e-6 * np.max(np.abs(Ks))
+    # row portions (start > 0) keep the plain path
+    K2 = torch.zeros((E, E), device=dev)
+    engine.classifier_kernel(op, op, 0, 400, eps, out=K2)
+    engine.classifier_kernel(op, op, 400, 500, eps, out=K2)
+    assert np.max(np.abs(K2.cpu().numpy() - Kp)) <= 2e-5 * np.max(np.abs(Kp))
+
+
 def test_voxel_selector_symmetric_equals_plain(dev):
     """Public API: one mask -> the symmetric pipeline by default; same (voxel, accuracy) list as the plain
     pipeline (the kernels differ only in the order of fp32 partial sums), host and GPU cross-validation."""

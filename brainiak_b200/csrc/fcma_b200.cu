@@ -446,6 +446,8 @@ struct Gemm2Params {
                                    // 8, 16 or 32: voxel rows i per LDS/STG transposition step (buffer = 32 x (tr_w + pad))
     uint32_t tr_warp_bytes;        // bytes of one warp's transposition buffer
     uint32_t bar_off;              // smem offset of the mbarriers
+    int tma_norm;                  // 1 (opt-in, A/B): the normal copy of a chunk also leaves through the staging buffer + a TMA
+                                   // bulk store (symmetric mode with tr_w == 0)
 };
 
 // Transposed copy of one 32 (column voxels j = lanes) x 32 (row voxels i = registers) accumulator chunk: W values per
@@ -651,7 +653,23 @@ __device__ __forceinline__ void gemm_epilogue_tile(const Gemm2Params &p, uint64_
             // columns >= V2 fall into the tile padding the caller allocated
             float *ptr = p.out + (((size_t)(ti * p.tiles_j + tj) * p.E + e) * 256 + c * 32) * 256 +
                          ((int)rank * 128 + q * 32 + lane);
-            if (p.debug & 32) {   // A/B: plain stores instead of streaming (evict-first) ones
+            if (p.tma_norm) {
+                // normal copy through the staging buffer: row r of the 32 x 32 box = voxel row c*32 + r, 128 bytes = this
+                // warp's 32 columns; lane j writes word j of every row (conflict-free) in the 128-byte TMA swizzle
+                const uint32_t tb = tr_buf + (uint32_t)(warp - 4) * p.tr_warp_bytes;
+                if (lane == 0) tma_store_wait_read0();
+                __syncwarp();
+                const uint32_t wlane = tb + ((uint32_t)lane & 3u) * 4u;
+                const uint32_t cl = (uint32_t)lane >> 2;
+#pragma unroll
+                for (int r = 0; r < 32; r++) sts32(wlane + (uint32_t)r * 128u + ((cl ^ (uint32_t)(r & 7)) << 4), v[r]);
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store_2d(tm_tA, tb, (int)rank * 128 + q * 32, (((ti * p.tiles_j + tj) * p.E + e) << 8) + c * 32);
+                    tma_store_commit();
+                }
+            } else if (p.debug & 32) {   // A/B: plain stores instead of streaming (evict-first) ones
 #pragma unroll
                 for (int r = 0; r < 32; r++) ptr[r * 256] = __uint_as_float(v[r]);
             } else {
@@ -1026,6 +1044,10 @@ static int launch_corr_umma(const void *rows_op, const void *cols_op, int precis
         if (tw && (atoi(tw) == 32 || atoi(tw) == 16 || (atoi(tw) == 8 && !half_out))) q.tr_w = atoi(tw);
         q.tr_warp_bytes = q.tr_w == 0 ? (half_out ? 2048u : 4096u)
                                       : (half_out ? 32u * (2u * q.tr_w + 16u) : 32u * (q.tr_w + 4u) * 4u);
+        // FCMA_GEMM_TMA_NORM=1: also the normal copy through the staging buffer + TMA bulk stores (A/B; measured neutral
+        // inside the power-capped step: 58.8-59.7 vs 60.3 ms of GEMM per step, so the plain streaming stores stay)
+        const char *tn = getenv("FCMA_GEMM_TMA_NORM");
+        q.tma_norm = (q.tr_w == 0 && !half_out && tn && tn[0] == '1') ? 1 : 0;
     }
     const size_t tr_bytes = !sym ? 0 : (size_t)q.epi_warps * q.tr_warp_bytes;
     const size_t cap = 227 * 1024 - 1024 /*alignment slack*/ - 256 /*barriers*/ - tr_bytes;

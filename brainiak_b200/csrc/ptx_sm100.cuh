@@ -254,6 +254,10 @@ __device__ __forceinline__ void sts128(uint32_t saddr, uint32_t a, uint32_t b, u
 {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
+__device__ __forceinline__ void sts32(uint32_t saddr, uint32_t a)
+{
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(saddr), "r"(a) : "memory");
+}
 __device__ __forceinline__ uint4 lds128(uint32_t saddr)
 {
     uint4 r;

@@ -88,10 +88,10 @@ def big():
     work = engine.SymWorkspace(E, V, 4096, dev)
     Ks = torch.empty((V, E, E), device=dev)
     F16 = _lib.FLAG_F16_INTERMEDIATE
-    for name, env, fl in (("sym fp32 block, column pass, streaming stores in the GEMM epilogue", {}, 0),
-                          ("sym fp32 block, column pass, plain stores", {"FCMA_GEMM_DEBUG": "32"}, 0),
-                          ("sym fp32 block, column pass, streaming stores (again)", {}, 0),
-                          ("sym fp32 block, column pass, plain stores (again)", {"FCMA_GEMM_DEBUG": "32"}, 0)):
+    for name, env, fl in (("sym fp32 block, column-direction pass over block A", {}, 0),
+                          ("sym fp32 block, column pass, normal copy through TMA bulk stores too", {"FCMA_GEMM_TMA_NORM": "1"}, 0),
+                          ("sym fp32 block, transposed copy B (TMA store) + row pass over it", {"FCMA_SYM_COLS": "0"}, 0),
+                          ("sym fp16 block, transposed copy B", {}, F16)):
         os.environ.update(env)
 
         def sym():

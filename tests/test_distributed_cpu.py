@@ -64,3 +64,56 @@ def test_run_world_size_2_gloo(monkeypatch):
     for (v0, a0), (v1, a1) in zip(res, res[1:]):
         if a0 == a1:
             assert v0 < v1
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Symmetric single-mask pipeline over several ranks: every rank contracts rows [s, s+n) with the
+# columns [s, V) only, adds every block to its row voxels AND (transposed) to its column voxels, and the ranks' partial
+# [V, E, E] arrays are summed with one all-reduce.  Here the device stage is the oracle's normalised correlation block, so
+# the decomposition (engine.sym_row_partition, the pass structure, exactly-once coverage) and the collective run on CPU.
+def _sym_partial(z, s, n, rows_per_pass):
+    """What fcma_voxel_kernels_sym(start=s, nb=n) accumulates: z = [V, E, V] normalised correlations (symmetric in
+    its first and last axis)."""
+    V, E, _ = z.shape
+    K = np.zeros((V, E, E), np.float64)
+    for a in range(s, s + n, rows_per_pass):
+        nn = min(rows_per_pass, s + n - a)
+        blk = z[a:a + nn, :, a:]                                    # block A: rows of the pass x columns [a, V)
+        K[a:a + nn] += np.einsum("iej,ifj->ief", blk, blk)          # row pass
+        right = blk[:, :, nn:]                                      # columns right of the diagonal part
+        K[a + nn:] += np.einsum("iej,ifj->jef", right, right)       # column pass: z(j, :, i) == z(i, :, j)
+    return K
+
+
+def _sym_worker(rank, world, port, V, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import fcma_oracle as orc
+        from brainiak_b200.fcma import engine
+        raw, _ = synthetic.make_epochs(V, 12, 8, seed=5)
+        _, z, _ = orc.voxel_block(raw, None, 0, V, 4, shrink=False)     # [V, E, V]
+        z = z.astype(np.float64)
+        for i in range(V):
+            z[i, :, i] = 0                                              # mask_self: the one non-symmetric column
+        s, n = engine.sym_row_partition(V, world, align=4)[rank]
+        part = torch.from_numpy(_sym_partial(z, s, n, rows_per_pass=8) if n > 0 else np.zeros((V, 8, 8)))
+        dist.all_reduce(part)                                           # the path's one exchange step
+        if rank == 0:
+            out["K"] = part.numpy()
+            out["full"] = np.einsum("iej,ifj->ief", z, z)
+            out["sym_err"] = float(np.max(np.abs(z - np.transpose(z, (2, 1, 0)))))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("world", [2, 3])
+def test_symmetric_decomposition_world_size_n_gloo(world):
+    V = 45
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_sym_worker, args=(world, _free_port(), V, out), nprocs=world, join=True)
+    assert out["sym_err"] <= 2e-6                  # the oracle's normalised correlations are symmetric (fp32 rounding)
+    scale = np.max(np.abs(out["full"]))
+    assert np.max(np.abs(out["K"] - out["full"])) <= 1e-5 * scale

@@ -252,8 +252,25 @@ def gen_preproc(m):
           (activity[0].shape[0], len(raw), len(raw2)))
 
 
+def gen_vs_sym(m):
+    """One mask, more than two 256-row tiles: pins the symmetric pipeline (blocks on/above the diagonal, row pass +
+    column pass) against the unmodified reference's kernels and accuracies for EVERY voxel."""
+    V, T, E, eps = 560, 20, 8, 4
+    raw, labels = synthetic.make_epochs(V, T, E, informative=10, signal=1.0, seed=20260921)
+    vs = m.VoxelSelector(labels, eps, 2, raw, voxel_unit=40, process_num=0)
+    acc = accs(reference.run_voxel_selection(vs, svc()), V)
+    _, _, k = stages_all(vs, V, 40)
+    np.savez_compressed(os.path.join(OUT, "vs_sym.npz"), raw=np.stack(raw), labels=np.array(labels), eps=eps,
+                        folds=2, acc=acc, kernels=k)
+    print("vs_sym: top voxels", np.argsort(-acc, kind="stable")[:10], "acc", np.sort(acc)[-10:])
+
+
 def main():
     m = reference.load()
+    if len(sys.argv) > 1 and sys.argv[1] == "vs_sym":      # add this fixture without regenerating the others
+        gen_vs_sym(m)
+        return
+    gen_vs_sym(m)
     gen_vs_small(m)
     gen_vs_mid(m)
     gen_clf(m)

@@ -735,6 +735,34 @@ def test_voxel_selector_gpu_cv_equals_host_cv(dev, golden):
     assert a == b
 
 
+def test_symmetric_pipeline_vs_reference_golden(dev, golden):
+    """vs_sym fixture: the UNMODIFIED reference's shrunk kernels and cross-validation accuracies of all 560 voxels of
+    a one-mask run.  The symmetric pipeline takes three passes here (256 + 256 + 48 rows: diagonal mirroring, row pass,
+    column pass, ragged tail); VoxelSelector.run picks it by default (V >= 512)."""
+    g = golden("vs_sym")
+    raw, eps, folds = list(g["raw"]), int(g["eps"]), int(g["folds"])
+    labels = [int(x) for x in g["labels"]]
+    V, E = raw[0].shape[1], len(raw)
+    ep, T_e = engine.stack_epochs(raw, dev)
+    ref = g["kernels"]
+    for prec in ("fp32", "tf32x3"):
+        op = engine.pack_epochs(ep, T_e, prec)
+        K = torch.zeros((V, E, E), device=dev)
+        engine.voxel_kernels_sym(op, 0, V, eps, work=engine.SymWorkspace(E, V, 256, dev), out=K)
+        K = K.cpu().numpy()
+        shrink_kernels_(K)
+        assert np.max(np.abs(K - ref)) <= k_tol(V) * np.max(np.abs(ref))
+    clf = svm.SVC(kernel="precomputed", shrinking=False, C=1)
+    vs = VoxelSelector(labels, eps, folds, raw, process_num=0, block_rows=256)
+    assert vs._symmetric_ok()
+    res = vs.run(clf)
+    acc = np.zeros(V)
+    for v, a in res:
+        acc[v] = a
+    assert np.mean(acc == g["acc"]) >= 0.97             # one test sample of 8 may move on a chance-level voxel
+    assert np.max(np.abs(acc - g["acc"])) <= 1.0 / 8 + 1e-9
+
+
 def test_classifier_kernel_single_mask_uses_symmetry(dev):
     """One mask, all voxels in one call: engine.classifier_kernel sums the symmetric pipeline's voxel kernels; same
     [E, E] matrix as the plain accumulation (classifier.py:334-339) and as the oracle."""

@@ -131,3 +131,21 @@ def test_epoch_normalize_vs_reference_golden_file(golden):
                                        atol=2e-6)
                     k += 1
     assert k == 12
+
+
+def test_oracle_vs_reference_golden_one_mask_all_voxels(golden):
+    """vs_sym fixture (unmodified reference, one mask, V = 560 > two 256-row tiles): the oracle reproduces the
+    reference's shrunk kernels of every voxel; the normalised correlations are symmetric in (i, j) up to fp32
+    rounding away from the self column -- the property the symmetric CUDA pipeline rests on."""
+    g = golden("vs_sym")
+    raw, eps = list(g["raw"]), int(g["eps"])
+    V = raw[0].shape[1]
+    for s0, nb in ((0, 64), (250, 70), (V - 40, 40)):
+        _, z, K = orc.voxel_block(raw, None, s0, nb, eps, shrink=True)
+        ref = g["kernels"][s0:s0 + nb]
+        assert np.max(np.abs(K - ref)) <= 2e-6 * np.max(np.abs(ref))
+    _, zA, _ = orc.voxel_block(raw, None, 0, 48, eps, shrink=False)          # rows 0..47
+    _, zB, _ = orc.voxel_block(raw, None, 300, 48, eps, shrink=False)        # rows 300..347
+    a = zA[:, :, 300:348]                                                    # z(i, :, j), i < 48, j in 300..347
+    b = np.transpose(zB[:, :, 0:48], (2, 1, 0))                              # z(j, :, i) rearranged to [i, e, j]
+    assert np.max(np.abs(a - b)) <= 5e-6

@@ -222,7 +222,9 @@ def run_b200_arm(args):
     bcast = torch.empty_like(epochs) if world > 1 else None   # receive buffer used inside the step
     # symmetric pipeline: scratch for a block and its transposed copy; K is the full [V, E, E] array every rank
     # accumulates its partial sums into (summed onto rank 0 with one NCCL reduce)
-    work = engine.SymWorkspace(E, V, block, dev, start=start) if sym else engine.Workspace(E, V, block, dev)
+    cols_variant = bool(sym and lib.fcma_sym_uses_column_pass(_lib.PREC[prec], E, eps, flags))
+    work = engine.SymWorkspace(E, V, block, dev, start=start, transposed_copy=not cols_variant) if sym \
+        else engine.Workspace(E, V, block, dev)
     K = torch.empty((V if sym else max(n, 1), E, E), dtype=torch.float32, device=dev)
     per = VoxelSelector.row_partition(V, world)[0][1]
     Kall = torch.empty((world * per, E, E), dtype=torch.float32, device=dev) if (world > 1 and rank == 0 and not sym) else None
@@ -379,7 +381,7 @@ def run_b200_arm(args):
         pass2_elems = 0.0        # correlations read by the normalise+SYRK launches of one step
         rows_elems = 0.0         # ... of which by the row pass over the block itself
         if sym:
-            rpp = work.rows
+            rpp = int(lib.fcma_sym_rows_per_pass(_lib.PREC[prec], E, eps, flags, V, start, work.buf.numel()))
             for a in range(start, start + n, rpp):
                 nn = min(rpp, start + n - a)
                 colsA, rowsB = V - a, V - a - nn
@@ -450,7 +452,7 @@ def run_b200_arm(args):
         traffic = None
         try:
             tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-            tag = ("symcols:rows%d" if cols_pass else "sym:rows%d") % work.rows if sym else "nb%d" % block
+            tag = ("symcols:rows%d" if cols_pass else "sym:rows%d") % min(rpp, 4096) if sym else "nb%d" % block
             traffic = tr.get("%s:%s:%s" % (dominant.split(" ")[0], prec, tag))
             if isinstance(traffic, dict):
                 # symmetric pipeline: launches differ in size; the ncu capture is the first (largest) launch, so the
@@ -463,7 +465,7 @@ def run_b200_arm(args):
                     "frac": ach / hbm_peak, "traffic": traffic,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
                     "launch_ms": kernels[dominant]["ms"],
-                    "launches_per_step": int(nl), "rows_per_launch": work.rows if sym else block,
+                    "launches_per_step": int(nl), "rows_per_launch": rpp if sym else block,
                     "pipeline": ("symmetric (blocks on/above the diagonal stored once, read row-wise and column-wise)" if cols_pass
                                  else "symmetric (blocks on/above the diagonal, each stored twice)" if sym else "plain"),
                     "algorithmic_bytes_per_launch": kernels[dominant]["algorithmic_bytes"],

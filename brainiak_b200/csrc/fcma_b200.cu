@@ -2440,8 +2440,8 @@ static int run_pipeline_sym(const void *op, int precision, int E, int T, long V,
     // column-direction pass (fp32 block, E <= 32): the column voxels' sums are taken from block A itself, no transposed
     // copy is stored.  FCMA_SYM_COLS=0 keeps the transposed block B (A/B).
     const bool use_cols = sym_uses_cols(precision, E, eps, flags);
-    // per block row: A needs E * round_up(V - a, 256) floats, B at most the same again
-    const size_t row_bytes = 2 * fcma_work_bytes_per_row(E, V - start);
+    // per block row: A needs E * round_up(V - a, 256) floats; with a transposed block B at most the same again
+    const size_t row_bytes = (use_cols ? 1 : 2) * fcma_work_bytes_per_row(E, V - start);
     long rows_per_pass = (long)(work_bytes / row_bytes) & ~255L;
     if (rows_per_pass < 256)
         return fail(FCMA_ENOMEM, "work buffer too small for the symmetric pipeline: %zu bytes < %zu (256 rows)", work_bytes, 256 * row_bytes);
@@ -2452,7 +2452,7 @@ static int run_pipeline_sym(const void *op, int precision, int E, int T, long V,
         const long rowsB = V - a - n;
         float *A = work;
         float *B = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(work) + (size_t)nt * t256 * E * 65536 * esz);
-        if ((size_t)((nt * t256 + (t256 - nt) * nt) * E) * 65536 * esz > work_bytes)
+        if ((size_t)((nt * t256 + (use_cols ? 0 : (t256 - nt) * nt)) * E) * 65536 * esz > work_bytes)
             return fail(FCMA_ENOMEM, "internal: symmetric pass does not fit the work buffer");
         cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
         if (g_timing_on) {
@@ -2487,6 +2487,12 @@ static int run_pipeline_sym(const void *op, int precision, int E, int T, long V,
         }
     }
     return FCMA_OK;
+}
+
+extern "C" long fcma_sym_rows_per_pass(int precision, int E, int eps, int flags, long V, long start, size_t work_bytes)
+{
+    const size_t row_bytes = (sym_uses_cols(precision, E, eps, flags) ? 1 : 2) * fcma_work_bytes_per_row(E, V - start);
+    return row_bytes ? (long)(work_bytes / row_bytes) & ~255L : 0;
 }
 
 extern "C" int fcma_voxel_kernels_sym(const void *op, int precision, int E, int T, long V, long start, long nb, int eps,

@@ -268,13 +268,22 @@ def sym_supported(E, eps, nb=None, start=0, V=None):
 
 
 class SymWorkspace(Workspace):
-    """Scratch of the symmetric pipeline: per block row the block itself and its transposed copy."""
+    """Scratch of the symmetric pipeline sized for `rows` block rows WITH a transposed copy (fp16 block, E > 32);
+    the column-pass variant (fp32 block, E <= 32) keeps only the block and takes twice as many rows per pass from the
+    same buffer (fcma_sym_rows_per_pass)."""
 
-    def __init__(self, E, V, rows, device, start=0):
+    def __init__(self, E, V, rows, device, start=0, transposed_copy=True):
         lib = _lib.load()
-        self.per_row = 2 * lib.fcma_work_bytes_per_row(E, V - start)
+        self.per_row = (2 if transposed_copy else 1) * lib.fcma_work_bytes_per_row(E, V - start)
         self.rows = max(256, (int(rows) + 255) // 256 * 256)
         self.buf = torch.empty(self.per_row * self.rows, dtype=torch.uint8, device=device)
+
+    @classmethod
+    def for_operand(cls, op, rows, eps, flags=0, start=0):
+        """Scratch for exactly `rows` block rows per pass of fcma_voxel_kernels_sym on this operand: the block alone
+        when the column pass applies (fp32 block, E <= 32), block + transposed copy otherwise."""
+        cols = bool(_lib.load().fcma_sym_uses_column_pass(_prec_code(op.precision), op.E, int(eps), int(flags)))
+        return cls(op.E, op.V, rows, op.device, start=start, transposed_copy=not cols)
 
 
 def voxel_kernels_sym(op, start, nb, eps, flags=0, work=None, out=None):
@@ -286,8 +295,8 @@ def voxel_kernels_sym(op, start, nb, eps, flags=0, work=None, out=None):
     if work is None:
         free, _ = torch.cuda.mem_get_info(op.device)
         per_row = 2 * lib.fcma_work_bytes_per_row(E, V - start)
-        rows = max(256, min((nb + 255) // 256 * 256, (min(free // 2, 64 << 30) // per_row) // 256 * 256))
-        work = SymWorkspace(E, V, rows, op.device, start)
+        rows = max(256, min((nb + 255) // 256 * 256, (min(free // 2, 64 << 30) // per_row) // 256 * 256, 4096))
+        work = SymWorkspace.for_operand(op, rows, eps, flags, start)
     if out is None:
         out = torch.zeros((V, E, E), dtype=torch.float32, device=op.device)
     with torch.cuda.device(op.device):

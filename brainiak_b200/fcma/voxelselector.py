@@ -290,11 +290,13 @@ class VoxelSelector:
                 free, _ = torch.cuda.mem_get_info(op.device)
                 per_row = 2 * _lib.load().fcma_work_bytes_per_row(E, V - s0)
                 rows = min(free // 2, 64 << 30) // per_row
-            rows = max(256, min((n0 + 255) // 256 * 256, rows // 256 * 256))
-            if not isinstance(self._work, engine.SymWorkspace) or \
-                    self._work.buf.numel() < 2 * rows * _lib.load().fcma_work_bytes_per_row(E, V - s0):
+            rows = max(256, min((n0 + 255) // 256 * 256, rows // 256 * 256, 4096 if not self.block_rows else 1 << 30))
+            flags = self._flags(True)
+            need = 256 <= _lib.load().fcma_sym_rows_per_pass(_lib.PREC[op.precision], E, self.epochs_per_subj, flags, V, s0,
+                                                             self._work.buf.numel() if self._work is not None else 0)
+            if not isinstance(self._work, engine.SymWorkspace) or not need or self._work.rows < rows:
                 self._work = None       # release the old scratch first
-                self._work = engine.SymWorkspace(E, V, rows, op.device, start=s0)
+                self._work = engine.SymWorkspace.for_operand(op, rows, self.epochs_per_subj, flags, start=s0)
             engine.voxel_kernels_sym(op, s0, n0, self.epochs_per_subj, flags=self._flags(True),
                                      work=self._work, out=K)
         if world > 1:

@@ -136,13 +136,16 @@ int fcma_voxel_kernels(const void *rows_op, const void *cols_op, int precision, 
  * (j >= start+nb) has received the columns in [start, start+nb).  Calling it once with (0, V), or once per shard
  * of a partition of [0, V) -- e.g. one shard per GPU followed by a sum (all-reduce) of the K arrays -- yields the
  * same kernels as fcma_voxel_kernels.  nb must be a multiple of 256 unless start+nb == V; eps a power of two
- * (fused path); work_dev should hold >= 2 * 256 * fcma_work_bytes_per_row(E, V - start) bytes. */
+ * (fused path); work_dev must hold at least 256 rows (see fcma_sym_rows_per_pass). */
 int fcma_voxel_kernels_sym(const void *op, int precision, int E, int T, long V, long start, long nb, int eps,
                            int flags, float *work_dev, size_t work_bytes, float *K_dev, void *stream);
 /* 1 if fcma_voxel_kernels_sym takes the column voxels' sums from the stored block itself (column-direction
  * normalise+SYRK pass: fp32 block, E <= 32, power-of-two eps <= 32), 0 if it stores a transposed copy of every
  * block and runs the row pass over it (fp16 block, E > 32).  Informational (bench accounting). */
 int fcma_sym_uses_column_pass(int precision, int E, int eps, int flags);
+/* voxel rows fcma_voxel_kernels_sym takes per pass with a scratch buffer of work_bytes (a multiple of 256; < 256 means
+ * the buffer is too small): the column-pass variant keeps only the block itself, the other one also its transposed copy */
+long fcma_sym_rows_per_pass(int precision, int E, int eps, int flags, long V, long start, size_t work_bytes);
 
 /* a9 -> a10 -> a11: K_dev[E][E] += sum over rows [start, start+nb) (beta = 1 semantics, caller zeroes
  * K first as classifier.py:311-313 does); eps <= 1 skips the normalisation (classifier.py:204). */

@@ -320,7 +320,7 @@ def test_symmetric_column_pass_all_eps(dev, E, eps):
     fl = _lib.FLAG_MASK_SELF
     plain = engine.voxel_kernels(op, op, 0, V, eps, flags=fl)
     K = torch.zeros((V, E, E), device=dev)
-    work = engine.SymWorkspace(E, V, 256, dev)
+    work = engine.Workspace(E, V, 256, dev)            # the column-pass variant keeps only the block itself
     work.buf.view(torch.float32).fill_(float("nan"))
     engine.voxel_kernels_sym(op, 0, V, eps, flags=fl, work=work, out=K)      # 6 passes of <= 256 rows
     # scale floor V: with eps = 1 every z-score is 0 in exact arithmetic (the kernels hold rounding residue ~1e-5 * V)
@@ -748,7 +748,7 @@ def test_symmetric_pipeline_vs_reference_golden(dev, golden):
     for prec in ("fp32", "tf32x3"):
         op = engine.pack_epochs(ep, T_e, prec)
         K = torch.zeros((V, E, E), device=dev)
-        engine.voxel_kernels_sym(op, 0, V, eps, work=engine.SymWorkspace(E, V, 256, dev), out=K)
+        engine.voxel_kernels_sym(op, 0, V, eps, work=engine.Workspace(E, V, 256, dev), out=K)
         K = K.cpu().numpy()
         shrink_kernels_(K)
         assert np.max(np.abs(K - ref)) <= k_tol(V) * np.max(np.abs(ref))

@@ -85,13 +85,13 @@ def big():
     Kp = K.clone()
     del work
     torch.cuda.empty_cache()
-    work = engine.SymWorkspace(E, V, 4096, dev)
     Ks = torch.empty((V, E, E), device=dev)
     F16 = _lib.FLAG_F16_INTERMEDIATE
-    for name, env, fl in (("sym fp32 block, column-direction pass over block A", {}, 0),
-                          ("sym fp32 block, column pass, normal copy through TMA bulk stores too", {"FCMA_GEMM_TMA_NORM": "1"}, 0),
-                          ("sym fp32 block, transposed copy B (TMA store) + row pass over it", {"FCMA_SYM_COLS": "0"}, 0),
-                          ("sym fp16 block, transposed copy B", {}, F16)):
+    for name, rows, env, fl in (("sym fp32 block, column pass, 4096 rows per pass (26 GB of scratch)", 2048, {}, 0),
+                                ("sym fp32 block, column pass, 8192 rows per pass (52 GB)", 4096, {}, 0),
+                                ("sym fp32 block, column pass, 4096 rows per pass (again)", 2048, {}, 0),
+                                ("sym fp32 block, column pass, 2048 rows per pass (13 GB)", 1024, {}, 0)):
+        work = engine.SymWorkspace(E, V, rows, dev)
         os.environ.update(env)
 
         def sym():
@@ -104,6 +104,8 @@ def big():
               "max|dK|/max|K| vs plain %.3g" % (name, ms, V * V * E / ms * 1e3, g, s, n, d), flush=True)
         for k in env:
             del os.environ[k]
+        del work
+        torch.cuda.empty_cache()
 
 
 if __name__ == "__main__":

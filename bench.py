@@ -288,13 +288,27 @@ def run_b200_arm(args):
             dist.all_reduce(launches, op=dist.ReduceOp.SUM)
         return float(ms[0]), int(launches[0])
 
+    pipe_state = {}
+
     def timed_e2e_pipelined(nsteps):
-        """N = 1 end-to-end: every step still copies its epochs from pinned host memory and its [V, E, E] kernels back,
-        but on a copy stream, double-buffered, so the copies of step k+1 / k-1 run under the kernels of step k (what a
-        service streaming datasets through the engine does).  The timed region covers all copies of all steps."""
-        main, cs = torch.cuda.current_stream(), torch.cuda.Stream(device=dev)
-        ebuf = [epochs, torch.empty_like(epochs)]
-        kbuf = [K, torch.empty_like(K)]
+        """End-to-end with the copies off the critical path: every step still copies its epochs from pinned host memory
+        (rank 0; N > 1: followed by the NCCL broadcast to the other ranks on a second communicator) and its [V, E, E]
+        kernels back, but on a copy stream, double-buffered, so the input of step k+1 and the result of step k-1 move
+        under the kernels of step k (what a service streaming datasets through the engine does).  The timed region
+        covers all copies and collectives of all steps."""
+        main = torch.cuda.current_stream()
+        if not pipe_state:
+            pipe_state["cs"] = torch.cuda.Stream(device=dev)
+            pipe_state["ebuf"] = [epochs, bcast if world > 1 else torch.empty_like(epochs)]
+            pipe_state["kbuf"] = [K, torch.empty_like(K)]
+            pipe_state["pg2"] = dist.new_group(backend="nccl") if world > 1 else None
+        cs, ebuf, kbuf, pg2 = pipe_state["cs"], pipe_state["ebuf"], pipe_state["kbuf"], pipe_state["pg2"]
+
+        def stage_in(buf):          # on the copy stream: host -> rank 0 -> all ranks
+            if rank == 0:
+                buf.copy_(host, non_blocking=True)
+            if world > 1:
+                dist.broadcast(buf, src=0, group=pg2)
         ready = [torch.cuda.Event() for _ in range(2)]
         consumed = [torch.cuda.Event() for _ in range(2)]
         kdone = [torch.cuda.Event() for _ in range(2)]
@@ -304,7 +318,7 @@ def run_b200_arm(args):
         ev0.record()
         with torch.cuda.stream(cs):
             cs.wait_event(ev0)
-            ebuf[0].copy_(host, non_blocking=True)
+            stage_in(ebuf[0])
             ready[0].record(cs)
         for k in range(nsteps):
             c = k & 1
@@ -312,27 +326,31 @@ def run_b200_arm(args):
                 with torch.cuda.stream(cs):
                     if k >= 1:
                         cs.wait_event(consumed[1 - c])      # step k-1 has packed ebuf[1-c]
-                    ebuf[1 - c].copy_(host, non_blocking=True)
+                    stage_in(ebuf[1 - c])
                     ready[1 - c].record(cs)
             main.wait_event(ready[c])
-            if k >= 2:
+            if k >= 2 and rank == 0:
                 main.wait_event(kread[c])                   # the readback of step k-2 has left kbuf[c]
             op = engine.pack_epochs(ebuf[c], None, prec)
             consumed[c].record(main)
-            if sym:
-                kbuf[c].zero_()
+            kbuf[c].zero_()
+            if n > 0:
                 engine.voxel_kernels_sym(op, start, n, eps, flags=flags, work=work, out=kbuf[c])
-            else:
-                engine.voxel_kernels(op, op, start, n, eps, flags=flags, work=work, out=kbuf[c])
+            if world > 1:
+                dist.reduce(kbuf[c], dst=0)
             kdone[c].record(main)
-            with torch.cuda.stream(cs):
-                cs.wait_event(kdone[c])
-                Khost.copy_(kbuf[c], non_blocking=True)
-                kread[c].record(cs)
+            if rank == 0:
+                with torch.cuda.stream(cs):
+                    cs.wait_event(kdone[c])
+                    Khost.copy_(kbuf[c], non_blocking=True)
+                    kread[c].record(cs)
         main.wait_stream(cs)
         ev1.record()
         barrier()
-        return ev0.elapsed_time(ev1)
+        ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms[0])
 
     for _ in range(max(args.warmup, 3)):
         step(False)
@@ -352,12 +370,13 @@ def run_b200_arm(args):
         ms_seq, _ = timed(ne, True)
         ms_seq /= ne
         ms_e2e, how = ms_seq, "copies and kernels of a step in sequence on one stream"
-        if world == 1:
+        if sym and os.environ.get("FCMA_BENCH_SEQ_E2E") != "1":
             ne = max(4, args.steps)
             timed_e2e_pipelined(2)
             ms_e2e = timed_e2e_pipelined(ne) / ne
-            how = ("copy stream + double buffers: the H2D of step k+1 and the D2H of step k-1 run under the kernels of step k; "
-                   "all copies of all %d steps are inside the timed region" % ne)
+            how = ("copy stream + double buffers: the H2D%s of step k+1 and the D2H of step k-1 run under the kernels of step k; "
+                   "all copies%s of all %d steps are inside the timed region"
+                   % (" + NCCL broadcast (second communicator)" if world > 1 else "", " and collectives" if world > 1 else "", ne))
         e2e = {"value": corr_total / (ms_e2e * 1e-3), "unit": UNIT,
                "h2d_bytes_per_step": int(E) * T * V * 4, "d2h_bytes_per_step": int(V) * E * E * 4,
                "ms_per_step": ms_e2e, "ms_per_step_unpipelined": ms_seq, "steps": ne,

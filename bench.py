@@ -371,7 +371,7 @@ def run_b200_arm(args):
         ms_seq /= ne
         ms_e2e, how = ms_seq, "copies and kernels of a step in sequence on one stream"
         if sym and os.environ.get("FCMA_BENCH_SEQ_E2E") != "1":
-            ne = max(4, args.steps)
+            ne = max(8, 2 * args.steps)      # the first copy-in and the last read-back cannot hide: amortise them
             timed_e2e_pipelined(2)
             ms_e2e = timed_e2e_pipelined(ne) / ne
             how = ("copy stream + double buffers: the H2D%s of step k+1 and the D2H of step k-1 run under the kernels of step k; "

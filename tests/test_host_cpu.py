@@ -180,3 +180,22 @@ def test_sym_row_partition_covers_and_balances():
     assert engine.sym_supported(32, 8, nb=512, start=0, V=1000)
     assert not engine.sym_supported(32, 8, nb=300, start=0, V=1000)
     assert engine.sym_supported(32, 8, nb=488, start=512, V=1000)
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """bench.py --impl reference (the reference's own CPU path, oracle/_ref or the oracle port) runs without a GPU and
+    prints exactly one JSON line with the contract's keys."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--voxels", "1500",
+                          "--steps", "1", "--warmup", "1"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "corr/s" and d["value"] > 0 and d["higher_is_better"] is True
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["gpu_launches"] == 0

@@ -87,10 +87,10 @@ def big():
     torch.cuda.empty_cache()
     Ks = torch.empty((V, E, E), device=dev)
     F16 = _lib.FLAG_F16_INTERMEDIATE
-    for name, rows, env, fl in (("sym fp32 block, column pass, 4096 rows per pass (26 GB of scratch)", 2048, {}, 0),
-                                ("sym fp32 block, column pass, 8192 rows per pass (52 GB)", 4096, {}, 0),
-                                ("sym fp32 block, column pass, 4096 rows per pass (again)", 2048, {}, 0),
-                                ("sym fp32 block, column pass, 2048 rows per pass (13 GB)", 1024, {}, 0)):
+    for name, rows, env, fl in (("sym fp32 block, column-direction pass over the block (default)", 2048, {}, 0),
+                                ("sym fp32 block, transposed copy B (TMA store) + row pass over it", 4096, {"FCMA_SYM_COLS": "0"}, 0),
+                                ("sym fp16 block, transposed copy B", 4096, {}, F16),
+                                ("sym fp32 block, column pass, grouped GEMM tile schedule", 2048, {"FCMA_GEMM_SCHED": "1"}, 0)):
         work = engine.SymWorkspace(E, V, rows, dev)
         os.environ.update(env)
 

@@ -1756,14 +1756,22 @@ constexpr int COLS_SEG_STEPS = FCMA_COLS_SEG_STEPS;   // 16-row steps between fo
 constexpr int COLS_BRICKS = 3;        // 64 KB bricks in flight / in use (cp.async pipeline depth)
 // CPW = columns per warp: 4 (8 warps, 4 accumulator sets, 255 registers) or 2 (16 warps, 2 accumulator sets, <= 128
 // registers: twice the warps to hide the dependent statistics / shuffle chains between the block barriers)
-template <int EPS, int CPW>
+// HALF: the block holds fp16 Fisher-z values (FCMA_FLAG_F16_INTERMEDIATE / single-product operand modes): a line
+// (epoch, row) of the strip is 64 bytes, two lines share a 128-byte smem row (16-byte unit (L & 1)*4 + piece, same
+// swizzle), a brick is 32 KB and warp w reads the 8 bytes of its columns 4w .. 4w+3 (LDS.64, two-way conflicts).
+template <int EPS, int CPW, bool HALF>
 __global__ void __launch_bounds__(32 * (32 / CPW), 1)
-    k_norm_syrk_cols(const float *__restrict__ A, long n, int E, long n2, long T256, long c0, float *K)
+    k_norm_syrk_cols(const void *__restrict__ Av, long n, int E, long n2, long T256, long c0, float *K)
 {
+    static_assert(!HALF || CPW == 4, "the fp16 variant takes 4 columns per warp");
     constexpr int R = 4, EP = 32, MT = 2, NT = 4;
     constexpr int NTHR = 32 * (32 / CPW);      // threads per CTA
-    constexpr int PPT = 4096 / NTHR;           // 16-byte pieces a thread copies per brick
-    constexpr int LS = NTHR / 8;               // line stride between a thread's pieces
+    constexpr int BRICK = HALF ? 32768 : 65536;   // bytes of one [32 epochs][16 rows][32 columns] brick
+    constexpr int PPL = HALF ? 4 : 8;          // 16-byte pieces per line
+    constexpr int PPT = BRICK / 16 / NTHR;     // 16-byte pieces a thread copies per brick
+    constexpr int LS = NTHR / PPL;             // line stride between a thread's pieces
+    using elem_t = std::conditional_t<HALF, __half, float>;
+    const elem_t *A = reinterpret_cast<const elem_t *>(Av);
     extern __shared__ __align__(1024) uint8_t cs_raw[];
     uint8_t *cs = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(cs_raw) + 1023) & ~uintptr_t(1023));
     const uint32_t brick0 = smem_u32(cs);            // 3 bricks of 64 KB; the first two double as [32 columns][EP*EP] fp32 at folds
@@ -1781,28 +1789,34 @@ __global__ void __launch_bounds__(32 * (32 / CPW), 1)
         // issue the cp.async copies of row step `st` into brick `b`.  Thread tid copies piece w = tid & 7 of the lines
         // (tid >> 3) + 32 k, k < 16: row (tid >> 3) & 15 of epochs (tid >> 7) + 2 k -- one source offset and one
         // destination offset per thread, the rest are compile-time strides (swz of those lines = c0 | ((k >> 1) & 1) << 2)
-        const int pf_w = tid & 7, pf_line0 = tid >> 3, pf_row = pf_line0 & 15, pf_e0 = pf_line0 >> 4;
+        const int pf_w = tid & (PPL - 1), pf_line0 = tid / PPL, pf_row = pf_line0 & 15, pf_e0 = pf_line0 >> 4;
         const uint32_t pf_c = (uint32_t)((pf_line0 >> 1) & 3);
-        const int pf_src = pf_e0 * 65536 + pf_row * 256 + pf_w * 4 + jo;
-        const uint32_t pf_dst = brick0 + (uint32_t)pf_line0 * 128u;
+        const int pf_src = pf_e0 * 65536 + pf_row * 256 + pf_w * (HALF ? 8 : 4) + jo;
+        // fp32: line L at L*128, unit = piece; fp16: lines 2m, 2m+1 share row m, unit = (L & 1)*4 + piece
+        const uint32_t pf_unit = HALF ? (uint32_t)((pf_line0 & 1) * 4 + pf_w) : (uint32_t)pf_w;
+        const uint32_t pf_dst = brick0 + (HALF ? (uint32_t)(pf_line0 >> 1) : (uint32_t)pf_line0) * 128u;
         auto prefetch = [&](long st, int b) {
             const long i0 = st * 16;
-            const float *src0 = A + ((size_t)((i0 >> 8) * T256 + tjx) * E) * 65536 + (size_t)(i0 & 255) * 256 + pf_src;
+            const elem_t *src0 = A + ((size_t)((i0 >> 8) * T256 + tjx) * E) * 65536 + (size_t)(i0 & 255) * 256 + pf_src;
             const bool row_ok = i0 + pf_row < n;
-            const uint32_t dst0 = pf_dst + (uint32_t)b * 65536u;
+            const uint32_t dst0 = pf_dst + (uint32_t)b * (uint32_t)BRICK;
 #pragma unroll
             for (int k = 0; k < PPT; k++) {
                 const bool ok = row_ok && pf_e0 + (LS / 16) * k < E;
-                const uint32_t piece = ((uint32_t)pf_w ^ pf_c ^ (uint32_t)((((k * LS) >> 6) & 1) << 2)) << 4;
-                cp_async_16_zfill_s(dst0 + (uint32_t)(k * LS) * 128u + piece, ok ? src0 + (size_t)k * ((LS / 16) * 65536) : A,
-                                    ok ? 16u : 0u);
+                const uint32_t piece = (pf_unit ^ pf_c ^ (uint32_t)((((k * LS) >> 6) & 1) << 2)) << 4;
+                cp_async_16_zfill_s(dst0 + (uint32_t)(k * LS) * (HALF ? 64u : 128u) + piece,
+                                    ok ? src0 + (size_t)k * ((LS / 16) * 65536) : A, ok ? 16u : 0u);
             }
         };
         // this lane's reads: piece `warp` of the lines (4g + r)*16 + row(sl, t); their swizzle is t | (g & 1) << 2 for
         // every (r, sl), so one base address per thread and immediate offsets (r*16 + (sl & 1) + 8 (sl >> 1)) * 128
-        const uint32_t rd_base = (uint32_t)((R * g) * 16 + 2 * t) * 128u +
-                                 ((((uint32_t)(warp * CPW) >> 2) ^ ((uint32_t)t | ((uint32_t)(g & 1) << 2))) << 4) +
-                                 (uint32_t)((warp * CPW) & 3) * 4u;
+        const uint32_t rd_swz = (uint32_t)t | ((uint32_t)(g & 1) << 2);
+        const uint32_t rd_base = HALF ? (uint32_t)(32 * g + t) * 128u + (uint32_t)(warp & 1) * 8u
+                                      : (uint32_t)((R * g) * 16 + 2 * t) * 128u + ((((uint32_t)(warp * CPW) >> 2) ^ rd_swz) << 4) +
+                                            (uint32_t)((warp * CPW) & 3) * 4u;
+        // fp16: 16-byte unit (sl & 1)*4 + (warp >> 1), swizzled -- two variants per lane
+        [[maybe_unused]] const uint32_t rd_x0 = (((uint32_t)(warp >> 1)) ^ rd_swz) << 4;
+        [[maybe_unused]] const uint32_t rd_x1 = ((4u + (uint32_t)(warp >> 1)) ^ rd_swz) << 4;
         for (long seg0 = 0; seg0 < nsteps; seg0 += COLS_SEG_STEPS) {
             const long seg1 = seg0 + COLS_SEG_STEPS < nsteps ? seg0 + COLS_SEG_STEPS : nsteps;
             float acc[CPW][MT][NT][4];
@@ -1826,12 +1840,17 @@ __global__ void __launch_bounds__(32 * (32 / CPW), 1)
                 cp_async_commit();
                 // ---- this lane's 4 epochs x 4 rows x 4 columns
                 float vals[R][4][CPW];
-                const uint32_t bb = brick0 + (uint32_t)buf * 65536u + rd_base;
+                const uint32_t bb = brick0 + (uint32_t)buf * (uint32_t)BRICK + rd_base;
 #pragma unroll
                 for (int r = 0; r < R; r++)
 #pragma unroll
                     for (int sl = 0; sl < 4; sl++) {
-                        if constexpr (CPW == 4) {
+                        if constexpr (HALF) {
+                            const uint2 q = lds64(bb + ((sl & 1) ? rd_x1 : rd_x0) + (uint32_t)((8 * r + 4 * (sl >> 1)) * 128));
+                            const float2 lo = __half22float2(*reinterpret_cast<const __half2 *>(&q.x));
+                            const float2 hi = __half22float2(*reinterpret_cast<const __half2 *>(&q.y));
+                            vals[r][sl][0] = lo.x, vals[r][sl][1] = lo.y, vals[r][sl][2] = hi.x, vals[r][sl][3] = hi.y;
+                        } else if constexpr (CPW == 4) {
                             const uint4 q = lds128(bb + (uint32_t)((r * 16 + (sl & 1) + 8 * (sl >> 1)) * 128));
                             vals[r][sl][0] = __uint_as_float(q.x), vals[r][sl][1] = __uint_as_float(q.y);
                             vals[r][sl][2] = __uint_as_float(q.z), vals[r][sl][3] = __uint_as_float(q.w);
@@ -2095,25 +2114,29 @@ static int launch_norm_syrk(const float *C, long nb, int E, long n2, long stride
 
 // column-direction pass over a tiled fp32 block (k_norm_syrk_cols): K[j] += ... for block columns [c0, n2)
 static bool cols_supported(int E, int eps) { return E <= 32 && eps >= 1 && eps <= 32 && (eps & (eps - 1)) == 0; }
-static int launch_norm_syrk_cols(const float *A, long n, int E, long n2, long T256, long c0, int eps, float *K,
-                                 cudaStream_t st)
+static int launch_norm_syrk_cols(const void *A, long n, int E, long n2, long T256, long c0, int eps, float *K,
+                                 cudaStream_t st, int half_in = 0)
 {
     if (!cols_supported(E, eps) || (c0 & 31) || c0 >= n2) return fail(FCMA_EINVAL, "internal: column pass unsupported E=%d eps=%d c0=%ld", E, eps, c0);
     const long nstrips = cdiv(n2 - c0, 32);
     const unsigned grid = (unsigned)(nstrips < g_sm_count ? nstrips : g_sm_count);
-    const size_t smem = (size_t)COLS_BRICKS * 65536 + 1024;
+    // bricks (3 x 64 KB fp32 / 3 x 32 KB fp16); the fold buffer [32 columns][32*32] fp32 = 128 KB overlays them
+    const size_t smem = (half_in ? (size_t)131072 : (size_t)COLS_BRICKS * 65536) + 1024;
     // 4 columns per warp (8 warps, 255 registers) by default; FCMA_COLS_CPW=2 selects 2 columns per warp (16 warps at 128
     // registers: measured 7 % slower -- 80 bytes of spills and two-way conflicts on the 8-byte LDS outweigh the occupancy)
     const char *cpw_env = getenv("FCMA_COLS_CPW");
     const bool cpw4 = !(cpw_env && cpw_env[0] == '2');
 #define FCMA_COLS_CASE(EPSV)                                                                                        \
     case EPSV:                                                                                                      \
-        if (cpw4) {                                                                                                 \
-            CUDA_TRY(cudaFuncSetAttribute(k_norm_syrk_cols<EPSV, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-            k_norm_syrk_cols<EPSV, 4><<<grid, 256, smem, st>>>(A, n, E, n2, T256, c0, K);                          \
+        if (half_in) {                                                                                              \
+            CUDA_TRY(cudaFuncSetAttribute(k_norm_syrk_cols<EPSV, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            k_norm_syrk_cols<EPSV, 4, true><<<grid, 256, smem, st>>>(A, n, E, n2, T256, c0, K);                    \
+        } else if (cpw4) {                                                                                          \
+            CUDA_TRY(cudaFuncSetAttribute(k_norm_syrk_cols<EPSV, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            k_norm_syrk_cols<EPSV, 4, false><<<grid, 256, smem, st>>>(A, n, E, n2, T256, c0, K);                   \
         } else {                                                                                                    \
-            CUDA_TRY(cudaFuncSetAttribute(k_norm_syrk_cols<EPSV, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-            k_norm_syrk_cols<EPSV, 2><<<grid, 512, smem, st>>>(A, n, E, n2, T256, c0, K);                          \
+            CUDA_TRY(cudaFuncSetAttribute(k_norm_syrk_cols<EPSV, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            k_norm_syrk_cols<EPSV, 2, false><<<grid, 512, smem, st>>>(A, n, E, n2, T256, c0, K);                   \
         }                                                                                                           \
         break;
     switch (eps) {
@@ -2405,14 +2428,19 @@ static int run_pipeline(const void *rows_op, const void *cols_op, int precision,
 // After all passes of all callers (ranks) every K[x] has received every column exactly once.  Half the MMAs and
 // half the Fisher transforms of the plain pipeline; HBM traffic per correlation is unchanged.
 // which variant run_pipeline_sym takes for the column voxels' sums: 1 = column-direction pass over block A
-// (fp32 block, E <= 32), 0 = transposed block B + row pass
+// (E <= 32, power-of-two eps <= 32; fp32 or fp16 block), 0 = transposed block B + row pass
 static bool sym_uses_cols(int precision, int E, int eps, int flags)
 {
     const char *f16i = getenv("FCMA_F16_INTERMEDIATE");
     bool half16 = (flags & FCMA_FLAG_F16_INTERMEDIATE) || precision == FCMA_PREC_BF16 || precision == FCMA_PREC_TF32;
     if (f16i && (f16i[0] == '0' || f16i[0] == '1')) half16 = f16i[0] == '1';
     const char *sc = getenv("FCMA_SYM_COLS");
-    return !half16 && cols_supported(E, eps) && !(sc && sc[0] == '0');
+    if (sc && sc[0] == '0') return false;
+    if (half16) {   // fp16 block: FCMA_SYM_COLS_F16=0 keeps the transposed copy + row pass (A/B)
+        const char *sh = getenv("FCMA_SYM_COLS_F16");
+        if (sh && sh[0] == '0') return false;
+    }
+    return cols_supported(E, eps);
 }
 extern "C" int fcma_sym_uses_column_pass(int precision, int E, int eps, int flags)
 {
@@ -2468,7 +2496,7 @@ static int run_pipeline_sym(const void *op, int precision, int E, int T, long V,
         if (rc) return rc;
         if (g_timing_on) CUDA_TRY(cudaEventRecord(ev[3], st));
         if (rowsB > 0 && use_cols) {
-            rc = launch_norm_syrk_cols(A, n, E, colsA, t256, n, eps, K + (size_t)a * E * E, st);
+            rc = launch_norm_syrk_cols(A, n, E, colsA, t256, n, eps, K + (size_t)a * E * E, st, half16 ? 1 : 0);
             if (rc) return rc;
         } else if (rowsB > 0) {
             rc = launch_norm_syrk(B, rowsB, E, n, 256, 65536, eps, 1, -1, 1.0f, K + (size_t)(a + n) * E * E, 0, st,

@@ -140,8 +140,8 @@ int fcma_voxel_kernels(const void *rows_op, const void *cols_op, int precision, 
 int fcma_voxel_kernels_sym(const void *op, int precision, int E, int T, long V, long start, long nb, int eps,
                            int flags, float *work_dev, size_t work_bytes, float *K_dev, void *stream);
 /* 1 if fcma_voxel_kernels_sym takes the column voxels' sums from the stored block itself (column-direction
- * normalise+SYRK pass: fp32 block, E <= 32, power-of-two eps <= 32), 0 if it stores a transposed copy of every
- * block and runs the row pass over it (fp16 block, E > 32).  Informational (bench accounting). */
+ * normalise+SYRK pass: E <= 32, power-of-two eps <= 32; fp32 or fp16 block), 0 if it stores a transposed copy of
+ * every block and runs the row pass over it (E > 32).  Informational (bench accounting, scratch sizing). */
 int fcma_sym_uses_column_pass(int precision, int E, int eps, int flags);
 /* voxel rows fcma_voxel_kernels_sym takes per pass with a scratch buffer of work_bytes (a multiple of 256; < 256 means
  * the buffer is too small): the column-pass variant keeps only the block itself, the other one also its transposed copy */

@@ -339,6 +339,36 @@ def test_symmetric_column_pass_all_eps(dev, E, eps):
         assert np.max(np.abs(K[s0:s0 + 30].cpu().numpy() - Kref)) <= tol
 
 
+@pytest.mark.parametrize("prec,flag", [("fp32", True), ("bf16", False)])
+def test_symmetric_fp16_block_column_pass(dev, prec, flag, monkeypatch):
+    """fp16 Fisher-z block (opt-in flag, or implied by the single-product operand modes): the symmetric pipeline's column
+    pass reads 64-byte lines of the fp16 block; same stored values as the plain fp16-block pipeline, so the kernels
+    agree to the order of the fp32 partial sums, and both stay within the fp16-block tolerance of the fp32 block."""
+    V, T, E, eps = 1400, 40, 16, 8
+    raw, _ = synthetic.make_epochs(V, T, E, seed=8642)
+    ep, T_e = engine.stack_epochs(raw, dev)
+    op = engine.pack_epochs(ep, T_e, prec)
+    fl = _lib.FLAG_MASK_SELF | (_lib.FLAG_F16_INTERMEDIATE if flag else 0)
+    assert _lib.load().fcma_sym_uses_column_pass(_lib.PREC[op.precision], E, eps, fl) == 1
+    plain = engine.voxel_kernels(op, op, 0, V, eps, flags=fl)
+    scale = float(plain.abs().max())
+    out = {}
+    for cols in ("1", "0"):                      # column pass over the block / transposed copy + row pass
+        monkeypatch.setenv("FCMA_SYM_COLS_F16", cols)
+        K = torch.zeros((V, E, E), device=dev)
+        work = engine.SymWorkspace(E, V, 512, dev)
+        work.buf.view(torch.float32).fill_(float("nan"))
+        for s0, n0 in engine.sym_row_partition(V, 2):
+            engine.voxel_kernels_sym(op, s0, n0, eps, flags=fl, work=work, out=K)
+        assert torch.isfinite(K).all()
+        assert float((K - K.transpose(1, 2)).abs().max()) == 0.0
+        assert float((K - plain).abs().max()) <= 1e-5 * scale
+        out[cols] = K
+    if flag:     # against the fp32 block: the averaged rounding of the stored values (DESIGN.md 3.3)
+        K32 = engine.voxel_kernels(op, op, 0, V, eps, flags=_lib.FLAG_MASK_SELF)
+        assert 0 < float((out["1"] - K32).abs().max()) <= 4e-3 / math.sqrt(V) * float(K32.abs().max())
+
+
 def test_pipeline_vs_reference_golden_kernels(dev, golden):
     g = golden("vs_mid")
     d1, d2 = list(g["d1"]), list(g["d2"])

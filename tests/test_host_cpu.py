@@ -208,18 +208,19 @@ def test_symmetric_pipeline_host_queries():
     lib = _lib.load()
     P = _lib.PREC
     F16 = _lib.FLAG_F16_INTERMEDIATE
-    # column pass: fp32 block, E <= 32, power-of-two eps <= 32
+    # column pass: E <= 32, power-of-two eps <= 32
     assert lib.fcma_sym_uses_column_pass(P["fp16x3"], 32, 8, 0) == 1
     assert lib.fcma_sym_uses_column_pass(P["tf32x3"], 16, 4, _lib.FLAG_MASK_SELF) == 1
     assert lib.fcma_sym_uses_column_pass(P["fp16x3"], 64, 8, 0) == 0          # E > 32: transposed copy + row pass
-    assert lib.fcma_sym_uses_column_pass(P["fp16x3"], 32, 8, F16) == 0        # fp16 block
-    assert lib.fcma_sym_uses_column_pass(P["bf16"], 32, 8, 0) == 0            # single-product modes imply the fp16 block
+    assert lib.fcma_sym_uses_column_pass(P["fp16x3"], 32, 8, F16) == 1        # fp16 block: column pass as well
+    assert lib.fcma_sym_uses_column_pass(P["bf16"], 32, 8, 0) == 1            # single-product modes imply the fp16 block
+    assert lib.fcma_sym_uses_column_pass(P["bf16"], 48, 16, 0) == 0
     assert lib.fcma_sym_uses_column_pass(P["fp16x3"], 32, 3, 0) == 0          # eps not a power of two
     per_row = lib.fcma_work_bytes_per_row(32, 50000)
     assert per_row == 32 * 50176 * 4
     # the column-pass variant keeps only the block: twice the rows of the variant with a transposed copy
     assert lib.fcma_sym_rows_per_pass(P["fp16x3"], 32, 8, 0, 50000, 0, 4096 * per_row) == 4096
-    assert lib.fcma_sym_rows_per_pass(P["fp16x3"], 32, 8, F16, 50000, 0, 4096 * per_row) == 2048
+    assert lib.fcma_sym_rows_per_pass(P["fp16x3"], 64, 8, 0, 50000, 0, 4096 * lib.fcma_work_bytes_per_row(64, 50000)) == 2048
     assert lib.fcma_sym_rows_per_pass(P["fp16x3"], 32, 8, 0, 50000, 0, 300 * per_row) == 256
     assert lib.fcma_sym_rows_per_pass(P["fp16x3"], 32, 8, 0, 50000, 0, 100 * per_row) == 0     # too small
     # a shard that starts further right needs less scratch per row

@@ -268,8 +268,8 @@ def sym_supported(E, eps, nb=None, start=0, V=None):
 
 
 class SymWorkspace(Workspace):
-    """Scratch of the symmetric pipeline sized for `rows` block rows WITH a transposed copy (fp16 block, E > 32);
-    the column-pass variant (fp32 block, E <= 32) keeps only the block and takes twice as many rows per pass from the
+    """Scratch of the symmetric pipeline sized for `rows` block rows WITH a transposed copy (E > 32);
+    the column-pass variant (E <= 32) keeps only the block and takes twice as many rows per pass from the
     same buffer (fcma_sym_rows_per_pass)."""
 
     def __init__(self, E, V, rows, device, start=0, transposed_copy=True):
@@ -281,7 +281,7 @@ class SymWorkspace(Workspace):
     @classmethod
     def for_operand(cls, op, rows, eps, flags=0, start=0):
         """Scratch for exactly `rows` block rows per pass of fcma_voxel_kernels_sym on this operand: the block alone
-        when the column pass applies (fp32 block, E <= 32), block + transposed copy otherwise."""
+        when the column pass applies (E <= 32), block + transposed copy otherwise."""
         cols = bool(_lib.load().fcma_sym_uses_column_pass(_prec_code(op.precision), op.E, int(eps), int(flags)))
         return cls(op.E, op.V, rows, op.device, start=start, transposed_copy=not cols)
 

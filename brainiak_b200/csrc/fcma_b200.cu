@@ -2465,8 +2465,8 @@ static int run_pipeline_sym(const void *op, int precision, int E, int T, long V,
     bool half16 = (flags & FCMA_FLAG_F16_INTERMEDIATE) || precision == FCMA_PREC_BF16 || precision == FCMA_PREC_TF32;
     if (f16i && (f16i[0] == '0' || f16i[0] == '1')) half16 = f16i[0] == '1';
     const size_t esz = half16 ? sizeof(__half) : sizeof(float);
-    // column-direction pass (fp32 block, E <= 32): the column voxels' sums are taken from block A itself, no transposed
-    // copy is stored.  FCMA_SYM_COLS=0 keeps the transposed block B (A/B).
+    // column-direction pass (E <= 32; fp32 or fp16 block): the column voxels' sums are taken from block A itself, no
+    // transposed copy is stored.  FCMA_SYM_COLS=0 (fp16 block: FCMA_SYM_COLS_F16=0) keeps the transposed block B (A/B).
     const bool use_cols = sym_uses_cols(precision, E, eps, flags);
     // per block row: A needs E * round_up(V - a, 256) floats; with a transposed block B at most the same again
     const size_t row_bytes = (use_cols ? 1 : 2) * fcma_work_bytes_per_row(E, V - start);

@@ -791,6 +791,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_MAX_THREADS, 1)
         if (elect_one_sync()) {
             int stage = 0;
             uint32_t phase = 0;
+            const uint64_t l2pol = l2_policy_evict_last();
             for (long grp = pair; grp < ngroups; grp += npairs)
             for (long tile = grp * p.grp_tiles; tile < (grp + 1) * p.grp_tiles; tile++) {
                 const int e = (int)(tile / tiles_per_e);
@@ -809,12 +810,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_MAX_THREADS, 1)
                     else
                         mbar_arrive_cluster(&full_bar[stage], 0);
                     uint8_t *base = tiles + (size_t)stage * p.stage_bytes;
-                    for (int pl = 0; pl < p.planes; pl++)
-                        tma_load_3d_2sm(&tm_cols, &full_bar[stage], base + pl * 16384, k0, col0, pl * p.E + e);
                     uint8_t *rbase = base + p.planes * 16384;
-                    for (int pl = 0; pl < p.planes; pl++)
-                        tma_load_3d_2sm(&tm_rows, &full_bar[stage], rbase + (size_t)pl * p.half_bytes, k0, row0,
-                                        pl * p.E + e);
+                    if (p.debug & 64) {   // A/B: operand loads with an L2 evict-last policy
+                        for (int pl = 0; pl < p.planes; pl++)
+                            tma_load_3d_2sm_hint(&tm_cols, &full_bar[stage], base + pl * 16384, k0, col0, pl * p.E + e, l2pol);
+                        for (int pl = 0; pl < p.planes; pl++)
+                            tma_load_3d_2sm_hint(&tm_rows, &full_bar[stage], rbase + (size_t)pl * p.half_bytes, k0, row0,
+                                                 pl * p.E + e, l2pol);
+                    } else {
+                        for (int pl = 0; pl < p.planes; pl++)
+                            tma_load_3d_2sm(&tm_cols, &full_bar[stage], base + pl * 16384, k0, col0, pl * p.E + e);
+                        for (int pl = 0; pl < p.planes; pl++)
+                            tma_load_3d_2sm(&tm_rows, &full_bar[stage], rbase + (size_t)pl * p.half_bytes, k0, row0,
+                                            pl * p.E + e);
+                    }
                     if (++stage == p.stages) {
                         stage = 0;
                         phase ^= 1;

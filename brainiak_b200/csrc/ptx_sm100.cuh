@@ -349,6 +349,25 @@ __device__ __forceinline__ void tma_load_3d_2sm(const CUtensorMap *m, uint64_t *
           "r"(c1), "r"(c2)
         : "memory");
 }
+// same with an L2 cache-policy operand (createpolicy): the operand tiles are re-read by every tile of a column
+// group while 26 GB of streaming stores pass through L2
+__device__ __forceinline__ uint64_t l2_policy_evict_last()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void tma_load_3d_2sm_hint(const CUtensorMap *m, uint64_t *bar, void *smem_dst, int c0,
+                                                     int c1, int c2, uint64_t policy)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4, %5}], [%2], %6;"
+        :
+        : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0),
+          "r"(c1), "r"(c2), "l"(policy)
+        : "memory");
+}
 __device__ __forceinline__ void tmem_alloc_2sm(uint32_t *smem_dst, uint32_t ncols)
 {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)),

@@ -88,10 +88,9 @@ def big():
     Ks = torch.empty((V, E, E), device=dev)
     F16 = _lib.FLAG_F16_INTERMEDIATE
     for name, rows, env, fl in (("sym fp32 block, column-direction pass over the block (default)", 2048, {}, 0),
-                                ("sym fp16 block, transposed copy B", 4096, {}, F16),
-                                ("sym fp16 block, column pass (FCMA_SYM_COLS_F16=1)", 2048, {"FCMA_SYM_COLS_F16": "1"}, F16),
-                                ("sym fp16 block, transposed copy B (again)", 4096, {}, F16),
-                                ("sym fp16 block, column pass (again)", 2048, {"FCMA_SYM_COLS_F16": "1"}, F16)):
+                                ("sym fp32 block, transposed copy B (TMA store) + row pass over it", 4096, {"FCMA_SYM_COLS": "0"}, 0),
+                                ("sym fp16 block, column pass", 2048, {}, F16),
+                                ("sym fp16 block, transposed copy B", 4096, {"FCMA_SYM_COLS_F16": "0"}, F16)):
         work = engine.SymWorkspace(E, V, rows, dev)
         os.environ.update(env)
 
@@ -122,15 +121,13 @@ if __name__ == "__main__":
     parity(3000, 200, 32, 8, 1024, shards=2, flags=_lib.FLAG_F16_INTERMEDIATE)     # fp16 blocks, both copies
     parity(2000, 64, 16, 4, 256, flags=_lib.FLAG_F16_INTERMEDIATE | _lib.FLAG_MASK_SELF)
     parity(1800, 200, 32, 8, 768, prec="bf16")
-    # fp16 block with the column pass (opt-in until validated): same values as the plain fp16-block pipeline
-    os.environ["FCMA_SYM_COLS_F16"] = "1"
+    # fp16 block with the column pass: same values as the plain fp16-block pipeline
     assert lib.fcma_sym_uses_column_pass(_lib.PREC["fp16x3"], 32, 8, _lib.FLAG_F16_INTERMEDIATE) == 1
     parity(3000, 200, 32, 8, 1024, shards=2, flags=_lib.FLAG_F16_INTERMEDIATE)
     parity(2000, 64, 16, 4, 256, flags=_lib.FLAG_F16_INTERMEDIATE | _lib.FLAG_MASK_SELF)
     parity(1800, 200, 32, 8, 768, prec="bf16")
     parity(1300, 24, 7, 2, 256, flags=_lib.FLAG_F16_INTERMEDIATE, tol=2e-3)
     parity(2600, 50, 24, 8, 512, flags=_lib.FLAG_F16_INTERMEDIATE)
-    del os.environ["FCMA_SYM_COLS_F16"]
     print("parity section: %.1f s, failures: %s" % (time.time() - t0, FAILS), flush=True)
     if "--no-big" not in sys.argv:
         big()

@@ -12,6 +12,8 @@
  *   fcma_extension.normalization                 fcma_extension.cc:29  fcma_within_subject_norm
  *   preprocessing._separate_epochs (z-score)     preprocessing.py:80   fcma_pack_operand(normalize=1)
  *   VoxelSelector._voxel_scoring stages 1-3      voxelselector.py:467  fcma_voxel_kernels
+ *   VoxelSelector._worker task loop, one mask    voxelselector.py:255  fcma_voxel_kernels_sym  (raw_data2 is None,
+ *                                                (+ :289-291)          uses corr[i][e][j] == corr[j][e][i])
  *   Classifier._compute_kernel_matrix_in_portion classifier.py:279     fcma_classifier_kernel
  *
  * Conventions
@@ -129,7 +131,8 @@ int fcma_voxel_kernels(const void *rows_op, const void *cols_op, int precision, 
                        long V2, long start, long nb, int eps, int flags, float *work_dev,
                        size_t work_bytes, float *K_dev, void *stream);
 
-/* Same result for SELF-correlation (raw_data2 is None) at half the tensor work, using corr[i][e][j] == corr[j][e][i]:
+/* Replaces the worker's whole task loop (voxelselector.py:255-282 over _voxel_scoring, :467-516) when raw_data2 is None
+ * (:289-291).  Same result for SELF-correlation at half the tensor work, using corr[i][e][j] == corr[j][e][i]:
  * rows [start, start+nb) are contracted with columns [start, V) only and every block is used twice, for its row
  * voxels and (transposed) for its column voxels.  K_dev is the FULL [V][E][E] array and is ACCUMULATED into
  * (caller zeroes it): after this call K[i] (start <= i < start+nb) holds the columns j >= start, and K[j]

@@ -16,6 +16,10 @@ PREC_NAMES = tuple(PREC) + ("fp32",)      # "fp32" = auto-select fp16x3 / tf32x3
 FLAG_MASK_SELF = 1
 FLAG_FISHER_IN_PASS2 = 2
 FLAG_F16_INTERMEDIATE = 4   # fp16 internal Fisher-z block (default only in the bf16 / tf32 operand modes)
+# alternate code paths with the same results (tests compare them against the defaults)
+FLAG_STRIDED_BLOCK = 8      # strided [nb][E][ld] correlation block instead of the tiled one
+FLAG_SYM_TRANSPOSED = 16    # symmetric pipeline: transposed copy + row pass instead of the column-direction pass
+FLAG_COLS_LDGSTS = 32       # column-direction pass fed by cp.async instead of TMA bricks
 
 c_void_p, c_int, c_long, c_size_t, c_float = (ctypes.c_void_p, ctypes.c_int, ctypes.c_long,
                                                ctypes.c_size_t, ctypes.c_float)
@@ -70,6 +74,15 @@ SIGNATURES = {
 }
 
 _lib = None
+
+
+def use_diag_build():
+    """tools/ only: bind the diagnostic build (libfcma_b200_diag.so, compiled with -DFCMA_DIAG, the only build that
+    reads the FCMA_* A/B and debug environment knobs).  Must be called before the first load()."""
+    global LIB_PATH
+    if _lib is not None:
+        raise RuntimeError("use_diag_build() must be called before the library is loaded")
+    LIB_PATH = os.path.join(_HERE, "libfcma_b200_diag.so")
 
 
 class FcmaLibraryMissing(RuntimeError):

@@ -61,6 +61,57 @@ static int fail(int code, const char *fmt, ...)
 static inline long cdiv(long a, long b) { return (a + b - 1) / b; }
 static inline long round_up(long a, long b) { return cdiv(a, b) * b; }
 
+// Tuning / diagnostic knobs (A/B switches of tools/, FCMA_GEMM_DEBUG bits that produce WRONG output on purpose) exist
+// only in the diagnostic build (-DFCMA_DIAG -> libfcma_b200_diag.so, `python -m brainiak_b200.build --diag`).  The
+// product library never reads the environment: a stray variable cannot change its numerics or layout.
+#ifdef FCMA_DIAG
+static inline const char *diag_env(const char *name) { return getenv(name); }
+#define FCMA_DBG(p, bit) ((p).debug & (bit))
+#else
+static inline const char *diag_env(const char *) { return nullptr; }
+#define FCMA_DBG(p, bit) false
+#endif
+
+// RAII holders so that early error returns do not leak stream-ordered allocations or events
+struct AsyncBuf {
+    void *p = nullptr;
+    cudaStream_t st = nullptr;
+    ~AsyncBuf()
+    {
+        if (p) cudaFreeAsync(p, st);
+    }
+    cudaError_t alloc(size_t n, cudaStream_t s)
+    {
+        st = s;
+        return cudaMallocAsync(&p, n ? n : 1, s);
+    }
+};
+template <int N>
+struct EventSet {
+    cudaEvent_t ev[N] = {};
+    bool on = false;
+    ~EventSet()
+    {
+        for (int k = 0; k < N; k++)
+            if (ev[k]) cudaEventDestroy(ev[k]);
+    }
+    cudaError_t create()
+    {
+        on = true;
+        for (int k = 0; k < N; k++) {
+            cudaError_t e = cudaEventCreate(&ev[k]);
+            if (e != cudaSuccess) return e;
+        }
+        return cudaSuccess;
+    }
+};
+// restores the caller's current device when a host-buffer entry point returns (they run on `device`)
+struct DeviceGuard {
+    int prev = -1;
+    DeviceGuard() { if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); prev = -1; } }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
 static int g_sm_count = 0;
 static int check_device()
 {
@@ -432,7 +483,8 @@ struct Gemm2Params {
                                    // 0: strided fp32 [i][e][j]
     int epi_warps;                 // 8 or 16 epilogue warps (blockDim = 128 + 32 * epi_warps)
     int debug;                     // FCMA_GEMM_DEBUG (diagnostics only; output is wrong when set):
-                                   //   4 no epilogue work (main loop only), 16 MMAs re-read stale stages (no loads)
+                                   //   4 no epilogue work (main loop only), 16 MMAs re-read stale stages (no loads),
+                                   //   128 every chunk stored transposed through TMA instead of 32 STG (timing experiment)
     // ---- symmetric (self-correlation) mode: corr[i][e][j] == corr[j][e][i], so a tile is computed once and stored
     // twice, as tile (ti, tj) and -- transposed through shared memory -- as tile (tj, ti)
     long col_start;                // first column voxel of the block: column tile tj starts at col_start + 256*tj
@@ -562,7 +614,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(const Gemm2Params &p, uint64_
     const long i0 = (long)ti * p.BN;
     const int nchunks = p.BN >> 5;
     bool released = false;
-    for (int c = (p.debug & 4) ? nchunks : part; c < nchunks; c += cstep) {
+    for (int c = FCMA_DBG(p, 4) ? nchunks : part; c < nchunks; c += cstep) {
         const long ic = i0 + c * 32;
         if (ic >= p.nb) break;
         uint32_t v[32];
@@ -653,6 +705,25 @@ __device__ __forceinline__ void gemm_epilogue_tile(const Gemm2Params &p, uint64_
             // columns >= V2 fall into the tile padding the caller allocated
             float *ptr = p.out + (((size_t)(ti * p.tiles_j + tj) * p.E + e) * 256 + c * 32) * 256 +
                          ((int)rank * 128 + q * 32 + lane);
+            if (FCMA_DBG(p, 128) && p.sym_diag && p.tr_w == 0) {
+                // diagnostics (timing only, output is the tile TRANSPOSED in place): every chunk leaves as 8 STS.128 + one
+                // TMA bulk store instead of 32 STG -- what a block stored as [j][i] tiles would cost the epilogue
+                const uint32_t tb = tr_buf + (uint32_t)(warp - 4) * p.tr_warp_bytes;
+                if (lane == 0) tma_store_wait_read0();
+                __syncwarp();
+                const uint32_t wr = tb + (uint32_t)lane * 128u;
+                const uint32_t sw = (uint32_t)lane & 7u;
+#pragma unroll
+                for (int k = 0; k < 8; k++)
+                    sts128(wr + ((((uint32_t)k) ^ sw) << 4), v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store_2d(tm_tA, tb, c * 32, (((ti * p.tiles_j + tj) * p.E + e) << 8) + (int)rank * 128 + q * 32);
+                    tma_store_commit();
+                }
+                continue;
+            }
             if (p.tma_norm) {
                 // normal copy through the staging buffer: row r of the 32 x 32 box = voxel row c*32 + r, 128 bytes = this
                 // warp's 32 columns; lane j writes word j of every row (conflict-free) in the 128-byte TMA swizzle
@@ -669,7 +740,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(const Gemm2Params &p, uint64_
                     tma_store_2d(tm_tA, tb, (int)rank * 128 + q * 32, (((ti * p.tiles_j + tj) * p.E + e) << 8) + c * 32);
                     tma_store_commit();
                 }
-            } else if (p.debug & 32) {   // A/B: plain stores instead of streaming (evict-first) ones
+            } else if (FCMA_DBG(p, 32)) {   // A/B: plain stores instead of streaming (evict-first) ones
 #pragma unroll
                 for (int r = 0; r < 32; r++) ptr[r * 256] = __uint_as_float(v[r]);
             } else {
@@ -801,7 +872,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_MAX_THREADS, 1)
                 if (p.sym_diag && tj < ti) continue;   // symmetric mode: tile (tj, ti) is mirrored from (ti, tj)
                 const int col0 = (int)p.col_start + tj * 256 + (int)rank * 128;
                 const int row0 = (int)(p.row_start + (long)ti * p.BN + (long)rank * halfN);
-                if ((p.debug & 16) && tile != pair * p.grp_tiles) continue;   // diagnostics: MMA-only loop
+                if (FCMA_DBG(p, 16) && tile != pair * p.grp_tiles) continue;   // diagnostics: MMA-only loop
                 for (int kb = 0; kb < p.kbs; kb++) {
                     const int k0 = kb * p.bk;
                     mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -811,7 +882,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_MAX_THREADS, 1)
                         mbar_arrive_cluster(&full_bar[stage], 0);
                     uint8_t *base = tiles + (size_t)stage * p.stage_bytes;
                     uint8_t *rbase = base + p.planes * 16384;
-                    if (p.debug & 64) {   // A/B: operand loads with an L2 evict-last policy
+                    if (FCMA_DBG(p, 64)) {   // A/B: operand loads with an L2 evict-last policy
                         for (int pl = 0; pl < p.planes; pl++)
                             tma_load_3d_2sm_hint(&tm_cols, &full_bar[stage], base + pl * 16384, k0, col0, pl * p.E + e, l2pol);
                         for (int pl = 0; pl < p.planes; pl++)
@@ -853,7 +924,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_MAX_THREADS, 1)
                 const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.BN);
                 uint32_t accumulate = 0;
                 for (int kb = 0; kb < p.kbs; kb++) {
-                    const bool stale = (p.debug & 16) && iter != 1;
+                    const bool stale = FCMA_DBG(p, 16) && iter != 1;
                     if (!stale) mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
                     if (elect_one_sync()) {
@@ -960,6 +1031,25 @@ static int make_transposed_map(CUtensorMap *m, const void *base, size_t rows, in
     return FCMA_OK;
 }
 
+// tiled block [ntg tile groups][E][256 i][256 j] (fp32 or fp16) as the 5-D tensor the TMA column pass reads:
+// (j, i%4, tile group * E/4 + e/4, (i%256)/4, e%4), box = one brick (32, 4, 8, 4, 4); see k_norm_syrk_cols_tma
+static int make_cols_map(CUtensorMap *m, const void *base, size_t ntg, int E, int half_in)
+{
+    PFN_tmEncodeTiled enc = get_encode_fn();
+    if (!enc) return fail(FCMA_ECUDA, "cuTensorMapEncodeTiled entry point not available");
+    const cuuint64_t esz = half_in ? 2 : 4;
+    cuuint64_t gdim[5] = {256, 4, (cuuint64_t)ntg * (cuuint64_t)(E / 4), 64, 4};
+    cuuint64_t gstr[4] = {256 * esz, 4 * 65536 * esz, 4 * 256 * esz, 65536 * esz};
+    cuuint32_t box[5] = {32, 4, 8, 4, 4};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(m, half_in ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5,
+                     const_cast<void *>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     half_in ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(FCMA_ECUDA, "cuTensorMapEncodeTiled (column pass) failed with CUresult %d", (int)r);
+    return FCMA_OK;
+}
+
 // self-correlation fix-up: out[i][e][start+i] = exact sequential-FMA r (optionally Fisher-transformed)
 __global__ void k_self_corr_fixup(const float *__restrict__ selfdiag, int E, long V, long start, long nb, float *out,
                                   long stride_i, long stride_e, int fisher_epochs, long tiled_t256, int half_out,
@@ -1035,12 +1125,12 @@ static int launch_corr_umma(const void *rows_op, const void *cols_op, int precis
         // epilogue warps: four per TMEM lane quadrant, or two in symmetric mode (the store stream, not the epilogue's
         // issue rate, bounds that kernel, and 8 x 4 KB of transposition buffers leave room for a third smem stage:
         // 83 vs 92 ms of GEMM per step).  FCMA_GEMM_EPI_WARPS=8|16 overrides (A/B).
-        const char *ew = getenv("FCMA_GEMM_EPI_WARPS");
+        const char *ew = diag_env("FCMA_GEMM_EPI_WARPS");
         q.epi_warps = sym ? 8 : 16;
         if (ew && (atoi(ew) == 8 || atoi(ew) == 16)) q.epi_warps = atoi(ew);
-        const char *dbg = getenv("FCMA_GEMM_DEBUG");
+        const char *dbg = diag_env("FCMA_GEMM_DEBUG");
         q.debug = dbg ? atoi(dbg) : 0;
-        const char *sched = getenv("FCMA_GEMM_SCHED");       // 1: a pair takes all row tiles of a column tile in a row
+        const char *sched = diag_env("FCMA_GEMM_SCHED");       // 1: a pair takes all row tiles of a column tile in a row
         q.grp_tiles = (sched && sched[0] == '1') ? q.tiles_i : 1;
     }
     // symmetric mode: one padded 32x32 fp32 transposition buffer per epilogue warp
@@ -1049,13 +1139,13 @@ static int launch_corr_umma(const void *rows_op, const void *cols_op, int precis
         // FCMA_SYM_TR=8|16|32 selects the LDS/STG transposition in steps of that many rows instead (A/B; a smaller
         // step needs a smaller buffer but writes shorter contiguous pieces).
         q.tr_w = 0;
-        const char *tw = getenv("FCMA_SYM_TR");
+        const char *tw = diag_env("FCMA_SYM_TR");
         if (tw && (atoi(tw) == 32 || atoi(tw) == 16 || (atoi(tw) == 8 && !half_out))) q.tr_w = atoi(tw);
         q.tr_warp_bytes = q.tr_w == 0 ? (half_out ? 2048u : 4096u)
                                       : (half_out ? 32u * (2u * q.tr_w + 16u) : 32u * (q.tr_w + 4u) * 4u);
         // FCMA_GEMM_TMA_NORM=1: also the normal copy through the staging buffer + TMA bulk stores (A/B; measured neutral
         // inside the power-capped step: 58.8-59.7 vs 60.3 ms of GEMM per step, so the plain streaming stores stay)
-        const char *tn = getenv("FCMA_GEMM_TMA_NORM");
+        const char *tn = diag_env("FCMA_GEMM_TMA_NORM");
         q.tma_norm = (q.tr_w == 0 && !half_out && tn && tn[0] == '1') ? 1 : 0;
     }
     const size_t tr_bytes = !sym ? 0 : (size_t)q.epi_warps * q.tr_warp_bytes;
@@ -1063,7 +1153,7 @@ static int launch_corr_umma(const void *rows_op, const void *cols_op, int precis
     int stages = (int)(cap / q.stage_bytes);
     if (stages > GEMM_MAX_STAGES) stages = GEMM_MAX_STAGES;
     {
-        const char *sg = getenv("FCMA_GEMM_STAGES");         // A/B: cap the number of smem stages
+        const char *sg = diag_env("FCMA_GEMM_STAGES");         // A/B: cap the number of smem stages
         if (sg && atoi(sg) >= 2 && atoi(sg) < stages) stages = atoi(sg);
     }
     if (stages < 2) return fail(FCMA_EINVAL, "internal: not enough shared memory for 2 stages");
@@ -2023,6 +2113,271 @@ __global__ void __launch_bounds__(32 * (32 / CPW), 1)
     }
 }
 
+// ============================================================================================
+// Column-direction pass, TMA version (default when E % 4 == 0): same arithmetic as k_norm_syrk_cols, but
+//   * a brick [32 epochs][16 rows][32 columns] arrives through ONE 5-D bulk tensor copy (UTMALDG) issued by one elected
+//     lane -- the 4096 LDGSTS per brick (8 LSU cycles each, the same port the LDS reads need) and their address
+//     arithmetic are gone;
+//   * bricks live in a 3-slot ring guarded by full/empty mbarriers: a warp waits for ITS brick and releases it when
+//     it is done, so warps run up to a brick apart instead of meeting at a bar.sync every 64 KB.
+// The tiled block [tile group][E][256 i][256 j] is described to TMA as a 5-D tensor whose dimension ORDER is chosen
+// for the reader, not for memory:   (j, i%4, tile group * E/4 + e/4, (i%256)/4, e%4)   with box (32, 4, 8, 4, 4).
+// Shared-memory line L = i%4 + 4*(e/4) + 32*(i/4 %4) + 128*(e%4) then lands at L*128 with the hardware 128-byte
+// swizzle (16-byte piece ^ (L & 7)).  Lane (g, t) of the mma fragment layout takes epochs 4g .. 4g+3 and rows
+// {t, t+4, t+8, t+12} (which rows a k-slot stands for is irrelevant to a sum over rows, as long as every lane uses the
+// same mapping), so the eight lanes of an LDS.128 phase (g in {2h, 2h+1}, t in 0..3) read lines with eight different
+// L & 7 = t + 4 (g & 1): conflict-free without a custom swizzle.  Offsets of (epoch r, row slot sl) are multiples of
+// 4 KB: immediate operands.  Rows >= n of a ragged last row tile hold stale scratch: masked after the load.
+// Epochs [E, 32) of the box belong to the next tile group (or are zero-filled beyond the tensor): they only reach
+// accumulator rows / columns >= E, which are never written back.
+// HALF: fp16 block, 64-byte lines, 64-byte swizzle, LDS.64 (two-way conflicts as in the cp.async version).
+// ============================================================================================
+template <int EPS, bool HALF>
+__global__ void __launch_bounds__(256, 1)
+    k_norm_syrk_cols_tma(const __grid_constant__ CUtensorMap tmA, long n, int E, long n2, long T256, long c0, float *K)
+{
+    constexpr int R = 4, EP = 32, MT = 2, NT = 4, CPW = 4, NTHR = 256;
+    constexpr uint32_t BRICK = HALF ? 32768u : 65536u;
+    constexpr uint32_t RING_BYTES = 196608u;   // 3 fp32 bricks; the fold buffer [32 columns][EP*EP] fp32 (128 KB) overlays it
+    extern __shared__ __align__(1024) uint8_t cs_raw[];
+    uint8_t *cs = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(cs_raw) + 1023) & ~uintptr_t(1023));
+    const uint32_t brick0 = smem_u32(cs);
+    float *s_fold = reinterpret_cast<float *>(cs);
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(cs + RING_BYTES);   // [3]
+    uint64_t *empty_bar = full_bar + COLS_BRICKS;                          // [3]
+    const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int S_eps = (E / EPS) * EPS;
+    const int e4 = E >> 2;
+    const long nstrips = (n2 - c0 + 31) / 32;
+    const long nsteps = (n + 15) / 16;
+
+    if (tid == 0) {
+        tma_prefetch_desc(&tmA);
+        for (int b = 0; b < COLS_BRICKS; b++) {
+            mbar_init(&full_bar[b], 1);
+            mbar_init(&empty_bar[b], NTHR / 32);
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    // this lane's reads: line L0 = t + 4g (+ 32 sl + 128 r), 16-byte piece `warp` (fp32) / 8 bytes of piece warp/2 (fp16)
+    const uint32_t L0 = (uint32_t)(t + 4 * g);
+    const uint32_t rd_base = HALF ? L0 * 64u + ((((uint32_t)warp >> 1) ^ ((L0 >> 1) & 3u)) << 4) + ((uint32_t)warp & 1u) * 8u
+                                  : L0 * 128u + ((((uint32_t)warp) ^ (L0 & 7u)) << 4);
+    constexpr uint32_t SL_STEP = HALF ? 2048u : 4096u, R_STEP = HALF ? 8192u : 16384u;
+
+    uint32_t it = 0;          // running brick count of this CTA: slot = it % 3, use = it / 3
+    uint32_t slot = 0, par = 0;   // slot / parity of brick `it`
+    for (long strip = blockIdx.x; strip < nstrips; strip += gridDim.x) {
+        const long j0 = c0 + strip * 32;
+        const int tjx = (int)(j0 >> 8), jo = (int)(j0 & 255);
+        // producer (one elected lane of warp 0): brick of row step st -> ring position idx
+        auto issue = [&](long st, uint32_t idx) {
+            const uint32_t sl = idx % COLS_BRICKS, use = idx / COLS_BRICKS;
+            mbar_wait(&empty_bar[sl], (use & 1u) ^ 1u);       // every warp has released the slot's previous brick
+            mbar_expect_tx(&full_bar[sl], BRICK);
+            const long i0 = st * 16;
+            tma_load_5d(&tmA, &full_bar[sl], brick0 + sl * BRICK, jo, 0, (int)(((i0 >> 8) * T256 + tjx) * e4),
+                        (int)((i0 & 255) >> 2), 0);
+        };
+        for (long seg0 = 0; seg0 < nsteps; seg0 += COLS_SEG_STEPS) {
+            const long seg1 = seg0 + COLS_SEG_STEPS < nsteps ? seg0 + COLS_SEG_STEPS : nsteps;
+            float acc[CPW][MT][NT][4];
+#pragma unroll
+            for (int c = 0; c < CPW; c++)
+#pragma unroll
+                for (int a = 0; a < MT; a++)
+#pragma unroll
+                    for (int b = 0; b < NT; b++)
+#pragma unroll
+                        for (int d = 0; d < 4; d++) acc[c][a][b][d] = 0.f;
+            if (warp == 0) {
+                if (elect_one_sync()) {
+                    issue(seg0, it);
+                    if (seg0 + 1 < seg1) issue(seg0 + 1, it + 1);
+                }
+                __syncwarp();
+            }
+            for (long st = seg0; st < seg1; st++) {
+                if (warp == 0) {
+                    if (st + 2 < seg1 && elect_one_sync()) issue(st + 2, it + 2);
+                    __syncwarp();
+                }
+                mbar_wait(&full_bar[slot], par);
+                // ---- this lane's 4 epochs x 4 rows x 4 columns
+                float vals[R][4][CPW];
+                const uint32_t bb = brick0 + slot * BRICK + rd_base;
+#pragma unroll
+                for (int r = 0; r < R; r++)
+#pragma unroll
+                    for (int sl = 0; sl < 4; sl++) {
+                        if constexpr (HALF) {
+                            const uint2 q = lds64(bb + (uint32_t)sl * SL_STEP + (uint32_t)r * R_STEP);
+                            const float2 lo = __half22float2(*reinterpret_cast<const __half2 *>(&q.x));
+                            const float2 hi = __half22float2(*reinterpret_cast<const __half2 *>(&q.y));
+                            vals[r][sl][0] = lo.x, vals[r][sl][1] = lo.y, vals[r][sl][2] = hi.x, vals[r][sl][3] = hi.y;
+                        } else {
+                            const uint4 q = lds128(bb + (uint32_t)sl * SL_STEP + (uint32_t)r * R_STEP);
+                            vals[r][sl][0] = __uint_as_float(q.x), vals[r][sl][1] = __uint_as_float(q.y);
+                            vals[r][sl][2] = __uint_as_float(q.z), vals[r][sl][3] = __uint_as_float(q.w);
+                        }
+                    }
+                // the brick is in registers: hand the slot back to the producer
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty_bar[slot]);
+                if (st * 16 + 16 > n) {   // ragged last row step (block-uniform): rows >= n hold stale scratch
+#pragma unroll
+                    for (int sl = 0; sl < 4; sl++)
+                        if (st * 16 + 4 * sl + t >= n) {
+#pragma unroll
+                            for (int r = 0; r < R; r++)
+#pragma unroll
+                                for (int c = 0; c < CPW; c++) vals[r][sl][c] = 0.f;
+                        }
+                }
+                // ---- within-subject z-score per (row, column): statistics over the EPS epochs of a subject
+                auto finish = [&](float2 msum, float2 s2sum, float2 &inv, float2 &mi) {
+                    const float2 nm = ffma2(msum, splat2(-1.0f / EPS), splat2(0.f));
+                    const float2 ns2 = ffma2(s2sum, splat2(-1.0f / EPS), splat2(0.f));
+                    const float2 negvar = ffma2(nm, nm, ns2);
+                    inv.x = negvar.x >= 0.f ? 0.f : rsqrt_ftz(-negvar.x);
+                    inv.y = negvar.y >= 0.f ? 0.f : rsqrt_ftz(-negvar.y);
+                    mi = ffma2(nm, inv, splat2(0.f));
+                };
+                if constexpr (EPS <= R) {
+                    constexpr int G = R / EPS;
+#pragma unroll
+                    for (int q = 0; q < G; q++) {
+                        const bool valid = R * g + q * EPS < S_eps;
+#pragma unroll
+                        for (int sl = 0; sl < 4; sl++)
+#pragma unroll
+                            for (int u = 0; u < CPW; u += 2) {
+                                float2 m = splat2(0.f), s2 = splat2(0.f);
+#pragma unroll
+                                for (int b = 0; b < EPS; b++) {
+                                    const float2 x = make_float2(vals[q * EPS + b][sl][u], vals[q * EPS + b][sl][u + 1]);
+                                    m = ffma2(x, splat2(1.f), m);
+                                    s2 = ffma2(x, x, s2);
+                                }
+                                float2 inv, mi;
+                                finish(m, s2, inv, mi);
+                                if (valid) {
+#pragma unroll
+                                    for (int b = 0; b < EPS; b++) {
+                                        const float2 z = ffma2(make_float2(vals[q * EPS + b][sl][u], vals[q * EPS + b][sl][u + 1]), inv, mi);
+                                        vals[q * EPS + b][sl][u] = z.x, vals[q * EPS + b][sl][u + 1] = z.y;
+                                    }
+                                }
+                            }
+                    }
+                } else {
+                    constexpr int L = EPS / R;   // adjacent g-lanes per subject
+                    const bool valid = R * g < S_eps;
+#pragma unroll
+                    for (int sl = 0; sl < 4; sl++)
+#pragma unroll
+                        for (int u = 0; u < CPW; u += 2) {
+                            float2 m = splat2(0.f), s2 = splat2(0.f);
+#pragma unroll
+                            for (int r = 0; r < R; r++) {
+                                const float2 x = make_float2(vals[r][sl][u], vals[r][sl][u + 1]);
+                                m = ffma2(x, splat2(1.f), m);
+                                s2 = ffma2(x, x, s2);
+                            }
+#pragma unroll
+                            for (int o = 1; o < L; o <<= 1) {
+                                m.x += __shfl_xor_sync(0xffffffffu, m.x, 4 * o);
+                                m.y += __shfl_xor_sync(0xffffffffu, m.y, 4 * o);
+                                s2.x += __shfl_xor_sync(0xffffffffu, s2.x, 4 * o);
+                                s2.y += __shfl_xor_sync(0xffffffffu, s2.y, 4 * o);
+                            }
+                            float2 inv, mi;
+                            finish(m, s2, inv, mi);
+                            if (valid) {
+#pragma unroll
+                                for (int r = 0; r < R; r++) {
+                                    const float2 z = ffma2(make_float2(vals[r][sl][u], vals[r][sl][u + 1]), inv, mi);
+                                    vals[r][sl][u] = z.x, vals[r][sl][u + 1] = z.y;
+                                }
+                            }
+                        }
+                }
+                // ---- K_j += Z Z^T: k-slots (2t, 2t+1) <-> row slots 0, 1 and (2t+8, 2t+9) <-> row slots 2, 3
+#pragma unroll
+                for (int c = 0; c < CPW; c++) {
+                    uint32_t h0[R], h1[R];
+#pragma unroll
+                    for (int r = 0; r < R; r++) {
+                        h0[r] = pack_half2_rn(vals[r][0][c], vals[r][1][c]);
+                        h1[r] = pack_half2_rn(vals[r][2][c], vals[r][3][c]);
+                    }
+#pragma unroll
+                    for (int mu = 0; mu < MT; mu++)
+#pragma unroll
+                        for (int nu = 0; nu < NT; nu++)
+                            mma_f16_16x8x16(acc[c][mu][nu], h0[2 * mu], h0[2 * mu + 1], h1[2 * mu], h1[2 * mu + 1], h0[nu], h1[nu]);
+                }
+                it++;
+                if (++slot == COLS_BRICKS) slot = 0, par ^= 1u;
+            }
+            // ---- fold the accumulators into K: registers -> smem [32 columns][EP*EP] -> mirrored, coalesced += on K.
+            // Every brick of the segment has been consumed (no bulk copy is in flight), all warps are past their reads.
+            __syncthreads();
+#pragma unroll
+            for (int c = 0; c < CPW; c++) {
+                float *dstk = s_fold + (size_t)(warp * CPW + c) * (EP * EP);
+#pragma unroll
+                for (int mu = 0; mu < MT; mu++)
+#pragma unroll
+                    for (int nu = 0; nu < NT; nu++) {
+                        const int row0 = R * g + 2 * mu, row1 = row0 + 1;
+                        const int col0 = R * (2 * t) + nu, col1 = R * (2 * t + 1) + nu;
+                        dstk[row0 * EP + col0] = acc[c][mu][nu][0];
+                        dstk[row0 * EP + col1] = acc[c][mu][nu][1];
+                        dstk[row1 * EP + col0] = acc[c][mu][nu][2];
+                        dstk[row1 * EP + col1] = acc[c][mu][nu][3];
+                    }
+            }
+            __syncthreads();
+            const int EE = E * E;
+            const long ncols = n2 - j0 < 32 ? n2 - j0 : 32;       // real columns of this strip
+            const int total = (int)ncols * EE;
+            float *Kst = K + (size_t)j0 * EE;                     // the strip's kernels are contiguous
+            auto folded = [&](int idx) {
+                const int col = idx / EE, rem = idx - col * EE;
+                const int a = rem / E, b = rem - a * E;
+                const float *sk = s_fold + (size_t)col * (EP * EP);
+                return a >= b ? sk[a * EP + b] : sk[b * EP + a];
+            };
+            // E % 4 == 0 here, and K + j0*E*E is 16-byte aligned whenever K is: 16-byte read-modify-write, 8 loads in flight
+            float4 *K4 = reinterpret_cast<float4 *>(Kst);
+            const int total4 = total >> 2;
+            for (int base = tid; base < total4; base += NTHR * 8) {
+                float4 old[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const int i4 = base + u * NTHR;
+                    if (i4 < total4) old[u] = K4[i4];
+                }
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const int i4 = base + u * NTHR;
+                    if (i4 < total4) {
+                        float4 o = old[u];
+                        o.x += folded(4 * i4), o.y += folded(4 * i4 + 1), o.z += folded(4 * i4 + 2), o.w += folded(4 * i4 + 3);
+                        K4[i4] = o;
+                    }
+                }
+            }
+            fence_proxy_async_smem();   // the fold's generic-proxy smem accesses are ordered before the next bulk copies
+            __syncthreads();
+        }
+    }
+}
+
 __global__ void k_scale(float *x, long n, float s)
 {
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
@@ -2124,16 +2479,47 @@ static int launch_norm_syrk(const float *C, long nb, int E, long n2, long stride
 // column-direction pass over a tiled fp32 block (k_norm_syrk_cols): K[j] += ... for block columns [c0, n2)
 static bool cols_supported(int E, int eps) { return E <= 32 && eps >= 1 && eps <= 32 && (eps & (eps - 1)) == 0; }
 static int launch_norm_syrk_cols(const void *A, long n, int E, long n2, long T256, long c0, int eps, float *K,
-                                 cudaStream_t st, int half_in = 0)
+                                 cudaStream_t st, int half_in = 0, bool force_ldgsts = false)
 {
     if (!cols_supported(E, eps) || (c0 & 31) || c0 >= n2) return fail(FCMA_EINVAL, "internal: column pass unsupported E=%d eps=%d c0=%ld", E, eps, c0);
     const long nstrips = cdiv(n2 - c0, 32);
     const unsigned grid = (unsigned)(nstrips < g_sm_count ? nstrips : g_sm_count);
+    // TMA-fed bricks + mbarrier ring (k_norm_syrk_cols_tma) whenever the block can be described to TMA (E a multiple of
+    // 4) and K allows 16-byte read-modify-writes; FCMA_COLS_TMA=0 (diagnostic build) forces the cp.async kernel (A/B)
+    const char *ct_env = diag_env("FCMA_COLS_TMA");
+    if ((E & 3) == 0 && ((uintptr_t)K & 15) == 0 && ((uintptr_t)A & 15) == 0 && !(ct_env && ct_env[0] == '0') && !force_ldgsts) {
+        CUtensorMap tmA;
+        int rc = make_cols_map(&tmA, A, (size_t)cdiv(n, 256) * (size_t)T256, E, half_in);
+        if (rc) return rc;
+        const size_t smem_t = 196608 + 64 + 1024;
+#define FCMA_COLS_TMA_CASE(EPSV)                                                                                    \
+    case EPSV:                                                                                                      \
+        if (half_in) {                                                                                              \
+            CUDA_TRY(cudaFuncSetAttribute(k_norm_syrk_cols_tma<EPSV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t)); \
+            k_norm_syrk_cols_tma<EPSV, true><<<grid, 256, smem_t, st>>>(tmA, n, E, n2, T256, c0, K);                \
+        } else {                                                                                                    \
+            CUDA_TRY(cudaFuncSetAttribute(k_norm_syrk_cols_tma<EPSV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t)); \
+            k_norm_syrk_cols_tma<EPSV, false><<<grid, 256, smem_t, st>>>(tmA, n, E, n2, T256, c0, K);               \
+        }                                                                                                           \
+        break;
+        switch (eps) {
+            FCMA_COLS_TMA_CASE(1)
+            FCMA_COLS_TMA_CASE(2)
+            FCMA_COLS_TMA_CASE(4)
+            FCMA_COLS_TMA_CASE(8)
+            FCMA_COLS_TMA_CASE(16)
+            FCMA_COLS_TMA_CASE(32)
+        default: return fail(FCMA_EINVAL, "internal: no k_norm_syrk_cols_tma instantiation for eps=%d", eps);
+        }
+#undef FCMA_COLS_TMA_CASE
+        LAUNCH_CHECK("k_norm_syrk_cols_tma");
+        return FCMA_OK;
+    }
     // bricks (3 x 64 KB fp32 / 3 x 32 KB fp16); the fold buffer [32 columns][32*32] fp32 = 128 KB overlays them
     const size_t smem = (half_in ? (size_t)131072 : (size_t)COLS_BRICKS * 65536) + 1024;
     // 4 columns per warp (8 warps, 255 registers) by default; FCMA_COLS_CPW=2 selects 2 columns per warp (16 warps at 128
     // registers: measured 7 % slower -- 80 bytes of spills and two-way conflicts on the 8-byte LDS outweigh the occupancy)
-    const char *cpw_env = getenv("FCMA_COLS_CPW");
+    const char *cpw_env = diag_env("FCMA_COLS_CPW");
     const bool cpw4 = !(cpw_env && cpw_env[0] == '2');
 #define FCMA_COLS_CASE(EPSV)                                                                                        \
     case EPSV:                                                                                                      \
@@ -2177,11 +2563,13 @@ extern "C" int fcma_pack_operand(const float *epochs_dev, int E, int T, long V, 
     size_t need = fcma_operand_bytes(precision, E, T, V);
     if (packed_bytes < need) return fail(FCMA_ENOMEM, "packed operand buffer too small: %zu < %zu", packed_bytes, need);
     cudaStream_t st = (cudaStream_t)stream;
+    AsyncBuf te_buf;
     int *d_Te = nullptr;
     if (T_e) {
         for (int e = 0; e < E; e++)
             if (T_e[e] <= 0 || T_e[e] > T) return fail(FCMA_EINVAL, "epoch %d has length %d outside (0, %d]", e, T_e[e], T);
-        CUDA_TRY(cudaMallocAsync(&d_Te, sizeof(int) * E, st));
+        CUDA_TRY(te_buf.alloc(sizeof(int) * E, st));
+        d_Te = static_cast<int *>(te_buf.p);
         CUDA_TRY(cudaMemcpyAsync(d_Te, T_e, sizeof(int) * E, cudaMemcpyHostToDevice, st));
     }
     const int Kp = fcma_operand_kp(precision, T);
@@ -2193,8 +2581,7 @@ extern "C" int fcma_pack_operand(const float *epochs_dev, int E, int T, long V, 
     if (pi.pack == 1 && pi.planes == 2) k_pack_operand<1, 2><<<grid, 256, 0, st>>>(epochs_dev, E, T, V, ld, d_Te, normalize, packed_dev, Kp, sd, pi.in_scale);
     if (pi.pack == 2 && pi.planes == 2) k_pack_operand<2, 2><<<grid, 256, 0, st>>>(epochs_dev, E, T, V, ld, d_Te, normalize, packed_dev, Kp, sd, pi.in_scale);
     LAUNCH_CHECK("k_pack_operand");
-    if (d_Te) CUDA_TRY(cudaFreeAsync(d_Te, st));
-    return FCMA_OK;
+    return FCMA_OK;   // te_buf is released in stream order by its destructor
 }
 
 extern "C" int fcma_epoch_normalize(float *epochs_dev, int E, int T, long V, long ld, const int *T_e, void *stream)
@@ -2203,15 +2590,16 @@ extern "C" int fcma_epoch_normalize(float *epochs_dev, int E, int T, long V, lon
     if (rc) return rc;
     if (!epochs_dev || E <= 0 || T <= 0 || V <= 0 || ld < V) return fail(FCMA_EINVAL, "fcma_epoch_normalize: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
+    AsyncBuf te_buf;
     int *d_Te = nullptr;
     if (T_e) {
-        CUDA_TRY(cudaMallocAsync(&d_Te, sizeof(int) * E, st));
+        CUDA_TRY(te_buf.alloc(sizeof(int) * E, st));
+        d_Te = static_cast<int *>(te_buf.p);
         CUDA_TRY(cudaMemcpyAsync(d_Te, T_e, sizeof(int) * E, cudaMemcpyHostToDevice, st));
     }
     dim3 grid((unsigned)cdiv(V, 32), (unsigned)E);
     k_epoch_normalize<<<grid, 256, 0, st>>>(epochs_dev, T, V, ld, d_Te);
     LAUNCH_CHECK("k_epoch_normalize");
-    if (d_Te) CUDA_TRY(cudaFreeAsync(d_Te, st));
     return FCMA_OK;
 }
 
@@ -2357,16 +2745,17 @@ static int run_pipeline(const void *rows_op, const void *cols_op, int precision,
     // (row block, column block) are adjacent, so the fused normalise+SYRK kernel reads row i as E runs of 1 KB,
     // 256 KB apart, inside one 8 MB region.  Needs the TMA-store epilogue and whole 256-row blocks of workspace.
     // FCMA_NO_TILED=1 falls back to the strided [i][e][j] block.
-    const char *no_tiled = getenv("FCMA_NO_TILED");
+    const char *no_tiled = diag_env("FCMA_NO_TILED");
     const long t256 = cdiv(V2, 256);
-    const bool tiled = !(no_tiled && no_tiled[0] == '1') && fused && V2 < (1L << 31) && rows_per_pass >= 256;
+    const bool tiled = !(no_tiled && no_tiled[0] == '1') && !(flags & FCMA_FLAG_STRIDED_BLOCK) && fused &&
+                       V2 < (1L << 31) && rows_per_pass >= 256;
     // fp16 intermediate (FCMA_FLAG_F16_INTERMEDIATE, and by default in the single-product reduced-precision operand
     // modes bf16 / tf32): the tiled block holds Fisher-z values rounded to fp16.  Their rounding errors
     // are independent across the V2 columns the kernel matrix sums over: measured max|dK|/max|K| = 1.5e-5 at
     // V2 = 50 000 (the reference's own fp32 ssyrk rounding noise is 1e-5), while both kernels move half the
     // bytes (-8..12 % per step).  The fp32-faithful modes keep an fp32 block unless the flag asks otherwise;
     // correlation values returned by fcma_corr_block are never rounded.  FCMA_F16_INTERMEDIATE=0|1 overrides (A/B).
-    const char *f16i = getenv("FCMA_F16_INTERMEDIATE");
+    const char *f16i = diag_env("FCMA_F16_INTERMEDIATE");
     const bool reduced = precision == FCMA_PREC_BF16 || precision == FCMA_PREC_TF32;
     bool half16 = (flags & FCMA_FLAG_F16_INTERMEDIATE) || reduced;
     if (f16i && (f16i[0] == '0' || f16i[0] == '1')) half16 = f16i[0] == '1';
@@ -2374,9 +2763,10 @@ static int run_pipeline(const void *rows_op, const void *cols_op, int precision,
     for (long done = 0; done < nb; done += rows_per_pass) {
         const long n = nb - done < rows_per_pass ? nb - done : rows_per_pass;
         int rc;
-        cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+        EventSet<3> evs;
+        cudaEvent_t *ev = evs.ev;
         if (g_timing_on) {
-            for (int k = 0; k < 3; k++) CUDA_TRY(cudaEventCreate(&ev[k]));
+            CUDA_TRY(evs.create());
             CUDA_TRY(cudaEventRecord(ev[0], st));
         }
         if (tiled)
@@ -2421,7 +2811,6 @@ static int run_pipeline(const void *rows_op, const void *cols_op, int precision,
             CUDA_TRY(cudaEventElapsedTime(&a, ev[0], ev[1]));
             CUDA_TRY(cudaEventElapsedTime(&b, ev[1], ev[2]));
             g_t_gemm += a, g_t_syrk += b, g_t_passes++;
-            for (int k = 0; k < 3; k++) cudaEventDestroy(ev[k]);
         }
     }
     return FCMA_OK;
@@ -2440,13 +2829,13 @@ static int run_pipeline(const void *rows_op, const void *cols_op, int precision,
 // (E <= 32, power-of-two eps <= 32; fp32 or fp16 block), 0 = transposed block B + row pass
 static bool sym_uses_cols(int precision, int E, int eps, int flags)
 {
-    const char *f16i = getenv("FCMA_F16_INTERMEDIATE");
+    const char *f16i = diag_env("FCMA_F16_INTERMEDIATE");
     bool half16 = (flags & FCMA_FLAG_F16_INTERMEDIATE) || precision == FCMA_PREC_BF16 || precision == FCMA_PREC_TF32;
     if (f16i && (f16i[0] == '0' || f16i[0] == '1')) half16 = f16i[0] == '1';
-    const char *sc = getenv("FCMA_SYM_COLS");
-    if (sc && sc[0] == '0') return false;
+    const char *sc = diag_env("FCMA_SYM_COLS");
+    if ((sc && sc[0] == '0') || (flags & FCMA_FLAG_SYM_TRANSPOSED)) return false;
     if (half16) {   // fp16 block: FCMA_SYM_COLS_F16=0 keeps the transposed copy + row pass (A/B)
-        const char *sh = getenv("FCMA_SYM_COLS_F16");
+        const char *sh = diag_env("FCMA_SYM_COLS_F16");
         if (sh && sh[0] == '0') return false;
     }
     return cols_supported(E, eps);
@@ -2470,7 +2859,7 @@ static int run_pipeline_sym(const void *op, int precision, int E, int T, long V,
     const bool mask_self = (flags & FCMA_FLAG_MASK_SELF) != 0;
     const int S_eps = (E / eps) * eps;
     // fp16 Fisher-z block: same rule as the plain pipeline (flag, or the single-product operand modes)
-    const char *f16i = getenv("FCMA_F16_INTERMEDIATE");
+    const char *f16i = diag_env("FCMA_F16_INTERMEDIATE");
     bool half16 = (flags & FCMA_FLAG_F16_INTERMEDIATE) || precision == FCMA_PREC_BF16 || precision == FCMA_PREC_TF32;
     if (f16i && (f16i[0] == '0' || f16i[0] == '1')) half16 = f16i[0] == '1';
     const size_t esz = half16 ? sizeof(__half) : sizeof(float);
@@ -2491,9 +2880,10 @@ static int run_pipeline_sym(const void *op, int precision, int E, int T, long V,
         float *B = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(work) + (size_t)nt * t256 * E * 65536 * esz);
         if ((size_t)((nt * t256 + (use_cols ? 0 : (t256 - nt) * nt)) * E) * 65536 * esz > work_bytes)
             return fail(FCMA_ENOMEM, "internal: symmetric pass does not fit the work buffer");
-        cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+        EventSet<4> evs;
+        cudaEvent_t *ev = evs.ev;
         if (g_timing_on) {
-            for (int k = 0; k < 4; k++) CUDA_TRY(cudaEventCreate(&ev[k]));
+            CUDA_TRY(evs.create());
             CUDA_TRY(cudaEventRecord(ev[0], st));
         }
         SymOut so{use_cols ? nullptr : B};
@@ -2505,7 +2895,8 @@ static int run_pipeline_sym(const void *op, int precision, int E, int T, long V,
         if (rc) return rc;
         if (g_timing_on) CUDA_TRY(cudaEventRecord(ev[3], st));
         if (rowsB > 0 && use_cols) {
-            rc = launch_norm_syrk_cols(A, n, E, colsA, t256, n, eps, K + (size_t)a * E * E, st, half16 ? 1 : 0);
+            rc = launch_norm_syrk_cols(A, n, E, colsA, t256, n, eps, K + (size_t)a * E * E, st, half16 ? 1 : 0,
+                                       (flags & FCMA_FLAG_COLS_LDGSTS) != 0);
             if (rc) return rc;
         } else if (rowsB > 0) {
             rc = launch_norm_syrk(B, rowsB, E, n, 256, 65536, eps, 1, -1, 1.0f, K + (size_t)(a + n) * E * E, 0, st,
@@ -2520,7 +2911,6 @@ static int run_pipeline_sym(const void *op, int precision, int E, int T, long V,
             CUDA_TRY(cudaEventElapsedTime(&y, ev[1], ev[2]));
             CUDA_TRY(cudaEventElapsedTime(&z, ev[3], ev[2]));
             g_t_gemm += x, g_t_syrk += y, g_t_syrk2 += z, g_t_passes++;
-            for (int k = 0; k < 4; k++) cudaEventDestroy(ev[k]);
         }
     }
     return FCMA_OK;
@@ -2912,8 +3302,9 @@ extern "C" int fcma_svm_cv_precomputed(const float *K_dev, long nv, int E, int n
             if (fh[f].test_idx[k] < 0 || fh[f].test_idx[k] >= E) return fail(FCMA_EINVAL, "fold %d: bad test index", f);
     }
     cudaStream_t st = (cudaStream_t)stream;
-    SvmFold *fd = nullptr;
-    CUDA_TRY(cudaMallocAsync(&fd, sizeof(SvmFold) * nfolds, st));
+    AsyncBuf fd_buf;
+    CUDA_TRY(fd_buf.alloc(sizeof(SvmFold) * nfolds, st));
+    SvmFold *fd = static_cast<SvmFold *>(fd_buf.p);
     CUDA_TRY(cudaMemcpyAsync(fd, fh, sizeof(SvmFold) * nfolds, cudaMemcpyHostToDevice, st));
     const size_t smem = (size_t)4 * 64 * 64 * sizeof(float);
     CUDA_TRY(cudaFuncSetAttribute(k_svm_cv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -2921,7 +3312,6 @@ extern "C" int fcma_svm_cv_precomputed(const float *K_dev, long nv, int E, int n
     k_svm_cv<<<(unsigned)cdiv(nprob, 4), 128, smem, st>>>(K_dev, nv, E, nfolds, fd, C, tol, max_iter, correct_dev,
                                                          iters_dev);
     LAUNCH_CHECK("k_svm_cv");
-    CUDA_TRY(cudaFreeAsync(fd, st));
     return FCMA_OK;
 }
 
@@ -2941,6 +3331,7 @@ extern "C" int fcma_host_voxel_kernels(const float *const *raw_host, const float
 {
     if (!raw_host || !T_e || !K_host || E <= 0 || V <= 0 || nb <= 0) return fail(FCMA_EINVAL, "fcma_host_voxel_kernels: bad arguments");
     if (fcma_device_count() == 0) return fail(FCMA_ENODEV, "no sm_100 device");
+    DeviceGuard guard;   // the caller's current device is restored on every return path
     CUDA_TRY(cudaSetDevice(device));
     int rc = check_device();
     if (rc) return rc;
@@ -3001,6 +3392,7 @@ extern "C" int fcma_host_within_subject_norm(float *corr_host, long n0, int E, l
 {
     if (!corr_host || n0 <= 0 || E <= 0 || n2 <= 0) return fail(FCMA_EINVAL, "fcma_host_within_subject_norm: bad shape");
     if (fcma_device_count() == 0) return fail(FCMA_ENODEV, "no sm_100 device");
+    DeviceGuard guard;
     CUDA_TRY(cudaSetDevice(device));
     DevBuf d;
     size_t bytes = (size_t)n0 * E * n2 * sizeof(float);

@@ -95,6 +95,19 @@ __device__ __forceinline__ void tma_load_3d(const CUtensorMap *m, uint64_t *bar,
         : "memory");
 }
 
+// 5-D tiled load global -> shared (column-direction pass: one bulk copy per [32 epochs][16 rows][32 columns] brick)
+__device__ __forceinline__ void tma_load_5d(const CUtensorMap *m, uint64_t *bar, uint32_t smem_dst, int c0, int c1,
+                                            int c2, int c3, int c4)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        :
+        : "r"(smem_dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3),
+          "r"(c4)
+        : "memory");
+}
+
 // ---------------------------------------------------------------- tcgen05 / TMEM
 __device__ __forceinline__ void tmem_alloc(uint32_t *smem_dst, uint32_t ncols)
 {

@@ -355,9 +355,13 @@ def row_normalize_(x, nan_to_zero=True):
 
 
 def host_voxel_kernels(raw_data, raw_data2, start, nb, eps, precision=_PREC_DEFAULT, normalize=False,
-                       flags=0, device=0):
-    """The C-ABI host entry point: numpy in, numpy out, all copies inside the call."""
+                       flags=0, device=None):
+    """The C-ABI host entry point: numpy in, numpy out, all copies inside the call.  ``device`` defaults to the
+    calling thread's current CUDA device (LOCAL_RANK's GPU in a rank process); the library restores the caller's
+    current device before it returns."""
     lib = _lib.load()
+    if device is None:
+        device = torch.cuda.current_device() if torch.cuda.is_available() else 0
     E = len(raw_data)
     V = raw_data[0].shape[1]
     keep = [np.ascontiguousarray(m, dtype=np.float32) for m in raw_data]

@@ -15,8 +15,12 @@ def compute_correlation(matrix1, matrix2, return_nans=False):
     a C-contiguous float32 ``[r1, r2]`` array.  Raises ``ValueError('Dimension discrepancy')``.
     """
     import torch
-    matrix1 = np.asarray(matrix1).astype(np.float32)
-    matrix2 = np.asarray(matrix2).astype(np.float32)
+    # self-correlation is decided on the caller's objects, BEFORE the float32 copies below (which never alias)
+    a1, a2 = np.asarray(matrix1), np.asarray(matrix2)
+    same = matrix2 is matrix1 or (a1.shape == a2.shape and a1.dtype == a2.dtype and a1.strides == a2.strides
+                                  and a1.size > 0 and a1.__array_interface__['data'][0] == a2.__array_interface__['data'][0])
+    matrix1 = a1.astype(np.float32)
+    matrix2 = matrix1 if same else a2.astype(np.float32)
     [r1, d1] = matrix1.shape
     [r2, d2] = matrix2.shape
     if d1 != d2:
@@ -24,7 +28,6 @@ def compute_correlation(matrix1, matrix2, return_nans=False):
     _lib.load()
     _lib.require_device()
     dev = torch.device("cuda", torch.cuda.current_device())
-    same = matrix2 is matrix1 or (matrix1.shape == matrix2.shape and np.shares_memory(matrix1, matrix2))
     m1 = torch.from_numpy(np.ascontiguousarray(matrix1)).to(dev)
     engine.row_normalize_(m1, nan_to_zero=not return_nans)
     if same:

@@ -126,6 +126,12 @@ class VoxelSelector:
             raise ValueError("unknown precision %r" % (precision,))
         self.precision = precision
         self.mask_self = bool(mask_self)
+        if self.mask_self and (raw_data2 is not None
+                               or not engine.fused_supported(len(raw_data), int(epochs_per_subj))):
+            # the self column only exists with one mask, and it is zeroed inside the fused normalise+kernel kernels
+            # (E <= 64, power-of-two epochs_per_subj): refuse loudly instead of returning unmasked results
+            raise ValueError('mask_self=True needs a single mask (raw_data2 is None), at most 64 epochs and a '
+                             'power-of-two epochs_per_subj')
         self.normalize = bool(normalize)
         self.device = device
         self.block_rows = block_rows
@@ -190,6 +196,7 @@ class VoxelSelector:
         return self._rows_op, self._cols_op
 
     def _flags(self, fused):
+        # __init__ guarantees that mask_self implies one mask and the fused path
         return _lib.FLAG_MASK_SELF if (self.mask_self and self.raw_data2 is None and fused) else 0
 
     # ------------------------------------------------------------------ public API
@@ -348,8 +355,11 @@ class VoxelSelector:
         return corr.cpu().numpy()
 
     def _correlation_normalization(self, corr):
-        """Within-subject normalisation (voxelselector.py:331-369 / fcma_extension.cc:52-84) on the
-        GPU; returns the normalised array like the reference's scipy path."""
+        """Within-subject normalisation on the GPU; returns the normalised array like the reference's scipy path
+        (voxelselector.py:331-369).  The arithmetic is that of the C++ normaliser the reference's hot loop actually
+        calls (fcma_extension.cc:52-84): it differs from the scipy path in two documented corner cases -- |r| >= 1 is
+        clamped (cc:68-72) instead of producing inf -> nan_to_num, and when the epoch count is not a multiple of
+        ``epochs_per_subj`` the trailing partial subject is left untouched (cc:52), where the scipy path z-scores it."""
         import torch
         _lib.load()
         _lib.require_device()

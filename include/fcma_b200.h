@@ -59,6 +59,14 @@ extern "C" {
                                         HBM traffic of both kernels; max|dK|/max|K| ~ 1.5e-5 at V2 = 50 000;
                                         always on for the single-product operand modes bf16 / tf32)            */
 
+/* alternate code paths with the SAME results (up to the order of fp32 partial sums), selectable per call so that tests
+ * can compare them; the library never reads the environment */
+#define FCMA_FLAG_STRIDED_BLOCK   8   /* fused pipelines: strided [nb][E][ld] correlation block instead of the tiled one */
+#define FCMA_FLAG_SYM_TRANSPOSED 16   /* symmetric pipeline: store a transposed copy of every block + row pass over it
+                                         instead of the column-direction pass (what E > 32 always does)              */
+#define FCMA_FLAG_COLS_LDGSTS    32   /* column-direction pass fed by cp.async + block barriers instead of TMA bricks +
+                                         an mbarrier ring (what E % 4 != 0 always does)                               */
+
 int         fcma_version(void);
 const char *fcma_last_error(void);
 /* number of usable sm_100 devices (0 if none); never fails */

@@ -232,9 +232,9 @@ def test_kernels_and_pipeline_vs_oracle(dev, case):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("two", [False, True])
-def test_tiled_intermediate_equals_strided(dev, two, monkeypatch):
+def test_tiled_intermediate_equals_strided(dev, two):
     """Fused pipeline with >= 256 rows of workspace stores the correlation block tiled
-    [nb/256][V2/256][E][256][256]; FCMA_NO_TILED=1 forces the reference's [nb][E][V2] layout.  Ragged last
+    [nb/256][V2/256][E][256][256]; FCMA_FLAG_STRIDED_BLOCK forces the reference's [nb][E][V2] layout.  Ragged last
     row tile (600 = 2*256 + 88), ragged last column tile, self columns crossing tile borders."""
     V, V2, T, E, eps, start, nb = 700, (530 if two else None), 40, 8, 4, 77, 600
     raw, _ = synthetic.make_epochs(V, T, E, seed=777)
@@ -249,13 +249,12 @@ def test_tiled_intermediate_equals_strided(dev, two, monkeypatch):
     work = engine.Workspace(E, n2, 768, dev)
     out = {}
     for no_tiled in ("0", "1"):
-        monkeypatch.setenv("FCMA_NO_TILED", no_tiled)
         work.buf.view(torch.float32).fill_(float("nan"))   # stale padding must never reach the kernels
-        out[no_tiled] = engine.voxel_kernels(rows, cols, start, nb, eps, flags=fl, work=work).cpu().numpy()
+        out[no_tiled] = engine.voxel_kernels(rows, cols, start, nb, eps, work=work,
+                                             flags=fl | (_lib.FLAG_STRIDED_BLOCK if no_tiled == "1" else 0)).cpu().numpy()
     assert np.array_equal(out["0"], out["1"])
     assert np.max(np.abs(out["0"] - Kref)) <= k_tol(n2) * np.max(np.abs(Kref))
     # fp16 intermediate (opt-in flag): same result up to the averaged rounding of the stored Fisher-z values
-    monkeypatch.setenv("FCMA_NO_TILED", "0")
     got16 = engine.voxel_kernels(rows, cols, start, nb, eps, flags=fl | _lib.FLAG_F16_INTERMEDIATE, work=work).cpu().numpy()
     d16 = np.max(np.abs(got16 - out["0"]))
     assert 0 < d16 <= 4e-3 / math.sqrt(n2) * np.max(np.abs(Kref))
@@ -265,7 +264,7 @@ def test_tiled_intermediate_equals_strided(dev, two, monkeypatch):
     assert np.array_equal(got, out["0"])
 
 
-@pytest.mark.parametrize("case", ["ragged_multi_pass", "whole_tiles_sharded", "wide_E64"])
+@pytest.mark.parametrize("case", ["ragged_multi_pass", "whole_tiles_sharded", "wide_E64", "long_column_walk"])
 def test_symmetric_pipeline_vs_oracle_and_plain(dev, case):
     """fcma_voxel_kernels_sym (self-correlation: only blocks on/above the diagonal are contracted, every block is
     used for its row voxels and -- transposed -- for its column voxels) against the CPU oracle and the plain
@@ -273,12 +272,15 @@ def test_symmetric_pipeline_vs_oracle_and_plain(dev, case):
     accumulate into one K (the multi-GPU scheme: sum of the shards' K arrays), self-column masking, E > 32."""
     cfg = {"ragged_multi_pass": dict(V=1100, T=40, E=8, eps=4, rows=256, shards=1),
            "whole_tiles_sharded": dict(V=1536, T=50, E=16, eps=8, rows=512, shards=3),
-           "wide_E64": dict(V=900, T=30, E=64, eps=16, rows=512, shards=2)}[case]
+           "wide_E64": dict(V=900, T=30, E=64, eps=16, rows=512, shards=2),
+           # 2048-row pass = 128 row steps of the column pass: two accumulator folds, the brick ring wraps 42 times
+           "long_column_walk": dict(V=2600, T=24, E=8, eps=4, rows=2048, shards=1)}[case]
     V, T, E, eps, rows, shards = (cfg[k] for k in ("V", "T", "E", "eps", "rows", "shards"))
     raw, _ = synthetic.make_epochs(V, T, E, seed=2468)
     ep, T_e = engine.stack_epochs(raw, dev)
     op = engine.pack_epochs(ep, T_e, "fp32")
-    work = engine.SymWorkspace(E, V, rows, dev)
+    # (a buffer sized for block + transposed copy gives the column-pass variant twice the rows per pass)
+    work = engine.SymWorkspace(E, V, rows, dev, transposed_copy=(case != "long_column_walk"))
     for fl in (_lib.FLAG_MASK_SELF, 0):
         plain = engine.voxel_kernels(op, op, 0, V, eps, flags=fl)
         work.buf.view(torch.float32).fill_(float("nan"))       # stale scratch must never reach the kernels
@@ -332,6 +334,14 @@ def test_symmetric_column_pass_all_eps(dev, E, eps):
     # than those of r(i, j)); a flipped pair moves one K entry by 2 of ~V
     loose = eps <= 2
     assert float((K - plain).abs().max()) <= (2e-3 if loose else 1e-5) * scale
+    # the two feeds of the column pass (TMA bricks + mbarrier ring when E % 4 == 0, cp.async + block barriers otherwise
+    # or on request) and the transposed-copy variant agree to the order of the fp32 partial sums
+    for extra in (_lib.FLAG_COLS_LDGSTS, _lib.FLAG_SYM_TRANSPOSED):
+        K2 = torch.zeros((V, E, E), device=dev)
+        w2 = engine.SymWorkspace(E, V, 256, dev)
+        w2.buf.view(torch.float32).fill_(float("nan"))
+        engine.voxel_kernels_sym(op, 0, V, eps, flags=fl | extra, work=w2, out=K2)
+        assert float((K2 - K).abs().max()) <= (2e-3 if loose else 1e-5) * scale
     for s0 in (0, 700, V - 30):
         _, z, _ = orc.voxel_block(raw, None, s0, 30, eps, shrink=False)
         Kref = orc.kernel_matrices(zero_self(z, s0), f64=True)
@@ -340,7 +350,7 @@ def test_symmetric_column_pass_all_eps(dev, E, eps):
 
 
 @pytest.mark.parametrize("prec,flag", [("fp32", True), ("bf16", False)])
-def test_symmetric_fp16_block_column_pass(dev, prec, flag, monkeypatch):
+def test_symmetric_fp16_block_column_pass(dev, prec, flag):
     """fp16 Fisher-z block (opt-in flag, or implied by the single-product operand modes): the symmetric pipeline's column
     pass reads 64-byte lines of the fp16 block; same stored values as the plain fp16-block pipeline, so the kernels
     agree to the order of the fp32 partial sums, and both stay within the fp16-block tolerance of the fp32 block."""
@@ -353,13 +363,13 @@ def test_symmetric_fp16_block_column_pass(dev, prec, flag, monkeypatch):
     plain = engine.voxel_kernels(op, op, 0, V, eps, flags=fl)
     scale = float(plain.abs().max())
     out = {}
-    for cols in ("1", "0"):                      # column pass over the block / transposed copy + row pass
-        monkeypatch.setenv("FCMA_SYM_COLS_F16", cols)
+    # column pass over the block (TMA bricks / cp.async bricks) / transposed copy + row pass
+    for cols, extra in (("1", 0), ("ldgsts", _lib.FLAG_COLS_LDGSTS), ("0", _lib.FLAG_SYM_TRANSPOSED)):
         K = torch.zeros((V, E, E), device=dev)
         work = engine.SymWorkspace(E, V, 512, dev)
         work.buf.view(torch.float32).fill_(float("nan"))
         for s0, n0 in engine.sym_row_partition(V, 2):
-            engine.voxel_kernels_sym(op, s0, n0, eps, flags=fl, work=work, out=K)
+            engine.voxel_kernels_sym(op, s0, n0, eps, flags=fl | extra, work=work, out=K)
         assert torch.isfinite(K).all()
         assert float((K - K.transpose(1, 2)).abs().max()) == 0.0
         assert float((K - plain).abs().max()) <= 1e-5 * scale

@@ -3,6 +3,9 @@
 import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from brainiak_b200 import _lib
+from brainiak_b200 import build as _build  # noqa: E402
+_build.build(diag=True)      # the FCMA_* knobs exist only in the diagnostic build (-DFCMA_DIAG)
+_lib.use_diag_build()
 from brainiak_b200.fcma import engine
 V, T, E, eps, nb = 50000, 200, 32, 8, 2048
 dev = torch.device("cuda:0")

@@ -5,6 +5,9 @@ python tools/ab_pipeline.py [nb]"""
 import ctypes, os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from brainiak_b200 import _lib
+from brainiak_b200 import build as _build  # noqa: E402
+_build.build(diag=True)      # the FCMA_* knobs exist only in the diagnostic build (-DFCMA_DIAG)
+_lib.use_diag_build()
 from brainiak_b200.fcma import engine
 lib = _lib.load()
 V, T, E, eps = 50000, 200, 32, 8

@@ -3,6 +3,9 @@
 tells whether a kernel's time is tensor-pipe time at a power-capped clock or pipeline bubbles."""
 import os, sys, time, threading, statistics, torch, pynvml
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from brainiak_b200 import _lib, build as _build
+_build.build(diag=True)      # the FCMA_* knobs exist only in the diagnostic build (-DFCMA_DIAG)
+_lib.use_diag_build()
 from brainiak_b200.fcma import engine
 V, T, E, nb = 50000, 200, 32, 4096
 dev = torch.device("cuda:0")

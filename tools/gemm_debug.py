@@ -6,6 +6,9 @@ switched off through FCMA_GEMM_DEBUG (outputs are WRONG while a bit is set -- ti
 and for T = 64 .. 256 (1 .. 4 k-blocks of 64) to expose per-stage costs.   python tools/gemm_debug.py [prec ...]"""
 import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from brainiak_b200 import _lib, build as _build
+_build.build(diag=True)      # the FCMA_* knobs exist only in the diagnostic build (-DFCMA_DIAG)
+_lib.use_diag_build()
 from brainiak_b200.fcma import engine
 V, E, nb = 50000, 32, 4096
 dev = torch.device("cuda:0")

@@ -1,6 +1,9 @@
 #!/usr/bin/env python
-"""Small tiled-pipeline run for compute-sanitizer (memcheck / racecheck):
-   compute-sanitizer --tool memcheck python tools/sanitize_small.py"""
+"""Small runs of every hot kernel for compute-sanitizer (memcheck / racecheck / synccheck):
+   compute-sanitizer --tool memcheck python tools/sanitize_small.py
+Covers the plain tiled pipeline (one and two masks, E > 32), the symmetric pipeline (symmetric GEMM with its TMA-store
+staging, row pass, column pass fed by TMA bricks and by cp.async, transposed-copy variant, fp16 block), the
+classifier kernel, the decimal shrink and the batched SVM cross-validation."""
 import os, sys, numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from brainiak_b200 import _lib
@@ -15,4 +18,23 @@ for (V, V2, T, E, eps, start, nb, rows) in ((700, None, 40, 8, 4, 77, 600, 768),
     work = engine.Workspace(E, V2 or V, rows, dev)
     K = engine.voxel_kernels(r, c, start, nb, eps, flags=0 if V2 else _lib.FLAG_MASK_SELF, work=work)
     torch.cuda.synchronize()
-    print("ok", V, V2, E, float(K.abs().max()))
+    print("plain ok", V, V2, E, float(K.abs().max()), flush=True)
+# symmetric pipeline: 3 passes of 256 rows + ragged tail, every variant of the column voxels' sums
+V, T, E, eps = 800, 24, 8, 4
+raw, labels = synthetic.make_epochs(V, T, E, seed=3)
+ep, T_e = engine.stack_epochs(raw, dev)
+op = engine.pack_epochs(ep, T_e, "fp32")
+ref = None
+for name, fl in (("tma", 0), ("ldgsts", _lib.FLAG_COLS_LDGSTS), ("transposed", _lib.FLAG_SYM_TRANSPOSED),
+                 ("f16", _lib.FLAG_F16_INTERMEDIATE), ("f16 ldgsts", _lib.FLAG_F16_INTERMEDIATE | _lib.FLAG_COLS_LDGSTS)):
+    K = torch.zeros((V, E, E), device=dev)
+    work = engine.SymWorkspace(E, V, 256, dev)
+    engine.voxel_kernels_sym(op, 0, V, eps, flags=fl | _lib.FLAG_MASK_SELF, work=work, out=K)
+    torch.cuda.synchronize()
+    ref = K if ref is None else ref
+    print("sym ok", name, float((K - ref).abs().max() / ref.abs().max()), flush=True)
+Kc = engine.classifier_kernel(op, op, 0, V, eps)
+engine.shrink_kernels_(ref)
+acc = engine.svm_cv_precomputed(ref[:64], labels, E // eps)
+torch.cuda.synchronize()
+print("classifier / shrink / svm cv ok", float(Kc.abs().max()), float(np.mean(acc)), flush=True)

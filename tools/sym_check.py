@@ -11,6 +11,9 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from brainiak_b200 import _lib  # noqa: E402
+from brainiak_b200 import build as _build  # noqa: E402
+_build.build(diag=True)      # the FCMA_* knobs exist only in the diagnostic build (-DFCMA_DIAG)
+_lib.use_diag_build()
 from brainiak_b200.fcma import engine  # noqa: E402
 
 lib = _lib.load()

@@ -4,20 +4,28 @@
   python bench.py --gpus N --steps K --warmup W            # B200 arm (one rank per GPU under torchrun)
   python bench.py --impl reference --steps K --warmup W    # the reference's own CPU path, same metric
 
-A *step* is one pass of the hot path over the whole synthetic workload (BASELINE.json: V=50 000
-voxels, T=200 TRs, E=32 epochs, eps=8): pack the (already normalised, HBM-resident) epochs, then for
-every voxel row the correlation GEMM -> Fisher-z + within-subject z-score -> E x E kernel matrix, with
-the [V, E, E] kernels left resident in HBM.  metric = V * V * E / step time.
+A *step* is one pass of the hot path over the whole synthetic workload (BASELINE.json configs[2]: V=50 000 voxels,
+T=200 TRs, E=32 epochs, eps=8): pack the (already normalised, HBM-resident) epochs, then for every voxel row the
+correlation GEMM -> Fisher-z + within-subject z-score -> E x E kernel matrix, with the [V, E, E] kernels left resident
+in HBM.  metric = V * V * E / step time.
 
-N > 1: voxel rows are sharded statically over the ranks (the reference's data-parallel scheme,
-voxelselector.py:198-238) with the epochs replicated in every rank's HBM (as after the reference's
-bcast, preprocessing.py:211-223); the per-rank kernels are gathered on rank 0 inside the timed step.
-The `e2e` figure starts from rank 0's host memory and includes the NCCL broadcast of the epochs.
-The total job is fixed, so scaling is "strong".
+N > 1: the symmetric pipeline's row shards (equal trapezoid areas) go to the ranks, the epochs are replicated in every
+rank's HBM before the timed region (as after the reference's bcast, preprocessing.py:211-223), and ONE NCCL
+reduce-scatter inside the timed step sums the ranks' partial kernels so that every rank ends up with the kernels of the
+rows it would cross-validate (voxelselector.py's row partition).  Total work is fixed: "scaling": "strong".
 
-One JSON line is printed by rank 0.  Extra objects: `roofline` (dominant kernel, measured live with
-CUDA events), `cpu_baseline` (reference path on this box's host cores, bounded sample), `e2e` (host
-buffers in, host buffers out, copies inside the timed region), `clocks`.
+`e2e` is the same metric from HOST buffers to HOST buffers, unpipelined, every copy inside the timed region:
+  N = 1: one call of the C-ABI host entry point fcma_host_voxel_kernels_sym per step (pinned host epochs in, pinned host
+         kernels out: H2D, packing, kernels, D2H);
+  N > 1: per step every rank uploads ITS share of the epochs (E/N of them) over its own PCIe link, the shares are
+         all-gathered over NVLink by the copy engines (CUDA IPC; brainiak_b200/fcma/exchange.py), then pack, kernels,
+         reduce-scatter and the read-back of the rank's own kernel rows.
+The pipelined variant (copies of step k+1 / k-1 under the kernels of step k) is reported beside it as `e2e.pipelined`.
+
+One JSON line is printed by rank 0.  Extra objects: `roofline` (dominant kernel, measured live with CUDA events),
+`kernels` (per-kernel table), `cpu_baseline` (reference path on this box's host cores, bounded sample),
+`parity_vs_reference` (three 64-row samples through the UNMODIFIED reference: first pass, a middle pass, ragged tail),
+`other_configs` (BASELINE configs[1], [3], [4] with their own roofline and parity sample), `clocks`.
 """
 import argparse
 import json
@@ -27,7 +35,14 @@ import sys
 import tempfile
 import time
 
-import numpy as np
+# the reference arm must see all host cores: torchrun exports OMP_NUM_THREADS=1, and OpenBLAS / libgomp read the
+# environment when they are loaded, i.e. before anything below imports numpy / scipy
+if "--impl" in sys.argv and "reference" in sys.argv:
+    _cores = str(len(os.sched_getaffinity(0)))
+    for _k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_k] = _cores
+
+import numpy as np  # noqa: E402
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -35,6 +50,11 @@ sys.path.insert(0, ROOT)
 WORKLOAD = dict(V=50000, T=200, E=32, eps=8)
 METRIC = "voxel-pair correlations/sec"
 UNIT = "corr/s"
+SEED = 1234567890
+
+
+def workload_string(V, T, E, eps):
+    return "FCMA VoxelSelector V=%d T=%d E=%d eps=%d (BASELINE configs[2] shape)" % (V, T, E, eps)
 
 
 def parse():
@@ -48,25 +68,50 @@ def parse():
     ap.add_argument("--block-rows", type=int, default=4096)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-sym", action="store_true",
-                    help="plain pipeline (every row against all columns) instead of the symmetric one")
+    ap.add_argument("--no-others", action="store_true", help="skip the other BASELINE configs")
+    ap.add_argument("--no-ipc", action="store_true", help="epoch exchange through NCCL all-gather instead of CUDA IPC copies")
     return ap.parse_args()
 
 
-def make_host_epochs(V, T, E, pin=False):
-    """Synthetic workload of SURVEY.md §8d, generated with torch's CPU generator (seeded):
-    Gaussian epochs, a planted common time course in the first V//100 voxels of odd epochs,
-    then the reference normalisation (zscore over TRs, ddof=0; / sqrt(T))."""
+def make_epoch(e, T, V, out=None):
+    """One synthetic epoch of SURVEY.md §8d (torch CPU generator seeded per epoch, so a rank can generate just its
+    share): Gaussian [T, V], a planted common time course in the first V//100 voxels of odd epochs, then the
+    reference normalisation (zscore over TRs, ddof=0; / sqrt(T); preprocessing.py:80-84)."""
     import torch
-    g = torch.Generator().manual_seed(1234567890)
-    x = torch.empty((E, T, V), dtype=torch.float32, pin_memory=pin)
-    for e in range(E):
-        m = torch.randn((T, V), generator=g)
-        if e % 2 == 1:
-            m[:, : V // 100] += 0.6 * torch.randn((T, 1), generator=g)
-        m = (m - m.mean(0, keepdim=True)) / m.std(0, unbiased=False, keepdim=True)
-        x[e] = torch.nan_to_num(m) / (T ** 0.5)
+    g = torch.Generator().manual_seed(SEED + e)
+    m = torch.randn((T, V), generator=g)
+    if e % 2 == 1:
+        m[:, : V // 100] += 0.6 * torch.randn((T, 1), generator=g)
+    m = (m - m.mean(0, keepdim=True)) / m.std(0, unbiased=False, keepdim=True)
+    m = torch.nan_to_num(m) / (T ** 0.5)
+    if out is not None:
+        out.copy_(m)
+        return out
+    return m
+
+
+def make_host_epochs(V, T, E, epochs=None, pin=False):
+    import torch
+    epochs = list(range(E)) if epochs is None else list(epochs)
+    x = torch.empty((len(epochs), T, V), dtype=torch.float32, pin_memory=pin)
+    for k, e in enumerate(epochs):
+        make_epoch(e, T, V, out=x[k])
     return x
+
+
+def device_epochs(V, T, E, dev, seed):
+    """Synthetic epochs generated ON the device (the big other configs: 12.8 GB at V=100 000, T=500, E=64), same
+    recipe; identical on every rank (same seed, same generator)."""
+    import torch
+    from brainiak_b200.fcma import engine
+    g = torch.Generator(device=dev).manual_seed(seed)
+    ep = torch.empty((E, T, V), dtype=torch.float32, device=dev)
+    for e in range(E):
+        torch.randn((T, V), generator=g, out=ep[e])
+        if e % 2 == 1:
+            ep[e, :, : V // 100] += 0.6 * torch.randn((T, 1), generator=g, device=dev)
+    engine.epoch_normalize_(ep)
+    return ep
 
 
 # ---------------------------------------------------------------------------------------------
@@ -126,18 +171,39 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------
 # reference arm / cpu baseline
 # ---------------------------------------------------------------------------------------------
-def reference_task_fn(host_epochs, eps):
-    """Returns (fn(start, n) -> seconds for the kernel path a4+a6+a7 of one task, kind, cores)."""
+def host_threads():
+    """Give the reference's BLAS / OpenMP every host core (torchrun exports OMP_NUM_THREADS=1); returns the count."""
+    cores = len(os.sched_getaffinity(0))
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=cores)
+    except Exception:  # pragma: no cover
+        pass
+    return cores
+
+
+def reference_selector(raw, eps):
+    """(module, unmodified reference VoxelSelector, clf, labels) on host arrays, or None if oracle/_ref is missing."""
     from sklearn import svm
-    E, T, V = host_epochs.shape
-    raw = [host_epochs[e].numpy() for e in range(E)]
+    from oracle import reference
+    if not reference.available():
+        return None
+    E = len(raw)
     labels = [e % 2 for e in range(E)]
     clf = svm.SVC(kernel="precomputed", shrinking=False, C=1)
-    from oracle import reference
-    if reference.available():
-        m = reference.load()
-        vs = m.VoxelSelector(labels, eps, E // eps, raw, voxel_unit=64, process_num=0)
-        cores = len(os.sched_getaffinity(0))
+    m = reference.load()
+    vs = m.VoxelSelector(labels, eps, E // eps, raw, voxel_unit=64, process_num=0)
+    return m, vs, clf, labels
+
+
+def reference_task_fn(host_epochs, eps):
+    """Returns (fn(start, n) -> seconds for the kernel path a4+a6+a7 of one task, kind, cores)."""
+    E, T, V = host_epochs.shape
+    raw = [host_epochs[e].numpy() for e in range(E)]
+    cores = host_threads()
+    ref = reference_selector(raw, eps)
+    if ref is not None:
+        m, vs, clf, _ = ref
 
         def fn(start, n):
             t0 = time.perf_counter()
@@ -155,6 +221,19 @@ def reference_task_fn(host_epochs, eps):
     return fn, "port", orc.num_threads()
 
 
+def time_reference_tasks(fn, V, ntasks, budget_s, rows=64, warm=1):
+    """Median task time over up to `ntasks` tasks of `rows` voxel rows spread over [0, V) (bounded by budget_s)."""
+    for w in range(warm):
+        fn(0, rows)
+    times, t_start = [], time.perf_counter()
+    stride = max(rows, ((V - rows) // max(ntasks, 1)) // rows * rows)
+    for k in range(ntasks):
+        times.append(fn(min(V - rows, (k * stride) % max(V - rows, 1)), rows))
+        if time.perf_counter() - t_start > budget_s and len(times) >= 5:
+            break
+    return float(np.median(times)), len(times), times
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -163,19 +242,23 @@ def run_reference_arm(args):
     host = make_host_epochs(V, T, E)
     fn, kind, cores = reference_task_fn(host, eps)
     rows = 64                                     # the reference's default voxel_unit
-    for w in range(args.warmup):
-        fn((w * rows) % (V - rows), rows)
-    tsum = 0.0
-    for k in range(args.steps):
-        tsum += fn(((args.warmup + k) * rows) % (V - rows), rows)
-    value = args.steps * rows * V * E / tsum
-    sample = "%d tasks of %d voxel rows x V=%d x E=%d (kernel path a4+a6+a7, no CV)" % (args.steps, rows, V, E)
+    # a "step" of this arm = one task of 64 voxel rows (bounded sample of the same workload); the value is taken from
+    # the MEDIAN task time of max(steps, 20) tasks after `warmup` tasks, extrapolated by the metric (linear in the
+    # number of tasks: every task contracts 64 rows with all V columns of all E epochs)
+    ntasks = max(args.steps, 20)
+    med, done, times = time_reference_tasks(fn, V, ntasks, 120.0, rows=rows, warm=max(args.warmup, 1))
+    value = rows * float(V) * E / med
+    sample = ("median of %d tasks of %d voxel rows x V=%d x E=%d (kernel path a4+a6+a7 = voxelselector.py:492-505, no CV), "
+              "%d BLAS/OpenMP threads" % (done, rows, V, E, cores))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tsum / args.steps,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * med,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": {"workload": "FCMA VoxelSelector V=%d T=%d E=%d eps=%d" % (V, T, E, eps),
-                                            "step": "one task of 64 voxel rows (bounded sample)"},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+            "data": "synthetic", "config": {"workload": workload_string(V, T, E, eps),
+                                            "step": "one task of 64 voxel rows against all V columns (bounded sample; "
+                                                    "the whole job is V/64 such tasks)",
+                                            "threads": cores, "omp_num_threads_env": os.environ.get("OMP_NUM_THREADS")},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample,
+                             "task_ms_min_median_max": [1e3 * min(times), 1e3 * med, 1e3 * max(times)]},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print_json(line)
@@ -183,13 +266,52 @@ def run_reference_arm(args):
 
 
 # ---------------------------------------------------------------------------------------------
+# parity against the unmodified reference (rank 0, host)
+# ---------------------------------------------------------------------------------------------
+def parity_samples(raw_list, eps, samples, K_rows, engine, dev):
+    """samples: [(start, n)]; K_rows: dict start -> unshrunk GPU kernels [n, E, E] (device tensors) of those rows.
+    The unmodified reference computes the same rows on the host: kernels (after its decimal shrink) and the
+    cross-validation accuracies of its own scikit-learn path vs the batched GPU SVM on the GPU kernels."""
+    ref = reference_selector(raw_list, eps)
+    if ref is None:
+        return None
+    m, rvs, clf, labels = ref
+    E = len(raw_list)
+    out = []
+    for (s0, n0) in samples:
+        corr = rvs._correlation_computation((s0, n0))
+        m.fcma_extension.normalization(corr, eps)
+        Kref = rvs._prepare_for_cross_validation(corr, clf)          # shrunk kernels [n0, E, E]
+        acc_ref = np.array([a for _, a in rvs._do_cross_validation(clf, Kref, (s0, n0))])
+        Kg = K_rows[s0].to(dev).clone()
+        engine.shrink_kernels_(Kg)
+        acc_gpu = engine.svm_cv_precomputed(Kg, labels, E // eps, C=1.0, tol=1e-3)
+        Kg = Kg.cpu().numpy()
+        out.append({"rows": [int(s0), int(s0 + n0)],
+                    "max_abs_dK_over_max_K": float(np.max(np.abs(Kg - Kref)) / np.max(np.abs(Kref))),
+                    "cv_accuracy_identical": int(np.sum(acc_gpu == acc_ref)), "cv_accuracy_total": int(n0),
+                    "max_abs_d_accuracy": float(np.max(np.abs(acc_gpu - acc_ref)))})
+    return out
+
+
+def sample_starts(V, rows_per_pass, n=64):
+    """first pass, a middle pass (its rows receive most of their sums from the column pass) and the ragged tail"""
+    mid = (V // 2 // 256) * 256 + 64
+    s = [(128, n), (min(mid, V - n), n), (V - n, n)]
+    return [x for k, x in enumerate(s) if x not in s[:k]]
+
+
+# ---------------------------------------------------------------------------------------------
 # B200 arm
 # ---------------------------------------------------------------------------------------------
 def run_b200_arm(args):
+    import ctypes as _ct
+
     import torch
     import torch.distributed as dist
     from brainiak_b200 import _lib
     from brainiak_b200.fcma import engine
+    from brainiak_b200.fcma.exchange import EpochExchange
     from brainiak_b200.fcma.voxelselector import VoxelSelector
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -200,150 +322,139 @@ def run_b200_arm(args):
             raise SystemExit("--gpus %d needs torchrun --nproc-per-node %d" % (args.gpus, args.gpus))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    pg2 = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        pg2 = dist.new_group(backend="nccl")       # collectives issued from the copy stream (epoch exchange)
     lib = _lib.load()
     _lib.require_device()
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    tf_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    peak_src = "MEASURED_PEAKS.json (hbm_gbs, bf16_tflops_sustained)" if peaks else "fallback 6650 GB/s, 1400 TFLOP/s"
 
     V, T, E, eps = args.voxels, WORKLOAD["T"], WORKLOAD["E"], WORKLOAD["eps"]
-    prec = args.precision
+    prec, code = args.precision, _lib.PREC[args.precision]
     flags = 0
-    sym = (not args.no_sym) and engine.sym_supported(E, eps) and V >= 512 * world
-    start, n = (engine.sym_row_partition(V, world) if sym else VoxelSelector.row_partition(V, world))[rank]
-    block = min(args.block_rows, max(n, 1))
-    if sym:
-        block = max(256, (block + 255) // 256 * 256)
-
-    # inputs: pinned host copy on rank 0 (for e2e) and the HBM-resident epochs
-    host = make_host_epochs(V, T, E, pin=True) if rank == 0 else None
-    epochs = torch.empty((E, T, V), dtype=torch.float32, device=dev)
-    if rank == 0:
-        epochs.copy_(host, non_blocking=True)
-    bcast = torch.empty_like(epochs) if world > 1 else None   # receive buffer used inside the step
-    # symmetric pipeline: scratch for a block and its transposed copy; K is the full [V, E, E] array every rank
-    # accumulates its partial sums into (summed onto rank 0 with one NCCL reduce)
-    cols_variant = bool(sym and lib.fcma_sym_uses_column_pass(_lib.PREC[prec], E, eps, flags))
-    work = engine.SymWorkspace(E, V, block, dev, start=start, transposed_copy=not cols_variant) if sym \
-        else engine.Workspace(E, V, block, dev)
-    K = torch.empty((V if sym else max(n, 1), E, E), dtype=torch.float32, device=dev)
-    per = VoxelSelector.row_partition(V, world)[0][1]
-    Kall = torch.empty((world * per, E, E), dtype=torch.float32, device=dev) if (world > 1 and rank == 0 and not sym) else None
-    Kpad = torch.zeros((per, E, E), dtype=torch.float32, device=dev) if (world > 1 and not sym) else None
-    Khost = torch.empty((V, E, E), dtype=torch.float32, pin_memory=True) if rank == 0 else None
-    torch.cuda.synchronize()
+    if not (engine.sym_supported(E, eps) and V >= 512 * world):
+        raise SystemExit("the bench workload needs the symmetric pipeline (E <= 64, power-of-two eps, V >= 512 per rank)")
+    parts = engine.sym_row_partition(V, world)
+    start, n = parts[rank]
+    block = max(256, (min(args.block_rows, max(n, 1)) + 255) // 256 * 256)
+    cv_parts = VoxelSelector.row_partition(V, world)       # the rows each rank cross-validates (and keeps)
+    per = cv_parts[0][1]
 
     def barrier():
         if world > 1:
             dist.barrier(device_ids=[local])
         torch.cuda.synchronize()
 
-    # N > 1: every rank holds the (replicated) normalised epochs in HBM before the timed region, exactly
-    # like the reference's ranks after prepare_fcma_data's bcast (preprocessing.py:211-223); the e2e
-    # variant starts from rank 0's host memory and includes the NCCL broadcast.
-    if world > 1:
-        dist.broadcast(epochs, src=0)
+    # ---- inputs: every rank holds ITS share of the epochs in pinned host memory (the source of the e2e copies);
+    # rank 0 also keeps all epochs on the host for the parity check against the reference
+    xch = EpochExchange(E, T, V, dev, group=pg2, nbuf=2, use_ipc=not args.no_ipc)
+    e0, ne = xch.share_of()
+    host_share = make_host_epochs(V, T, E, epochs=range(e0, e0 + ne), pin=True)
+    host_all = None
+    if rank == 0 and (world > 1) and not (args.no_cpu_baseline and args.no_e2e):
+        host_all = make_host_epochs(V, T, E)
+    elif rank == 0:
+        host_all = host_share
+    epochs = xch.gather(0, host_share)           # replicated in every rank's HBM before the timed region
+    cols_variant = bool(lib.fcma_sym_uses_column_pass(code, E, eps, flags))
+    work = engine.SymWorkspace(E, V, block, dev, start=start, transposed_copy=not cols_variant)
+    Kfull = torch.zeros((world * per, E, E), dtype=torch.float32, device=dev)     # this rank's partial sums, all rows
+    Kmine = torch.empty((per, E, E), dtype=torch.float32, device=dev) if world > 1 else None
+    Khost = torch.empty((per if world > 1 else V, E, E), dtype=torch.float32, pin_memory=True)
+    op_buf = engine.pack_epochs(epochs, None, prec, v_begin=start)
+    torch.cuda.synchronize()
 
-    def step(from_host):
-        """One pass of the hot path. from_host: include the pinned-host -> HBM copy (+ NCCL broadcast
-        of the epochs for N > 1) and the readback of the [V, E, E] kernels."""
-        src = epochs
-        if from_host:
-            if rank == 0:
-                epochs.copy_(host, non_blocking=True)
-            if world > 1:
-                if rank == 0:
-                    bcast.copy_(epochs)
-                dist.broadcast(bcast, src=0)
-                src = bcast
-        op = engine.pack_epochs(src, None, prec)
-        if sym:
-            K.zero_()
-            if n > 0:
-                engine.voxel_kernels_sym(op, start, n, eps, flags=flags, work=work, out=K)
-            if world > 1:
-                dist.reduce(K, dst=0)
-        else:
-            if n > 0:
-                engine.voxel_kernels(op, op, start, n, eps, flags=flags, work=work, out=K)
-            if world > 1:
-                Kpad[:n].copy_(K[:n])
-                dist.gather(Kpad, list(Kall.view(world, per, E, E).unbind(0)) if rank == 0 else None, dst=0)
-        if from_host and rank == 0:
-            res = Kall.view(-1, E, E)[:V] if (world > 1 and not sym) else K
-            Khost.copy_(res, non_blocking=True)
+    def kernels_step(src, Kdst):
+        """pack (only the voxels this shard touches) + symmetric pipeline + reduce-scatter of the partial kernels"""
+        op = engine.pack_epochs(src, None, prec, v_begin=start, out=op_buf)
+        Kdst[start:].zero_()                 # rows < start are never written by this rank and stay zero
+        if n > 0:
+            engine.voxel_kernels_sym(op, start, n, eps, flags=flags, work=work, out=Kdst[:V])
+        if world > 1:
+            dist.reduce_scatter_tensor(Kmine, Kdst)
 
-    def timed(nsteps, from_host):
+    def e2e_step():
+        """host -> host, unpipelined: this rank's share H2D + epoch exchange, kernels, read-back of the rank's rows"""
+        if world == 1:
+            engine.host_voxel_kernels_sym(host_share, eps, precision=prec, flags=flags, device=local,
+                                          rows_per_pass=block, out=Khost)
+            return
+        src = xch.gather(1, host_share)
+        kernels_step(src, Kfull)
+        Khost.copy_(Kmine, non_blocking=True)
+
+    def timed(nsteps, fn):
         barrier()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = lib.fcma_launch_count()
+        t0 = time.perf_counter()
         ev0.record()
         for _ in range(nsteps):
-            step(from_host)
+            fn()
         ev1.record()
         barrier()
-        ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+        wall = (time.perf_counter() - t0) * 1e3
+        # device time between the events; the synchronous host entry point (N = 1 e2e) is also bracketed by wall clock
+        ms = torch.tensor([ev0.elapsed_time(ev1), wall], device=dev)
         launches = torch.tensor([float(lib.fcma_launch_count() - l0)], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
             dist.all_reduce(launches, op=dist.ReduceOp.SUM)
-        return float(ms[0]), int(launches[0])
+        return float(ms[0]), int(launches[0]), float(ms[1])
 
     pipe_state = {}
 
     def timed_e2e_pipelined(nsteps):
-        """End-to-end with the copies off the critical path: every step still copies its epochs from pinned host memory
-        (rank 0; N > 1: followed by the NCCL broadcast to the other ranks on a second communicator) and its [V, E, E]
-        kernels back, but on a copy stream, double-buffered, so the input of step k+1 and the result of step k-1 move
-        under the kernels of step k (what a service streaming datasets through the engine does).  The timed region
-        covers all copies and collectives of all steps."""
+        """The same host -> host work with the copies off the critical path: the input of step k+1 (H2D of the share +
+        epoch exchange) and the read-back of step k-1 run on a copy stream under the kernels of step k (what a service
+        streaming datasets through the engine does).  All copies / collectives of all steps are inside the timed region."""
         main = torch.cuda.current_stream()
         if not pipe_state:
             pipe_state["cs"] = torch.cuda.Stream(device=dev)
-            pipe_state["ebuf"] = [epochs, bcast if world > 1 else torch.empty_like(epochs)]
-            pipe_state["kbuf"] = [K, torch.empty_like(K)]
-            pipe_state["pg2"] = dist.new_group(backend="nccl") if world > 1 else None
-        cs, ebuf, kbuf, pg2 = pipe_state["cs"], pipe_state["ebuf"], pipe_state["kbuf"], pipe_state["pg2"]
-
-        def stage_in(buf):          # on the copy stream: host -> rank 0 -> all ranks
-            if rank == 0:
-                buf.copy_(host, non_blocking=True)
-            if world > 1:
-                dist.broadcast(buf, src=0, group=pg2)
+            pipe_state["kbuf"] = [Kfull, torch.zeros_like(Kfull)]
+            pipe_state["kmine"] = [Kmine, torch.empty_like(Kmine)] if world > 1 else None
+        cs, kbuf, kmine = pipe_state["cs"], pipe_state["kbuf"], pipe_state["kmine"]
         ready = [torch.cuda.Event() for _ in range(2)]
-        consumed = [torch.cuda.Event() for _ in range(2)]
-        kdone = [torch.cuda.Event() for _ in range(2)]
+        stepdone = [torch.cuda.Event() for _ in range(2)]
         kread = [torch.cuda.Event() for _ in range(2)]
         barrier()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
-        with torch.cuda.stream(cs):
-            cs.wait_event(ev0)
-            stage_in(ebuf[0])
-            ready[0].record(cs)
+        cs.wait_event(ev0)
+        xch.gather(0, host_share, stream=cs)
+        ready[0].record(cs)
         for k in range(nsteps):
             c = k & 1
             if k + 1 < nsteps:
-                with torch.cuda.stream(cs):
-                    if k >= 1:
-                        cs.wait_event(consumed[1 - c])      # step k-1 has packed ebuf[1-c]
-                    stage_in(ebuf[1 - c])
-                    ready[1 - c].record(cs)
+                if k >= 1:
+                    # buffer 1-c was packed by step k-1 on EVERY rank once that step's reduce-scatter has completed here
+                    cs.wait_event(stepdone[1 - c])
+                xch.gather(1 - c, host_share, stream=cs)
+                ready[1 - c].record(cs)
             main.wait_event(ready[c])
-            if k >= 2 and rank == 0:
-                main.wait_event(kread[c])                   # the readback of step k-2 has left kbuf[c]
-            op = engine.pack_epochs(ebuf[c], None, prec)
-            consumed[c].record(main)
-            kbuf[c].zero_()
+            if k >= 2:
+                main.wait_event(kread[c])                   # the read-back of step k-2 has left the result buffer
+            op = engine.pack_epochs(xch.buffers[c], None, prec, v_begin=start, out=op_buf)
+            kbuf[c][start:].zero_()
             if n > 0:
-                engine.voxel_kernels_sym(op, start, n, eps, flags=flags, work=work, out=kbuf[c])
+                engine.voxel_kernels_sym(op, start, n, eps, flags=flags, work=work, out=kbuf[c][:V])
+            res = kbuf[c][:V]
             if world > 1:
-                dist.reduce(kbuf[c], dst=0)
-            kdone[c].record(main)
-            if rank == 0:
-                with torch.cuda.stream(cs):
-                    cs.wait_event(kdone[c])
-                    Khost.copy_(kbuf[c], non_blocking=True)
-                    kread[c].record(cs)
+                dist.reduce_scatter_tensor(kmine[c], kbuf[c])
+                res = kmine[c]
+            stepdone[c].record(main)
+            cs.wait_event(stepdone[c])
+            with torch.cuda.stream(cs):
+                Khost.copy_(res, non_blocking=True)
+            kread[c].record(cs)
         main.wait_stream(cs)
         ev1.record()
         barrier()
@@ -352,155 +463,148 @@ def run_b200_arm(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms[0])
 
+    # ---- headline: kernel path with the inputs resident in HBM
     for _ in range(max(args.warmup, 3)):
-        step(False)
+        kernels_step(epochs, Kfull)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ms_total, launches = timed(args.steps, False)
+    ms_total, launches, _ = timed(args.steps, lambda: kernels_step(epochs, Kfull))
     clocks = sampler.stop() if rank == 0 else None
     ms_step = ms_total / args.steps
     corr_total = float(V) * V * E
     value = corr_total / (ms_step * 1e-3)
 
+    # per-rank time of the shard alone (no collective): the load balance of the equal-area partition
+    balance = None
+    if world > 1:
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dist.barrier(device_ids=[local])
+        a.record()
+        for _ in range(2):
+            engine.pack_epochs(epochs, None, prec, v_begin=start, out=op_buf)
+            Kfull[start:].zero_()
+            engine.voxel_kernels_sym(op_buf, start, n, eps, flags=flags, work=work, out=Kfull[:V])
+        b.record()
+        torch.cuda.synchronize()
+        mine = torch.tensor([a.elapsed_time(b) / 2], device=dev)
+        allms = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allms, mine)
+        balance = {"shard_ms_per_rank": [round(float(x[0]), 3) for x in allms],
+                   "shard_rows": [[s, s + m] for s, m in parts]}
+
+    # ---- e2e: host -> host
     e2e = None
     if not args.no_e2e:
-        step(True)
-        ne = max(2, min(args.steps, 3))
-        ms_seq, _ = timed(ne, True)
-        ms_seq /= ne
-        ms_e2e, how = ms_seq, "copies and kernels of a step in sequence on one stream"
-        if sym and os.environ.get("FCMA_BENCH_SEQ_E2E") != "1":
-            ne = max(8, 2 * args.steps)      # the first copy-in and the last read-back cannot hide: amortise them
-            timed_e2e_pipelined(2)
-            ms_e2e = timed_e2e_pipelined(ne) / ne
-            how = ("copy stream + double buffers: the H2D%s of step k+1 and the D2H of step k-1 run under the kernels of step k; "
-                   "all copies%s of all %d steps are inside the timed region"
-                   % (" + NCCL broadcast (second communicator)" if world > 1 else "", " and collectives" if world > 1 else "", ne))
-        e2e = {"value": corr_total / (ms_e2e * 1e-3), "unit": UNIT,
+        e2e_step()
+        ne_steps = max(2, min(args.steps, 4))
+        ms_dev, _, ms_wall = timed(ne_steps, e2e_step)
+        ms_seq = (ms_wall if world == 1 else ms_dev) / ne_steps
+        npipe = max(8, 2 * args.steps)      # the first copy-in and the last read-back cannot hide: amortise them
+        timed_e2e_pipelined(2)
+        ms_pipe = timed_e2e_pipelined(npipe) / npipe
+        share_bytes = int(ne) * T * V * 4
+        e2e = {"value": corr_total / (ms_seq * 1e-3), "unit": UNIT,
                "h2d_bytes_per_step": int(E) * T * V * 4, "d2h_bytes_per_step": int(V) * E * E * 4,
-               "ms_per_step": ms_e2e, "ms_per_step_unpipelined": ms_seq, "steps": ne,
-               "path": "pinned host epochs -> HBM -> pack -> fcma_voxel_kernels%s -> [V,E,E] kernels -> pinned host; %s"
-                       % ("_sym" if sym else "", how)}
+               "h2d_bytes_per_step_per_rank": share_bytes, "d2h_bytes_per_step_per_rank": int(Khost.numel()) * 4,
+               "ms_per_step": ms_seq, "steps": ne_steps,
+               "path": ("one fcma_host_voxel_kernels_sym call per step (C ABI, include/fcma_b200.h): pinned host epochs -> H2D "
+                        "-> pack -> symmetric pipeline -> D2H -> pinned host kernels, synchronous, timed by wall clock"
+                        if world == 1 else
+                        "per step and rank: H2D of the rank's E/N epochs over its own PCIe link -> all-gather of the shares over "
+                        "NVLink (%s) -> pack -> symmetric pipeline -> NCCL reduce-scatter -> D2H of the rank's own kernel rows; "
+                        "unpipelined, CUDA events, max over ranks" % xch.mode),
+               "epoch_exchange": xch.mode,
+               "pipelined": {"value": corr_total / (ms_pipe * 1e-3), "unit": UNIT, "ms_per_step": ms_pipe, "steps": npipe,
+                             "how": "copy stream + double buffers: input of step k+1 and read-back of step k-1 under the kernels "
+                                    "of step k; every copy and collective of all steps inside the timed region"}}
 
-    # ---- roofline of the dominant kernel, measured live with CUDA events on the launch stream
-    roofline = None
+    # ---- roofline of the step's kernels, measured live with CUDA events on the launch stream (rank 0's shard)
+    roofline, kernels = None, None
     if rank == 0:
-        import ctypes as _ct
-        op = engine.pack_epochs(epochs, None, prec)
-        planes = lib.fcma_operand_planes(_lib.PREC[prec])
-        kp = lib.fcma_operand_kp(_lib.PREC[prec], T)
-        op_bytes = lib.fcma_operand_bytes(_lib.PREC[prec], E, T, V)
+        planes = lib.fcma_operand_planes(code)
+        kp = lib.fcma_operand_kp(code, T)
+        op_bytes = lib.fcma_operand_bytes(code, E, T, V)
         nprod = 3 if planes == 2 else 1
-        # the launches of one step of this rank: (correlations stored by the GEMM, operand columns read,
-        # 256x256 tiles contracted)
-        launches_desc = []
-        # symmetric pipeline: does pass 2 read block A column-wise (no transposed copy stored) or a transposed block B?
-        cols_pass = bool(sym and lib.fcma_sym_uses_column_pass(_lib.PREC[prec], E, eps, flags))
-        pass2_elems = 0.0        # correlations read by the normalise+SYRK launches of one step
-        rows_elems = 0.0         # ... of which by the row pass over the block itself
-        if sym:
-            rpp = int(lib.fcma_sym_rows_per_pass(_lib.PREC[prec], E, eps, flags, V, start, work.buf.numel()))
-            for a in range(start, start + n, rpp):
-                nn = min(rpp, start + n - a)
-                colsA, rowsB = V - a, V - a - nn
-                nt, t256 = -(-nn // 256), -(-colsA // 256)
-                stored = float(nn) * colsA + (0.0 if cols_pass else float(rowsB) * nn)
-                launches_desc.append((stored, colsA, nt * (nt + 1) // 2 + (t256 - nt) * nt))
-                pass2_elems += float(nn) * colsA + float(rowsB) * nn
-                rows_elems += float(nn) * colsA
-        else:
-            for a in range(start, start + n, block):
-                nn = min(block, start + n - a)
-                launches_desc.append((float(nn) * V, V, -(-nn // 256) * -(-V // 256)))
-                pass2_elems += float(nn) * V
-                rows_elems += float(nn) * V
-
-        def one_pass():
-            if sym:
-                K.zero_()
-                engine.voxel_kernels_sym(op, start, n, eps, flags=flags, work=work, out=K)
-            else:
-                engine.voxel_kernels(op, op, start, n, eps, flags=flags, work=work, out=K)
-        # live per-kernel times of the SAME launches the timed step makes (events inside the C pipeline)
-        reps = 2
-        one_pass()
-        torch.cuda.synchronize()
-        lib.fcma_timing_enable(1)
-        for r in range(reps):
-            one_pass()
-        torch.cuda.synchronize()
-        g_ms, s_ms, s2_ms = _ct.c_double(0), _ct.c_double(0), _ct.c_double(0)
-        npass = lib.fcma_timing_read3(_ct.byref(g_ms), _ct.byref(s_ms), _ct.byref(s2_ms))
-        lib.fcma_timing_enable(0)
-        assert npass == reps * len(launches_desc), (npass, len(launches_desc))
-        nl = float(len(launches_desc))
-        # average launch durations: GEMM, normalise+SYRK over the rows of the block, and (symmetric pipeline) the second
-        # normalise+SYRK launch of a pass: column-direction pass over the same block, or row pass over the transposed one
-        tg, ts, ts2 = g_ms.value / npass, s_ms.value / npass, s2_ms.value / npass
-        corr_launch = sum(d[0] for d in launches_desc) * E / nl   # correlations stored per GEMM launch (average)
-        opread_launch = sum(d[1] for d in launches_desc) / nl / V * op_bytes
-        tiles_launch = sum(d[2] for d in launches_desc) / nl * E
-        rows_bytes = 4.0 * rows_elems * E / nl                    # read by the row pass over the block, per launch
-        second_bytes = 4.0 * (pass2_elems - rows_elems) * E / nl  # read by the second normalise+SYRK launch
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        tf_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
-        # algorithmic bytes of a GEMM launch: write 4 B per stored correlation + read the operand once
-        alg_bytes = 4.0 * corr_launch + opread_launch
-        flop_exec = nprod * 2.0 * kp * tiles_launch * 65536.0
-        second_name = "k_norm_syrk_cols" if cols_pass else "k_norm_syrk (transposed block)"
-        kernels = {
-            "k_corr_umma": {"ms": tg, "algorithmic_bytes": alg_bytes, "hbm_gbs": alg_bytes / (tg * 1e-3) / 1e9,
-                            # correlations delivered (each counted 2*T flops) vs MMAs actually issued
-                            # (padded K, 3 products in the hi/lo split modes, computed tiles only)
-                            "tensor_tflops_executed": flop_exec / (tg * 1e-3) / 1e12,
-                            "tensor_executed_frac_of_bf16_sustained": flop_exec / (tg * 1e-3) / 1e12 / tf_peak,
-                            "operand_planes": planes},
-            "k_norm_syrk": {"ms": ts, "algorithmic_bytes": rows_bytes, "hbm_gbs": rows_bytes / (ts * 1e-3) / 1e9}}
-        if sym and ts2 > 0:
-            kernels[second_name] = {"ms": ts2, "algorithmic_bytes": second_bytes, "hbm_gbs": second_bytes / (ts2 * 1e-3) / 1e9}
-        for kd in kernels.values():
-            kd["frac_of_hbm_peak"] = kd["hbm_gbs"] / hbm_peak
-            kd["share_of_step"] = kd["ms"] / (tg + ts + ts2)
+        rpp = int(lib.fcma_sym_rows_per_pass(code, E, eps, flags, V, start, work.buf.numel()))
+        kernels, summary = sym_kernel_table(lib, engine, torch, op_buf, start, n, V, T, E, eps, flags, work, Kfull[:V], rpp,
+                                            cols_variant, op_bytes, nprod, kp, hbm_peak, tf_peak)
         dominant = max(kernels, key=lambda k: kernels[k]["ms"])
-        traffic = None
+        traffic, traffic_src = None, None
         try:
             tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-            tag = ("symcols:rows%d" if cols_pass else "sym:rows%d") % min(rpp, 4096) if sym else "nb%d" % block
-            traffic = tr.get("%s:%s:%s" % (dominant.split(" ")[0], prec, tag))
-            if isinstance(traffic, dict):
-                # symmetric pipeline: launches differ in size; the ncu capture is the first (largest) launch, so the
-                # measured DRAM-bytes / algorithmic-bytes ratio of that launch is applied to the average launch
-                traffic = traffic["ratio"] * kernels[dominant]["algorithmic_bytes"]
+            tag = "symcols:rows%d" % min(rpp, 4096)
+            ent = tr.get("%s:%s:%s" % (dominant.split(" ")[0], prec, tag)) or \
+                tr.get("%s:%s:%s" % (dominant.split(" ")[0].replace("umma2", "umma"), prec, tag))
+            if isinstance(ent, dict):
+                traffic = ent["ratio"] * kernels[dominant]["algorithmic_bytes"]
+                traffic_src = ("static: dram bytes / algorithmic bytes = %.3f of the first (largest) launch under ncu --set full "
+                               "(profiles/traffic.json), applied to the average launch" % ent["ratio"])
         except Exception:
             pass
         ach = kernels[dominant]["hbm_gbs"]
+        # step level: bytes the design moves per step (block written once, read by the row pass and by the column pass,
+        # operand read once per pass) against the HBM peak, and the delivered flops (2T + E + 1 per
+        # correlation) against the sustained tensor peak
+        flop_per_corr = 2.0 * T + E + 1
         roofline = {"kernel": dominant, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": ach / hbm_peak, "traffic": traffic,
-                    "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
-                    "launch_ms": kernels[dominant]["ms"],
-                    "launches_per_step": int(nl), "rows_per_launch": rpp if sym else block,
-                    "pipeline": ("symmetric (blocks on/above the diagonal stored once, read row-wise and column-wise)" if cols_pass
-                                 else "symmetric (blocks on/above the diagonal, each stored twice)" if sym else "plain"),
+                    "frac": ach / hbm_peak, "traffic": traffic, "traffic_source": traffic_src,
+                    "peak_source": peak_src, "launch_ms": kernels[dominant]["ms"],
+                    "launches_per_step": summary["passes"], "rows_per_launch": rpp,
                     "algorithmic_bytes_per_launch": kernels[dominant]["algorithmic_bytes"],
-                    "kernels": kernels}
+                    "tensor": {"delivered_tflops": value * flop_per_corr / 1e12, "peak_tflops": tf_peak,
+                               "frac": value * flop_per_corr / 1e12 / tf_peak,
+                               "flop_per_corr": flop_per_corr, "note": "SURVEY §8d delivered flops (one product, symmetric halves not "
+                               "double counted) / sustained cuBLAS bf16 peak; the fp32-faithful split EXECUTES 3 products"},
+                    "step": {"algorithmic_bytes": summary["step_bytes"] * (world if world > 1 else 1),
+                             "hbm_frac": summary["step_bytes"] / (summary["sum_ms"] * 1e-3) / 1e9 / hbm_peak,
+                             "note": "bytes the two-pass design moves per step (rank 0's shard) / (sum of its kernel times x HBM peak)"},
+                    "pipeline": "symmetric (blocks on/above the diagonal stored once, read row-wise and column-wise)" if cols_variant
+                                else "symmetric (blocks on/above the diagonal, each stored twice)"}
+
+    # ---- parity against the UNMODIFIED reference at the full shape: three 64-row samples
+    parity = None
+    samples = sample_starts(V, block)
+    if not args.no_cpu_baseline or world > 1:
+        kernels_step(epochs, Kfull)
+        rows = {}
+        if world > 1:
+            # the reduce-scattered result: sample rows live on the rank that owns them
+            for (s0, n0) in samples:
+                owner = min(s0 // per, world - 1)
+                buf = torch.zeros((n0, E, E), device=dev)
+                if rank == owner:
+                    buf.copy_(Kmine[s0 - owner * per: s0 - owner * per + n0])
+                dist.broadcast(buf, src=owner)
+                rows[s0] = buf
+        else:
+            rows = {s0: Kfull[s0:s0 + n0].clone() for (s0, n0) in samples}
+        if rank == 0 and host_all is not None:
+            host_threads()
+            raw_list = [host_all[e].numpy() for e in range(E)]
+            res = parity_samples(raw_list, eps, samples, rows, engine, dev)
+            if res is not None:
+                parity = {"vs": "unmodified reference (oracle/_ref) on the host, same inputs; kernels after the decimal shrink, "
+                                "CV accuracies of its scikit-learn path vs the batched GPU SVM",
+                          "pipeline": "symmetric, %d GPU%s%s" % (world, "s" if world > 1 else "",
+                                                                 " (after the NCCL reduce-scatter)" if world > 1 else ""),
+                          "samples": res,
+                          "max_abs_dK_over_max_K": max(r["max_abs_dK_over_max_K"] for r in res),
+                          "cv_accuracy_identical": sum(r["cv_accuracy_identical"] for r in res),
+                          "cv_accuracy_total": sum(r["cv_accuracy_total"] for r in res)}
 
     # ---- the public API end to end: VoxelSelector.run(clf) incl. the batched GPU SVM cross-validation
     run_api = None
     if rank == 0 and world == 1 and not args.no_e2e:
         from sklearn import svm as _svm
-        raw_list = [host[e].numpy() for e in range(E)]
+        raw_list = [host_all[e].numpy() for e in range(E)]
         labels = [e % 2 for e in range(E)]
         clf = _svm.SVC(kernel="precomputed", shrinking=False, C=1)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         vs = VoxelSelector(labels, eps, E // eps, raw_list, voxel_unit=64, process_num=0, precision=prec,
-                           block_rows=block, symmetric=sym)
+                           block_rows=block)
         vs._work = work
         res = vs.run(clf)
         torch.cuda.synchronize()
@@ -514,96 +618,19 @@ def run_b200_arm(args):
 
     cpu_baseline = None
     if rank == 0 and not args.no_cpu_baseline and world == 1:
-        fn, kind, cores = reference_task_fn(host, eps)
-        rows, tsum, ntask = 64, 0.0, 0
-        fn(0, rows)
-        t_start = time.perf_counter()
-        while ntask < 8 and (time.perf_counter() - t_start) < 20.0:
-            tsum += fn((ntask + 1) * rows, rows)
-            ntask += 1
-        cpu_baseline = {"value": ntask * rows * float(V) * E / tsum, "unit": UNIT, "cores": cores, "kind": kind,
-                        "sample": "%d tasks of 64 voxel rows x V=%d x E=%d, kernel path a4+a6+a7 "
-                                  "(reference voxelselector.py:492-505), no CV" % (ntask, V, E)}
+        fn, kind, cores = reference_task_fn(host_all, eps)
+        med, done, times = time_reference_tasks(fn, V, 20, 25.0)
+        cpu_baseline = {"value": 64 * float(V) * E / med, "unit": UNIT, "cores": cores, "kind": kind,
+                        "sample": "median of %d tasks of 64 voxel rows x V=%d x E=%d, kernel path a4+a6+a7 "
+                                  "(reference voxelselector.py:492-505), no CV; %d threads" % (done, V, E, cores),
+                        "task_ms_min_median_max": [1e3 * min(times), 1e3 * med, 1e3 * max(times)]}
 
-    # ---- the other BASELINE.json configs that share this path (informational, short)
+    # ---- the other BASELINE.json configs on the same path, each with its own roofline and parity sample
     others = None
-    if rank == 0 and world == 1 and not args.no_e2e:
-        others = {}
-        op = engine.pack_epochs(epochs, None, prec)
-
-        def ev_time(fn, reps=2):
-            fn()
-            torch.cuda.synchronize()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            for _ in range(reps):
-                fn()
-            b.record()
-            torch.cuda.synchronize()
-            return a.elapsed_time(b) / reps
-        # configs[4]: Classifier precomputed corr-kernel matrix, V=50 000, E=32 (one [E,E] kernel)
-        Kc = torch.zeros((E, E), dtype=torch.float32, device=dev)
-        ms_c = ev_time(lambda: engine.classifier_kernel(op, op, 0, V, eps, work=work, out=Kc), reps=1)
-        others["classifier_kernel_V%d_E%d" % (V, E)] = {"ms": ms_c, "value": corr_total / (ms_c * 1e-3), "unit": UNIT}
-        # explicit reduced precision (BASELINE configs[2] wording "bf16/fp32-accum")
-        opb = engine.pack_epochs(epochs, None, "bf16")
-
-        def whole(o, fl):        # all V rows with the pipeline of the headline (symmetric or plain)
-            if sym:
-                K.zero_()
-                engine.voxel_kernels_sym(o, 0, V, eps, flags=fl, work=work, out=K)
-            else:
-                engine.voxel_kernels(o, o, 0, V, eps, flags=fl, work=work, out=K)
-        ms_b = ev_time(lambda: whole(opb, 0), reps=2)
-        others["voxel_kernels_bf16_operands"] = {"ms": ms_b, "value": corr_total / (ms_b * 1e-3), "unit": UNIT,
-                                                 "note": "|dr| <= 8e-3, fp16 Fisher-z intermediate; the headline uses "
-                                                         "the fp32-faithful fp16x3 split with an fp32 intermediate"}
-        # the headline operands with the opt-in fp16 intermediate (max|dK|/max|K| ~ 1.8e-5)
-        ms_h = ev_time(lambda: whole(op, _lib.FLAG_F16_INTERMEDIATE), reps=2)
-        others["voxel_kernels_f16_intermediate"] = {"ms": ms_h, "value": corr_total / (ms_h * 1e-3), "unit": UNIT,
-                                                    "note": "headline operands (%s), FCMA_FLAG_F16_INTERMEDIATE" % prec}
-        if sym:      # the plain pipeline (every row block against all columns; what two-mask runs use)
-            wp = engine.Workspace(E, V, block, dev)
-            Kp = torch.empty((V, E, E), dtype=torch.float32, device=dev)
-            ms_p = ev_time(lambda: engine.voxel_kernels(op, op, 0, V, eps, work=wp, out=Kp), reps=2)
-            whole(op, 0)
-            others["voxel_kernels_plain_pipeline"] = {
-                "ms": ms_p, "value": corr_total / (ms_p * 1e-3), "unit": UNIT,
-                "max_abs_dK_over_max_K_vs_symmetric": float((Kp - K).abs().max() / Kp.abs().max()),
-                "note": "fcma_voxel_kernels: no use of the symmetry (two-mask runs, symmetric=False)"}
-            del wp, Kp
-        del opb, op
-
-    # ---- direct parity at the full shape: 64 rows through the UNMODIFIED reference vs the GPU pipeline
-    parity = None
-    if rank == 0 and cpu_baseline is not None and cpu_baseline["kind"] == "reference":
-        from oracle import reference
-        from sklearn import svm as _svm
-        m = reference.load()
-        raw_list = [host[e].numpy() for e in range(E)]
-        labels = [e % 2 for e in range(E)]
-        clf = _svm.SVC(kernel="precomputed", shrinking=False, C=1)
-        rvs = m.VoxelSelector(labels, eps, E // eps, raw_list, voxel_unit=64, process_num=0)
-        s0, n0 = 128, 64
-        corr = rvs._correlation_computation((s0, n0))
-        m.fcma_extension.normalization(corr, eps)
-        Kref = rvs._prepare_for_cross_validation(corr, clf)          # shrunk kernels [64, E, E]
-        acc_ref = np.array([a for _, a in rvs._do_cross_validation(clf, Kref, (s0, n0))])
-        op = engine.pack_epochs(epochs, None, prec)
-        if sym:      # the kernels of the timed (symmetric) pipeline for these rows
-            K.zero_()
-            engine.voxel_kernels_sym(op, 0, V, eps, flags=flags, work=work, out=K)
-            Kg = K[s0:s0 + n0].clone()
-        else:
-            Kg = engine.voxel_kernels(op, op, s0, n0, eps, work=work)
-        engine.shrink_kernels_(Kg)
-        acc_gpu = engine.svm_cv_precomputed(Kg, labels, E // eps, C=1.0, tol=1e-3)
-        Kg = Kg.cpu().numpy()
-        parity = {"rows": [s0, s0 + n0], "vs": "unmodified reference (oracle/_ref) on the host, same inputs",
-                  "pipeline": "symmetric" if sym else "plain",
-                  "max_abs_dK_over_max_K": float(np.max(np.abs(Kg - Kref)) / np.max(np.abs(Kref))),
-                  "cv_accuracy_identical": int(np.sum(acc_gpu == acc_ref)), "cv_accuracy_total": int(n0),
-                  "max_abs_d_accuracy": float(np.max(np.abs(acc_gpu - acc_ref)))}
+    if not args.no_others:
+        del work, op_buf
+        torch.cuda.empty_cache()
+        others = other_configs(args, lib, engine, torch, dist, dev, rank, world, local, hbm_peak, tf_peak)
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -612,26 +639,216 @@ def run_b200_arm(args):
                 "dtype": {"fp16x3": "f16x3 (hi/lo split, f32 accumulate)", "tf32x3": "tf32x3 (hi/lo split, f32 accumulate)",
                           "bf16x3": "bf16x3", "tf32": "tf32", "bf16": "bf16"}.get(prec, prec),
                 "data": "synthetic",
-                "config": {"workload": "FCMA VoxelSelector V=%d T=%d E=%d eps=%d (BASELINE configs[2] shape)" % (V, T, E, eps),
+                "config": {"workload": workload_string(V, T, E, eps),
                            "precision": prec + (" (3-product hi/lo split, fp32-faithful: |dr| <= 1e-6)" if prec in ("tf32x3", "fp16x3") else ""),
                            "parallelism": "rows%d" % world, "rows_per_pass": block,
-                           "pipeline": ("symmetric self-correlation: blocks on/above the diagonal contracted once, used for "
-                                        "row and column voxels; shards = equal-area row ranges" if sym else
-                                        "plain: every row block against all columns"),
+                           "pipeline": "symmetric self-correlation: blocks on/above the diagonal contracted once, used for row and "
+                                       "column voxels; shards = equal-area row ranges",
                            "l2": "inputs_exceed_l2 (operand %.1f GB, correlation block %.1f GB per pass)"
-                                 % (lib.fcma_operand_bytes(_lib.PREC[prec], E, T, V) / 1e9,
-                                    lib.fcma_work_bytes_per_row(E, V) * block / 1e9),
+                                 % (lib.fcma_operand_bytes(code, E, T, V) / 1e9, lib.fcma_work_bytes_per_row(E, V) * block / 1e9),
                            "step": "pack + corr GEMM + Fisher/z-score + kernel build for all V rows"
-                                   + ("; epochs replicated in every rank's HBM beforehand, NCCL %s of the kernels inside the step; " % ("reduce (sum of the shards' partial [V,E,E] arrays)" if sym else "gather")
-                                      +
-                                      "e2e adds H2D on rank 0 + NCCL broadcast + D2H" if world > 1 else "")},
-                "gpu_launches": launches, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu_baseline,
-                "voxel_selection_run": run_api, "parity_vs_reference": parity, "other_configs": others,
-                "clocks": clocks}
+                                   + ("; epochs replicated in every rank's HBM beforehand, one NCCL reduce-scatter of the partial "
+                                      "[V,E,E] kernels inside the step (every rank keeps the rows it cross-validates)" if world > 1 else "")},
+                "gpu_launches": launches, "e2e": e2e, "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu_baseline,
+                "voxel_selection_run": run_api, "parity_vs_reference": parity, "load_balance": balance,
+                "other_configs": others, "clocks": clocks}
         print_json(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def sym_kernel_table(lib, engine, torch, op, start, n, V, T, E, eps, flags, work, K, rpp, cols_pass, op_bytes, nprod, kp,
+                     hbm_peak, tf_peak, reps=2):
+    """Live per-kernel times (CUDA events inside the C pipeline, fcma_timing_*) of the launches of one symmetric step over
+    rows [start, start+n), with the algorithmic bytes of each kernel: GEMM = 4 B per stored correlation + operand read
+    once; row pass = the block read once; column pass = the block right of the diagonal part read once."""
+    import ctypes as _ct
+    esz = 4.0
+    launches_desc, pass2, rows_el = [], 0.0, 0.0
+    for a in range(start, start + n, rpp):
+        nn = min(rpp, start + n - a)
+        colsA, rowsB = V - a, V - a - nn
+        nt, t256 = -(-nn // 256), -(-colsA // 256)
+        stored = float(nn) * colsA + (0.0 if cols_pass else float(rowsB) * nn)
+        launches_desc.append((stored, colsA, nt * (nt + 1) // 2 + (t256 - nt) * nt))
+        pass2 += float(nn) * colsA + float(rowsB) * nn
+        rows_el += float(nn) * colsA
+
+    def one_pass():
+        K[start:].zero_()
+        engine.voxel_kernels_sym(op, start, n, eps, flags=flags, work=work, out=K)
+    one_pass()
+    torch.cuda.synchronize()
+    lib.fcma_timing_enable(1)
+    for _ in range(reps):
+        one_pass()
+    torch.cuda.synchronize()
+    g_ms, s_ms, s2_ms = _ct.c_double(0), _ct.c_double(0), _ct.c_double(0)
+    npass = lib.fcma_timing_read3(_ct.byref(g_ms), _ct.byref(s_ms), _ct.byref(s2_ms))
+    lib.fcma_timing_enable(0)
+    assert npass == reps * len(launches_desc), (npass, len(launches_desc))
+    nl = float(len(launches_desc))
+    tg, ts, ts2 = g_ms.value / npass, s_ms.value / npass, s2_ms.value / npass
+    corr_launch = sum(d[0] for d in launches_desc) * E / nl
+    opread = sum(d[1] for d in launches_desc) / nl / V * op_bytes
+    tiles = sum(d[2] for d in launches_desc) / nl * E
+    rows_bytes = esz * rows_el * E / nl
+    second_bytes = esz * (pass2 - rows_el) * E / nl
+    alg = esz * corr_launch + opread
+    flop_exec = nprod * 2.0 * kp * tiles * 65536.0
+    kernels = {
+        "k_corr_umma2": {"ms": tg, "algorithmic_bytes": alg, "hbm_gbs": alg / (tg * 1e-3) / 1e9,
+                         "tensor_tflops_executed": flop_exec / (tg * 1e-3) / 1e12,
+                         "tensor_executed_frac_of_bf16_sustained": flop_exec / (tg * 1e-3) / 1e12 / tf_peak},
+        "k_norm_syrk": {"ms": ts, "algorithmic_bytes": rows_bytes, "hbm_gbs": rows_bytes / (ts * 1e-3) / 1e9}}
+    if ts2 > 0:
+        name = "k_norm_syrk_cols" if cols_pass else "k_norm_syrk (transposed block)"
+        kernels[name] = {"ms": ts2, "algorithmic_bytes": second_bytes, "hbm_gbs": second_bytes / (ts2 * 1e-3) / 1e9}
+    for kd in kernels.values():
+        kd["frac_of_hbm_peak"] = kd["hbm_gbs"] / hbm_peak
+        kd["share_of_step"] = kd["ms"] / (tg + ts + ts2)
+        kd["ms_per_step"] = kd["ms"] * nl
+    step_bytes = (alg + rows_bytes + second_bytes) * nl
+    return kernels, {"passes": int(nl), "step_bytes": step_bytes, "sum_ms": (tg + ts + ts2) * nl}
+
+
+def other_configs(args, lib, engine, torch, dist, dev, rank, world, local, hbm_peak, tf_peak):
+    """BASELINE.json configs[1] (V=30 000 T=200 E=16, 1 GPU), configs[3] (V=100 000 T=500 E=64, row shards over all
+    ranks) and configs[4] (Classifier kernel, V=50 000 E=32, 1 GPU): device-timed step, per-kernel roofline and one parity
+    sample through the unmodified reference each.  Inputs are generated on the device (identical on every rank)."""
+    from brainiak_b200 import _lib
+    from brainiak_b200.fcma.voxelselector import VoxelSelector
+    out = {}
+    prec = args.precision
+    code = _lib.PREC[prec]
+
+    def run_cfg(name, V, T, E, eps, rows_req, sharded, ref_rows=32):
+        w = world if sharded else 1
+        if not sharded and rank != 0:
+            return
+        start, n = engine.sym_row_partition(V, w)[rank if sharded else 0]
+        ep = device_epochs(V, T, E, dev, seed=SEED + 17 * E + T)
+        op = engine.pack_epochs(ep, None, prec, v_begin=start)
+        cols = bool(lib.fcma_sym_uses_column_pass(code, E, eps, 0))
+        per_row = (1 if cols else 2) * lib.fcma_work_bytes_per_row(E, V - start)
+        free, _ = torch.cuda.mem_get_info(dev)
+        rows = max(256, min(rows_req, (n + 255) // 256 * 256, int((free - (6 << 30)) // per_row) // 256 * 256))
+        work = engine.SymWorkspace(E, V, rows, dev, start=start, transposed_copy=not cols)
+        per = VoxelSelector.row_partition(V, w)[0][1]
+        K = torch.zeros((w * per, E, E), dtype=torch.float32, device=dev)
+        Kmine = torch.empty((per, E, E), dtype=torch.float32, device=dev) if w > 1 else None
+
+        def step():
+            engine.pack_epochs(ep, None, prec, v_begin=start, out=op)
+            K[start:].zero_()
+            engine.voxel_kernels_sym(op, start, n, eps, work=work, out=K[:V])
+            if w > 1:
+                dist.reduce_scatter_tensor(Kmine, K)
+        step()
+        if w > 1:
+            dist.barrier(device_ids=[local])
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 2
+        a.record()
+        for _ in range(reps):
+            step()
+        b.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([a.elapsed_time(b) / reps], device=dev)
+        if w > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        ms = float(ms[0])
+        corr_total = float(V) * V * E
+        # parity sample: the reference on the host for ref_rows rows of the tail of rank 0's shard ... of the whole job
+        samples = [(min(V - ref_rows, (V // 2 // 256) * 256 + 32), ref_rows)]
+        rows_k = {}
+        for (s0, n0) in samples:
+            if w > 1:
+                owner = min(s0 // per, w - 1)
+                buf = torch.zeros((n0, E, E), device=dev)
+                if rank == owner:
+                    buf.copy_(Kmine[s0 - owner * per: s0 - owner * per + n0])
+                dist.broadcast(buf, src=owner)
+                rows_k[s0] = buf
+            else:
+                rows_k[s0] = K[s0:s0 + n0].clone()
+        entry = None
+        if rank == 0:
+            planes = lib.fcma_operand_planes(code)
+            rpp = int(lib.fcma_sym_rows_per_pass(code, E, eps, 0, V, start, work.buf.numel()))
+            kern, summ = sym_kernel_table(lib, engine, torch, op, start, n, V, T, E, eps, 0, work, K[:V], rpp, cols,
+                                          lib.fcma_operand_bytes(code, E, T, V), 3 if planes == 2 else 1,
+                                          lib.fcma_operand_kp(code, T), hbm_peak, tf_peak, reps=1)
+            dom = max(kern, key=lambda k: kern[k]["ms"])
+            flop_per_corr = 2.0 * T + E + 1
+            entry = {"workload": "FCMA VoxelSelector V=%d T=%d E=%d eps=%d" % (V, T, E, eps), "n_gpus": w,
+                     "ms_per_step": ms, "value": corr_total / (ms * 1e-3), "unit": UNIT, "rows_per_pass": rpp,
+                     "pipeline": "symmetric, " + ("column pass over the stored block" if cols else
+                                                  "transposed copy of every block + row pass (E > 32)"),
+                     "roofline": {"kernel": dom, "bound": "hbm", "achieved": kern[dom]["hbm_gbs"], "peak": hbm_peak,
+                                  "unit": "GB/s", "frac": kern[dom]["frac_of_hbm_peak"],
+                                  "tensor_frac": corr_total / (ms * 1e-3) * flop_per_corr / 1e12 / tf_peak,
+                                  "step_hbm_frac": summ["step_bytes"] / (summ["sum_ms"] * 1e-3) / 1e9 / hbm_peak},
+                     "kernels": {k: {"ms_per_step": v["ms_per_step"], "frac_of_hbm_peak": v["frac_of_hbm_peak"]} for k, v in kern.items()}}
+            if not args.no_cpu_baseline or w > 1:
+                host_threads()
+                hostep = ep.cpu()
+                raw_list = [hostep[e].numpy() for e in range(E)]
+                res = parity_samples(raw_list, eps, samples, rows_k, engine, dev)
+                entry["parity_vs_reference"] = res[0] if res else None
+                del hostep, raw_list
+            out[name] = entry
+        del work, K, op, ep
+        torch.cuda.empty_cache()
+
+    run_cfg("configs[1] V=30000 T=200 E=16 (1 GPU)", 30000, 200, 16, 8, 4096, sharded=False)
+    if os.environ.get("FCMA_BENCH_SKIP_CONFIG3") != "1":
+        run_cfg("configs[3] V=100000 T=500 E=64 (%d GPU%s)" % (world, "s" if world > 1 else ""), 100000, 500, 64, 8,
+                2048, sharded=True, ref_rows=16)
+    if rank == 0:
+        # configs[4]: Classifier precomputed corr-kernel matrix, V=50 000 E=32: ONE [E, E] kernel = sum over all voxel rows
+        V, T, E, eps = 50000, 200, 32, 8
+        ep = device_epochs(V, T, E, dev, seed=SEED + 4)
+        op = engine.pack_epochs(ep, None, prec)
+        work = engine.SymWorkspace(E, V, 4096, dev, transposed_copy=False)
+        Kc = torch.zeros((E, E), dtype=torch.float32, device=dev)
+        engine.classifier_kernel(op, op, 0, V, eps, work=work, out=Kc)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        Kc.zero_()
+        engine.classifier_kernel(op, op, 0, V, eps, work=work, out=Kc)
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b)
+        # parity: K_classifier == sum of the per-voxel kernels (fp64 sum on the GPU), and sampled per-voxel kernels against
+        # the reference's own (the full reference run of this config is ~0.5 h of CPU)
+        Kv = torch.zeros((V, E, E), dtype=torch.float32, device=dev)
+        engine.voxel_kernels_sym(op, 0, V, eps, work=work, out=Kv)
+        Ksum = Kv.to(torch.float64).sum(0)
+        ent = {"workload": "FCMA Classifier precomputed corr-kernel matrix V=%d T=%d E=%d eps=%d (one [E,E] kernel)" % (V, T, E, eps),
+               "n_gpus": 1, "ms_per_step": ms, "value": float(V) * V * E / (ms * 1e-3), "unit": UNIT,
+               "pipeline": "symmetric pipeline + sum over the voxel kernels (engine.classifier_kernel)",
+               "max_abs_dK_vs_fp64_sum_of_voxel_kernels": float((Kc.to(torch.float64) - Ksum).abs().max() / Ksum.abs().max())}
+        code = _lib.PREC[prec]
+        kern, summ = sym_kernel_table(lib, engine, torch, op, 0, V, V, T, E, eps, 0, work, Kv, 4096, True,
+                                      lib.fcma_operand_bytes(code, E, T, V), 3 if lib.fcma_operand_planes(code) == 2 else 1,
+                                      lib.fcma_operand_kp(code, T), hbm_peak, tf_peak, reps=1)
+        dom = max(kern, key=lambda k: kern[k]["ms"])
+        ent["roofline"] = {"kernel": dom, "bound": "hbm", "achieved": kern[dom]["hbm_gbs"], "peak": hbm_peak, "unit": "GB/s",
+                           "frac": kern[dom]["frac_of_hbm_peak"],
+                           "step_hbm_frac": summ["step_bytes"] / (summ["sum_ms"] * 1e-3) / 1e9 / hbm_peak}
+        if not args.no_cpu_baseline:
+            host_threads()
+            hostep = ep.cpu()
+            raw_list = [hostep[e].numpy() for e in range(E)]
+            s0 = (V // 2 // 256) * 256 + 32
+            res = parity_samples(raw_list, eps, [(s0, 32)], {s0: Kv[s0:s0 + 32].clone()}, engine, dev)
+            ent["parity_vs_reference_voxel_kernels"] = res[0] if res else None
+        out["configs[4] Classifier kernel V=50000 E=32 (1 GPU)"] = ent
+    return out if rank == 0 else None
 
 
 def main():

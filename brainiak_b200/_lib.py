@@ -19,7 +19,7 @@ FLAG_F16_INTERMEDIATE = 4   # fp16 internal Fisher-z block (default only in the 
 # alternate code paths with the same results (tests compare them against the defaults)
 FLAG_STRIDED_BLOCK = 8      # strided [nb][E][ld] correlation block instead of the tiled one
 FLAG_SYM_TRANSPOSED = 16    # symmetric pipeline: transposed copy + row pass instead of the column-direction pass
-FLAG_COLS_LDGSTS = 32       # column-direction pass fed by cp.async instead of TMA bricks
+FLAG_COLS_TMA = 32          # column-direction pass fed by TMA bricks + mbarrier ring instead of cp.async (E % 4 == 0)
 
 c_void_p, c_int, c_long, c_size_t, c_float = (ctypes.c_void_p, ctypes.c_int, ctypes.c_long,
                                                ctypes.c_size_t, ctypes.c_float)
@@ -36,6 +36,8 @@ SIGNATURES = {
     "fcma_operand_bytes": (c_size_t, [c_int, c_int, c_int, c_long]),
     "fcma_pack_operand": (c_int, [c_void_p, c_int, c_int, c_long, c_long, c_int_p, c_int, c_int,
                                   c_void_p, c_size_t, c_void_p]),
+    "fcma_pack_operand_range": (c_int, [c_void_p, c_int, c_int, c_long, c_long, c_int_p, c_int, c_int, c_long, c_long,
+                                        c_void_p, c_size_t, c_void_p]),
     "fcma_epoch_normalize": (c_int, [c_void_p, c_int, c_int, c_long, c_long, c_int_p, c_void_p]),
     "fcma_corr_block": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_long, c_long, c_long,
                                 c_long, c_void_p, c_long, c_long, c_int, c_void_p]),
@@ -65,6 +67,12 @@ SIGNATURES = {
     "fcma_host_voxel_kernels": (c_int, [c_float_pp, c_float_pp, c_int_p, c_int, c_long, c_long,
                                         c_long, c_long, c_int, c_int, c_int, c_int, c_int,
                                         c_void_p]),
+    "fcma_host_voxel_kernels_sym": (c_int, [c_float_pp, c_int_p, c_int, c_long, c_int, c_int, c_int, c_int, c_int, c_long,
+                                            c_void_p]),
+    "fcma_ipc_get_handle": (c_int, [c_void_p, c_void_p, ctypes.POINTER(c_size_t)]),
+    "fcma_ipc_open_handle": (c_int, [c_void_p, ctypes.POINTER(c_void_p)]),
+    "fcma_ipc_close_handle": (c_int, [c_void_p]),
+    "fcma_peer_copy_async": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
     "fcma_host_within_subject_norm": (c_int, [c_void_p, c_long, c_int, c_long, c_int, c_int]),
     "fcma_launch_count": (c_long, []),
     "fcma_timing_enable": (None, [c_int]),

@@ -224,18 +224,18 @@ __device__ __forceinline__ float tf32_rn(float x)
 template <int KIND, int PLANES>
 __global__ void __launch_bounds__(256) k_pack_operand(const float *__restrict__ src, int E, int T, long V, long ld,
                                                       const int *__restrict__ T_e, int normalize, void *dst, int Kp,
-                                                      float *__restrict__ selfdiag, float in_scale)
+                                                      float *__restrict__ selfdiag, float in_scale, long v_begin, long v_end)
 {
     __shared__ double s_red[8][33];
     __shared__ float s_mean[32], s_scale[32];
     __shared__ float s_tile[32][65];
     const int e = blockIdx.y;
-    const long v0 = (long)blockIdx.x * 32;
+    const long v0 = v_begin + (long)blockIdx.x * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int Te = T_e ? T_e[e] : T;
     const float *ep = src + (size_t)e * T * ld;
     const long v = v0 + tx;
-    const bool vok = v < V;
+    const bool vok = v < v_end;   // voxels [v_begin, v_end) of the V-voxel layout
 
     float mean = 0.f, scale = 1.f;
     if (normalize) {
@@ -272,19 +272,10 @@ __global__ void __launch_bounds__(256) k_pack_operand(const float *__restrict__ 
 
     // Exact self-correlation of each voxel: the reference's sgemm (OpenBLAS FMA micro-kernel) is
     // bit-identical to a sequential fp32 FMA chain over t (verified against reference outputs,
-    // tests/golden), so this reproduces its r[i,e,i] = 1 +- ulp rounding pattern exactly.
-    if (ty == 0 && vok) {
-        float acc = 0.f;
-        for (int t = 0; t < Te; t++) {
-            float x = ep[(size_t)t * ld + v];
-            if (normalize) {
-                x = (x - mean) * scale;
-                if (!(x == x)) x = 0.f;
-            }
-            acc = fmaf(x, x, acc);
-        }
-        selfdiag[(size_t)e * V + v] = acc;
-    }
+    // tests/golden), so this reproduces its r[i,e,i] = 1 +- ulp rounding pattern exactly.  Warp 0 runs the chain
+    // on the values of each slab while they sit in shared memory (rows t >= Te hold 0 and leave it unchanged):
+    // no extra pass over the epoch in HBM.
+    float diag_acc = 0.f;
     const size_t plane_stride = (size_t)E * V * Kp;
     for (int k0 = 0; k0 < Kp; k0 += 64) {
         // load a [64 t][32 v] slab coalesced along v, transpose through smem
@@ -301,10 +292,17 @@ __global__ void __launch_bounds__(256) k_pack_operand(const float *__restrict__ 
             s_tile[tx][tt] = x;
         }
         __syncthreads();
+        if (ty == 0) {
+#pragma unroll 16
+            for (int tt = 0; tt < 64; tt++) {
+                const float x = s_tile[tx][tt];
+                diag_acc = fmaf(x, x, diag_acc);
+            }
+        }
         // 8 warps x 4 voxels; a warp writes 64 consecutive k of one voxel row
         for (int vv = ty * 4; vv < ty * 4 + 4; vv++) {
             long vo = v0 + vv;
-            if (vo >= V) continue;
+            if (vo >= v_end) continue;
             for (int kk = tx; kk < 64; kk += 32) {
                 int k = k0 + kk;
                 if (k >= Kp) continue;
@@ -331,6 +329,7 @@ __global__ void __launch_bounds__(256) k_pack_operand(const float *__restrict__ 
         }
         __syncthreads();
     }
+    if (ty == 0 && vok) selfdiag[(size_t)e * V + v] = diag_acc;
 }
 
 // a14 in place on [E][T][ld]
@@ -2114,7 +2113,7 @@ __global__ void __launch_bounds__(32 * (32 / CPW), 1)
 }
 
 // ============================================================================================
-// Column-direction pass, TMA version (default when E % 4 == 0): same arithmetic as k_norm_syrk_cols, but
+// Column-direction pass, TMA version (FCMA_FLAG_COLS_TMA, needs E % 4 == 0): same arithmetic as k_norm_syrk_cols, but
 //   * a brick [32 epochs][16 rows][32 columns] arrives through ONE 5-D bulk tensor copy (UTMALDG) issued by one elected
 //     lane -- the 4096 LDGSTS per brick (8 LSU cycles each, the same port the LDS reads need) and their address
 //     arithmetic are gone;
@@ -2132,11 +2131,13 @@ __global__ void __launch_bounds__(32 * (32 / CPW), 1)
 // accumulator rows / columns >= E, which are never written back.
 // HALF: fp16 block, 64-byte lines, 64-byte swizzle, LDS.64 (two-way conflicts as in the cp.async version).
 // ============================================================================================
-template <int EPS, bool HALF>
-__global__ void __launch_bounds__(256, 1)
-    k_norm_syrk_cols_tma(const __grid_constant__ CUtensorMap tmA, long n, int E, long n2, long T256, long c0, float *K)
+// CPW = 4: 8 warps x 4 columns (255 registers); CPW = 2: 16 warps x 2 columns (<= 128 registers, LDS.64)
+template <int EPS, bool HALF, int CPW>
+__global__ void __launch_bounds__(32 * (32 / CPW), 1)
+    k_norm_syrk_cols_tma(const __grid_constant__ CUtensorMap tmA, int n, int E, int n2, int T256, int c0, float *K)
 {
-    constexpr int R = 4, EP = 32, MT = 2, NT = 4, CPW = 4, NTHR = 256;
+    static_assert(CPW == 4 || (CPW == 2 && !HALF), "2 columns per warp only for the fp32 block");
+    constexpr int R = 4, EP = 32, MT = 2, NT = 4, NTHR = 32 * (32 / CPW);
     constexpr uint32_t BRICK = HALF ? 32768u : 65536u;
     constexpr uint32_t RING_BYTES = 196608u;   // 3 fp32 bricks; the fold buffer [32 columns][EP*EP] fp32 (128 KB) overlays it
     extern __shared__ __align__(1024) uint8_t cs_raw[];
@@ -2149,8 +2150,8 @@ __global__ void __launch_bounds__(256, 1)
     const int g = lane >> 2, t = lane & 3;
     const int S_eps = (E / EPS) * EPS;
     const int e4 = E >> 2;
-    const long nstrips = (n2 - c0 + 31) / 32;
-    const long nsteps = (n + 15) / 16;
+    const int nstrips = (n2 - c0 + 31) / 32;
+    const int nsteps = (n + 15) / 16;
 
     if (tid == 0) {
         tma_prefetch_desc(&tmA);
@@ -2165,25 +2166,25 @@ __global__ void __launch_bounds__(256, 1)
     // this lane's reads: line L0 = t + 4g (+ 32 sl + 128 r), 16-byte piece `warp` (fp32) / 8 bytes of piece warp/2 (fp16)
     const uint32_t L0 = (uint32_t)(t + 4 * g);
     const uint32_t rd_base = HALF ? L0 * 64u + ((((uint32_t)warp >> 1) ^ ((L0 >> 1) & 3u)) << 4) + ((uint32_t)warp & 1u) * 8u
-                                  : L0 * 128u + ((((uint32_t)warp) ^ (L0 & 7u)) << 4);
+                             : CPW == 4 ? L0 * 128u + ((((uint32_t)warp) ^ (L0 & 7u)) << 4)
+                                        : L0 * 128u + ((((uint32_t)warp >> 1) ^ (L0 & 7u)) << 4) + ((uint32_t)warp & 1u) * 8u;
     constexpr uint32_t SL_STEP = HALF ? 2048u : 4096u, R_STEP = HALF ? 8192u : 16384u;
 
     uint32_t it = 0;          // running brick count of this CTA: slot = it % 3, use = it / 3
     uint32_t slot = 0, par = 0;   // slot / parity of brick `it`
-    for (long strip = blockIdx.x; strip < nstrips; strip += gridDim.x) {
-        const long j0 = c0 + strip * 32;
+    for (int strip = blockIdx.x; strip < nstrips; strip += gridDim.x) {
+        const int j0 = c0 + strip * 32;
         const int tjx = (int)(j0 >> 8), jo = (int)(j0 & 255);
         // producer (one elected lane of warp 0): brick of row step st -> ring position idx
-        auto issue = [&](long st, uint32_t idx) {
+        auto issue = [&](int st, uint32_t idx) {
             const uint32_t sl = idx % COLS_BRICKS, use = idx / COLS_BRICKS;
             mbar_wait(&empty_bar[sl], (use & 1u) ^ 1u);       // every warp has released the slot's previous brick
             mbar_expect_tx(&full_bar[sl], BRICK);
-            const long i0 = st * 16;
-            tma_load_5d(&tmA, &full_bar[sl], brick0 + sl * BRICK, jo, 0, (int)(((i0 >> 8) * T256 + tjx) * e4),
-                        (int)((i0 & 255) >> 2), 0);
+            const int i0 = st * 16;
+            tma_load_5d(&tmA, &full_bar[sl], brick0 + sl * BRICK, jo, 0, ((i0 >> 8) * T256 + tjx) * e4, (i0 & 255) >> 2, 0);
         };
-        for (long seg0 = 0; seg0 < nsteps; seg0 += COLS_SEG_STEPS) {
-            const long seg1 = seg0 + COLS_SEG_STEPS < nsteps ? seg0 + COLS_SEG_STEPS : nsteps;
+        for (int seg0 = 0; seg0 < nsteps; seg0 += COLS_SEG_STEPS) {
+            const int seg1 = seg0 + COLS_SEG_STEPS < nsteps ? seg0 + COLS_SEG_STEPS : nsteps;
             float acc[CPW][MT][NT][4];
 #pragma unroll
             for (int c = 0; c < CPW; c++)
@@ -2200,7 +2201,7 @@ __global__ void __launch_bounds__(256, 1)
                 }
                 __syncwarp();
             }
-            for (long st = seg0; st < seg1; st++) {
+            for (int st = seg0; st < seg1; st++) {
                 if (warp == 0) {
                     if (st + 2 < seg1 && elect_one_sync()) issue(st + 2, it + 2);
                     __syncwarp();
@@ -2218,10 +2219,13 @@ __global__ void __launch_bounds__(256, 1)
                             const float2 lo = __half22float2(*reinterpret_cast<const __half2 *>(&q.x));
                             const float2 hi = __half22float2(*reinterpret_cast<const __half2 *>(&q.y));
                             vals[r][sl][0] = lo.x, vals[r][sl][1] = lo.y, vals[r][sl][2] = hi.x, vals[r][sl][3] = hi.y;
-                        } else {
+                        } else if constexpr (CPW == 4) {
                             const uint4 q = lds128(bb + (uint32_t)sl * SL_STEP + (uint32_t)r * R_STEP);
                             vals[r][sl][0] = __uint_as_float(q.x), vals[r][sl][1] = __uint_as_float(q.y);
                             vals[r][sl][2] = __uint_as_float(q.z), vals[r][sl][3] = __uint_as_float(q.w);
+                        } else {
+                            const uint2 q = lds64(bb + (uint32_t)sl * SL_STEP + (uint32_t)r * R_STEP);
+                            vals[r][sl][0] = __uint_as_float(q.x), vals[r][sl][1] = __uint_as_float(q.y);
                         }
                     }
                 // the brick is in registers: hand the slot back to the producer
@@ -2343,8 +2347,8 @@ __global__ void __launch_bounds__(256, 1)
             }
             __syncthreads();
             const int EE = E * E;
-            const long ncols = n2 - j0 < 32 ? n2 - j0 : 32;       // real columns of this strip
-            const int total = (int)ncols * EE;
+            const int ncols = n2 - j0 < 32 ? n2 - j0 : 32;       // real columns of this strip
+            const int total = ncols * EE;
             float *Kst = K + (size_t)j0 * EE;                     // the strip's kernels are contiguous
             auto folded = [&](int idx) {
                 const int col = idx / EE, rem = idx - col * EE;
@@ -2479,27 +2483,33 @@ static int launch_norm_syrk(const float *C, long nb, int E, long n2, long stride
 // column-direction pass over a tiled fp32 block (k_norm_syrk_cols): K[j] += ... for block columns [c0, n2)
 static bool cols_supported(int E, int eps) { return E <= 32 && eps >= 1 && eps <= 32 && (eps & (eps - 1)) == 0; }
 static int launch_norm_syrk_cols(const void *A, long n, int E, long n2, long T256, long c0, int eps, float *K,
-                                 cudaStream_t st, int half_in = 0, bool force_ldgsts = false)
+                                 cudaStream_t st, int half_in = 0, bool use_tma = false)
 {
     if (!cols_supported(E, eps) || (c0 & 31) || c0 >= n2) return fail(FCMA_EINVAL, "internal: column pass unsupported E=%d eps=%d c0=%ld", E, eps, c0);
     const long nstrips = cdiv(n2 - c0, 32);
     const unsigned grid = (unsigned)(nstrips < g_sm_count ? nstrips : g_sm_count);
-    // TMA-fed bricks + mbarrier ring (k_norm_syrk_cols_tma) whenever the block can be described to TMA (E a multiple of
-    // 4) and K allows 16-byte read-modify-writes; FCMA_COLS_TMA=0 (diagnostic build) forces the cp.async kernel (A/B)
-    const char *ct_env = diag_env("FCMA_COLS_TMA");
-    if ((E & 3) == 0 && ((uintptr_t)K & 15) == 0 && ((uintptr_t)A & 15) == 0 && !(ct_env && ct_env[0] == '0') && !force_ldgsts) {
+    // FCMA_FLAG_COLS_TMA: TMA-fed bricks + mbarrier ring (k_norm_syrk_cols_tma) when the block can be described to TMA (E a
+    // multiple of 4) and K allows 16-byte read-modify-writes.  Round-2 A/B (profiles/README.md): it removes the 4096
+    // LDGSTS per brick and the per-brick bar.sync, but inside the power-capped step it is 5-8 % SLOWER than the cp.async
+    // kernel below (37.8-40.8 vs 36.0-38.1 ms per step), so it is opt-in.
+    if (use_tma && (E & 3) == 0 && ((uintptr_t)K & 15) == 0 && ((uintptr_t)A & 15) == 0) {
         CUtensorMap tmA;
         int rc = make_cols_map(&tmA, A, (size_t)cdiv(n, 256) * (size_t)T256, E, half_in);
         if (rc) return rc;
         const size_t smem_t = 196608 + 64 + 1024;
+        const char *tc_env = diag_env("FCMA_COLS_TMA_CPW");     // diagnostic build: 2 = 16 warps x 2 columns (A/B)
+        const bool cpw2 = tc_env && tc_env[0] == '2' && !half_in;
 #define FCMA_COLS_TMA_CASE(EPSV)                                                                                    \
     case EPSV:                                                                                                      \
         if (half_in) {                                                                                              \
-            CUDA_TRY(cudaFuncSetAttribute(k_norm_syrk_cols_tma<EPSV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t)); \
-            k_norm_syrk_cols_tma<EPSV, true><<<grid, 256, smem_t, st>>>(tmA, n, E, n2, T256, c0, K);                \
+            CUDA_TRY(cudaFuncSetAttribute(k_norm_syrk_cols_tma<EPSV, true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t)); \
+            k_norm_syrk_cols_tma<EPSV, true, 4><<<grid, 256, smem_t, st>>>(tmA, (int)n, E, (int)n2, (int)T256, (int)c0, K);             \
+        } else if (cpw2) {                                                                                          \
+            CUDA_TRY(cudaFuncSetAttribute(k_norm_syrk_cols_tma<EPSV, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t)); \
+            k_norm_syrk_cols_tma<EPSV, false, 2><<<grid, 512, smem_t, st>>>(tmA, (int)n, E, (int)n2, (int)T256, (int)c0, K);            \
         } else {                                                                                                    \
-            CUDA_TRY(cudaFuncSetAttribute(k_norm_syrk_cols_tma<EPSV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t)); \
-            k_norm_syrk_cols_tma<EPSV, false><<<grid, 256, smem_t, st>>>(tmA, n, E, n2, T256, c0, K);               \
+            CUDA_TRY(cudaFuncSetAttribute(k_norm_syrk_cols_tma<EPSV, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t)); \
+            k_norm_syrk_cols_tma<EPSV, false, 4><<<grid, 256, smem_t, st>>>(tmA, (int)n, E, (int)n2, (int)T256, (int)c0, K);            \
         }                                                                                                           \
         break;
         switch (eps) {
@@ -2554,12 +2564,21 @@ static int launch_norm_syrk_cols(const void *A, long n, int E, long n2, long T25
 extern "C" int fcma_pack_operand(const float *epochs_dev, int E, int T, long V, long ld, const int *T_e, int normalize,
                                  int precision, void *packed_dev, size_t packed_bytes, void *stream)
 {
+    return fcma_pack_operand_range(epochs_dev, E, T, V, ld, T_e, normalize, precision, 0, V, packed_dev, packed_bytes, stream);
+}
+
+extern "C" int fcma_pack_operand_range(const float *epochs_dev, int E, int T, long V, long ld, const int *T_e, int normalize,
+                                       int precision, long v_begin, long v_end, void *packed_dev, size_t packed_bytes,
+                                       void *stream)
+{
     int rc = check_device();
     if (rc) return rc;
     PrecInfo pi;
     if (!prec_info(precision, &pi)) return fail(FCMA_EINVAL, "unknown precision %d", precision);
     if (!epochs_dev || !packed_dev || E <= 0 || T <= 0 || V <= 0 || ld < V)
         return fail(FCMA_EINVAL, "fcma_pack_operand: bad arguments E=%d T=%d V=%ld ld=%ld", E, T, V, ld);
+    if (v_begin < 0 || v_end > V || v_begin >= v_end)
+        return fail(FCMA_EINVAL, "fcma_pack_operand_range: voxels [%ld, %ld) outside [0, %ld)", v_begin, v_end, V);
     size_t need = fcma_operand_bytes(precision, E, T, V);
     if (packed_bytes < need) return fail(FCMA_ENOMEM, "packed operand buffer too small: %zu < %zu", packed_bytes, need);
     cudaStream_t st = (cudaStream_t)stream;
@@ -2574,12 +2593,12 @@ extern "C" int fcma_pack_operand(const float *epochs_dev, int E, int T, long V, 
     }
     const int Kp = fcma_operand_kp(precision, T);
     float *sd = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(packed_dev) + operand_plane_bytes(pi, precision, E, T, V));
-    dim3 grid((unsigned)cdiv(V, 32), (unsigned)E);
-    if (pi.pack == 0 && pi.planes == 1) k_pack_operand<0, 1><<<grid, 256, 0, st>>>(epochs_dev, E, T, V, ld, d_Te, normalize, packed_dev, Kp, sd, pi.in_scale);
-    if (pi.pack == 0 && pi.planes == 2) k_pack_operand<0, 2><<<grid, 256, 0, st>>>(epochs_dev, E, T, V, ld, d_Te, normalize, packed_dev, Kp, sd, pi.in_scale);
-    if (pi.pack == 1 && pi.planes == 1) k_pack_operand<1, 1><<<grid, 256, 0, st>>>(epochs_dev, E, T, V, ld, d_Te, normalize, packed_dev, Kp, sd, pi.in_scale);
-    if (pi.pack == 1 && pi.planes == 2) k_pack_operand<1, 2><<<grid, 256, 0, st>>>(epochs_dev, E, T, V, ld, d_Te, normalize, packed_dev, Kp, sd, pi.in_scale);
-    if (pi.pack == 2 && pi.planes == 2) k_pack_operand<2, 2><<<grid, 256, 0, st>>>(epochs_dev, E, T, V, ld, d_Te, normalize, packed_dev, Kp, sd, pi.in_scale);
+    dim3 grid((unsigned)cdiv(v_end - v_begin, 32), (unsigned)E);
+    if (pi.pack == 0 && pi.planes == 1) k_pack_operand<0, 1><<<grid, 256, 0, st>>>(epochs_dev, E, T, V, ld, d_Te, normalize, packed_dev, Kp, sd, pi.in_scale, v_begin, v_end);
+    if (pi.pack == 0 && pi.planes == 2) k_pack_operand<0, 2><<<grid, 256, 0, st>>>(epochs_dev, E, T, V, ld, d_Te, normalize, packed_dev, Kp, sd, pi.in_scale, v_begin, v_end);
+    if (pi.pack == 1 && pi.planes == 1) k_pack_operand<1, 1><<<grid, 256, 0, st>>>(epochs_dev, E, T, V, ld, d_Te, normalize, packed_dev, Kp, sd, pi.in_scale, v_begin, v_end);
+    if (pi.pack == 1 && pi.planes == 2) k_pack_operand<1, 2><<<grid, 256, 0, st>>>(epochs_dev, E, T, V, ld, d_Te, normalize, packed_dev, Kp, sd, pi.in_scale, v_begin, v_end);
+    if (pi.pack == 2 && pi.planes == 2) k_pack_operand<2, 2><<<grid, 256, 0, st>>>(epochs_dev, E, T, V, ld, d_Te, normalize, packed_dev, Kp, sd, pi.in_scale, v_begin, v_end);
     LAUNCH_CHECK("k_pack_operand");
     return FCMA_OK;   // te_buf is released in stream order by its destructor
 }
@@ -2896,7 +2915,7 @@ static int run_pipeline_sym(const void *op, int precision, int E, int T, long V,
         if (g_timing_on) CUDA_TRY(cudaEventRecord(ev[3], st));
         if (rowsB > 0 && use_cols) {
             rc = launch_norm_syrk_cols(A, n, E, colsA, t256, n, eps, K + (size_t)a * E * E, st, half16 ? 1 : 0,
-                                       (flags & FCMA_FLAG_COLS_LDGSTS) != 0);
+                                       (flags & FCMA_FLAG_COLS_TMA) != 0);
             if (rc) return rc;
         } else if (rowsB > 0) {
             rc = launch_norm_syrk(B, rowsB, E, n, 256, 65536, eps, 1, -1, 1.0f, K + (size_t)(a + n) * E * E, 0, st,
@@ -3385,6 +3404,114 @@ extern "C" int fcma_host_voxel_kernels(const float *const *raw_host, const float
     if (rc) return rc;
     CUDA_TRY(cudaMemcpyAsync(K_host, K.p, (size_t)nb * E * E * sizeof(float), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
+    return FCMA_OK;
+}
+
+// Single-mask worker loop from HOST buffers (what a ctypes / cgo binding of the reference's VoxelSelector would call when
+// raw_data2 is None): H2D of the E epochs, packing, fcma_voxel_kernels_sym over all V rows, D2H of the [V][E][E] kernels,
+// synchronously on `device`.  Device buffers come from the device's default stream-ordered pool, whose release threshold is
+// raised once so that repeated calls reuse the memory instead of going back to the OS.
+extern "C" int fcma_host_voxel_kernels_sym(const float *const *raw_host, const int *T_e, int E, long V, int eps,
+                                           int precision, int normalize, int flags, int device, long rows_per_pass,
+                                           float *K_host)
+{
+    if (!raw_host || !T_e || !K_host || E <= 0 || V <= 0) return fail(FCMA_EINVAL, "fcma_host_voxel_kernels_sym: bad arguments");
+    if (fcma_device_count() == 0) return fail(FCMA_ENODEV, "no sm_100 device");
+    DeviceGuard guard;
+    CUDA_TRY(cudaSetDevice(device));
+    int rc = check_device();
+    if (rc) return rc;
+    int T = 0;
+    for (int e = 0; e < E; e++) {
+        if (T_e[e] <= 0) return fail(FCMA_EINVAL, "epoch %d has non-positive length", e);
+        if (T_e[e] > T) T = T_e[e];
+    }
+    static std::once_flag pool_once[64];
+    if (device >= 0 && device < 64)
+        std::call_once(pool_once[device], [&] {
+            cudaMemPool_t pool;
+            if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+                uint64_t keep = UINT64_MAX;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            }
+            cudaGetLastError();
+        });
+    cudaStream_t st = 0;
+    const size_t opb = fcma_operand_bytes(precision, E, T, V);
+    if (!opb) return fail(FCMA_EINVAL, "unknown precision %d", precision);
+    AsyncBuf epochs, op, work, K;
+    const size_t ep_bytes = (size_t)E * T * V * sizeof(float), k_bytes = (size_t)V * E * E * sizeof(float);
+    CUDA_TRY(epochs.alloc(ep_bytes, st));
+    bool ragged = false;
+    for (int e = 0; e < E; e++) ragged = ragged || T_e[e] != T;
+    if (ragged) CUDA_TRY(cudaMemsetAsync(epochs.p, 0, ep_bytes, st));
+    for (int e = 0; e < E; e++)
+        CUDA_TRY(cudaMemcpyAsync((float *)epochs.p + (size_t)e * T * V, raw_host[e], (size_t)T_e[e] * V * sizeof(float),
+                                 cudaMemcpyHostToDevice, st));
+    CUDA_TRY(op.alloc(opb, st));
+    rc = fcma_pack_operand((const float *)epochs.p, E, T, V, V, ragged ? T_e : nullptr, normalize, precision, op.p, opb, st);
+    if (rc) return rc;
+    const size_t per_row = (sym_uses_cols(precision, E, eps, flags) ? 1 : 2) * fcma_work_bytes_per_row(E, V);
+    size_t freeb = 0, totalb = 0;
+    CUDA_TRY(cudaMemGetInfo(&freeb, &totalb));
+    long rows = rows_per_pass > 0 ? rows_per_pass : 4096;
+    const long fit = (long)((freeb / 2) / per_row);
+    if (rows > fit) rows = fit;
+    if (rows > round_up(V, 256)) rows = round_up(V, 256);
+    rows = rows / 256 * 256;
+    if (rows < 256) return fail(FCMA_ENOMEM, "not enough device memory for a 256-row correlation block (%zu bytes per row)", per_row);
+    CUDA_TRY(work.alloc(per_row * rows, st));
+    CUDA_TRY(K.alloc(k_bytes, st));
+    CUDA_TRY(cudaMemsetAsync(K.p, 0, k_bytes, st));
+    rc = run_pipeline_sym(op.p, precision, E, T, V, 0, V, eps, flags, (float *)work.p, per_row * rows, (float *)K.p, st);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(K_host, K.p, k_bytes, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return FCMA_OK;
+}
+
+// ---------------------------------------------------------------- inter-process peer copies (one process per GPU)
+// Copy-engine exchange of the epoch shards between the ranks of one box (the replacement of the reference's per-epoch
+// comm.bcast loop, preprocessing.py:211-223, that does not occupy SMs the persistent GEMM needs): a rank exports the
+// allocation behind a device pointer as a 64-byte CUDA IPC handle, the peers map it and cudaMemcpyAsync into / out of
+// it over NVLink.  The library keeps no state: the caller owns handles, mappings and streams.
+typedef CUresult (*PFN_cuMemGetAddressRange)(CUdeviceptr *, size_t *, CUdeviceptr);
+extern "C" int fcma_ipc_get_handle(const void *dev_ptr, void *handle64, size_t *offset)
+{
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+    if (!dev_ptr || !handle64 || !offset) return fail(FCMA_EINVAL, "fcma_ipc_get_handle: null pointer");
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    CUDA_TRY(cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &q));
+    if (q != cudaDriverEntryPointSuccess || !fn) return fail(FCMA_ECUDA, "cuMemGetAddressRange entry point not available");
+    CUdeviceptr base = 0;
+    size_t size = 0;
+    CUresult r = reinterpret_cast<PFN_cuMemGetAddressRange>(fn)(&base, &size, (CUdeviceptr)dev_ptr);
+    if (r != CUDA_SUCCESS) return fail(FCMA_ECUDA, "cuMemGetAddressRange failed with CUresult %d", (int)r);
+    cudaIpcMemHandle_t h;
+    CUDA_TRY(cudaIpcGetMemHandle(&h, (void *)base));
+    memcpy(handle64, &h, 64);
+    *offset = (size_t)((CUdeviceptr)dev_ptr - base);
+    return FCMA_OK;
+}
+extern "C" int fcma_ipc_open_handle(const void *handle64, void **base_ptr)
+{
+    if (!handle64 || !base_ptr) return fail(FCMA_EINVAL, "fcma_ipc_open_handle: null pointer");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    CUDA_TRY(cudaIpcOpenMemHandle(base_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return FCMA_OK;
+}
+extern "C" int fcma_ipc_close_handle(void *base_ptr)
+{
+    if (!base_ptr) return FCMA_OK;
+    CUDA_TRY(cudaIpcCloseMemHandle(base_ptr));
+    return FCMA_OK;
+}
+extern "C" int fcma_peer_copy_async(void *dst, const void *src, size_t bytes, void *stream)
+{
+    if (!dst || !src) return fail(FCMA_EINVAL, "fcma_peer_copy_async: null pointer");
+    CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, (cudaStream_t)stream));
     return FCMA_OK;
 }
 

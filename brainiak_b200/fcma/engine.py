@@ -88,8 +88,12 @@ class PackedOperand:
         return self.buf.device
 
 
-def pack_epochs(epochs, T_e=None, precision=_PREC_DEFAULT, normalize=False):
-    """epochs: float32 CUDA ``[E, T, V]``.  normalize=True applies preprocessing.py:80-84 on the fly."""
+def pack_epochs(epochs, T_e=None, precision=_PREC_DEFAULT, normalize=False, v_begin=0, out=None):
+    """epochs: float32 CUDA ``[E, T, V]``.  normalize=True applies preprocessing.py:80-84 on the fly.
+
+    ``v_begin``: pack only the voxels ``[v_begin, V)`` (into their places of the V-voxel operand): a shard of the
+    symmetric pipeline that starts at row ``s`` never touches voxels below ``s``.  ``out``: a PackedOperand of the
+    same shape / precision whose buffer is reused."""
     lib = _lib.load()
     _lib.require_device()
     if epochs.dtype != torch.float32 or not epochs.is_cuda or not epochs.is_contiguous():
@@ -100,13 +104,18 @@ def pack_epochs(epochs, T_e=None, precision=_PREC_DEFAULT, normalize=False):
     if code == _lib.PREC["f32simt"]:
         raise ValueError("f32simt works on unpacked epochs")
     nbytes = lib.fcma_operand_bytes(code, E, T, V)
-    buf = torch.empty(nbytes, dtype=torch.uint8, device=epochs.device)
+    if out is not None:
+        if (out.E, out.T, out.V, out.precision) != (E, T, V, precision) or out.buf.numel() < nbytes:
+            raise ValueError("`out` operand does not match the epochs / precision")
+        buf = out.buf
+    else:
+        buf = torch.empty(nbytes, dtype=torch.uint8, device=epochs.device)
     te = None
     if T_e is not None and any(t != T for t in T_e):
         te = (ctypes.c_int * E)(*T_e)
     with torch.cuda.device(epochs.device):
-        _lib.check(lib.fcma_pack_operand(_ptr(epochs), E, T, V, V, te, int(bool(normalize)), code,
-                                         _ptr(buf), nbytes, _stream_ptr()))
+        _lib.check(lib.fcma_pack_operand_range(_ptr(epochs), E, T, V, V, te, int(bool(normalize)), code,
+                                               int(v_begin), V, _ptr(buf), nbytes, _stream_ptr()))
     return PackedOperand(buf, E, T, V, precision, list(T_e) if T_e is not None else [T] * E)
 
 
@@ -378,6 +387,37 @@ def host_voxel_kernels(raw_data, raw_data2, start, nb, eps, precision=_PREC_DEFA
                                            _prec_code(precision), int(bool(normalize)), int(flags),
                                            int(device), K.ctypes.data_as(ctypes.c_void_p)))
     return K
+
+
+def host_voxel_kernels_sym(raw_data, eps, precision="fp16x3", normalize=False, flags=0, device=None, rows_per_pass=0,
+                           out=None):
+    """The C-ABI host entry point of the single-mask worker loop (fcma_host_voxel_kernels_sym): E host arrays
+    ``[T_e, V]`` (or one host tensor ``[E, T, V]``; pinned memory makes the copies asynchronous DMA) in, the unshrunk
+    kernels ``[V, E, E]`` out (``out``: a host float32 tensor / array to fill, e.g. pinned).  H2D, packing, the symmetric
+    pipeline and D2H all happen inside the call."""
+    lib = _lib.load()
+    if device is None:
+        device = torch.cuda.current_device() if torch.cuda.is_available() else 0
+    if isinstance(raw_data, torch.Tensor):
+        if raw_data.is_cuda or raw_data.dtype != torch.float32 or not raw_data.is_contiguous() or raw_data.dim() != 3:
+            raise ValueError("host epochs tensor must be contiguous float32 [E, T, V] in host memory")
+        E, T, V = raw_data.shape
+        ptrs = [raw_data.data_ptr() + e * T * V * 4 for e in range(E)]
+        Ts, keep = [T] * E, raw_data
+    else:
+        keep = [np.ascontiguousarray(m, dtype=np.float32) for m in raw_data]
+        E, V = len(keep), keep[0].shape[1]
+        ptrs = [m.ctypes.data for m in keep]
+        Ts = [m.shape[0] for m in keep]
+    arr = (ctypes.POINTER(ctypes.c_float) * E)(*[ctypes.cast(p, ctypes.POINTER(ctypes.c_float)) for p in ptrs])
+    te = (ctypes.c_int * E)(*Ts)
+    if out is None:
+        out = np.empty((V, E, E), np.float32)
+    optr = out.data_ptr() if isinstance(out, torch.Tensor) else out.ctypes.data
+    _lib.check(lib.fcma_host_voxel_kernels_sym(arr, te, E, V, int(eps), _prec_code(precision), int(bool(normalize)),
+                                               int(flags), int(device), int(rows_per_pass), ctypes.c_void_p(optr)))
+    del keep
+    return out
 
 
 # ------------------------------------------------------------------ a7 tail + a8 on the GPU

@@ -1,0 +1,130 @@
+"""Epoch exchange between the GPUs of one box without SMs: every rank uploads ITS share of the epochs over its own
+PCIe link and the shares are all-gathered over NVLink by the copy engines (CUDA IPC mappings of the peers' buffers +
+``cudaMemcpyAsync``), so the transfer can run under the persistent correlation GEMM of the previous dataset without
+taking SMs away from it.
+
+This replaces the reference's distribution step -- rank 0 reads everything and ``comm.bcast``s it epoch by epoch
+(``prepare_fcma_data``, reference preprocessing.py:211-223) -- for the case where the data already sits in (shared)
+host memory or on a parallel file system every rank can read: one PCIe link moves 1/W of the bytes instead of all.
+"""
+import ctypes
+
+import torch
+import torch.distributed as dist
+
+from .. import _lib
+
+__all__ = ["EpochExchange", "epoch_partition"]
+
+
+def epoch_partition(E, world):
+    """Contiguous shares of the E epochs: rank r uploads epochs [e0, e0 + n)."""
+    per, extra = divmod(E, world)
+    out, e0 = [], 0
+    for r in range(world):
+        n = per + (1 if r < extra else 0)
+        out.append((e0, n))
+        e0 += n
+    return out
+
+
+class EpochExchange:
+    """``nbuf`` replicated epoch buffers ``[E, T, V]`` per rank, mapped into every peer.
+
+    ``gather(k, host_share, stream)`` on every rank: H2D of this rank's epochs into its own buffer ``k``, peer copies
+    of that share into buffer ``k`` of every other rank (copy engines, NVLink), then a one-element NCCL all-reduce as
+    the stream-ordered "all shares have landed everywhere" barrier.  Afterwards ``buffers[k]`` holds all E epochs on
+    every rank.  ``use_ipc=False`` (or a failed IPC mapping) falls back to ``all_gather_into_tensor`` in place."""
+
+    def __init__(self, E, T, V, device, group=None, nbuf=2, use_ipc=True):
+        self.lib = _lib.load()
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.E, self.T, self.V = E, T, V
+        self.device = torch.device(device)
+        self.shares = epoch_partition(E, self.world)
+        self.buffers = [torch.empty((E, T, V), dtype=torch.float32, device=self.device) for _ in range(nbuf)]
+        self._flag = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self._peer = None          # [buffer][rank] -> device address of that rank's buffer in this process
+        self._opened = []
+        self.mode = "single"
+        if self.world > 1:
+            self.mode = "nccl-allgather"
+            if use_ipc:
+                try:
+                    self._map_peers()
+                    self.mode = "ipc-copy-engine"
+                except Exception as exc:     # pragma: no cover - depends on the box
+                    self._peer = None
+                    self.ipc_error = repr(exc)
+                ok = torch.tensor([1.0 if self._peer is not None else 0.0], device=self.device)
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)      # all ranks take the same path
+                if float(ok[0]) == 0.0:
+                    self._peer, self.mode = None, "nccl-allgather"
+
+    def _map_peers(self):
+        mine = []
+        for b in self.buffers:
+            h = (ctypes.c_ubyte * 64)()
+            off = ctypes.c_size_t(0)
+            _lib.check(self.lib.fcma_ipc_get_handle(ctypes.c_void_p(b.data_ptr()), h, ctypes.byref(off)))
+            mine.append((bytes(h), int(off.value)))
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, mine, group=self.group)
+        self._peer = []
+        cache = {}
+        with torch.cuda.device(self.device):
+            for k in range(len(self.buffers)):
+                row = []
+                for r in range(self.world):
+                    if r == self.rank:
+                        row.append(self.buffers[k].data_ptr())
+                        continue
+                    hb, off = everyone[r][k]
+                    if (r, hb) not in cache:
+                        base = ctypes.c_void_p()
+                        buf = (ctypes.c_ubyte * 64).from_buffer_copy(hb)
+                        _lib.check(self.lib.fcma_ipc_open_handle(buf, ctypes.byref(base)))
+                        cache[(r, hb)] = base.value
+                        self._opened.append(base.value)
+                    row.append(cache[(r, hb)] + off)
+                self._peer.append(row)
+
+    def close(self):
+        for base in self._opened:
+            self.lib.fcma_ipc_close_handle(ctypes.c_void_p(base))
+        self._opened = []
+
+    def share_of(self, rank=None):
+        return self.shares[self.rank if rank is None else rank]
+
+    def gather(self, k, host_share, stream=None):
+        """host_share: this rank's epochs, a (pinned) host float32 tensor ``[n, T, V]``.  Everything is enqueued on
+        ``stream`` (default: the current stream); returns ``buffers[k]``."""
+        stream = stream or torch.cuda.current_stream(self.device)
+        e0, n = self.shares[self.rank]
+        buf = self.buffers[k]
+        with torch.cuda.stream(stream):
+            if n:
+                buf[e0:e0 + n].copy_(host_share, non_blocking=True)
+            if self.world == 1:
+                return buf
+            if self._peer is None:
+                if len(set(m for _, m in self.shares)) == 1:
+                    dist.all_gather_into_tensor(buf, buf[e0:e0 + n], group=self.group)
+                else:
+                    parts = [buf[a:a + m] for a, m in self.shares]
+                    dist.all_gather(parts, buf[e0:e0 + n].clone(), group=self.group)
+                return buf
+            if n:
+                nbytes = n * self.T * self.V * 4
+                off = e0 * self.T * self.V * 4
+                sp = ctypes.c_void_p(stream.cuda_stream)
+                with torch.cuda.device(self.device):
+                    for d in range(1, self.world):          # staggered so that no peer is everybody's first target
+                        r = (self.rank + d) % self.world
+                        _lib.check(self.lib.fcma_peer_copy_async(ctypes.c_void_p(self._peer[k][r] + off),
+                                                                 ctypes.c_void_p(buf.data_ptr() + off), nbytes, sp))
+            dist.all_reduce(self._flag, group=self.group)    # stream-ordered barrier: every rank's copies are done
+        return buf

@@ -64,8 +64,9 @@ extern "C" {
 #define FCMA_FLAG_STRIDED_BLOCK   8   /* fused pipelines: strided [nb][E][ld] correlation block instead of the tiled one */
 #define FCMA_FLAG_SYM_TRANSPOSED 16   /* symmetric pipeline: store a transposed copy of every block + row pass over it
                                          instead of the column-direction pass (what E > 32 always does)              */
-#define FCMA_FLAG_COLS_LDGSTS    32   /* column-direction pass fed by cp.async + block barriers instead of TMA bricks +
-                                         an mbarrier ring (what E % 4 != 0 always does)                               */
+#define FCMA_FLAG_COLS_TMA       32   /* column-direction pass fed by 5-D TMA bricks + an mbarrier ring instead of cp.async +
+                                         block barriers (needs E % 4 == 0; measured 5-8 % slower inside the power-capped
+                                         step, profiles/README.md, so it is not the default)                          */
 
 int         fcma_version(void);
 const char *fcma_last_error(void);
@@ -89,6 +90,12 @@ size_t fcma_operand_bytes(int precision, int E, int T, long V);
 int fcma_pack_operand(const float *epochs_dev, int E, int T, long V, long ld, const int *T_e,
                       int normalize, int precision, void *packed_dev, size_t packed_bytes,
                       void *stream);
+
+/* same for the voxels [v_begin, v_end) only, written to their places in the V-voxel operand: a shard of the symmetric
+ * pipeline that starts at row s only ever touches voxels >= s (rows [s, s+n) against columns [s, V)) */
+int fcma_pack_operand_range(const float *epochs_dev, int E, int T, long V, long ld, const int *T_e,
+                            int normalize, int precision, long v_begin, long v_end, void *packed_dev,
+                            size_t packed_bytes, void *stream);
 
 /* a14 alone, in place on float32 [E][T][ld] (preprocessing.py:80-84). */
 int fcma_epoch_normalize(float *epochs_dev, int E, int T, long V, long ld, const int *T_e,
@@ -190,6 +197,23 @@ int fcma_row_normalize(float *X_dev, long R, long D, long ld, int nan_to_zero, v
 int fcma_host_voxel_kernels(const float *const *raw_host, const float *const *raw2_host,
                             const int *T_e, int E, long V, long V2, long start, long nb, int eps,
                             int precision, int normalize, int flags, int device, float *K_host);
+
+/* the worker's whole task loop for ONE mask from host buffers (voxelselector.py:255-282 with raw_data2 None): H2D, packing,
+ * fcma_voxel_kernels_sym over all V rows, D2H of K_host = float32 [V][E][E] (unshrunk), synchronously.  rows_per_pass <= 0:
+ * 4096 (clamped to what fits).  Device buffers come from the device's stream-ordered pool and are reused across calls. */
+int fcma_host_voxel_kernels_sym(const float *const *raw_host, const int *T_e, int E, long V, int eps,
+                                int precision, int normalize, int flags, int device, long rows_per_pass,
+                                float *K_host);
+
+/* ---- inter-process peer copies over NVLink with the copy engines (one process per GPU of a box) ------------------
+ * Replaces the per-epoch comm.bcast loop of prepare_fcma_data (preprocessing.py:211-223) without occupying SMs:
+ * every rank uploads ITS share of the epochs over its own PCIe link, exports the destination buffer as a CUDA IPC
+ * handle (64 bytes + the offset of dev_ptr inside its allocation), the peers map it and copy their shares into it.
+ * The library keeps no state; mappings are closed by the caller. */
+int fcma_ipc_get_handle(const void *dev_ptr, void *handle64, size_t *offset);
+int fcma_ipc_open_handle(const void *handle64, void **base_ptr);
+int fcma_ipc_close_handle(void *base_ptr);
+int fcma_peer_copy_async(void *dst_dev, const void *src_dev, size_t bytes, void *stream);
 
 /* in-place host variants of the reference's native functions */
 int fcma_host_within_subject_norm(float *corr_host, long n0, int E, long n2, int eps, int device);

@@ -281,8 +281,11 @@ def test_symmetric_pipeline_vs_oracle_and_plain(dev, case):
     op = engine.pack_epochs(ep, T_e, "fp32")
     # (a buffer sized for block + transposed copy gives the column-pass variant twice the rows per pass)
     work = engine.SymWorkspace(E, V, rows, dev, transposed_copy=(case != "long_column_walk"))
-    for fl in (_lib.FLAG_MASK_SELF, 0):
-        plain = engine.voxel_kernels(op, op, 0, V, eps, flags=fl)
+    fls = (_lib.FLAG_MASK_SELF, 0)
+    if case == "long_column_walk":      # also the TMA-fed column pass: ring wrap-around and folds over a long walk
+        fls = (_lib.FLAG_MASK_SELF, _lib.FLAG_MASK_SELF | _lib.FLAG_COLS_TMA, 0)
+    for fl in fls:
+        plain = engine.voxel_kernels(op, op, 0, V, eps, flags=fl & _lib.FLAG_MASK_SELF)
         work.buf.view(torch.float32).fill_(float("nan"))       # stale scratch must never reach the kernels
         K = torch.zeros((V, E, E), device=dev)
         for s, n in engine.sym_row_partition(V, shards):
@@ -293,7 +296,7 @@ def test_symmetric_pipeline_vs_oracle_and_plain(dev, case):
         assert float((K - K.transpose(1, 2)).abs().max()) == 0.0
         # same values, summed in a different order: fp32 rounding of the partial sums only
         assert float((K - plain).abs().max()) <= 1e-5 * scale      # measured 4e-7 .. 4e-6 (E = 64)
-        if fl:        # the oracle comparison uses the masked self column (the raw one is rounding noise)
+        if fl & _lib.FLAG_MASK_SELF:   # the oracle comparison uses the masked self column (the raw one is rounding noise)
             sel = np.r_[0:40, V // 2:V // 2 + 40, V - 40:V]
             for blk in (slice(0, 40), slice(V // 2, V // 2 + 40), slice(V - 40, V)):
                 _, z, _ = orc.voxel_block(raw, None, blk.start, 40, eps, shrink=False)
@@ -334,9 +337,9 @@ def test_symmetric_column_pass_all_eps(dev, E, eps):
     # than those of r(i, j)); a flipped pair moves one K entry by 2 of ~V
     loose = eps <= 2
     assert float((K - plain).abs().max()) <= (2e-3 if loose else 1e-5) * scale
-    # the two feeds of the column pass (TMA bricks + mbarrier ring when E % 4 == 0, cp.async + block barriers otherwise
-    # or on request) and the transposed-copy variant agree to the order of the fp32 partial sums
-    for extra in (_lib.FLAG_COLS_LDGSTS, _lib.FLAG_SYM_TRANSPOSED):
+    # the two feeds of the column pass (cp.async + block barriers; TMA bricks + mbarrier ring on request when
+    # E % 4 == 0) and the transposed-copy variant agree to the order of the fp32 partial sums
+    for extra in (_lib.FLAG_COLS_TMA, _lib.FLAG_SYM_TRANSPOSED):
         K2 = torch.zeros((V, E, E), device=dev)
         w2 = engine.SymWorkspace(E, V, 256, dev)
         w2.buf.view(torch.float32).fill_(float("nan"))
@@ -363,8 +366,8 @@ def test_symmetric_fp16_block_column_pass(dev, prec, flag):
     plain = engine.voxel_kernels(op, op, 0, V, eps, flags=fl)
     scale = float(plain.abs().max())
     out = {}
-    # column pass over the block (TMA bricks / cp.async bricks) / transposed copy + row pass
-    for cols, extra in (("1", 0), ("ldgsts", _lib.FLAG_COLS_LDGSTS), ("0", _lib.FLAG_SYM_TRANSPOSED)):
+    # column pass over the block (cp.async bricks / TMA bricks) / transposed copy + row pass
+    for cols, extra in (("1", 0), ("tma", _lib.FLAG_COLS_TMA), ("0", _lib.FLAG_SYM_TRANSPOSED)):
         K = torch.zeros((V, E, E), device=dev)
         work = engine.SymWorkspace(E, V, 512, dev)
         work.buf.view(torch.float32).fill_(float("nan"))

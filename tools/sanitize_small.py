@@ -25,8 +25,8 @@ raw, labels = synthetic.make_epochs(V, T, E, seed=3)
 ep, T_e = engine.stack_epochs(raw, dev)
 op = engine.pack_epochs(ep, T_e, "fp32")
 ref = None
-for name, fl in (("tma", 0), ("ldgsts", _lib.FLAG_COLS_LDGSTS), ("transposed", _lib.FLAG_SYM_TRANSPOSED),
-                 ("f16", _lib.FLAG_F16_INTERMEDIATE), ("f16 ldgsts", _lib.FLAG_F16_INTERMEDIATE | _lib.FLAG_COLS_LDGSTS)):
+for name, fl in (("ldgsts", 0), ("tma", _lib.FLAG_COLS_TMA), ("transposed", _lib.FLAG_SYM_TRANSPOSED),
+                 ("f16", _lib.FLAG_F16_INTERMEDIATE), ("f16 tma", _lib.FLAG_F16_INTERMEDIATE | _lib.FLAG_COLS_TMA)):
     K = torch.zeros((V, E, E), device=dev)
     work = engine.SymWorkspace(E, V, 256, dev)
     engine.voxel_kernels_sym(op, 0, V, eps, flags=fl | _lib.FLAG_MASK_SELF, work=work, out=K)

@@ -76,6 +76,38 @@ def stack_epochs(raw_data, device):
     return host.to(device, non_blocking=True), T_e
 
 
+def upload_epochs_sharded(raw_data, device, group=None, use_ipc=True):
+    """Multi-GPU upload of the epochs when every rank can see the host data (the usual case after
+    ``prepare_fcma_data``: all ranks hold ``raw_data``): each rank stages and uploads only ITS contiguous share of the
+    epochs over its own PCIe link, then the shares are all-gathered over NVLink by the copy engines
+    (``exchange.EpochExchange``; NCCL all-gather if CUDA IPC is unavailable).  Returns (``[E, Tmax, V]`` float32 CUDA
+    tensor, list of T_e) like ``stack_epochs``.  Replaces W full uploads (or rank 0's upload + ``comm.bcast``,
+    reference preprocessing.py:211-223) by 1/W of the bytes per link."""
+    from .exchange import EpochExchange
+    E = len(raw_data)
+    if E == 0:
+        raise ValueError("no epochs")
+    V = raw_data[0].shape[1]
+    T_e = [int(m.shape[0]) for m in raw_data]
+    T = max(T_e)
+    for m in raw_data:
+        if m.ndim != 2 or m.shape[1] != V:
+            raise ValueError("all epochs must be 2D with the same number of voxels")
+    xch = EpochExchange(E, T, V, device, group=group, nbuf=1, use_ipc=use_ipc)
+    e0, n = xch.share_of()
+    same = all(t == T for t in T_e[e0:e0 + n])
+    host = (torch.empty if same else torch.zeros)((max(n, 1), T, V), dtype=torch.float32, pin_memory=True)
+    hn = host.numpy()
+    for j in range(n):
+        hn[j, :T_e[e0 + j], :] = raw_data[e0 + j]
+    ep = xch.gather(0, host[:n])
+    torch.cuda.current_stream(ep.device).synchronize()      # the peers' mappings of this buffer are closed below
+    if torch.distributed.is_initialized() and xch.world > 1:
+        torch.distributed.barrier(group=group, device_ids=[ep.device.index])
+    xch.close()
+    return ep, T_e
+
+
 class PackedOperand:
     """K-major, precision-split copy of one set of epochs, ready for TMA."""
 
@@ -253,17 +285,41 @@ def voxel_kernels(rows, cols, start, nb, eps, flags=0, work=None, out=None):
     return out
 
 
-def sym_row_partition(num_voxels, world_size, align=256):
-    """Shards of [0, V) for the symmetric pipeline: shard r contracts its rows with the columns at or to
-    the right of its first row, so equal WORK means equal trapezoid areas, s_r = V (1 - sqrt(1 - r/W)),
-    rounded to whole 256-row tiles (the last shard takes the ragged tail).  Returns [(start, n)]."""
+def sym_row_partition(num_voxels, world_size, align=256, pack_frac=0.01):
+    """Shards of [0, V) for the symmetric pipeline.  Shard r contracts its rows with the columns at or to the right of
+    its first row, so the work of rows [a, b) is the trapezoid area (1 - a/V)^2 - (1 - b/V)^2 of the upper triangle, plus
+    the packing of the voxels [a, V) it touches (``pack_frac`` = time of packing ALL voxels as a fraction of a whole
+    single-GPU step; measured ~0.01 at the bench shape).  Cuts must be whole 256-row tiles (the last shard takes the
+    ragged tail), so the shards are chosen as the min-max linear partition over those tiles (binary search on the
+    bottleneck cost + greedy packing: optimal for contiguous shards).  Returns [(start, n)]."""
     V, W = int(num_voxels), int(world_size)
-    cuts = [0]
-    for r in range(1, W):
-        s = V * (1.0 - (1.0 - r / float(W)) ** 0.5)
-        s = int(round(s / align)) * align
-        cuts.append(min(max(s, cuts[-1]), V))
-    cuts.append(V)
+    if W <= 1:
+        return [(0, V)]
+    ntiles = (V + align - 1) // align
+    edge = [min(k * align, V) for k in range(ntiles + 1)]
+
+    def cost(a, b):                    # rows [a, b): kernel share + pack share of the whole step
+        return ((1.0 - a / float(V)) ** 2 - (1.0 - b / float(V)) ** 2) + pack_frac * (1.0 - a / float(V))
+
+    def greedy(limit):
+        cuts, k = [0], 0
+        for _ in range(W):
+            k0 = k
+            while k < ntiles and cost(edge[k0], edge[k + 1]) <= limit:
+                k += 1
+            if k == k0 and k < ntiles:
+                return None                       # a single tile exceeds the limit
+            cuts.append(edge[k])
+        return cuts if k == ntiles else None
+
+    lo, hi = 0.0, 1.0 + pack_frac
+    for _ in range(50):
+        mid = 0.5 * (lo + hi)
+        if greedy(mid) is None:
+            lo = mid
+        else:
+            hi = mid
+    cuts = greedy(hi)
     return [(cuts[r], cuts[r + 1] - cuts[r]) for r in range(W)]
 
 

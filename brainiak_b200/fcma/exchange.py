@@ -48,6 +48,7 @@ class EpochExchange:
         self._flag = torch.zeros(1, dtype=torch.float32, device=self.device)
         self._peer = None          # [buffer][rank] -> device address of that rank's buffer in this process
         self._opened = []
+        self._aux, self._landed = None, None
         self.mode = "single"
         if self.world > 1:
             self.mode = "nccl-allgather"
@@ -101,30 +102,41 @@ class EpochExchange:
 
     def gather(self, k, host_share, stream=None):
         """host_share: this rank's epochs, a (pinned) host float32 tensor ``[n, T, V]``.  Everything is enqueued on
-        ``stream`` (default: the current stream); returns ``buffers[k]``."""
+        ``stream`` (default: the current stream); returns ``buffers[k]``.  The share goes up epoch by epoch and every
+        epoch is forwarded to the peers (on an auxiliary stream) as soon as it has landed, so the PCIe upload and the
+        NVLink copies overlap."""
         stream = stream or torch.cuda.current_stream(self.device)
         e0, n = self.shares[self.rank]
         buf = self.buffers[k]
         with torch.cuda.stream(stream):
-            if n:
-                buf[e0:e0 + n].copy_(host_share, non_blocking=True)
-            if self.world == 1:
-                return buf
-            if self._peer is None:
+            if self.world == 1 or self._peer is None:
+                if n:
+                    buf[e0:e0 + n].copy_(host_share, non_blocking=True)
+                if self.world == 1:
+                    return buf
                 if len(set(m for _, m in self.shares)) == 1:
                     dist.all_gather_into_tensor(buf, buf[e0:e0 + n], group=self.group)
                 else:
                     parts = [buf[a:a + m] for a, m in self.shares]
                     dist.all_gather(parts, buf[e0:e0 + n].clone(), group=self.group)
                 return buf
-            if n:
-                nbytes = n * self.T * self.V * 4
-                off = e0 * self.T * self.V * 4
-                sp = ctypes.c_void_p(stream.cuda_stream)
-                with torch.cuda.device(self.device):
+            if self._aux is None:
+                self._aux = torch.cuda.Stream(device=self.device)
+                self._landed = [torch.cuda.Event() for _ in range(max(m for _, m in self.shares))]
+            aux = self._aux
+            aux.wait_stream(stream)              # the destination buffers are free as of this point of `stream`
+            ebytes = self.T * self.V * 4
+            sp = ctypes.c_void_p(aux.cuda_stream)
+            with torch.cuda.device(self.device):
+                for j in range(n):
+                    buf[e0 + j].copy_(host_share[j], non_blocking=True)
+                    self._landed[j].record(stream)
+                    aux.wait_event(self._landed[j])
+                    off = (e0 + j) * ebytes
                     for d in range(1, self.world):          # staggered so that no peer is everybody's first target
                         r = (self.rank + d) % self.world
                         _lib.check(self.lib.fcma_peer_copy_async(ctypes.c_void_p(self._peer[k][r] + off),
-                                                                 ctypes.c_void_p(buf.data_ptr() + off), nbytes, sp))
+                                                                 ctypes.c_void_p(buf.data_ptr() + off), ebytes, sp))
+            stream.wait_stream(aux)
             dist.all_reduce(self._flag, group=self.group)    # stream-ordered barrier: every rank's copies are done
         return buf

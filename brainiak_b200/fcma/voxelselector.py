@@ -181,11 +181,19 @@ class VoxelSelector:
             _lib.load()
             _lib.require_device()
             dev = self._torch_device()
-            ep, T_e = engine.stack_epochs(self.raw_data, dev)
+            rank, world = self._world()
+            sharded = False
+            if world > 1:
+                import torch.distributed as dist
+                sharded = dist.get_backend() == "nccl" and len(self.raw_data) >= world
+            # several GPUs: every rank uploads its share of the epochs, NVLink all-gather (engine.upload_epochs_sharded)
+            upload = (lambda rd: engine.upload_epochs_sharded(rd, dev)) if sharded else \
+                (lambda rd: engine.stack_epochs(rd, dev))
+            ep, T_e = upload(self.raw_data)
             prec = engine.resolve_precision(self.precision, ep, self.normalize)
             ep2 = None
             if self.raw_data2 is not None:
-                ep2, T_e2 = engine.stack_epochs(self.raw_data2, dev)
+                ep2, T_e2 = upload(self.raw_data2)
                 if T_e2 != T_e:
                     raise ValueError("raw_data and raw_data2 must have the same epoch lengths")
                 if engine.resolve_precision(self.precision, ep2, self.normalize) != prec:
@@ -290,7 +298,10 @@ class VoxelSelector:
         op, _ = self._operands()
         E, V = op.E, self.num_voxels
         s0, n0 = engine.sym_row_partition(V, world)[rank]
-        K = torch.zeros((V, E, E), dtype=torch.float32, device=op.device)
+        per = self.row_partition(V, world)[0][1]
+        # this rank's partial sums for ALL rows (rows left of its shard stay zero), padded to world * per rows so that
+        # one reduce-scatter hands every rank the summed kernels of exactly the rows it cross-validates
+        K = torch.zeros((world * per, E, E), dtype=torch.float32, device=op.device)
         if n0 > 0:
             rows = self.block_rows or None
             if rows is None:
@@ -305,17 +316,22 @@ class VoxelSelector:
                 self._work = None       # release the old scratch first
                 self._work = engine.SymWorkspace.for_operand(op, rows, self.epochs_per_subj, flags, start=s0)
             engine.voxel_kernels_sym(op, s0, n0, self.epochs_per_subj, flags=self._flags(True),
-                                     work=self._work, out=K)
+                                     work=self._work, out=K[:V])
         if world > 1:
             import torch.distributed as dist
-            dist.all_reduce(K)
+            mine = torch.empty((per, E, E), dtype=torch.float32, device=op.device)
+            dist.reduce_scatter_tensor(mine, K)      # NVLink; every rank keeps the rows [rank * per, ...) it scores
+            del K
+            K, k0 = mine, start
+        else:
+            k0 = 0
         on_gpu = self.gpu_cv and engine.svm_cv_supported(clf, self.labels, self.num_folds, E)
         folds = engine.make_svm_folds(self.labels, self.num_folds) if on_gpu else None
         results = []
         block = 8192
         for s in range(start, start + n, block):
             nb = min(block, start + n - s)
-            results += self._cv_block(K[s:s + nb], s, nb, clf, on_gpu, folds)
+            results += self._cv_block(K[s - k0:s - k0 + nb], s, nb, clf, on_gpu, folds)
         return results
 
     def _score_rows(self, start, n, clf):

@@ -864,3 +864,160 @@ def test_voxel_selector_multi_gpu_nccl(dev):
                          capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert "multi-GPU == single-GPU result: OK" in out.stdout
+
+
+# ------------------------------------------------------------------------------- round 2: BASELINE config shapes,
+# noise floor, host entry point of the symmetric pipeline, range packing
+def _reference_or_skip():
+    from oracle import reference
+    if not reference.available():
+        pytest.skip("oracle/_ref (the unmodified reference, oracle/build_ref.sh) is not built")
+    return reference.load()
+
+
+def _reference_rows(m, raw, labels, eps, folds, s0, n0, mask_self=False, host_cv=True):
+    """Rows [s0, s0+n0) through the UNMODIFIED reference's stages (voxelselector.py:492-505): shrunk kernels and
+    cross-validation accuracies.  mask_self: zero the self column after its normaliser."""
+    vs = m.VoxelSelector(labels, eps, folds, raw, voxel_unit=n0, process_num=0)
+    clf = svm.SVC(kernel='precomputed', shrinking=False, C=1)
+    corr = vs._correlation_computation((s0, n0))
+    m.fcma_extension.normalization(corr, eps)
+    if mask_self:
+        for i in range(n0):
+            corr[i, :, s0 + i] = 0
+    K = vs._prepare_for_cross_validation(corr, clf)
+    acc = np.array([a for _, a in vs._do_cross_validation(clf, K, (s0, n0))]) if host_cv else None
+    return K, acc
+
+
+def _gpu_rows_acc(K_rows, labels, folds):
+    Kg = K_rows.clone()
+    engine.shrink_kernels_(Kg)
+    return Kg.cpu().numpy(), engine.svm_cv_precomputed(Kg, labels, folds, C=1.0, tol=1e-3)
+
+
+@pytest.mark.timeout(600)
+def test_config1_shape_vs_reference(dev):
+    """BASELINE configs[1] at FULL size (V=30 000, T=200, E=16, eps=8, fp32-faithful, one GPU): the symmetric pipeline
+    (E=16 instantiations of the row and column passes, 8 passes of 4096 rows, ragged tail 30 000 = 117*256 + 48) against
+    the unmodified reference on three 32-row samples: first pass, a middle pass, the ragged tail."""
+    m = _reference_or_skip()
+    V, T, E, eps, folds = 30000, 200, 16, 8, 2
+    raw, labels = synthetic.make_epochs(V, T, E)
+    ep, T_e = engine.stack_epochs(raw, dev)
+    op = engine.pack_epochs(ep, T_e, "fp32")
+    K = torch.zeros((V, E, E), device=dev)
+    work = engine.SymWorkspace(E, V, 4096, dev, transposed_copy=False)
+    engine.voxel_kernels_sym(op, 0, V, eps, work=work, out=K)
+    same, total = 0, 0
+    for s0 in (64, 15008, V - 32):
+        Kref, acc_ref = _reference_rows(m, raw, labels, eps, folds, s0, 32)
+        Kg, acc = _gpu_rows_acc(K[s0:s0 + 32], labels, folds)
+        assert np.max(np.abs(Kg - Kref)) <= 3e-5 * np.max(np.abs(Kref))      # measured 1.3e-5 (reference's own ssyrk noise ~1e-5)
+        same += int(np.sum(acc == acc_ref))
+        total += 32
+        assert np.max(np.abs(acc - acc_ref)) <= 2.0 / E + 1e-9
+    assert same >= total - 4          # measured: all identical
+
+
+@pytest.mark.timeout(600)
+def test_config4_classifier_kernel_at_scale(dev):
+    """BASELINE configs[4] shape class (Classifier precomputed kernel, one mask, V = 20 000, E = 32): the one [E, E]
+    kernel of engine.classifier_kernel equals the fp64 sum of the per-voxel kernels, and sampled per-voxel kernels equal
+    the unmodified reference's (its own full classifier run at this size is ~10 min of CPU: classifier.py:279-348 is the
+    same per-row arithmetic summed over rows, pinned at small size by test_classifier_big_kernel_vs_reference)."""
+    m = _reference_or_skip()
+    V, T, E, eps = 20000, 200, 32, 8
+    raw, labels = synthetic.make_epochs(V, T, E)
+    ep, T_e = engine.stack_epochs(raw, dev)
+    op = engine.pack_epochs(ep, T_e, "fp32")
+    Kc = engine.classifier_kernel(op, op, 0, V, eps)
+    Kv = engine.voxel_kernels_sym(op, 0, V, eps)
+    Ksum = Kv.to(torch.float64).sum(0)
+    assert float((Kc.to(torch.float64) - Ksum).abs().max()) <= 2e-6 * float(Ksum.abs().max())
+    assert float((Kc - Kc.t()).abs().max()) == 0.0 or float((Kc - Kc.t()).abs().max()) <= 1e-6 * float(Kc.abs().max())
+    for s0 in (256, 10016, V - 32):
+        Kref, _ = _reference_rows(m, raw, labels, eps, 4, s0, 32, host_cv=False)
+        Kg, _ = _gpu_rows_acc(Kv[s0:s0 + 32], labels, 4)
+        assert np.max(np.abs(Kg - Kref)) <= 3e-5 * np.max(np.abs(Kref))
+    # the classifier's decimal shrink rule (classifier.py:343-347) on the summed kernel
+    nd = len(str(int(float(Kc[0, 0]))))
+    assert nd > 2       # ~1e8: the shrink matters at this size
+
+
+@pytest.mark.timeout(900)
+def test_result_level_noise_floor(dev):
+    """SURVEY Appendix B.2 result-level contract, measured in this run: with the self column present ("drop-in" mode)
+    even the reference re-run on TR-permuted inputs (identical mathematics) changes the accuracy of a large share of the
+    chance-level voxels; a precision mode must not disagree with the reference more than that noise floor (plus a small
+    margin), and must agree almost everywhere once the self column is masked on both sides."""
+    m = _reference_or_skip()
+    V, T, E, eps, folds = 768, 200, 32, 8, 4
+    raw, labels = synthetic.make_epochs(V, T, E)
+    perm = np.random.RandomState(7).permutation(T)
+    raw_p = [np.ascontiguousarray(x[perm]) for x in raw]
+    _, acc_ref = _reference_rows(m, raw, labels, eps, folds, 0, V)
+    _, acc_perm = _reference_rows(m, raw_p, labels, eps, folds, 0, V)
+    floor = float(np.mean(acc_ref != acc_perm))            # e.g. 0.1 - 0.2 (SURVEY: 352 / 2000)
+    Kref_m, _ = _reference_rows(m, raw, labels, eps, folds, 0, V, mask_self=True, host_cv=False)
+    # masked reference accuracies through the batched GPU SVM (== scikit-learn, test_gpu_svm_cv_matches_sklearn)
+    acc_ref_m = engine.svm_cv_precomputed(torch.from_numpy(Kref_m).to(dev), labels, folds, C=1.0, tol=1e-3)
+    planted = set(range(V // 100))
+    clf = svm.SVC(kernel='precomputed', shrinking=False, C=1)
+    bounds = {"fp32": (1.25, 0.02, 0.99), "tf32x3": (1.25, 0.02, 0.99), "bf16x3": (1.25, 0.02, 0.985),
+              "tf32": (1.5, 0.03, 0.90), "bf16": (1.5, 0.04, 0.80)}
+    for prec, (mult, add, masked_min) in bounds.items():
+        res = VoxelSelector(labels, eps, folds, raw, process_num=0, precision=prec).run(clf)
+        acc = np.zeros(V)
+        for v, a in res:
+            acc[v] = a
+        differ = float(np.mean(acc != acc_ref))
+        assert differ <= mult * floor + add, (prec, differ, floor)
+        assert np.max(np.abs(acc - acc_ref)) <= 3.0 / E + 1e-9
+        assert planted <= set(v for v, _ in res[:max(len(planted) * 2, 10)])        # the informative voxels stay on top
+        res_m = VoxelSelector(labels, eps, folds, raw, process_num=0, precision=prec, mask_self=True).run(clf)
+        acc_m = np.zeros(V)
+        for v, a in res_m:
+            acc_m[v] = a
+        assert float(np.mean(acc_m == acc_ref_m)) >= masked_min, (prec, float(np.mean(acc_m == acc_ref_m)))
+
+
+def test_host_entry_point_symmetric_and_range_packing(dev):
+    """fcma_host_voxel_kernels_sym (host buffers in, host buffers out, everything inside the call) equals the device
+    path; fcma_pack_operand_range packs exactly the voxels it is asked for, bit-identically to a full pack."""
+    V, T, E, eps = 1100, 40, 8, 4
+    raw, _ = synthetic.make_epochs(V, T, E, seed=4242)
+    ep, T_e = engine.stack_epochs(raw, dev)
+    op = engine.pack_epochs(ep, T_e, "fp16x3")
+    Kdev = engine.voxel_kernels_sym(op, 0, V, eps).cpu().numpy()
+    Kh = engine.host_voxel_kernels_sym(raw, eps, precision="fp16x3", rows_per_pass=512)
+    assert np.max(np.abs(Kh - Kdev)) <= 1e-5 * np.max(np.abs(Kdev))
+    host = torch.from_numpy(np.stack(raw)).pin_memory()
+    out = torch.empty((V, E, E), dtype=torch.float32).pin_memory()
+    engine.host_voxel_kernels_sym(host, eps, precision="fp16x3", out=out, rows_per_pass=256)
+    assert np.max(np.abs(out.numpy() - Kdev)) <= 1e-5 * np.max(np.abs(Kdev))
+    assert torch.cuda.current_device() == dev.index          # the entry point restores the caller's device
+    # range packing: voxels >= 512 only, into a buffer pre-filled with a pattern
+    full = op.buf.clone()
+    part = engine.PackedOperand(torch.full_like(op.buf, 0x5A), E, T, V, op.precision, op.T_e)
+    engine.pack_epochs(ep, T_e, "fp16x3", v_begin=512, out=part)
+    kp = _lib.load().fcma_operand_kp(_lib.PREC["fp16x3"], T)
+    planes = full[: 2 * E * V * kp * 2].view(2, E, V, kp * 2)
+    got = part.buf[: 2 * E * V * kp * 2].view(2, E, V, kp * 2)
+    assert torch.equal(got[:, :, 512:], planes[:, :, 512:])
+    assert bool((got[:, :, :512] == 0x5A).all())
+    Kp = engine.voxel_kernels_sym(part, 512, V - 512, eps).cpu().numpy()
+    Kf = engine.voxel_kernels_sym(op, 512, V - 512, eps).cpu().numpy()
+    assert np.array_equal(Kp, Kf)
+
+
+def test_epoch_exchange_single_rank(dev):
+    """EpochExchange without a process group: the share is everything, gather is one H2D copy."""
+    from brainiak_b200.fcma.exchange import EpochExchange, epoch_partition
+    assert epoch_partition(32, 8) == [(4 * r, 4) for r in range(8)]
+    assert epoch_partition(10, 4) == [(0, 3), (3, 3), (6, 2), (8, 2)]
+    x = EpochExchange(4, 8, 64, dev, nbuf=2)
+    host = torch.randn((4, 8, 64)).pin_memory()
+    out = x.gather(1, host)
+    torch.cuda.synchronize()
+    assert x.mode == "single" and torch.equal(out.cpu(), host)

@@ -225,3 +225,38 @@ def test_symmetric_pipeline_host_queries():
     assert lib.fcma_sym_rows_per_pass(P["fp16x3"], 32, 8, 0, 50000, 0, 100 * per_row) == 0     # too small
     # a shard that starts further right needs less scratch per row
     assert lib.fcma_sym_rows_per_pass(P["fp16x3"], 32, 8, 0, 50000, 25088, 4096 * per_row) > 8000
+
+
+def test_sym_row_partition_is_min_max_over_whole_tiles():
+    """Shards of the symmetric pipeline: contiguous, whole 256-row tiles (ragged tail only at V), covering [0, V) exactly
+    once, and balanced: the bottleneck shard is within one tile's worth of work of the ideal share."""
+    from brainiak_b200.fcma import engine
+
+    def cost(V, s, n, pf=0.01):
+        return ((1 - s / V) ** 2 - (1 - (s + n) / V) ** 2) + pf * (1 - s / V)
+    for V, W in ((50000, 1), (50000, 2), (50000, 4), (50000, 8), (100000, 8), (30000, 3), (1536, 3), (1100, 2)):
+        parts = engine.sym_row_partition(V, W)
+        assert len(parts) == W and parts[0][0] == 0
+        pos = 0
+        for s, n in parts:
+            assert s == pos and n >= 0
+            assert n % 256 == 0 or s + n == V
+            assert s % 256 == 0 or n == 0
+            pos += n
+        assert pos == V
+        costs = [cost(V, s, n) for s, n in parts]
+        ideal = sum(costs) / W
+        one_tile = cost(V, 0, min(256, V))
+        assert max(costs) <= ideal + one_tile + 1e-12
+    # more ranks than tiles: the surplus ranks get empty shards at the end
+    parts = engine.sym_row_partition(600, 4)
+    assert sum(n for _, n in parts) == 600 and parts[-1][1] == 0
+
+
+def test_epoch_partition_covers_all_epochs():
+    from brainiak_b200.fcma.exchange import epoch_partition
+    for E, W in ((32, 8), (64, 8), (10, 4), (3, 8), (16, 1)):
+        p = epoch_partition(E, W)
+        assert len(p) == W and p[0][0] == 0 and sum(n for _, n in p) == E
+        assert all(p[r][0] + p[r][1] == p[r + 1][0] for r in range(W - 1))
+        assert max(n for _, n in p) - min(n for _, n in p) <= 1

@@ -974,7 +974,9 @@ def test_result_level_noise_floor(dev):
         differ = float(np.mean(acc != acc_ref))
         assert differ <= mult * floor + add, (prec, differ, floor)
         assert np.max(np.abs(acc - acc_ref)) <= 3.0 / E + 1e-9
-        assert planted <= set(v for v, _ in res[:max(len(planted) * 2, 10)])        # the informative voxels stay on top
+        # the informative (planted) voxels score like the reference says, whatever the chance-level ones do
+        pl = sorted(planted)
+        assert np.max(np.abs(acc[pl] - acc_ref[pl])) <= 1.0 / E + 1e-9
         res_m = VoxelSelector(labels, eps, folds, raw, process_num=0, precision=prec, mask_self=True).run(clf)
         acc_m = np.zeros(V)
         for v, a in res_m:

@@ -1182,6 +1182,12 @@ static int launch_corr_umma(const void *rows_op, const void *cols_op, int precis
     const unsigned gemm_threads = 128u + 32u * (unsigned)q.epi_warps;
     const long ngroups = q.total_tiles / q.grp_tiles;
     if (ngroups < pairs) pairs = ngroups;
+    {
+        // diagnostic build: FCMA_GEMM_PAIRS=n caps the persistent grid at n CTA pairs, leaving SMs to kernels of another
+        // stream (tools/r2_overlap.py: does overlapping the write-bound GEMM with the read-bound passes pay?)
+        const char *gp = diag_env("FCMA_GEMM_PAIRS");
+        if (gp && atoi(gp) >= 1 && atoi(gp) < pairs) pairs = atoi(gp);
+    }
 #define FCMA_LAUNCH_GEMM(KK, HH)                                                                                      \
     do {                                                                                                              \
         CUDA_TRY(cudaFuncSetAttribute(k_corr_umma2<KK, HH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
@@ -1471,7 +1477,7 @@ __global__ void __launch_bounds__(256, (R == 4 ? 2 : 1))
     using elem_t = std::conditional_t<VEC == 2, __half, float>;
     [[maybe_unused]] float *s_part =
         reinterpret_cast<float *>(dyn_smem + (VEC ? (size_t)8 * 2 * CPL * 32 * sizeof(float4) : 0));
-    constexpr int FLUSH = R == 4 ? 8 : 32;   // chunks between flushes (E > 32: atomics are dearer, flush less often)
+    constexpr int FLUSH = 8;   // chunks between flushes of the MMA accumulators (bounds the truncating accumulation chain)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, t = lane & 3;
     const int S_eps = EPS > 0 ? (E / EPS) * EPS : 0;  // epochs that get normalised
@@ -1510,20 +1516,27 @@ __global__ void __launch_bounds__(256, (R == 4 ? 2 : 1))
                     for (int c = 0; c < 4; c++) acc[mu][nu][c] = 0.f;
                 }
         };
+        // R == 8: the block's s_K is kept in FRAGMENT order, element ((mu*NT + nu)*4 + c)*32 + lane, so that the 32 lanes
+        // of an atomic instruction hit 32 different banks (in (row, col) order they collide 16-way: rows 8g.. are 512
+        // floats apart); frag_index() below maps (row, col) back when the row is written out.
         auto flush_atomic = [&]() {
 #pragma unroll
             for (int mu = 0; mu < MT; mu++)
 #pragma unroll
                 for (int nu = 0; nu < NT; nu++) {
-                    const int row0 = R * g + 2 * mu, row1 = row0 + 1;
-                    const int col0 = R * (2 * t) + nu, col1 = R * (2 * t + 1) + nu;
-                    atomicAdd(&s_K[row0 * EP + col0], acc[mu][nu][0]);
-                    atomicAdd(&s_K[row0 * EP + col1], acc[mu][nu][1]);
-                    atomicAdd(&s_K[row1 * EP + col0], acc[mu][nu][2]);
-                    atomicAdd(&s_K[row1 * EP + col1], acc[mu][nu][3]);
 #pragma unroll
-                    for (int c = 0; c < 4; c++) acc[mu][nu][c] = 0.f;
+                    for (int c = 0; c < 4; c++) {
+                        atomicAdd(&s_K[((mu * NT + nu) * 4 + c) * 32 + lane], acc[mu][nu][c]);
+                        acc[mu][nu][c] = 0.f;
+                    }
                 }
+        };
+        // (row, col) of the padded EP x EP matrix -> position in fragment order: row = R*g + 2*mu + (c >> 1),
+        // col = R*(2*t + (c & 1)) + nu, lane = 4*g + t
+        [[maybe_unused]] auto frag_index = [](int row, int col) {
+            const int gg = row / R, mu = (row % R) >> 1, ch = row & 1;
+            const int q = col / R, nu = col % R, tt = q >> 1, cl = q & 1;
+            return ((mu * NT + nu) * 4 + (ch * 2 + cl)) * 32 + 4 * gg + tt;
         };
         if constexpr (R == 4) {
             float *part = s_part + warp * (EP * EP);
@@ -1791,9 +1804,9 @@ __global__ void __launch_bounds__(256, (R == 4 ? 2 : 1))
                 }
             } else {
                 // R == 8: no shared memory left for per-warp partials: every FLUSH chunks a warp adds its
-                // MMA accumulators into the block's s_K with shared-memory atomics (round-to-nearest adds; the
-                // order in which the 8 warps arrive is not fixed, so the E > 32 kernels are reproducible only
-                // to fp32 rounding, ~1e-7 relative -- the E <= 32 path above is bit-reproducible)
+                // MMA accumulators into the block's s_K (fragment order: conflict-free) with shared-memory atomics
+                // (round-to-nearest adds; the order in which the 8 warps arrive is not fixed, so the E > 32 kernels are
+                // reproducible only to fp32 rounding, ~1e-7 relative -- the E <= 32 path above is bit-reproducible)
                 if (++since_flush == FLUSH) {
                     flush_atomic();
                     since_flush = 0;
@@ -1819,7 +1832,11 @@ __global__ void __launch_bounds__(256, (R == 4 ? 2 : 1))
         // ---- write: symmetric by construction from the lower triangle (cython_blas.pyx:200-207)
         for (int idx = threadIdx.x; idx < E * E; idx += 256) {
             const int a = idx / E, b = idx - a * E;
-            const float v = a >= b ? s_K[a * EP + b] : s_K[b * EP + a];
+            float v;
+            if constexpr (R == 4)
+                v = a >= b ? s_K[a * EP + b] : s_K[b * EP + a];
+            else
+                v = a >= b ? s_K[frag_index(a, b)] : s_K[frag_index(b, a)];
             if (sum_over_rows) {
                 atomicAdd(&K[idx], v);
             } else {

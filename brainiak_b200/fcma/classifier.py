@@ -10,6 +10,11 @@ libfcma_b200.so:
 * ``_compute_kernel_matrix_in_portion`` (classifier.py:279-348, a11) -> fused GEMM -> normalise ->
   ``K += Z Z^T`` without ever materialising the ``[E, rows, V2]`` correlation block on the host
 * ``_prepare_test_data``          (classifier.py:222-277, a12) -> NT GEMM against the training features
+
+Large masks: after a portion-mode fit the reference cannot ``predict(X)`` new data because it would
+need ``training_data_`` = ``[n_train, V1*V2]`` features (320 GB at V = 50 000).  Here the classifier keeps references to
+the raw TRAINING epochs instead (1.3 GB) and ``predict`` / ``decision_function`` stream the test-vs-train similarity
+portion by portion on the GPU (``_streamed_similarity``) without ever materialising the features.
 """
 import logging
 import time
@@ -56,6 +61,7 @@ class Classifier(BaseEstimator):
         self.precision = precision
         self.device = device
         self.num_digits_ = 0
+        self._train_raw_ = None
         return
 
     # ------------------------------------------------------------------ device helpers
@@ -197,8 +203,13 @@ class Classifier(BaseEstimator):
             if self.num_processed_voxels >= self.num_voxels_:
                 self.training_data_ = normalized_corr_data.reshape(self.num_samples_,
                                                                    self.num_features_)
+                self._train_raw_ = None
             else:
                 self.training_data_ = None
+                # references (no copies) to the raw training epochs: what streamed prediction needs instead of the
+                # [n_train, V1*V2] features
+                n_train = num_training_samples if num_training_samples is not None else self.num_samples_
+                self._train_raw_ = (list(X1[:n_train]), list(X2[:n_train]))
             logger.debug('kernel computation done')
         return data
 
@@ -252,9 +263,46 @@ class Classifier(BaseEstimator):
             'the number of features does not match the model'
         num_test_samples = len(X1)
         self.test_raw_data_ = X
+        if _is_precomputed_svc(self.clf) and self.training_data_ is None and \
+                getattr(self, "_train_raw_", None) is not None:
+            self.test_data_ = self._streamed_similarity(X1, X2)
+            return
         corr_data = self._prepare_corerelation_data(X1, X2)
         normalized_corr_data = self._normalize_correlation_data(corr_data, num_test_samples)
         self.test_data_ = self._prepare_test_data(normalized_corr_data)
+
+    def _streamed_similarity(self, X1, X2, max_bytes=8 << 30):
+        """Test-vs-train similarity ``[n_test, n_train]`` for large masks, never materialising the features
+        (the reference's ``_prepare_test_data``, classifier.py:222-277, needs ``training_data_``).
+
+        The training and the test epochs form one sample list; per portion of voxel rows the tensor-core GEMM writes
+        the correlation block ``[samples, rows, V2]`` (a9), the training part is normalised within subject with
+        ``epochs_per_subj`` as ``fit`` does (classifier.py:325-327), the test part over all test samples as ``predict``
+        does (classifier.py:554-556), and ``K += Z Z^T`` accumulates the Gram matrix over the portions (a11); its
+        test x train block, scaled with the ``num_digits_`` of the training kernel, is the similarity."""
+        import torch
+        tr1, tr2 = self._train_raw_
+        n_train, n_test = len(tr1), len(X1)
+        if tr1[0].shape[1] != X1[0].shape[1]:        # fit() may have swapped the masks so that X1 is the larger one
+            tr1, tr2 = tr2, tr1
+        op1, op2 = self._pack_pair(list(tr1) + list(X1), list(tr2) + list(X2))
+        Es = n_train + n_test
+        V1, V2 = op1.V, op2.V
+        rows = int(max(1, min(self.num_processed_voxels, V1, max_bytes // (Es * V2 * 4))))
+        K = torch.zeros((Es, Es), dtype=torch.float32, device=op1.device)
+        for start in range(0, V1, rows):
+            nb = min(rows, V1 - start)
+            corr = engine.corr_block(op1, op2, start, nb, layout=1)                    # [Es, nb, V2]
+            if self.epochs_per_subj > 1:
+                engine.within_subject_norm_(corr[:n_train].view(1, n_train, nb * V2), self.epochs_per_subj)
+            if n_test > 1:
+                engine.within_subject_norm_(corr[n_train:].view(1, n_test, nb * V2), n_test)
+            engine.kernel_matrices(corr.view(1, Es, nb * V2), beta=1.0, out=K, sum_over_rows=True)
+        data = K[n_train:, :n_train].cpu().numpy()
+        if self.num_digits_ > 2:
+            data *= 10 ** (2 - self.num_digits_)
+        logger.debug('streamed similarity vectors computation done')
+        return np.ascontiguousarray(data)
 
     def predict(self, X=None):
         """Use a trained model to predict correlation data (classifier.py:506-566)."""

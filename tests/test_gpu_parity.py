@@ -1023,3 +1023,79 @@ def test_epoch_exchange_single_rank(dev):
     out = x.gather(1, host)
     torch.cuda.synchronize()
     assert x.mode == "single" and torch.equal(out.cpu(), host)
+
+
+@pytest.mark.parametrize("two", [False, True])
+def test_classifier_streamed_prediction(dev, two):
+    """after a portion-mode fit (training_data_ is None) predict / decision_function on NEW data
+    stream the test-vs-train similarity portion by portion from the raw training epochs; same decision values as the
+    small-mask path that materialises training_data_ (classifier.py:222-277, 506-566)."""
+    prng = RandomState(1234567890)
+    nv1, nv2 = (9, 6) if two else (9, 9)
+    a = [_create_clf_epoch(prng, i, nv1) for i in range(20)]
+    b = [_create_clf_epoch(prng, i, nv2) for i in range(20)] if two else a
+    labels = [0, 1] * 10
+    X = list(zip(a, b))
+    full = Classifier(svm.SVC(kernel='precomputed', shrinking=False, C=1), epochs_per_subj=4)
+    full.fit(X[:12], labels[:12])
+    assert full.training_data_ is not None
+    conf_full = full.decision_function(X[12:])
+    # portion mode: 2 voxel rows per portion, the kernel over all 20 samples, the first 12 for training
+    part = Classifier(svm.SVC(kernel='precomputed', shrinking=False, C=1), num_processed_voxels=2, epochs_per_subj=4)
+    part.fit(X, labels, num_training_samples=12)
+    assert part.training_data_ is None and part._train_raw_ is not None and len(part._train_raw_[0]) == 12
+    sim_full = full.test_data_.copy()               # [8, 12] similarity from the materialised features
+    conf = part.decision_function(X[12:])            # NEW data after a portion-mode fit -> streamed similarity
+    assert part.test_data_.shape == (8, 12)
+    assert np.allclose(part.test_data_, sim_full, rtol=2e-4, atol=2e-4 * np.max(np.abs(sim_full)))
+    assert np.allclose(conf, conf_full, atol=2e-3)
+    assert np.array_equal(part.predict(X[12:]), full.predict(X[12:]))
+    # score() in portion mode scores the cached test part (classifier.py:652-690): here the same 8 samples
+    assert np.isclose(part.score(X[12:], labels[12:]), full.score(X[12:], labels[12:]))
+
+
+def test_prepare_fcma_data_matches_reference_arithmetic(dev):
+    """prepare_fcma_data (reference preprocessing.py:156-232) on synthetic 4-D images: masking (image.py:107-140),
+    voxel randomisation with the reference's seeding, epoch separation + z-score on the GPU -- against the same steps in
+    numpy / scipy."""
+    from brainiak_b200.fcma.preprocessing import RandomType, prepare_fcma_data
+    prng = RandomState(42)
+    nsub, shape, ntr = 3, (5, 4, 3), 40
+    images = [prng.randn(*shape, ntr).astype(np.float32) * 3 + 10 for _ in range(nsub)]
+    mask1 = prng.rand(*shape) > 0.4
+    mask2 = prng.rand(*shape) > 0.6
+    cond = np.zeros((2, 4, ntr), np.int8)       # 2 conditions, 4 epochs of 8 TRs each
+    for e in range(4):
+        cond[e % 2, e, 2 + 9 * e: 10 + 9 * e] = 1
+    conditions = [cond] * nsub
+
+    def expected(mask, random):
+        act = [im.astype(np.float32)[mask] for im in images]
+        if random == RandomType.REPRODUCIBLE:
+            for i in range(len(act)):
+                np.random.seed(i)
+                np.random.shuffle(act[i])
+        raw, labels = [], []
+        for sid in range(nsub):
+            for c in range(2):
+                for e in range(4):
+                    sel = cond[c, e] == 1
+                    if sel.sum() > 0:
+                        mat = np.ascontiguousarray(act[sid][:, sel].T)
+                        mat = np.nan_to_num(zscore(mat, axis=0, ddof=0)) / math.sqrt(sel.sum())
+                        raw.append(mat.astype(np.float32))
+                        labels.append(c)
+        return raw, labels
+    for random in (RandomType.NORANDOM, RandomType.REPRODUCIBLE):
+        r1, r2, labels = prepare_fcma_data(images, conditions, mask1, mask2, random=random)
+        e1, el = expected(mask1, random)
+        e2, _ = expected(mask2, random)
+        assert list(labels) == el and len(r1) == len(e1) == 12 and len(r2) == 12
+        for got, ref in zip(r1 + r2, e1 + e2):
+            assert got.shape == ref.shape and got.dtype == np.float32 and np.allclose(got, ref, atol=2e-6)
+    r1, r2, labels = prepare_fcma_data(images, conditions, mask1)
+    assert r2 is None and len(r1) == 12
+    (ep, T_e), none2, labels = prepare_fcma_data(images, conditions, mask1, return_device=True)
+    assert none2 is None and ep.is_cuda and tuple(ep.shape) == (12, 8, int(mask1.sum())) and T_e == [8] * 12
+    with pytest.raises(ValueError, match="different shapes"):
+        prepare_fcma_data(images, conditions, mask1[:-1])

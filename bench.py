@@ -118,7 +118,10 @@ def device_epochs(V, T, E, dev, seed):
 # clocks
 # ---------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    """nvidia-smi sampled every 20 ms from the START of the run (the process needs a few hundred ms before its first
+    line, longer than a whole multi-GPU timed region); `window(t0, t1)` then picks the samples whose own timestamps
+    fall inside the timed region."""
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -130,42 +133,59 @@ class ClockSampler:
     def start(self):
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                       "--format=csv,noheader,nounits", "-lms", "20"],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
 
     def stop(self):
         if self.p is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return
         self.p.terminate()
         try:
             self.p.wait(timeout=5)
         except subprocess.TimeoutExpired:
             self.p.kill()
+        self.p = None
+
+    def window(self, t0, t1):
+        """Clock record of the samples stamped inside [t0, t1] (time.time() values)."""
+        import datetime
+        if self.f is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.f.flush()
         self.f.seek(0)
-        sm, mx, reasons, power = [], 0, set(), []
+        sm, mx, reasons, power, inside = [], 0, set(), [], 0
         for line in self.f.read().splitlines():
             parts = [s.strip() for s in line.split(",")]
-            if len(parts) < 9:
+            if len(parts) < 10:
                 continue
             try:
-                c, m, pw = float(parts[1]), float(parts[2]), float(parts[3])
+                ts = datetime.datetime.strptime(parts[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                c, m, pw = float(parts[2]), float(parts[3]), float(parts[4])
             except ValueError:
                 continue
             mx = max(mx, m)
+            if ts < t0 - 0.005 or ts > t1 + 0.005:
+                continue
+            inside += 1
             power.append(pw)
-            if pw > 250:          # under load
-                sm.append(c)
+            sm.append(c)
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
-                                "sw_power_cap"), parts[5:9]):
+                                "sw_power_cap"), parts[6:10]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        os.unlink(self.f.name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None,
-                "reasons": sorted(reasons), "samples_under_load": len(sm),
-                "power_w_max": max(power) if power else None}
+                "reasons": sorted(reasons), "samples_in_timed_region": inside,
+                "power_w_median": float(np.median(power)) if power else None,
+                "power_w_max": max(power) if power else None, "sampling": "nvidia-smi -lms 20, samples stamped inside the timed region"}
+
+    def close(self):
+        self.stop()
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
 
 
 # ---------------------------------------------------------------------------------------------
@@ -333,6 +353,9 @@ def run_b200_arm(args):
         pg2 = dist.new_group(backend="nccl")       # collectives issued from the copy stream (epoch exchange)
     lib = _lib.load()
     _lib.require_device()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -471,11 +494,14 @@ def run_b200_arm(args):
     # ---- headline: kernel path with the inputs resident in HBM
     for _ in range(max(args.warmup, 3)):
         kernels_step(epochs, Kfull)
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    t_begin = time.time()
     ms_total, launches, _ = timed(args.steps, lambda: kernels_step(epochs, Kfull))
-    clocks = sampler.stop() if rank == 0 else None
+    t_end = time.time()
+    clocks = None
+    if rank == 0:
+        time.sleep(0.05)
+        clocks = sampler.window(t_begin, t_end)
+        sampler.close()
     ms_step = ms_total / args.steps
     corr_total = float(V) * V * E
     value = corr_total / (ms_step * 1e-3)

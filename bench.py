@@ -70,6 +70,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-others", action="store_true", help="skip the other BASELINE configs")
     ap.add_argument("--no-ipc", action="store_true", help="epoch exchange through NCCL all-gather instead of CUDA IPC copies")
+    ap.add_argument("--clock-interval-ms", type=int, default=20, help="nvidia-smi sampling interval")
     return ap.parse_args()
 
 
@@ -125,15 +126,16 @@ class ClockSampler:
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
+    def __init__(self, index, interval_ms=20):
         self.index = index
+        self.interval_ms = int(interval_ms)
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.p = None
 
     def start(self):
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                       "--format=csv,noheader,nounits", "-lms", "20"],
+                                       "--format=csv,noheader,nounits", "-lms", str(self.interval_ms)],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
@@ -178,7 +180,7 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None,
                 "reasons": sorted(reasons), "samples_in_timed_region": inside,
                 "power_w_median": float(np.median(power)) if power else None,
-                "power_w_max": max(power) if power else None, "sampling": "nvidia-smi -lms 20, samples stamped inside the timed region"}
+                "power_w_max": max(power) if power else None, "sampling": "nvidia-smi -lms %d, samples stamped inside the timed region" % self.interval_ms}
 
     def close(self):
         self.stop()
@@ -353,7 +355,7 @@ def run_b200_arm(args):
         pg2 = dist.new_group(backend="nccl")       # collectives issued from the copy stream (epoch exchange)
     lib = _lib.load()
     _lib.require_device()
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(local, args.clock_interval_ms)
     if rank == 0:
         sampler.start()
     peaks = {}

@@ -1830,18 +1830,45 @@ __global__ void __launch_bounds__(256, (R == 4 ? 2 : 1))
             __syncthreads();
         }
         // ---- write: symmetric by construction from the lower triangle (cython_blas.pyx:200-207)
-        for (int idx = threadIdx.x; idx < E * E; idx += 256) {
+        auto kval = [&](int idx) {
             const int a = idx / E, b = idx - a * E;
-            float v;
             if constexpr (R == 4)
-                v = a >= b ? s_K[a * EP + b] : s_K[b * EP + a];
+                return a >= b ? s_K[a * EP + b] : s_K[b * EP + a];
             else
-                v = a >= b ? s_K[frag_index(a, b)] : s_K[frag_index(b, a)];
-            if (sum_over_rows) {
-                atomicAdd(&K[idx], v);
-            } else {
-                float *dst = &K[(size_t)i * E * E + idx];
-                *dst = (beta == 0.f ? 0.f : beta * *dst) + v;
+                return a >= b ? s_K[frag_index(a, b)] : s_K[frag_index(b, a)];
+        };
+        float *Ki = K + (size_t)i * E * E;
+        if (!sum_over_rows && ((E * E) & 3) == 0 && ((reinterpret_cast<uintptr_t>(Ki) & 15) == 0)) {
+            // K[i] = beta * K[i] + v as 16-byte read-modify-writes with all of a thread's loads in flight at once
+            // (the dependent scalar loop was latency-bound: ~16 us per row at E = 64, most of a short row's time)
+            constexpr int PT = (EP * EP / 4 + 255) / 256;      // float4 pieces per thread (1 at EP = 32, 4 at EP = 64)
+            float4 *K4 = reinterpret_cast<float4 *>(Ki);
+            const int total4 = (E * E) >> 2;
+            float4 old[PT];
+#pragma unroll
+            for (int u = 0; u < PT; u++) {
+                const int i4 = (int)threadIdx.x + u * 256;
+                old[u] = (beta != 0.f && i4 < total4) ? K4[i4] : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < PT; u++) {
+                const int i4 = (int)threadIdx.x + u * 256;
+                if (i4 < total4) {
+                    float4 o = old[u];
+                    o.x = beta * o.x + kval(4 * i4), o.y = beta * o.y + kval(4 * i4 + 1);
+                    o.z = beta * o.z + kval(4 * i4 + 2), o.w = beta * o.w + kval(4 * i4 + 3);
+                    K4[i4] = o;
+                }
+            }
+        } else {
+            for (int idx = threadIdx.x; idx < E * E; idx += 256) {
+                const float v = kval(idx);
+                if (sum_over_rows) {
+                    atomicAdd(&K[idx], v);
+                } else {
+                    float *dst = &Ki[idx];
+                    *dst = (beta == 0.f ? 0.f : beta * *dst) + v;
+                }
             }
         }
         __syncthreads();

@@ -494,11 +494,18 @@ def shrink_kernels_(K, return_digits=False):
     return digits
 
 
-def svm_cv_supported(clf, labels, num_folds, E):
+def svm_cv_supported(clf, labels, num_folds, E, allow_shrinking=False):
     """True if ``cross_val_score(clf, K, labels, cv=StratifiedKFold(num_folds))`` can run on the GPU:
-    binary ``SVC(kernel='precomputed')`` without class weights / probability, E <= 64."""
+    binary ``SVC(kernel='precomputed')`` without class weights / probability, E <= 64.
+
+    The GPU solver restates libsvm's SMO WITHOUT the shrinking heuristic: bit-identical decisions for
+    ``shrinking=False`` (what the reference's tests and examples use, tests/fcma/test_voxel_selection.py:70), the same
+    optimum within ``tol`` for ``shrinking=True`` (scikit-learn's default) -- there an accuracy can differ by one test
+    sample, so such classifiers go to the host unless ``allow_shrinking`` (``VoxelSelector(gpu_cv="always")``)."""
     import sklearn.svm
     if not (isinstance(clf, sklearn.svm.SVC) and clf.kernel == 'precomputed'):
+        return False
+    if getattr(clf, 'shrinking', False) and not allow_shrinking:
         return False
     # scikit-learn >= 1.9 uses the string 'deprecated' as the default of `probability`
     if clf.class_weight is not None or getattr(clf, 'probability', False) is True or E > 64 or num_folds > 64:

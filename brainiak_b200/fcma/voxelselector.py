@@ -89,10 +89,13 @@ class VoxelSelector:
     symmetric: with a single mask (``raw_data2 is None``) use ``corr[i, e, j] == corr[j, e, i]``: only the
         blocks on and above the diagonal are contracted and each is used for its row and its column voxels
         (engine.voxel_kernels_sym; half the tensor work, same kernels up to fp32 summation order).  Over
-        several GPUs the shards' partial kernel arrays are summed with one NCCL all-reduce.
-    gpu_cv: run the voxelwise cross validation of a binary ``SVC(kernel='precomputed')`` on the GPU
-        (batched restatement of libsvm's SMO, see engine.svm_cv_precomputed); ``False`` or any other
-        classifier -> scikit-learn on the host, exactly as the reference (voxelselector.py:41-53)
+        several GPUs the shards' partial kernel arrays are summed with one NCCL reduce-scatter (every rank keeps the
+        rows it cross-validates).
+    gpu_cv: run the voxelwise cross validation of a binary ``SVC(kernel='precomputed', shrinking=False)`` on the GPU
+        (batched restatement of libsvm's SMO with bit-identical decisions, see engine.svm_cv_precomputed);
+        ``"always"`` also takes ``shrinking=True`` classifiers to the GPU (same optimum within ``tol``, an accuracy may
+        differ by one test sample); ``False`` or any other classifier -> scikit-learn on the host, exactly as the
+        reference (voxelselector.py:41-53)
     """
 
     def __init__(self, labels, epochs_per_subj, num_folds, raw_data, raw_data2=None,
@@ -135,7 +138,7 @@ class VoxelSelector:
         self.normalize = bool(normalize)
         self.device = device
         self.block_rows = block_rows
-        self.gpu_cv = bool(gpu_cv)
+        self.gpu_cv = gpu_cv if gpu_cv == "always" else bool(gpu_cv)
         self.symmetric = bool(symmetric)
         self._rows_op = None
         self._cols_op = None
@@ -325,7 +328,8 @@ class VoxelSelector:
             K, k0 = mine, start
         else:
             k0 = 0
-        on_gpu = self.gpu_cv and engine.svm_cv_supported(clf, self.labels, self.num_folds, E)
+        on_gpu = self.gpu_cv and engine.svm_cv_supported(clf, self.labels, self.num_folds, E,
+                                                         allow_shrinking=self.gpu_cv == "always")
         folds = engine.make_svm_folds(self.labels, self.num_folds) if on_gpu else None
         results = []
         block = 8192
@@ -349,7 +353,8 @@ class VoxelSelector:
             if self._work is None or self._work.rows < block or isinstance(self._work, engine.SymWorkspace):
                 self._work = None
                 self._work = engine.Workspace(E, self.num_voxels2, block, rows_op.device)
-            on_gpu = self.gpu_cv and engine.svm_cv_supported(clf, self.labels, self.num_folds, E)
+            on_gpu = self.gpu_cv and engine.svm_cv_supported(clf, self.labels, self.num_folds, E,
+                                                             allow_shrinking=self.gpu_cv == "always")
             folds = engine.make_svm_folds(self.labels, self.num_folds) if on_gpu else None
             for s in range(start, start + n, block):
                 nb = min(block, start + n - s)

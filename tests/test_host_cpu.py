@@ -155,8 +155,12 @@ def test_svm_fold_descriptors_follow_sklearn_splits():
     assert ctypes.sizeof(folds[0]) == 592                    # layout of struct SvmFold in the library
     with pytest.raises(ValueError):
         engine.make_svm_folds([0, 1, 2] * 4, 2)              # multi-class -> host scikit-learn path
-    clf = svm.SVC(kernel="precomputed")
+    clf = svm.SVC(kernel="precomputed", shrinking=False)
     assert engine.svm_cv_supported(clf, [0, 1] * 8, 4, 16)
+    # scikit-learn's default shrinking=True: the GPU solver (no shrinking heuristic) is equal within tol, not bit-identical,
+    # so it is opt-in (VoxelSelector(gpu_cv="always"))
+    assert not engine.svm_cv_supported(svm.SVC(kernel="precomputed"), [0, 1] * 8, 4, 16)
+    assert engine.svm_cv_supported(svm.SVC(kernel="precomputed"), [0, 1] * 8, 4, 16, allow_shrinking=True)
     assert not engine.svm_cv_supported(clf, [0, 1, 2] * 4, 2, 12)
     assert not engine.svm_cv_supported(svm.SVC(kernel="linear"), [0, 1] * 8, 4, 16)
     assert not engine.svm_cv_supported(clf, [0, 1] * 40, 4, 80)

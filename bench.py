@@ -865,7 +865,7 @@ def other_configs(args, lib, engine, torch, dist, dev, rank, world, local, hbm_p
     run_cfg("configs[1] V=30000 T=200 E=16 (1 GPU)", 30000, 200, 16, 8, 4096, sharded=False)
     if os.environ.get("FCMA_BENCH_SKIP_CONFIG3") != "1":
         run_cfg("configs[3] V=100000 T=500 E=64 (%d GPU%s)" % (world, "s" if world > 1 else ""), 100000, 500, 64, 8,
-                2048, sharded=True, ref_rows=16)
+                4096, sharded=True, ref_rows=16)
     if rank == 0:
         # configs[4]: Classifier precomputed corr-kernel matrix, V=50 000 E=32: ONE [E, E] kernel = sum over all voxel rows
         V, T, E, eps = 50000, 200, 32, 8

@@ -2157,6 +2157,233 @@ __global__ void __launch_bounds__(32 * (32 / CPW), 1)
 }
 
 // ============================================================================================
+// Column-direction pass, version 2 (FCMA_FLAG_COLS_V2, fp32 block): normalise ONCE per value in a thread-per-row layout,
+// then feed the MMAs with ldmatrix.  Measured as fast as k_norm_syrk_cols -- not faster -- inside the power-capped step.
+//
+// k_norm_syrk_cols above loads a brick straight into mma fragment layout (lane = (4 epochs, 4 rows)), so the statistics
+// of a subject are spread over lanes (shuffles), every value pair has to be re-paired for the packed fp32x2 FMAs
+// (15 % of its dynamic instructions are IMAD.MOV) and each lane repeats its partner's `finish`: ~680 warp
+// instructions per warp and brick, issue-latency-bound at two warps per scheduler (profiles/r2_prof_sym_*.txt).
+// Here warp w still owns columns 4w .. 4w+3 of the 32-column strip, but per brick [32 epochs][16 rows][32 columns]
+//   phase 1: lane l takes row (l & 15) and epochs 16*(l >> 4) .. +15: sixteen LDS.128 (4 adjacent columns of one
+//            (epoch, row) each), the subject statistics are plain in-thread sums over epochs on NATURAL fp32x2 pairs
+//            (columns 0|1 and 2|3) -- no shuffles (EPS = 32: one exchange with lane l ^ 16), one `finish` per (subject,
+//            column pair); the z-scored values are rounded to fp16 and stored as [column][row][32 epochs] (64 B per
+//            (column, row), 16-byte pieces swizzled with (row >> 1) & 3, bit 2 of the bank group from row & 1) into the
+//            warp's own 4 KB staging buffer;
+//   phase 2: per column two ldmatrix.x4.trans (rows 0-7 -> k-slots 2t, 2t+1; rows 8-15 -> k-slots 2t+8, 2t+9) deliver
+//            the eight fragment registers that serve as A AND B operands of the eight mma.m16n8k16 of Z Z^T, with lane
+//            g <-> epoch 8*block + g: the accumulators are in NATURAL epoch order (no permutation to undo).
+// Only a __syncwarp separates the phases (a warp consumes what it staged).  The cp.async brick ring, the folds and the
+// arithmetic are those of k_norm_syrk_cols; the smem line swizzle is L & 7 (phase 1 reads 8 consecutive rows of one epoch).
+// ============================================================================================
+template <int EPS>
+__global__ void __launch_bounds__(256, 1)
+    k_norm_syrk_cols2(const float *__restrict__ A, long n, int E, long n2, long T256, long c0, float *K)
+{
+    constexpr int EP = 32, MT = 2, NT = 4, CPW = 4, NTHR = 256;
+    constexpr int BRICK = 65536, PPT = BRICK / 16 / NTHR, LS = NTHR / 8;     // 16 pieces per thread, 32 lines apart
+    constexpr uint32_t STAGE_OFF = COLS_BRICKS * BRICK;                      // 8 x 4 KB fp16 staging buffers behind the bricks
+    extern __shared__ __align__(1024) uint8_t cs_raw[];
+    uint8_t *cs = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(cs_raw) + 1023) & ~uintptr_t(1023));
+    const uint32_t brick0 = smem_u32(cs);
+    float *s_fold = reinterpret_cast<float *>(cs);         // [32 columns][EP*EP] fp32 (128 KB) overlays bricks 0 and 1 at folds
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int S_eps = (E / EPS) * EPS;
+    const long nstrips = (n2 - c0 + 31) / 32;
+    const long nsteps = (n + 15) / 16;
+    // phase 1: this lane's row and epoch half
+    const int prow = lane & 15, phalf = lane >> 4;
+    const uint32_t rd_base = (uint32_t)((phalf * 16) * 16 + prow) * 128u + ((((uint32_t)warp) ^ ((uint32_t)prow & 7u)) << 4);
+    const uint32_t stage = brick0 + STAGE_OFF + (uint32_t)warp * 4096u;
+    // staged piece (column c, row, epoch block eb) lives at  c*1024 + row*64 + ((eb ^ ((row >> 1) & 3)) << 4)
+    const uint32_t st_row = stage + (uint32_t)prow * 64u;
+    const uint32_t st_swz = ((uint32_t)prow >> 1) & 3u;
+    // phase 2: ldmatrix row address of this lane: matrix (lane >> 3) = epoch block, row (lane & 7) (+8 for the second load)
+    const uint32_t lm_row = (uint32_t)lane & 7u, lm_eb = (uint32_t)lane >> 3;
+    const uint32_t lm_lo = stage + lm_row * 64u + ((lm_eb ^ ((lm_row >> 1) & 3u)) << 4);
+    const uint32_t lm_hi = stage + (lm_row + 8u) * 64u + ((lm_eb ^ (((lm_row + 8u) >> 1) & 3u)) << 4);
+
+    for (long strip = blockIdx.x; strip < nstrips; strip += gridDim.x) {
+        const long j0 = c0 + strip * 32;
+        const long tjx = j0 >> 8;
+        const int jo = (int)(j0 & 255);
+        // cp.async: thread tid copies piece w = tid & 7 of the lines (tid >> 3) + 32 k, k < 16 (row (tid >> 3) & 15 of
+        // epochs (tid >> 7) + 2 k); L & 7 is the same for all of them
+        const int pf_w = tid & 7, pf_line0 = tid >> 3, pf_row = pf_line0 & 15, pf_e0 = pf_line0 >> 4;
+        const int pf_src = pf_e0 * 65536 + pf_row * 256 + pf_w * 4 + jo;
+        const uint32_t pf_dst = brick0 + (uint32_t)pf_line0 * 128u + ((((uint32_t)pf_w) ^ ((uint32_t)pf_line0 & 7u)) << 4);
+        auto prefetch = [&](long st, int b) {
+            const long i0 = st * 16;
+            const float *src0 = A + ((size_t)((i0 >> 8) * T256 + tjx) * E) * 65536 + (size_t)(i0 & 255) * 256 + pf_src;
+            const bool row_ok = i0 + pf_row < n;
+            const uint32_t dst0 = pf_dst + (uint32_t)b * (uint32_t)BRICK;
+#pragma unroll
+            for (int k = 0; k < PPT; k++) {
+                const bool ok = row_ok && pf_e0 + 2 * k < E;
+                cp_async_16_zfill_s(dst0 + (uint32_t)(k * LS) * 128u, ok ? src0 + (size_t)k * (2 * 65536) : A, ok ? 16u : 0u);
+            }
+        };
+        for (long seg0 = 0; seg0 < nsteps; seg0 += COLS_SEG_STEPS) {
+            const long seg1 = seg0 + COLS_SEG_STEPS < nsteps ? seg0 + COLS_SEG_STEPS : nsteps;
+            float acc[CPW][MT][NT][4];
+#pragma unroll
+            for (int c = 0; c < CPW; c++)
+#pragma unroll
+                for (int a = 0; a < MT; a++)
+#pragma unroll
+                    for (int b = 0; b < NT; b++)
+#pragma unroll
+                        for (int d = 0; d < 4; d++) acc[c][a][b][d] = 0.f;
+            int buf = 0;
+            prefetch(seg0, 0);
+            cp_async_commit();
+            if (seg0 + 1 < seg1) prefetch(seg0 + 1, 1);
+            cp_async_commit();
+            for (long st = seg0; st < seg1; st++) {
+                cp_async_wait<1>();        // brick `st` has landed (this thread's copies) ...
+                __syncthreads();           // ... and everybody's; every warp is also done with brick st-1,
+                if (st + 2 < seg1) prefetch(st + 2, buf == 0 ? 2 : buf - 1);   // whose buffer takes brick st+2
+                cp_async_commit();
+                const uint32_t bb = brick0 + (uint32_t)buf * (uint32_t)BRICK + rd_base;
+                // ---- phase 1: 16 epochs x 4 columns of this lane's row, 8 epochs (one staged piece) at a time
+                float2 lo[16], hi[16];     // columns (0, 1) and (2, 3) of epoch 16*phalf + e
+#pragma unroll
+                for (int e = 0; e < 16; e++) {
+                    const uint4 q = lds128(bb + (uint32_t)e * 2048u);
+                    lo[e] = make_float2(__uint_as_float(q.x), __uint_as_float(q.y));
+                    hi[e] = make_float2(__uint_as_float(q.z), __uint_as_float(q.w));
+                }
+                auto finish = [&](float2 msum, float2 s2sum, float2 &inv, float2 &mi) {
+                    const float2 nm = ffma2(msum, splat2(-1.0f / EPS), splat2(0.f));
+                    const float2 ns2 = ffma2(s2sum, splat2(-1.0f / EPS), splat2(0.f));
+                    const float2 negvar = ffma2(nm, nm, ns2);
+                    inv.x = negvar.x >= 0.f ? 0.f : rsqrt_ftz(-negvar.x);
+                    inv.y = negvar.y >= 0.f ? 0.f : rsqrt_ftz(-negvar.y);
+                    mi = ffma2(nm, inv, splat2(0.f));
+                };
+                constexpr int SPAN = EPS < 16 ? EPS : 16;          // epochs of one subject inside this lane
+#pragma unroll
+                for (int s0 = 0; s0 < 16; s0 += SPAN) {
+                    float2 ml = splat2(0.f), mh = splat2(0.f), ql = splat2(0.f), qh = splat2(0.f);
+#pragma unroll
+                    for (int e = s0; e < s0 + SPAN; e++) {
+                        ml = fadd2(ml, lo[e]), mh = fadd2(mh, hi[e]);
+                        ql = ffma2(lo[e], lo[e], ql), qh = ffma2(hi[e], hi[e], qh);
+                    }
+                    if constexpr (EPS == 32) {       // the subject's other 16 epochs live in lane ^ 16
+                        ml.x += __shfl_xor_sync(0xffffffffu, ml.x, 16), ml.y += __shfl_xor_sync(0xffffffffu, ml.y, 16);
+                        mh.x += __shfl_xor_sync(0xffffffffu, mh.x, 16), mh.y += __shfl_xor_sync(0xffffffffu, mh.y, 16);
+                        ql.x += __shfl_xor_sync(0xffffffffu, ql.x, 16), ql.y += __shfl_xor_sync(0xffffffffu, ql.y, 16);
+                        qh.x += __shfl_xor_sync(0xffffffffu, qh.x, 16), qh.y += __shfl_xor_sync(0xffffffffu, qh.y, 16);
+                    }
+                    float2 il, cl, ih, ch;
+                    finish(ml, ql, il, cl);
+                    finish(mh, qh, ih, ch);
+                    if (16 * phalf + s0 < S_eps) {       // epochs outside a complete subject stay as they are
+#pragma unroll
+                        for (int e = s0; e < s0 + SPAN; e++) lo[e] = ffma2(lo[e], il, cl), hi[e] = ffma2(hi[e], ih, ch);
+                    }
+                }
+                // ---- stage: per column two 16-byte pieces (epochs 16*phalf .. +7 and +8 .. +15) of this lane's row
+#pragma unroll
+                for (int pc = 0; pc < 2; pc++) {
+                    const uint32_t piece = st_row + ((((uint32_t)(2 * phalf + pc)) ^ st_swz) << 4);
+                    const int e0 = 8 * pc;
+                    sts128(piece + 0 * 1024u, pack_half2_rn(lo[e0].x, lo[e0 + 1].x), pack_half2_rn(lo[e0 + 2].x, lo[e0 + 3].x),
+                           pack_half2_rn(lo[e0 + 4].x, lo[e0 + 5].x), pack_half2_rn(lo[e0 + 6].x, lo[e0 + 7].x));
+                    sts128(piece + 1 * 1024u, pack_half2_rn(lo[e0].y, lo[e0 + 1].y), pack_half2_rn(lo[e0 + 2].y, lo[e0 + 3].y),
+                           pack_half2_rn(lo[e0 + 4].y, lo[e0 + 5].y), pack_half2_rn(lo[e0 + 6].y, lo[e0 + 7].y));
+                    sts128(piece + 2 * 1024u, pack_half2_rn(hi[e0].x, hi[e0 + 1].x), pack_half2_rn(hi[e0 + 2].x, hi[e0 + 3].x),
+                           pack_half2_rn(hi[e0 + 4].x, hi[e0 + 5].x), pack_half2_rn(hi[e0 + 6].x, hi[e0 + 7].x));
+                    sts128(piece + 3 * 1024u, pack_half2_rn(hi[e0].y, hi[e0 + 1].y), pack_half2_rn(hi[e0 + 2].y, hi[e0 + 3].y),
+                           pack_half2_rn(hi[e0 + 4].y, hi[e0 + 5].y), pack_half2_rn(hi[e0 + 6].y, hi[e0 + 7].y));
+                }
+                __syncwarp();
+                // ---- phase 2: K_j += Z Z^T for the warp's four columns
+#pragma unroll
+                for (int c = 0; c < CPW; c++) {
+                    uint32_t h0[4], h1[4];      // epoch block r: rows (2t, 2t+1) / (2t+8, 2t+9) of epoch 8r + g
+                    ldmatrix_x4_trans(lm_lo + (uint32_t)c * 1024u, h0[0], h0[1], h0[2], h0[3]);
+                    ldmatrix_x4_trans(lm_hi + (uint32_t)c * 1024u, h1[0], h1[1], h1[2], h1[3]);
+#pragma unroll
+                    for (int mu = 0; mu < MT; mu++)
+#pragma unroll
+                        for (int nu = 0; nu < NT; nu++)
+                            mma_f16_16x8x16(acc[c][mu][nu], h0[2 * mu], h0[2 * mu + 1], h1[2 * mu], h1[2 * mu + 1], h0[nu], h1[nu]);
+                }
+                __syncwarp();      // the staging buffer is rewritten in the next step
+                buf = buf == COLS_BRICKS - 1 ? 0 : buf + 1;
+            }
+            // ---- fold the accumulators into K: registers -> smem [32 columns][EP*EP] -> mirrored, coalesced += on K.
+            // Natural epoch order: acc[c][mu][nu][{0,1}] = K[16 mu + g][8 nu + 2t + {0,1}], [{2,3}] = row 16 mu + g + 8.
+            cp_async_wait<0>();
+            __syncthreads();
+#pragma unroll
+            for (int c = 0; c < CPW; c++) {
+                float *dstk = s_fold + (size_t)(warp * CPW + c) * (EP * EP);
+#pragma unroll
+                for (int mu = 0; mu < MT; mu++)
+#pragma unroll
+                    for (int nu = 0; nu < NT; nu++) {
+                        const int row0 = 16 * mu + g, col0 = 8 * nu + 2 * t;
+                        *reinterpret_cast<float2 *>(&dstk[row0 * EP + col0]) = make_float2(acc[c][mu][nu][0], acc[c][mu][nu][1]);
+                        *reinterpret_cast<float2 *>(&dstk[(row0 + 8) * EP + col0]) = make_float2(acc[c][mu][nu][2], acc[c][mu][nu][3]);
+                    }
+            }
+            __syncthreads();
+            const int EE = E * E;
+            const long ncols = n2 - j0 < 32 ? n2 - j0 : 32;       // real columns of this strip
+            const int total = (int)ncols * EE;
+            float *Kst = K + (size_t)j0 * EE;                     // the strip's kernels are contiguous
+            auto folded = [&](int idx) {
+                const int col = idx / EE, rem = idx - col * EE;
+                const int a = rem / E, b = rem - a * E;
+                const float *sk = s_fold + (size_t)col * (EP * EP);
+                return a >= b ? sk[a * EP + b] : sk[b * EP + a];
+            };
+            if ((EE & 3) == 0 && ((reinterpret_cast<uintptr_t>(Kst) & 15) == 0)) {
+                float4 *K4 = reinterpret_cast<float4 *>(Kst);
+                const int total4 = total >> 2;
+                for (int base = tid; base < total4; base += NTHR * 8) {
+                    float4 old[8];
+#pragma unroll
+                    for (int u = 0; u < 8; u++) {
+                        const int i4 = base + u * NTHR;
+                        if (i4 < total4) old[u] = K4[i4];
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; u++) {
+                        const int i4 = base + u * NTHR;
+                        if (i4 < total4) {
+                            float4 o = old[u];
+                            o.x += folded(4 * i4), o.y += folded(4 * i4 + 1), o.z += folded(4 * i4 + 2), o.w += folded(4 * i4 + 3);
+                            K4[i4] = o;
+                        }
+                    }
+                }
+            } else {
+                for (int base = tid; base < total; base += NTHR * 8) {
+                    float old[8];
+#pragma unroll
+                    for (int u = 0; u < 8; u++) {
+                        const int i1 = base + u * NTHR;
+                        if (i1 < total) old[u] = Kst[i1];
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; u++) {
+                        const int i1 = base + u * NTHR;
+                        if (i1 < total) Kst[i1] = old[u] + folded(i1);
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// ============================================================================================
 // Column-direction pass, TMA version (FCMA_FLAG_COLS_TMA, needs E % 4 == 0): same arithmetic as k_norm_syrk_cols, but
 //   * a brick [32 epochs][16 rows][32 columns] arrives through ONE 5-D bulk tensor copy (UTMALDG) issued by one elected
 //     lane -- the 4096 LDGSTS per brick (8 LSU cycles each, the same port the LDS reads need) and their address
@@ -2527,7 +2754,7 @@ static int launch_norm_syrk(const float *C, long nb, int E, long n2, long stride
 // column-direction pass over a tiled fp32 block (k_norm_syrk_cols): K[j] += ... for block columns [c0, n2)
 static bool cols_supported(int E, int eps) { return E <= 32 && eps >= 1 && eps <= 32 && (eps & (eps - 1)) == 0; }
 static int launch_norm_syrk_cols(const void *A, long n, int E, long n2, long T256, long c0, int eps, float *K,
-                                 cudaStream_t st, int half_in = 0, bool use_tma = false)
+                                 cudaStream_t st, int half_in = 0, bool use_tma = false, bool v2 = false)
 {
     if (!cols_supported(E, eps) || (c0 & 31) || c0 >= n2) return fail(FCMA_EINVAL, "internal: column pass unsupported E=%d eps=%d c0=%ld", E, eps, c0);
     const long nstrips = cdiv(n2 - c0, 32);
@@ -2541,19 +2768,14 @@ static int launch_norm_syrk_cols(const void *A, long n, int E, long n2, long T25
         int rc = make_cols_map(&tmA, A, (size_t)cdiv(n, 256) * (size_t)T256, E, half_in);
         if (rc) return rc;
         const size_t smem_t = 196608 + 64 + 1024;
-        const char *tc_env = diag_env("FCMA_COLS_TMA_CPW");     // diagnostic build: 2 = 16 warps x 2 columns (A/B)
-        const bool cpw2 = tc_env && tc_env[0] == '2' && !half_in;
 #define FCMA_COLS_TMA_CASE(EPSV)                                                                                    \
     case EPSV:                                                                                                      \
         if (half_in) {                                                                                              \
             CUDA_TRY(cudaFuncSetAttribute(k_norm_syrk_cols_tma<EPSV, true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t)); \
-            k_norm_syrk_cols_tma<EPSV, true, 4><<<grid, 256, smem_t, st>>>(tmA, (int)n, E, (int)n2, (int)T256, (int)c0, K);             \
-        } else if (cpw2) {                                                                                          \
-            CUDA_TRY(cudaFuncSetAttribute(k_norm_syrk_cols_tma<EPSV, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t)); \
-            k_norm_syrk_cols_tma<EPSV, false, 2><<<grid, 512, smem_t, st>>>(tmA, (int)n, E, (int)n2, (int)T256, (int)c0, K);            \
+            k_norm_syrk_cols_tma<EPSV, true, 4><<<grid, 256, smem_t, st>>>(tmA, (int)n, E, (int)n2, (int)T256, (int)c0, K); \
         } else {                                                                                                    \
             CUDA_TRY(cudaFuncSetAttribute(k_norm_syrk_cols_tma<EPSV, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t)); \
-            k_norm_syrk_cols_tma<EPSV, false, 4><<<grid, 256, smem_t, st>>>(tmA, (int)n, E, (int)n2, (int)T256, (int)c0, K);            \
+            k_norm_syrk_cols_tma<EPSV, false, 4><<<grid, 256, smem_t, st>>>(tmA, (int)n, E, (int)n2, (int)T256, (int)c0, K); \
         }                                                                                                           \
         break;
         switch (eps) {
@@ -2567,6 +2789,30 @@ static int launch_norm_syrk_cols(const void *A, long n, int E, long n2, long T25
         }
 #undef FCMA_COLS_TMA_CASE
         LAUNCH_CHECK("k_norm_syrk_cols_tma");
+        return FCMA_OK;
+    }
+    // FCMA_FLAG_COLS_V2: thread-per-row normalisation, fp16 staging, ldmatrix fragments (k_norm_syrk_cols2, fp32 block).
+    // ~2x fewer instructions than the fragment-layout kernel below and exactly as fast inside the power-capped step
+    // (37.0-37.8 vs 36.1-36.7 ms per step, also with a 256-byte L2 prefetch hint on its loads): the column pass is
+    // bound by what it moves, not by what it issues.  Opt-in, tested.
+    if (!half_in && v2) {
+        const size_t smem2 = (size_t)COLS_BRICKS * 65536 + 32768 + 1024;
+#define FCMA_COLS2_CASE(EPSV)                                                                                       \
+    case EPSV:                                                                                                      \
+        CUDA_TRY(cudaFuncSetAttribute(k_norm_syrk_cols2<EPSV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2)); \
+        k_norm_syrk_cols2<EPSV><<<grid, 256, smem2, st>>>(reinterpret_cast<const float *>(A), n, E, n2, T256, c0, K); \
+        break;
+        switch (eps) {
+            FCMA_COLS2_CASE(1)
+            FCMA_COLS2_CASE(2)
+            FCMA_COLS2_CASE(4)
+            FCMA_COLS2_CASE(8)
+            FCMA_COLS2_CASE(16)
+            FCMA_COLS2_CASE(32)
+        default: return fail(FCMA_EINVAL, "internal: no k_norm_syrk_cols2 instantiation for eps=%d", eps);
+        }
+#undef FCMA_COLS2_CASE
+        LAUNCH_CHECK("k_norm_syrk_cols2");
         return FCMA_OK;
     }
     // bricks (3 x 64 KB fp32 / 3 x 32 KB fp16); the fold buffer [32 columns][32*32] fp32 = 128 KB overlays them
@@ -2959,7 +3205,7 @@ static int run_pipeline_sym(const void *op, int precision, int E, int T, long V,
         if (g_timing_on) CUDA_TRY(cudaEventRecord(ev[3], st));
         if (rowsB > 0 && use_cols) {
             rc = launch_norm_syrk_cols(A, n, E, colsA, t256, n, eps, K + (size_t)a * E * E, st, half16 ? 1 : 0,
-                                       (flags & FCMA_FLAG_COLS_TMA) != 0);
+                                       (flags & FCMA_FLAG_COLS_TMA) != 0, (flags & FCMA_FLAG_COLS_V2) != 0);
             if (rc) return rc;
         } else if (rowsB > 0) {
             rc = launch_norm_syrk(B, rowsB, E, n, 256, 65536, eps, 1, -1, 1.0f, K + (size_t)(a + n) * E * E, 0, st,

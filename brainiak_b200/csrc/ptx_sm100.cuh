@@ -234,6 +234,12 @@ __device__ __forceinline__ void cp_async_16_zfill_s(uint32_t smem_dst, const voi
 {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gsrc), "r"(src_bytes) : "memory");
 }
+// same with a 256-byte L2 prefetch hint: the miss also brings the other 128-byte half of the 256-byte granule into L2
+// (the column pass reads 128-byte lines 1 KB apart; the neighbouring strip's CTA wants the other half at about the same time)
+__device__ __forceinline__ void cp_async_16_zfill_s_l2_256(uint32_t smem_dst, const void *gsrc, uint32_t src_bytes)
+{
+    asm volatile("cp.async.cg.shared.global.L2::256B [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gsrc), "r"(src_bytes) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit()
 {
     asm volatile("cp.async.commit_group;" ::: "memory");
@@ -304,6 +310,27 @@ __device__ __forceinline__ void tma_store_wait_all()
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
+// four 8x8 b16 matrices, transposed on the way: lane l supplies the address of row (l % 8) of matrix (l / 8); register k
+// of lane (g = l / 4, t = l % 4) receives elements [2t][g], [2t+1][g] of matrix k as a half2
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t saddr, uint32_t &r0, uint32_t &r1, uint32_t &r2, uint32_t &r3)
+{
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+                 : "r"(saddr)
+                 : "memory");
+}
+// packed fp32x2 add
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b)
+{
+    float2 d;
+    asm("{\n\t.reg .b64 ra, rb, rd;\n\t"
+        "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+        "add.rn.f32x2 rd, ra, rb;\n\t"
+        "mov.b64 {%0, %1}, rd;\n\t}"
+        : "=f"(d.x), "=f"(d.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+}
 __device__ __forceinline__ uint2 lds64(uint32_t saddr)
 {
     uint2 r;

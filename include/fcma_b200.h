@@ -67,6 +67,9 @@ extern "C" {
 #define FCMA_FLAG_COLS_TMA       32   /* column-direction pass fed by 5-D TMA bricks + an mbarrier ring instead of cp.async +
                                          block barriers (needs E % 4 == 0; measured 5-8 % slower inside the power-capped
                                          step, profiles/README.md, so it is not the default)                          */
+#define FCMA_FLAG_COLS_V2        64   /* column-direction pass of the fp32 block, version 2: thread-per-row normalisation
+                                         (no shuffles), fp16 staging, ldmatrix fragments -- half the instructions, the
+                                         same time inside the power-capped step (profiles/README.md), not the default   */
 
 int         fcma_version(void);
 const char *fcma_last_error(void);

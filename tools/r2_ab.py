@@ -11,7 +11,7 @@ from brainiak_b200.fcma import engine
 lib = _lib.load()
 V = int(sys.argv[1]) if len(sys.argv) > 1 else 50000
 T, E, eps, rows = 200, 32, 8, 4096
-default = ["base:0:", "cols_tma:%d:" % _lib.FLAG_COLS_TMA, "gemm_tma_transposed:0:FCMA_GEMM_DEBUG=128",
+default = ["base:0:", "cols_v2:%d:" % _lib.FLAG_COLS_V2, "cols_tma:%d:" % _lib.FLAG_COLS_TMA, "gemm_tma_transposed:0:FCMA_GEMM_DEBUG=128",
            "gemm_no_epilogue:0:FCMA_GEMM_DEBUG=4", "f16_block:%d:" % _lib.FLAG_F16_INTERMEDIATE]
 variants = []
 for a in (sys.argv[2:] or default):

@@ -16,7 +16,8 @@ rows it would cross-validate (voxelselector.py's row partition).  Total work is 
 
 `e2e` is the same metric from HOST buffers to HOST buffers, unpipelined, every copy inside the timed region:
   N = 1: one call of the C-ABI host entry point fcma_host_voxel_kernels_sym per step (pinned host epochs in, pinned host
-         kernels out: H2D, packing, kernels, D2H);
+         kernels out: H2D, packing, kernels, D2H -- synchronous; inside the call the first pass' GEMM follows the upload
+         epoch group by epoch group and a pass' kernels are read back under the next pass);
   N > 1: per step every rank uploads ITS share of the epochs (E/N of them) over its own PCIe link, the shares are
          all-gathered over NVLink by the copy engines (CUDA IPC; brainiak_b200/fcma/exchange.py), then pack, kernels,
          reduce-scatter and the read-back of the rank's own kernel rows.

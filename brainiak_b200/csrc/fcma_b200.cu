@@ -224,12 +224,12 @@ __device__ __forceinline__ float tf32_rn(float x)
 template <int KIND, int PLANES>
 __global__ void __launch_bounds__(256) k_pack_operand(const float *__restrict__ src, int E, int T, long V, long ld,
                                                       const int *__restrict__ T_e, int normalize, void *dst, int Kp,
-                                                      float *__restrict__ selfdiag, float in_scale, long v_begin, long v_end)
+                                                      float *__restrict__ selfdiag, float in_scale, long v_begin, long v_end, int e_begin)
 {
     __shared__ double s_red[8][33];
     __shared__ float s_mean[32], s_scale[32];
     __shared__ float s_tile[32][65];
-    const int e = blockIdx.y;
+    const int e = e_begin + blockIdx.y;          // grid.y = epochs packed by this launch
     const long v0 = v_begin + (long)blockIdx.x * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int Te = T_e ? T_e[e] : T;
@@ -497,6 +497,7 @@ struct Gemm2Params {
                                    // 8, 16 or 32: voxel rows i per LDS/STG transposition step (buffer = 32 x (tr_w + pad))
     uint32_t tr_warp_bytes;        // bytes of one warp's transposition buffer
     uint32_t bar_off;              // smem offset of the mbarriers
+    int e_begin;                   // first epoch of this launch (the tile loop covers epochs [e_begin, e_begin + total_tiles / tiles per epoch))
     int tma_norm;                  // 1 (opt-in, A/B): the normal copy of a chunk also leaves through the staging buffer + a TMA
                                    // bulk store (symmetric mode with tr_w == 0)
 };
@@ -864,8 +865,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_MAX_THREADS, 1)
             const uint64_t l2pol = l2_policy_evict_last();
             for (long grp = pair; grp < ngroups; grp += npairs)
             for (long tile = grp * p.grp_tiles; tile < (grp + 1) * p.grp_tiles; tile++) {
-                const int e = (int)(tile / tiles_per_e);
-                const long rem = tile - (long)e * tiles_per_e;
+                const int el = (int)(tile / tiles_per_e);          // epoch index inside this launch's range
+                const int e = p.e_begin + el;
+                const long rem = tile - (long)el * tiles_per_e;
                 const int tj = (int)(rem / p.tiles_i);
                 const int ti = (int)(rem - (long)tj * p.tiles_i);
                 if (p.sym_diag && tj < ti) continue;   // symmetric mode: tile (tj, ti) is mirrored from (ti, tj)
@@ -951,8 +953,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_MAX_THREADS, 1)
         const uint32_t tr_buf = smem_u32(smem + p.tr_off);
         for (long grp = pair; grp < ngroups; grp += npairs)
         for (long tile = grp * p.grp_tiles; tile < (grp + 1) * p.grp_tiles; tile++) {
-            const int e = (int)(tile / tiles_per_e);
-            const long rem = tile - (long)e * tiles_per_e;
+            const int el = (int)(tile / tiles_per_e);          // epoch index inside this launch's range
+            const int e = p.e_begin + el;
+            const long rem = tile - (long)el * tiles_per_e;
             const int tj = (int)(rem / p.tiles_i);
             const int ti = (int)(rem - (long)tj * p.tiles_i);
             if (p.sym_diag && tj < ti) continue;
@@ -1083,7 +1086,8 @@ struct SymOut {
 };
 static int launch_corr_umma(const void *rows_op, const void *cols_op, int precision, int E, int T, long V, long V2,
                             long start, long nb, float *out, long stride_i, long stride_e, int fisher_epochs,
-                            cudaStream_t st, long tiled_t256 = 0, int half_out = 0, const SymOut *sym = nullptr)
+                            cudaStream_t st, long tiled_t256 = 0, int half_out = 0, const SymOut *sym = nullptr,
+                            int e_begin = 0, int e_count = -1, bool fixup = true)
 {
     PrecInfo pi;
     if (!prec_info(precision, &pi)) return fail(FCMA_EINVAL, "unknown precision %d", precision);
@@ -1111,7 +1115,10 @@ static int launch_corr_umma(const void *rows_op, const void *cols_op, int precis
         q.t_tj0 = q.tiles_i;
         q.out_t = q.tiles_j > q.tiles_i ? sym->out_t : nullptr;
     }
-    q.total_tiles = (long)q.tiles_j * q.tiles_i * E;
+    if (e_count < 0) e_count = E - e_begin;
+    if (e_begin < 0 || e_count <= 0 || e_begin + e_count > E) return fail(FCMA_EINVAL, "internal: bad epoch range [%d, +%d) of %d", e_begin, e_count, E);
+    q.e_begin = e_begin;
+    q.total_tiles = (long)q.tiles_j * q.tiles_i * e_count;
     q.out = out, q.stride_i = stride_i, q.stride_e = stride_e, q.fisher_epochs = fisher_epochs;
     q.fmt = pi.fmt, q.out_scale = 1.0f / (pi.in_scale * pi.in_scale);
     q.half_bytes = (uint32_t)(q.BN / 2) * 128;
@@ -1201,7 +1208,7 @@ static int launch_corr_umma(const void *rows_op, const void *cols_op, int precis
 #undef FCMA_LAUNCH_GEMM
     LAUNCH_CHECK("k_corr_umma2");
 
-    if (rows_op == cols_op && V == V2) {
+    if (rows_op == cols_op && V == V2 && fixup) {
         // self-correlation: replace the diagonal by the reference-exact values kept with the operand
         const float *sd = reinterpret_cast<const float *>(reinterpret_cast<const uint8_t *>(rows_op) +
                                                           operand_plane_bytes(pi, precision, E, T, V));
@@ -2857,9 +2864,19 @@ extern "C" int fcma_pack_operand(const float *epochs_dev, int E, int T, long V, 
     return fcma_pack_operand_range(epochs_dev, E, T, V, ld, T_e, normalize, precision, 0, V, packed_dev, packed_bytes, stream);
 }
 
+static int pack_operand_impl(const float *epochs_dev, int E, int T, long V, long ld, const int *T_e, int normalize,
+                             int precision, long v_begin, long v_end, int e_begin, int e_count, void *packed_dev,
+                             size_t packed_bytes, void *stream);
 extern "C" int fcma_pack_operand_range(const float *epochs_dev, int E, int T, long V, long ld, const int *T_e, int normalize,
                                        int precision, long v_begin, long v_end, void *packed_dev, size_t packed_bytes,
                                        void *stream)
+{
+    return pack_operand_impl(epochs_dev, E, T, V, ld, T_e, normalize, precision, v_begin, v_end, 0, E, packed_dev, packed_bytes, stream);
+}
+// voxels [v_begin, v_end) of epochs [e_begin, e_begin + e_count)
+static int pack_operand_impl(const float *epochs_dev, int E, int T, long V, long ld, const int *T_e, int normalize,
+                             int precision, long v_begin, long v_end, int e_begin, int e_count, void *packed_dev,
+                             size_t packed_bytes, void *stream)
 {
     int rc = check_device();
     if (rc) return rc;
@@ -2869,6 +2886,7 @@ extern "C" int fcma_pack_operand_range(const float *epochs_dev, int E, int T, lo
         return fail(FCMA_EINVAL, "fcma_pack_operand: bad arguments E=%d T=%d V=%ld ld=%ld", E, T, V, ld);
     if (v_begin < 0 || v_end > V || v_begin >= v_end)
         return fail(FCMA_EINVAL, "fcma_pack_operand_range: voxels [%ld, %ld) outside [0, %ld)", v_begin, v_end, V);
+    if (e_begin < 0 || e_count <= 0 || e_begin + e_count > E) return fail(FCMA_EINVAL, "internal: bad epoch range for packing");
     size_t need = fcma_operand_bytes(precision, E, T, V);
     if (packed_bytes < need) return fail(FCMA_ENOMEM, "packed operand buffer too small: %zu < %zu", packed_bytes, need);
     cudaStream_t st = (cudaStream_t)stream;
@@ -2883,12 +2901,12 @@ extern "C" int fcma_pack_operand_range(const float *epochs_dev, int E, int T, lo
     }
     const int Kp = fcma_operand_kp(precision, T);
     float *sd = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(packed_dev) + operand_plane_bytes(pi, precision, E, T, V));
-    dim3 grid((unsigned)cdiv(v_end - v_begin, 32), (unsigned)E);
-    if (pi.pack == 0 && pi.planes == 1) k_pack_operand<0, 1><<<grid, 256, 0, st>>>(epochs_dev, E, T, V, ld, d_Te, normalize, packed_dev, Kp, sd, pi.in_scale, v_begin, v_end);
-    if (pi.pack == 0 && pi.planes == 2) k_pack_operand<0, 2><<<grid, 256, 0, st>>>(epochs_dev, E, T, V, ld, d_Te, normalize, packed_dev, Kp, sd, pi.in_scale, v_begin, v_end);
-    if (pi.pack == 1 && pi.planes == 1) k_pack_operand<1, 1><<<grid, 256, 0, st>>>(epochs_dev, E, T, V, ld, d_Te, normalize, packed_dev, Kp, sd, pi.in_scale, v_begin, v_end);
-    if (pi.pack == 1 && pi.planes == 2) k_pack_operand<1, 2><<<grid, 256, 0, st>>>(epochs_dev, E, T, V, ld, d_Te, normalize, packed_dev, Kp, sd, pi.in_scale, v_begin, v_end);
-    if (pi.pack == 2 && pi.planes == 2) k_pack_operand<2, 2><<<grid, 256, 0, st>>>(epochs_dev, E, T, V, ld, d_Te, normalize, packed_dev, Kp, sd, pi.in_scale, v_begin, v_end);
+    dim3 grid((unsigned)cdiv(v_end - v_begin, 32), (unsigned)e_count);
+    if (pi.pack == 0 && pi.planes == 1) k_pack_operand<0, 1><<<grid, 256, 0, st>>>(epochs_dev, E, T, V, ld, d_Te, normalize, packed_dev, Kp, sd, pi.in_scale, v_begin, v_end, e_begin);
+    if (pi.pack == 0 && pi.planes == 2) k_pack_operand<0, 2><<<grid, 256, 0, st>>>(epochs_dev, E, T, V, ld, d_Te, normalize, packed_dev, Kp, sd, pi.in_scale, v_begin, v_end, e_begin);
+    if (pi.pack == 1 && pi.planes == 1) k_pack_operand<1, 1><<<grid, 256, 0, st>>>(epochs_dev, E, T, V, ld, d_Te, normalize, packed_dev, Kp, sd, pi.in_scale, v_begin, v_end, e_begin);
+    if (pi.pack == 1 && pi.planes == 2) k_pack_operand<1, 2><<<grid, 256, 0, st>>>(epochs_dev, E, T, V, ld, d_Te, normalize, packed_dev, Kp, sd, pi.in_scale, v_begin, v_end, e_begin);
+    if (pi.pack == 2 && pi.planes == 2) k_pack_operand<2, 2><<<grid, 256, 0, st>>>(epochs_dev, E, T, V, ld, d_Te, normalize, packed_dev, Kp, sd, pi.in_scale, v_begin, v_end, e_begin);
     LAUNCH_CHECK("k_pack_operand");
     return FCMA_OK;   // te_buf is released in stream order by its destructor
 }
@@ -3154,8 +3172,20 @@ extern "C" int fcma_sym_uses_column_pass(int precision, int E, int eps, int flag
     return sym_uses_cols(precision, E, eps, flags) ? 1 : 0;
 }
 
+// Hooks of the host-buffer entry point (fcma_host_voxel_kernels_sym): the first pass' GEMM runs epoch group by epoch group
+// as the groups arrive from the host (a GEMM tile needs only its own epoch), and the kernels of a pass are read back while the
+// next pass computes (K rows [a, a+n) are final once the pass' row kernel has run).
+struct SymHostHooks {
+    int ngroups = 0;
+    const int *e0 = nullptr, *cnt = nullptr;                  // epoch groups of the upload
+    int (*prepare)(void *ctx, int g, cudaStream_t st) = nullptr;   // make group g's packed operand available on `st`
+    void *ctx = nullptr;
+    cudaStream_t copy = nullptr;                              // read-back stream
+    float *K_host = nullptr;
+};
+
 static int run_pipeline_sym(const void *op, int precision, int E, int T, long V, long start, long nb, int eps, int flags,
-                            float *work, size_t work_bytes, float *K, cudaStream_t st)
+                            float *work, size_t work_bytes, float *K, cudaStream_t st, const SymHostHooks *hooks = nullptr)
 {
     if (!op || !work || !K) return fail(FCMA_EINVAL, "pipeline: null pointer");
     if (nb <= 0 || start < 0 || start + nb > V) return fail(FCMA_EINVAL, "pipeline: rows [%ld, %ld) outside [0, %ld)", start, start + nb, V);
@@ -3196,13 +3226,33 @@ static int run_pipeline_sym(const void *op, int precision, int E, int T, long V,
             CUDA_TRY(cudaEventRecord(ev[0], st));
         }
         SymOut so{use_cols ? nullptr : B};
-        int rc = launch_corr_umma(op, op, precision, E, T, V, V, a, n, A, 4, 4, S_eps, st, t256, half16 ? 1 : 0, &so);
+        int rc = FCMA_OK;
+        if (hooks && hooks->ngroups > 0 && done == 0) {
+            // first pass from host buffers: one GEMM launch per uploaded epoch group, the diagonal fix-up after the last
+            for (int gi = 0; gi < hooks->ngroups && !rc; gi++) {
+                rc = hooks->prepare(hooks->ctx, gi, st);
+                if (!rc)
+                    rc = launch_corr_umma(op, op, precision, E, T, V, V, a, n, A, 4, 4, S_eps, st, t256, half16 ? 1 : 0, &so,
+                                          hooks->e0[gi], hooks->cnt[gi], gi == hooks->ngroups - 1);
+            }
+        } else {
+            rc = launch_corr_umma(op, op, precision, E, T, V, V, a, n, A, 4, 4, S_eps, st, t256, half16 ? 1 : 0, &so);
+        }
         if (rc) return rc;
         if (g_timing_on) CUDA_TRY(cudaEventRecord(ev[1], st));
         rc = launch_norm_syrk(A, n, E, colsA, 256, 65536, eps, 1, mask_self ? 0 : -1, 1.0f, K + (size_t)a * E * E, 0, st,
                               (long)E * 65536, half16 ? 1 : 0);
         if (rc) return rc;
         if (g_timing_on) CUDA_TRY(cudaEventRecord(ev[3], st));
+        if (hooks && hooks->K_host) {
+            // rows [a, a+n) of K are final now (the columns left of this pass arrived through earlier column passes)
+            EventSet<1> rowdone;
+            CUDA_TRY(rowdone.create());
+            CUDA_TRY(cudaEventRecord(rowdone.ev[0], st));
+            CUDA_TRY(cudaStreamWaitEvent(hooks->copy, rowdone.ev[0], 0));
+            CUDA_TRY(cudaMemcpyAsync(hooks->K_host + (size_t)a * E * E, K + (size_t)a * E * E, (size_t)n * E * E * sizeof(float),
+                                     cudaMemcpyDeviceToHost, hooks->copy));
+        }
         if (rowsB > 0 && use_cols) {
             rc = launch_norm_syrk_cols(A, n, E, colsA, t256, n, eps, K + (size_t)a * E * E, st, half16 ? 1 : 0,
                                        (flags & FCMA_FLAG_COLS_TMA) != 0, (flags & FCMA_FLAG_COLS_V2) != 0);
@@ -3699,8 +3749,29 @@ extern "C" int fcma_host_voxel_kernels(const float *const *raw_host, const float
 
 // Single-mask worker loop from HOST buffers (what a ctypes / cgo binding of the reference's VoxelSelector would call when
 // raw_data2 is None): H2D of the E epochs, packing, fcma_voxel_kernels_sym over all V rows, D2H of the [V][E][E] kernels,
-// synchronously on `device`.  Device buffers come from the device's default stream-ordered pool, whose release threshold is
-// raised once so that repeated calls reuse the memory instead of going back to the OS.
+// synchronously on `device`.  The copies overlap the kernels where the data flow allows it: the epochs go up in four
+// groups and the first pass' GEMM follows group by group; the kernels of a pass are read back while the next pass runs.
+// Device buffers come from the device's default stream-ordered pool, whose release threshold is raised once so that
+// repeated calls reuse the memory instead of going back to the OS.
+struct HostSymCtx {
+    const float *epochs;
+    int E, T;
+    long V;
+    const int *T_e;          // nullptr unless ragged
+    int normalize, precision;
+    void *op;
+    size_t opb;
+    const int *e0, *cnt;
+    cudaEvent_t *landed;     // per group: its epochs are in HBM (recorded on the upload stream)
+};
+static int host_sym_prepare(void *vctx, int g, cudaStream_t st)
+{
+    HostSymCtx *c = static_cast<HostSymCtx *>(vctx);
+    CUDA_TRY(cudaStreamWaitEvent(st, c->landed[g], 0));
+    return pack_operand_impl(c->epochs, c->E, c->T, c->V, c->V, c->T_e, c->normalize, c->precision, 0, c->V, c->e0[g],
+                             c->cnt[g], c->op, c->opb, st);
+}
+
 extern "C" int fcma_host_voxel_kernels_sym(const float *const *raw_host, const int *T_e, int E, long V, int eps,
                                            int precision, int normalize, int flags, int device, long rows_per_pass,
                                            float *K_host)
@@ -3726,37 +3797,82 @@ extern "C" int fcma_host_voxel_kernels_sym(const float *const *raw_host, const i
             }
             cudaGetLastError();
         });
-    cudaStream_t st = 0;
+    // two private streams: uploads / read-backs run beside the kernels (pinned host buffers make them asynchronous DMA)
+    struct Streams {
+        cudaStream_t main = nullptr, copy = nullptr;
+        ~Streams()
+        {
+            if (main) cudaStreamDestroy(main);
+            if (copy) cudaStreamDestroy(copy);
+        }
+    } ss;
+    CUDA_TRY(cudaStreamCreateWithFlags(&ss.main, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&ss.copy, cudaStreamNonBlocking));
+    cudaStream_t st = ss.main;
     const size_t opb = fcma_operand_bytes(precision, E, T, V);
     if (!opb) return fail(FCMA_EINVAL, "unknown precision %d", precision);
-    AsyncBuf epochs, op, work, K;
     const size_t ep_bytes = (size_t)E * T * V * sizeof(float), k_bytes = (size_t)V * E * E * sizeof(float);
-    CUDA_TRY(epochs.alloc(ep_bytes, st));
-    bool ragged = false;
-    for (int e = 0; e < E; e++) ragged = ragged || T_e[e] != T;
-    if (ragged) CUDA_TRY(cudaMemsetAsync(epochs.p, 0, ep_bytes, st));
-    for (int e = 0; e < E; e++)
-        CUDA_TRY(cudaMemcpyAsync((float *)epochs.p + (size_t)e * T * V, raw_host[e], (size_t)T_e[e] * V * sizeof(float),
-                                 cudaMemcpyHostToDevice, st));
-    CUDA_TRY(op.alloc(opb, st));
-    rc = fcma_pack_operand((const float *)epochs.p, E, T, V, V, ragged ? T_e : nullptr, normalize, precision, op.p, opb, st);
-    if (rc) return rc;
     const size_t per_row = (sym_uses_cols(precision, E, eps, flags) ? 1 : 2) * fcma_work_bytes_per_row(E, V);
     size_t freeb = 0, totalb = 0;
     CUDA_TRY(cudaMemGetInfo(&freeb, &totalb));
+    {
+        // buffers of a previous call are cached in the pool: reusable, although cudaMemGetInfo counts them as used
+        cudaMemPool_t pool;
+        uint64_t reserved = 0, used = 0;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess &&
+            cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved) == cudaSuccess &&
+            cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used) == cudaSuccess && reserved > used)
+            freeb += (size_t)(reserved - used);
+        cudaGetLastError();
+    }
     long rows = rows_per_pass > 0 ? rows_per_pass : 4096;
-    const long fit = (long)((freeb / 2) / per_row);
+    const size_t fixed = ep_bytes + opb + k_bytes + ((size_t)1 << 30);
+    const long fit = freeb > fixed ? (long)((freeb - fixed) / per_row) : 0;
     if (rows > fit) rows = fit;
     if (rows > round_up(V, 256)) rows = round_up(V, 256);
     rows = rows / 256 * 256;
     if (rows < 256) return fail(FCMA_ENOMEM, "not enough device memory for a 256-row correlation block (%zu bytes per row)", per_row);
-    CUDA_TRY(work.alloc(per_row * rows, st));
-    CUDA_TRY(K.alloc(k_bytes, st));
-    CUDA_TRY(cudaMemsetAsync(K.p, 0, k_bytes, st));
-    rc = run_pipeline_sym(op.p, precision, E, T, V, 0, V, eps, flags, (float *)work.p, per_row * rows, (float *)K.p, st);
-    if (rc) return rc;
-    CUDA_TRY(cudaMemcpyAsync(K_host, K.p, k_bytes, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
+    int rc_run = FCMA_OK;
+    {
+        AsyncBuf epochs, op, work, K;       // released in stream order on `st` when this scope ends
+        CUDA_TRY(epochs.alloc(ep_bytes, st));
+        CUDA_TRY(op.alloc(opb, st));
+        CUDA_TRY(work.alloc(per_row * rows, st));
+        CUDA_TRY(K.alloc(k_bytes, st));
+        CUDA_TRY(cudaMemsetAsync(K.p, 0, k_bytes, st));
+        bool ragged = false;
+        for (int e = 0; e < E; e++) ragged = ragged || T_e[e] != T;
+        if (ragged) CUDA_TRY(cudaMemsetAsync(epochs.p, 0, ep_bytes, st));
+        // upload in up to 4 epoch groups on the copy stream; the first pass' GEMM follows group by group
+        EventSet<1> alloc_done;
+        CUDA_TRY(alloc_done.create());
+        CUDA_TRY(cudaEventRecord(alloc_done.ev[0], st));
+        CUDA_TRY(cudaStreamWaitEvent(ss.copy, alloc_done.ev[0], 0));
+        constexpr int MAXG = 4;
+        const int ng = E >= MAXG ? MAXG : 1;
+        int e0[MAXG], cnt[MAXG];
+        EventSet<MAXG> landed;
+        CUDA_TRY(landed.create());
+        for (int gi = 0, e = 0; gi < ng; gi++) {
+            e0[gi] = e;
+            cnt[gi] = (E - e) / (ng - gi);
+            for (int k = 0; k < cnt[gi]; k++, e++)
+                CUDA_TRY(cudaMemcpyAsync((float *)epochs.p + (size_t)e * T * V, raw_host[e], (size_t)T_e[e] * V * sizeof(float),
+                                         cudaMemcpyHostToDevice, ss.copy));
+            CUDA_TRY(cudaEventRecord(landed.ev[gi], ss.copy));
+        }
+        HostSymCtx ctx{(const float *)epochs.p, E, T, V, ragged ? T_e : nullptr, normalize, precision, op.p, opb, e0, cnt, landed.ev};
+        SymHostHooks hooks;
+        hooks.ngroups = ng, hooks.e0 = e0, hooks.cnt = cnt, hooks.prepare = host_sym_prepare, hooks.ctx = &ctx;
+        hooks.copy = ss.copy, hooks.K_host = K_host;
+        rc_run = run_pipeline_sym(op.p, precision, E, T, V, 0, V, eps, flags, (float *)work.p, per_row * rows, (float *)K.p, st, &hooks);
+        // everything enqueued so far must finish before the buffers go back to the pool and the function returns
+        cudaError_t e1 = cudaStreamSynchronize(st), e2 = cudaStreamSynchronize(ss.copy);
+        if (!rc_run && (e1 != cudaSuccess || e2 != cudaSuccess))
+            rc_run = fail(FCMA_ECUDA, "fcma_host_voxel_kernels_sym: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+    }
+    if (rc_run) return rc_run;
+    CUDA_TRY(cudaStreamSynchronize(st));      // the stream-ordered frees
     return FCMA_OK;
 }
 

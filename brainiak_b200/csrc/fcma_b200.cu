@@ -1467,7 +1467,7 @@ constexpr bool F16_MMA = true;
 constexpr bool F16_MMA = false;
 #endif
 template <int R, int EPS, bool FISHER, int VEC>
-__global__ void __launch_bounds__(256, (R == 4 ? 2 : 1))
+__global__ void __launch_bounds__(256, (R <= 4 ? 2 : 1))
     k_norm_syrk(const float *__restrict__ C, long nb, int E, long n2, long stride_i, long ld, long chunk_step,
                 long self_col0, float beta, float *K, int sum_over_rows)
 {
@@ -1476,7 +1476,7 @@ __global__ void __launch_bounds__(256, (R == 4 ? 2 : 1))
     __shared__ float s_K[EP * EP];
     extern __shared__ __align__(16) uint8_t dyn_smem[];
     float4 *s_stage = reinterpret_cast<float4 *>(dyn_smem);  // VEC only: [warp][buf][copy][lane]
-    // R == 4 only: per-warp fp32 partial kernels [8][EP*EP].  The warp MMA adds into its accumulator
+    // R <= 4 only: per-warp fp32 partial kernels [8][EP*EP].  The warp MMA adds into its accumulator
     // with truncation, so a long chain at growing magnitude biases the sums (measured 5e-5 relative on
     // the diagonal at V2 = 50 000); flushing the MMA accumulators into these round-to-nearest partials
     // every FLUSH chunks bounds the chain length (bias ~1e-6).  Every (row, col) has exactly one owner lane.
@@ -1545,7 +1545,7 @@ __global__ void __launch_bounds__(256, (R == 4 ? 2 : 1))
             const int q = col / R, nu = col % R, tt = q >> 1, cl = q & 1;
             return ((mu * NT + nu) * 4 + (ch * 2 + cl)) * 32 + 4 * gg + tt;
         };
-        if constexpr (R == 4) {
+        if constexpr (R <= 4) {
             float *part = s_part + warp * (EP * EP);
             for (int idx = lane; idx < EP * EP; idx += 32) part[idx] = 0.f;
             __syncwarp();
@@ -1804,7 +1804,7 @@ __global__ void __launch_bounds__(256, (R == 4 ? 2 : 1))
                                             tv[nu][h][2 * w + 1]);
             }
             }  // ch < nchunks
-            if constexpr (R == 4) {
+            if constexpr (R <= 4) {
                 if (++since_flush == FLUSH) {
                     flush();
                     since_flush = 0;
@@ -1822,7 +1822,7 @@ __global__ void __launch_bounds__(256, (R == 4 ? 2 : 1))
         }
 
         // ---- deterministic cross-warp reduction into s_K (epoch order restored)
-        if constexpr (R == 4) {
+        if constexpr (R <= 4) {
             flush();
             __syncthreads();
             for (int idx = threadIdx.x; idx < EP * EP; idx += 256) {
@@ -1839,7 +1839,7 @@ __global__ void __launch_bounds__(256, (R == 4 ? 2 : 1))
         // ---- write: symmetric by construction from the lower triangle (cython_blas.pyx:200-207)
         auto kval = [&](int idx) {
             const int a = idx / E, b = idx - a * E;
-            if constexpr (R == 4)
+            if constexpr (R <= 4)
                 return a >= b ? s_K[a * EP + b] : s_K[b * EP + a];
             else
                 return a >= b ? s_K[frag_index(a, b)] : s_K[frag_index(b, a)];
@@ -2671,7 +2671,7 @@ static bool dispatch_eps(int eps, dim3 grid, cudaStream_t st, const float *C, lo
                          long ld, long chunk_step, long self_col0, float beta, float *K, int sum)
 {
     constexpr size_t smem = (VEC ? (size_t)8 * 2 * (VEC == 2 ? R : 2 * R) * 32 * sizeof(float4) : 0) +
-                            (R == 4 ? (size_t)8 * (8 * R) * (8 * R) * sizeof(float) : 0);
+                            (R <= 4 ? (size_t)8 * (8 * R) * (8 * R) * sizeof(float) : 0);
 #define FCMA_CASE(EPSV)                                                                                          \
     case EPSV:                                                                                                   \
         if (smem > 48 * 1024)                                                                                    \
@@ -2686,7 +2686,14 @@ static bool dispatch_eps(int eps, dim3 grid, cudaStream_t st, const float *C, lo
         FCMA_CASE(4)
         FCMA_CASE(8)
         FCMA_CASE(16)
-        FCMA_CASE(32)
+    case 32:
+        if constexpr (R >= 4) {      // R = 2 (E <= 16): a subject never spans 32 epochs
+            if (smem > 48 * 1024)
+                cudaFuncSetAttribute(k_norm_syrk<R, 32, FISHER, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            k_norm_syrk<R, 32, FISHER, VEC><<<grid, 256, smem, st>>>(C, nb, E, n2, stride_i, ld, chunk_step, self_col0, beta, K, sum);
+            return true;
+        }
+        return false;
     case 64:
         if constexpr (R == 8) {
             if (smem > 48 * 1024)
@@ -2737,7 +2744,11 @@ static int launch_norm_syrk(const float *C, long nb, int E, long n2, long stride
     bool ok;
 #define FCMA_DISPATCH(RR, FI, VV) \
     dispatch_eps<RR, FI, VV>(eps_mode, grid, st, C, nb, E, n2, stride_i, ld, chunk_step, self_col0, beta, K, sum_over_rows)
-    if (E <= 32) {
+    if (E <= 16 && eps_mode <= 16 && !half_in && !fisher && vec) {
+        // 16 padded epochs instead of 32 (lane = 2 epochs): half the statistics and MMA work per byte of the pipelines'
+        // fp32 block (BASELINE configs[1]: E = 16)
+        ok = FCMA_DISPATCH(2, false, 1);
+    } else if (E <= 32) {
         if (half_in)
             ok = FCMA_DISPATCH(4, false, 2);
         else if (fisher)

@@ -3193,6 +3193,7 @@ struct SymHostHooks {
     void *ctx = nullptr;
     cudaStream_t copy = nullptr;                              // read-back stream
     float *K_host = nullptr;
+    bool two_buffers = false;                                 // `work` may be split in two blocks: two passes follow the upload
 };
 
 static int run_pipeline_sym(const void *op, int precision, int E, int T, long V, long start, long nb, int eps, int flags,
@@ -3218,61 +3219,88 @@ static int run_pipeline_sym(const void *op, int precision, int E, int T, long V,
     const bool use_cols = sym_uses_cols(precision, E, eps, flags);
     // per block row: A needs E * round_up(V - a, 256) floats; with a transposed block B at most the same again
     const size_t row_bytes = (use_cols ? 1 : 2) * fcma_work_bytes_per_row(E, V - start);
-    long rows_per_pass = (long)(work_bytes / row_bytes) & ~255L;
+    // host-buffer mode with room for two blocks: the first TWO passes' GEMMs follow the upload group by group
+    const bool grouped = hooks && hooks->ngroups > 0;
+    const bool two = grouped && hooks->two_buffers && work_bytes / 2 / row_bytes >= 256;
+    const size_t buf_bytes = two ? (work_bytes / 2) & ~(size_t)255 : work_bytes;
+    long rows_per_pass = (long)(buf_bytes / row_bytes) & ~255L;
     if (rows_per_pass < 256)
         return fail(FCMA_ENOMEM, "work buffer too small for the symmetric pipeline: %zu bytes < %zu (256 rows)", work_bytes, 256 * row_bytes);
-    for (long done = 0; done < nb; done += rows_per_pass) {
-        const long a = start + done;
-        const long n = nb - done < rows_per_pass ? nb - done : rows_per_pass;
-        const long colsA = V - a, t256 = cdiv(colsA, 256), nt = cdiv(n, 256);
-        const long rowsB = V - a - n;
-        float *A = work;
-        float *B = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(work) + (size_t)nt * t256 * E * 65536 * esz);
-        if ((size_t)((nt * t256 + (use_cols ? 0 : (t256 - nt) * nt)) * E) * 65536 * esz > work_bytes)
+    const long npass = cdiv(nb, rows_per_pass);
+    struct Pass {
+        long a, n, colsA, t256, nt, rowsB;
+    };
+    auto geometry = [&](long p) {
+        Pass g;
+        g.a = start + p * rows_per_pass;
+        g.n = nb - p * rows_per_pass < rows_per_pass ? nb - p * rows_per_pass : rows_per_pass;
+        g.colsA = V - g.a, g.t256 = cdiv(g.colsA, 256), g.nt = cdiv(g.n, 256), g.rowsB = V - g.a - g.n;
+        return g;
+    };
+    auto blockB = [&](const Pass &g, float *A) {
+        return reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(A) + (size_t)g.nt * g.t256 * E * 65536 * esz);
+    };
+    auto gemm_pass = [&](const Pass &g, float *A, int e_begin, int e_count, bool fixup) -> int {
+        if ((size_t)((g.nt * g.t256 + (use_cols ? 0 : (g.t256 - g.nt) * g.nt)) * E) * 65536 * esz > buf_bytes)
             return fail(FCMA_ENOMEM, "internal: symmetric pass does not fit the work buffer");
-        EventSet<4> evs;
-        cudaEvent_t *ev = evs.ev;
-        if (g_timing_on) {
-            CUDA_TRY(evs.create());
-            CUDA_TRY(cudaEventRecord(ev[0], st));
-        }
-        SymOut so{use_cols ? nullptr : B};
-        int rc = FCMA_OK;
-        if (hooks && hooks->ngroups > 0 && done == 0) {
-            // first pass from host buffers: one GEMM launch per uploaded epoch group, the diagonal fix-up after the last
-            for (int gi = 0; gi < hooks->ngroups && !rc; gi++) {
-                rc = hooks->prepare(hooks->ctx, gi, st);
-                if (!rc)
-                    rc = launch_corr_umma(op, op, precision, E, T, V, V, a, n, A, 4, 4, S_eps, st, t256, half16 ? 1 : 0, &so,
-                                          hooks->e0[gi], hooks->cnt[gi], gi == hooks->ngroups - 1);
-            }
-        } else {
-            rc = launch_corr_umma(op, op, precision, E, T, V, V, a, n, A, 4, 4, S_eps, st, t256, half16 ? 1 : 0, &so);
-        }
+        SymOut so{use_cols ? nullptr : blockB(g, A)};
+        return launch_corr_umma(op, op, precision, E, T, V, V, g.a, g.n, A, 4, 4, S_eps, st, g.t256, half16 ? 1 : 0, &so,
+                                e_begin, e_count, fixup);
+    };
+    // normalise + SYRK of one pass: rows of the block, then its columns (or the rows of the transposed copy)
+    auto syrk_pass = [&](const Pass &g, float *A, cudaEvent_t after_rows) -> int {
+        int rc = launch_norm_syrk(A, g.n, E, g.colsA, 256, 65536, eps, 1, mask_self ? 0 : -1, 1.0f, K + (size_t)g.a * E * E, 0,
+                                  st, (long)E * 65536, half16 ? 1 : 0);
         if (rc) return rc;
-        if (g_timing_on) CUDA_TRY(cudaEventRecord(ev[1], st));
-        rc = launch_norm_syrk(A, n, E, colsA, 256, 65536, eps, 1, mask_self ? 0 : -1, 1.0f, K + (size_t)a * E * E, 0, st,
-                              (long)E * 65536, half16 ? 1 : 0);
-        if (rc) return rc;
-        if (g_timing_on) CUDA_TRY(cudaEventRecord(ev[3], st));
+        if (after_rows) CUDA_TRY(cudaEventRecord(after_rows, st));
         if (hooks && hooks->K_host) {
             // rows [a, a+n) of K are final now (the columns left of this pass arrived through earlier column passes)
             EventSet<1> rowdone;
             CUDA_TRY(rowdone.create());
             CUDA_TRY(cudaEventRecord(rowdone.ev[0], st));
             CUDA_TRY(cudaStreamWaitEvent(hooks->copy, rowdone.ev[0], 0));
-            CUDA_TRY(cudaMemcpyAsync(hooks->K_host + (size_t)a * E * E, K + (size_t)a * E * E, (size_t)n * E * E * sizeof(float),
-                                     cudaMemcpyDeviceToHost, hooks->copy));
+            CUDA_TRY(cudaMemcpyAsync(hooks->K_host + (size_t)g.a * E * E, K + (size_t)g.a * E * E,
+                                     (size_t)g.n * E * E * sizeof(float), cudaMemcpyDeviceToHost, hooks->copy));
         }
-        if (rowsB > 0 && use_cols) {
-            rc = launch_norm_syrk_cols(A, n, E, colsA, t256, n, eps, K + (size_t)a * E * E, st, half16 ? 1 : 0,
-                                       (flags & FCMA_FLAG_COLS_TMA) != 0, (flags & FCMA_FLAG_COLS_V2) != 0);
-            if (rc) return rc;
-        } else if (rowsB > 0) {
-            rc = launch_norm_syrk(B, rowsB, E, n, 256, 65536, eps, 1, -1, 1.0f, K + (size_t)(a + n) * E * E, 0, st,
-                                  (long)E * 65536, half16 ? 1 : 0);
+        if (g.rowsB > 0 && use_cols)
+            return launch_norm_syrk_cols(A, g.n, E, g.colsA, g.t256, g.n, eps, K + (size_t)g.a * E * E, st, half16 ? 1 : 0,
+                                         (flags & FCMA_FLAG_COLS_TMA) != 0, (flags & FCMA_FLAG_COLS_V2) != 0);
+        if (g.rowsB > 0)
+            return launch_norm_syrk(blockB(g, A), g.rowsB, E, g.n, 256, 65536, eps, 1, -1, 1.0f,
+                                    K + (size_t)(g.a + g.n) * E * E, 0, st, (long)E * 65536, half16 ? 1 : 0);
+        return FCMA_OK;
+    };
+    float *buf0 = work;
+    float *buf1 = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(work) + buf_bytes);
+    long first = 0;
+    if (grouped) {
+        // one GEMM launch per uploaded epoch group (a tile needs only its own epoch), the diagonal fix-up after the last
+        const long ahead = (two && npass > 1) ? 2 : 1;
+        for (int gi = 0; gi < hooks->ngroups; gi++) {
+            int rc = hooks->prepare(hooks->ctx, gi, st);
+            for (long p = 0; p < ahead && !rc; p++)
+                rc = gemm_pass(geometry(p), p == 0 ? buf0 : buf1, hooks->e0[gi], hooks->cnt[gi], gi == hooks->ngroups - 1);
             if (rc) return rc;
         }
+        for (long p = 0; p < ahead; p++) {
+            int rc = syrk_pass(geometry(p), p == 0 ? buf0 : buf1, nullptr);
+            if (rc) return rc;
+        }
+        first = ahead;
+    }
+    for (long p = first; p < npass; p++) {
+        const Pass g = geometry(p);
+        EventSet<4> evs;
+        cudaEvent_t *ev = evs.ev;
+        if (g_timing_on) {
+            CUDA_TRY(evs.create());
+            CUDA_TRY(cudaEventRecord(ev[0], st));
+        }
+        int rc = gemm_pass(g, buf0, 0, E, true);
+        if (rc) return rc;
+        if (g_timing_on) CUDA_TRY(cudaEventRecord(ev[1], st));
+        rc = syrk_pass(g, buf0, g_timing_on ? ev[3] : nullptr);
+        if (rc) return rc;
         if (g_timing_on) {
             CUDA_TRY(cudaEventRecord(ev[2], st));
             CUDA_TRY(cudaEventSynchronize(ev[2]));
@@ -3843,12 +3871,15 @@ extern "C" int fcma_host_voxel_kernels_sym(const float *const *raw_host, const i
     if (rows > round_up(V, 256)) rows = round_up(V, 256);
     rows = rows / 256 * 256;
     if (rows < 256) return fail(FCMA_ENOMEM, "not enough device memory for a 256-row correlation block (%zu bytes per row)", per_row);
+    // a second block lets the GEMMs of the first TWO passes follow the upload (more of the copy hidden)
+    const bool two_blocks = fit >= 2 * rows && rows < round_up(V, 256);
+    const size_t work_bytes_total = per_row * rows * (two_blocks ? 2 : 1);
     int rc_run = FCMA_OK;
     {
         AsyncBuf epochs, op, work, K;       // released in stream order on `st` when this scope ends
         CUDA_TRY(epochs.alloc(ep_bytes, st));
         CUDA_TRY(op.alloc(opb, st));
-        CUDA_TRY(work.alloc(per_row * rows, st));
+        CUDA_TRY(work.alloc(work_bytes_total, st));
         CUDA_TRY(K.alloc(k_bytes, st));
         CUDA_TRY(cudaMemsetAsync(K.p, 0, k_bytes, st));
         bool ragged = false;
@@ -3875,8 +3906,8 @@ extern "C" int fcma_host_voxel_kernels_sym(const float *const *raw_host, const i
         HostSymCtx ctx{(const float *)epochs.p, E, T, V, ragged ? T_e : nullptr, normalize, precision, op.p, opb, e0, cnt, landed.ev};
         SymHostHooks hooks;
         hooks.ngroups = ng, hooks.e0 = e0, hooks.cnt = cnt, hooks.prepare = host_sym_prepare, hooks.ctx = &ctx;
-        hooks.copy = ss.copy, hooks.K_host = K_host;
-        rc_run = run_pipeline_sym(op.p, precision, E, T, V, 0, V, eps, flags, (float *)work.p, per_row * rows, (float *)K.p, st, &hooks);
+        hooks.copy = ss.copy, hooks.K_host = K_host, hooks.two_buffers = two_blocks;
+        rc_run = run_pipeline_sym(op.p, precision, E, T, V, 0, V, eps, flags, (float *)work.p, work_bytes_total, (float *)K.p, st, &hooks);
         // everything enqueued so far must finish before the buffers go back to the pool and the function returns
         cudaError_t e1 = cudaStreamSynchronize(st), e2 = cudaStreamSynchronize(ss.copy);
         if (!rc_run && (e1 != cudaSuccess || e2 != cudaSuccess))

@@ -412,14 +412,27 @@ def run_b200_arm(args):
         if world > 1:
             dist.reduce_scatter_tensor(Kmine, Kdst)
 
+    # N > 1 e2e: interleaved shares (rank r holds epochs r, r + W, ...) so that contiguous epoch groups complete one after
+    # the other and the first passes' GEMMs can follow them (engine.voxel_kernels_sym_grouped); a scratch of two blocks
+    e2e_state = {}
+
     def e2e_step():
         """host -> host, unpipelined: this rank's share H2D + epoch exchange, kernels, read-back of the rank's rows"""
         if world == 1:
             engine.host_voxel_kernels_sym(host_share, eps, precision=prec, flags=flags, device=local,
                                           rows_per_pass=block, out=Khost)
             return
-        src = xch.gather(1, host_share)
-        kernels_step(src, Kfull)
+        if not e2e_state:
+            e2e_state["cs"] = torch.cuda.Stream(device=dev)
+            e2e_state["host"] = make_host_epochs(V, T, E, epochs=xch.interleaved_share(), pin=True)
+            e2e_state["work"] = engine.SymWorkspace(E, V, 2 * block, dev, start=start, transposed_copy=not cols_variant)
+        cs, main = e2e_state["cs"], torch.cuda.current_stream()
+        cs.wait_stream(main)
+        src, groups, events = xch.gather_groups(1, e2e_state["host"], stream=cs, ngroups=4)
+        Kfull[start:].zero_()
+        engine.voxel_kernels_sym_grouped(src, op_buf, start, n, eps, groups, events, flags=flags, work=e2e_state["work"],
+                                         out=Kfull[:V])
+        dist.reduce_scatter_tensor(Kmine, Kfull)
         Khost.copy_(Kmine, non_blocking=True)
 
     def timed(nsteps, fn):
@@ -535,6 +548,16 @@ def run_b200_arm(args):
         ne_steps = max(2, min(args.steps, 4))
         ms_dev, _, ms_wall = timed(ne_steps, e2e_step)
         ms_seq = (ms_wall if world == 1 else ms_dev) / ne_steps
+        # the host -> host result against the kernel path's (same inputs): both must be the same kernels
+        torch.cuda.synchronize()
+        Kh = Khost.to(dev)
+        kernels_step(epochs, Kfull)
+        Kd = Kmine if world > 1 else Kfull[:V]
+        e2e_check = torch.stack([(Kh - Kd).abs().max(), Kd.abs().max()])
+        if world > 1:
+            dist.all_reduce(e2e_check, op=dist.ReduceOp.MAX)
+        e2e_dk = float(e2e_check[0] / e2e_check[1])
+        del Kh
         npipe = max(8, 2 * args.steps)      # the first copy-in and the last read-back cannot hide: amortise them
         timed_e2e_pipelined(2)
         ms_pipe = timed_e2e_pipelined(npipe) / npipe
@@ -543,12 +566,15 @@ def run_b200_arm(args):
                "h2d_bytes_per_step": int(E) * T * V * 4, "d2h_bytes_per_step": int(V) * E * E * 4,
                "h2d_bytes_per_step_per_rank": share_bytes, "d2h_bytes_per_step_per_rank": int(Khost.numel()) * 4,
                "ms_per_step": ms_seq, "steps": ne_steps,
+               "max_abs_dK_over_max_K_vs_kernel_path": e2e_dk,
                "path": ("one fcma_host_voxel_kernels_sym call per step (C ABI, include/fcma_b200.h): pinned host epochs -> H2D "
                         "-> pack -> symmetric pipeline -> D2H -> pinned host kernels, synchronous, timed by wall clock"
                         if world == 1 else
-                        "per step and rank: H2D of the rank's E/N epochs over its own PCIe link -> all-gather of the shares over "
-                        "NVLink (%s) -> pack -> symmetric pipeline -> NCCL reduce-scatter -> D2H of the rank's own kernel rows; "
-                        "unpipelined, CUDA events, max over ranks" % xch.mode),
+                        "per step and rank: H2D of the rank's E/N epochs (interleaved share) over its own PCIe link -> all-gather of "
+                        "the shares over NVLink (%s), completing in 4 contiguous epoch groups -> per group: pack + GEMMs of the "
+                        "first two passes (fcma_voxel_kernels_sym_grouped), then the rest of the symmetric pipeline -> NCCL "
+                        "reduce-scatter -> D2H of the rank's own kernel rows; one step at a time, CUDA events, max over ranks"
+                        % xch.mode),
                "epoch_exchange": xch.mode,
                "pipelined": {"value": corr_total / (ms_pipe * 1e-3), "unit": UNIT, "ms_per_step": ms_pipe, "steps": npipe,
                              "how": "copy stream + double buffers: input of step k+1 and read-back of step k-1 under the kernels "
@@ -663,6 +689,7 @@ def run_b200_arm(args):
     others = None
     if not args.no_others:
         del work, op_buf
+        e2e_state.clear()
         torch.cuda.empty_cache()
         others = other_configs(args, lib, engine, torch, dist, dev, rank, world, local, hbm_peak, tf_peak)
 

@@ -54,6 +54,9 @@ SIGNATURES = {
                                    c_long, c_int, c_int, c_void_p, c_size_t, c_void_p, c_void_p]),
     "fcma_voxel_kernels_sym": (c_int, [c_void_p, c_int, c_int, c_int, c_long, c_long, c_long, c_int, c_int,
                                        c_void_p, c_size_t, c_void_p, c_void_p]),
+    "fcma_voxel_kernels_sym_grouped": (c_int, [c_void_p, c_int_p, c_int, c_void_p, c_size_t, c_int, c_int, c_int, c_long,
+                                               c_long, c_long, c_int, c_int, c_int, c_int_p, c_int_p,
+                                               ctypes.POINTER(c_void_p), c_void_p, c_size_t, c_void_p, c_void_p]),
     "fcma_sym_uses_column_pass": (c_int, [c_int, c_int, c_int, c_int]),
     "fcma_sym_rows_per_pass": (c_long, [c_int, c_int, c_int, c_int, c_long, c_long, c_size_t]),
     "fcma_classifier_kernel": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_long, c_long,

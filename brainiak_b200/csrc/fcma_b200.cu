@@ -3328,6 +3328,54 @@ extern "C" int fcma_voxel_kernels_sym(const void *op, int precision, int E, int 
     return run_pipeline_sym(op, precision, E, T, V, start, nb, eps, flags, work_dev, work_bytes, K_dev, (cudaStream_t)stream);
 }
 
+// fcma_voxel_kernels_sym for epochs that are still ARRIVING (multi-GPU input exchange, exchange.py): the epochs come in
+// `ngroups` contiguous groups, ready_events[g] (cudaEvent_t) fires when group g is complete in epochs_dev.  The library
+// packs each group (voxels [start, V) only) as soon as its event has fired and runs the GEMMs of the first pass -- of the
+// first two passes if `work` holds two blocks -- group by group, so that the upload hides under them; everything else
+// follows as in fcma_voxel_kernels_sym.  Same results.
+struct GroupedCtx {
+    const float *epochs;
+    int E, T;
+    long V, start;
+    const int *T_e;
+    int normalize, precision;
+    void *op;
+    size_t opb;
+    const int *e0, *cnt;
+    void *const *ready;
+};
+static int grouped_prepare(void *vctx, int g, cudaStream_t st)
+{
+    GroupedCtx *c = static_cast<GroupedCtx *>(vctx);
+    if (c->ready && c->ready[g]) CUDA_TRY(cudaStreamWaitEvent(st, (cudaEvent_t)c->ready[g], 0));
+    return pack_operand_impl(c->epochs, c->E, c->T, c->V, c->V, c->T_e, c->normalize, c->precision, c->start, c->V, c->e0[g],
+                             c->cnt[g], c->op, c->opb, st);
+}
+extern "C" int fcma_voxel_kernels_sym_grouped(const float *epochs_dev, const int *T_e, int normalize, void *op_dev,
+                                              size_t op_bytes, int precision, int E, int T, long V, long start, long nb,
+                                              int eps, int flags, int ngroups, const int *e0, const int *cnt,
+                                              void *const *ready_events, float *work_dev, size_t work_bytes, float *K_dev,
+                                              void *stream)
+{
+    int rc = check_device();
+    if (rc) return rc;
+    if (!epochs_dev || !op_dev || !e0 || !cnt || ngroups < 1 || ngroups > 64)
+        return fail(FCMA_EINVAL, "fcma_voxel_kernels_sym_grouped: bad arguments");
+    int next = 0;
+    for (int g = 0; g < ngroups; g++) {
+        if (e0[g] != next || cnt[g] <= 0) return fail(FCMA_EINVAL, "epoch groups must be contiguous and cover [0, E)");
+        next += cnt[g];
+    }
+    if (next != E) return fail(FCMA_EINVAL, "epoch groups must be contiguous and cover [0, E)");
+    if (op_bytes < fcma_operand_bytes(precision, E, T, V)) return fail(FCMA_ENOMEM, "packed operand buffer too small");
+    GroupedCtx ctx{epochs_dev, E, T, V, start, T_e, normalize, precision, op_dev, op_bytes, e0, cnt, ready_events};
+    SymHostHooks hooks;
+    hooks.ngroups = ngroups, hooks.e0 = e0, hooks.cnt = cnt, hooks.prepare = grouped_prepare, hooks.ctx = &ctx;
+    hooks.two_buffers = true;
+    return run_pipeline_sym(op_dev, precision, E, T, V, start, nb, eps, flags, work_dev, work_bytes, K_dev, (cudaStream_t)stream,
+                            &hooks);
+}
+
 extern "C" int fcma_voxel_kernels(const void *rows_op, const void *cols_op, int precision, int E, int T, long V, long V2,
                                   long start, long nb, int eps, int flags, float *work_dev, size_t work_bytes,
                                   float *K_dev, void *stream)

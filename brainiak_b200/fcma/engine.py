@@ -371,6 +371,30 @@ def voxel_kernels_sym(op, start, nb, eps, flags=0, work=None, out=None):
     return out
 
 
+def voxel_kernels_sym_grouped(epochs, op, start, nb, eps, groups, events, flags=0, work=None, out=None, normalize=False):
+    """``voxel_kernels_sym`` for epochs that are still arriving (``exchange.EpochExchange.gather_groups``): ``groups`` =
+    ``[(e0, count)]`` contiguous epoch groups of ``epochs`` (float32 CUDA ``[E, T, V]``), ``events[g]`` a
+    ``torch.cuda.Event`` (or None) that fires when group g is complete.  Packing (into ``op``, voxels ``[start, V)``) and
+    the GEMMs of the first pass(es) follow the groups, the rest is the ordinary symmetric pipeline."""
+    lib = _lib.load()
+    E, T, V = epochs.shape
+    if (op.E, op.T, op.V) != (E, T, V):
+        raise ValueError("operand does not match the epochs")
+    if work is None:
+        work = SymWorkspace.for_operand(op, 2 * min(4096, (nb + 255) // 256 * 256), eps, flags, start)
+    if out is None:
+        out = torch.zeros((V, E, E), dtype=torch.float32, device=op.device)
+    ng = len(groups)
+    e0 = (ctypes.c_int * ng)(*[int(a) for a, _ in groups])
+    cnt = (ctypes.c_int * ng)(*[int(c) for _, c in groups])
+    evs = (ctypes.c_void_p * ng)(*[ctypes.c_void_p(ev.cuda_event) if ev is not None else None for ev in events])
+    with torch.cuda.device(op.device):
+        _lib.check(lib.fcma_voxel_kernels_sym_grouped(_ptr(epochs), None, int(bool(normalize)), _ptr(op.buf), op.buf.numel(),
+                                                      _prec_code(op.precision), E, T, V, start, nb, int(eps), int(flags), ng,
+                                                      e0, cnt, evs, _ptr(work.buf), work.buf.numel(), _ptr(out), _stream_ptr()))
+    return out
+
+
 def classifier_kernel(rows, cols, start, nb, eps, flags=0, work=None, out=None, symmetric=True):
     """a9 -> a10 -> a11: accumulates sum_i Z_i Z_i^T over rows [start, start+nb) into ``out`` [E, E].
 

@@ -14,7 +14,7 @@ import torch.distributed as dist
 
 from .. import _lib
 
-__all__ = ["EpochExchange", "epoch_partition"]
+__all__ = ["EpochExchange", "epoch_partition", "epoch_groups"]
 
 
 def epoch_partition(E, world):
@@ -25,6 +25,17 @@ def epoch_partition(E, world):
         n = per + (1 if r < extra else 0)
         out.append((e0, n))
         e0 += n
+    return out
+
+
+def epoch_groups(E, ngroups=4):
+    """Contiguous epoch groups [(e0, count)] in which an interleaved exchange completes (``gather_groups``)."""
+    ngroups = max(1, min(int(ngroups), E))
+    out, e = [], 0
+    for g in range(ngroups):
+        n = (E - e) // (ngroups - g)
+        out.append((e, n))
+        e += n
     return out
 
 
@@ -99,6 +110,60 @@ class EpochExchange:
 
     def share_of(self, rank=None):
         return self.shares[self.rank if rank is None else rank]
+
+    def interleaved_share(self, rank=None):
+        """Epochs ``rank, rank + W, rank + 2W, ...``: the share of ``gather_groups`` (every W consecutive epochs come from
+        W different ranks, so contiguous epoch groups complete one after the other)."""
+        r = self.rank if rank is None else rank
+        return list(range(r, self.E, self.world))
+
+    def gather_groups(self, k, host_share, stream=None, ngroups=4):
+        """Like ``gather`` with INTERLEAVED shares (``host_share[j]`` = epoch ``interleaved_share()[j]``): returns
+        ``(buffers[k], groups, events)`` where ``events[g]`` (on ``stream``) fires when the contiguous epoch group
+        ``groups[g]`` is complete on THIS rank, i.e. has been uploaded / pushed by every rank.  A consumer
+        (``engine.voxel_kernels_sym_grouped``) can start on group 0 while the later ones are still in flight."""
+        stream = stream or torch.cuda.current_stream(self.device)
+        buf = self.buffers[k]
+        groups = epoch_groups(self.E, ngroups)
+        mine = self.interleaved_share()
+        events = []
+        ebytes = self.T * self.V * 4
+        with torch.cuda.stream(stream):
+            use_ipc = self.world > 1 and self._peer is not None
+            if use_ipc and self._aux is None:
+                self._aux = torch.cuda.Stream(device=self.device)
+                self._landed = [torch.cuda.Event() for _ in range(max(1, -(-self.E // self.world)))]
+            if use_ipc:
+                self._aux.wait_stream(stream)
+            j = 0
+            for (g0, gn) in groups:
+                while j < len(mine) and mine[j] < g0 + gn:
+                    e = mine[j]
+                    buf[e].copy_(host_share[j], non_blocking=True)
+                    if use_ipc:
+                        self._landed[j].record(stream)
+                        self._aux.wait_event(self._landed[j])
+                        sp = ctypes.c_void_p(self._aux.cuda_stream)
+                        off = e * ebytes
+                        with torch.cuda.device(self.device):
+                            for d in range(1, self.world):
+                                r = (self.rank + d) % self.world
+                                _lib.check(self.lib.fcma_peer_copy_async(ctypes.c_void_p(self._peer[k][r] + off),
+                                                                         ctypes.c_void_p(buf.data_ptr() + off), ebytes, sp))
+                    j += 1
+                if self.world > 1:
+                    if use_ipc:
+                        stream.wait_stream(self._aux)
+                        dist.all_reduce(self._flag, group=self.group)      # every rank's epochs of this group have landed
+                    else:
+                        # NCCL fallback: broadcast every epoch of the group from its owner
+                        for e in range(g0, g0 + gn):
+                            dist.broadcast(buf[e], src=dist.get_global_rank(self.group, e % self.world)
+                                           if self.group is not None else e % self.world, group=self.group)
+                ev = torch.cuda.Event()
+                ev.record(stream)
+                events.append(ev)
+        return buf, groups, events
 
     def gather(self, k, host_share, stream=None):
         """host_share: this rank's epochs, a (pinned) host float32 tensor ``[n, T, V]``.  Everything is enqueued on

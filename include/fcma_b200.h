@@ -160,6 +160,14 @@ int fcma_voxel_kernels(const void *rows_op, const void *cols_op, int precision, 
  * (fused path); work_dev must hold at least 256 rows (see fcma_sym_rows_per_pass). */
 int fcma_voxel_kernels_sym(const void *op, int precision, int E, int T, long V, long start, long nb, int eps,
                            int flags, float *work_dev, size_t work_bytes, float *K_dev, void *stream);
+/* The same for epochs that are still arriving (multi-GPU input exchange): epochs_dev receives `ngroups` contiguous epoch
+ * groups [e0[g], e0[g] + cnt[g]); ready_events[g] is a cudaEvent_t (NULL: already there) that fires when group g is complete.
+ * The library packs each group into op_dev (voxels [start, V) only) once its event has fired and runs the GEMMs of the first
+ * pass -- of the first two passes if work_dev holds two blocks -- group by group, hiding the upload; then as above. */
+int fcma_voxel_kernels_sym_grouped(const float *epochs_dev, const int *T_e, int normalize, void *op_dev, size_t op_bytes,
+                                   int precision, int E, int T, long V, long start, long nb, int eps, int flags,
+                                   int ngroups, const int *e0, const int *cnt, void *const *ready_events,
+                                   float *work_dev, size_t work_bytes, float *K_dev, void *stream);
 /* 1 if fcma_voxel_kernels_sym takes the column voxels' sums from the stored block itself (column-direction
  * normalise+SYRK pass: E <= 32, power-of-two eps <= 32; fp32 or fp16 block), 0 if it stores a transposed copy of
  * every block and runs the row pass over it (E > 32).  Informational (bench accounting, scratch sizing). */

@@ -1099,3 +1099,38 @@ def test_prepare_fcma_data_matches_reference_arithmetic(dev):
     assert none2 is None and ep.is_cuda and tuple(ep.shape) == (12, 8, int(mask1.sum())) and T_e == [8] * 12
     with pytest.raises(ValueError, match="different shapes"):
         prepare_fcma_data(images, conditions, mask1[:-1])
+
+
+def test_grouped_symmetric_pipeline_follows_arriving_epochs(dev):
+    """fcma_voxel_kernels_sym_grouped: the epochs arrive in contiguous groups on a copy stream (EpochExchange.gather_groups),
+    packing and the GEMMs of the first two passes follow group by group (epoch sub-range launches), the result equals the
+    ordinary call; also for a shard that starts in the middle (range packing) and without events."""
+    from brainiak_b200.fcma.exchange import EpochExchange, epoch_groups
+    V, T, E, eps = 1100, 40, 8, 4
+    raw, _ = synthetic.make_epochs(V, T, E, seed=555)
+    ep, T_e = engine.stack_epochs(raw, dev)
+    op = engine.pack_epochs(ep, T_e, "fp16x3")
+    host = torch.from_numpy(np.stack(raw)).pin_memory()
+    x = EpochExchange(E, T, V, dev, nbuf=1)
+    assert x.interleaved_share() == list(range(E)) and epoch_groups(E, 4) == [(0, 2), (2, 2), (4, 2), (6, 2)]
+    cs = torch.cuda.Stream(device=dev)
+    for start in (0, 512):
+        nb = V - start
+        ref = engine.voxel_kernels_sym(op, start, nb, eps, flags=_lib.FLAG_MASK_SELF,
+                                       work=engine.SymWorkspace(E, V, 256, dev, start=start, transposed_copy=False))
+        x.buffers[0].fill_(float("nan"))
+        cs.wait_stream(torch.cuda.current_stream())
+        buf, groups, events = x.gather_groups(0, host, stream=cs, ngroups=4)
+        op2 = engine.PackedOperand(torch.zeros_like(op.buf), E, T, V, op.precision, op.T_e)
+        work = engine.SymWorkspace(E, V, 512, dev, start=start, transposed_copy=False)       # two 256-row blocks
+        work.buf.view(torch.float32).fill_(float("nan"))
+        K = engine.voxel_kernels_sym_grouped(buf, op2, start, nb, eps, groups, events, flags=_lib.FLAG_MASK_SELF, work=work)
+        torch.cuda.synchronize()
+        assert torch.isfinite(K).all()
+        assert float((K - ref).abs().max()) <= 1e-6 * float(ref.abs().max())
+    # no events (everything already there), one group
+    K1 = engine.voxel_kernels_sym_grouped(ep, op2, 0, V, eps, [(0, E)], [None], flags=_lib.FLAG_MASK_SELF)
+    ref0 = engine.voxel_kernels_sym(op, 0, V, eps, flags=_lib.FLAG_MASK_SELF)
+    assert float((K1 - ref0).abs().max()) <= 1e-6 * float(ref0.abs().max())
+    with pytest.raises(ValueError):
+        engine.voxel_kernels_sym_grouped(ep, op2, 0, V, eps, [(0, 3), (4, 4)], [None, None])      # groups must tile [0, E)

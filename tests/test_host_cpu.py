@@ -264,3 +264,20 @@ def test_epoch_partition_covers_all_epochs():
         assert len(p) == W and p[0][0] == 0 and sum(n for _, n in p) == E
         assert all(p[r][0] + p[r][1] == p[r + 1][0] for r in range(W - 1))
         assert max(n for _, n in p) - min(n for _, n in p) <= 1
+
+
+def test_epoch_groups_and_interleaved_shares_tile_the_epochs():
+    """The grouped exchange: rank r uploads epochs r, r + W, ...; contiguous epoch groups complete one after the other,
+    and every group contains epochs of (almost) every rank, so all PCIe links work on every group."""
+    from brainiak_b200.fcma.exchange import epoch_groups
+    for E, G in ((32, 4), (64, 4), (10, 4), (3, 4), (16, 1)):
+        groups = epoch_groups(E, G)
+        assert groups[0][0] == 0 and sum(n for _, n in groups) == E
+        assert all(groups[k][0] + groups[k][1] == groups[k + 1][0] for k in range(len(groups) - 1))
+        assert max(n for _, n in groups) - min(n for _, n in groups) <= 1
+    for E, W in ((32, 8), (32, 2), (10, 4)):
+        shares = [list(range(r, E, W)) for r in range(W)]
+        assert sorted(e for sh in shares for e in sh) == list(range(E))
+        for (e0, n) in epoch_groups(E, 4):
+            owners = {e % W for e in range(e0, e0 + n)}
+            assert len(owners) == min(W, n)

@@ -2391,6 +2391,172 @@ __global__ void __launch_bounds__(256, 1)
 }
 
 // ============================================================================================
+// Column-direction pass for E <= 16 (default there, fp32 block): the structure of version 2 with 16-epoch bricks
+// [16 epochs][16 rows][32 columns] (32 KB) instead of bricks padded to 32 epochs -- half the shared-memory traffic,
+// statistics and MMAs per byte of the block (BASELINE configs[1], E = 16: the padded kernels ran at 0.40 of the HBM peak).
+//   phase 1: lane l takes row (l & 15), ALL 16 epochs and two of the warp's four columns (l >> 4): sixteen LDS.64, in-thread
+//            subject statistics on one natural fp32x2 pair, z-scores staged as fp16 [column][row][16 epochs] (32 B per
+//            (column, row); the two 16-byte pieces swapped for rows 4-7 / 12-15 so that eight rows hit eight bank groups);
+//   phase 2: per column ONE ldmatrix.x4.trans = {epochs 0-7, 8-15} x {rows 0-7, 8-15} -> the four fragment registers of
+//            the two mma.m16n8k16 of a 16 x 16 kernel; 8 accumulator registers per column.
+// 3 bricks + 16 KB of staging = 112 KB and ~110 registers: two CTAs per SM.
+// ============================================================================================
+template <int EPS>
+__global__ void __launch_bounds__(256, 2)
+    k_norm_syrk_cols16(const float *__restrict__ A, long n, int E, long n2, long T256, long c0, float *K)
+{
+    static_assert(EPS <= 16, "a subject spans at most the 16 epochs of this kernel");
+    constexpr int EP = 16, NT = 2, CPW = 4, NTHR = 256;
+    constexpr int BRICK = 32768, PPT = BRICK / 16 / NTHR, LS = NTHR / 8;     // 8 pieces per thread, 32 lines apart
+    constexpr uint32_t STAGE_OFF = COLS_BRICKS * BRICK;
+    extern __shared__ __align__(1024) uint8_t cs_raw[];
+    // 128-byte alignment is all the swizzles need; the smaller slack keeps two CTAs (2 x 113 KB) inside one SM's 228 KB
+    uint8_t *cs = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(cs_raw) + 127) & ~uintptr_t(127));
+    const uint32_t brick0 = smem_u32(cs);
+    float *s_fold = reinterpret_cast<float *>(cs);         // [32 columns][EP*EP] fp32 (32 KB) overlays brick 0 at folds
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int S_eps = (E / EPS) * EPS;
+    const long nstrips = (n2 - c0 + 31) / 32;
+    const long nsteps = (n + 15) / 16;
+    const int prow = lane & 15, pcp = lane >> 4;           // phase 1: row, column pair (columns 2*pcp, 2*pcp + 1 of the warp's 4)
+    const uint32_t rd_base = (uint32_t)prow * 128u + ((((uint32_t)warp) ^ ((uint32_t)prow & 7u)) << 4) + (uint32_t)pcp * 8u;
+    const uint32_t stage = brick0 + STAGE_OFF + (uint32_t)warp * 2048u;
+    // staged piece (column c, row, epoch block eb in {0, 1}) at  c*512 + row*32 + ((eb ^ ((row >> 2) & 1)) << 4)
+    const uint32_t st_row = stage + (uint32_t)prow * 32u;
+    const uint32_t st_swz = ((uint32_t)prow >> 2) & 1u;
+    // ldmatrix: matrix m = lane >> 3: epoch block m & 1, rows 8*(m >> 1) .. +7; this lane supplies row (lane & 7) of it
+    const uint32_t lm_r = ((uint32_t)lane & 7u) + 8u * ((uint32_t)lane >> 4), lm_eb = ((uint32_t)lane >> 3) & 1u;
+    const uint32_t lm_addr = stage + lm_r * 32u + ((lm_eb ^ ((lm_r >> 2) & 1u)) << 4);
+
+    for (long strip = blockIdx.x; strip < nstrips; strip += gridDim.x) {
+        const long j0 = c0 + strip * 32;
+        const long tjx = j0 >> 8;
+        const int jo = (int)(j0 & 255);
+        const int pf_w = tid & 7, pf_line0 = tid >> 3, pf_row = pf_line0 & 15, pf_e0 = pf_line0 >> 4;
+        const int pf_src = pf_e0 * 65536 + pf_row * 256 + pf_w * 4 + jo;
+        const uint32_t pf_dst = brick0 + (uint32_t)pf_line0 * 128u + ((((uint32_t)pf_w) ^ ((uint32_t)pf_line0 & 7u)) << 4);
+        auto prefetch = [&](long st, int b) {
+            const long i0 = st * 16;
+            const float *src0 = A + ((size_t)((i0 >> 8) * T256 + tjx) * E) * 65536 + (size_t)(i0 & 255) * 256 + pf_src;
+            const bool row_ok = i0 + pf_row < n;
+            const uint32_t dst0 = pf_dst + (uint32_t)b * (uint32_t)BRICK;
+#pragma unroll
+            for (int k = 0; k < PPT; k++) {
+                const bool ok = row_ok && pf_e0 + 2 * k < E;
+                cp_async_16_zfill_s(dst0 + (uint32_t)(k * LS) * 128u, ok ? src0 + (size_t)k * (2 * 65536) : A, ok ? 16u : 0u);
+            }
+        };
+        for (long seg0 = 0; seg0 < nsteps; seg0 += COLS_SEG_STEPS) {
+            const long seg1 = seg0 + COLS_SEG_STEPS < nsteps ? seg0 + COLS_SEG_STEPS : nsteps;
+            float acc[CPW][NT][4];
+#pragma unroll
+            for (int c = 0; c < CPW; c++)
+#pragma unroll
+                for (int b = 0; b < NT; b++)
+#pragma unroll
+                    for (int d = 0; d < 4; d++) acc[c][b][d] = 0.f;
+            int buf = 0;
+            prefetch(seg0, 0);
+            cp_async_commit();
+            if (seg0 + 1 < seg1) prefetch(seg0 + 1, 1);
+            cp_async_commit();
+            for (long st = seg0; st < seg1; st++) {
+                cp_async_wait<1>();
+                __syncthreads();
+                if (st + 2 < seg1) prefetch(st + 2, buf == 0 ? 2 : buf - 1);
+                cp_async_commit();
+                const uint32_t bb = brick0 + (uint32_t)buf * (uint32_t)BRICK + rd_base;
+                // ---- phase 1: 16 epochs x 2 columns of this lane's row
+                float2 v[16];
+#pragma unroll
+                for (int e = 0; e < 16; e++) {
+                    const uint2 q = lds64(bb + (uint32_t)e * 2048u);
+                    v[e] = make_float2(__uint_as_float(q.x), __uint_as_float(q.y));
+                }
+#pragma unroll
+                for (int s0 = 0; s0 < 16; s0 += EPS) {
+                    float2 m = splat2(0.f), q2 = splat2(0.f);
+#pragma unroll
+                    for (int e = s0; e < s0 + EPS; e++) m = fadd2(m, v[e]), q2 = ffma2(v[e], v[e], q2);
+                    const float2 nm = ffma2(m, splat2(-1.0f / EPS), splat2(0.f));
+                    const float2 ns2 = ffma2(q2, splat2(-1.0f / EPS), splat2(0.f));
+                    const float2 negvar = ffma2(nm, nm, ns2);
+                    float2 inv;
+                    inv.x = negvar.x >= 0.f ? 0.f : rsqrt_ftz(-negvar.x);
+                    inv.y = negvar.y >= 0.f ? 0.f : rsqrt_ftz(-negvar.y);
+                    const float2 mi = ffma2(nm, inv, splat2(0.f));
+                    if (s0 < S_eps) {
+#pragma unroll
+                        for (int e = s0; e < s0 + EPS; e++) v[e] = ffma2(v[e], inv, mi);
+                    }
+                }
+                // ---- stage: per column two 16-byte pieces (epochs 0-7 and 8-15) of this lane's row
+#pragma unroll
+                for (int pc = 0; pc < 2; pc++) {
+                    const uint32_t piece = st_row + ((((uint32_t)pc) ^ st_swz) << 4) + (uint32_t)(2 * pcp) * 512u;
+                    const int e0 = 8 * pc;
+                    sts128(piece, pack_half2_rn(v[e0].x, v[e0 + 1].x), pack_half2_rn(v[e0 + 2].x, v[e0 + 3].x),
+                           pack_half2_rn(v[e0 + 4].x, v[e0 + 5].x), pack_half2_rn(v[e0 + 6].x, v[e0 + 7].x));
+                    sts128(piece + 512u, pack_half2_rn(v[e0].y, v[e0 + 1].y), pack_half2_rn(v[e0 + 2].y, v[e0 + 3].y),
+                           pack_half2_rn(v[e0 + 4].y, v[e0 + 5].y), pack_half2_rn(v[e0 + 6].y, v[e0 + 7].y));
+                }
+                __syncwarp();
+                // ---- phase 2: one ldmatrix and two MMAs per column
+#pragma unroll
+                for (int c = 0; c < CPW; c++) {
+                    uint32_t h00, h01, h10, h11;    // h{rows half}{epoch block}: epochs 8*block + g, rows (2t, 2t+1) (+8)
+                    ldmatrix_x4_trans(lm_addr + (uint32_t)c * 512u, h00, h01, h10, h11);
+#pragma unroll
+                    for (int nu = 0; nu < NT; nu++)
+                        mma_f16_16x8x16(acc[c][nu], h00, h01, h10, h11, nu == 0 ? h00 : h01, nu == 0 ? h10 : h11);
+                }
+                __syncwarp();
+                buf = buf == COLS_BRICKS - 1 ? 0 : buf + 1;
+            }
+            // ---- fold: acc[c][nu][{0,1}] = K[g][8 nu + 2t + {0,1}], [{2,3}] = row g + 8
+            cp_async_wait<0>();
+            __syncthreads();
+#pragma unroll
+            for (int c = 0; c < CPW; c++) {
+                float *dstk = s_fold + (size_t)(warp * CPW + c) * (EP * EP);
+#pragma unroll
+                for (int nu = 0; nu < NT; nu++) {
+                    const int col0 = 8 * nu + 2 * t;
+                    *reinterpret_cast<float2 *>(&dstk[g * EP + col0]) = make_float2(acc[c][nu][0], acc[c][nu][1]);
+                    *reinterpret_cast<float2 *>(&dstk[(g + 8) * EP + col0]) = make_float2(acc[c][nu][2], acc[c][nu][3]);
+                }
+            }
+            __syncthreads();
+            const int EE = E * E;
+            const long ncols = n2 - j0 < 32 ? n2 - j0 : 32;
+            const int total = (int)ncols * EE;
+            float *Kst = K + (size_t)j0 * EE;
+            auto folded = [&](int idx) {
+                const int col = idx / EE, rem = idx - col * EE;
+                const int a = rem / E, b = rem - a * E;
+                const float *sk = s_fold + (size_t)col * (EP * EP);
+                return a >= b ? sk[a * EP + b] : sk[b * EP + a];
+            };
+            for (int base = tid; base < total; base += NTHR * 8) {
+                float old[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const int i1 = base + u * NTHR;
+                    if (i1 < total) old[u] = Kst[i1];
+                }
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const int i1 = base + u * NTHR;
+                    if (i1 < total) Kst[i1] = old[u] + folded(i1);
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// ============================================================================================
 // Column-direction pass, TMA version (FCMA_FLAG_COLS_TMA, needs E % 4 == 0): same arithmetic as k_norm_syrk_cols, but
 //   * a brick [32 epochs][16 rows][32 columns] arrives through ONE 5-D bulk tensor copy (UTMALDG) issued by one elected
 //     lane -- the 4096 LDGSTS per brick (8 LSU cycles each, the same port the LDS reads need) and their address
@@ -2772,7 +2938,7 @@ static int launch_norm_syrk(const float *C, long nb, int E, long n2, long stride
 // column-direction pass over a tiled fp32 block (k_norm_syrk_cols): K[j] += ... for block columns [c0, n2)
 static bool cols_supported(int E, int eps) { return E <= 32 && eps >= 1 && eps <= 32 && (eps & (eps - 1)) == 0; }
 static int launch_norm_syrk_cols(const void *A, long n, int E, long n2, long T256, long c0, int eps, float *K,
-                                 cudaStream_t st, int half_in = 0, bool use_tma = false, bool v2 = false)
+                                 cudaStream_t st, int half_in = 0, bool use_tma = false, bool v2 = false, bool pad32 = false)
 {
     if (!cols_supported(E, eps) || (c0 & 31) || c0 >= n2) return fail(FCMA_EINVAL, "internal: column pass unsupported E=%d eps=%d c0=%ld", E, eps, c0);
     const long nstrips = cdiv(n2 - c0, 32);
@@ -2807,6 +2973,27 @@ static int launch_norm_syrk_cols(const void *A, long n, int E, long n2, long T25
         }
 #undef FCMA_COLS_TMA_CASE
         LAUNCH_CHECK("k_norm_syrk_cols_tma");
+        return FCMA_OK;
+    }
+    // E <= 16 (fp32 block): 16-epoch bricks, two CTAs per SM (k_norm_syrk_cols16); the kernels below pad to 32 epochs
+    if (!half_in && E <= 16 && eps <= 16 && !use_tma && !v2 && !pad32) {
+        const size_t smem16 = (size_t)COLS_BRICKS * 32768 + 16384 + 128;
+        const unsigned grid16 = (unsigned)(nstrips < 2L * g_sm_count ? nstrips : 2L * g_sm_count);
+#define FCMA_COLS16_CASE(EPSV)                                                                                      \
+    case EPSV:                                                                                                      \
+        CUDA_TRY(cudaFuncSetAttribute(k_norm_syrk_cols16<EPSV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16)); \
+        k_norm_syrk_cols16<EPSV><<<grid16, 256, smem16, st>>>(reinterpret_cast<const float *>(A), n, E, n2, T256, c0, K); \
+        break;
+        switch (eps) {
+            FCMA_COLS16_CASE(1)
+            FCMA_COLS16_CASE(2)
+            FCMA_COLS16_CASE(4)
+            FCMA_COLS16_CASE(8)
+            FCMA_COLS16_CASE(16)
+        default: return fail(FCMA_EINVAL, "internal: no k_norm_syrk_cols16 instantiation for eps=%d", eps);
+        }
+#undef FCMA_COLS16_CASE
+        LAUNCH_CHECK("k_norm_syrk_cols16");
         return FCMA_OK;
     }
     // FCMA_FLAG_COLS_V2: thread-per-row normalisation, fp16 staging, ldmatrix fragments (k_norm_syrk_cols2, fp32 block).
@@ -3264,7 +3451,8 @@ static int run_pipeline_sym(const void *op, int precision, int E, int T, long V,
         }
         if (g.rowsB > 0 && use_cols)
             return launch_norm_syrk_cols(A, g.n, E, g.colsA, g.t256, g.n, eps, K + (size_t)g.a * E * E, st, half16 ? 1 : 0,
-                                         (flags & FCMA_FLAG_COLS_TMA) != 0, (flags & FCMA_FLAG_COLS_V2) != 0);
+                                         (flags & FCMA_FLAG_COLS_TMA) != 0, (flags & FCMA_FLAG_COLS_V2) != 0,
+                                         (flags & FCMA_FLAG_COLS_PAD32) != 0);
         if (g.rowsB > 0)
             return launch_norm_syrk(blockB(g, A), g.rowsB, E, g.n, 256, 65536, eps, 1, -1, 1.0f,
                                     K + (size_t)(g.a + g.n) * E * E, 0, st, (long)E * 65536, half16 ? 1 : 0);

@@ -70,6 +70,8 @@ extern "C" {
 #define FCMA_FLAG_COLS_V2        64   /* column-direction pass of the fp32 block, version 2: thread-per-row normalisation
                                          (no shuffles), fp16 staging, ldmatrix fragments -- half the instructions, the
                                          same time inside the power-capped step (profiles/README.md), not the default   */
+#define FCMA_FLAG_COLS_PAD32    128   /* E <= 16: column-direction pass with the 32-epoch (padded) kernel instead of the
+                                         16-epoch one                                                                   */
 
 int         fcma_version(void);
 const char *fcma_last_error(void);

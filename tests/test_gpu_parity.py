@@ -339,7 +339,8 @@ def test_symmetric_column_pass_all_eps(dev, E, eps):
     assert float((K - plain).abs().max()) <= (2e-3 if loose else 1e-5) * scale
     # the three column-pass kernels (default fragment-layout kernel; version 2 = thread-per-row normalisation +
     # ldmatrix; the TMA-fed variant when E % 4 == 0) and the transposed-copy variant agree to the order of the fp32 sums
-    for extra in (_lib.FLAG_COLS_V2, _lib.FLAG_COLS_TMA, _lib.FLAG_SYM_TRANSPOSED):
+    # (E <= 16 takes the 16-epoch kernel by default: FLAG_COLS_PAD32 selects the padded 32-epoch one)
+    for extra in (_lib.FLAG_COLS_PAD32, _lib.FLAG_COLS_V2, _lib.FLAG_COLS_TMA, _lib.FLAG_SYM_TRANSPOSED):
         K2 = torch.zeros((V, E, E), device=dev)
         w2 = engine.SymWorkspace(E, V, 256, dev)
         w2.buf.view(torch.float32).fill_(float("nan"))

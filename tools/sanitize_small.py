@@ -20,7 +20,7 @@ for (V, V2, T, E, eps, start, nb, rows) in ((700, None, 40, 8, 4, 77, 600, 768),
     torch.cuda.synchronize()
     print("plain ok", V, V2, E, float(K.abs().max()), flush=True)
 # symmetric pipeline: 3 passes of 256 rows + ragged tail, every variant of the column voxels' sums
-V, T, E, eps = 800, 24, 8, 4
+V, T, E, eps = 800, 24, 32, 8
 raw, labels = synthetic.make_epochs(V, T, E, seed=3)
 ep, T_e = engine.stack_epochs(raw, dev)
 op = engine.pack_epochs(ep, T_e, "fp32")
@@ -33,6 +33,14 @@ for name, fl in (("cols", 0), ("cols v2", _lib.FLAG_COLS_V2), ("tma", _lib.FLAG_
     torch.cuda.synchronize()
     ref = K if ref is None else ref
     print("sym ok", name, float((K - ref).abs().max() / ref.abs().max()), flush=True)
+# E <= 16: 16-epoch row and column kernels
+raw16, _ = synthetic.make_epochs(V, T, 12, seed=4)
+ep16, T16 = engine.stack_epochs(raw16, dev)
+op16 = engine.pack_epochs(ep16, T16, "fp32")
+K16 = torch.zeros((V, 12, 12), device=dev)
+engine.voxel_kernels_sym(op16, 0, V, 4, flags=_lib.FLAG_MASK_SELF, work=engine.SymWorkspace(12, V, 256, dev), out=K16)
+torch.cuda.synchronize()
+print("sym ok E=12 (16-epoch kernels)", float(K16.abs().max()), flush=True)
 Kc = engine.classifier_kernel(op, op, 0, V, eps)
 engine.shrink_kernels_(ref)
 acc = engine.svm_cv_precomputed(ref[:64], labels, E // eps)

@@ -2184,12 +2184,14 @@ __global__ void __launch_bounds__(32 * (32 / CPW), 1)
 // Only a __syncwarp separates the phases (a warp consumes what it staged).  The cp.async brick ring, the folds and the
 // arithmetic are those of k_norm_syrk_cols; the smem line swizzle is L & 7 (phase 1 reads 8 consecutive rows of one epoch).
 // ============================================================================================
-template <int EPS>
-__global__ void __launch_bounds__(256, 1)
+// CPW = 4: 8 warps x 4 columns (255 registers); CPW = 2: 16 warps x 2 columns (<= 128 registers, LDS.64): four warps per
+// scheduler instead of two
+template <int EPS, int CPW>
+__global__ void __launch_bounds__(32 * (32 / CPW), 1)
     k_norm_syrk_cols2(const float *__restrict__ A, long n, int E, long n2, long T256, long c0, float *K)
 {
-    constexpr int EP = 32, MT = 2, NT = 4, CPW = 4, NTHR = 256;
-    constexpr int BRICK = 65536, PPT = BRICK / 16 / NTHR, LS = NTHR / 8;     // 16 pieces per thread, 32 lines apart
+    constexpr int EP = 32, MT = 2, NT = 4, NTHR = 32 * (32 / CPW);
+    constexpr int BRICK = 65536, PPT = BRICK / 16 / NTHR, LS = NTHR / 8;     // pieces per thread, lines between them
     constexpr uint32_t STAGE_OFF = COLS_BRICKS * BRICK;                      // 8 x 4 KB fp16 staging buffers behind the bricks
     extern __shared__ __align__(1024) uint8_t cs_raw[];
     uint8_t *cs = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(cs_raw) + 1023) & ~uintptr_t(1023));
@@ -2202,8 +2204,10 @@ __global__ void __launch_bounds__(256, 1)
     const long nsteps = (n + 15) / 16;
     // phase 1: this lane's row and epoch half
     const int prow = lane & 15, phalf = lane >> 4;
-    const uint32_t rd_base = (uint32_t)((phalf * 16) * 16 + prow) * 128u + ((((uint32_t)warp) ^ ((uint32_t)prow & 7u)) << 4);
-    const uint32_t stage = brick0 + STAGE_OFF + (uint32_t)warp * 4096u;
+    const uint32_t rd_piece = CPW == 4 ? (uint32_t)warp : (uint32_t)warp >> 1;
+    const uint32_t rd_base = (uint32_t)((phalf * 16) * 16 + prow) * 128u + ((rd_piece ^ ((uint32_t)prow & 7u)) << 4) +
+                             (CPW == 4 ? 0u : ((uint32_t)warp & 1u) * 8u);
+    const uint32_t stage = brick0 + STAGE_OFF + (uint32_t)warp * (uint32_t)(CPW * 1024);
     // staged piece (column c, row, epoch block eb) lives at  c*1024 + row*64 + ((eb ^ ((row >> 1) & 3)) << 4)
     const uint32_t st_row = stage + (uint32_t)prow * 64u;
     const uint32_t st_swz = ((uint32_t)prow >> 1) & 3u;
@@ -2220,6 +2224,7 @@ __global__ void __launch_bounds__(256, 1)
         // epochs (tid >> 7) + 2 k); L & 7 is the same for all of them
         const int pf_w = tid & 7, pf_line0 = tid >> 3, pf_row = pf_line0 & 15, pf_e0 = pf_line0 >> 4;
         const int pf_src = pf_e0 * 65536 + pf_row * 256 + pf_w * 4 + jo;
+        constexpr int EPK = LS / 16;          // epochs between a thread's pieces
         const uint32_t pf_dst = brick0 + (uint32_t)pf_line0 * 128u + ((((uint32_t)pf_w) ^ ((uint32_t)pf_line0 & 7u)) << 4);
         auto prefetch = [&](long st, int b) {
             const long i0 = st * 16;
@@ -2228,8 +2233,8 @@ __global__ void __launch_bounds__(256, 1)
             const uint32_t dst0 = pf_dst + (uint32_t)b * (uint32_t)BRICK;
 #pragma unroll
             for (int k = 0; k < PPT; k++) {
-                const bool ok = row_ok && pf_e0 + 2 * k < E;
-                cp_async_16_zfill_s(dst0 + (uint32_t)(k * LS) * 128u, ok ? src0 + (size_t)k * (2 * 65536) : A, ok ? 16u : 0u);
+                const bool ok = row_ok && pf_e0 + EPK * k < E;
+                cp_async_16_zfill_s(dst0 + (uint32_t)(k * LS) * 128u, ok ? src0 + (size_t)k * (EPK * 65536) : A, ok ? 16u : 0u);
             }
         };
         for (long seg0 = 0; seg0 < nsteps; seg0 += COLS_SEG_STEPS) {
@@ -2255,12 +2260,17 @@ __global__ void __launch_bounds__(256, 1)
                 cp_async_commit();
                 const uint32_t bb = brick0 + (uint32_t)buf * (uint32_t)BRICK + rd_base;
                 // ---- phase 1: 16 epochs x 4 columns of this lane's row, 8 epochs (one staged piece) at a time
-                float2 lo[16], hi[16];     // columns (0, 1) and (2, 3) of epoch 16*phalf + e
+                float2 lo[16], hi[CPW == 4 ? 16 : 1];     // columns (0, 1) and (2, 3) of epoch 16*phalf + e
 #pragma unroll
                 for (int e = 0; e < 16; e++) {
-                    const uint4 q = lds128(bb + (uint32_t)e * 2048u);
-                    lo[e] = make_float2(__uint_as_float(q.x), __uint_as_float(q.y));
-                    hi[e] = make_float2(__uint_as_float(q.z), __uint_as_float(q.w));
+                    if constexpr (CPW == 4) {
+                        const uint4 q = lds128(bb + (uint32_t)e * 2048u);
+                        lo[e] = make_float2(__uint_as_float(q.x), __uint_as_float(q.y));
+                        hi[e] = make_float2(__uint_as_float(q.z), __uint_as_float(q.w));
+                    } else {
+                        const uint2 q = lds64(bb + (uint32_t)e * 2048u);
+                        lo[e] = make_float2(__uint_as_float(q.x), __uint_as_float(q.y));
+                    }
                 }
                 auto finish = [&](float2 msum, float2 s2sum, float2 &inv, float2 &mi) {
                     const float2 nm = ffma2(msum, splat2(-1.0f / EPS), splat2(0.f));
@@ -2276,21 +2286,26 @@ __global__ void __launch_bounds__(256, 1)
                     float2 ml = splat2(0.f), mh = splat2(0.f), ql = splat2(0.f), qh = splat2(0.f);
 #pragma unroll
                     for (int e = s0; e < s0 + SPAN; e++) {
-                        ml = fadd2(ml, lo[e]), mh = fadd2(mh, hi[e]);
-                        ql = ffma2(lo[e], lo[e], ql), qh = ffma2(hi[e], hi[e], qh);
+                        ml = fadd2(ml, lo[e]), ql = ffma2(lo[e], lo[e], ql);
+                        if constexpr (CPW == 4) mh = fadd2(mh, hi[e]), qh = ffma2(hi[e], hi[e], qh);
                     }
                     if constexpr (EPS == 32) {       // the subject's other 16 epochs live in lane ^ 16
                         ml.x += __shfl_xor_sync(0xffffffffu, ml.x, 16), ml.y += __shfl_xor_sync(0xffffffffu, ml.y, 16);
-                        mh.x += __shfl_xor_sync(0xffffffffu, mh.x, 16), mh.y += __shfl_xor_sync(0xffffffffu, mh.y, 16);
                         ql.x += __shfl_xor_sync(0xffffffffu, ql.x, 16), ql.y += __shfl_xor_sync(0xffffffffu, ql.y, 16);
-                        qh.x += __shfl_xor_sync(0xffffffffu, qh.x, 16), qh.y += __shfl_xor_sync(0xffffffffu, qh.y, 16);
+                        if constexpr (CPW == 4) {
+                            mh.x += __shfl_xor_sync(0xffffffffu, mh.x, 16), mh.y += __shfl_xor_sync(0xffffffffu, mh.y, 16);
+                            qh.x += __shfl_xor_sync(0xffffffffu, qh.x, 16), qh.y += __shfl_xor_sync(0xffffffffu, qh.y, 16);
+                        }
                     }
-                    float2 il, cl, ih, ch;
+                    float2 il, cl, ih = splat2(0.f), ch = splat2(0.f);
                     finish(ml, ql, il, cl);
-                    finish(mh, qh, ih, ch);
+                    if constexpr (CPW == 4) finish(mh, qh, ih, ch);
                     if (16 * phalf + s0 < S_eps) {       // epochs outside a complete subject stay as they are
 #pragma unroll
-                        for (int e = s0; e < s0 + SPAN; e++) lo[e] = ffma2(lo[e], il, cl), hi[e] = ffma2(hi[e], ih, ch);
+                        for (int e = s0; e < s0 + SPAN; e++) {
+                            lo[e] = ffma2(lo[e], il, cl);
+                            if constexpr (CPW == 4) hi[e] = ffma2(hi[e], ih, ch);
+                        }
                     }
                 }
                 // ---- stage: per column two 16-byte pieces (epochs 16*phalf .. +7 and +8 .. +15) of this lane's row
@@ -2302,10 +2317,12 @@ __global__ void __launch_bounds__(256, 1)
                            pack_half2_rn(lo[e0 + 4].x, lo[e0 + 5].x), pack_half2_rn(lo[e0 + 6].x, lo[e0 + 7].x));
                     sts128(piece + 1 * 1024u, pack_half2_rn(lo[e0].y, lo[e0 + 1].y), pack_half2_rn(lo[e0 + 2].y, lo[e0 + 3].y),
                            pack_half2_rn(lo[e0 + 4].y, lo[e0 + 5].y), pack_half2_rn(lo[e0 + 6].y, lo[e0 + 7].y));
-                    sts128(piece + 2 * 1024u, pack_half2_rn(hi[e0].x, hi[e0 + 1].x), pack_half2_rn(hi[e0 + 2].x, hi[e0 + 3].x),
-                           pack_half2_rn(hi[e0 + 4].x, hi[e0 + 5].x), pack_half2_rn(hi[e0 + 6].x, hi[e0 + 7].x));
-                    sts128(piece + 3 * 1024u, pack_half2_rn(hi[e0].y, hi[e0 + 1].y), pack_half2_rn(hi[e0 + 2].y, hi[e0 + 3].y),
-                           pack_half2_rn(hi[e0 + 4].y, hi[e0 + 5].y), pack_half2_rn(hi[e0 + 6].y, hi[e0 + 7].y));
+                    if constexpr (CPW == 4) {
+                        sts128(piece + 2 * 1024u, pack_half2_rn(hi[e0].x, hi[e0 + 1].x), pack_half2_rn(hi[e0 + 2].x, hi[e0 + 3].x),
+                               pack_half2_rn(hi[e0 + 4].x, hi[e0 + 5].x), pack_half2_rn(hi[e0 + 6].x, hi[e0 + 7].x));
+                        sts128(piece + 3 * 1024u, pack_half2_rn(hi[e0].y, hi[e0 + 1].y), pack_half2_rn(hi[e0 + 2].y, hi[e0 + 3].y),
+                               pack_half2_rn(hi[e0 + 4].y, hi[e0 + 5].y), pack_half2_rn(hi[e0 + 6].y, hi[e0 + 7].y));
+                    }
                 }
                 __syncwarp();
                 // ---- phase 2: K_j += Z Z^T for the warp's four columns
@@ -3002,10 +3019,24 @@ static int launch_norm_syrk_cols(const void *A, long n, int E, long n2, long T25
     // bound by what it moves, not by what it issues.  Opt-in, tested.
     if (!half_in && v2) {
         const size_t smem2 = (size_t)COLS_BRICKS * 65536 + 32768 + 1024;
+        // diagnostic build only: FCMA_COLS_V2_CPW=2 = 16 warps x 2 columns (A/B: 40.3-40.9 vs 36.6-37.3 ms per step)
+        const char *c2_env = diag_env("FCMA_COLS_V2_CPW");
+        const bool v2_cpw2 = c2_env && c2_env[0] == '2';
+#ifdef FCMA_DIAG
+#define FCMA_COLS2_CPW2(EPSV)                                                                                       \
+    CUDA_TRY(cudaFuncSetAttribute(k_norm_syrk_cols2<EPSV, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2)); \
+    k_norm_syrk_cols2<EPSV, 2><<<grid, 512, smem2, st>>>(reinterpret_cast<const float *>(A), n, E, n2, T256, c0, K);
+#else
+#define FCMA_COLS2_CPW2(EPSV)
+#endif
 #define FCMA_COLS2_CASE(EPSV)                                                                                       \
     case EPSV:                                                                                                      \
-        CUDA_TRY(cudaFuncSetAttribute(k_norm_syrk_cols2<EPSV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2)); \
-        k_norm_syrk_cols2<EPSV><<<grid, 256, smem2, st>>>(reinterpret_cast<const float *>(A), n, E, n2, T256, c0, K); \
+        if (v2_cpw2) {                                                                                              \
+            FCMA_COLS2_CPW2(EPSV)                                                                                   \
+        } else {                                                                                                    \
+            CUDA_TRY(cudaFuncSetAttribute(k_norm_syrk_cols2<EPSV, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2)); \
+            k_norm_syrk_cols2<EPSV, 4><<<grid, 256, smem2, st>>>(reinterpret_cast<const float *>(A), n, E, n2, T256, c0, K); \
+        }                                                                                                           \
         break;
         switch (eps) {
             FCMA_COLS2_CASE(1)
@@ -3017,6 +3048,7 @@ static int launch_norm_syrk_cols(const void *A, long n, int E, long n2, long T25
         default: return fail(FCMA_EINVAL, "internal: no k_norm_syrk_cols2 instantiation for eps=%d", eps);
         }
 #undef FCMA_COLS2_CASE
+#undef FCMA_COLS2_CPW2
         LAUNCH_CHECK("k_norm_syrk_cols2");
         return FCMA_OK;
     }

@@ -32,6 +32,7 @@ def step(fl):
     engine.voxel_kernels_sym(op, 0, V, eps, flags=fl, work=work, out=K)
 
 
+ref = None
 for rep in range(2):
     for name, fl, env in variants:
         for k in keys:
@@ -52,6 +53,9 @@ for rep in range(2):
         x, y, z = ctypes.c_double(0), ctypes.c_double(0), ctypes.c_double(0)
         lib.fcma_timing_read3(ctypes.byref(x), ctypes.byref(y), ctypes.byref(z))
         lib.fcma_timing_enable(0)
-        print("%-22s step %.1f ms | gemm %.1f  rows %.1f  cols %.1f ms (timed per pass)" % (name, ms, x.value, y.value, z.value), flush=True)
+        if ref is None:
+            ref = K.clone()
+        err = float((K - ref).abs().max() / ref.abs().max())
+        print("%-22s step %.1f ms | gemm %.1f  rows %.1f  cols %.1f ms (timed per pass) | max|dK|/max|K| vs first %.1e" % (name, ms, x.value, y.value, z.value, err), flush=True)
 for k in keys:
     os.environ.pop(k, None)

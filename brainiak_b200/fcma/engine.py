@@ -68,6 +68,14 @@ def stack_epochs(raw_data, device):
         if m.ndim != 2 or m.shape[1] != V:
             raise ValueError("all epochs must be 2D with the same number of voxels")
     same = all(t == T for t in T_e)
+    if all(isinstance(m, np.ndarray) and m.dtype == np.float32 and m.flags.c_contiguous for m in raw_data):
+        # the reference's contract (C-contiguous float32): copy every epoch straight from the caller's array.  A pageable
+        # source goes through the driver's staging buffers at ~10 GB/s -- 0.12 s for 1.28 GB, against 0.7 s for
+        # allocating a pinned staging tensor first (tools/h2d_probe.py)
+        dev_t = (torch.empty if same else torch.zeros)((E, T, V), dtype=torch.float32, device=device)
+        for e, m in enumerate(raw_data):
+            dev_t[e, :T_e[e]].copy_(torch.from_numpy(m))
+        return dev_t, T_e
     host = torch.empty((E, T, V), dtype=torch.float32, pin_memory=True) if same else \
         torch.zeros((E, T, V), dtype=torch.float32, pin_memory=True)
     hn = host.numpy()

@@ -1135,3 +1135,14 @@ def test_grouped_symmetric_pipeline_follows_arriving_epochs(dev):
     assert float((K1 - ref0).abs().max()) <= 1e-6 * float(ref0.abs().max())
     with pytest.raises(ValueError):
         engine.voxel_kernels_sym_grouped(ep, op2, 0, V, eps, [(0, 3), (4, 4)], [None, None])      # groups must tile [0, E)
+
+
+def test_host_entry_point_tiny_mask(dev):
+    """fcma_host_voxel_kernels_sym on a mask smaller than one 256-voxel tile (single ragged tile, one pass, no column pass)."""
+    V, T, E, eps = 70, 20, 4, 2
+    raw, _ = synthetic.make_epochs(V, T, E, seed=99)
+    Kh = engine.host_voxel_kernels_sym(raw, eps, precision="tf32x3", flags=_lib.FLAG_MASK_SELF)
+    ep, T_e = engine.stack_epochs(raw, dev)
+    op = engine.pack_epochs(ep, T_e, "tf32x3")
+    Kp = engine.voxel_kernels(op, op, 0, V, eps, flags=_lib.FLAG_MASK_SELF).cpu().numpy()
+    assert np.isfinite(Kh).all() and np.max(np.abs(Kh - Kp)) <= 1e-5 * max(np.max(np.abs(Kp)), 1.0)

@@ -493,7 +493,11 @@ def test_voxel_selection_ranking_vs_reference(dev, golden):
     raw = list(g["rawf"])
     labels = [int(x) for x in g["labelsf"]]
     clf = svm.SVC(kernel='precomputed', shrinking=False, C=1)
-    for prec in ("tf32x3", "bf16"):
+    # per-precision bounds (measured, tools/tolerance_probe.py: the fp32-faithful modes reproduce the reference's accuracies
+    # of all 128 voxels exactly -- its self column included, thanks to the exact diagonal; tf32 0.992, bf16 0.977)
+    bounds = {"fp32": (1.0, 0.0, 12), "tf32x3": (1.0, 0.0, 12), "bf16x3": (0.99, 1.0 / 16, 12),
+              "tf32": (0.97, 1.0 / 16, 12), "bf16": (0.95, 2.0 / 16, 11)}
+    for prec, (min_same, max_diff, min_top) in bounds.items():
         vs = VoxelSelector(labels, int(g["epsf"]), 4, raw, voxel_unit=32, process_num=2, precision=prec)
         res = vs.run(clf)
         acc = np.zeros(raw[0].shape[1])
@@ -504,11 +508,9 @@ def test_voxel_selection_ranking_vs_reference(dev, golden):
         # planted voxels 0..11 are the top of both rankings
         top_ref = set(int(v) for v in np.argsort(-ref, kind="stable")[:12])
         top_got = set(v for v, _ in res[:12])
-        assert len(top_ref & top_got) >= 11
-        # chance-level voxels may move by a few fold-samples because of the reference's self-column
-        # clamp noise; everything else is identical
-        assert np.mean(acc == ref) >= 0.75
-        assert np.max(np.abs(acc - ref)) <= 3.0 / 16 + 1e-9
+        assert len(top_ref & top_got) >= min_top, prec
+        assert np.mean(acc == ref) >= min_same, (prec, np.mean(acc == ref))
+        assert np.max(np.abs(acc - ref)) <= max_diff + 1e-9, (prec, np.max(np.abs(acc - ref)))
 
 
 def _create_clf_epoch(prng, idx, num_voxels):
@@ -803,7 +805,7 @@ def test_symmetric_pipeline_vs_reference_golden(dev, golden):
     acc = np.zeros(V)
     for v, a in res:
         acc[v] = a
-    assert np.mean(acc == g["acc"]) >= 0.97             # one test sample of 8 may move on a chance-level voxel
+    assert np.mean(acc == g["acc"]) >= 0.99             # measured 0.9964: 2 of 560 chance-level voxels move by one test sample of 8
     assert np.max(np.abs(acc - g["acc"])) <= 1.0 / 8 + 1e-9
 
 

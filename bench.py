@@ -910,23 +910,36 @@ def other_configs(args, lib, engine, torch, dist, dev, rank, world, local, hbm_p
         b.record()
         torch.cuda.synchronize()
         ms = a.elapsed_time(b)
+        # live per-kernel times of the classifier path: per pass one symmetric GEMM (block stored once) and the row passes
+        # over it (diagonal square + the columns right of it = the block read ONCE); no column-direction pass
+        import ctypes as _ct
+        lib.fcma_timing_enable(1)
+        Kc2 = torch.zeros((E, E), dtype=torch.float32, device=dev)
+        engine.classifier_kernel(op, op, 0, V, eps, work=work, out=Kc2)
+        torch.cuda.synchronize()
+        g_ms, s_ms = _ct.c_double(0), _ct.c_double(0)
+        npass = lib.fcma_timing_read(_ct.byref(g_ms), _ct.byref(s_ms))
+        lib.fcma_timing_enable(0)
+        code = _lib.PREC[prec]
+        blk = sum(float(min(4096, V - a)) * -(-(V - a) // 256) * 256 for a in range(0, V, 4096)) * E * 4.0     # bytes of all blocks
+        opb = sum(float(V - a) / V for a in range(0, V, 4096)) * lib.fcma_operand_bytes(code, E, T, V)
+        kern = {"k_corr_umma2": {"ms_per_step": g_ms.value, "frac_of_hbm_peak": (blk + opb) / (g_ms.value * 1e-3) / 1e9 / hbm_peak},
+                "k_norm_syrk (square + rest)": {"ms_per_step": s_ms.value, "frac_of_hbm_peak": blk / (s_ms.value * 1e-3) / 1e9 / hbm_peak}}
+        dom = max(kern, key=lambda k: kern[k]["ms_per_step"])
         # parity: K_classifier == sum of the per-voxel kernels (fp64 sum on the GPU), and sampled per-voxel kernels against
         # the reference's own (the full reference run of this config is ~0.5 h of CPU)
         Kv = torch.zeros((V, E, E), dtype=torch.float32, device=dev)
         engine.voxel_kernels_sym(op, 0, V, eps, work=work, out=Kv)
         Ksum = Kv.to(torch.float64).sum(0)
         ent = {"workload": "FCMA Classifier precomputed corr-kernel matrix V=%d T=%d E=%d eps=%d (one [E,E] kernel)" % (V, T, E, eps),
-               "n_gpus": 1, "ms_per_step": ms, "value": float(V) * V * E / (ms * 1e-3), "unit": UNIT,
-               "pipeline": "symmetric pipeline + sum over the voxel kernels (engine.classifier_kernel)",
-               "max_abs_dK_vs_fp64_sum_of_voxel_kernels": float((Kc.to(torch.float64) - Ksum).abs().max() / Ksum.abs().max())}
-        code = _lib.PREC[prec]
-        kern, summ = sym_kernel_table(lib, engine, torch, op, 0, V, V, T, E, eps, 0, work, Kv, 4096, True,
-                                      lib.fcma_operand_bytes(code, E, T, V), 3 if lib.fcma_operand_planes(code) == 2 else 1,
-                                      lib.fcma_operand_kp(code, T), hbm_peak, tf_peak, reps=1)
-        dom = max(kern, key=lambda k: kern[k]["ms"])
-        ent["roofline"] = {"kernel": dom, "bound": "hbm", "achieved": kern[dom]["hbm_gbs"], "peak": hbm_peak, "unit": "GB/s",
-                           "frac": kern[dom]["frac_of_hbm_peak"],
-                           "step_hbm_frac": summ["step_bytes"] / (summ["sum_ms"] * 1e-3) / 1e9 / hbm_peak}
+               "n_gpus": 1, "ms_per_step": ms, "value": float(V) * V * E / (ms * 1e-3), "unit": UNIT, "passes": int(npass),
+               "pipeline": "fcma_classifier_kernel_sym: symmetric GEMM + row passes only (diagonal squares once, the blocks right "
+                           "of them twice), fp64 accumulation",
+               "max_abs_dK_vs_fp64_sum_of_voxel_kernels": float((Kc.to(torch.float64) - Ksum).abs().max() / Ksum.abs().max()),
+               "kernels": kern,
+               "roofline": {"kernel": dom, "bound": "hbm", "achieved": kern[dom]["frac_of_hbm_peak"] * hbm_peak, "peak": hbm_peak,
+                            "unit": "GB/s", "frac": kern[dom]["frac_of_hbm_peak"],
+                            "step_hbm_frac": (2 * blk + opb) / ((g_ms.value + s_ms.value) * 1e-3) / 1e9 / hbm_peak}}
         if not args.no_cpu_baseline:
             host_threads()
             hostep = ep.cpu()

@@ -63,6 +63,8 @@ SIGNATURES = {
     "fcma_classifier_kernel": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_long, c_long,
                                        c_long, c_long, c_int, c_int, c_void_p, c_size_t, c_void_p,
                                        c_void_p]),
+    "fcma_classifier_kernel_sym": (c_int, [c_void_p, c_int, c_int, c_int, c_long, c_int, c_int, c_void_p, c_size_t, c_void_p,
+                                           c_void_p]),
     "fcma_shrink_kernels": (c_int, [c_void_p, c_long, c_int, c_void_p, c_void_p]),
     "fcma_svm_cv_precomputed": (c_int, [c_void_p, c_long, c_int, c_int, c_void_p, ctypes.c_double,
                                         ctypes.c_double, c_int, c_void_p, c_void_p, c_void_p]),

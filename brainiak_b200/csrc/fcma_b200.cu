@@ -1469,7 +1469,7 @@ constexpr bool F16_MMA = false;
 template <int R, int EPS, bool FISHER, int VEC>
 __global__ void __launch_bounds__(256, (R <= 4 ? 2 : 1))
     k_norm_syrk(const float *__restrict__ C, long nb, int E, long n2, long stride_i, long ld, long chunk_step,
-                long self_col0, float beta, float *K, int sum_over_rows)
+                long self_col0, float beta, float *K, int sum_over_rows, long rb_stride, double *K64)
 {
     constexpr int EP = 8 * R;
     constexpr int MT = EP / 16, NT = EP / 8;
@@ -1496,7 +1496,8 @@ __global__ void __launch_bounds__(256, (R <= 4 ? 2 : 1))
         const elem_t *Cb = reinterpret_cast<const elem_t *>(C);
         const elem_t *Ci = chunk_step == 256
                                ? Cb + (size_t)i * stride_i
-                               : Cb + (size_t)(i >> 8) * (size_t)(((n2 + 255) >> 8) * chunk_step) + (size_t)(i & 255) * stride_i;
+                               : Cb + (size_t)(i >> 8) * (size_t)(rb_stride ? rb_stride : ((n2 + 255) >> 8) * chunk_step) +
+                                     (size_t)(i & 255) * stride_i;
         const long self_col = self_col0 >= 0 ? self_col0 + i : -1;
         float acc[MT][NT][4];
 #pragma unroll
@@ -1871,7 +1872,10 @@ __global__ void __launch_bounds__(256, (R <= 4 ? 2 : 1))
             for (int idx = threadIdx.x; idx < E * E; idx += 256) {
                 const float v = kval(idx);
                 if (sum_over_rows) {
-                    atomicAdd(&K[idx], v);
+                    // one kernel for all rows (Classifier): double-precision atomics when the caller gave a fp64 accumulator
+                    // (50 000 row kernels of ~1e5 each: fp32 atomics would lose ~1e-5 of the sum)
+                    if (K64) atomicAdd(&K64[idx], (double)v);
+                    else atomicAdd(&K[idx], v);
                 } else {
                     float *dst = &Ki[idx];
                     *dst = (beta == 0.f ? 0.f : beta * *dst) + v;
@@ -2851,7 +2855,7 @@ __global__ void k_scale(float *x, long n, float s)
 
 template <int R, bool FISHER, int VEC>
 static bool dispatch_eps(int eps, dim3 grid, cudaStream_t st, const float *C, long nb, int E, long n2, long stride_i,
-                         long ld, long chunk_step, long self_col0, float beta, float *K, int sum)
+                         long ld, long chunk_step, long self_col0, float beta, float *K, int sum, long rb_stride, double *K64)
 {
     constexpr size_t smem = (VEC ? (size_t)8 * 2 * (VEC == 2 ? R : 2 * R) * 32 * sizeof(float4) : 0) +
                             (R <= 4 ? (size_t)8 * (8 * R) * (8 * R) * sizeof(float) : 0);
@@ -2860,7 +2864,7 @@ static bool dispatch_eps(int eps, dim3 grid, cudaStream_t st, const float *C, lo
         if (smem > 48 * 1024)                                                                                    \
             cudaFuncSetAttribute(k_norm_syrk<R, EPSV, FISHER, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                  (int)smem);                                                                     \
-        k_norm_syrk<R, EPSV, FISHER, VEC><<<grid, 256, smem, st>>>(C, nb, E, n2, stride_i, ld, chunk_step, self_col0, beta, K, sum); \
+        k_norm_syrk<R, EPSV, FISHER, VEC><<<grid, 256, smem, st>>>(C, nb, E, n2, stride_i, ld, chunk_step, self_col0, beta, K, sum, rb_stride, K64); \
         return true;
     switch (eps) {
         FCMA_CASE(0)
@@ -2873,7 +2877,7 @@ static bool dispatch_eps(int eps, dim3 grid, cudaStream_t st, const float *C, lo
         if constexpr (R >= 4) {      // R = 2 (E <= 16): a subject never spans 32 epochs
             if (smem > 48 * 1024)
                 cudaFuncSetAttribute(k_norm_syrk<R, 32, FISHER, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            k_norm_syrk<R, 32, FISHER, VEC><<<grid, 256, smem, st>>>(C, nb, E, n2, stride_i, ld, chunk_step, self_col0, beta, K, sum);
+            k_norm_syrk<R, 32, FISHER, VEC><<<grid, 256, smem, st>>>(C, nb, E, n2, stride_i, ld, chunk_step, self_col0, beta, K, sum, rb_stride, K64);
             return true;
         }
         return false;
@@ -2882,7 +2886,7 @@ static bool dispatch_eps(int eps, dim3 grid, cudaStream_t st, const float *C, lo
             if (smem > 48 * 1024)
                 cudaFuncSetAttribute(k_norm_syrk<R, 64, FISHER, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)smem);
-            k_norm_syrk<R, 64, FISHER, VEC><<<grid, 256, smem, st>>>(C, nb, E, n2, stride_i, ld, chunk_step, self_col0, beta, K, sum);
+            k_norm_syrk<R, 64, FISHER, VEC><<<grid, 256, smem, st>>>(C, nb, E, n2, stride_i, ld, chunk_step, self_col0, beta, K, sum, rb_stride, K64);
             return true;
         }
         return false;
@@ -2906,12 +2910,14 @@ static bool fused_supported(int E, int eps_mode)
 // (every 256x256 pair tile of the GEMM is one contiguous 256 KB run; the E tiles of one (row block, column
 // block) are adjacent): stride_i = 256, ld = 65536, chunk_step = E*65536, and i -> (i/256)*T256*chunk_step +
 // (i%256)*stride_i inside the kernel.
+// rb_stride: elements between 256-row blocks of a tiled block when the kernel is given only a column RANGE of it (0: the
+// range is the whole block); K64: optional fp64 accumulator [E][E] for sum_over_rows (then K is not touched)
 static int launch_norm_syrk(const float *C, long nb, int E, long n2, long stride_i, long ld, int eps_mode,
                             int fisher_done, long self_col0, float beta, float *K, int sum_over_rows, cudaStream_t st,
-                            long chunk_step = 256, int half_in = 0)
+                            long chunk_step = 256, int half_in = 0, long rb_stride = 0, double *K64 = nullptr)
 {
     if (!fused_supported(E, eps_mode)) return fail(FCMA_EINVAL, "internal: fused norm+syrk unsupported E=%d eps=%d", E, eps_mode);
-    if (sum_over_rows) {
+    if (sum_over_rows && !K64) {
         // K = beta*K, then atomically accumulate the per-row kernels
         k_scale<<<1, 256, 0, st>>>(K, (long)E * E, beta);
         LAUNCH_CHECK("k_scale");
@@ -2926,7 +2932,7 @@ static int launch_norm_syrk(const float *C, long nb, int E, long n2, long stride
     dim3 grid((unsigned)g);
     bool ok;
 #define FCMA_DISPATCH(RR, FI, VV) \
-    dispatch_eps<RR, FI, VV>(eps_mode, grid, st, C, nb, E, n2, stride_i, ld, chunk_step, self_col0, beta, K, sum_over_rows)
+    dispatch_eps<RR, FI, VV>(eps_mode, grid, st, C, nb, E, n2, stride_i, ld, chunk_step, self_col0, beta, K, sum_over_rows, rb_stride, K64)
     if (E <= 16 && eps_mode <= 16 && !half_in && !fisher && vec) {
         // 16 padded epochs instead of 32 (lane = 2 epochs): half the statistics and MMA work per byte of the pipelines'
         // fp32 block (BASELINE configs[1]: E = 16)
@@ -3532,6 +3538,79 @@ static int run_pipeline_sym(const void *op, int precision, int E, int T, long V,
         }
     }
     return FCMA_OK;
+}
+
+// Classifier kernel of ONE mask (a9 -> a10 -> a11, classifier.py:279-348) on the symmetric GEMM:  sum over ALL voxel pairs
+//     K = sum_i sum_j z(i,:,j) z(i,:,j)^T,   z(i,:,j) == z(j,:,i)
+// needs every pair once, so per pass  K += rowpass(diagonal square: holds (i,j) AND (j,i)) + 2 * rowpass(columns right of it)
+// -- no column-direction pass and no transposed copy at all (a third less traffic than summing the per-voxel kernels).
+// The two parts accumulate in fp64 (device atomics) and are combined at the end.
+__global__ void k_classifier_combine(const double *S, int EE, float *K)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < EE) K[idx] += (float)(S[idx] + 2.0 * S[EE + idx]);
+}
+static int run_classifier_sym(const void *op, int precision, int E, int T, long V, int eps, int flags, float *work,
+                              size_t work_bytes, float *K, cudaStream_t st)
+{
+    if (!op || !work || !K) return fail(FCMA_EINVAL, "pipeline: null pointer");
+    if (eps < 2 || !fused_supported(E, eps)) return fail(FCMA_EINVAL, "symmetric classifier kernel needs the fused path (E <= 64, power-of-two eps >= 2)");
+    const bool mask_self = (flags & FCMA_FLAG_MASK_SELF) != 0;
+    const int S_eps = (E / eps) * eps;
+    bool half16 = (flags & FCMA_FLAG_F16_INTERMEDIATE) || precision == FCMA_PREC_BF16 || precision == FCMA_PREC_TF32;
+    const size_t esz = half16 ? sizeof(__half) : sizeof(float);
+    const size_t row_bytes = fcma_work_bytes_per_row(E, V);
+    const long rows_per_pass = (long)(work_bytes / row_bytes) & ~255L;
+    if (rows_per_pass < 256) return fail(FCMA_ENOMEM, "work buffer too small for the symmetric pipeline");
+    AsyncBuf sums;
+    CUDA_TRY(sums.alloc(sizeof(double) * 2 * E * E, st));
+    CUDA_TRY(cudaMemsetAsync(sums.p, 0, sizeof(double) * 2 * E * E, st));
+    double *S = static_cast<double *>(sums.p);
+    for (long a = 0; a < V; a += rows_per_pass) {
+        const long n = V - a < rows_per_pass ? V - a : rows_per_pass;
+        const long colsA = V - a, t256 = cdiv(colsA, 256), nt = cdiv(n, 256);
+        if ((size_t)(nt * t256 * E) * 65536 * esz > work_bytes) return fail(FCMA_ENOMEM, "internal: symmetric pass does not fit the work buffer");
+        SymOut so{nullptr};
+        EventSet<3> evs;
+        if (g_timing_on) {
+            CUDA_TRY(evs.create());
+            CUDA_TRY(cudaEventRecord(evs.ev[0], st));
+        }
+        int rc = launch_corr_umma(op, op, precision, E, T, V, V, a, n, work, 4, 4, S_eps, st, t256, half16 ? 1 : 0, &so);
+        if (rc) return rc;
+        if (g_timing_on) CUDA_TRY(cudaEventRecord(evs.ev[1], st));
+        const long rb = t256 * (long)E * 65536;                       // elements between the 256-row blocks of the block
+        const long sq = nt * 256 < colsA ? nt * 256 : colsA;          // columns of the diagonal square
+        rc = launch_norm_syrk(work, n, E, sq, 256, 65536, eps, 1, mask_self ? 0 : -1, 1.0f, K, 1, st, (long)E * 65536,
+                              half16 ? 1 : 0, rb, S);
+        if (rc) return rc;
+        if (colsA > sq) {
+            const float *rest = half16 ? reinterpret_cast<const float *>(reinterpret_cast<const __half *>(work) + (size_t)nt * E * 65536)
+                                       : work + (size_t)nt * E * 65536;
+            rc = launch_norm_syrk(rest, n, E, colsA - sq, 256, 65536, eps, 1, -1, 1.0f, K, 1, st, (long)E * 65536,
+                                  half16 ? 1 : 0, rb, S + (size_t)E * E);
+            if (rc) return rc;
+        }
+        if (g_timing_on) {
+            CUDA_TRY(cudaEventRecord(evs.ev[2], st));
+            CUDA_TRY(cudaEventSynchronize(evs.ev[2]));
+            float x = 0.f, y = 0.f;
+            CUDA_TRY(cudaEventElapsedTime(&x, evs.ev[0], evs.ev[1]));
+            CUDA_TRY(cudaEventElapsedTime(&y, evs.ev[1], evs.ev[2]));
+            g_t_gemm += x, g_t_syrk += y, g_t_passes++;
+        }
+    }
+    k_classifier_combine<<<(unsigned)cdiv((long)E * E, 256), 256, 0, st>>>(S, E * E, K);
+    LAUNCH_CHECK("k_classifier_combine");
+    return FCMA_OK;
+}
+
+extern "C" int fcma_classifier_kernel_sym(const void *op, int precision, int E, int T, long V, int eps, int flags,
+                                          float *work_dev, size_t work_bytes, float *K_dev, void *stream)
+{
+    int rc = check_device();
+    if (rc) return rc;
+    return run_classifier_sym(op, precision, E, T, V, eps, flags, work_dev, work_bytes, K_dev, (cudaStream_t)stream);
 }
 
 extern "C" long fcma_sym_rows_per_pass(int precision, int E, int eps, int flags, long V, long start, size_t work_bytes)

@@ -406,18 +406,25 @@ def voxel_kernels_sym_grouped(epochs, op, start, nb, eps, groups, events, flags=
 def classifier_kernel(rows, cols, start, nb, eps, flags=0, work=None, out=None, symmetric=True):
     """a9 -> a10 -> a11: accumulates sum_i Z_i Z_i^T over rows [start, start+nb) into ``out`` [E, E].
 
-    One mask, all rows at once and a fused-path eps: the sum over voxels of the symmetric pipeline's kernels
-    (z(i, :, j) == z(j, :, i), so only the blocks on/above the diagonal are contracted)."""
+    One mask, all rows at once and a fused-path eps: the symmetric pipeline's GEMM (z(i, :, j) == z(j, :, i), so only the
+    blocks on/above the diagonal are contracted) followed by row passes only."""
     lib = _lib.load()
     _check_pair(rows, cols)
     E, V2 = rows.E, cols.V
     if (symmetric and rows is cols and start == 0 and nb == rows.V and eps > 1 and rows.V >= 512
             and sym_supported(E, eps) and not (flags & _lib.FLAG_FISHER_IN_PASS2)):
+        # one mask: every voxel pair is contracted ONCE (symmetric GEMM) and summed by row passes only -- the diagonal
+        # squares once, the blocks right of them twice (fcma_classifier_kernel_sym); no per-voxel kernels are formed
         if out is None:
             out = torch.zeros((E, E), dtype=torch.float32, device=rows.device)
-        w = work if isinstance(work, SymWorkspace) and work.buf.numel() >= 2 * 256 * lib.fcma_work_bytes_per_row(E, V2) else None
-        Kfull = voxel_kernels_sym(rows, 0, nb, eps, flags=flags, work=w)
-        out += Kfull.sum(0)
+        per_row = lib.fcma_work_bytes_per_row(E, V2)
+        if work is None or work.buf.numel() < 256 * per_row:
+            free, _ = torch.cuda.mem_get_info(rows.device)
+            nrows = max(256, min((nb + 255) // 256 * 256, (min(free // 2, 64 << 30) // per_row) // 256 * 256, 4096))
+            work = SymWorkspace(E, V2, nrows, rows.device, transposed_copy=False)
+        with torch.cuda.device(rows.device):
+            _lib.check(lib.fcma_classifier_kernel_sym(_ptr(rows.buf), _prec_code(rows.precision), E, rows.T, rows.V, int(eps),
+                                                      int(flags), _ptr(work.buf), work.buf.numel(), _ptr(out), _stream_ptr()))
         return out
     if work is None:
         work = Workspace(E, V2, Workspace.rows_for(E, V2, nb, rows.device), rows.device)

@@ -184,6 +184,12 @@ int fcma_classifier_kernel(const void *rows_op, const void *cols_op, int precisi
                            long V, long V2, long start, long nb, int eps, int flags, float *work_dev,
                            size_t work_bytes, float *K_dev, void *stream);
 
+/* The same for ONE mask (rows == columns == all V voxels, eps >= 2 a power of two, E <= 64) on the symmetric GEMM: every
+ * voxel pair is contracted once, K_dev[E][E] += sum over all pairs -- row passes only (diagonal squares once, the blocks
+ * right of them twice), fp64 accumulation on the device.  work_dev: at least 256 rows of fcma_work_bytes_per_row(E, V). */
+int fcma_classifier_kernel_sym(const void *op, int precision, int E, int T, long V, int eps, int flags,
+                               float *work_dev, size_t work_bytes, float *K_dev, void *stream);
+
 /* ---- a7 tail + a8 on the GPU ------------------------------------------------ */
 /* decimal shrink of voxelselector.py:409-412 on every [E][E] kernel, in place; digits_dev (optional,
  * int[nv]) receives len(str(int(K[0][0]))) */

@@ -828,6 +828,19 @@ def test_classifier_kernel_single_mask_uses_symmetry(dev):
     engine.classifier_kernel(op, op, 0, 400, eps, out=K2)
     engine.classifier_kernel(op, op, 400, 500, eps, out=K2)
     assert np.max(np.abs(K2.cpu().numpy() - Kp)) <= 2e-5 * np.max(np.abs(Kp))
+    # fcma_classifier_kernel_sym in several 256-row passes (diagonal squares once, the blocks right of them twice), with the
+    # self column masked, with E > 32 (no transposed copy needed here) and with the fp16 block: always the fp64 sum of the
+    # symmetric pipeline's per-voxel kernels
+    for (E2, eps2, fl) in ((16, 4, _lib.FLAG_MASK_SELF), (48, 8, 0), (24, 8, _lib.FLAG_F16_INTERMEDIATE)):
+        raw2, _ = synthetic.make_epochs(V, T, E2, seed=900 + E2)
+        ep2, T2 = engine.stack_epochs(raw2, dev)
+        op2 = engine.pack_epochs(ep2, T2, "fp32")
+        small = engine.SymWorkspace(E2, V, 256, dev, transposed_copy=False)
+        small.buf.view(torch.float32).fill_(float("nan"))
+        Kc = engine.classifier_kernel(op2, op2, 0, V, eps2, flags=fl, work=small)
+        Kv = engine.voxel_kernels_sym(op2, 0, V, eps2, flags=fl).to(torch.float64).sum(0)
+        assert torch.isfinite(Kc).all()
+        assert float((Kc.to(torch.float64) - Kv).abs().max()) <= 2e-6 * float(Kv.abs().max()), (E2, eps2, fl)
 
 
 def test_voxel_selector_symmetric_equals_plain(dev):

@@ -3784,7 +3784,8 @@ __device__ __forceinline__ void warp_argbest(double &val, int &idx, bool want_ma
 
 __global__ void __launch_bounds__(128) k_svm_cv(const float *__restrict__ K, long nv, int E, int nfolds,
                                                const SvmFold *__restrict__ folds, double C, double eps, int max_iter,
-                                               int *__restrict__ correct, int *__restrict__ iters)
+                                               int *__restrict__ correct, int *__restrict__ iters,
+                                               unsigned long long *__restrict__ dec_bits)
 {
     extern __shared__ float s_q[];   // [4 warps][nmax][nmax]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -4000,6 +4001,7 @@ __global__ void __launch_bounds__(128) k_svm_cv(const float *__restrict__ K, lon
 
     // ---- predict the held-out samples: dec = sum_k alpha_k y_k K(test, k) - rho;  dec > 0 -> class +
     int ok = 0;
+    unsigned long long bits = 0ull;   // bit t: held-out sample t falls on the side of the first (smaller-label) class
     for (int t = 0; t < fd.n_test; t++) {
         const int it = fd.test_idx[t];
         double part = 0.0;
@@ -4010,10 +4012,12 @@ __global__ void __launch_bounds__(128) k_svm_cv(const float *__restrict__ K, lon
         for (int off = 16; off > 0; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
         const bool pred_pos = (part - rho) > 0;
         ok += (pred_pos == (fd.test_pos[t] != 0)) ? 1 : 0;
+        bits |= pred_pos ? (1ull << t) : 0ull;
     }
     if (lane == 0) {
-        correct[prob] = ok;
+        if (correct) correct[prob] = ok;
         if (iters) iters[prob] = iter;
+        if (dec_bits) dec_bits[prob] = bits;
     }
 }
 
@@ -4027,14 +4031,30 @@ extern "C" int fcma_shrink_kernels(float *K_dev, long nv, int E, int *digits_dev
     return FCMA_OK;
 }
 
+static int svm_cv_impl(const float *K_dev, long nv, int E, int nfolds, const void *folds_host, double C, double tol,
+                       int max_iter, int *correct_dev, int *iters_dev, unsigned long long *bits_dev, void *stream);
 extern "C" int fcma_svm_cv_precomputed(const float *K_dev, long nv, int E, int nfolds, const void *folds_host,
                                        double C, double tol, int max_iter, int *correct_dev, int *iters_dev,
                                        void *stream)
 {
+    if (!correct_dev) return fail(FCMA_EINVAL, "fcma_svm_cv_precomputed: null output");
+    return svm_cv_impl(K_dev, nv, E, nfolds, folds_host, C, tol, max_iter, correct_dev, iters_dev, nullptr, stream);
+}
+// the same solver, returning the binary DECISIONS of every held-out sample (bit t of bits_dev[v * nproblems + p]): the
+// building block of one-vs-one multi-class cross-validation (one "fold" struct per (fold, class pair), votes on the caller's side)
+extern "C" int fcma_svm_cv_decisions(const float *K_dev, long nv, int E, int nproblems, const void *folds_host, double C,
+                                     double tol, int max_iter, unsigned long long *bits_dev, int *iters_dev, void *stream)
+{
+    if (!bits_dev) return fail(FCMA_EINVAL, "fcma_svm_cv_decisions: null output");
+    return svm_cv_impl(K_dev, nv, E, nproblems, folds_host, C, tol, max_iter, nullptr, iters_dev, bits_dev, stream);
+}
+static int svm_cv_impl(const float *K_dev, long nv, int E, int nfolds, const void *folds_host, double C, double tol,
+                       int max_iter, int *correct_dev, int *iters_dev, unsigned long long *bits_dev, void *stream)
+{
     int rc = check_device();
     if (rc) return rc;
-    if (!K_dev || !folds_host || !correct_dev || nv <= 0 || E <= 0 || E > 64 || nfolds <= 0 || nfolds > 64)
-        return fail(FCMA_EINVAL, "fcma_svm_cv_precomputed: bad arguments (E <= 64, nfolds <= 64)");
+    if (!K_dev || !folds_host || nv <= 0 || E <= 0 || E > 64 || nfolds <= 0 || nfolds > 4096)
+        return fail(FCMA_EINVAL, "fcma_svm_cv_precomputed: bad arguments (E <= 64, at most 4096 fold problems)");
     if (!(C > 0) || !(tol > 0)) return fail(FCMA_EINVAL, "fcma_svm_cv_precomputed: C and tol must be positive");
     const SvmFold *fh = reinterpret_cast<const SvmFold *>(folds_host);
     for (int f = 0; f < nfolds; f++) {
@@ -4055,7 +4075,7 @@ extern "C" int fcma_svm_cv_precomputed(const float *K_dev, long nv, int E, int n
     CUDA_TRY(cudaFuncSetAttribute(k_svm_cv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long nprob = nv * nfolds;
     k_svm_cv<<<(unsigned)cdiv(nprob, 4), 128, smem, st>>>(K_dev, nv, E, nfolds, fd, C, tol, max_iter, correct_dev,
-                                                         iters_dev);
+                                                         iters_dev, bits_dev);
     LAUNCH_CHECK("k_svm_cv");
     return FCMA_OK;
 }

@@ -535,7 +535,8 @@ def shrink_kernels_(K, return_digits=False):
 
 def svm_cv_supported(clf, labels, num_folds, E, allow_shrinking=False):
     """True if ``cross_val_score(clf, K, labels, cv=StratifiedKFold(num_folds))`` can run on the GPU:
-    binary ``SVC(kernel='precomputed')`` without class weights / probability, E <= 64.
+    ``SVC(kernel='precomputed')`` without class weights / probability / tie breaking, E <= 64; two classes, or more
+    (one-vs-one, as libsvm does) when every class is in the training part of every fold.
 
     The GPU solver restates libsvm's SMO WITHOUT the shrinking heuristic: bit-identical decisions for
     ``shrinking=False`` (what the reference's tests and examples use, tests/fcma/test_voxel_selection.py:70), the same
@@ -549,53 +550,118 @@ def svm_cv_supported(clf, labels, num_folds, E, allow_shrinking=False):
     # scikit-learn >= 1.9 uses the string 'deprecated' as the default of `probability`
     if clf.class_weight is not None or getattr(clf, 'probability', False) is True or E > 64 or num_folds > 64:
         return False
-    return len(np.unique(np.asarray(labels))) == 2
+    y = np.asarray(labels)
+    classes = np.unique(y)
+    if len(classes) == 2:
+        return True
+    if len(classes) < 2 or getattr(clf, 'break_ties', False):
+        return False
+    try:
+        make_svm_folds(y, num_folds)
+    except ValueError:
+        return False
+    return True
+
+
+class SvmFolds:
+    """Fold problems for the batched GPU solver: ``structs`` holds one _SvmFold per (fold, class pair) -- pair-major
+    inside a fold, pairs in libsvm's order (0,1), (0,2), ..., (1,2), ... -- and everything the vote needs."""
+
+    def __init__(self, structs, n_test, classes, pairs, test_labels):
+        self.structs, self.n_test, self.classes, self.pairs, self.test_labels = structs, n_test, classes, pairs, test_labels
+        self.num_folds = len(n_test)
+        self.nproblems = len(structs)
+
+    def __iter__(self):          # (structs, n_test) unpacking of the two-class form
+        return iter((self.structs, self.n_test))
 
 
 def make_svm_folds(labels, num_folds):
-    """Fold descriptions for fcma_svm_cv_precomputed from sklearn's own splitter
-    (StratifiedKFold(n_splits, shuffle=False), reference voxelselector.py:44-45)."""
+    """Fold descriptions for fcma_svm_cv_precomputed / fcma_svm_cv_decisions from sklearn's own splitter
+    (StratifiedKFold(n_splits, shuffle=False), reference voxelselector.py:44-45).  With k > 2 classes each fold becomes
+    k(k-1)/2 two-class problems (libsvm's one-vs-one: the pair (a, b), a < b, trains on the fold's samples of those two
+    classes with class a as +1 and is evaluated on ALL held-out samples of the fold)."""
     from sklearn import model_selection
     y = np.asarray(labels)
     classes = np.unique(y)
-    if len(classes) != 2:
-        raise ValueError("GPU SVM cross-validation handles two classes")
+    if len(classes) < 2:
+        raise ValueError("GPU SVM cross-validation needs at least two classes")
+    code = np.searchsorted(classes, y)
+    k = len(classes)
+    pairs = [(a, b) for a in range(k) for b in range(a + 1, k)]
     skf = model_selection.StratifiedKFold(n_splits=num_folds, shuffle=False)
-    folds = (_SvmFold * num_folds)()
-    n_test = []
+    folds = (_SvmFold * (num_folds * len(pairs)))()
+    n_test, test_labels = [], []
     for f, (tr, te) in enumerate(skf.split(np.zeros((len(y), 1)), y)):
-        pos = [int(i) for i in tr if y[i] == classes[0]]     # smaller label first = class +1
-        neg = [int(i) for i in tr if y[i] == classes[1]]
-        if not pos or not neg:
-            raise ValueError("a training fold contains a single class")
-        order = pos + neg
-        fd = folds[f]
-        fd.n_train, fd.n_pos, fd.n_test = len(order), len(pos), len(te)
-        for k, i in enumerate(order):
-            fd.train_idx[k] = i
-        for k, i in enumerate(te):
-            fd.test_idx[k] = int(i)
-            fd.test_pos[k] = 1 if y[i] == classes[0] else 0
+        if len(te) > 64:
+            raise ValueError("more than 64 held-out samples in a fold")
+        for q, (a, b) in enumerate(pairs):
+            pos = [int(i) for i in tr if code[i] == a]     # smaller label first = class +1
+            neg = [int(i) for i in tr if code[i] == b]
+            if not pos or not neg:
+                raise ValueError("a training fold misses a class")
+            order = pos + neg
+            if len(order) > 64:
+                raise ValueError("more than 64 training samples in a class pair")
+            fd = folds[f * len(pairs) + q]
+            fd.n_train, fd.n_pos, fd.n_test = len(order), len(pos), len(te)
+            for j, i in enumerate(order):
+                fd.train_idx[j] = i
+            for j, i in enumerate(te):
+                fd.test_idx[j] = int(i)
+                fd.test_pos[j] = 1 if code[i] == a else 0
         n_test.append(len(te))
-    return folds, np.asarray(n_test, dtype=np.float64)
+        test_labels.append(code[te].astype(np.int64))
+    return SvmFolds(folds, np.asarray(n_test, dtype=np.float64), classes, pairs, test_labels)
+
+
+def _ovo_vote(bits, folds):
+    """libsvm's svm_predict vote on the device: ``bits`` int64 ``[nv, nproblems]`` (bit t = held-out sample t on the side
+    of the pair's first class) -> number of correctly predicted held-out samples per (voxel, fold).  Ties go to the
+    smallest class index (the first maximum), as in libsvm."""
+    nv = bits.shape[0]
+    k, npairs = len(folds.classes), len(folds.pairs)
+    correct = torch.zeros((nv, folds.num_folds), dtype=torch.int32, device=bits.device)
+    for f in range(folds.num_folds):
+        nt = int(folds.n_test[f])
+        shifts = torch.arange(nt, device=bits.device, dtype=torch.int64)
+        votes = torch.zeros((nv, nt, k), dtype=torch.int32, device=bits.device)
+        for q, (a, b) in enumerate(folds.pairs):
+            side = ((bits[:, f * npairs + q, None] >> shifts[None, :]) & 1).to(torch.int32)   # [nv, nt]
+            votes[:, :, a] += side
+            votes[:, :, b] += 1 - side
+        # first maximum: argmax of votes * k + (k - 1 - class)
+        key = votes * k + torch.arange(k - 1, -1, -1, device=bits.device, dtype=torch.int32)[None, None, :]
+        pred = key.argmax(dim=2)
+        truth = torch.as_tensor(folds.test_labels[f], device=bits.device)
+        correct[:, f] = (pred == truth[None, :]).sum(dim=1).to(torch.int32)
+    return correct
 
 
 def svm_cv_precomputed(K, labels, num_folds, C=1.0, tol=1e-3, max_iter=-1, folds=None, return_iters=False):
     """Mean cross-validation accuracy of ``SVC(kernel='precomputed', C, tol)`` for every kernel of
     ``K`` (float32 CUDA ``[nv, E, E]``), computed by the batched GPU SMO solver.  Equivalent to
-    ``cross_val_score(clf, K[v], y=labels, cv=StratifiedKFold(num_folds)).mean()`` per voxel."""
+    ``cross_val_score(clf, K[v], y=labels, cv=StratifiedKFold(num_folds)).mean()`` per voxel; more than two classes are
+    handled one-vs-one with libsvm's vote."""
     lib = _lib.load()
     nv, E, _ = K.shape
     if folds is None:
         folds = make_svm_folds(labels, num_folds)
-    fstructs, n_test = folds
-    correct = torch.empty((nv, num_folds), dtype=torch.int32, device=K.device)
-    iters = torch.empty((nv, num_folds), dtype=torch.int32, device=K.device) if return_iters else None
+    nprob = folds.nproblems
+    cap = int(max_iter if max_iter and max_iter > 0 else 10000000)
+    iters = torch.empty((nv, nprob), dtype=torch.int32, device=K.device) if return_iters else None
     with torch.cuda.device(K.device):
-        _lib.check(lib.fcma_svm_cv_precomputed(_ptr(K), nv, E, num_folds, ctypes.cast(fstructs, ctypes.c_void_p),
-                                               float(C), float(tol), int(max_iter if max_iter and max_iter > 0 else 10000000),
-                                               _ptr(correct), _ptr(iters) if iters is not None else None,
-                                               _stream_ptr()))
-    scores = correct.cpu().numpy().astype(np.float64) / n_test[None, :]   # accuracy_score per fold
-    acc = scores.mean(axis=1)                                             # cross_val_score(...).mean()
+        if len(folds.classes) == 2:
+            correct = torch.empty((nv, nprob), dtype=torch.int32, device=K.device)
+            _lib.check(lib.fcma_svm_cv_precomputed(_ptr(K), nv, E, nprob, ctypes.cast(folds.structs, ctypes.c_void_p),
+                                                   float(C), float(tol), cap, _ptr(correct),
+                                                   _ptr(iters) if iters is not None else None, _stream_ptr()))
+        else:
+            bits = torch.empty((nv, nprob), dtype=torch.int64, device=K.device)
+            _lib.check(lib.fcma_svm_cv_decisions(_ptr(K), nv, E, nprob, ctypes.cast(folds.structs, ctypes.c_void_p),
+                                                 float(C), float(tol), cap, _ptr(bits),
+                                                 _ptr(iters) if iters is not None else None, _stream_ptr()))
+            correct = _ovo_vote(bits, folds)
+    scores = correct.cpu().numpy().astype(np.float64) / folds.n_test[None, :]   # accuracy_score per fold
+    acc = scores.mean(axis=1)                                                   # cross_val_score(...).mean()
     return (acc, iters.cpu().numpy()) if return_iters else acc

@@ -91,8 +91,9 @@ class VoxelSelector:
         (engine.voxel_kernels_sym; half the tensor work, same kernels up to fp32 summation order).  Over
         several GPUs the shards' partial kernel arrays are summed with one NCCL reduce-scatter (every rank keeps the
         rows it cross-validates).
-    gpu_cv: run the voxelwise cross validation of a binary ``SVC(kernel='precomputed', shrinking=False)`` on the GPU
-        (batched restatement of libsvm's SMO with bit-identical decisions, see engine.svm_cv_precomputed);
+    gpu_cv: run the voxelwise cross validation of an ``SVC(kernel='precomputed', shrinking=False)`` on the GPU
+        (batched restatement of libsvm's SMO with bit-identical decisions; more than two conditions one-vs-one with
+        libsvm's vote, see engine.svm_cv_precomputed);
         ``"always"`` also takes ``shrinking=True`` classifiers to the GPU (same optimum within ``tol``, an accuracy may
         differ by one test sample); ``False`` or any other classifier -> scikit-learn on the host, exactly as the
         reference (voxelselector.py:41-53)

@@ -768,6 +768,38 @@ def test_gpu_svm_cv_matches_sklearn(dev, golden):
     assert np.array_equal(got, ref)
 
 
+def test_gpu_svm_cv_multiclass_matches_sklearn(dev):
+    """More than two conditions: one-vs-one problems on the GPU solver + libsvm's vote (first maximum wins) give the
+    accuracies of sklearn.cross_val_score, exactly, including label values other than 0..k-1, unbalanced classes and
+    folds whose held-out part is not the same size."""
+    rng = RandomState(77)
+    E, nv = 36, 250
+    for k, folds, lab in ((3, 3, [e % 3 for e in range(36)]),
+                          (4, 3, [(7, 2, 11, 5)[e % 4] for e in range(36)]),
+                          (3, 4, [0] * 9 + [1] * 14 + [2] * 13)):
+        Z = rng.randn(nv, E, 120).astype(np.float32)
+        code = np.searchsorted(np.unique(lab), lab)
+        for c in range(k):
+            Z[:, code == c, 10 * c:10 * c + 10] += 0.3      # some signal: accuracies spread between chance and 1
+        K = np.einsum('vej,vfj->vef', Z, Z).astype(np.float32)
+        shrink_kernels_(K)
+        for C, tol in ((1.0, 1e-3), (0.02, 1e-3)):
+            ref = _sklearn_cv(K, lab, folds, C=C, tol=tol, shrinking=False)
+            got = engine.svm_cv_precomputed(torch.from_numpy(K).to(dev), lab, folds, C=C, tol=tol)
+            assert np.array_equal(got, ref), (k, folds, C, np.flatnonzero(got != ref)[:5])
+            assert ref.std() > 0.02                          # not a degenerate comparison
+    # and through VoxelSelector: three conditions stay on the device, same result list as the host scikit-learn loop
+    clf = svm.SVC(kernel='precomputed', shrinking=False, C=1)
+    lab3 = [e % 3 for e in range(24)]
+    assert engine.svm_cv_supported(clf, lab3, 2, 24)
+    raw = [rng.randn(40, 150).astype(np.float32) for _ in range(24)]
+    for e in range(24):
+        raw[e][:, :20] += 0.4 * rng.randn(40, 1).astype(np.float32) * (lab3[e] + 1)
+    a = VoxelSelector(lab3, 12, 2, raw, voxel_unit=64, process_num=0, gpu_cv=True).run(clf)
+    b = VoxelSelector(lab3, 12, 2, raw, voxel_unit=64, process_num=0, gpu_cv=False).run(clf)
+    assert a == b
+
+
 def test_voxel_selector_gpu_cv_equals_host_cv(dev, golden):
     g = golden("vs_mid")
     raw = list(g["rawf"])

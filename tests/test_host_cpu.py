@@ -153,15 +153,31 @@ def test_svm_fold_descriptors_follow_sklearn_splits():
         assert list(fd.test_idx[:fd.n_test]) == list(te)
         assert [bool(b) for b in fd.test_pos[:fd.n_test]] == [y[i] == 3 for i in te]
     assert ctypes.sizeof(folds[0]) == 592                    # layout of struct SvmFold in the library
+    # more than two classes: one problem per (fold, class pair), libsvm's pair order, all held-out samples in each
+    y3 = np.asarray([5, 1, 9, 1, 9, 5, 9, 5, 1, 5, 9, 1, 1, 5])
+    mc = engine.make_svm_folds(y3, 2)
+    assert list(mc.classes) == [1, 5, 9] and mc.pairs == [(0, 1), (0, 2), (1, 2)] and mc.nproblems == 6
+    skf = model_selection.StratifiedKFold(n_splits=2, shuffle=False)
+    for f, (tr, te) in enumerate(skf.split(np.zeros((len(y3), 1)), y3)):
+        for q, (a, b) in enumerate(mc.pairs):
+            fd = mc.structs[f * 3 + q]
+            pos = [i for i in tr if y3[i] == mc.classes[a]]
+            neg = [i for i in tr if y3[i] == mc.classes[b]]
+            assert list(fd.train_idx[:fd.n_train]) == pos + neg and fd.n_pos == len(pos)
+            assert list(fd.test_idx[:fd.n_test]) == list(te)
+        assert list(mc.test_labels[f]) == list(np.searchsorted(mc.classes, y3[te]))
     with pytest.raises(ValueError):
-        engine.make_svm_folds([0, 1, 2] * 4, 2)              # multi-class -> host scikit-learn path
+        engine.make_svm_folds([0] * 8, 2)                    # a single class
     clf = svm.SVC(kernel="precomputed", shrinking=False)
     assert engine.svm_cv_supported(clf, [0, 1] * 8, 4, 16)
     # scikit-learn's default shrinking=True: the GPU solver (no shrinking heuristic) is equal within tol, not bit-identical,
     # so it is opt-in (VoxelSelector(gpu_cv="always"))
     assert not engine.svm_cv_supported(svm.SVC(kernel="precomputed"), [0, 1] * 8, 4, 16)
     assert engine.svm_cv_supported(svm.SVC(kernel="precomputed"), [0, 1] * 8, 4, 16, allow_shrinking=True)
-    assert not engine.svm_cv_supported(clf, [0, 1, 2] * 4, 2, 12)
+    assert engine.svm_cv_supported(clf, [0, 1, 2] * 4, 2, 12)                    # one-vs-one on the GPU
+    assert not engine.svm_cv_supported(svm.SVC(kernel="precomputed", shrinking=False, break_ties=True,
+                                               decision_function_shape="ovr"), [0, 1, 2] * 4, 2, 12)
+    assert not engine.svm_cv_supported(clf, [0] * 12, 2, 12)
     assert not engine.svm_cv_supported(svm.SVC(kernel="linear"), [0, 1] * 8, 4, 16)
     assert not engine.svm_cv_supported(clf, [0, 1] * 40, 4, 80)
 

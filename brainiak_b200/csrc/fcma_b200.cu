@@ -3782,6 +3782,72 @@ __device__ __forceinline__ void warp_argbest(double &val, int &idx, bool want_ma
     }
 }
 
+// libsvm's analytic two-variable step with its clipping order (Solver::Solve, "update alpha[i] and alpha[j]")
+__device__ __forceinline__ void smo_pair_update(double &ai, double &aj, double yi, double yj, double QDi, double QDj,
+                                                double Qij, double Gi, double Gj, double C)
+{
+    const double TAU = 1e-12;
+    if (yi != yj) {
+        double quad = QDi + QDj + 2 * Qij;
+        if (quad <= 0) quad = TAU;
+        const double delta = (-Gi - Gj) / quad;
+        const double diff = ai - aj;
+        ai += delta;
+        aj += delta;
+        if (diff > 0) {
+            if (aj < 0) {
+                aj = 0;
+                ai = diff;
+            }
+        } else {
+            if (ai < 0) {
+                ai = 0;
+                aj = -diff;
+            }
+        }
+        if (diff > C - C) {
+            if (ai > C) {
+                ai = C;
+                aj = C - diff;
+            }
+        } else {
+            if (aj > C) {
+                aj = C;
+                ai = C + diff;
+            }
+        }
+    } else {
+        double quad = QDi + QDj - 2 * Qij;
+        if (quad <= 0) quad = TAU;
+        const double delta = (Gi - Gj) / quad;
+        const double sum = ai + aj;
+        ai -= delta;
+        aj += delta;
+        if (sum > C) {
+            if (ai > C) {
+                ai = C;
+                aj = sum - C;
+            }
+        } else {
+            if (aj < 0) {
+                aj = 0;
+                ai = sum;
+            }
+        }
+        if (sum > C) {
+            if (aj > C) {
+                aj = C;
+                ai = sum - C;
+            }
+        } else {
+            if (ai < 0) {
+                ai = 0;
+                aj = sum;
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(128) k_svm_cv(const float *__restrict__ K, long nv, int E, int nfolds,
                                                const SvmFold *__restrict__ folds, double C, double eps, int max_iter,
                                                int *__restrict__ correct, int *__restrict__ iters,
@@ -3902,66 +3968,7 @@ __global__ void __launch_bounds__(128) k_svm_cv(const float *__restrict__ K, lon
         double ai = __shfl_sync(0xffffffffu, (i >> 5) ? alpha[1] : alpha[0], i & 31);
         double aj = __shfl_sync(0xffffffffu, (j >> 5) ? alpha[1] : alpha[0], j & 31);
         const double old_ai = ai, old_aj = aj;
-        const double Qij = (double)Q[i * 64 + j];
-        if (yi != yj) {
-            double quad = QDi + QDj + 2 * Qij;
-            if (quad <= 0) quad = TAU;
-            const double delta = (-Gi - Gj) / quad;
-            const double diff = ai - aj;
-            ai += delta;
-            aj += delta;
-            if (diff > 0) {
-                if (aj < 0) {
-                    aj = 0;
-                    ai = diff;
-                }
-            } else {
-                if (ai < 0) {
-                    ai = 0;
-                    aj = -diff;
-                }
-            }
-            if (diff > C - C) {
-                if (ai > C) {
-                    ai = C;
-                    aj = C - diff;
-                }
-            } else {
-                if (aj > C) {
-                    aj = C;
-                    ai = C + diff;
-                }
-            }
-        } else {
-            double quad = QDi + QDj - 2 * Qij;
-            if (quad <= 0) quad = TAU;
-            const double delta = (Gi - Gj) / quad;
-            const double sum = ai + aj;
-            ai -= delta;
-            aj += delta;
-            if (sum > C) {
-                if (ai > C) {
-                    ai = C;
-                    aj = sum - C;
-                }
-            } else {
-                if (aj < 0) {
-                    aj = 0;
-                    ai = sum;
-                }
-            }
-            if (sum > C) {
-                if (aj > C) {
-                    aj = C;
-                    ai = sum - C;
-                }
-            } else {
-                if (ai < 0) {
-                    ai = 0;
-                    aj = sum;
-                }
-            }
-        }
+        smo_pair_update(ai, aj, yi, yj, QDi, QDj, (double)Q[i * 64 + j], Gi, Gj, C);
         const double dai = ai - old_ai, daj = aj - old_aj;
 #pragma unroll
         for (int s = 0; s < 2; s++) {
@@ -4021,6 +4028,346 @@ __global__ void __launch_bounds__(128) k_svm_cv(const float *__restrict__ K, lon
     }
 }
 
+// ---- the same solver WITH libsvm's shrinking heuristic (scikit-learn's default shrinking=True): Solver::do_shrinking,
+// be_shrunk, reconstruct_gradient, swap_index and the counter / unshrink logic of Solver::Solve restated for one warp.
+// Lanes own POSITIONS lane and lane+32 of libsvm's permuted arrays; an item's state (y, alpha, G, G_bar, QD and its
+// index `pm` in the unpermuted sub-problem = active_set[]) travels between positions through a shared staging area when
+// do_shrinking swaps; Q stays in the unpermuted order and is addressed through pm.  Working-set selection, the G update
+// and rho run over [0, active); G_bar over all n.
+__global__ void __launch_bounds__(128) k_svm_cv_shrink(const float *__restrict__ K, long nv, int E, int nfolds,
+                                                      const SvmFold *__restrict__ folds, double C, double eps,
+                                                      int max_iter, int *__restrict__ correct, int *__restrict__ iters,
+                                                      unsigned long long *__restrict__ dec_bits)
+{
+    extern __shared__ float s_q[];   // [4 warps][64][64] Q, then per warp: 4 x 64 doubles, 2 x 64 ints, 64 bytes
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long prob = (long)blockIdx.x * 4 + warp;
+    if (prob >= nv * nfolds) return;
+    const long v = prob / nfolds;
+    const int f = (int)(prob - v * nfolds);
+    const SvmFold &fd = folds[f];
+    const int n = fd.n_train;
+    const float *Kv = K + (size_t)v * E * E;
+    float *Q = s_q + (size_t)warp * 64 * 64;
+    double *stg_d = reinterpret_cast<double *>(s_q + 4 * 64 * 64) + warp * 4 * 64;
+    int *stg_i = reinterpret_cast<int *>(reinterpret_cast<double *>(s_q + 4 * 64 * 64) + 4 * 4 * 64) + warp * 2 * 64;
+    unsigned char *map =
+        reinterpret_cast<unsigned char *>(reinterpret_cast<int *>(reinterpret_cast<double *>(s_q + 4 * 64 * 64) + 4 * 4 * 64) + 4 * 2 * 64) +
+        warp * 64;
+    const double INF = __longlong_as_double(0x7ff0000000000000LL);
+    const double TAU = 1e-12;
+    const unsigned FULL = 0xffffffffu;
+
+    int pm[2];
+    double y[2], alpha[2], G[2], Gb[2], QD[2];
+#pragma unroll
+    for (int s = 0; s < 2; s++) {
+        const int k = lane + 32 * s;
+        pm[s] = k < n ? k : 0;
+        y[s] = k < fd.n_pos ? 1.0 : -1.0;
+        alpha[s] = 0.0;
+        G[s] = -1.0;   // p = -1
+        Gb[s] = 0.0;
+    }
+    for (int a = 0; a < n; a++) {
+        const int ia = fd.train_idx[a];
+        const float ya = a < fd.n_pos ? 1.f : -1.f;
+#pragma unroll
+        for (int s = 0; s < 2; s++) {
+            const int k = lane + 32 * s;
+            if (k < n) Q[a * 64 + k] = ya * (float)y[s] * Kv[(size_t)ia * E + fd.train_idx[k]];
+        }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int s = 0; s < 2; s++) {
+        const int k = lane + 32 * s;
+        const int ik = k < n ? fd.train_idx[k] : 0;
+        QD[s] = k < n ? (double)Kv[(size_t)ik * E + ik] : 0.0;
+    }
+
+    int active = n;
+    bool unshrink = false;
+    int counter = (n < 1000 ? n : 1000) + 1;
+#define AT(arr, pos) __shfl_sync(FULL, ((pos) >> 5) ? arr[1] : arr[0], (pos) & 31)
+
+    // Solver::select_working_set over [0, active); true = already optimal (libsvm returns 1)
+    auto select = [&](int &i, int &j) -> bool {
+        double Gmax = -INF;
+        i = -1;
+#pragma unroll
+        for (int s = 0; s < 2; s++) {
+            const int k = lane + 32 * s;
+            if (k >= active) continue;
+            double cand = -INF;
+            if (y[s] > 0) {
+                if (!(alpha[s] >= C)) cand = -G[s];
+            } else {
+                if (!(alpha[s] <= 0)) cand = G[s];
+            }
+            if (cand >= Gmax && cand > -INF) {
+                Gmax = cand;
+                i = k;
+            }
+        }
+        warp_argbest(Gmax, i, true);
+        j = -1;
+        if (i < 0) return true;
+        const double yi = AT(y, i), QDi = AT(QD, i);
+        const int pmi = AT(pm, i);
+        double Gmax2 = -INF, obj_min = INF;
+#pragma unroll
+        for (int s = 0; s < 2; s++) {
+            const int k = lane + 32 * s;
+            if (k >= active) continue;
+            const double Qik = (double)Q[pmi * 64 + pm[s]];
+            if (y[s] > 0) {
+                if (!(alpha[s] <= 0)) {
+                    const double gd = Gmax + G[s];
+                    if (G[s] >= Gmax2) Gmax2 = G[s];
+                    if (gd > 0) {
+                        const double quad = QDi + QD[s] - 2.0 * yi * Qik;
+                        const double obj = quad > 0 ? -(gd * gd) / quad : -(gd * gd) / TAU;
+                        if (obj <= obj_min) {
+                            j = k;
+                            obj_min = obj;
+                        }
+                    }
+                }
+            } else {
+                if (!(alpha[s] >= C)) {
+                    const double gd = Gmax - G[s];
+                    if (-G[s] >= Gmax2) Gmax2 = -G[s];
+                    if (gd > 0) {
+                        const double quad = QDi + QD[s] + 2.0 * yi * Qik;
+                        const double obj = quad > 0 ? -(gd * gd) / quad : -(gd * gd) / TAU;
+                        if (obj <= obj_min) {
+                            j = k;
+                            obj_min = obj;
+                        }
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            double o = __shfl_xor_sync(FULL, Gmax2, off);
+            Gmax2 = o > Gmax2 ? o : Gmax2;
+        }
+        warp_argbest(obj_min, j, false);
+        return (Gmax + Gmax2 < eps) || j < 0;
+    };
+
+    // Solver::reconstruct_gradient: G of the inactive positions from G_bar and the free active variables (both of libsvm's
+    // loop orders add the free variables in ascending position; they differ in which triangle of Q they read)
+    auto reconstruct = [&]() {
+        if (active == n) return;
+        int nr_free = 0;
+#pragma unroll
+        for (int s = 0; s < 2; s++) {
+            const int k = lane + 32 * s;
+            if (k >= active && k < n) G[s] = __dadd_rn(Gb[s], -1.0);
+            if (k < active && !(alpha[s] >= C) && !(alpha[s] <= 0)) ++nr_free;
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) nr_free += __shfl_xor_sync(FULL, nr_free, off);
+        const bool by_rows = (long)nr_free * n > 2L * active * (n - active);
+        for (int jj = 0; jj < active; jj++) {
+            const double a_j = AT(alpha, jj);
+            const int pm_j = AT(pm, jj);
+            if (a_j >= C || a_j <= 0) continue;
+#pragma unroll
+            for (int s = 0; s < 2; s++) {
+                const int k = lane + 32 * s;
+                if (k >= active && k < n) {
+                    const float q = by_rows ? Q[pm[s] * 64 + pm_j] : Q[pm_j * 64 + pm[s]];
+                    G[s] = __dadd_rn(G[s], __dmul_rn(a_j, (double)q));
+                }
+            }
+        }
+    };
+
+    // Solver::do_shrinking
+    auto do_shrinking = [&]() {
+        double g1 = -INF, g2 = -INF;
+#pragma unroll
+        for (int s = 0; s < 2; s++) {
+            const int k = lane + 32 * s;
+            if (k >= active) continue;
+            const bool up = alpha[s] >= C, low = alpha[s] <= 0;
+            if (y[s] > 0) {
+                if (!up && -G[s] >= g1) g1 = -G[s];
+                if (!low && G[s] >= g2) g2 = G[s];
+            } else {
+                if (!up && -G[s] >= g2) g2 = -G[s];
+                if (!low && G[s] >= g1) g1 = G[s];
+            }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const double o1 = __shfl_xor_sync(FULL, g1, off), o2 = __shfl_xor_sync(FULL, g2, off);
+            g1 = o1 > g1 ? o1 : g1;
+            g2 = o2 > g2 ? o2 : g2;
+        }
+        if (!unshrink && g1 + g2 <= eps * 10) {
+            unshrink = true;
+            reconstruct();
+            active = n;
+        }
+        bool fl[2];
+#pragma unroll
+        for (int s = 0; s < 2; s++) {
+            const int k = lane + 32 * s;
+            fl[s] = false;
+            if (k >= active) continue;
+            if (alpha[s] >= C)
+                fl[s] = y[s] > 0 ? (-G[s] > g1) : (-G[s] > g2);
+            else if (alpha[s] <= 0)
+                fl[s] = y[s] > 0 ? (G[s] > g2) : (G[s] > g1);
+        }
+        unsigned long long F = (unsigned long long)__ballot_sync(FULL, fl[0]) |
+                               ((unsigned long long)__ballot_sync(FULL, fl[1]) << 32);
+        if (F == 0ull) return;
+        map[lane] = (unsigned char)lane;
+        map[lane + 32] = (unsigned char)(lane + 32);
+        __syncwarp();
+        int act = active, swaps = 0;
+        if (lane == 0) {
+            // the serial scan of libsvm (flags travel with the items: after swap_index(i, act) position i holds the
+            // unflagged item and position act the flagged one)
+            for (int i = 0; i < act; i++)
+                if ((F >> i) & 1ull) {
+                    act--;
+                    while (act > i) {
+                        if (!((F >> act) & 1ull)) {
+                            const unsigned char t = map[i];
+                            map[i] = map[act];
+                            map[act] = t;
+                            F ^= (1ull << i) | (1ull << act);
+                            ++swaps;
+                            break;
+                        }
+                        act--;
+                    }
+                }
+        }
+        act = __shfl_sync(FULL, act, 0);
+        swaps = __shfl_sync(FULL, swaps, 0);
+        active = act;
+        if (swaps == 0) return;
+#pragma unroll
+        for (int s = 0; s < 2; s++) {
+            const int k = lane + 32 * s;
+            stg_d[k] = G[s];
+            stg_d[64 + k] = Gb[s];
+            stg_d[128 + k] = alpha[s];
+            stg_d[192 + k] = QD[s];
+            stg_i[k] = pm[s];
+            stg_i[64 + k] = y[s] > 0 ? 1 : 0;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int s = 0; s < 2; s++) {
+            const int k = lane + 32 * s;
+            if (k >= n) continue;
+            const int src = map[k];
+            G[s] = stg_d[src];
+            Gb[s] = stg_d[64 + src];
+            alpha[s] = stg_d[128 + src];
+            QD[s] = stg_d[192 + src];
+            pm[s] = stg_i[src];
+            y[s] = stg_i[64 + src] ? 1.0 : -1.0;
+        }
+        __syncwarp();
+    };
+
+    int iter = 0;
+    while (true) {
+        if (max_iter > 0 && iter >= max_iter) break;
+        if (--counter == 0) {
+            counter = n < 1000 ? n : 1000;
+            do_shrinking();
+        }
+        int i, j;
+        if (select(i, j)) {
+            reconstruct();
+            active = n;
+            if (select(i, j)) break;
+            counter = 1;   // do shrinking next iteration
+        }
+        ++iter;
+        const double yi = AT(y, i), yj = AT(y, j), QDi = AT(QD, i), QDj = AT(QD, j);
+        const double Gi = AT(G, i), Gj = AT(G, j);
+        const int pmi = AT(pm, i), pmj = AT(pm, j);
+        double ai = AT(alpha, i), aj = AT(alpha, j);
+        const double old_ai = ai, old_aj = aj;
+        smo_pair_update(ai, aj, yi, yj, QDi, QDj, (double)Q[pmi * 64 + pmj], Gi, Gj, C);
+        const double dai = ai - old_ai, daj = aj - old_aj;
+        const bool ui = old_ai >= C, uj = old_aj >= C, ui2 = ai >= C, uj2 = aj >= C;
+#pragma unroll
+        for (int s = 0; s < 2; s++) {
+            const int k = lane + 32 * s;
+            if (k >= n) continue;
+            const double qi = (double)Q[pmi * 64 + pm[s]], qj = (double)Q[pmj * 64 + pm[s]];
+            if (k < active) G[s] = __dadd_rn(G[s], __dadd_rn(__dmul_rn(qi, dai), __dmul_rn(qj, daj)));
+            if (ui != ui2) Gb[s] = ui ? __dsub_rn(Gb[s], __dmul_rn(C, qi)) : __dadd_rn(Gb[s], __dmul_rn(C, qi));
+            if (uj != uj2) Gb[s] = uj ? __dsub_rn(Gb[s], __dmul_rn(C, qj)) : __dadd_rn(Gb[s], __dmul_rn(C, qj));
+            if (k == i) alpha[s] = ai;
+            if (k == j) alpha[s] = aj;
+        }
+    }
+#undef AT
+
+    // ---- rho (calculate_rho over the active positions: all of them unless max_iter cut the loop)
+    double ub = INF, lb = -INF, sum_free = 0.0;
+    int nr_free = 0;
+#pragma unroll
+    for (int s = 0; s < 2; s++) {
+        const int k = lane + 32 * s;
+        if (k >= active) continue;
+        const double yG = y[s] * G[s];
+        if (alpha[s] >= C) {
+            if (y[s] < 0) ub = fmin(ub, yG); else lb = fmax(lb, yG);
+        } else if (alpha[s] <= 0) {
+            if (y[s] > 0) ub = fmin(ub, yG); else lb = fmax(lb, yG);
+        } else {
+            ++nr_free;
+            sum_free += yG;
+        }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        ub = fmin(ub, __shfl_xor_sync(FULL, ub, off));
+        lb = fmax(lb, __shfl_xor_sync(FULL, lb, off));
+        sum_free += __shfl_xor_sync(FULL, sum_free, off);
+        nr_free += __shfl_xor_sync(FULL, nr_free, off);
+    }
+    const double rho = nr_free > 0 ? sum_free / nr_free : (ub + lb) / 2;
+
+    int ok = 0;
+    unsigned long long bits = 0ull;
+    int idx[2];
+#pragma unroll
+    for (int s = 0; s < 2; s++) idx[s] = (lane + 32 * s) < n ? fd.train_idx[pm[s]] : 0;
+    for (int t = 0; t < fd.n_test; t++) {
+        const int it = fd.test_idx[t];
+        double part = 0.0;
+#pragma unroll
+        for (int s = 0; s < 2; s++)
+            if ((lane + 32 * s) < n && alpha[s] != 0.0) part += alpha[s] * y[s] * (double)Kv[(size_t)it * E + idx[s]];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) part += __shfl_xor_sync(FULL, part, off);
+        const bool pred_pos = (part - rho) > 0;
+        ok += (pred_pos == (fd.test_pos[t] != 0)) ? 1 : 0;
+        bits |= pred_pos ? (1ull << t) : 0ull;
+    }
+    if (lane == 0) {
+        if (correct) correct[prob] = ok;
+        if (iters) iters[prob] = iter;
+        if (dec_bits) dec_bits[prob] = bits;
+    }
+}
+
 extern "C" int fcma_shrink_kernels(float *K_dev, long nv, int E, int *digits_dev, void *stream)
 {
     int rc = check_device();
@@ -4032,24 +4379,29 @@ extern "C" int fcma_shrink_kernels(float *K_dev, long nv, int E, int *digits_dev
 }
 
 static int svm_cv_impl(const float *K_dev, long nv, int E, int nfolds, const void *folds_host, double C, double tol,
-                       int max_iter, int *correct_dev, int *iters_dev, unsigned long long *bits_dev, void *stream);
+                       int max_iter, int shrinking, int *correct_dev, int *iters_dev, unsigned long long *bits_dev,
+                       void *stream);
 extern "C" int fcma_svm_cv_precomputed(const float *K_dev, long nv, int E, int nfolds, const void *folds_host,
                                        double C, double tol, int max_iter, int *correct_dev, int *iters_dev,
                                        void *stream)
 {
     if (!correct_dev) return fail(FCMA_EINVAL, "fcma_svm_cv_precomputed: null output");
-    return svm_cv_impl(K_dev, nv, E, nfolds, folds_host, C, tol, max_iter, correct_dev, iters_dev, nullptr, stream);
+    return svm_cv_impl(K_dev, nv, E, nfolds, folds_host, C, tol, max_iter, 0, correct_dev, iters_dev, nullptr, stream);
 }
-// the same solver, returning the binary DECISIONS of every held-out sample (bit t of bits_dev[v * nproblems + p]): the
-// building block of one-vs-one multi-class cross-validation (one "fold" struct per (fold, class pair), votes on the caller's side)
-extern "C" int fcma_svm_cv_decisions(const float *K_dev, long nv, int E, int nproblems, const void *folds_host, double C,
-                                     double tol, int max_iter, unsigned long long *bits_dev, int *iters_dev, void *stream)
+// the general form: `shrinking` selects the restatement of libsvm's shrinking heuristic (scikit-learn's default); bits_dev
+// (optional) receives the binary DECISION of every held-out sample (bit t of bits_dev[v * nproblems + p]) -- the building
+// block of one-vs-one multi-class cross-validation (one "fold" struct per (fold, class pair), votes on the caller's side)
+extern "C" int fcma_svm_cv_solve(const float *K_dev, long nv, int E, int nproblems, const void *folds_host, double C,
+                                 double tol, int max_iter, int shrinking, int *correct_dev,
+                                 unsigned long long *bits_dev, int *iters_dev, void *stream)
 {
-    if (!bits_dev) return fail(FCMA_EINVAL, "fcma_svm_cv_decisions: null output");
-    return svm_cv_impl(K_dev, nv, E, nproblems, folds_host, C, tol, max_iter, nullptr, iters_dev, bits_dev, stream);
+    if (!bits_dev && !correct_dev) return fail(FCMA_EINVAL, "fcma_svm_cv_solve: no output requested");
+    return svm_cv_impl(K_dev, nv, E, nproblems, folds_host, C, tol, max_iter, shrinking, correct_dev, iters_dev, bits_dev,
+                       stream);
 }
 static int svm_cv_impl(const float *K_dev, long nv, int E, int nfolds, const void *folds_host, double C, double tol,
-                       int max_iter, int *correct_dev, int *iters_dev, unsigned long long *bits_dev, void *stream)
+                       int max_iter, int shrinking, int *correct_dev, int *iters_dev, unsigned long long *bits_dev,
+                       void *stream)
 {
     int rc = check_device();
     if (rc) return rc;
@@ -4071,9 +4423,17 @@ static int svm_cv_impl(const float *K_dev, long nv, int E, int nfolds, const voi
     CUDA_TRY(fd_buf.alloc(sizeof(SvmFold) * nfolds, st));
     SvmFold *fd = static_cast<SvmFold *>(fd_buf.p);
     CUDA_TRY(cudaMemcpyAsync(fd, fh, sizeof(SvmFold) * nfolds, cudaMemcpyHostToDevice, st));
+    const long nprob = nv * nfolds;
+    if (shrinking) {
+        const size_t smem = (size_t)4 * 64 * 64 * sizeof(float) + 4 * (4 * 64 * sizeof(double) + 2 * 64 * sizeof(int) + 64);
+        CUDA_TRY(cudaFuncSetAttribute(k_svm_cv_shrink, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_svm_cv_shrink<<<(unsigned)cdiv(nprob, 4), 128, smem, st>>>(K_dev, nv, E, nfolds, fd, C, tol, max_iter,
+                                                                    correct_dev, iters_dev, bits_dev);
+        LAUNCH_CHECK("k_svm_cv_shrink");
+        return FCMA_OK;
+    }
     const size_t smem = (size_t)4 * 64 * 64 * sizeof(float);
     CUDA_TRY(cudaFuncSetAttribute(k_svm_cv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const long nprob = nv * nfolds;
     k_svm_cv<<<(unsigned)cdiv(nprob, 4), 128, smem, st>>>(K_dev, nv, E, nfolds, fd, C, tol, max_iter, correct_dev,
                                                          iters_dev, bits_dev);
     LAUNCH_CHECK("k_svm_cv");

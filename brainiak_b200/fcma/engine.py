@@ -533,15 +533,14 @@ def shrink_kernels_(K, return_digits=False):
     return digits
 
 
-def svm_cv_supported(clf, labels, num_folds, E, allow_shrinking=False):
+def svm_cv_supported(clf, labels, num_folds, E, allow_shrinking=True):
     """True if ``cross_val_score(clf, K, labels, cv=StratifiedKFold(num_folds))`` can run on the GPU:
     ``SVC(kernel='precomputed')`` without class weights / probability / tie breaking, E <= 64; two classes, or more
     (one-vs-one, as libsvm does) when every class is in the training part of every fold.
 
-    The GPU solver restates libsvm's SMO WITHOUT the shrinking heuristic: bit-identical decisions for
-    ``shrinking=False`` (what the reference's tests and examples use, tests/fcma/test_voxel_selection.py:70), the same
-    optimum within ``tol`` for ``shrinking=True`` (scikit-learn's default) -- there an accuracy can differ by one test
-    sample, so such classifiers go to the host unless ``allow_shrinking`` (``VoxelSelector(gpu_cv="always")``)."""
+    The GPU solver restates libsvm's SMO with and without the shrinking heuristic (``clf.shrinking``; the reference's tests
+    and examples use ``shrinking=False``, tests/fcma/test_voxel_selection.py:70; scikit-learn's default is ``True``).
+    ``allow_shrinking=False`` sends ``shrinking=True`` classifiers to the host."""
     import sklearn.svm
     if not (isinstance(clf, sklearn.svm.SVC) and clf.kernel == 'precomputed'):
         return False
@@ -577,7 +576,7 @@ class SvmFolds:
 
 
 def make_svm_folds(labels, num_folds):
-    """Fold descriptions for fcma_svm_cv_precomputed / fcma_svm_cv_decisions from sklearn's own splitter
+    """Fold descriptions for fcma_svm_cv_precomputed / fcma_svm_cv_solve from sklearn's own splitter
     (StratifiedKFold(n_splits, shuffle=False), reference voxelselector.py:44-45).  With k > 2 classes each fold becomes
     k(k-1)/2 two-class problems (libsvm's one-vs-one: the pair (a, b), a < b, trains on the fold's samples of those two
     classes with class a as +1 and is evaluated on ALL held-out samples of the fold)."""
@@ -638,11 +637,12 @@ def _ovo_vote(bits, folds):
     return correct
 
 
-def svm_cv_precomputed(K, labels, num_folds, C=1.0, tol=1e-3, max_iter=-1, folds=None, return_iters=False):
-    """Mean cross-validation accuracy of ``SVC(kernel='precomputed', C, tol)`` for every kernel of
+def svm_cv_precomputed(K, labels, num_folds, C=1.0, tol=1e-3, max_iter=-1, folds=None, return_iters=False,
+                       shrinking=False):
+    """Mean cross-validation accuracy of ``SVC(kernel='precomputed', C, tol, shrinking)`` for every kernel of
     ``K`` (float32 CUDA ``[nv, E, E]``), computed by the batched GPU SMO solver.  Equivalent to
     ``cross_val_score(clf, K[v], y=labels, cv=StratifiedKFold(num_folds)).mean()`` per voxel; more than two classes are
-    handled one-vs-one with libsvm's vote."""
+    handled one-vs-one with libsvm's vote; ``shrinking`` selects the restatement of libsvm's shrinking heuristic."""
     lib = _lib.load()
     nv, E, _ = K.shape
     if folds is None:
@@ -650,17 +650,15 @@ def svm_cv_precomputed(K, labels, num_folds, C=1.0, tol=1e-3, max_iter=-1, folds
     nprob = folds.nproblems
     cap = int(max_iter if max_iter and max_iter > 0 else 10000000)
     iters = torch.empty((nv, nprob), dtype=torch.int32, device=K.device) if return_iters else None
+    two = len(folds.classes) == 2
     with torch.cuda.device(K.device):
-        if len(folds.classes) == 2:
-            correct = torch.empty((nv, nprob), dtype=torch.int32, device=K.device)
-            _lib.check(lib.fcma_svm_cv_precomputed(_ptr(K), nv, E, nprob, ctypes.cast(folds.structs, ctypes.c_void_p),
-                                                   float(C), float(tol), cap, _ptr(correct),
-                                                   _ptr(iters) if iters is not None else None, _stream_ptr()))
-        else:
-            bits = torch.empty((nv, nprob), dtype=torch.int64, device=K.device)
-            _lib.check(lib.fcma_svm_cv_decisions(_ptr(K), nv, E, nprob, ctypes.cast(folds.structs, ctypes.c_void_p),
-                                                 float(C), float(tol), cap, _ptr(bits),
-                                                 _ptr(iters) if iters is not None else None, _stream_ptr()))
+        correct = torch.empty((nv, nprob), dtype=torch.int32, device=K.device) if two else None
+        bits = None if two else torch.empty((nv, nprob), dtype=torch.int64, device=K.device)
+        _lib.check(lib.fcma_svm_cv_solve(_ptr(K), nv, E, nprob, ctypes.cast(folds.structs, ctypes.c_void_p),
+                                         float(C), float(tol), cap, 1 if shrinking else 0,
+                                         _ptr(correct) if two else None, _ptr(bits) if not two else None,
+                                         _ptr(iters) if iters is not None else None, _stream_ptr()))
+        if not two:
             correct = _ovo_vote(bits, folds)
     scores = correct.cpu().numpy().astype(np.float64) / folds.n_test[None, :]   # accuracy_score per fold
     acc = scores.mean(axis=1)                                                   # cross_val_score(...).mean()

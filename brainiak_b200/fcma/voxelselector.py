@@ -91,11 +91,10 @@ class VoxelSelector:
         (engine.voxel_kernels_sym; half the tensor work, same kernels up to fp32 summation order).  Over
         several GPUs the shards' partial kernel arrays are summed with one NCCL reduce-scatter (every rank keeps the
         rows it cross-validates).
-    gpu_cv: run the voxelwise cross validation of an ``SVC(kernel='precomputed', shrinking=False)`` on the GPU
-        (batched restatement of libsvm's SMO with bit-identical decisions; more than two conditions one-vs-one with
-        libsvm's vote, see engine.svm_cv_precomputed);
-        ``"always"`` also takes ``shrinking=True`` classifiers to the GPU (same optimum within ``tol``, an accuracy may
-        differ by one test sample); ``False`` or any other classifier -> scikit-learn on the host, exactly as the
+    gpu_cv: run the voxelwise cross validation of an ``SVC(kernel='precomputed')`` on the GPU (batched restatement of
+        libsvm's SMO, with or without its shrinking heuristic as ``clf.shrinking`` says, with the same iterations and
+        decisions as scikit-learn; more than two conditions one-vs-one with libsvm's vote, see
+        engine.svm_cv_precomputed); ``False`` or any other classifier -> scikit-learn on the host, exactly as the
         reference (voxelselector.py:41-53)
     """
 
@@ -139,7 +138,7 @@ class VoxelSelector:
         self.normalize = bool(normalize)
         self.device = device
         self.block_rows = block_rows
-        self.gpu_cv = gpu_cv if gpu_cv == "always" else bool(gpu_cv)
+        self.gpu_cv = bool(gpu_cv)
         self.symmetric = bool(symmetric)
         self._rows_op = None
         self._cols_op = None
@@ -284,7 +283,7 @@ class VoxelSelector:
             # shrink + cross validation without leaving the device
             engine.shrink_kernels_(K)
             acc = engine.svm_cv_precomputed(K, self.labels, self.num_folds, C=clf.C, tol=clf.tol,
-                                            max_iter=clf.max_iter, folds=folds)
+                                            max_iter=clf.max_iter, folds=folds, shrinking=bool(clf.shrinking))
             logger.debug('rows [%d, %d): GPU cv %.3f s', s, s + nb, time.time() - t0)
             return [(int(s + k), acc[k]) for k in range(nb)]
         kernels = K.cpu().numpy()
@@ -329,8 +328,7 @@ class VoxelSelector:
             K, k0 = mine, start
         else:
             k0 = 0
-        on_gpu = self.gpu_cv and engine.svm_cv_supported(clf, self.labels, self.num_folds, E,
-                                                         allow_shrinking=self.gpu_cv == "always")
+        on_gpu = self.gpu_cv and engine.svm_cv_supported(clf, self.labels, self.num_folds, E)
         folds = engine.make_svm_folds(self.labels, self.num_folds) if on_gpu else None
         results = []
         block = 8192
@@ -354,8 +352,7 @@ class VoxelSelector:
             if self._work is None or self._work.rows < block or isinstance(self._work, engine.SymWorkspace):
                 self._work = None
                 self._work = engine.Workspace(E, self.num_voxels2, block, rows_op.device)
-            on_gpu = self.gpu_cv and engine.svm_cv_supported(clf, self.labels, self.num_folds, E,
-                                                             allow_shrinking=self.gpu_cv == "always")
+            on_gpu = self.gpu_cv and engine.svm_cv_supported(clf, self.labels, self.num_folds, E)
             folds = engine.make_svm_folds(self.labels, self.num_folds) if on_gpu else None
             for s in range(start, start + n, block):
                 nb = min(block, start + n - s)

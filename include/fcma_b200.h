@@ -203,11 +203,14 @@ int fcma_shrink_kernels(float *K_dev, long nv, int E, int *digits_dev, void *str
 int fcma_svm_cv_precomputed(const float *K_dev, long nv, int E, int nfolds, const void *folds_host, double C,
                             double tol, int max_iter, int *correct_dev, int *iters_dev, void *stream);
 
-/* the same solver returning the binary decision of every held-out sample: bit t of bits_dev[v*nproblems + p] is set when
- * sample test_idx[t] of problem p falls on the side of the first (smaller-label) class.  One struct per (fold, class pair)
- * gives one-vs-one multi-class cross-validation (votes as in libsvm's svm_predict: first maximum wins). */
-int fcma_svm_cv_decisions(const float *K_dev, long nv, int E, int nproblems, const void *folds_host, double C,
-                          double tol, int max_iter, unsigned long long *bits_dev, int *iters_dev, void *stream);
+/* the general form of the solver.  shrinking != 0: libsvm's shrinking heuristic restated as well (do_shrinking, be_shrunk,
+ * reconstruct_gradient, the counter / unshrink logic of Solver::Solve) = scikit-learn's default SVC(shrinking=True).
+ * correct_dev and bits_dev are both optional (at least one): bit t of bits_dev[v*nproblems + p] is set when sample test_idx[t]
+ * of problem p falls on the side of the first (smaller-label) class.  One struct per (fold, class pair) gives one-vs-one
+ * multi-class cross-validation (votes as in libsvm's svm_predict: first maximum wins). */
+int fcma_svm_cv_solve(const float *K_dev, long nv, int E, int nproblems, const void *folds_host, double C, double tol,
+                      int max_iter, int shrinking, int *correct_dev, unsigned long long *bits_dev, int *iters_dev,
+                      void *stream);
 
 /* ---- a12 / a15: plain NT GEMM  C[m][n] = sum_k A[m][k]*B[n][k]  (fp32 FFMA, row-major) ---------- */
 int fcma_gemm_nt(const float *A_dev, const float *B_dev, float *C_dev, long M, long N, long K,

@@ -758,14 +758,52 @@ def test_gpu_svm_cv_matches_sklearn(dev, golden):
         got, iters = engine.svm_cv_precomputed(Kd, lab, folds, C=C, tol=tol, return_iters=True)
         assert np.array_equal(got, ref), (folds, C, tol, np.flatnonzero(got != ref)[:5])
         assert iters.max() < 100000 and iters.min() >= 1
+    # scikit-learn's default shrinking=True against the solver WITHOUT the heuristic: same optimum within tol
     ref = _sklearn_cv(K, lab, 4, C=1.0, shrinking=True)
     got = engine.svm_cv_precomputed(Kd, lab, 4, C=1.0)
     assert np.mean(got == ref) >= 0.99
+    # ... and against the restatement of the heuristic: exact
+    got = engine.svm_cv_precomputed(Kd, lab, 4, C=1.0, shrinking=True)
+    assert np.array_equal(got, ref)
     # unbalanced labels / odd fold sizes / label values other than 0,1
     lab2 = [3 if e < 14 else 7 for e in range(E)]
     ref = _sklearn_cv(K[:60], lab2, 3, C=1.0, shrinking=False)
     got = engine.svm_cv_precomputed(Kd[:60], lab2, 3, C=1.0)
     assert np.array_equal(got, ref)
+
+
+def test_gpu_svm_shrinking_follows_libsvm_iteration_by_iteration(dev):
+    """libsvm's shrinking heuristic (do_shrinking / be_shrunk / reconstruct_gradient / the counter and unshrink logic of
+    Solver::Solve) restated in k_svm_cv_shrink: on problems that need several hundred iterations -- where variables are
+    shrunk, swapped and the gradient is reconstructed -- the iteration count of EVERY problem equals scikit-learn's
+    SVC.n_iter_ and the accuracies are identical; the counts differ from the unshrunk solver's, i.e. the heuristic ran."""
+    from sklearn import model_selection
+    rng = RandomState(11)
+    heuristic_ran = False
+    for E, folds, C, T, nv in ((64, 4, 1.0, 60, 60), (48, 3, 1.0, 20, 60), (64, 2, 100.0, 30, 40)):
+        Z = rng.randn(nv, E, T).astype(np.float32)
+        lab = np.asarray([e % 2 for e in range(E)])
+        Z[:, lab == 1, :5] += 0.2
+        K = np.einsum('vej,vfj->vef', Z, Z).astype(np.float32)
+        shrink_kernels_(K)
+        Kd = torch.from_numpy(K).to(dev)
+        got, it_s = engine.svm_cv_precomputed(Kd, list(lab), folds, C=C, return_iters=True, shrinking=True)
+        _, it_n = engine.svm_cv_precomputed(Kd, list(lab), folds, C=C, return_iters=True, shrinking=False)
+        ref_it = np.zeros_like(it_s)
+        ref_acc = np.zeros(nv)
+        skf = model_selection.StratifiedKFold(n_splits=folds, shuffle=False)
+        for v in range(nv):
+            accs = []
+            for f, (tr, te) in enumerate(skf.split(np.zeros((E, 1)), lab)):
+                clf = svm.SVC(kernel="precomputed", C=C, shrinking=True)
+                clf.fit(K[v][np.ix_(tr, tr)].astype(np.float64), lab[tr])
+                ref_it[v, f] = int(np.asarray(clf.n_iter_).ravel()[0])
+                accs.append(np.mean(clf.predict(K[v][np.ix_(te, tr)].astype(np.float64)) == lab[te]))
+            ref_acc[v] = np.mean(accs)
+        assert np.array_equal(it_s, ref_it), (E, folds, C, int(np.sum(it_s != ref_it)))
+        assert np.array_equal(got, ref_acc)
+        heuristic_ran |= bool(np.any(it_s != it_n))
+    assert heuristic_ran
 
 
 def test_gpu_svm_cv_multiclass_matches_sklearn(dev):
@@ -784,9 +822,10 @@ def test_gpu_svm_cv_multiclass_matches_sklearn(dev):
         K = np.einsum('vej,vfj->vef', Z, Z).astype(np.float32)
         shrink_kernels_(K)
         for C, tol in ((1.0, 1e-3), (0.02, 1e-3)):
-            ref = _sklearn_cv(K, lab, folds, C=C, tol=tol, shrinking=False)
-            got = engine.svm_cv_precomputed(torch.from_numpy(K).to(dev), lab, folds, C=C, tol=tol)
-            assert np.array_equal(got, ref), (k, folds, C, np.flatnonzero(got != ref)[:5])
+            for shrinking in (False, True):
+                ref = _sklearn_cv(K, lab, folds, C=C, tol=tol, shrinking=shrinking)
+                got = engine.svm_cv_precomputed(torch.from_numpy(K).to(dev), lab, folds, C=C, tol=tol, shrinking=shrinking)
+                assert np.array_equal(got, ref), (k, folds, C, shrinking, np.flatnonzero(got != ref)[:5])
             assert ref.std() > 0.02                          # not a degenerate comparison
     # and through VoxelSelector: three conditions stay on the device, same result list as the host scikit-learn loop
     clf = svm.SVC(kernel='precomputed', shrinking=False, C=1)
@@ -810,6 +849,12 @@ def test_voxel_selector_gpu_cv_equals_host_cv(dev, golden):
     assert not engine.svm_cv_supported(svm.SVC(kernel='precomputed', class_weight='balanced'), labels, 4, 16)
     a = VoxelSelector(labels, int(g["epsf"]), 4, raw, voxel_unit=32, process_num=0, gpu_cv=True).run(clf)
     b = VoxelSelector(labels, int(g["epsf"]), 4, raw, voxel_unit=32, process_num=0, gpu_cv=False).run(clf)
+    assert a == b
+    # scikit-learn's default classifier (shrinking=True) stays on the device too, same result list
+    clf_d = svm.SVC(kernel='precomputed')
+    assert engine.svm_cv_supported(clf_d, labels, 4, 16)
+    a = VoxelSelector(labels, int(g["epsf"]), 4, raw, voxel_unit=32, process_num=0, gpu_cv=True).run(clf_d)
+    b = VoxelSelector(labels, int(g["epsf"]), 4, raw, voxel_unit=32, process_num=0, gpu_cv=False).run(clf_d)
     assert a == b
 
 

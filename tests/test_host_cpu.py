@@ -170,10 +170,9 @@ def test_svm_fold_descriptors_follow_sklearn_splits():
         engine.make_svm_folds([0] * 8, 2)                    # a single class
     clf = svm.SVC(kernel="precomputed", shrinking=False)
     assert engine.svm_cv_supported(clf, [0, 1] * 8, 4, 16)
-    # scikit-learn's default shrinking=True: the GPU solver (no shrinking heuristic) is equal within tol, not bit-identical,
-    # so it is opt-in (VoxelSelector(gpu_cv="always"))
-    assert not engine.svm_cv_supported(svm.SVC(kernel="precomputed"), [0, 1] * 8, 4, 16)
-    assert engine.svm_cv_supported(svm.SVC(kernel="precomputed"), [0, 1] * 8, 4, 16, allow_shrinking=True)
+    # scikit-learn's default shrinking=True: restated as well (k_svm_cv_shrink); allow_shrinking=False keeps it on the host
+    assert engine.svm_cv_supported(svm.SVC(kernel="precomputed"), [0, 1] * 8, 4, 16)
+    assert not engine.svm_cv_supported(svm.SVC(kernel="precomputed"), [0, 1] * 8, 4, 16, allow_shrinking=False)
     assert engine.svm_cv_supported(clf, [0, 1, 2] * 4, 2, 12)                    # one-vs-one on the GPU
     assert not engine.svm_cv_supported(svm.SVC(kernel="precomputed", shrinking=False, break_ties=True,
                                                decision_function_shape="ovr"), [0, 1, 2] * 4, 2, 12)

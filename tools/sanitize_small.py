@@ -46,3 +46,12 @@ engine.shrink_kernels_(ref)
 acc = engine.svm_cv_precomputed(ref[:64], labels, E // eps)
 torch.cuda.synchronize()
 print("classifier / shrink / svm cv ok", float(Kc.abs().max()), float(np.mean(acc)), flush=True)
+# the shrinking solver on problems long enough to shrink, swap and reconstruct; and the one-vs-one decisions
+rs = np.random.RandomState(3)
+Zs = rs.randn(24, 48, 20).astype(np.float32)
+Ks = torch.from_numpy(np.einsum('vej,vfj->vef', Zs, Zs).astype(np.float32)).to(dev)
+engine.shrink_kernels_(Ks)
+acc_s, it_s = engine.svm_cv_precomputed(Ks, [e % 2 for e in range(48)], 3, shrinking=True, return_iters=True)
+acc_m = engine.svm_cv_precomputed(Ks, [e % 3 for e in range(48)], 3, shrinking=True)
+torch.cuda.synchronize()
+print("svm cv with shrinking / three classes ok", float(np.mean(acc_s)), int(it_s.max()), float(np.mean(acc_m)), flush=True)

@@ -296,3 +296,27 @@ def test_epoch_groups_and_interleaved_shares_tile_the_epochs():
         for (e0, n) in epoch_groups(E, 4):
             owners = {e % W for e in range(e0, e0 + n)}
             assert len(owners) == min(W, n)
+
+
+def test_one_vs_one_vote_is_libsvm_first_maximum():
+    """engine._ovo_vote (torch ops, device-agnostic): decision bits of the k(k-1)/2 pair problems -> correct held-out samples per
+    (voxel, fold), against a plain loop that votes as libsvm's svm_predict_values does (ties: smallest class index)."""
+    import torch
+    rng = np.random.RandomState(0)
+    y = np.asarray([4, 8, 6, 2] * 5 + [2, 4])
+    folds = engine.make_svm_folds(y, 2)
+    k, npairs = len(folds.classes), len(folds.pairs)
+    assert (k, npairs, folds.nproblems) == (4, 6, 12)
+    nv = 50
+    bits = rng.randint(0, 2 ** 11, size=(nv, folds.nproblems)).astype(np.int64)
+    got = engine._ovo_vote(torch.from_numpy(bits), folds).numpy()
+    for v in range(nv):
+        for f in range(2):
+            ok = 0
+            for t in range(int(folds.n_test[f])):
+                votes = [0] * k
+                for q, (a, b) in enumerate(folds.pairs):
+                    votes[a if (bits[v, f * npairs + q] >> t) & 1 else b] += 1
+                pred = max(range(k), key=lambda c: (votes[c], -c))
+                ok += int(pred == folds.test_labels[f][t])
+            assert got[v, f] == ok

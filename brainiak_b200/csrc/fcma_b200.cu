@@ -2578,6 +2578,236 @@ __global__ void __launch_bounds__(256, 2)
 }
 
 // ============================================================================================
+// Column-direction pass for 32 < E <= 64 (fp32 block): the 64 x 64 accumulator of ONE column voxel fills a warp's registers
+// (4 x 8 MMA tiles = 128), so a CTA of 8 warps owns a strip of 8 adjacent columns -- 32 bytes of every (epoch, row) line; the
+// CTAs of neighbouring strips walk down the same rows at the same time and find the rest of the 128-byte line in L2.  A brick
+// is [64 epochs][16 rows][8 columns] = 32 KB; 4-byte cp.async scatter it into a column-major shared layout
+//     word(col, e, row) = col * 1092 + (e >> 3) * 136 + (e & 7) * 16 + row
+// (136: the eight epoch groups of a half warp's LDS.64 fall into distinct banks; 1092: the eight columns of a copying warp do),
+// so lane (g, t) of warp `col` reads its 8 epochs 8g .. 8g+7 x rows {2t, 2t+1}, {2t+8, 2t+9} with 16 conflict-free LDS.64.
+// Statistics, z-score, fragment roles and the fold are those of k_norm_syrk_cols with R = 8 epochs per lane.
+// ============================================================================================
+template <int EPS>
+__global__ void __launch_bounds__(256, 1)
+    k_norm_syrk_cols64(const float *__restrict__ A, long n, int E, long n2, long T256, long c0, float *K)
+{
+    constexpr int R = 8, EP = 64, MT = 4, NT = 8, NTHR = 256;
+    constexpr int COLW = 1092;                 // words per column of a brick
+    constexpr int BRICK = 8 * COLW * 4;        // bytes
+    extern __shared__ __align__(1024) uint8_t cs_raw[];
+    uint8_t *cs = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(cs_raw) + 127) & ~uintptr_t(127));
+    const uint32_t brick0 = smem_u32(cs);            // 3 bricks; the fold area [8 columns][64*64] fp32 (128 KB) overlays them
+    float *s_fold = reinterpret_cast<float *>(cs);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int S_eps = (E / EPS) * EPS;
+    const long nstrips = (n2 - c0 + 7) / 8;
+    const long nsteps = (n + 15) / 16;
+    // copies: thread = (column tid & 7, row (tid >> 3) & 15, epochs (tid >> 7) + 2k, k < 32)
+    const int pf_col = tid & 7, pf_row = (tid >> 3) & 15, pf_e0 = tid >> 7;
+    const uint32_t pf_dst = brick0 + (uint32_t)(pf_col * COLW + pf_e0 * 16 + pf_row) * 4u;
+    const uint32_t rd_base = (uint32_t)(warp * COLW + g * 136 + 2 * t) * 4u;
+
+    for (long strip = blockIdx.x; strip < nstrips; strip += gridDim.x) {
+        const long j0 = c0 + strip * 8;
+        const long tjx = j0 >> 8;
+        const int jo = (int)(j0 & 255);
+        const bool col_ok = j0 + pf_col < n2;
+        const bool strip_full = E == 64 && j0 + 8 <= n2;
+        auto prefetch = [&](long st, int b) {
+            const long i0 = st * 16;
+            const float *src0 = A + ((size_t)((i0 >> 8) * T256 + tjx) * E) * 65536 + (size_t)((i0 & 255) + pf_row) * 256 + jo + pf_col +
+                                (size_t)pf_e0 * 65536;
+            const uint32_t dst0 = pf_dst + (uint32_t)b * (uint32_t)BRICK;
+            if (strip_full && i0 + 16 <= n) {
+                // the common case (CTA-uniform): 32 unconditional copies off one source and one destination register
+#pragma unroll
+                for (int k = 0; k < 32; k++)
+                    cp_async_4_s(dst0 + (uint32_t)((k >> 2) * 136 + 2 * (k & 3) * 16) * 4u, src0 + (size_t)k * 131072);
+                return;
+            }
+            const bool ok0 = col_ok && i0 + pf_row < n;
+#pragma unroll 4
+            for (int k = 0; k < 32; k++) {
+                const bool ok = ok0 && pf_e0 + 2 * k < E;
+                // epoch e = pf_e0 + 2k: group k >> 2, slot pf_e0 + 2 (k & 3)
+                cp_async_4_zfill_s(dst0 + (uint32_t)((k >> 2) * 136 + 2 * (k & 3) * 16) * 4u, ok ? src0 + (size_t)k * 131072 : A,
+                                   ok ? 4u : 0u);
+            }
+        };
+        for (long seg0 = 0; seg0 < nsteps; seg0 += COLS_SEG_STEPS) {
+            const long seg1 = seg0 + COLS_SEG_STEPS < nsteps ? seg0 + COLS_SEG_STEPS : nsteps;
+            float acc[MT][NT][4];
+#pragma unroll
+            for (int a = 0; a < MT; a++)
+#pragma unroll
+                for (int b = 0; b < NT; b++)
+#pragma unroll
+                    for (int d = 0; d < 4; d++) acc[a][b][d] = 0.f;
+            int buf = 0;
+            prefetch(seg0, 0);
+            cp_async_commit();
+            if (seg0 + 1 < seg1) prefetch(seg0 + 1, 1);
+            cp_async_commit();
+            for (long st = seg0; st < seg1; st++) {
+                cp_async_wait<1>();
+                __syncthreads();
+                if (st + 2 < seg1) prefetch(st + 2, buf == 0 ? 2 : buf - 1);
+                cp_async_commit();
+                float2 lo[R], hi[R];     // rows (2t, 2t+1) and (2t+8, 2t+9) of epoch 8g + r, this warp's column
+                const uint32_t bb = brick0 + (uint32_t)buf * (uint32_t)BRICK + rd_base;
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    const uint2 q0 = lds64(bb + (uint32_t)(r * 16) * 4u);
+                    const uint2 q1 = lds64(bb + (uint32_t)(r * 16 + 8) * 4u);
+                    lo[r] = make_float2(__uint_as_float(q0.x), __uint_as_float(q0.y));
+                    hi[r] = make_float2(__uint_as_float(q1.x), __uint_as_float(q1.y));
+                }
+                auto finish = [&](float2 msum, float2 s2sum, float2 &inv, float2 &mi) {
+                    const float2 nm = ffma2(msum, splat2(-1.0f / EPS), splat2(0.f));
+                    const float2 ns2 = ffma2(s2sum, splat2(-1.0f / EPS), splat2(0.f));
+                    const float2 negvar = ffma2(nm, nm, ns2);
+                    inv.x = negvar.x >= 0.f ? 0.f : rsqrt_ftz(-negvar.x);
+                    inv.y = negvar.y >= 0.f ? 0.f : rsqrt_ftz(-negvar.y);
+                    mi = ffma2(nm, inv, splat2(0.f));
+                };
+                auto zscore = [&](float2 (&x)[R]) {
+                    if constexpr (EPS <= R) {
+                        constexpr int G = R / EPS;
+#pragma unroll
+                        for (int q = 0; q < G; q++) {
+                            float2 m = splat2(0.f), s2 = splat2(0.f);
+#pragma unroll
+                            for (int b = 0; b < EPS; b++) {
+                                m = ffma2(x[q * EPS + b], splat2(1.f), m);
+                                s2 = ffma2(x[q * EPS + b], x[q * EPS + b], s2);
+                            }
+                            float2 inv, mi;
+                            finish(m, s2, inv, mi);
+                            if (R * g + q * EPS < S_eps) {
+#pragma unroll
+                                for (int b = 0; b < EPS; b++) x[q * EPS + b] = ffma2(x[q * EPS + b], inv, mi);
+                            }
+                        }
+                    } else {
+                        constexpr int L = EPS / R;   // adjacent g-lanes per subject
+                        float2 m = splat2(0.f), s2 = splat2(0.f);
+#pragma unroll
+                        for (int r = 0; r < R; r++) {
+                            m = ffma2(x[r], splat2(1.f), m);
+                            s2 = ffma2(x[r], x[r], s2);
+                        }
+#pragma unroll
+                        for (int o = 1; o < L; o <<= 1) {
+                            m.x += __shfl_xor_sync(0xffffffffu, m.x, 4 * o);
+                            m.y += __shfl_xor_sync(0xffffffffu, m.y, 4 * o);
+                            s2.x += __shfl_xor_sync(0xffffffffu, s2.x, 4 * o);
+                            s2.y += __shfl_xor_sync(0xffffffffu, s2.y, 4 * o);
+                        }
+                        float2 inv, mi;
+                        finish(m, s2, inv, mi);
+                        if (R * g < S_eps) {
+#pragma unroll
+                            for (int r = 0; r < R; r++) x[r] = ffma2(x[r], inv, mi);
+                        }
+                    }
+                };
+                zscore(lo);
+                zscore(hi);
+                uint32_t h0[R], h1[R];
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    h0[r] = pack_half2_rn(lo[r].x, lo[r].y);
+                    h1[r] = pack_half2_rn(hi[r].x, hi[r].y);
+                }
+#pragma unroll
+                for (int mu = 0; mu < MT; mu++)
+#pragma unroll
+                    for (int nu = 0; nu < NT; nu++)
+                        mma_f16_16x8x16(acc[mu][nu], h0[2 * mu], h0[2 * mu + 1], h1[2 * mu], h1[2 * mu + 1], h0[nu], h1[nu]);
+                buf = buf == COLS_BRICKS - 1 ? 0 : buf + 1;
+            }
+            // ---- fold: registers -> smem [8 columns][64*64] -> mirrored, coalesced += on K
+            cp_async_wait<0>();
+            __syncthreads();
+            {
+                float *dstk = s_fold + (size_t)warp * (EP * EP);
+#pragma unroll
+                for (int mu = 0; mu < MT; mu++)
+#pragma unroll
+                    for (int nu = 0; nu < NT; nu++) {
+                        const int row0 = R * g + 2 * mu, row1 = row0 + 1;
+                        const int col0 = R * (2 * t) + nu, col1 = R * (2 * t + 1) + nu;
+                        dstk[row0 * EP + col0] = acc[mu][nu][0];
+                        dstk[row0 * EP + col1] = acc[mu][nu][1];
+                        dstk[row1 * EP + col0] = acc[mu][nu][2];
+                        dstk[row1 * EP + col1] = acc[mu][nu][3];
+                    }
+            }
+            __syncthreads();
+            const int EE = E * E;
+            const long ncols = n2 - j0 < 8 ? n2 - j0 : 8;
+            const int total = (int)ncols * EE;
+            float *Kst = K + (size_t)j0 * EE;
+            auto folded = [&](int idx) {
+                const int col = idx / EE, rem = idx - col * EE;
+                const int a = rem / E, b = rem - a * E;
+                const float *sk = s_fold + (size_t)col * (EP * EP);
+                return a >= b ? sk[a * EP + b] : sk[b * EP + a];
+            };
+            if (E == 64 && ((reinterpret_cast<uintptr_t>(Kst) & 15) == 0)) {
+                // 16-byte read-modify-write, 8 independent loads in flight per thread; entry (a, b) of column `col`
+                float4 *K4 = reinterpret_cast<float4 *>(Kst);
+                const int total4 = total >> 2;
+                auto folded4 = [&](int i4) {
+                    const int col = i4 >> 10, a = (i4 >> 4) & 63, b = (i4 & 15) * 4;
+                    const float *sk = s_fold + (size_t)col * (EP * EP);
+                    float4 r;
+                    r.x = a >= b ? sk[a * EP + b] : sk[b * EP + a];
+                    r.y = a >= b + 1 ? sk[a * EP + b + 1] : sk[(b + 1) * EP + a];
+                    r.z = a >= b + 2 ? sk[a * EP + b + 2] : sk[(b + 2) * EP + a];
+                    r.w = a >= b + 3 ? sk[a * EP + b + 3] : sk[(b + 3) * EP + a];
+                    return r;
+                };
+                for (int base = tid; base < total4; base += NTHR * 8) {
+                    float4 old[8];
+#pragma unroll
+                    for (int u = 0; u < 8; u++) {
+                        const int i4 = base + u * NTHR;
+                        if (i4 < total4) old[u] = K4[i4];
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; u++) {
+                        const int i4 = base + u * NTHR;
+                        if (i4 < total4) {
+                            const float4 f = folded4(i4);
+                            float4 o = old[u];
+                            o.x += f.x, o.y += f.y, o.z += f.z, o.w += f.w;
+                            K4[i4] = o;
+                        }
+                    }
+                }
+            } else {
+                for (int base = tid; base < total; base += NTHR * 8) {
+                    float old[8];
+#pragma unroll
+                    for (int u = 0; u < 8; u++) {
+                        const int i1 = base + u * NTHR;
+                        if (i1 < total) old[u] = Kst[i1];
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; u++) {
+                        const int i1 = base + u * NTHR;
+                        if (i1 < total) Kst[i1] = old[u] + folded(i1);
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// ============================================================================================
 // Column-direction pass, TMA version (FCMA_FLAG_COLS_TMA, needs E % 4 == 0): same arithmetic as k_norm_syrk_cols, but
 //   * a brick [32 epochs][16 rows][32 columns] arrives through ONE 5-D bulk tensor copy (UTMALDG) issued by one elected
 //     lane -- the 4096 LDGSTS per brick (8 LSU cycles each, the same port the LDS reads need) and their address
@@ -2959,11 +3189,38 @@ static int launch_norm_syrk(const float *C, long nb, int E, long n2, long stride
 }
 
 // column-direction pass over a tiled fp32 block (k_norm_syrk_cols): K[j] += ... for block columns [c0, n2)
-static bool cols_supported(int E, int eps) { return E <= 32 && eps >= 1 && eps <= 32 && (eps & (eps - 1)) == 0; }
+static bool cols_supported(int E, int eps)
+{
+    return E <= 64 && eps >= 1 && eps <= (E <= 32 ? 32 : 64) && (eps & (eps - 1)) == 0;
+}
 static int launch_norm_syrk_cols(const void *A, long n, int E, long n2, long T256, long c0, int eps, float *K,
                                  cudaStream_t st, int half_in = 0, bool use_tma = false, bool v2 = false, bool pad32 = false)
 {
     if (!cols_supported(E, eps) || (c0 & 31) || c0 >= n2) return fail(FCMA_EINVAL, "internal: column pass unsupported E=%d eps=%d c0=%ld", E, eps, c0);
+    if (E > 32) {   // 32 < E <= 64, fp32 block: one column per warp, 8-column strips (k_norm_syrk_cols64)
+        if (half_in) return fail(FCMA_EINVAL, "internal: no column pass over an fp16 block for E=%d", E);
+        const long nstrips8 = cdiv(n2 - c0, 8);
+        const unsigned grid64 = (unsigned)(nstrips8 < g_sm_count ? nstrips8 : g_sm_count);
+        const size_t smem64 = (size_t)8 * 64 * 64 * sizeof(float) + 128;   // the fold area; the 3 bricks (102 KB) lie inside it
+#define FCMA_COLS64_CASE(EPSV)                                                                                      \
+    case EPSV:                                                                                                      \
+        CUDA_TRY(cudaFuncSetAttribute(k_norm_syrk_cols64<EPSV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem64)); \
+        k_norm_syrk_cols64<EPSV><<<grid64, 256, smem64, st>>>(reinterpret_cast<const float *>(A), n, E, n2, T256, c0, K); \
+        break;
+        switch (eps) {
+            FCMA_COLS64_CASE(1)
+            FCMA_COLS64_CASE(2)
+            FCMA_COLS64_CASE(4)
+            FCMA_COLS64_CASE(8)
+            FCMA_COLS64_CASE(16)
+            FCMA_COLS64_CASE(32)
+            FCMA_COLS64_CASE(64)
+        default: return fail(FCMA_EINVAL, "internal: no k_norm_syrk_cols64 instantiation for eps=%d", eps);
+        }
+#undef FCMA_COLS64_CASE
+        LAUNCH_CHECK("k_norm_syrk_cols64");
+        return FCMA_OK;
+    }
     const long nstrips = cdiv(n2 - c0, 32);
     const unsigned grid = (unsigned)(nstrips < g_sm_count ? nstrips : g_sm_count);
     // FCMA_FLAG_COLS_TMA: TMA-fed bricks + mbarrier ring (k_norm_syrk_cols_tma) when the block can be described to TMA (E a
@@ -3401,6 +3658,9 @@ static bool sym_uses_cols(int precision, int E, int eps, int flags)
         const char *sh = diag_env("FCMA_SYM_COLS_F16");
         if (sh && sh[0] == '0') return false;
     }
+    // 32 < E <= 64: the column kernel (fp32 block only) is opt-in -- 4 % slower than the transposed copy + row pass at
+    // V = 40 000, E = 64 (profiles/r2_e64_column_pass.txt); it halves the scratch per block row
+    if (E > 32 && (half16 || !(flags & FCMA_FLAG_COLS_WIDE))) return false;
     return cols_supported(E, eps);
 }
 extern "C" int fcma_sym_uses_column_pass(int precision, int E, int eps, int flags)

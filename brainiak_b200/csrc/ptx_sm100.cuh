@@ -240,6 +240,17 @@ __device__ __forceinline__ void cp_async_16_zfill_s_l2_256(uint32_t smem_dst, co
 {
     asm volatile("cp.async.cg.shared.global.L2::256B [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gsrc), "r"(src_bytes) : "memory");
 }
+// 4-byte copy (cp.async.ca; zero-filled when src_bytes == 0): scatters single words, used where the shared layout is a
+// transpose of the global one (k_norm_syrk_cols64)
+__device__ __forceinline__ void cp_async_4_zfill_s(uint32_t smem_dst, const void *gsrc, uint32_t src_bytes)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_dst), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+// unconditional 4-byte copy
+__device__ __forceinline__ void cp_async_4_s(uint32_t smem_dst, const void *gsrc)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit()
 {
     asm volatile("cp.async.commit_group;" ::: "memory");

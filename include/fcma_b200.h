@@ -63,7 +63,7 @@ extern "C" {
  * can compare them; the library never reads the environment */
 #define FCMA_FLAG_STRIDED_BLOCK   8   /* fused pipelines: strided [nb][E][ld] correlation block instead of the tiled one */
 #define FCMA_FLAG_SYM_TRANSPOSED 16   /* symmetric pipeline: store a transposed copy of every block + row pass over it
-                                         instead of the column-direction pass (what E > 32 always does)              */
+                                         instead of the column-direction pass (the default for E > 32)               */
 #define FCMA_FLAG_COLS_TMA       32   /* column-direction pass fed by 5-D TMA bricks + an mbarrier ring instead of cp.async +
                                          block barriers (needs E % 4 == 0; measured 5-8 % slower inside the power-capped
                                          step, profiles/README.md, so it is not the default)                          */
@@ -72,6 +72,10 @@ extern "C" {
                                          same time inside the power-capped step (profiles/README.md), not the default   */
 #define FCMA_FLAG_COLS_PAD32    128   /* E <= 16: column-direction pass with the 32-epoch (padded) kernel instead of the
                                          16-epoch one                                                                   */
+#define FCMA_FLAG_COLS_WIDE     256   /* 32 < E <= 64, fp32 block: column-direction pass (k_norm_syrk_cols64: one column voxel
+                                         per warp, 8-column strips) instead of the transposed copy: half the scratch per block
+                                         row, but 4 % slower at V = 40 000, E = 64 (profiles/r2_e64_column_pass.txt), so it
+                                         is not the default                                                             */
 
 int         fcma_version(void);
 const char *fcma_last_error(void);

@@ -353,6 +353,51 @@ def test_symmetric_column_pass_all_eps(dev, E, eps):
         assert np.max(np.abs(K[s0:s0 + 30].cpu().numpy() - Kref)) <= tol
 
 
+@pytest.mark.parametrize("E,eps,rows", [(64, 1, 256), (64, 2, 256), (64, 4, 256), (64, 8, 256), (64, 16, 256), (64, 32, 256),
+                                        (64, 64, 256), (48, 16, 256), (40, 8, 256), (33, 1, 256), (36, 4, 256), (64, 8, 2048)])
+def test_symmetric_column_pass_wide(dev, E, eps, rows):
+    """32 < E <= 64: the 64-epoch column kernel (k_norm_syrk_cols64: one column voxel per warp, 8-column strips, bricks
+    scattered column-major by 4-byte cp.async) for every eps instantiation, epoch counts that are not multiples of 8 or 4,
+    trailing epochs outside a complete subject, a ragged last strip (V % 8 = 4), and a 2048-row pass that folds the
+    accumulators twice: equal to the plain pipeline, to the transposed-copy variant and to the oracle."""
+    V, T = (1300, 24) if rows == 256 else (2604, 20)
+    raw, _ = synthetic.make_epochs(V, T, E, seed=2000 + 41 * E + eps)
+    ep, T_e = engine.stack_epochs(raw, dev)
+    op = engine.pack_epochs(ep, T_e, "fp32")
+    wide = _lib.FLAG_COLS_WIDE
+    assert _lib.load().fcma_sym_uses_column_pass(_lib.PREC[op.precision], E, eps, 0) == 0      # opt-in (4 % slower at scale)
+    assert _lib.load().fcma_sym_uses_column_pass(_lib.PREC[op.precision], E, eps, wide) == 1
+    assert _lib.load().fcma_sym_uses_column_pass(_lib.PREC[op.precision], E, eps, wide | _lib.FLAG_F16_INTERMEDIATE) == 0
+    fl = _lib.FLAG_MASK_SELF
+    plain = engine.voxel_kernels(op, op, 0, V, eps, flags=fl)
+    K = torch.zeros((V, E, E), device=dev)
+    work = engine.Workspace(E, V, rows, dev)
+    work.buf.view(torch.float32).fill_(float("nan"))
+    engine.voxel_kernels_sym(op, 0, V, eps, flags=fl | wide, work=work, out=K)
+    scale = max(float(plain.abs().max()), float(V))
+    loose = eps <= 2
+    assert torch.isfinite(K).all()
+    assert float((K - K.transpose(1, 2)).abs().max()) == 0.0
+    assert float((K - plain).abs().max()) <= (2e-3 if loose else 1e-5) * scale
+    K2 = torch.zeros((V, E, E), device=dev)
+    w2 = engine.SymWorkspace(E, V, rows, dev)
+    w2.buf.view(torch.float32).fill_(float("nan"))
+    engine.voxel_kernels_sym(op, 0, V, eps, flags=fl, work=w2, out=K2)          # the default: transposed copy + row pass
+    assert float((K2 - K).abs().max()) <= (2e-3 if loose else 1e-5) * scale
+    for s0 in (0, 700, V - 30):
+        _, z, _ = orc.voxel_block(raw, None, s0, 30, eps, shrink=False)
+        Kref = orc.kernel_matrices(zero_self(z, s0), f64=True)
+        if loose:
+            # eps <= 2: z = sign(x1 - x2) -- and where fp32 E[x^2] - m^2 of two near-equal Fisher values cancels, 0 or a huge
+            # value, in the reference as on the GPU but not the same one (tools/r2_wide_eps_probe.py: a single such pair moves a
+            # diagonal entry by 40 .. 500 of V = 1300): compare all but the few entries such pairs touch
+            d = np.abs(K[s0:s0 + 30].cpu().numpy() - Kref)
+            assert np.mean(d > 1e-2 * float(V)) < 0.02
+            continue
+        tol = k_tol(V) * max(np.max(np.abs(Kref)), float(V))
+        assert np.max(np.abs(K[s0:s0 + 30].cpu().numpy() - Kref)) <= tol
+
+
 @pytest.mark.parametrize("prec,flag", [("fp32", True), ("bf16", False)])
 def test_symmetric_fp16_block_column_pass(dev, prec, flag):
     """fp16 Fisher-z block (opt-in flag, or implied by the single-product operand modes): the symmetric pipeline's column

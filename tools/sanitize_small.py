@@ -41,6 +41,14 @@ K16 = torch.zeros((V, 12, 12), device=dev)
 engine.voxel_kernels_sym(op16, 0, V, 4, flags=_lib.FLAG_MASK_SELF, work=engine.SymWorkspace(12, V, 256, dev), out=K16)
 torch.cuda.synchronize()
 print("sym ok E=12 (16-epoch kernels)", float(K16.abs().max()), flush=True)
+# 32 < E <= 64: the 64-epoch column kernel (8-column strips, ragged last strip: 812 % 8 = 4)
+raw40, _ = synthetic.make_epochs(812, 24, 40, seed=5)
+ep40, T40 = engine.stack_epochs(raw40, dev)
+op40 = engine.pack_epochs(ep40, T40, "fp32")
+K40 = torch.zeros((812, 40, 40), device=dev)
+engine.voxel_kernels_sym(op40, 0, 812, 8, flags=_lib.FLAG_MASK_SELF | _lib.FLAG_COLS_WIDE, work=engine.Workspace(40, 812, 256, dev), out=K40)
+torch.cuda.synchronize()
+print("sym ok E=40 (64-epoch column kernel)", float(K40.abs().max()), flush=True)
 Kc = engine.classifier_kernel(op, op, 0, V, eps)
 engine.shrink_kernels_(ref)
 acc = engine.svm_cv_precomputed(ref[:64], labels, E // eps)

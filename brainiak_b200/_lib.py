@@ -21,6 +21,7 @@ FLAG_STRIDED_BLOCK = 8      # strided [nb][E][ld] correlation block instead of t
 FLAG_SYM_TRANSPOSED = 16    # symmetric pipeline: transposed copy + row pass instead of the column-direction pass
 FLAG_COLS_V2 = 64           # column-direction pass, version 2 (thread-per-row normalisation + ldmatrix); not the default
 FLAG_COLS_PAD32 = 128       # E <= 16: the padded 32-epoch column kernel instead of the 16-epoch one
+FLAG_COLS_UMMA = 512        # E <= 32, eps <= 8: column pass with the SYRK on tcgen05 (accumulators in tensor memory)
 FLAG_COLS_WIDE = 256        # 32 < E <= 64: column pass over the block (k_norm_syrk_cols64) instead of the transposed copy
 FLAG_COLS_TMA = 32          # column-direction pass fed by TMA bricks + mbarrier ring instead of cp.async (E % 4 == 0)
 

@@ -2808,6 +2808,202 @@ __global__ void __launch_bounds__(256, 1)
 }
 
 // ============================================================================================
+// Column-direction pass with the SYRK on tcgen05 (FCMA_FLAG_COLS_UMMA; E <= 32, eps <= 8, fp32 block).
+// The mma.sync kernels above keep a column voxel's E x E accumulator in registers, which caps them at 8 warps per SM at
+// ~255 registers -- two latency-bound warps per scheduler.  Here the accumulators live in TENSOR MEMORY: a CTA of 16 warps
+// owns a strip of 16 columns = 4 units of 4 columns; unit u accumulates D_u = Z_u Z_u^T (128 x 128, rows/columns =
+// 4 columns x 32 epochs) in TMEM columns [128u, 128u+128) -- the four 32 x 32 diagonal blocks are the kernels of its four
+// column voxels (the off-diagonal blocks are discarded: the tensor pipe has 10x the throughput this pass can use).
+// Per 16-row step:
+//   cp.async      : brick [32 epochs][16 rows][16 columns] fp32 -> shared, lines padded to 80 bytes (3 stages)
+//   16 warps      : thread = (row k, column pair, epoch octet s): 8 conflict-free LDS.64, within-subject z-score in the thread
+//                   (the arithmetic of k_norm_syrk_cols), 8 fp16 -> one STS.128 into the MN-major, 128-byte-swizzled
+//                   operand tile [k][128 m] of its unit (m = column * 32 + epoch; the same tile is A and B)
+//   one thread    : 4 x tcgen05.mma.cta_group::1.kind::f16 (M = N = 128, K = 16), commit -> mbarrier of the operand stage
+// Every COLS_SEG_STEPS steps the accumulators are read back (tcgen05.ld, warp w: TMEM lanes 32 (w & 3) .. of unit w >> 2 =
+// the 32 x 32 block of column w & 3) and folded into K with the symmetric mirror through shared memory.
+// ============================================================================================
+template <int EPS>
+__global__ void __launch_bounds__(512, 1)
+    k_norm_syrk_cols_umma(const float *__restrict__ A, long n, int E, long n2, long T256, long c0, float *K)
+{
+    static_assert(EPS <= 8, "a subject's epochs sit in one thread");
+    constexpr int NR = 4, NO = 2;
+    constexpr uint32_t RAW_STAGE = 32 * 16 * 80, OP_STAGE = 4 * 4096;
+    extern __shared__ __align__(1024) uint8_t cs_raw[];
+    uint8_t *cs = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(cs_raw) + 1023) & ~uintptr_t(1023));
+    const uint32_t op0 = smem_u32(cs);                       // NO operand stages (1024-byte aligned tiles)
+    const uint32_t raw0 = op0 + NO * OP_STAGE;               // NR raw stages; the fold staging overlays them
+    float *s_fold = reinterpret_cast<float *>(cs + NO * OP_STAGE);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(cs + NO * OP_STAGE + NR * RAW_STAGE);   // [NO] stage free, [NO] = segment done
+    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bars + NO + 1);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int S_eps = (E / EPS) * EPS;
+    const long nstrips = (n2 - c0 + 15) / 16;
+    const long nsteps = (n + 15) / 16;
+
+    if (tid == 0) {
+        for (int b = 0; b <= NO; b++) mbar_init(&bars[b], 1);
+        fence_mbar_init();
+    }
+    if (warp == 0) {
+        tmem_alloc(s_tmem, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *s_tmem;
+    const uint32_t idesc = make_idesc_f16_mn(128, 128);
+
+    // normalising role: lane = (k & 7) + 8 * (column pair of the unit) + 16 * (k >> 3), warp = (epoch octet s) + 4 * (unit u):
+    // a thread takes 8 epochs of ONE row and TWO adjacent columns (LDS.64: a half warp = 8 rows x 2 pairs hits 16 distinct
+    // bank pairs with the 80-byte lines)
+    const int k3 = lane & 7, cp = (lane >> 3) & 1, kh = lane >> 4, so = warp & 3, un = warp >> 2;
+    const uint32_t rd_off = (uint32_t)(((8 * so) * 16 + k3 + 8 * kh) * 80 + (4 * un + 2 * cp) * 4);        // + i * 1280 (epoch)
+    // the two columns of the pair are (c & 1) = 0, 1 of sub-tile cp: chunks (so) ^ k3 and (4 + so) ^ k3 of row k
+    const uint32_t wr_row = (uint32_t)(un * 4096 + cp * 2048 + kh * 1024 + k3 * 128);
+    const uint32_t wr_c0 = wr_row + (uint32_t)((so ^ k3) << 4), wr_c1 = wr_row + (uint32_t)(((4 + so) ^ k3) << 4);
+    // copying role: 4 16-byte pieces per thread and brick: piece = tid + 512 q -> column quad tid & 3, line (tid >> 2) + 128 q
+    const int pq = tid & 3, pl0 = tid >> 2;
+
+    uint32_t gstep = 0, nseg = 0;     // operand-stage uses and segments so far (mbarrier phases)
+    for (long strip = blockIdx.x; strip < nstrips; strip += gridDim.x) {
+        const long j0 = c0 + strip * 16;
+        const long tjx = j0 >> 8;
+        const int jo = (int)(j0 & 255);
+        const bool strip_full = E == 32 && j0 + 16 <= n2;
+        auto prefetch = [&](long st, int b) {
+            const long i0 = st * 16;
+            // line = pl0 + 128 q: row pl0 & 15, epoch (pl0 >> 4) + 8 q
+            const float *src = A + ((size_t)((i0 >> 8) * T256 + tjx) * E) * 65536 + (size_t)((i0 & 255) + (pl0 & 15)) * 256 + jo + pq * 4 +
+                               (size_t)(pl0 >> 4) * 65536;
+            const uint32_t dst = raw0 + (uint32_t)b * RAW_STAGE + (uint32_t)pq * 16u + (uint32_t)pl0 * 80u;
+            if (strip_full && i0 + 16 <= n) {      // CTA-uniform: the whole brick exists
+#pragma unroll
+                for (int q = 0; q < 4; q++) cp_async_16_s(dst + (uint32_t)q * (128u * 80u), src + (size_t)q * (8 * 65536));
+                return;
+            }
+            const long left = n2 - (j0 + pq * 4);
+            const uint32_t cb = left >= 4 ? 16u : (left > 0 ? (uint32_t)left * 4u : 0u);
+            const bool row_ok = i0 + (pl0 & 15) < n;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const uint32_t bytes = (row_ok && (pl0 >> 4) + 8 * q < E) ? cb : 0u;
+                cp_async_16_zfill_s(dst + (uint32_t)q * (128u * 80u), bytes ? src + (size_t)q * (8 * 65536) : A, bytes);
+            }
+        };
+        for (long seg0 = 0; seg0 < nsteps; seg0 += COLS_SEG_STEPS) {
+            const long seg1 = seg0 + COLS_SEG_STEPS < nsteps ? seg0 + COLS_SEG_STEPS : nsteps;
+            prefetch(seg0, 0);
+            cp_async_commit();
+            if (seg0 + 1 < seg1) prefetch(seg0 + 1, 1);
+            cp_async_commit();
+            if (seg0 + 2 < seg1) prefetch(seg0 + 2, 2);
+            cp_async_commit();
+            if (seg0 + 3 < seg1) prefetch(seg0 + 3, 3);
+            cp_async_commit();
+            cp_async_wait<3>();
+            __syncthreads();
+            int rb = 0;
+            for (long st = seg0; st < seg1; st++) {
+                const uint32_t ob = gstep % NO;
+                if (gstep >= NO) mbar_wait(&bars[ob], ((gstep / NO) - 1) & 1);   // the MMAs that read this stage are done
+                // ---- 8 epochs x rows (k3, k3 + 8) of column (un, cu): z-score inside the thread
+                float2 x[8];     // (column 2 cp, column 2 cp + 1) of epoch 8 so + i
+                const uint32_t rbase = raw0 + (uint32_t)rb * RAW_STAGE + rd_off;
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const uint2 q = lds64(rbase + (uint32_t)i * 1280u);
+                    x[i] = make_float2(__uint_as_float(q.x), __uint_as_float(q.y));
+                }
+                constexpr int G = 8 / EPS;
+#pragma unroll
+                for (int q = 0; q < G; q++) {
+                    float2 m = splat2(0.f), s2 = splat2(0.f);
+#pragma unroll
+                    for (int b = 0; b < EPS; b++) {
+                        m = ffma2(x[q * EPS + b], splat2(1.f), m);
+                        s2 = ffma2(x[q * EPS + b], x[q * EPS + b], s2);
+                    }
+                    const float2 nm = ffma2(m, splat2(-1.0f / EPS), splat2(0.f));
+                    const float2 ns2 = ffma2(s2, splat2(-1.0f / EPS), splat2(0.f));
+                    const float2 negvar = ffma2(nm, nm, ns2);
+                    float2 inv, mi;
+                    inv.x = negvar.x >= 0.f ? 0.f : rsqrt_ftz(-negvar.x);
+                    inv.y = negvar.y >= 0.f ? 0.f : rsqrt_ftz(-negvar.y);
+                    mi = ffma2(nm, inv, splat2(0.f));
+                    if (8 * so + q * EPS < S_eps) {
+#pragma unroll
+                        for (int b = 0; b < EPS; b++) x[q * EPS + b] = ffma2(x[q * EPS + b], inv, mi);
+                    }
+                }
+                const uint32_t wbase = op0 + ob * OP_STAGE;
+                sts128(wbase + wr_c0, pack_half2_rn(x[0].x, x[1].x), pack_half2_rn(x[2].x, x[3].x), pack_half2_rn(x[4].x, x[5].x),
+                       pack_half2_rn(x[6].x, x[7].x));
+                sts128(wbase + wr_c1, pack_half2_rn(x[0].y, x[1].y), pack_half2_rn(x[2].y, x[3].y), pack_half2_rn(x[4].y, x[5].y),
+                       pack_half2_rn(x[6].y, x[7].y));
+                fence_proxy_async_smem();      // generic-proxy stores -> visible to the tensor core's async proxy
+                cp_async_wait<2>();            // brick st+1 has landed (this thread's copies); st+2, st+3 in flight
+                __syncthreads();               // operand stage complete; brick st+1 visible; everybody is done with brick st
+                if (tid == 0) {
+                    tc_fence_after();
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const uint64_t d = make_smem_desc_sw128_mn(op0 + ob * OP_STAGE + (uint32_t)u * 4096u, 2048u, 1024u);
+                        tc_mma<0>(tmem + (uint32_t)u * 128u, d, d, idesc, st > seg0 ? 1u : 0u);
+                    }
+                    tc_commit(&bars[ob]);
+                    if (st + 1 == seg1) tc_commit(&bars[NO]);
+                }
+                if (st + 4 < seg1) prefetch(st + 4, rb);
+                cp_async_commit();
+                rb = rb == NR - 1 ? 0 : rb + 1;
+                ++gstep;
+            }
+            // ---- fold: TMEM -> registers -> shared (mirror) -> K
+            cp_async_wait<0>();
+            mbar_wait(&bars[NO], nseg & 1);
+            ++nseg;
+            tc_fence_after();
+            uint32_t v[32];
+            tmem_ld32(tmem + ((uint32_t)(32 * so) << 16) + (uint32_t)(un * 128 + 32 * so), v);   // warp's lanes 32 (w & 3) ..; column w & 3 of unit w >> 2
+            tmem_ld_wait();
+            tc_fence_before();
+            float *sk = s_fold + (size_t)warp * (32 * 33);
+#pragma unroll
+            for (int b = 0; b < 32; b++) sk[lane * 33 + b] = __uint_as_float(v[b]);
+            __syncthreads();      // every warp has read its accumulators (the next segment overwrites them) and written its block
+            const long col = j0 + 4 * un + so;
+            if (col < n2) {
+                const int EE = E * E;
+                float *Kc = K + (size_t)col * EE;
+                for (int base = lane; base < EE; base += 32 * 8) {
+                    float old[8];
+#pragma unroll
+                    for (int u8 = 0; u8 < 8; u8++) {
+                        const int idx = base + 32 * u8;
+                        if (idx < EE) old[u8] = Kc[idx];
+                    }
+#pragma unroll
+                    for (int u8 = 0; u8 < 8; u8++) {
+                        const int idx = base + 32 * u8;
+                        if (idx < EE) {
+                            const int a = idx / E, b = idx - a * E;
+                            Kc[idx] = old[u8] + (a >= b ? sk[a * 33 + b] : sk[b * 33 + a]);
+                        }
+                    }
+                }
+            }
+            __syncthreads();      // the staging area is raw stage space again
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+// ============================================================================================
 // Column-direction pass, TMA version (FCMA_FLAG_COLS_TMA, needs E % 4 == 0): same arithmetic as k_norm_syrk_cols, but
 //   * a brick [32 epochs][16 rows][32 columns] arrives through ONE 5-D bulk tensor copy (UTMALDG) issued by one elected
 //     lane -- the 4096 LDGSTS per brick (8 LSU cycles each, the same port the LDS reads need) and their address
@@ -3194,7 +3390,8 @@ static bool cols_supported(int E, int eps)
     return E <= 64 && eps >= 1 && eps <= (E <= 32 ? 32 : 64) && (eps & (eps - 1)) == 0;
 }
 static int launch_norm_syrk_cols(const void *A, long n, int E, long n2, long T256, long c0, int eps, float *K,
-                                 cudaStream_t st, int half_in = 0, bool use_tma = false, bool v2 = false, bool pad32 = false)
+                                 cudaStream_t st, int half_in = 0, bool use_tma = false, bool v2 = false, bool pad32 = false,
+                                 bool umma = false)
 {
     if (!cols_supported(E, eps) || (c0 & 31) || c0 >= n2) return fail(FCMA_EINVAL, "internal: column pass unsupported E=%d eps=%d c0=%ld", E, eps, c0);
     if (E > 32) {   // 32 < E <= 64, fp32 block: one column per warp, 8-column strips (k_norm_syrk_cols64)
@@ -3219,6 +3416,26 @@ static int launch_norm_syrk_cols(const void *A, long n, int E, long n2, long T25
         }
 #undef FCMA_COLS64_CASE
         LAUNCH_CHECK("k_norm_syrk_cols64");
+        return FCMA_OK;
+    }
+    if (umma && !half_in && E <= 32 && eps <= 8) {   // FCMA_FLAG_COLS_UMMA: SYRK on tcgen05, accumulators in tensor memory
+        const long nstrips16 = cdiv(n2 - c0, 16);
+        const unsigned gridu = (unsigned)(nstrips16 < g_sm_count ? nstrips16 : g_sm_count);
+        const size_t smemu = (size_t)2 * 16384 + (size_t)4 * 40960 + 64 + 1024;
+#define FCMA_COLSU_CASE(EPSV)                                                                                       \
+    case EPSV:                                                                                                      \
+        CUDA_TRY(cudaFuncSetAttribute(k_norm_syrk_cols_umma<EPSV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemu)); \
+        k_norm_syrk_cols_umma<EPSV><<<gridu, 512, smemu, st>>>(reinterpret_cast<const float *>(A), n, E, n2, T256, c0, K); \
+        break;
+        switch (eps) {
+            FCMA_COLSU_CASE(1)
+            FCMA_COLSU_CASE(2)
+            FCMA_COLSU_CASE(4)
+            FCMA_COLSU_CASE(8)
+        default: return fail(FCMA_EINVAL, "internal: no k_norm_syrk_cols_umma instantiation for eps=%d", eps);
+        }
+#undef FCMA_COLSU_CASE
+        LAUNCH_CHECK("k_norm_syrk_cols_umma");
         return FCMA_OK;
     }
     const long nstrips = cdiv(n2 - c0, 32);
@@ -3750,7 +3967,7 @@ static int run_pipeline_sym(const void *op, int precision, int E, int T, long V,
         if (g.rowsB > 0 && use_cols)
             return launch_norm_syrk_cols(A, g.n, E, g.colsA, g.t256, g.n, eps, K + (size_t)g.a * E * E, st, half16 ? 1 : 0,
                                          (flags & FCMA_FLAG_COLS_TMA) != 0, (flags & FCMA_FLAG_COLS_V2) != 0,
-                                         (flags & FCMA_FLAG_COLS_PAD32) != 0);
+                                         (flags & FCMA_FLAG_COLS_PAD32) != 0, (flags & FCMA_FLAG_COLS_UMMA) != 0);
         if (g.rowsB > 0)
             return launch_norm_syrk(blockB(g, A), g.rowsB, E, g.n, 256, 65536, eps, 1, -1, 1.0f,
                                     K + (size_t)(g.a + g.n) * E * E, 0, st, (long)E * 65536, half16 ? 1 : 0);

@@ -177,6 +177,25 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr)
 }
 
 
+// shared-memory matrix descriptor: MN-major tile, 128-byte swizzle (canonical layout, in 16-byte units,
+// ((8, n), (8, k)) : ((1, LBO), (8, SBO)): a row of 64 MN-elements (128 B) per k, 8 k-rows per 1024-byte swizzle atom,
+// atoms `sbo` bytes apart along K and `lbo` bytes apart along MN).  Tile base must be 1024-byte aligned.
+__device__ __forceinline__ uint64_t make_smem_desc_sw128_mn(uint32_t smem_addr, uint32_t lbo, uint32_t sbo)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);       // bits [0,14)
+    d |= (uint64_t)(lbo >> 4) << 16;                   // LBO, bits [16,30)
+    d |= (uint64_t)(sbo >> 4) << 32;                   // SBO, bits [32,46)
+    d |= (uint64_t)1 << 46;                            // descriptor version
+    d |= (uint64_t)2 << 61;                            // SWIZZLE_128B
+    return d;
+}
+// instruction descriptor, fp16 operands, fp32 accumulate, both operands MN-major ([15] A major, [16] B major = 1)
+__device__ __forceinline__ uint32_t make_idesc_f16_mn(uint32_t M, uint32_t N)
+{
+    return (1u << 4) | (1u << 15) | (1u << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+
 // instruction descriptor for kind::f16 / kind::tf32, fp32 accumulate, both operands K-major
 //   [4,6) D format (1 = f32) | [7,10) A format | [10,13) B format (1 = bf16, 2 = tf32)
 //   [15] A major (0 = K) | [16] B major | [17,23) N >> 3 | [24,29) M >> 4
@@ -234,6 +253,11 @@ __device__ __forceinline__ void cp_async_16_zfill_s(uint32_t smem_dst, const voi
 {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gsrc), "r"(src_bytes) : "memory");
 }
+// unconditional 16-byte copy
+__device__ __forceinline__ void cp_async_16_s(uint32_t smem_dst, const void *gsrc)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
 // same with a 256-byte L2 prefetch hint: the miss also brings the other 128-byte half of the 256-byte granule into L2
 // (the column pass reads 128-byte lines 1 KB apart; the neighbouring strip's CTA wants the other half at about the same time)
 __device__ __forceinline__ void cp_async_16_zfill_s_l2_256(uint32_t smem_dst, const void *gsrc, uint32_t src_bytes)
@@ -287,6 +311,12 @@ __device__ __forceinline__ void sts128(uint32_t saddr, uint32_t a, uint32_t b, u
 __device__ __forceinline__ void sts32(uint32_t saddr, uint32_t a)
 {
     asm volatile("st.shared.b32 [%0], %1;" ::"r"(saddr), "r"(a) : "memory");
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t saddr)
+{
+    uint32_t r;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(r) : "r"(saddr) : "memory");
+    return r;
 }
 __device__ __forceinline__ uint4 lds128(uint32_t saddr)
 {

@@ -77,6 +77,9 @@ extern "C" {
                                          row, but 4 % slower at V = 40 000, E = 64 (profiles/r2_e64_column_pass.txt), so it
                                          is not the default                                                             */
 
+#define FCMA_FLAG_COLS_UMMA     512   /* E <= 32, eps <= 8, fp32 block: column-direction pass with the SYRK on tcgen05 and the
+                                         accumulators in tensor memory (k_norm_syrk_cols_umma: 16 warps per SM instead of 8) */
+
 int         fcma_version(void);
 const char *fcma_last_error(void);
 /* number of usable sm_100 devices (0 if none); never fails */

@@ -283,7 +283,8 @@ def test_symmetric_pipeline_vs_oracle_and_plain(dev, case):
     work = engine.SymWorkspace(E, V, rows, dev, transposed_copy=(case != "long_column_walk"))
     fls = (_lib.FLAG_MASK_SELF, 0)
     if case == "long_column_walk":      # also the TMA-fed column pass: ring wrap-around and folds over a long walk
-        fls = (_lib.FLAG_MASK_SELF, _lib.FLAG_MASK_SELF | _lib.FLAG_COLS_TMA, _lib.FLAG_MASK_SELF | _lib.FLAG_COLS_V2, 0)
+        fls = (_lib.FLAG_MASK_SELF, _lib.FLAG_MASK_SELF | _lib.FLAG_COLS_TMA, _lib.FLAG_MASK_SELF | _lib.FLAG_COLS_V2,
+               _lib.FLAG_MASK_SELF | _lib.FLAG_COLS_UMMA, 0)
     for fl in fls:
         plain = engine.voxel_kernels(op, op, 0, V, eps, flags=fl & _lib.FLAG_MASK_SELF)
         work.buf.view(torch.float32).fill_(float("nan"))       # stale scratch must never reach the kernels
@@ -340,7 +341,8 @@ def test_symmetric_column_pass_all_eps(dev, E, eps):
     # the three column-pass kernels (default fragment-layout kernel; version 2 = thread-per-row normalisation +
     # ldmatrix; the TMA-fed variant when E % 4 == 0) and the transposed-copy variant agree to the order of the fp32 sums
     # (E <= 16 takes the 16-epoch kernel by default: FLAG_COLS_PAD32 selects the padded 32-epoch one)
-    for extra in (_lib.FLAG_COLS_PAD32, _lib.FLAG_COLS_V2, _lib.FLAG_COLS_TMA, _lib.FLAG_SYM_TRANSPOSED):
+    # FLAG_COLS_UMMA: the SYRK on tcgen05 with the accumulators in tensor memory (eps <= 8; ignored otherwise)
+    for extra in (_lib.FLAG_COLS_PAD32, _lib.FLAG_COLS_V2, _lib.FLAG_COLS_TMA, _lib.FLAG_SYM_TRANSPOSED, _lib.FLAG_COLS_UMMA):
         K2 = torch.zeros((V, E, E), device=dev)
         w2 = engine.SymWorkspace(E, V, 256, dev)
         w2.buf.view(torch.float32).fill_(float("nan"))

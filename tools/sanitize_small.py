@@ -25,7 +25,7 @@ raw, labels = synthetic.make_epochs(V, T, E, seed=3)
 ep, T_e = engine.stack_epochs(raw, dev)
 op = engine.pack_epochs(ep, T_e, "fp32")
 ref = None
-for name, fl in (("cols", 0), ("cols v2", _lib.FLAG_COLS_V2), ("tma", _lib.FLAG_COLS_TMA), ("transposed", _lib.FLAG_SYM_TRANSPOSED),
+for name, fl in (("cols", 0), ("cols umma", _lib.FLAG_COLS_UMMA), ("cols v2", _lib.FLAG_COLS_V2), ("tma", _lib.FLAG_COLS_TMA), ("transposed", _lib.FLAG_SYM_TRANSPOSED),
                  ("f16", _lib.FLAG_F16_INTERMEDIATE), ("f16 tma", _lib.FLAG_F16_INTERMEDIATE | _lib.FLAG_COLS_TMA)):
     K = torch.zeros((V, E, E), device=dev)
     work = engine.SymWorkspace(E, V, 256, dev)

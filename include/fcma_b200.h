@@ -206,7 +206,9 @@ int fcma_shrink_kernels(float *K_dev, long nv, int E, int *digits_dev, void *str
  * scikit-learn's sklearn/svm/src/libsvm/svm.cpp) on nv kernels [E][E]: folds_host points to nfolds
  * structs {int n_train, n_pos, n_test, pad; int train_idx[64]; int test_idx[64]; unsigned char test_pos[64]}
  * (training samples of the smaller label first = class +1, as svm_group_classes orders them);
- * correct_dev[v*nfolds + f] = number of correctly predicted held-out samples; iters_dev optional. */
+ * correct_dev[v*nfolds + f] = number of correctly predicted held-out samples; iters_dev optional.
+ * E <= 64, at most 4096 fold problems, 2 <= n_train <= 64, n_test <= 64.  Replaces voxelselector.py:41-53 (_cross_validation_for_one_voxel)
+ * as called by _do_cross_validation (voxelselector.py:423-465) for SVC(kernel='precomputed', shrinking=False). */
 int fcma_svm_cv_precomputed(const float *K_dev, long nv, int E, int nfolds, const void *folds_host, double C,
                             double tol, int max_iter, int *correct_dev, int *iters_dev, void *stream);
 

@@ -16,9 +16,9 @@ _lib = None
 
 
 def build(force=False):
-    src = os.path.join(_HERE, "fcma_oracle.c")
+    srcs = [os.path.join(_HERE, f) for f in ("fcma_oracle.c", "svm_oracle.c")]
     if force or not os.path.exists(_LIB_PATH) or \
-            os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+            os.path.getmtime(_LIB_PATH) < max(os.path.getmtime(f) for f in srcs):
         subprocess.check_call(["make", "-C", _HERE, "liboracle.so"],
                               stdout=subprocess.DEVNULL)
     return _LIB_PATH
@@ -183,3 +183,61 @@ def compute_correlation(m1, m2, return_nans=False):
             z = np.nan_to_num(z)
         return z / math.sqrt(d.shape[1])
     return (norm(m1) @ norm(m2).T).astype(np.float32)
+
+
+def svm_smo(K, train_idx, n_pos, C=1.0, tol=1e-3, max_iter=-1, shrinking=False):
+    """One two-class C-SVC problem on the precomputed kernel ``K`` ([E, E] float32): training samples ``train_idx`` with the
+    ``n_pos`` samples of class +1 first.  Restates scikit-learn's libsvm solver (svm_oracle.c; the reference reaches it through
+    voxelselector.py:41-53).  Returns (alpha in the order of train_idx, rho, iterations)."""
+    K = np.ascontiguousarray(K, dtype=np.float32)
+    idx = np.ascontiguousarray(train_idx, dtype=np.int32)
+    alpha = np.zeros(len(idx), np.float64)
+    rho = ctypes.c_double(0)
+    f = lib().oracle_svm_smo
+    f.restype = ctypes.c_int
+    f.argtypes = [ctypes.POINTER(ctypes.c_float), ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.c_int, ctypes.c_int,
+                  ctypes.c_double, ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_double),
+                  ctypes.POINTER(ctypes.c_double)]
+    it = f(_fptr(K), K.shape[0], idx.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), len(idx), int(n_pos), float(C), float(tol),
+           int(max_iter), 1 if shrinking else 0, alpha.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), ctypes.byref(rho))
+    if it < 0:
+        raise ValueError("svm_smo: 2 <= n <= 64 training samples of both classes are required")
+    return alpha, rho.value, it
+
+
+def svm_last_stats():
+    """(smallest active set, gradient reconstructions) of the last svm_smo call: whether the shrinking heuristic acted."""
+    a, b = ctypes.c_int(0), ctypes.c_int(0)
+    lib().oracle_svm_last_stats(ctypes.byref(a), ctypes.byref(b))
+    return a.value, b.value
+
+
+def svm_cv(K, labels, num_folds, C=1.0, tol=1e-3, shrinking=False):
+    """cross_val_score(SVC(kernel='precomputed', C, tol, shrinking), K, labels, cv=StratifiedKFold(num_folds)) restated:
+    scikit-learn's own splits, one-vs-one problems for more than two classes (pairs in libsvm's order, the smaller label is
+    class +1), libsvm's vote (first maximum).  Returns (mean accuracy, iterations per (fold, pair))."""
+    from sklearn import model_selection
+    K = np.ascontiguousarray(K, dtype=np.float32)
+    y = np.asarray(labels)
+    classes = np.unique(y)
+    code = np.searchsorted(classes, y)
+    k = len(classes)
+    pairs = [(a, b) for a in range(k) for b in range(a + 1, k)]
+    skf = model_selection.StratifiedKFold(n_splits=num_folds, shuffle=False)
+    scores, iters = [], []
+    for tr, te in skf.split(np.zeros((len(y), 1)), y):
+        votes = np.zeros((len(te), k), np.int64)
+        for a, b in pairs:
+            pos = [int(i) for i in tr if code[i] == a]
+            neg = [int(i) for i in tr if code[i] == b]
+            alpha, rho, it = svm_smo(K, pos + neg, len(pos), C, tol, -1, shrinking)
+            iters.append(it)
+            idx = np.asarray(pos + neg)
+            coef = alpha * np.r_[np.ones(len(pos)), -np.ones(len(neg))]
+            for t, i in enumerate(te):
+                sv = alpha != 0
+                dec = float(np.sum(coef[sv] * K[i, idx[sv]].astype(np.float64))) - rho
+                votes[t, a if dec > 0 else b] += 1
+        pred = np.argmax(votes, axis=1)          # first maximum, as libsvm
+        scores.append(float(np.mean(pred == code[te])))
+    return float(np.mean(scores)), iters

@@ -149,3 +149,70 @@ def test_oracle_vs_reference_golden_one_mask_all_voxels(golden):
     a = zA[:, :, 300:348]                                                    # z(i, :, j), i < 48, j in 300..347
     b = np.transpose(zB[:, :, 0:48], (2, 1, 0))                              # z(j, :, i) rearranged to [i, e, j]
     assert np.max(np.abs(a - b)) <= 5e-6
+
+
+def _svm_problem(rng, E, T, sig, classes=2):
+    lab = np.array([e % classes for e in range(E)])
+    Z = rng.randn(E, T).astype(np.float32)
+    for c in range(classes):
+        Z[lab == c, 5 * c:5 * c + 5] += sig
+    K = (Z @ Z.T).astype(np.float32)
+    digits = len(str(int(K[0, 0])))
+    if digits > 2:                                   # the decimal shrink of voxelselector.py:409-412
+        K = (K * np.float32(10.0 ** (2 - digits))).astype(np.float32)
+    return K, lab
+
+
+@pytest.mark.parametrize("E,T,sig,C,tol", [(32, 200, 0.35, 1.0, 1e-3), (64, 60, 0.2, 1.0, 1e-3), (48, 20, 0.3, 1.0, 1e-3),
+                                           (64, 30, 0.1, 100.0, 1e-3), (32, 200, 0.3, 0.05, 1e-4)])
+def test_svm_solver_restatement_equals_scikit_learn(E, T, sig, C, tol):
+    """a8 (voxelselector.py:41-53 -> scikit-learn's libsvm, a third-party dependency of the reference): the sequential
+    restatement in oracle/svm_oracle.c -- the algorithm the CUDA solvers k_svm_cv / k_svm_cv_shrink implement -- against
+    SVC.fit on the same precomputed kernels: iteration count, support set, dual coefficients and offset are IDENTICAL, without
+    and with the shrinking heuristic (which demonstrably acts on the longer problems: svm_last_stats)."""
+    from sklearn import svm
+    rng = np.random.RandomState(E + T)
+    shrunk = 0
+    for _ in range(8):
+        K, lab = _svm_problem(rng, E, T, sig)
+        tr = np.arange(E)[np.arange(E) % 4 != 0]
+        pos = [int(i) for i in tr if lab[i] == 0]
+        neg = [int(i) for i in tr if lab[i] == 1]
+        its = {}
+        for shrinking in (False, True):
+            clf = svm.SVC(kernel="precomputed", C=C, tol=tol, shrinking=shrinking)
+            clf.fit(K[np.ix_(tr, tr)].astype(np.float64), lab[tr])
+            alpha, rho, it = orc.svm_smo(K, pos + neg, len(pos), C, tol, -1, shrinking)
+            its[shrinking] = it
+            min_active, reconstructs = orc.svm_last_stats()
+            assert shrinking or (min_active == len(tr) and reconstructs == 0)
+            shrunk += shrinking and min_active < len(tr) and reconstructs > 0
+            assert it == int(np.asarray(clf.n_iter_).ravel()[0])
+            coef = alpha * np.r_[np.ones(len(pos)), -np.ones(len(neg))]
+            mine = {i: coef[k] for k, i in enumerate(pos + neg) if alpha[k] != 0}
+            sv = [int(i) for i in tr[clf.support_]]
+            assert sorted(mine) == sorted(sv)
+            # scikit-learn flips the signs of a two-class model (classes_[1] is the positive side of decision_function)
+            assert all(mine[i] == -clf.dual_coef_[0][k] for k, i in enumerate(sv))
+            assert rho == clf.intercept_[0]
+    if T < 200:          # the problems of several hundred iterations: variables were shrunk and the gradient reconstructed
+        assert shrunk >= 4
+
+
+@pytest.mark.parametrize("classes,folds", [(2, 4), (3, 3), (4, 3)])
+def test_svm_cross_validation_restatement_equals_scikit_learn(classes, folds):
+    """The whole of voxelselector.py:41-53 for one voxel: StratifiedKFold splits, one-vs-one problems (libsvm's pair order,
+    smaller label = +1), libsvm's vote -- mean accuracy equal to cross_val_score's, two to four conditions."""
+    from sklearn import svm, model_selection
+    rng = np.random.RandomState(10 * classes + folds)
+    E = 36
+    for shrinking in (False, True):
+        for _ in range(6):
+            K, lab = _svm_problem(rng, E, 120, 0.3, classes)
+            lab = np.array([7, 2, 11, 5])[lab]                      # label values other than 0..k-1
+            skf = model_selection.StratifiedKFold(n_splits=folds, shuffle=False)
+            ref = model_selection.cross_val_score(svm.SVC(kernel="precomputed", shrinking=shrinking), K.astype(np.float64),
+                                                  y=lab, cv=skf, n_jobs=1).mean()
+            got, iters = orc.svm_cv(K, lab, folds, shrinking=shrinking)
+            assert got == ref
+            assert len(iters) == folds * classes * (classes - 1) // 2 and min(iters) >= 1
